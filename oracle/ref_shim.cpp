@@ -1,0 +1,34 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE.  Thin extern "C" exports over the REFERENCE's own C++
+// sources, compiled where they lie under /root/reference by oracle/Makefile (target `ref`), output
+// oracle/_ref/libzkref.so.  Nothing from the reference is copied into this repository: this file only
+// includes
+//   crates/core/machine/include/kb31_t.hpp            (field class, host branch :458-623)
+//   crates/recursion/core/include/poseidon2_wide.hpp   (populate_perm :96-146)
+//   crates/recursion/core/include/poseidon2.hpp        (linear layers :21-71)
+//   crates/recursion/core/include/poseidon2_constants.hpp
+// through a shim for the cbindgen-generated header they expect (written by the Makefile; it carries
+// the constants of crates/recursion/core/src/chips/poseidon2_wide/mod.rs:18-23 and
+// chips/poseidon2_skinny/trace.rs:47).
+#include "kb31_t.hpp"
+#include "poseidon2_wide.hpp"
+#include <cstdint>
+
+using namespace zkm_recursion_core_sys;
+
+extern "C" {
+uint32_t ref_add(uint32_t a, uint32_t b) { return (kb31_t(a) + kb31_t(b)).val; }
+uint32_t ref_sub(uint32_t a, uint32_t b) { return (kb31_t(a) - kb31_t(b)).val; }
+uint32_t ref_mul(uint32_t a, uint32_t b) { return (kb31_t(a) * kb31_t(b)).val; }
+uint32_t ref_inv(uint32_t a) { return kb31_t(a).reciprocal().val; }
+uint32_t ref_to_monty(uint32_t c) { return kb31_t::to_monty(c); }
+uint32_t ref_from_monty(uint32_t m) { return kb31_t::from_monty(m); }
+// Poseidon2 permutation exactly as the reference's trace filler computes it (Montgomery in/out).
+void ref_poseidon2_permute(uint32_t state[16]) {
+  kb31_t in[WIDTH], ext_state[WIDTH * NUM_EXTERNAL_ROUNDS], int_state[WIDTH],
+      s0[NUM_INTERNAL_ROUNDS - 1], ext_sbox[WIDTH * NUM_EXTERNAL_ROUNDS], int_sbox[NUM_INTERNAL_ROUNDS],
+      out[WIDTH];
+  for (size_t i = 0; i < WIDTH; i++) in[i] = kb31_t(state[i]);
+  poseidon2_wide::populate_perm<kb31_t>(in, ext_state, int_state, s0, ext_sbox, int_sbox, out);
+  for (size_t i = 0; i < WIDTH; i++) state[i] = out[i].val;
+}
+}
