@@ -1,0 +1,109 @@
+// poseidon2.cuh -- Poseidon2 width-16 KoalaBear permutation, register resident, one permutation per thread.
+//
+// Algorithm: x^3 S-box, 4 + 4 external rounds, 13 internal rounds; round constants
+// crates/primitives/src/lib.rs:563-1121 (selection :1107-1121); linear layers as restated by the
+// reference at crates/recursion/core/include/poseidon2.hpp:21-71; internal diagonal
+// V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24]
+// (poseidon2_constants.hpp:1083-1100).  Sponge / compression: PaddingFreeSponge<16,8,8> and
+// TruncatedPermutation<2,8,16> (crates/stark/src/kb31_poseidon2.rs:173-177; semantics
+// crates/recursion/circuit/src/hash.rs:40-49,76-81).
+//
+// The state lives in 16 registers; every loop is fully unrolled so round constants become immediates
+// of the IADD3 that adds them (no constant-bank or shared-memory traffic).  The kernel is bound by the
+// integer pipes (fma: IMAD*, alu: IADD3/VIADDMNMX), not by memory -- see DESIGN.md.
+#pragma once
+#include "kb31.cuh"
+#include "../../include/zk_poseidon2_rc.h"
+
+namespace p2 {
+
+__device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
+__device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
+
+// Montgomery forms of 2^-k used by the internal diagonal: x * 2^-k = mul(x, R * 2^-k mod p).
+// R = 2^32, so R * 2^-k = 2^(32-k) for k <= 32 (all < p for k >= 2; 2^31 mod p = 2^24 - 1).
+constexpr uint32_t INV_2_8 = 1u << 24;   // 2^-8  * R
+constexpr uint32_t INV_2_3 = 1u << 29;   // 1/8   * R
+constexpr uint32_t INV_2_4 = 1u << 28;   // 1/16  * R
+constexpr uint32_t INV_2_24 = 1u << 8;   // 2^-24 * R
+
+__device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
+  uint32_t t01 = kb::add(x0, x1);
+  uint32_t t23 = kb::add(x2, x3);
+  uint32_t t0123 = kb::add(t01, t23);
+  uint32_t t01123 = kb::add(t0123, x1);
+  uint32_t t01233 = kb::add(t0123, x3);
+  uint32_t n3 = kb::add(t01233, kb::dbl(x0));
+  uint32_t n1 = kb::add(t01123, kb::dbl(x2));
+  uint32_t n0 = kb::add(t01123, t01);
+  uint32_t n2 = kb::add(t01233, t23);
+  x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+}
+
+__device__ __forceinline__ void external_layer(uint32_t (&s)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+  uint32_t sums[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) sums[k] = kb::add(kb::add(s[k], s[4 + k]), kb::add(s[8 + k], s[12 + k]));
+#pragma unroll
+  for (int j = 0; j < 16; j++) s[j] = kb::add(s[j], sums[j & 3]);
+}
+
+__device__ __forceinline__ void internal_layer(uint32_t (&s)[16]) {
+  // tree sum of the 16 lanes
+  uint32_t a0 = kb::add(s[0], s[1]), a1 = kb::add(s[2], s[3]), a2 = kb::add(s[4], s[5]), a3 = kb::add(s[6], s[7]);
+  uint32_t a4 = kb::add(s[8], s[9]), a5 = kb::add(s[10], s[11]), a6 = kb::add(s[12], s[13]), a7 = kb::add(s[14], s[15]);
+  uint32_t b0 = kb::add(a0, a1), b1 = kb::add(a2, a3), b2 = kb::add(a4, a5), b3 = kb::add(a6, a7);
+  uint32_t sum = kb::add(kb::add(b0, b1), kb::add(b2, b3));
+  uint32_t d;
+  s[0] = kb::sub(sum, kb::dbl(s[0]));                    // -2
+  s[1] = kb::add(sum, s[1]);                             //  1
+  s[2] = kb::add(sum, kb::dbl(s[2]));                    //  2
+  s[3] = kb::add(sum, kb::halve(s[3]));                  //  1/2
+  d = kb::dbl(s[4]);  s[4] = kb::add(sum, kb::add(d, s[4]));   //  3
+  s[5] = kb::add(sum, kb::dbl(kb::dbl(s[5])));           //  4
+  s[6] = kb::sub(sum, kb::halve(s[6]));                  // -1/2
+  d = kb::dbl(s[7]);  s[7] = kb::sub(sum, kb::add(d, s[7]));   // -3
+  s[8] = kb::sub(sum, kb::dbl(kb::dbl(s[8])));           // -4
+  s[9] = kb::add(sum, kb::mul(s[9], INV_2_8));           //  1/2^8
+  s[10] = kb::add(sum, kb::mul(s[10], INV_2_3));         //  1/8
+  s[11] = kb::add(sum, kb::mul(s[11], INV_2_24));        //  1/2^24
+  s[12] = kb::sub(sum, kb::mul(s[12], INV_2_8));         // -1/2^8
+  s[13] = kb::sub(sum, kb::mul(s[13], INV_2_3));         // -1/8
+  s[14] = kb::sub(sum, kb::mul(s[14], INV_2_4));         // -1/16
+  s[15] = kb::sub(sum, kb::mul(s[15], INV_2_24));        // -1/2^24
+}
+
+__device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+  external_layer(s);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = kb::cube(kb::add(s[i], EXT_RC[r][i]));
+    external_layer(s);
+  }
+#pragma unroll
+  for (int r = 0; r < 13; r++) {
+    s[0] = kb::cube(kb::add(s[0], INT_RC[r]));
+    internal_layer(s);
+  }
+#pragma unroll
+  for (int r = 4; r < 8; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = kb::cube(kb::add(s[i], EXT_RC[r][i]));
+    external_layer(s);
+  }
+}
+
+// TruncatedPermutation<2,8,16>: digest = permute(l || r)[0..8]
+__device__ __forceinline__ void compress(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) {
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { s[i] = l[i]; s[8 + i] = r[i]; }
+  permute(s);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = s[i];
+}
+
+}  // namespace p2
