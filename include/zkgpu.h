@@ -1,0 +1,122 @@
+/* zkgpu.h -- C ABI of libzkgpu.so, the B200 (sm_100a) implementation of Ziren's STARK trace-commitment,
+ * quotient and FRI hot path.
+ *
+ * This is the boundary a thin Rust `-sys` crate binds, following the reference's own FFI idiom
+ * (`extern "C-unwind"` over `u32` Montgomery words: crates/core/machine/src/sys.rs:14-42,
+ * crates/core/machine/cpp/extern.cpp:12).  INTEGRATION.md shows the Rust side.
+ *
+ * Conventions
+ *   - every field element is a uint32 canonical Montgomery residue of KoalaBear (R = 2^32), i.e. the
+ *     in-memory form of a Rust `KoalaBear` (crates/core/machine/include/kb31_t.hpp:27-34);
+ *     an extension element (F_p[X]/(X^4-3)) is 4 such words, coefficient 0 first
+ *     (crates/stark/src/air/extension.rs:14-25);
+ *   - matrices are row-major (`RowMajorMatrix<KoalaBear>`), heights are powers of two;
+ *   - every function returns 0 on success and a negative zk_status otherwise; nothing throws or
+ *     unwinds across the boundary; zk_last_error() gives the text of the calling thread's last error;
+ *   - `*_host` pointers are caller-owned host memory, `zk_dptr` values are device addresses owned by the
+ *     library (or handed in by the caller for the `_dev` variants);
+ *   - a zk_ctx is bound to one GPU and one CUDA stream; calls on the same ctx are serialised by an
+ *     internal mutex, so rayon workers may share it (crates/core/machine/src/utils/prove.rs:487-497).
+ *   - there is NO CPU fallback: without a CUDA device zk_ctx_create fails with ZK_ERR_CUDA.
+ */
+#ifndef ZKGPU_H
+#define ZKGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ZK_OK = 0,
+  ZK_ERR_ARG = -1,    /* bad argument (null pointer, height not a power of two, ...) */
+  ZK_ERR_CUDA = -2,   /* CUDA runtime error; see zk_last_error() */
+  ZK_ERR_STATE = -3,  /* object used in the wrong state */
+  ZK_ERR_VERIFY = -4  /* a verification entry point rejected its input */
+} zk_status;
+
+typedef struct zk_ctx zk_ctx;
+typedef struct zk_pdata zk_pdata; /* = Mmcs::ProverData: LDE matrices + digest layers, device resident */
+typedef uint64_t zk_dptr;          /* device address */
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* One context per GPU (shard dispatch places one shard per GPU: crates/core/machine/src/utils/prove.rs:480-526). */
+int32_t zk_ctx_create(int32_t device, zk_ctx** out);
+/* Same, but all work is enqueued on the caller's cudaStream_t (e.g. the host framework's current stream). */
+int32_t zk_ctx_create_on_stream(int32_t device, void* cuda_stream, zk_ctx** out);
+void zk_ctx_destroy(zk_ctx* ctx);
+int32_t zk_ctx_sync(zk_ctx* ctx);
+const char* zk_last_error(void);
+/* "sm_100a;<git-less build tag>" -- lets a binding check it loaded the right library. */
+const char* zk_build_info(void);
+
+/* Per-stage device timings (CUDA events on the ctx stream).  enable=1 starts recording. */
+int32_t zk_prof_enable(zk_ctx* ctx, int32_t enable);
+int32_t zk_prof_reset(zk_ctx* ctx);
+int32_t zk_prof_count(zk_ctx* ctx);
+int32_t zk_prof_get(zk_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* ms, uint64_t* launches);
+/* number of kernels of this library launched on the ctx since creation */
+uint64_t zk_launch_count(zk_ctx* ctx);
+
+/* ---- device memory plumbing --------------------------------------------------------------------- */
+int32_t zk_dev_alloc(zk_ctx* ctx, uint64_t bytes, zk_dptr* out);
+int32_t zk_dev_free(zk_ctx* ctx, zk_dptr p);
+int32_t zk_h2d(zk_ctx* ctx, zk_dptr dst, const void* src_host, uint64_t bytes);
+int32_t zk_d2h(zk_ctx* ctx, void* dst_host, zk_dptr src, uint64_t bytes);
+
+/* ---- unit-level entry points (parity tests, micro-benchmarks) ------------------------------------ */
+/* Poseidon2 width-16 permutation (crates/primitives/src/lib.rs:1107-1121 `poseidon2_init`) of n states. */
+int32_t zk_poseidon2_permute(zk_ctx* ctx, uint32_t* states_host, uint64_t n);
+/* PaddingFreeSponge<Perm,16,8,8> of every row (crates/stark/src/kb31_poseidon2.rs:173). digests: h*8 words. */
+int32_t zk_hash_rows(zk_ctx* ctx, const uint32_t* mat_host, uint64_t h, uint32_t w, uint32_t* digests_host);
+/* TruncatedPermutation<Perm,2,8,16> of n_out adjacent digest pairs (kb31_poseidon2.rs:175). */
+int32_t zk_compress_layer(zk_ctx* ctx, const uint32_t* prev_host, uint64_t n_out, uint32_t* out_host);
+/* TwoAdicSubgroupDft::dft_batch: natural-order DFT of every column (out[k] = sum_j in[j] g^(jk)). */
+int32_t zk_dft_batch(zk_ctx* ctx, const uint32_t* in_host, uint64_t h, uint32_t w, uint32_t* out_host);
+/* TwoAdicSubgroupDft::coset_lde_batch(in, log_blowup, shift).bit_reverse_rows(). */
+int32_t zk_coset_lde(zk_ctx* ctx, const uint32_t* in_host, uint64_t h, uint32_t w, uint32_t log_blowup,
+                     uint32_t shift, uint32_t* out_host);
+int32_t zk_coset_lde_dev(zk_ctx* ctx, zk_dptr in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                         zk_dptr out);
+
+/* ---- Pcs::commit (TwoAdicFriPcs::commit; call sites crates/stark/src/prover.rs:277,403,497 and
+ *      crates/stark/src/machine.rs:397) -------------------------------------------------------------
+ * For every (domain, evals): LDE with shift GENERATOR/domain_shift, rows bit-reversed; then one mixed-
+ * height Poseidon2 Merkle tree over all LDEs.  root = Com (8 words).  The LDEs stay on the device. */
+int32_t zk_commit(zk_ctx* ctx, uint32_t n_mats, const uint32_t* const* mats_host, const uint64_t* heights,
+                  const uint32_t* widths, const uint32_t* domain_shifts, uint32_t log_blowup, uint32_t root[8],
+                  zk_pdata** out);
+/* Same with the traces already resident in HBM (device trace generation, or uploaded by zk_h2d). */
+int32_t zk_commit_dev(zk_ctx* ctx, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
+                      const uint32_t* widths, const uint32_t* domain_shifts, uint32_t log_blowup,
+                      uint32_t root[8], zk_pdata** out);
+/* Mmcs::commit without LDE (MerkleTreeMmcs::commit; used for FRI layers through ExtensionMmcs). */
+int32_t zk_mmcs_commit(zk_ctx* ctx, uint32_t n_mats, const uint32_t* const* mats_host, const uint64_t* heights,
+                       const uint32_t* widths, uint32_t root[8], zk_pdata** out);
+int32_t zk_mmcs_commit_dev(zk_ctx* ctx, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
+                           const uint32_t* widths, uint32_t root[8], zk_pdata** out);
+
+/* ---- ProverData accessors -------------------------------------------------------------------------- */
+void zk_pdata_free(zk_pdata* pd);
+uint32_t zk_pdata_num_matrices(const zk_pdata* pd);
+uint64_t zk_pdata_height(const zk_pdata* pd, uint32_t i); /* committed (LDE) height */
+uint32_t zk_pdata_width(const zk_pdata* pd, uint32_t i);
+uint32_t zk_pdata_log_max_height(const zk_pdata* pd);
+int32_t zk_pdata_root(const zk_pdata* pd, uint32_t root[8]);
+/* Pcs::get_evaluations_on_domain (crates/stark/src/prover.rs:437-445): the committed LDE, no copy.
+ * Row r of the returned matrix is the evaluation at GENERATOR * g^bitrev(r). */
+zk_dptr zk_pdata_lde(const zk_pdata* pd, uint32_t i);
+/* Mmcs::get_matrices / Serialize support: copy an LDE matrix or a digest layer (0 = leaves) to the host. */
+int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* out_host);
+int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out_host);
+/* Mmcs::open_batch for n_idx indices at once (crates/recursion/circuit/src/fri.rs:383-387):
+ * opened: for each index, the rows of all matrices back to back in matrix order (sum of widths words);
+ * proofs: for each index, log_max_height siblings of 8 words, bottom-up. */
+int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const uint64_t* indices, uint32_t* opened_host,
+                            uint32_t* proofs_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

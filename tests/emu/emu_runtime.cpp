@@ -1,0 +1,28 @@
+// tests/emu/emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY (see include/cuda_runtime.h in this directory).
+#include <cuda_runtime.h>
+
+namespace zkemu {
+thread_local Dim t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+thread_local std::barrier<>* t_barrier = nullptr;
+thread_local unsigned t_lane_base = 0;
+
+void launch(unsigned grid, unsigned block, const std::function<void()>& f, bool coop) {
+  for (unsigned b = 0; b < grid; b++) {
+    if (!coop) {
+      t_blockIdx.x = b; t_blockDim.x = block; t_gridDim.x = grid; t_barrier = nullptr;
+      for (unsigned t = 0; t < block; t++) { t_threadIdx.x = t; f(); }
+    } else {
+      std::barrier<> bar(block);
+      std::vector<std::thread> th;
+      th.reserve(block);
+      for (unsigned t = 0; t < block; t++)
+        th.emplace_back([&, t]() {
+          t_blockIdx.x = b; t_blockDim.x = block; t_gridDim.x = grid; t_threadIdx.x = t; t_barrier = &bar;
+          f();
+          bar.arrive_and_drop();
+        });
+      for (auto& x : th) x.join();
+    }
+  }
+}
+}  // namespace zkemu

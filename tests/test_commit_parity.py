@@ -1,0 +1,166 @@
+"""Parity of the commit path (Poseidon2, sponge, compression, NTT, coset LDE, MMCS, Pcs::commit)
+with the CPU oracle, bit for bit.  Every case runs twice: on the CPU emulator build (small sizes, no
+GPU needed; debugging aid only) and -- marked `gpu` -- on the real library through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tests import backends, util
+
+P = util.P
+
+
+def _backend(name):
+    return backends.gpu() if name == "gpu" else backends.emu()
+
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)]
+
+
+def _mont(h, w, kind="rand", seed=0):
+    return ob.to_monty(util.canon_matrix(h, w, kind, seed=0x5A4B4D49 + seed))
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_permute_matches_oracle(be):
+    ctx = _backend(be)
+    rng = np.random.default_rng(11)
+    s = rng.integers(0, P, (67, 16)).astype(np.uint32)
+    s[0] = 0
+    s[1] = P - 1
+    got = ctx.poseidon2_permute(s)
+    exp = np.stack([ob.permute(x) for x in s])
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+@pytest.mark.parametrize("h,w", [(1, 8), (4, 1), (64, 7), (32, 8), (128, 24), (16, 100), (8, 0)])
+def test_hash_rows(be, h, w):
+    ctx = _backend(be)
+    m = _mont(h, w)
+    assert (ctx.hash_rows(m) == ob.hash_rows(m)).all()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_compress_layer(be):
+    ctx = _backend(be)
+    d = _mont(64, 8)
+    exp = np.stack([ob.compress(d[2 * i], d[2 * i + 1]) for i in range(32)])
+    assert (ctx.compress_layer(d) == exp).all()
+
+
+# log heights chosen to hit every pass kernel: register-only (1..5), shared-memory (6..10), and
+# two-pass plans (11 = 1+10, 12 = 2+10)
+EMU_LOGS = [0, 1, 2, 3, 5, 6, 7, 9, 10, 11, 12]
+GPU_LOGS = EMU_LOGS + [13, 14, 15, 16, 17, 20, 21]
+
+
+def _dft_cases():
+    out = []
+    for n in GPU_LOGS:
+        w = 3 if n >= 9 else 20
+        marks = [] if n in EMU_LOGS else [pytest.mark.gpu]
+        out.append(pytest.param("emu", n, w, id=f"emu-2^{n}x{w}", marks=marks + ([pytest.mark.skip("gpu only size")] if n not in EMU_LOGS else [])))
+        out.append(pytest.param("gpu", n, w, id=f"gpu-2^{n}x{w}", marks=[pytest.mark.gpu]))
+    return out
+
+
+@pytest.mark.parametrize("be,n,w", _dft_cases())
+def test_dft_batch(be, n, w):
+    ctx = _backend(be)
+    m = _mont(1 << n, w, seed=n)
+    assert (ctx.dft_batch(m) == ob.dft_batch(m)).all()
+
+
+@pytest.mark.parametrize("be,n,w", _dft_cases())
+@pytest.mark.parametrize("log_blowup", [1, 2])
+def test_coset_lde(be, n, w, log_blowup):
+    if n + log_blowup > 22 and be == "emu":
+        pytest.skip("too large for the emulator")
+    ctx = _backend(be)
+    m = _mont(1 << n, w, seed=100 + n)
+    shift = ob.lib().ork_to_monty(3)
+    assert (ctx.coset_lde(m, log_blowup, shift) == ob.coset_lde(m, log_blowup, shift)).all()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_coset_lde_other_shift_and_wide(be):
+    ctx = _backend(be)
+    L = ob.lib()
+    m = _mont(1 << 7, 37, seed=5)
+    # quotient-chunk style shift: GENERATOR / (GENERATOR * g_8) = g_8^-1
+    shift = L.ork_inv(L.ork_two_adic_generator(8))
+    assert (ctx.coset_lde(m, 1, shift) == ob.coset_lde(m, 1, shift)).all()
+    assert (ctx.coset_lde(m, 0, shift) == ob.coset_lde(m, 0, shift)).all()
+
+
+def _check_commit(ctx, mats, shifts, log_blowup):
+    root, pd = ctx.commit(mats, shifts, log_blowup)
+    tree = ob.pcs_commit(mats, log_blowup, shifts)
+    assert (root == tree.root).all()
+    assert pd.log_max_height() == tree.log_max_height
+    for i in range(len(mats)):
+        assert (pd.lde(i) == tree.matrix(i)).all()
+    for l in range(tree.log_max_height + 1):
+        assert (pd.layer(l) == tree.layer(l)).all()
+    # open_batch + the oracle's transliterated verify_batch
+    hmax = 1 << tree.log_max_height
+    idx = sorted({0, hmax - 1, hmax // 3, 5 % hmax})
+    opened, proofs = pd.open_batch(idx)
+    dims = [tree.dims(i) for i in range(len(mats))]
+    for k, index in enumerate(idx):
+        rows_o, proof_o = tree.open(index)
+        off = 0
+        rows = []
+        for (h, w) in dims:
+            rows.append(opened[k, off:off + w])
+            off += w
+        for a, b in zip(rows, rows_o):
+            assert (a == b).all()
+        assert (proofs[k] == proof_o).all()
+        assert ob.mmcs_verify(root, dims, index, rows, proofs[k])
+    pd.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_commit_single(be):
+    ctx = _backend(be)
+    one = ob.lib().ork_to_monty(1)
+    _check_commit(ctx, [_mont(64, 16)], [one], 1)
+    _check_commit(ctx, [_mont(32, 5)], [one], 2)
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_commit_mixed_heights(be):
+    """size_gaps-style batch (crates/recursion/circuit/src/fri.rs:580-624): several matrices per height
+    class, gaps between classes, widths that are not multiples of 8, a zero-width matrix."""
+    ctx = _backend(be)
+    L = ob.lib()
+    one = L.ork_to_monty(1)
+    mats = [_mont(16, 3, seed=1), _mont(128, 9, seed=2), _mont(128, 8, seed=3), _mont(2, 12, seed=4),
+            _mont(16, 0, seed=5), _mont(1, 4, seed=6), _mont(64, 1, seed=7)]
+    shifts = [one] * len(mats)
+    # one quotient-chunk-like shifted domain: shift = GENERATOR * g^c
+    shifts[2] = L.ork_mul(L.ork_to_monty(3), L.ork_two_adic_generator(8))
+    _check_commit(ctx, mats, shifts, 1)
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_mmcs_commit_no_lde(be):
+    ctx = _backend(be)
+    mats = [_mont(32, 8, seed=9), _mont(8, 4, seed=10)]
+    root, pd = ctx.mmcs_commit(mats)
+    tree = ob.mmcs_commit(mats)
+    assert (root == tree.root).all()
+    pd.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_bad_arguments(be):
+    from zkmips_b200 import ZkError
+    ctx = _backend(be)
+    one = ob.lib().ork_to_monty(1)
+    with pytest.raises(ZkError):
+        ctx.commit([np.zeros((3, 4), np.uint32)], [one], 1)  # height not a power of two
+    with pytest.raises(ZkError):
+        ctx.commit([np.zeros((4, 4), np.uint32)], [0], 1)  # zero shift

@@ -1,0 +1,118 @@
+// merkle.cuh -- Poseidon2 Merkle kernels: leaf sponge over matrix rows, 2-to-1 compression layers with
+// the mixed-height injection rule of Plonky3's MerkleTreeMmcs.
+//
+// Replaces `MerkleTreeMmcs<_, _, MyHash, MyCompress, 8>::commit` (crates/stark/src/kb31_poseidon2.rs:173-177);
+// tree layout pinned by the in-repo verifier crates/recursion/circuit/src/fri.rs:363-405:
+//   leaf[r]      = H(concat over the tallest matrices, in input order, of row r)
+//   node         = C(left, right); when shorter matrices have exactly this layer's height:
+//   node         = C(node, H(concat of their rows at this index))
+//
+// One thread owns one sponge (one row): the 16-word state stays in registers for the whole row and
+// the next 32-byte chunk is fetched while the current permutation runs.  These kernels are bound by
+// the integer pipes, not by HBM.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "poseidon2.cuh"
+
+namespace mk {
+
+struct MatDesc {
+  const uint32_t* ptr;
+  uint32_t w;
+};
+
+__device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&s)[16]) {
+  uint4* o = reinterpret_cast<uint4*>(out);
+  o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// Single matrix, width a multiple of 8, 32-byte aligned rows: vector loads, software prefetch.
+__global__ void __launch_bounds__(256) hash_rows_w8(const uint32_t* __restrict__ mat, uint32_t w, uint64_t h,
+                                                    uint32_t* __restrict__ out) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  const uint4* row = reinterpret_cast<const uint4*>(mat + r * w);
+  const uint32_t nchunk = w >> 3;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = 0;
+  uint4 a = __ldg(row), b = __ldg(row + 1);
+  for (uint32_t c = 0; c < nchunk; c++) {
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if (c + 1 < nchunk) {
+      a = __ldg(row + 2 * (c + 1));
+      b = __ldg(row + 2 * (c + 1) + 1);
+    }
+    p2::permute(s);
+  }
+  store_digest(out + r * 8, s);
+}
+
+// General case: the row is the concatenation of the rows of several matrices of any widths.
+__global__ void __launch_bounds__(256) hash_rows_multi(const MatDesc* __restrict__ gm, uint32_t gn, uint64_t h,
+                                                       uint32_t* __restrict__ out) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = 0;
+  uint32_t mi = 0, c = 0;
+  while (mi < gn && gm[mi].w == 0) mi++;
+  const uint32_t* row = mi < gn ? gm[mi].ptr + r * gm[mi].w : nullptr;
+  while (mi < gn) {
+    uint32_t got = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (mi < gn) {
+        s[i] = __ldg(row + c);
+        got++;
+        c++;
+        if (c == gm[mi].w) {
+          c = 0;
+          mi++;
+          while (mi < gn && gm[mi].w == 0) mi++;
+          if (mi < gn) row = gm[mi].ptr + r * gm[mi].w;
+        }
+      }
+    }
+    if (got) p2::permute(s);
+  }
+  store_digest(out + r * 8, s);
+}
+
+// cur[i] = C(prev[2i], prev[2i+1]), then (optionally) cur[i] = C(cur[i], inject[i]).
+__global__ void __launch_bounds__(256) compress_layer(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur,
+                                                      uint64_t n, const uint32_t* __restrict__ inject) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* p = reinterpret_cast<const uint4*>(prev + i * 16);
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+  p2::permute(s);
+  if (inject) {
+    const uint4* q = reinterpret_cast<const uint4*>(inject + i * 8);
+    uint4 e = __ldg(q), f = __ldg(q + 1);
+    s[8] = e.x; s[9] = e.y; s[10] = e.z; s[11] = e.w;
+    s[12] = f.x; s[13] = f.y; s[14] = f.z; s[15] = f.w;
+    p2::permute(s);
+  }
+  store_digest(cur + i * 8, s);
+}
+
+// Raw permutation of n independent 16-word states (unit entry point / known-answer tests).
+__global__ void __launch_bounds__(256) permute_states(uint32_t* st, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) s[k] = st[i * 16 + k];
+  p2::permute(s);
+#pragma unroll
+  for (int k = 0; k < 16; k++) st[i * 16 + k] = s[k];
+}
+
+}  // namespace mk

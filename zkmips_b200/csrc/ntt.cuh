@@ -1,0 +1,270 @@
+// ntt.cuh -- batched multi-column NTT over KoalaBear for row-major matrices (sm_100a).
+//
+// Replaces Plonky3 `Radix2DitParallel` behind `TwoAdicSubgroupDft::{dft_batch, coset_lde_batch}`
+// (type alias crates/stark/src/kb31_poseidon2.rs:179; called from TwoAdicFriPcs::commit, call sites
+// crates/stark/src/prover.rs:277,403,497).  The transform result is mathematically unique, so the
+// decomposition below is free to differ from the CPU one while staying bit-exact.
+//
+// Layout: a matrix is h rows x w columns, row-major, u32 Montgomery words.  Every column is one
+// polynomial; all columns share the butterfly schedule, so a warp always touches a contiguous run of
+// columns of one row (coalesced) and twiddles are warp-uniform.
+//
+// Decomposition (decimation in frequency, natural order in, bit-reversed order out), "four-step" at
+// two levels so that almost all twiddles are compile-time constants:
+//   * the n stages are cut into passes of k <= 10 stages; a pass tile is 2^k rows (stride 2^(n-s0-k))
+//     x 16 columns; after its local size-2^k DFT each element is multiplied by the pass twiddle
+//     g_n^(lo * 2^s0 * bitrev_k(i)), which makes the remaining stages independent smaller DFTs;
+//   * inside a tile (k = 5 + B) each thread keeps 32 elements of one column in registers: a size-32
+//     DFT with constant twiddles (powers of w_32 from the constant bank), one twiddle multiply by
+//     w_{2^k}^(tau * bitrev_5(q)) from a shared-memory table, ONE shared-memory exchange, then
+//     2^(5-B) size-2^B DFTs with constant twiddles.  One HBM read + one HBM write per pass.
+//   * passes with k <= 5 need no shared memory at all (ntt_pass_reg).
+// Fused into the first pass of a transform: bit-reversed row gather (hands the bit-reversed output of
+// the inverse transform to the forward one without a separate permutation kernel) and a per-row
+// scale vector (coset shift powers and 1/n).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kb31.cuh"
+#include "launch.cuh"
+
+namespace ntt {
+
+constexpr int DIR_FWD = 0;
+constexpr int DIR_INV = 1;
+constexpr int TILE_COLS = 16;
+
+// c_w32[dir][e] = w_32^(+e) / w_32^(-e), e < 16, Montgomery form; filled by zk_ctx_create.
+__constant__ uint32_t c_w32[2][16];
+
+struct PassArgs {
+  const uint32_t* src;
+  uint32_t* dst;
+  const uint32_t* tw;     // tw[e] = g_L^(+-e) for this direction, e < 2^(L-1)
+  const uint32_t* scale;  // optional: element of natural row j is multiplied by scale[j] on load
+  uint32_t w;             // columns = row pitch in words
+  uint32_t log_n;         // transform size
+  uint32_t s0;            // stages done by earlier passes
+  uint32_t log_L;         // size of the twiddle table's group
+  uint32_t src_bitrev;    // read natural row j from memory row bitrev_n(j)
+};
+
+// g_n^(+-E) from the table of g_L powers (E < 2^n); the upper half of the circle is the negated lower.
+__device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ tw, uint32_t log_L, uint32_t log_n,
+                                             uint32_t E) {
+  uint32_t idx = E << (log_L - log_n);
+  uint32_t half = 1u << (log_L - 1);
+  if (idx >= half) return kb::P - __ldg(tw + (idx - half));
+  return __ldg(tw + idx);
+}
+
+// N / 2^LG independent size-2^LG DIF transforms on consecutive groups of v, twiddles from c_w32.
+template <int LG, int DIR, int N>
+__device__ __forceinline__ void dif_groups(uint32_t (&v)[N]) {
+#pragma unroll
+  for (int t = 0; t < LG; t++) {
+    const int half = 1 << (LG - 1 - t);
+#pragma unroll
+    for (int x = 0; x < N; x++) {
+      if ((x & half) == 0) {
+        const int e32 = ((x & (half - 1)) << t) << (5 - LG);
+        uint32_t u = v[x], z = v[x + half];
+        v[x] = kb::add(u, z);
+        if (e32 == 0)
+          v[x + half] = kb::sub(u, z);
+        else
+          v[x + half] = kb::mul(u - z + kb::P, c_w32[DIR][e32]);
+      }
+    }
+  }
+}
+
+__host__ __device__ constexpr int brev5(int q) {
+  return ((q & 1) << 4) | ((q & 2) << 2) | (q & 4) | ((q & 8) >> 2) | ((q & 16) >> 4);
+}
+
+// ---- pass with k = 5 + B stages (B in 1..5) -------------------------------------------------
+template <int B>
+constexpr size_t pass_smem_bytes() {
+  constexpr int ROWS = 1 << (5 + B);
+  return (size_t)(ROWS + ROWS / 32) * TILE_COLS * 4 + (size_t)ROWS * 4;
+}
+
+template <int B, int DIR>
+__global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_smem(PassArgs A) {
+  constexpr int K = 5 + B, ROWS = 1 << K, C = TILE_COLS, NT = C << B;
+  ZK_DYN_SMEM(sm);
+  uint32_t* sdat = sm;
+  uint32_t* stw = sm + (ROWS + ROWS / 32) * C;
+
+  const uint32_t cc = threadIdx.x & (C - 1), tau = threadIdx.x >> 4;
+  const uint32_t ncg = (A.w + C - 1) / C;
+  const uint32_t cg = blockIdx.x % ncg, tile = blockIdx.x / ncg;
+  const uint32_t n = A.log_n, rem = n - A.s0 - K;
+  const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
+  const uint32_t col = cg * C + cc;
+  const bool ok = col < A.w;
+  const uint32_t jbase = (hi << (n - A.s0)) + lo;
+
+  for (uint32_t e = threadIdx.x; e < ROWS; e += NT) stw[e] = root_pow(A.tw, A.log_L, K, e);
+
+  uint32_t v[32];
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = ((uint32_t)q << B) + tau;
+    uint32_t j = jbase + (i << rem);
+    uint32_t srow = A.src_bitrev ? (__brev(j) >> (32 - n)) : j;
+    uint32_t x = ok ? __ldg(A.src + (size_t)srow * A.w + col) : 0u;
+    if (A.scale) x = kb::mul(x, __ldg(A.scale + j));
+    v[q] = x;
+  }
+  dif_groups<5, DIR, 32>(v);
+  __syncthreads();  // stw complete
+#pragma unroll
+  for (int q = 1; q < 32; q++) v[q] = kb::mul(v[q], stw[tau * brev5(q)]);
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = ((uint32_t)q << B) + tau;
+    sdat[(i + (i >> 5)) * C + cc] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = tau * 32 + q;
+    v[q] = sdat[(i + (i >> 5)) * C + cc];
+  }
+  dif_groups<B, DIR, 32>(v);
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = tau * 32 + q;
+    uint32_t x = v[q];
+    if (rem > 0) {
+      uint32_t E = (lo << A.s0) * (__brev(i) >> (32 - K));
+      x = kb::mul(x, root_pow(A.tw, A.log_L, n, E));
+    }
+    if (ok) A.dst[(size_t)(jbase + (i << rem)) * A.w + col] = x;
+  }
+}
+
+// ---- pass with k <= 5 stages: registers only --------------------------------------------------
+template <int K, int DIR>
+__global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /* tiles * w */) {
+  uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const uint32_t col = (uint32_t)(gid % A.w);
+  const uint32_t tile = (uint32_t)(gid / A.w);
+  const uint32_t n = A.log_n, rem = n - A.s0 - K;
+  const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
+  const uint32_t jbase = (hi << (n - A.s0)) + lo;
+  constexpr int R = 1 << K;
+  uint32_t v[R];
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    uint32_t j = jbase + ((uint32_t)i << rem);
+    uint32_t srow = (A.src_bitrev && n > 0) ? (__brev(j) >> (32 - n)) : j;
+    uint32_t x = __ldg(A.src + (size_t)srow * A.w + col);
+    if (A.scale) x = kb::mul(x, __ldg(A.scale + j));
+    v[i] = x;
+  }
+  if constexpr (K > 0) dif_groups<K, DIR, R>(v);
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    uint32_t x = v[i];
+    if (K > 0 && rem > 0) {
+      uint32_t E = (lo << A.s0) * (__brev((uint32_t)i) >> (32 - (K > 0 ? K : 1)));
+      x = kb::mul(x, root_pow(A.tw, A.log_L, n, E));
+    }
+    A.dst[(size_t)(jbase + ((uint32_t)i << rem)) * A.w + col] = x;
+  }
+}
+
+// ---- host-side launch -------------------------------------------------------------------------
+template <int B, int DIR>
+inline cudaError_t launch_smem(const PassArgs& A, cudaStream_t st) {
+  static bool configured = false;
+  constexpr size_t bytes = pass_smem_bytes<B>();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  uint32_t ncg = (A.w + TILE_COLS - 1) / TILE_COLS;
+  uint64_t tiles = 1ull << (A.log_n - (5 + B));
+  uint64_t blocks = tiles * ncg;
+  auto kfn = ntt_pass_smem<B, DIR>;
+  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, TILE_COLS << B, bytes, st, A);
+  return cudaGetLastError();
+}
+template <int K, int DIR>
+inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
+  uint64_t total = (uint64_t)A.w << (A.log_n - K);
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  auto kfn = ntt_pass_reg<K, DIR>;
+  ZK_LAUNCH(kfn, blocks, 256, 0, st, A, total);
+  return cudaGetLastError();
+}
+
+template <int DIR>
+inline cudaError_t launch_pass(const PassArgs& A, uint32_t k, cudaStream_t st) {
+  switch (k) {
+    case 0: return launch_reg<0, DIR>(A, st);
+    case 1: return launch_reg<1, DIR>(A, st);
+    case 2: return launch_reg<2, DIR>(A, st);
+    case 3: return launch_reg<3, DIR>(A, st);
+    case 4: return launch_reg<4, DIR>(A, st);
+    case 5: return launch_reg<5, DIR>(A, st);
+    case 6: return launch_smem<1, DIR>(A, st);
+    case 7: return launch_smem<2, DIR>(A, st);
+    case 8: return launch_smem<3, DIR>(A, st);
+    case 9: return launch_smem<4, DIR>(A, st);
+    case 10: return launch_smem<5, DIR>(A, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Full transform of every column of an (2^log_n x w) matrix: natural-order rows in (optionally
+// gathered through a bit reversal and scaled), bit-reversed rows out.  dst may equal src only when
+// src_bitrev == 0.
+inline cudaError_t transform(const uint32_t* src, uint32_t* dst, uint32_t log_n, uint32_t w, int dir,
+                             const uint32_t* tw, uint32_t log_L, const uint32_t* scale, bool src_bitrev,
+                             cudaStream_t st) {
+  if (w == 0) return cudaSuccess;
+  uint32_t npass = log_n == 0 ? 1 : (log_n + 9) / 10;
+  uint32_t k0 = log_n - 10 * (npass - 1);
+  uint32_t s0 = 0;
+  for (uint32_t p = 0; p < npass; p++) {
+    uint32_t k = p == 0 ? k0 : 10;
+    PassArgs A;
+    A.src = p == 0 ? src : dst;
+    A.dst = dst;
+    A.tw = tw;
+    A.scale = p == 0 ? scale : nullptr;
+    A.w = w;
+    A.log_n = log_n;
+    A.s0 = s0;
+    A.log_L = log_L;
+    A.src_bitrev = (p == 0 && src_bitrev) ? 1u : 0u;
+    cudaError_t e = dir == DIR_FWD ? launch_pass<DIR_FWD>(A, k, st) : launch_pass<DIR_INV>(A, k, st);
+    if (e != cudaSuccess) return e;
+    s0 += k;
+  }
+  return cudaSuccess;
+}
+
+// tw[e] = base^e for e < count (base = g_L or its inverse); one thread per entry, square-and-multiply.
+__global__ void powers_kernel(uint32_t* out, uint64_t count, uint32_t base, uint32_t init) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  uint32_t r = init, b = base;
+  uint64_t k = e;
+  while (k) {
+    if (k & 1) r = kb::mul(r, b);
+    b = kb::mul(b, b);
+    k >>= 1;
+  }
+  out[e] = r;
+}
+
+}  // namespace ntt

@@ -1,0 +1,664 @@
+// zkgpu.cu -- libzkgpu.so: context, Pcs::commit path (coset LDE + Poseidon2 MMCS) and the C ABI of
+// include/zkgpu.h.  sm_100a only; no CPU fallback.
+#include "zkgpu_internal.cuh"
+
+thread_local std::string g_last_error;
+
+int32_t zk_fail(int32_t code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels local to this file
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// out row r = in row bitrev(r)  (natural <-> bit-reversed order), one thread per word
+__global__ void bitrev_rows_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t log_h,
+                                   uint32_t w, uint64_t total) {
+  uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  uint32_t r = (uint32_t)(gid / w), c = (uint32_t)(gid % w);
+  uint32_t s = log_h ? (__brev(r) >> (32 - log_h)) : 0u;
+  out[gid] = in[(size_t)s * w + c];
+}
+
+// Mmcs::open_batch gather: block b = query index b
+__global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32_t n_mats, uint32_t sum_w,
+                                   const uint32_t* __restrict__ digests, const uint64_t* __restrict__ layer_off,
+                                   uint32_t log_max, const uint64_t* __restrict__ indices,
+                                   uint32_t* __restrict__ opened, uint32_t* __restrict__ proofs) {
+  uint64_t index = indices[blockIdx.x];
+  uint32_t* o = opened + (size_t)blockIdx.x * sum_w;
+  for (uint32_t m = 0; m < n_mats; m++) {
+    zk_open_desc d = mats[m];
+    uint64_t r = index >> (log_max - d.log_h);
+    const uint32_t* row = d.ptr + r * d.w;
+    for (uint32_t c = threadIdx.x; c < d.w; c += blockDim.x) o[d.off + c] = row[c];
+  }
+  uint32_t* p = proofs + (size_t)blockIdx.x * log_max * 8;
+  for (uint32_t t = threadIdx.x; t < log_max * 8; t += blockDim.x) {
+    uint32_t l = t >> 3, k = t & 7;
+    p[t] = digests[layer_off[l] + (((index >> l) ^ 1) << 3) + k];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static int32_t ctx_init(zk_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major != 10)
+    return zk_fail(ZK_ERR_CUDA, "libzkgpu is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                                    std::to_string(prop.minor));
+  if (!c->stream) {
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  uint64_t thr = UINT64_MAX;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  // constant twiddles of the size-32 DFT
+  uint32_t w32[2][16];
+  uint32_t g5 = kbh::two_adic_generator(5), g5i = kbh::inv(g5);
+  for (int e = 0; e < 16; e++) {
+    w32[0][e] = kbh::pow(g5, e);
+    w32[1][e] = kbh::pow(g5i, e);
+  }
+  CK(cudaMemcpyToSymbolAsync(ntt::c_w32, w32, sizeof w32, 0, cudaMemcpyHostToDevice, c->stream));
+  // global tables of g_L^(+-e)
+  uint64_t half = 1ull << (c->log_L - 1);
+  uint32_t gL = kbh::two_adic_generator(c->log_L);
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMalloc(&c->tw[d], half * 4));
+    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((half + 255) / 256), 256, 0, c->stream, c->tw[d], half,
+                                                                              d == 0 ? gL : kbh::inv(gL), kbh::ONE);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+
+extern "C" int32_t zk_ctx_create_on_stream(int32_t device, void* stream, zk_ctx** out) {
+  if (!out) return zk_fail(ZK_ERR_ARG, "out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return zk_fail(ZK_ERR_CUDA, std::string("no CUDA device (libzkgpu has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return zk_fail(ZK_ERR_ARG, "device index out of range");
+  zk_ctx* c = new zk_ctx();
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  int32_t rc = ctx_init(c);
+  if (rc != ZK_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return ZK_OK;
+}
+extern "C" int32_t zk_ctx_create(int32_t device, zk_ctx** out) { return zk_ctx_create_on_stream(device, nullptr, out); }
+
+extern "C" void zk_ctx_destroy(zk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" int32_t zk_ctx_sync(zk_ctx* c) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "ctx is null");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+extern "C" const char* zk_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* zk_build_info(void) { return "libzkgpu sm_100a " __DATE__ " " __TIME__; }
+
+extern "C" int32_t zk_prof_enable(zk_ctx* c, int32_t enable) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "ctx is null");
+  std::lock_guard<std::mutex> g(c->mu);
+  c->prof = enable != 0;
+  return ZK_OK;
+}
+extern "C" int32_t zk_prof_reset(zk_ctx* c) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "ctx is null");
+  std::lock_guard<std::mutex> g(c->mu);
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c->recs.clear();
+  return ZK_OK;
+}
+extern "C" int32_t zk_prof_count(zk_ctx* c) { return c ? (int32_t)c->recs.size() : 0; }
+extern "C" int32_t zk_prof_get(zk_ctx* c, int32_t i, char* name, int32_t cap, float* ms, uint64_t* launches) {
+  if (!c || i < 0 || i >= (int32_t)c->recs.size()) return zk_fail(ZK_ERR_ARG, "bad profile record index");
+  auto& r = c->recs[i];
+  CK(cudaEventSynchronize(r.b));
+  float t = 0;
+  CK(cudaEventElapsedTime(&t, r.a, r.b));
+  if (ms) *ms = t;
+  if (launches) *launches = r.launches;
+  if (name && cap > 0) {
+    strncpy(name, r.name.c_str(), cap - 1);
+    name[cap - 1] = 0;
+  }
+  return ZK_OK;
+}
+extern "C" uint64_t zk_launch_count(zk_ctx* c) { return c ? c->launches : 0; }
+
+ProfScope::ProfScope(zk_ctx* c, const char* name) : c(c) {
+  if (!c->prof) return;
+  idx = (int)c->recs.size();
+  zk_ctx::Rec r;
+  r.name = name;
+  r.launches = c->launches;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c->stream);
+  c->recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  auto& r = c->recs[idx];
+  cudaEventRecord(r.b, c->stream);
+  r.launches = c->launches - r.launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device memory
+// ------------------------------------------------------------------------------------------------
+int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out) {
+  if (bytes == 0) bytes = 4;
+  CK(cudaMallocAsync(out, bytes, c->stream));
+  return ZK_OK;
+}
+int32_t dev_free(zk_ctx* c, void* p) {
+  if (p) CK(cudaFreeAsync(p, c->stream));
+  return ZK_OK;
+}
+extern "C" int32_t zk_dev_alloc(zk_ctx* c, uint64_t bytes, zk_dptr* out) {
+  if (!c || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  void* p = nullptr;
+  int32_t rc = dev_alloc(c, bytes, &p);
+  *out = (zk_dptr)p;
+  return rc;
+}
+extern "C" int32_t zk_dev_free(zk_ctx* c, zk_dptr p) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  return dev_free(c, (void*)p);
+}
+extern "C" int32_t zk_h2d(zk_ctx* c, zk_dptr dst, const void* src, uint64_t bytes) {
+  if (!c || (!src && bytes)) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync((void*)dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+extern "C" int32_t zk_d2h(zk_ctx* c, void* dst, zk_dptr src, uint64_t bytes) {
+  if (!c || (!dst && bytes)) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, (const void*)src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LDE
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t num_passes(uint32_t log_n) { return log_n == 0 ? 1 : (log_n + 9) / 10; }
+
+// coset_lde_batch(in, log_blowup, shift).bit_reverse_rows()  (SURVEY A.7).
+// Block t of the output (rows [t*h, (t+1)*h)) is the size-h DFT, bit-reversed, of the coefficients
+// scaled by (shift * g_{n+b}^bitrev_b(t))^i: 2^b independent coset transforms, no zero padding.
+int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                uint32_t* out) {
+  if (h == 0 || (h & (h - 1))) return zk_fail(ZK_ERR_ARG, "height must be a power of two");
+  uint32_t n = kbh::log2_exact(h);
+  if (n > c->log_L) return zk_fail(ZK_ERR_ARG, "trace height above 2^22 is not supported");
+  if (n + log_blowup > kbh::TWO_ADICITY) return zk_fail(ZK_ERR_ARG, "LDE height exceeds the two-adicity of the field");
+  if (w == 0) return ZK_OK;
+  uint32_t *coef = nullptr, *scale = nullptr;
+  int32_t rc;
+  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&coef))) return rc;
+  if ((rc = dev_alloc(c, h * 4ull, (void**)&scale))) return rc;
+  {
+    ProfScope ps(c, "idft");
+    CK(ntt::transform(in, coef, n, w, ntt::DIR_INV, c->tw[1], c->log_L, nullptr, false, c->stream));
+    c->launches += num_passes(n);
+  }
+  uint32_t gnb = kbh::two_adic_generator(n + log_blowup);
+  uint32_t hinv = kbh::inv(kbh::to_monty((uint32_t)(h % kbh::P)));
+  for (uint32_t t = 0; t < (1u << log_blowup); t++) {
+    ProfScope ps(c, "coset_dft");
+    uint32_t sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
+    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, scale, h, sigma, hinv);
+    CK(cudaGetLastError());
+    CK(ntt::transform(coef, out + (size_t)t * h * w, n, w, ntt::DIR_FWD, c->tw[0], c->log_L, scale, true, c->stream));
+    c->launches += 1 + num_passes(n);
+  }
+  if ((rc = dev_free(c, coef))) return rc;
+  if ((rc = dev_free(c, scale))) return rc;
+  return ZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MMCS
+// ------------------------------------------------------------------------------------------------
+static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t h, uint32_t* out) {
+  unsigned blocks = (unsigned)((h + 255) / 256);
+  if (g.size() == 1 && g[0].w % 8 == 0 && g[0].w > 0 && ((uintptr_t)g[0].ptr % 32) == 0) {
+    ZK_LAUNCH(mk::hash_rows_w8, blocks, 256, 0, c->stream, g[0].ptr, g[0].w, h, out);
+  } else {
+    mk::MatDesc* d = nullptr;
+    int32_t rc;
+    if ((rc = dev_alloc(c, g.size() * sizeof(mk::MatDesc), (void**)&d))) return rc;
+    CK(cudaMemcpyAsync(d, g.data(), g.size() * sizeof(mk::MatDesc), cudaMemcpyHostToDevice, c->stream));
+    ZK_LAUNCH(mk::hash_rows_multi, blocks, 256, 0, c->stream, d, (uint32_t)g.size(), h, out);
+    CK(cudaGetLastError());
+    if ((rc = dev_free(c, d))) return rc;
+  }
+  CK(cudaGetLastError());
+  c->launches++;
+  return ZK_OK;
+}
+
+// Builds the digest layers over pd->mats (already on the device) and fills root.
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd) {
+  uint32_t n = pd->n;
+  pd->order.resize(n);
+  for (uint32_t i = 0; i < n; i++) pd->order[i] = i;
+  std::stable_sort(pd->order.begin(), pd->order.end(),
+                   [&](uint32_t a, uint32_t b) { return pd->heights[a] > pd->heights[b]; });
+  uint64_t hmax = pd->heights[pd->order[0]];
+  pd->log_max = kbh::log2_exact(hmax);
+  pd->layer_off.resize(pd->log_max + 1);
+  uint64_t words = 0;
+  for (uint32_t l = 0; l <= pd->log_max; l++) {
+    pd->layer_off[l] = words;
+    words += (hmax >> l) * 8;
+  }
+  int32_t rc;
+  if ((rc = dev_alloc(c, words * 4, (void**)&pd->digests))) return rc;
+  uint32_t* inj = nullptr;
+  uint32_t next = 0;
+  auto take_group = [&](uint64_t height, std::vector<mk::MatDesc>& g) {
+    g.clear();
+    while (next < n && pd->heights[pd->order[next]] == height) {
+      uint32_t m = pd->order[next++];
+      g.push_back(mk::MatDesc{pd->mats[m], pd->widths[m]});
+    }
+  };
+  std::vector<mk::MatDesc> g;
+  {
+    ProfScope ps(c, "leaf_hash");
+    take_group(hmax, g);
+    if ((rc = hash_group(c, g, hmax, pd->digests))) return rc;
+  }
+  {
+    ProfScope ps(c, "tree");
+    for (uint32_t l = 1; l <= pd->log_max; l++) {
+      uint64_t len = hmax >> l;
+      take_group(len, g);
+      const uint32_t* injp = nullptr;
+      if (!g.empty()) {
+        if (!inj && (rc = dev_alloc(c, (hmax >> 1) * 32, (void**)&inj))) return rc;
+        if ((rc = hash_group(c, g, len, inj))) return rc;
+        injp = inj;
+      }
+      ZK_LAUNCH(mk::compress_layer, (unsigned)((len + 255) / 256), 256, 0, c->stream, 
+          pd->digests + pd->layer_off[l - 1], pd->digests + pd->layer_off[l], len, injp);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  if (inj && (rc = dev_free(c, inj))) return rc;
+  // open_batch descriptors
+  std::vector<zk_open_desc> od(n);
+  uint32_t off = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
+    off += pd->widths[i];
+  }
+  pd->sum_w = off;
+  if ((rc = dev_alloc(c, n * sizeof(zk_open_desc), (void**)&pd->d_desc))) return rc;
+  CK(cudaMemcpyAsync(pd->d_desc, od.data(), n * sizeof(zk_open_desc), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = dev_alloc(c, (pd->log_max + 1) * 8, (void**)&pd->d_layer_off))) return rc;
+  CK(cudaMemcpyAsync(pd->d_layer_off, pd->layer_off.data(), (pd->log_max + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off[pd->log_max], 32, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+
+static int32_t check_shapes(uint32_t n_mats, const void* ptrs, const uint64_t* heights, const uint32_t* widths) {
+  if (n_mats == 0 || !ptrs || !heights || !widths) return zk_fail(ZK_ERR_ARG, "empty or null matrix list");
+  for (uint32_t i = 0; i < n_mats; i++)
+    if (heights[i] == 0 || (heights[i] & (heights[i] - 1)))
+      return zk_fail(ZK_ERR_ARG, "matrix height must be a non-zero power of two");
+  return ZK_OK;
+}
+
+void pdata_release(zk_pdata* pd) {
+  zk_ctx* c = pd->ctx;
+  cudaSetDevice(c->device);
+  for (uint32_t i = 0; i < pd->mats.size(); i++)
+    if (pd->owned[i] && pd->mats[i]) cudaFreeAsync(pd->mats[i], c->stream);
+  if (pd->digests) cudaFreeAsync(pd->digests, c->stream);
+  if (pd->d_desc) cudaFreeAsync(pd->d_desc, c->stream);
+  if (pd->d_layer_off) cudaFreeAsync(pd->d_layer_off, c->stream);
+  delete pd;
+}
+
+// common tail of the four commit entry points.  `src[i]` are DEVICE pointers to the input matrices.
+static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* src, const uint64_t* heights,
+                             const uint32_t* widths, const uint32_t* domain_shifts, bool do_lde, uint32_t log_blowup,
+                             uint32_t root[8], zk_pdata** out) {
+  zk_pdata* pd = new zk_pdata();
+  pd->ctx = c;
+  pd->n = n_mats;
+  pd->heights.resize(n_mats);
+  pd->widths.assign(widths, widths + n_mats);
+  pd->mats.assign(n_mats, nullptr);
+  pd->owned.assign(n_mats, false);
+  int32_t rc = ZK_OK;
+  for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
+    if (do_lde) {
+      pd->heights[i] = heights[i] << log_blowup;
+      pd->owned[i] = true;
+      rc = dev_alloc(c, pd->heights[i] * widths[i] * 4ull, (void**)&pd->mats[i]);
+      if (rc) break;
+      if (domain_shifts[i] == 0) {
+        rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
+        break;
+      }
+      uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
+      rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
+    } else {
+      pd->heights[i] = heights[i];
+      pd->mats[i] = const_cast<uint32_t*>(src[i]);
+    }
+  }
+  if (rc == ZK_OK) rc = mmcs_build(c, pd);
+  if (rc != ZK_OK) {
+    pdata_release(pd);
+    return rc;
+  }
+  if (root) memcpy(root, pd->root, 32);
+  *out = pd;
+  return ZK_OK;
+}
+
+// uploads host matrices; when keep != nullptr the uploads are handed to the pdata (no LDE case)
+static int32_t upload_all(zk_ctx* c, uint32_t n_mats, const uint32_t* const* host, const uint64_t* heights,
+                          const uint32_t* widths, std::vector<uint32_t*>& dev) {
+  dev.assign(n_mats, nullptr);
+  ProfScope ps(c, "h2d");
+  for (uint32_t i = 0; i < n_mats; i++) {
+    uint64_t bytes = heights[i] * widths[i] * 4ull;
+    int32_t rc = dev_alloc(c, bytes, (void**)&dev[i]);
+    if (rc) return rc;
+    if (bytes) {
+      if (!host[i]) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
+      CK(cudaMemcpyAsync(dev[i], host[i], bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  return ZK_OK;
+}
+
+extern "C" int32_t zk_commit(zk_ctx* c, uint32_t n_mats, const uint32_t* const* mats_host, const uint64_t* heights,
+                             const uint32_t* widths, const uint32_t* domain_shifts, uint32_t log_blowup,
+                             uint32_t root[8], zk_pdata** out) {
+  if (!c || !out || !domain_shifts) return zk_fail(ZK_ERR_ARG, "null argument");
+  int32_t rc = check_shapes(n_mats, mats_host, heights, widths);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  std::vector<uint32_t*> dev;
+  rc = upload_all(c, n_mats, mats_host, heights, widths, dev);
+  if (rc == ZK_OK) rc = commit_common(c, n_mats, dev.data(), heights, widths, domain_shifts, true, log_blowup, root, out);
+  for (auto p : dev) dev_free(c, p);
+  return rc;
+}
+extern "C" int32_t zk_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
+                                 const uint32_t* widths, const uint32_t* domain_shifts, uint32_t log_blowup,
+                                 uint32_t root[8], zk_pdata** out) {
+  if (!c || !out || !domain_shifts) return zk_fail(ZK_ERR_ARG, "null argument");
+  int32_t rc = check_shapes(n_mats, mats_dev, heights, widths);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  std::vector<const uint32_t*> src(n_mats);
+  for (uint32_t i = 0; i < n_mats; i++) src[i] = (const uint32_t*)mats_dev[i];
+  return commit_common(c, n_mats, src.data(), heights, widths, domain_shifts, true, log_blowup, root, out);
+}
+extern "C" int32_t zk_mmcs_commit(zk_ctx* c, uint32_t n_mats, const uint32_t* const* mats_host, const uint64_t* heights,
+                                  const uint32_t* widths, uint32_t root[8], zk_pdata** out) {
+  if (!c || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  int32_t rc = check_shapes(n_mats, mats_host, heights, widths);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  std::vector<uint32_t*> dev;
+  rc = upload_all(c, n_mats, mats_host, heights, widths, dev);
+  if (rc == ZK_OK) rc = commit_common(c, n_mats, dev.data(), heights, widths, nullptr, false, 0, root, out);
+  if (rc == ZK_OK) {
+    for (uint32_t i = 0; i < n_mats; i++) (*out)->owned[i] = true;  // the uploads now belong to the pdata
+  } else {
+    for (auto p : dev) dev_free(c, p);
+  }
+  return rc;
+}
+extern "C" int32_t zk_mmcs_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
+                                      const uint32_t* widths, uint32_t root[8], zk_pdata** out) {
+  if (!c || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  int32_t rc = check_shapes(n_mats, mats_dev, heights, widths);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  std::vector<const uint32_t*> src(n_mats);
+  for (uint32_t i = 0; i < n_mats; i++) src[i] = (const uint32_t*)mats_dev[i];
+  return commit_common(c, n_mats, src.data(), heights, widths, nullptr, false, 0, root, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pdata accessors
+// ------------------------------------------------------------------------------------------------
+extern "C" void zk_pdata_free(zk_pdata* pd) {
+  if (!pd) return;
+  std::lock_guard<std::mutex> g(pd->ctx->mu);
+  pdata_release(pd);
+}
+extern "C" uint32_t zk_pdata_num_matrices(const zk_pdata* pd) { return pd ? pd->n : 0; }
+extern "C" uint64_t zk_pdata_height(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? pd->heights[i] : 0; }
+extern "C" uint32_t zk_pdata_width(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? pd->widths[i] : 0; }
+extern "C" uint32_t zk_pdata_log_max_height(const zk_pdata* pd) { return pd ? pd->log_max : 0; }
+extern "C" int32_t zk_pdata_root(const zk_pdata* pd, uint32_t root[8]) {
+  if (!pd || !root) return zk_fail(ZK_ERR_ARG, "null argument");
+  memcpy(root, pd->root, 32);
+  return ZK_OK;
+}
+extern "C" zk_dptr zk_pdata_lde(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? (zk_dptr)pd->mats[i] : 0; }
+extern "C" int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* out) {
+  if (!pd || i >= pd->n || !out) return zk_fail(ZK_ERR_ARG, "bad argument");
+  zk_ctx* c = pd->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, pd->mats[i], pd->heights[i] * pd->widths[i] * 4ull, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+extern "C" int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out) {
+  if (!pd || layer > pd->log_max || !out) return zk_fail(ZK_ERR_ARG, "bad argument");
+  zk_ctx* c = pd->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint64_t len = (pd->heights[pd->order[0]] >> layer) * 32;
+  CK(cudaMemcpyAsync(out, pd->digests + pd->layer_off[layer], len, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ZK_OK;
+}
+
+int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t* d_opened,
+                       uint32_t* d_proofs) {
+  ZK_LAUNCH(open_gather_kernel, n_idx, 128, 0, c->stream, pd->d_desc, pd->n, pd->sum_w, pd->digests, pd->d_layer_off,
+                                                   pd->log_max, d_idx, d_opened, d_proofs);
+  CK(cudaGetLastError());
+  c->launches++;
+  return ZK_OK;
+}
+
+extern "C" int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const uint64_t* indices, uint32_t* opened,
+                                       uint32_t* proofs) {
+  if (!pd || !indices || !opened || (!proofs && pd->log_max)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (n_idx == 0) return ZK_OK;
+  uint64_t hmax = 1ull << pd->log_max;
+  for (uint32_t i = 0; i < n_idx; i++)
+    if (indices[i] >= hmax) return zk_fail(ZK_ERR_ARG, "open index out of range");
+  zk_ctx* c = pd->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint64_t* d_idx = nullptr;
+  uint32_t *d_op = nullptr, *d_pr = nullptr;
+  int32_t rc;
+  uint64_t ob = (uint64_t)n_idx * pd->sum_w * 4, pb = (uint64_t)n_idx * pd->log_max * 32;
+  if ((rc = dev_alloc(c, n_idx * 8ull, (void**)&d_idx))) return rc;
+  if ((rc = dev_alloc(c, ob, (void**)&d_op))) return rc;
+  if ((rc = dev_alloc(c, pb, (void**)&d_pr))) return rc;
+  CK(cudaMemcpyAsync(d_idx, indices, n_idx * 8ull, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = pdata_open_dev(c, pd, n_idx, d_idx, d_op, d_pr))) return rc;
+  if (ob) CK(cudaMemcpyAsync(opened, d_op, ob, cudaMemcpyDeviceToHost, c->stream));
+  if (pb) CK(cudaMemcpyAsync(proofs, d_pr, pb, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d_idx);
+  dev_free(c, d_op);
+  dev_free(c, d_pr);
+  return ZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unit-level entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t zk_poseidon2_permute(zk_ctx* c, uint32_t* states, uint64_t n) {
+  if (!c || (!states && n)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (n == 0) return ZK_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint32_t* d = nullptr;
+  int32_t rc;
+  if ((rc = dev_alloc(c, n * 64, (void**)&d))) return rc;
+  CK(cudaMemcpyAsync(d, states, n * 64, cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(mk::permute_states, (unsigned)((n + 255) / 256), 256, 0, c->stream, d, n);
+  CK(cudaGetLastError());
+  c->launches++;
+  CK(cudaMemcpyAsync(states, d, n * 64, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return dev_free(c, d);
+}
+
+extern "C" int32_t zk_hash_rows(zk_ctx* c, const uint32_t* mat, uint64_t h, uint32_t w, uint32_t* digests) {
+  if (!c || !digests || (!mat && h * w)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (h == 0) return ZK_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint32_t *d = nullptr, *o = nullptr;
+  int32_t rc;
+  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&d))) return rc;
+  if ((rc = dev_alloc(c, h * 32, (void**)&o))) return rc;
+  if (h * w) CK(cudaMemcpyAsync(d, mat, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
+  std::vector<mk::MatDesc> grp{mk::MatDesc{d, w}};
+  if ((rc = hash_group(c, grp, h, o))) return rc;
+  CK(cudaMemcpyAsync(digests, o, h * 32, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d);
+  return dev_free(c, o);
+}
+
+extern "C" int32_t zk_compress_layer(zk_ctx* c, const uint32_t* prev, uint64_t n_out, uint32_t* out) {
+  if (!c || !prev || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (n_out == 0) return ZK_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint32_t *d = nullptr, *o = nullptr;
+  int32_t rc;
+  if ((rc = dev_alloc(c, n_out * 64, (void**)&d))) return rc;
+  if ((rc = dev_alloc(c, n_out * 32, (void**)&o))) return rc;
+  CK(cudaMemcpyAsync(d, prev, n_out * 64, cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(mk::compress_layer, (unsigned)((n_out + 255) / 256), 256, 0, c->stream, d, o, n_out, nullptr);
+  CK(cudaGetLastError());
+  c->launches++;
+  CK(cudaMemcpyAsync(out, o, n_out * 32, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d);
+  return dev_free(c, o);
+}
+
+extern "C" int32_t zk_coset_lde_dev(zk_ctx* c, zk_dptr in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                                    zk_dptr out) {
+  if (!c || !in || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  return lde_dev(c, (const uint32_t*)in, h, w, log_blowup, shift, (uint32_t*)out);
+}
+
+extern "C" int32_t zk_coset_lde(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup,
+                                uint32_t shift, uint32_t* out) {
+  if (!c || !in || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint32_t *d = nullptr, *o = nullptr;
+  int32_t rc;
+  uint64_t ib = h * w * 4ull, obytes = ib << log_blowup;
+  if ((rc = dev_alloc(c, ib, (void**)&d))) return rc;
+  if ((rc = dev_alloc(c, obytes, (void**)&o))) return rc;
+  CK(cudaMemcpyAsync(d, in, ib, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = lde_dev(c, d, h, w, log_blowup, shift, o))) return rc;
+  CK(cudaMemcpyAsync(out, o, obytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d);
+  return dev_free(c, o);
+}
+
+extern "C" int32_t zk_dft_batch(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t* out) {
+  if (!c || !in || !out) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (h == 0 || (h & (h - 1))) return zk_fail(ZK_ERR_ARG, "height must be a power of two");
+  uint32_t n = kbh::log2_exact(h);
+  if (n > c->log_L) return zk_fail(ZK_ERR_ARG, "height above 2^22 is not supported");
+  if (w == 0) return ZK_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  uint32_t *d = nullptr, *o = nullptr;
+  int32_t rc;
+  uint64_t bytes = h * w * 4ull;
+  if ((rc = dev_alloc(c, bytes, (void**)&d))) return rc;
+  if ((rc = dev_alloc(c, bytes, (void**)&o))) return rc;
+  CK(cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(ntt::transform(d, d, n, w, ntt::DIR_FWD, c->tw[0], c->log_L, nullptr, false, c->stream));
+  uint64_t total = h * w;
+  ZK_LAUNCH(bitrev_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, c->stream, d, o, n, w, total);
+  CK(cudaGetLastError());
+  c->launches += num_passes(n) + 1;
+  CK(cudaMemcpyAsync(out, o, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d);
+  return dev_free(c, o);
+}

@@ -1,0 +1,82 @@
+// zkgpu_internal.cuh -- shared declarations of the libzkgpu translation units (not part of the ABI).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/zkgpu.h"
+#include "kb31_host.h"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+int32_t zk_fail(int32_t code, const std::string& msg);
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+      return zk_fail(ZK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                                      ":" + std::to_string(__LINE__) + ")");                              \
+  } while (0)
+
+struct zk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::mutex mu;
+  uint32_t log_L = 22;                    // NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
+  uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
+  bool prof = false;
+  struct Rec {
+    std::string name;
+    cudaEvent_t a, b;
+    uint64_t launches;
+  };
+  std::vector<Rec> recs;
+  uint64_t launches = 0;
+};
+
+struct ProfScope {
+  zk_ctx* c;
+  int idx = -1;
+  ProfScope(zk_ctx* c, const char* name);
+  ~ProfScope();
+};
+
+struct zk_open_desc {
+  const uint32_t* ptr;
+  uint32_t w;
+  uint32_t log_h;
+  uint32_t off;
+};
+
+struct zk_pdata {
+  zk_ctx* ctx = nullptr;
+  uint32_t n = 0;
+  std::vector<uint64_t> heights;  // committed heights
+  std::vector<uint32_t> widths;
+  std::vector<uint32_t*> mats;    // device
+  std::vector<bool> owned;
+  std::vector<uint32_t> order;    // indices by height descending, stable
+  uint32_t log_max = 0;
+  uint32_t sum_w = 0;
+  uint32_t* digests = nullptr;    // all layers, leaves first
+  std::vector<uint64_t> layer_off;  // word offset of each layer
+  zk_open_desc* d_desc = nullptr;
+  uint64_t* d_layer_off = nullptr;
+  uint32_t root[8] = {0};
+};
+
+int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out);
+int32_t dev_free(zk_ctx* c, void* p);
+int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                uint32_t* out);
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd);
+void pdata_release(zk_pdata* pd);
+int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t* d_opened,
+                       uint32_t* d_proofs);

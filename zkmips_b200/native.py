@@ -1,0 +1,304 @@
+"""ctypes binding of libzkgpu.so (include/zkgpu.h).  No torch types cross this boundary.
+
+`load()` opens the in-tree CUDA library and nothing else; it raises if the library is missing.  The
+optional `path` argument exists for the test-only emulator build (tests/emu), never for production.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_SO = os.path.join(HERE, "libzkgpu.so")
+
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+i32, u32, u64 = C.c_int32, C.c_uint32, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/zkgpu.h one to one (checked by tests/test_abi.py)
+PROTOTYPES = {
+    "zk_ctx_create": (i32, [i32, C.POINTER(vp)]),
+    "zk_ctx_create_on_stream": (i32, [i32, vp, C.POINTER(vp)]),
+    "zk_ctx_destroy": (None, [vp]),
+    "zk_ctx_sync": (i32, [vp]),
+    "zk_last_error": (C.c_char_p, []),
+    "zk_build_info": (C.c_char_p, []),
+    "zk_prof_enable": (i32, [vp, i32]),
+    "zk_prof_reset": (i32, [vp]),
+    "zk_prof_count": (i32, [vp]),
+    "zk_prof_get": (i32, [vp, i32, C.c_char_p, i32, C.POINTER(C.c_float), u64p]),
+    "zk_launch_count": (u64, [vp]),
+    "zk_dev_alloc": (i32, [vp, u64, u64p]),
+    "zk_dev_free": (i32, [vp, u64]),
+    "zk_h2d": (i32, [vp, u64, vp, u64]),
+    "zk_d2h": (i32, [vp, vp, u64, u64]),
+    "zk_poseidon2_permute": (i32, [vp, u32p, u64]),
+    "zk_hash_rows": (i32, [vp, u32p, u64, u32, u32p]),
+    "zk_compress_layer": (i32, [vp, u32p, u64, u32p]),
+    "zk_dft_batch": (i32, [vp, u32p, u64, u32, u32p]),
+    "zk_coset_lde": (i32, [vp, u32p, u64, u32, u32, u32, u32p]),
+    "zk_coset_lde_dev": (i32, [vp, u64, u64, u32, u32, u32, u64]),
+    "zk_commit": (i32, [vp, u32, C.POINTER(vp), u64p, u32p, u32p, u32, u32p, C.POINTER(vp)]),
+    "zk_commit_dev": (i32, [vp, u32, u64p, u64p, u32p, u32p, u32, u32p, C.POINTER(vp)]),
+    "zk_mmcs_commit": (i32, [vp, u32, C.POINTER(vp), u64p, u32p, u32p, C.POINTER(vp)]),
+    "zk_mmcs_commit_dev": (i32, [vp, u32, u64p, u64p, u32p, u32p, C.POINTER(vp)]),
+    "zk_pdata_free": (None, [vp]),
+    "zk_pdata_num_matrices": (u32, [vp]),
+    "zk_pdata_height": (u64, [vp, u32]),
+    "zk_pdata_width": (u32, [vp, u32]),
+    "zk_pdata_log_max_height": (u32, [vp]),
+    "zk_pdata_root": (i32, [vp, u32p]),
+    "zk_pdata_lde": (u64, [vp, u32]),
+    "zk_pdata_copy_lde": (i32, [vp, u32, u32p]),
+    "zk_pdata_copy_layer": (i32, [vp, u32, u32p]),
+    "zk_pdata_open_batch": (i32, [vp, u32, u64p, u32p, u32p]),
+}
+
+
+class ZkError(RuntimeError):
+    pass
+
+
+def _p32(a):
+    return a.ctypes.data_as(u32p)
+
+
+def _arr(x, dt):
+    return np.ascontiguousarray(np.asarray(x, dtype=dt))
+
+
+class Lib:
+    """One loaded libzkgpu.so.  Methods are 1:1 with the C ABI, with numpy arrays for host buffers."""
+
+    def __init__(self, path=None):
+        path = path or DEFAULT_SO
+        if not os.path.exists(path):
+            raise ZkError(f"{path} is missing: build it with `python -m zkmips_b200.build` "
+                          "(there is no CPU fallback)")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            if name not in EXTRA_OPTIONAL or hasattr(self.dll, name):
+                fn = getattr(self.dll, name)
+                fn.restype = res
+                fn.argtypes = args
+
+    def check(self, rc):
+        if rc != 0:
+            raise ZkError(f"libzkgpu status {rc}: {self.dll.zk_last_error().decode()}")
+
+    # ---- context
+    def ctx_create(self, device=0, stream=None):
+        h = vp()
+        if stream is None:
+            self.check(self.dll.zk_ctx_create(device, C.byref(h)))
+        else:
+            self.check(self.dll.zk_ctx_create_on_stream(device, vp(stream), C.byref(h)))
+        return Ctx(self, h)
+
+
+EXTRA_OPTIONAL = set()
+
+
+class PData:
+    """Mmcs::ProverData handle (LDE matrices + digest layers resident on the device)."""
+
+    def __init__(self, ctx, h, root):
+        self.ctx, self.h, self.root = ctx, h, root
+
+    @property
+    def d(self):
+        return self.ctx.lib.dll
+
+    def free(self):
+        if self.h:
+            self.d.zk_pdata_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def num_matrices(self):
+        return self.d.zk_pdata_num_matrices(self.h)
+
+    def height(self, i):
+        return self.d.zk_pdata_height(self.h, i)
+
+    def width(self, i):
+        return self.d.zk_pdata_width(self.h, i)
+
+    def log_max_height(self):
+        return self.d.zk_pdata_log_max_height(self.h)
+
+    def lde_ptr(self, i):
+        return self.d.zk_pdata_lde(self.h, i)
+
+    def lde(self, i):
+        out = np.empty((self.height(i), self.width(i)), np.uint32)
+        self.ctx.lib.check(self.d.zk_pdata_copy_lde(self.h, i, _p32(out)))
+        return out
+
+    def layer(self, l):
+        out = np.empty(((1 << self.log_max_height()) >> l, 8), np.uint32)
+        self.ctx.lib.check(self.d.zk_pdata_copy_layer(self.h, l, _p32(out)))
+        return out
+
+    def open_batch(self, indices):
+        idx = _arr(indices, np.uint64)
+        n = len(idx)
+        sw = sum(self.width(i) for i in range(self.num_matrices()))
+        L = self.log_max_height()
+        opened = np.empty((n, sw), np.uint32)
+        proofs = np.empty((n, L, 8), np.uint32)
+        self.ctx.lib.check(self.d.zk_pdata_open_batch(self.h, n, idx.ctypes.data_as(u64p), _p32(opened), _p32(proofs)))
+        return opened, proofs
+
+
+class Ctx:
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    @property
+    def d(self):
+        return self.lib.dll
+
+    def destroy(self):
+        if self.h:
+            self.d.zk_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self.lib.check(self.d.zk_ctx_sync(self.h))
+
+    def launch_count(self):
+        return self.d.zk_launch_count(self.h)
+
+    # ---- profiling
+    def prof_enable(self, on=True):
+        self.lib.check(self.d.zk_prof_enable(self.h, 1 if on else 0))
+
+    def prof_reset(self):
+        self.lib.check(self.d.zk_prof_reset(self.h))
+
+    def prof_records(self):
+        out = []
+        buf = C.create_string_buffer(64)
+        ms = C.c_float()
+        nl = C.c_uint64()
+        for i in range(self.d.zk_prof_count(self.h)):
+            self.lib.check(self.d.zk_prof_get(self.h, i, buf, 64, C.byref(ms), C.byref(nl)))
+            out.append((buf.value.decode(), ms.value, nl.value))
+        return out
+
+    # ---- device memory
+    def dev_alloc(self, nbytes):
+        p = u64()
+        self.lib.check(self.d.zk_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self.lib.check(self.d.zk_dev_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self.lib.check(self.d.zk_h2d(self.h, dptr, arr.ctypes.data_as(vp), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self.lib.check(self.d.zk_d2h(self.h, arr.ctypes.data_as(vp), dptr, arr.nbytes))
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.dev_alloc(arr.nbytes)
+        self.h2d(p, arr)
+        return p
+
+    # ---- unit entry points
+    def poseidon2_permute(self, states):
+        s = _arr(states, np.uint32).reshape(-1, 16).copy()
+        self.lib.check(self.d.zk_poseidon2_permute(self.h, _p32(s), s.shape[0]))
+        return s
+
+    def hash_rows(self, mat):
+        m = _arr(mat, np.uint32)
+        h, w = m.shape
+        out = np.empty((h, 8), np.uint32)
+        self.lib.check(self.d.zk_hash_rows(self.h, _p32(m), h, w, _p32(out)))
+        return out
+
+    def compress_layer(self, prev):
+        p = _arr(prev, np.uint32).reshape(-1, 8)
+        n = p.shape[0] // 2
+        out = np.empty((n, 8), np.uint32)
+        self.lib.check(self.d.zk_compress_layer(self.h, _p32(p), n, _p32(out)))
+        return out
+
+    def dft_batch(self, mat):
+        m = _arr(mat, np.uint32)
+        h, w = m.shape
+        out = np.empty((h, w), np.uint32)
+        self.lib.check(self.d.zk_dft_batch(self.h, _p32(m), h, w, _p32(out)))
+        return out
+
+    def coset_lde(self, mat, log_blowup, shift):
+        m = _arr(mat, np.uint32)
+        h, w = m.shape
+        out = np.empty((h << log_blowup, w), np.uint32)
+        self.lib.check(self.d.zk_coset_lde(self.h, _p32(m), h, w, log_blowup, shift, _p32(out)))
+        return out
+
+    # ---- commit
+    @staticmethod
+    def _shape_args(mats_hw):
+        heights = _arr([h for h, _ in mats_hw], np.uint64)
+        widths = _arr([w for _, w in mats_hw], np.uint32)
+        return heights, widths
+
+    def commit(self, mats, domain_shifts, log_blowup=1):
+        """TwoAdicFriPcs::commit on host matrices (list of (h, w) uint32 Montgomery arrays)."""
+        ms = [_arr(m, np.uint32) for m in mats]
+        heights, widths = self._shape_args([m.shape for m in ms])
+        ptrs = (vp * len(ms))(*[m.ctypes.data_as(vp) for m in ms])
+        shifts = _arr(domain_shifts, np.uint32)
+        root = np.empty(8, np.uint32)
+        pd = vp()
+        self.lib.check(self.d.zk_commit(self.h, len(ms), ptrs, heights.ctypes.data_as(u64p), _p32(widths),
+                                        _p32(shifts), log_blowup, _p32(root), C.byref(pd)))
+        return root, PData(self, pd, root)
+
+    def commit_dev(self, dptrs, shapes, domain_shifts, log_blowup=1):
+        heights, widths = self._shape_args(shapes)
+        ptrs = _arr(dptrs, np.uint64)
+        shifts = _arr(domain_shifts, np.uint32)
+        root = np.empty(8, np.uint32)
+        pd = vp()
+        self.lib.check(self.d.zk_commit_dev(self.h, len(shapes), ptrs.ctypes.data_as(u64p),
+                                            heights.ctypes.data_as(u64p), _p32(widths), _p32(shifts),
+                                            log_blowup, _p32(root), C.byref(pd)))
+        return root, PData(self, pd, root)
+
+    def mmcs_commit(self, mats):
+        ms = [_arr(m, np.uint32) for m in mats]
+        heights, widths = self._shape_args([m.shape for m in ms])
+        ptrs = (vp * len(ms))(*[m.ctypes.data_as(vp) for m in ms])
+        root = np.empty(8, np.uint32)
+        pd = vp()
+        self.lib.check(self.d.zk_mmcs_commit(self.h, len(ms), ptrs, heights.ctypes.data_as(u64p), _p32(widths),
+                                             _p32(root), C.byref(pd)))
+        return root, PData(self, pd, root)
+
+
+_default = None
+
+
+def load(path=None):
+    """Load the product library (default) or an explicit path (tests/emu only)."""
+    global _default
+    if path is not None:
+        return Lib(path)
+    if _default is None:
+        _default = Lib()
+    return _default
