@@ -81,6 +81,42 @@ int32_t ork_pcs_commit(uint32_t n_mats, const uint32_t* const* mats, const uint6
 
 int32_t ork_num_threads(void);
 
+/* ---- DuplexChallenger<Val, Perm, 16, 8> ---- */
+typedef struct {
+  uint32_t state[16];
+  uint32_t in[8];
+  uint32_t n_in;
+  uint32_t out[8];
+  uint32_t n_out;
+} ork_challenger;
+void ork_ch_init(ork_challenger* c);
+void ork_ch_observe(ork_challenger* c, const uint32_t* v, uint32_t n);
+uint32_t ork_ch_sample(ork_challenger* c);
+void ork_ch_sample_ext(ork_challenger* c, uint32_t out[4]);
+uint32_t ork_ch_sample_bits(ork_challenger* c, uint32_t bits);
+int32_t ork_ch_check_witness(ork_challenger* c, uint32_t bits, uint32_t witness);
+uint32_t ork_ch_grind(ork_challenger* c, uint32_t bits); /* smallest canonical witness, Montgomery form */
+
+/* ---- TwoAdicFriPcs::open / verify ----
+ * Matrices are described round by round, in commit order; n_points[k] / points (4 words each) list the
+ * opening points of matrix k.  The proof is one flat u32 buffer:
+ *   opened values : for round, matrix, point: width ext elements
+ *   fri           : n_layers * 8 (commit-phase roots), final_poly (4), pow_witness (1)
+ *   queries       : num_queries x { per round: opened rows (sum of widths) + path (log_max_r * 8);
+ *                                   per layer i: sibling (4) + path ((log_max - i - 1) * 8) }
+ * inject_witness >= 0 uses that pow witness instead of grinding (parity with a given transcript). */
+uint64_t ork_pcs_proof_words(uint32_t n_rounds, const uint32_t* n_mats, const uint64_t* lde_heights,
+                             const uint32_t* widths, const uint32_t* n_points, uint32_t log_blowup,
+                             uint32_t num_queries);
+int32_t ork_pcs_open(uint32_t n_rounds, const ork_tree* const* trees, const uint32_t* n_points,
+                     const uint32_t* points, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                     ork_challenger* ch, int64_t inject_witness, uint32_t* proof, uint64_t proof_cap);
+/* returns 1 when the proof is accepted, a negative code naming the failed check otherwise */
+int32_t ork_pcs_verify(uint32_t n_rounds, const uint32_t* roots, const uint32_t* n_mats,
+                       const uint64_t* lde_heights, const uint32_t* widths, const uint32_t* n_points,
+                       const uint32_t* points, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                       ork_challenger* ch, const uint32_t* proof, uint64_t proof_words);
+
 #ifdef __cplusplus
 }
 #endif
