@@ -95,7 +95,7 @@ def lib():
 
 def _bind_fri(L):
     """Signatures of oracle/zk_oracle_fri.c (filled in as that file grows)."""
-    if not hasattr(L, "ork_challenger_new"):
+    if not hasattr(L, "ork_ch_init"):
         return
     from . import binding_fri
     binding_fri.bind(L)

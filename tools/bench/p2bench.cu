@@ -1,0 +1,188 @@
+// tools/bench/p2bench.cu -- microbenchmark of Poseidon2 permutation variants (register resident, no memory
+// traffic) to pick the instruction mix that best balances the fmaheavy (IMAD*) and alu pipes on sm_100a.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bench/p2bench tools/bench/p2bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../zkmips_b200/csrc/kb31.cuh"
+#include "../../include/zk_poseidon2_rc.h"
+
+__device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
+__device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
+constexpr uint32_t P = kb::P;
+
+// MUL variants -------------------------------------------------------------
+struct MulSub {  // product code: subtractive form, umulhi
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return kb::mul(a, b); }
+  static __device__ __forceinline__ uint32_t lazy(uint32_t a, uint32_t b) { return kb::mul_lazy(a, b); }
+};
+struct MulAdd {  // additive form: t + m*p with one IMAD.WIDE accumulate
+  static __device__ __forceinline__ uint32_t lazy(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t m = (uint32_t)t * 0x7effffffu;
+    uint64_t t2 = (uint64_t)m * P + t;
+    return (uint32_t)(t2 >> 32);
+  }
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { uint32_t r = lazy(a, b); return min(r, r - P); }
+};
+struct MulLea {  // subtractive form, m = lo * MU through shifts (alu pipe) instead of IMAD
+  static __device__ __forceinline__ uint32_t core(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t lo = (uint32_t)t;
+    uint32_t m = lo + (lo << 24) + (lo << 31);
+    uint32_t u = __umulhi(m, P);
+    return (uint32_t)(t >> 32) - u;
+  }
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { uint32_t r = core(a, b); return min(r, r + P); }
+  static __device__ __forceinline__ uint32_t lazy(uint32_t a, uint32_t b) { return core(a, b) + P; }
+};
+
+template <class M> __device__ __forceinline__ uint32_t cube(uint32_t a) { return M::mul(M::lazy(a, a), a); }
+
+__device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
+  uint32_t t01 = kb::add(x0, x1), t23 = kb::add(x2, x3), t0123 = kb::add(t01, t23);
+  uint32_t t01123 = kb::add(t0123, x1), t01233 = kb::add(t0123, x3);
+  uint32_t n3 = kb::add(t01233, kb::dbl(x0)), n1 = kb::add(t01123, kb::dbl(x2));
+  uint32_t n0 = kb::add(t01123, t01), n2 = kb::add(t01233, t23);
+  x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+}
+__device__ __forceinline__ void external_layer(uint32_t (&s)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+  uint32_t sums[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) sums[k] = kb::add(kb::add(s[k], s[4 + k]), kb::add(s[8 + k], s[12 + k]));
+#pragma unroll
+  for (int j = 0; j < 16; j++) s[j] = kb::add(s[j], sums[j & 3]);
+}
+// x * 2^-k mod p = (x >> k) - (x & (2^k-1)) * ((p-1) >> k)   since 2^-k = -(p-1)/2^k  (p = 127*2^24 + 1)
+template <int K> __device__ __forceinline__ uint32_t div2k(uint32_t x) {
+  constexpr uint32_t c = (P - 1) >> K;
+  uint32_t q = x >> K, r = x & ((1u << K) - 1);
+  uint32_t d = q - r * c;
+  return min(d, d + P);
+}
+template <class M, int DIAG> __device__ __forceinline__ void internal_layer(uint32_t (&s)[16]) {
+  uint32_t a0 = kb::add(s[0], s[1]), a1 = kb::add(s[2], s[3]), a2 = kb::add(s[4], s[5]), a3 = kb::add(s[6], s[7]);
+  uint32_t a4 = kb::add(s[8], s[9]), a5 = kb::add(s[10], s[11]), a6 = kb::add(s[12], s[13]), a7 = kb::add(s[14], s[15]);
+  uint32_t sum = kb::add(kb::add(kb::add(a0, a1), kb::add(a2, a3)), kb::add(kb::add(a4, a5), kb::add(a6, a7)));
+  uint32_t d;
+  s[0] = kb::sub(sum, kb::dbl(s[0]));
+  s[1] = kb::add(sum, s[1]);
+  s[2] = kb::add(sum, kb::dbl(s[2]));
+  s[3] = kb::add(sum, kb::halve(s[3]));
+  d = kb::dbl(s[4]); s[4] = kb::add(sum, kb::add(d, s[4]));
+  s[5] = kb::add(sum, kb::dbl(kb::dbl(s[5])));
+  s[6] = kb::sub(sum, kb::halve(s[6]));
+  d = kb::dbl(s[7]); s[7] = kb::sub(sum, kb::add(d, s[7]));
+  s[8] = kb::sub(sum, kb::dbl(kb::dbl(s[8])));
+  if (DIAG == 0) {
+    s[9] = kb::add(sum, M::mul(s[9], 1u << 24));
+    s[10] = kb::add(sum, M::mul(s[10], 1u << 29));
+    s[11] = kb::add(sum, M::mul(s[11], 1u << 8));
+    s[12] = kb::sub(sum, M::mul(s[12], 1u << 24));
+    s[13] = kb::sub(sum, M::mul(s[13], 1u << 29));
+    s[14] = kb::sub(sum, M::mul(s[14], 1u << 28));
+    s[15] = kb::sub(sum, M::mul(s[15], 1u << 8));
+  } else {
+    s[9] = kb::add(sum, div2k<8>(s[9]));
+    s[10] = kb::add(sum, div2k<3>(s[10]));
+    s[11] = kb::add(sum, div2k<24>(s[11]));
+    s[12] = kb::sub(sum, div2k<8>(s[12]));
+    s[13] = kb::sub(sum, div2k<3>(s[13]));
+    s[14] = kb::sub(sum, div2k<4>(s[14]));
+    s[15] = kb::sub(sum, div2k<24>(s[15]));
+  }
+}
+template <class M, int DIAG> __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+  external_layer(s);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = cube<M>(kb::add(s[i], EXT_RC[r][i]));
+    external_layer(s);
+  }
+#pragma unroll
+  for (int r = 0; r < 13; r++) {
+    s[0] = cube<M>(kb::add(s[0], INT_RC[r]));
+    internal_layer<M, DIAG>(s);
+  }
+#pragma unroll
+  for (int r = 4; r < 8; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = cube<M>(kb::add(s[i], EXT_RC[r][i]));
+    external_layer(s);
+  }
+}
+
+template <class M, int DIAG, int ILP, int MINB>
+__global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
+  uint32_t s[ILP][16];
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < ILP; k++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[k][i] = (tid * 2654435761u + i * 40503u + k * 977u) % P;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < ILP; k++) permute<M, DIAG>(s[k]);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < ILP; k++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= s[k][i] + i;
+  out[tid * ILP] = acc;
+  if (ILP > 1) out[tid * ILP + 1] = s[ILP - 1][3];
+}
+
+template <class M, int DIAG, int ILP, int MINB>
+void run(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
+  int blocks = sms * 8, iters = 128;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, bench<M, DIAG, ILP, MINB>);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench<M, DIAG, ILP, MINB>, 256, 0);
+  blocks = sms * occ;
+  bench<M, DIAG, ILP, MINB><<<blocks, 256>>>(d_out, 4);
+  cudaDeviceSynchronize();
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e9;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(a);
+    bench<M, DIAG, ILP, MINB><<<blocks, 256>>>(d_out, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  double perms = (double)blocks * 256 * ILP * iters;
+  // correctness: first thread's first word after `iters` perms must agree between variants (ILP==1 layout)
+  uint32_t h[2];
+  cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+  const char* ok = "";
+  if (ILP == 1) { if (h_ref[0] == 0xffffffffu) h_ref[0] = h[0]; ok = (h[0] == h_ref[0]) ? " same-result" : " RESULT-DIFFERS"; }
+  printf("%-28s regs=%3d occ=%d blocks/SM  %.3f ms  %.2f Gperm/s  %.1f clk/perm/SM@1.9GHz%s err=%s\n", name, fa.numRegs, occ, best,
+         perms / best / 1e6, best * 1e-3 * 1.9e9 * sms / perms, ok, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  int sms = p.multiProcessorCount;
+  printf("%s, %d SMs\n", p.name, sms);
+  uint32_t* d; cudaMalloc(&d, (size_t)sms * 16 * 256 * 2 * 4);
+  uint32_t ref[1] = {0xffffffffu};
+  run<MulSub, 0, 1, 1>("sub/diagmul", d, ref, sms);
+  run<MulSub, 1, 1, 1>("sub/diagshift", d, ref, sms);
+  run<MulAdd, 0, 1, 1>("add/diagmul", d, ref, sms);
+  run<MulAdd, 1, 1, 1>("add/diagshift", d, ref, sms);
+  run<MulLea, 1, 1, 1>("lea/diagshift", d, ref, sms);
+  run<MulSub, 1, 1, 6>("sub/diagshift minb6", d, ref, sms);
+  run<MulAdd, 1, 1, 6>("add/diagshift minb6", d, ref, sms);
+  run<MulAdd, 1, 1, 8>("add/diagshift minb8", d, ref, sms);
+  run<MulSub, 1, 2, 1>("sub/diagshift ilp2", d, ref, sms);
+  run<MulAdd, 1, 2, 1>("add/diagshift ilp2", d, ref, sms);
+  run<MulAdd, 1, 2, 3>("add/diagshift ilp2 minb3", d, ref, sms);
+  return 0;
+}

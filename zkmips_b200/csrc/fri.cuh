@@ -1,0 +1,322 @@
+// fri.cuh -- kernels of TwoAdicFriPcs::open: device-resident duplex challenger, opening reduction
+// (barycentric evaluation + alpha-reduced quotients), FRI folding, proof-of-work grind and query gather.
+//
+// Replaces the CPU loops of Plonky3 `TwoAdicFriPcs::open` / `p3_fri::prover::{commit_phase, answer_query}`
+// / `DuplexChallenger` behind the call at crates/stark/src/prover.rs:546-556.  Semantics: SURVEY A.6 and
+// A.10, pinned by the in-repo verifier crates/recursion/circuit/src/fri.rs:34-405 and
+// crates/recursion/circuit/src/challenger.rs:90-233.
+//
+// The Fiat-Shamir transcript lives in device memory (Chal) and is advanced by one-thread kernels, so the
+// whole commit phase (fold -> Merkle commit -> observe root -> sample beta -> fold ...) is enqueued on one
+// stream without a host round trip per layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "launch.cuh"
+#include "poseidon2.cuh"
+
+namespace fri {
+
+struct Chal {  // same 34-word image as zk_challenger in include/zkgpu.h
+  uint32_t state[16];
+  uint32_t in[8];
+  uint32_t n_in;
+  uint32_t out[8];
+  uint32_t n_out;
+};
+
+__device__ __forceinline__ void ch_duplex(Chal& c) {  // challenger.rs:221-232
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = (i < 8 && (uint32_t)i < c.n_in) ? c.in[i] : c.state[i];
+  c.n_in = 0;
+  p2::permute(s);
+#pragma unroll
+  for (int i = 0; i < 16; i++) c.state[i] = s[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.out[i] = s[i];
+  c.n_out = 8;
+}
+__device__ __forceinline__ void ch_observe(Chal& c, uint32_t v) {  // challenger.rs:90-98
+  c.n_out = 0;
+  c.in[c.n_in++] = v;
+  if (c.n_in == 8) ch_duplex(c);
+}
+__device__ __forceinline__ uint32_t ch_sample(Chal& c) {  // challenger.rs:100-106
+  if (c.n_in != 0 || c.n_out == 0) ch_duplex(c);
+  return c.out[--c.n_out];
+}
+
+__global__ void ch_observe_kernel(Chal* ch, const uint32_t* vals, uint32_t n) {
+  if (threadIdx.x | blockIdx.x) return;
+  Chal c = *ch;
+  for (uint32_t i = 0; i < n; i++) ch_observe(c, vals[i]);
+  *ch = c;
+}
+// samples n_ext extension elements (4 base samples each, coefficient 0 first: challenger.rs:201-207)
+__global__ void ch_sample_ext_kernel(Chal* ch, uint32_t* out, uint32_t n_ext) {
+  if (threadIdx.x | blockIdx.x) return;
+  Chal c = *ch;
+  for (uint32_t i = 0; i < 4 * n_ext; i++) out[i] = ch_sample(c);
+  *ch = c;
+}
+__global__ void ch_sample_bits_kernel(Chal* ch, uint32_t bits, uint32_t n, uint64_t* out) {
+  if (threadIdx.x | blockIdx.x) return;
+  Chal c = *ch;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t v = kb::from_monty(ch_sample(c));
+    out[i] = bits >= 32 ? v : (v & ((1u << bits) - 1));
+  }
+  *ch = c;
+}
+// Proof of work: found = min canonical w in [base, base + threads) with check_witness(bits, w).
+// (Plonky3 takes any hit; the smallest one makes runs reproducible.)
+__global__ void __launch_bounds__(256) grind_kernel(const Chal* ch, uint32_t bits, uint32_t base, uint32_t count,
+                                                    uint32_t* found) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  uint32_t w = base + t;
+  if (w >= kb::P) return;
+  Chal c = *ch;
+  ch_observe(c, kb::to_monty(w));
+  uint32_t v = kb::from_monty(ch_sample(c));
+  if ((v & ((1u << bits) - 1)) == 0) atomicMin(found, w);
+}
+// Applies the witness (found by grind, or injected) to the real transcript: check_witness (challenger.rs:209-219).
+// status[0] |= 1 when the witness does not satisfy the proof-of-work condition.
+__global__ void ch_witness_kernel(Chal* ch, uint32_t bits, const uint32_t* found, int64_t inject, uint32_t* slot,
+                                  uint32_t* status) {
+  if (threadIdx.x | blockIdx.x) return;
+  uint32_t wm = inject >= 0 ? (uint32_t)inject : kb::to_monty(*found);
+  if (inject < 0 && *found == 0xffffffffu) status[0] |= 2u;
+  Chal c = *ch;
+  ch_observe(c, wm);
+  uint32_t v = kb::from_monty(ch_sample(c));
+  if ((v & ((1u << bits) - 1)) != 0) status[0] |= 1u;
+  *ch = c;
+  *slot = wm;
+}
+
+// ---- extension helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ kb::Ext ld_ext(const uint32_t* p) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  return kb::Ext{{v.x, v.y, v.z, v.w}};
+}
+__device__ __forceinline__ void st_ext(uint32_t* p, kb::Ext e) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(e.c[0], e.c[1], e.c[2], e.c[3]);
+}
+
+// out[j] = alpha^j, j < n
+__global__ void ext_powers_kernel(const uint32_t* alpha, uint32_t* out, uint32_t n) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  st_ext(out + 4 * (size_t)j, kb::ext_pow(ld_ext(alpha), j));
+}
+
+// x_r = GENERATOR * g_L^{bitrev_L(r)}: the point of row r of a bit-reversed LDE of height 2^L
+__device__ __forceinline__ uint32_t lde_point(uint32_t r, uint32_t L, uint32_t gL) {
+  return kb::mul(kb::GEN, kb::pow(gL, kb::bitrev(r, L)));
+}
+
+// rowred[r] = sum_j alpha^j m[r][j]   (Matrix::dot_ext_powers).  One thread per row; alpha powers in smem.
+constexpr int RR_CHUNK = 512;  // alpha powers staged per pass
+__global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
+                                                         const uint32_t* __restrict__ apow, uint32_t* __restrict__ rowred) {
+  __shared__ uint32_t sp[RR_CHUNK * 4];
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t* row = mat + (r < H ? r : 0) * w;
+  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // sums of Montgomery-reduced products, < w * p
+  for (uint32_t c0 = 0; c0 < w; c0 += RR_CHUNK) {
+    uint32_t nc = min(w - c0, (uint32_t)RR_CHUNK);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nc * 4; i += blockDim.x) sp[i] = apow[(size_t)c0 * 4 + i];
+    __syncthreads();
+    if (r < H) {
+      for (uint32_t j = 0; j < nc; j++) {
+        uint32_t v = __ldg(row + c0 + j);
+        a0 += kb::mul(sp[4 * j + 0], v);
+        a1 += kb::mul(sp[4 * j + 1], v);
+        a2 += kb::mul(sp[4 * j + 2], v);
+        a3 += kb::mul(sp[4 * j + 3], v);
+      }
+    }
+  }
+  if (r < H) {
+    kb::Ext e{{(uint32_t)(a0 % kb::P), (uint32_t)(a1 % kb::P), (uint32_t)(a2 % kb::P), (uint32_t)(a3 % kb::P)}};
+    st_ext(rowred + 4 * r, e);
+  }
+}
+
+// Barycentric weights over the low coset: wts[p][r] = x_r / (z_p - x_r), r < N = 2^n
+__global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __restrict__ pts, uint32_t npts, uint32_t n,
+                                                           uint32_t gn, uint32_t* __restrict__ wts) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (1u << n)) return;
+  uint32_t x = lde_point(r, n, gn);
+  for (uint32_t p = 0; p < npts; p++) {
+    kb::Ext z = ld_ext(pts + 4 * p);
+    kb::Ext d = kb::ext_inv(kb::ext_sub_base(z, x));
+    st_ext(wts + 4 * (((size_t)p << n) + r), kb::ext_mul_base(d, x));
+  }
+}
+
+// partial[chunk][p][c] = sum over the rows of the chunk of wts[p][r] * m[r][c].
+// Block = 32 columns x 8 row lanes; rows of the chunk are strided over the 8 lanes, then reduced in smem.
+constexpr int BARY_ROWS = 2048;  // rows per chunk
+__global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
+                                                           const uint32_t* __restrict__ wts, uint32_t npts,
+                                                           uint32_t* __restrict__ partial) {
+  __shared__ uint32_t red[8][2][4][32];
+  const uint32_t lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const uint32_t ntile = (w + 31) / 32;
+  const uint32_t tile = blockIdx.x % ntile, chunk = blockIdx.x / ntile;
+  const uint32_t col = tile * 32 + lane;
+  const uint64_t N = 1ull << n;
+  uint64_t r0 = (uint64_t)chunk * BARY_ROWS, r1 = min(N, r0 + BARY_ROWS);
+  uint64_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (col < w) {
+    for (uint64_t r = r0 + sub; r < r1; r += 8) {
+      uint32_t v = __ldg(mat + r * w + col);
+      for (uint32_t p = 0; p < npts; p++) {
+        uint4 wt = __ldg(reinterpret_cast<const uint4*>(wts + 4 * (((size_t)p << n) + r)));
+        acc[p][0] += kb::mul(wt.x, v);
+        acc[p][1] += kb::mul(wt.y, v);
+        acc[p][2] += kb::mul(wt.z, v);
+        acc[p][3] += kb::mul(wt.w, v);
+      }
+    }
+  }
+  for (int p = 0; p < 2; p++)
+    for (int k = 0; k < 4; k++) red[sub][p][k][lane] = (uint32_t)(acc[p][k] % kb::P);
+  __syncthreads();
+  if (sub == 0 && col < w) {
+    for (uint32_t p = 0; p < npts; p++) {
+      kb::Ext e;
+      for (int k = 0; k < 4; k++) {
+        uint32_t s = 0;
+        for (int q = 0; q < 8; q++) s = kb::add(s, red[q][p][k][lane]);
+        e.c[k] = s;
+      }
+      st_ext(partial + 4 * (((size_t)chunk * npts + p) * w + col), e);
+    }
+  }
+}
+
+// ys[p][c] = scale_p * sum_chunks partial;  scale_p = (z^N - s^N) / (N s^N), s = GENERATOR.
+// Writes the opened values into the proof (point-major, width ext each).
+__global__ void __launch_bounds__(256) bary_final_kernel(const uint32_t* __restrict__ partial, uint32_t nchunks,
+                                                         uint32_t w, uint32_t n, const uint32_t* __restrict__ pts,
+                                                         uint32_t npts, uint32_t* __restrict__ ys) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= w) return;
+  for (uint32_t p = 0; p < npts; p++) {
+    kb::Ext acc = kb::ext_zero();
+    for (uint32_t k = 0; k < nchunks; k++) acc = kb::ext_add(acc, ld_ext(partial + 4 * (((size_t)k * npts + p) * w + c)));
+    kb::Ext z = ld_ext(pts + 4 * p);
+    kb::Ext zN = z;
+    uint32_t sN = kb::GEN;
+    for (uint32_t i = 0; i < n; i++) {
+      zN = kb::ext_sqr(zN);
+      sN = kb::sqr(sN);
+    }
+    uint32_t Nm = kb::to_monty(1u << n);  // n <= 22
+    kb::Ext scale = kb::ext_mul_base(kb::ext_sub_base(zN, sN), kb::inv(kb::mul(Nm, sN)));
+    st_ext(ys + 4 * ((size_t)p * w + c), kb::ext_mul(acc, scale));
+  }
+}
+
+// red[p] = sum_j alpha^j ys[p][j];  aoff[p] = alpha^(offset + p * w).   One block.
+__global__ void __launch_bounds__(256) reduce_ys_kernel(const uint32_t* __restrict__ ys, const uint32_t* __restrict__ apow,
+                                                        const uint32_t* __restrict__ alpha, uint32_t w, uint32_t npts,
+                                                        uint64_t offset, uint32_t* __restrict__ red_ys,
+                                                        uint32_t* __restrict__ aoff) {
+  __shared__ uint32_t sm[256 * 4];
+  for (uint32_t p = 0; p < npts; p++) {
+    kb::Ext acc = kb::ext_zero();
+    for (uint32_t j = threadIdx.x; j < w; j += blockDim.x)
+      acc = kb::ext_add(acc, kb::ext_mul(ld_ext(apow + 4 * (size_t)j), ld_ext(ys + 4 * ((size_t)p * w + j))));
+    __syncthreads();
+    st_ext(sm + 4 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) st_ext(sm + 4 * threadIdx.x, kb::ext_add(ld_ext(sm + 4 * threadIdx.x), ld_ext(sm + 4 * (threadIdx.x + s))));
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      st_ext(red_ys + 4 * p, ld_ext(sm));
+      st_ext(aoff + 4 * p, kb::ext_pow(ld_ext(alpha), offset + (uint64_t)p * w));
+    }
+  }
+}
+
+// ro[r] += sum_p aoff[p] * (rowred[r] - red_ys[p]) / (x_r - z_p)
+__global__ void __launch_bounds__(256) ro_accumulate_kernel(uint32_t* __restrict__ ro, const uint32_t* __restrict__ rowred,
+                                                            uint32_t L, uint32_t gL, const uint32_t* __restrict__ pts,
+                                                            uint32_t npts, const uint32_t* __restrict__ red_ys,
+                                                            const uint32_t* __restrict__ aoff) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (1u << L)) return;
+  uint32_t x = lde_point(r, L, gL);
+  kb::Ext rr = ld_ext(rowred + 4 * (size_t)r);
+  kb::Ext acc = ld_ext(ro + 4 * (size_t)r);
+  for (uint32_t p = 0; p < npts; p++) {
+    kb::Ext z = ld_ext(pts + 4 * p);
+    kb::Ext inv_den = kb::ext_inv(kb::ext_neg(kb::ext_sub_base(z, x)));  // 1 / (x - z)
+    kb::Ext t = kb::ext_mul(kb::ext_sub(rr, ld_ext(red_ys + 4 * p)), inv_den);
+    acc = kb::ext_add(acc, kb::ext_mul(ld_ext(aoff + 4 * p), t));
+  }
+  st_ext(ro + 4 * (size_t)r, acc);
+}
+
+// FRI fold (TwoAdicFriGenericConfig::fold_matrix + the beta^2 roll-in of commit_phase; mirror fri.rs:308-351):
+// out[k] = (1/2 + beta/(2 x_k)) in[2k] + (1/2 - beta/(2 x_k)) in[2k+1] + beta^2 * ro_next[k],
+// x_k = g_L^{bitrev_{L-1}(k)}, L = log2(len(in)).
+__global__ void __launch_bounds__(256) fold_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t L,
+                                                   uint32_t gL_inv, const uint32_t* __restrict__ beta,
+                                                   const uint32_t* __restrict__ ro_next) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (1u << (L - 1))) return;
+  kb::Ext b = ld_ext(beta);
+  uint32_t inv_x = kb::pow(gL_inv, kb::bitrev(k, L - 1));
+  kb::Ext pw = kb::ext_mul_base(b, kb::mul(kb::HALF, inv_x));
+  kb::Ext ca = kb::ext_add_base(pw, kb::HALF);
+  kb::Ext cb = kb::ext_neg(kb::ext_sub_base(pw, kb::HALF));
+  kb::Ext e0 = ld_ext(in + 8 * (size_t)k), e1 = ld_ext(in + 8 * (size_t)k + 4);
+  kb::Ext f = kb::ext_add(kb::ext_mul(ca, e0), kb::ext_mul(cb, e1));
+  if (ro_next) f = kb::ext_add(f, kb::ext_mul(kb::ext_sqr(b), ld_ext(ro_next + 4 * (size_t)k)));
+  st_ext(out + 4 * (size_t)k, f);
+}
+
+// status |= 4 when the final folded vector is not constant; writes final_poly.
+__global__ void final_poly_kernel(const uint32_t* __restrict__ folded, uint32_t len, uint32_t* __restrict__ slot,
+                                  uint32_t* status) {
+  if (threadIdx.x | blockIdx.x) return;
+  kb::Ext f0 = ld_ext(folded);
+  for (uint32_t k = 1; k < len; k++) {
+    kb::Ext f = ld_ext(folded + 4 * k);
+    if (f.c[0] != f0.c[0] || f.c[1] != f0.c[1] || f.c[2] != f0.c[2] || f.c[3] != f0.c[3]) status[0] |= 4u;
+  }
+  st_ext(slot, f0);
+}
+
+// answer_query for one commit-phase layer (p3_fri::prover::answer_query): block q = query q.
+// Writes sibling value (4 words) then the path of the pair leaf into proof[q * query_stride + off ...].
+__global__ void fri_layer_query_kernel(const uint32_t* __restrict__ leaves /* ext pairs */, const uint32_t* __restrict__ digests,
+                                       const uint64_t* __restrict__ layer_off, uint32_t log_h /* of the layer tree */,
+                                       uint32_t layer_i, const uint64_t* __restrict__ indices, uint32_t* __restrict__ proof,
+                                       uint64_t query_stride, uint64_t off) {
+  uint64_t index_i = indices[blockIdx.x] >> layer_i;
+  uint64_t pair = index_i >> 1;
+  uint32_t* o = proof + blockIdx.x * query_stride + off;
+  for (uint32_t t = threadIdx.x; t < 4 + log_h * 8; t += blockDim.x) {
+    if (t < 4) {
+      o[t] = leaves[pair * 8 + 4 * ((index_i ^ 1) & 1) + t];
+    } else {
+      uint32_t l = (t - 4) >> 3, k = (t - 4) & 7;
+      o[t] = digests[layer_off[l] + (((pair >> l) ^ 1) << 3) + k];
+    }
+  }
+}
+
+}  // namespace fri
