@@ -116,6 +116,47 @@ int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out_ho
 int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const uint64_t* indices, uint32_t* opened_host,
                             uint32_t* proofs_host);
 
+/* ---- DuplexChallenger<Val, Perm, 16, 8> (crates/stark/src/kb31_poseidon2.rs:180; semantics restated at
+ *      crates/recursion/circuit/src/challenger.rs:90-233) ------------------------------------------------
+ * The 34-word image of a Plonky3 DuplexChallenger: sponge_state, input_buffer (+ length), output_buffer
+ * (+ length; samples pop from the END).  The Rust side converts its challenger to/from this struct around
+ * zk_pcs_open; the zk_challenger_* calls run the same transcript operations on the device. */
+typedef struct {
+  uint32_t state[16];
+  uint32_t in[8];
+  uint32_t n_in;
+  uint32_t out[8];
+  uint32_t n_out;
+} zk_challenger;
+int32_t zk_challenger_init(zk_challenger* ch);
+int32_t zk_challenger_observe(zk_ctx* ctx, zk_challenger* ch, const uint32_t* vals, uint32_t n);
+int32_t zk_challenger_sample_ext(zk_ctx* ctx, zk_challenger* ch, uint32_t n_ext, uint32_t* out /* 4*n_ext */);
+int32_t zk_challenger_sample_bits(zk_ctx* ctx, zk_challenger* ch, uint32_t bits, uint32_t n, uint64_t* out);
+/* DuplexChallenger::grind: finds the SMALLEST canonical witness (Plonky3 takes any), applies it to ch. */
+int32_t zk_challenger_grind(zk_ctx* ctx, zk_challenger* ch, uint32_t bits, uint32_t* witness);
+
+/* ---- Pcs::open (TwoAdicFriPcs::open; call site crates/stark/src/prover.rs:546-556) --------------------
+ * rounds[r] = prover data of round r (e.g. preprocessed, main, permutation, quotient); n_points[k] and
+ * points (4 words each, flattened) give the opening points of matrix k, matrices counted round by round
+ * in commit order.  Steps: alpha = sample_ext; opened values by barycentric evaluation;
+ * reduced openings per height class; FRI commit phase (fold, ExtensionMmcs commit, observe, beta);
+ * final_poly; proof-of-work; num_queries query openings.
+ *
+ * Flat proof layout (u32 words), shared with the CPU oracle:
+ *   opened values : for round, matrix, point: width extension elements
+ *   fri           : n_layers * 8 commit-phase roots, final_poly (4), pow_witness (1)
+ *   queries       : num_queries x { per round: opened rows (sum of widths) + path (log_max_r * 8);
+ *                                   per layer i: sibling value (4) + path ((log_max - i - 1) * 8) }
+ * with log_max = log2 of the tallest committed matrix and n_layers = log_max - log_blowup.
+ * inject_witness >= 0 uses that (Montgomery) pow witness instead of grinding, so a transcript produced by
+ * the reference prover (whose grind is non-deterministic) can be reproduced bit for bit.
+ * ch is advanced exactly as the reference's challenger would be. */
+uint64_t zk_pcs_proof_words(uint32_t n_rounds, const zk_pdata* const* rounds, const uint32_t* n_points,
+                            uint32_t log_blowup, uint32_t num_queries);
+int32_t zk_pcs_open(zk_ctx* ctx, uint32_t n_rounds, const zk_pdata* const* rounds, const uint32_t* n_points,
+                    const uint32_t* points, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                    zk_challenger* ch, int64_t inject_witness, uint32_t* proof_host, uint64_t proof_cap);
+
 #ifdef __cplusplus
 }
 #endif

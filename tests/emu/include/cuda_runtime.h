@@ -26,7 +26,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __constant__
-#define __shared__
+#define __shared__ static
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };

@@ -4,4 +4,4 @@ The product is the C-ABI CUDA library `libzkgpu.so` (include/zkgpu.h).  This pac
 sources (csrc/), the build recipe (build.py) and a thin ctypes binding used by the tests and bench.py;
 there is no CPU fallback: every compute entry point needs a CUDA device.
 """
-from .native import Lib, ZkError, load  # noqa: F401
+from .native import Challenger, Lib, ZkError, load, pcs_open  # noqa: F401

@@ -1,6 +1,7 @@
 // zkgpu.cu -- libzkgpu.so: context, Pcs::commit path (coset LDE + Poseidon2 MMCS) and the C ABI of
 // include/zkgpu.h.  sm_100a only; no CPU fallback.
 #include "zkgpu_internal.cuh"
+#include "ntt.cuh"
 
 thread_local std::string g_last_error;
 
@@ -27,17 +28,18 @@ __global__ void bitrev_rows_kernel(const uint32_t* __restrict__ in, uint32_t* __
 // Mmcs::open_batch gather: block b = query index b
 __global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32_t n_mats, uint32_t sum_w,
                                    const uint32_t* __restrict__ digests, const uint64_t* __restrict__ layer_off,
-                                   uint32_t log_max, const uint64_t* __restrict__ indices,
-                                   uint32_t* __restrict__ opened, uint32_t* __restrict__ proofs) {
-  uint64_t index = indices[blockIdx.x];
-  uint32_t* o = opened + (size_t)blockIdx.x * sum_w;
+                                   uint32_t log_max, const uint64_t* __restrict__ indices, uint32_t shift,
+                                   uint32_t* __restrict__ opened, uint64_t opened_stride,
+                                   uint32_t* __restrict__ proofs, uint64_t proofs_stride) {
+  uint64_t index = indices[blockIdx.x] >> shift;
+  uint32_t* o = opened + (size_t)blockIdx.x * opened_stride;
   for (uint32_t m = 0; m < n_mats; m++) {
     zk_open_desc d = mats[m];
     uint64_t r = index >> (log_max - d.log_h);
     const uint32_t* row = d.ptr + r * d.w;
     for (uint32_t c = threadIdx.x; c < d.w; c += blockDim.x) o[d.off + c] = row[c];
   }
-  uint32_t* p = proofs + (size_t)blockIdx.x * log_max * 8;
+  uint32_t* p = proofs + (size_t)blockIdx.x * proofs_stride;
   for (uint32_t t = threadIdx.x; t < log_max * 8; t += blockDim.x) {
     uint32_t l = t >> 3, k = t & 7;
     p[t] = digests[layer_off[l] + (((index >> l) ^ 1) << 3) + k];
@@ -284,7 +286,7 @@ static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t
 }
 
 // Builds the digest layers over pd->mats (already on the device) and fills root.
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd) {
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root) {
   uint32_t n = pd->n;
   pd->order.resize(n);
   for (uint32_t i = 0; i < n; i++) pd->order[i] = i;
@@ -345,8 +347,29 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd) {
   CK(cudaMemcpyAsync(pd->d_desc, od.data(), n * sizeof(zk_open_desc), cudaMemcpyHostToDevice, c->stream));
   if ((rc = dev_alloc(c, (pd->log_max + 1) * 8, (void**)&pd->d_layer_off))) return rc;
   CK(cudaMemcpyAsync(pd->d_layer_off, pd->layer_off.data(), (pd->log_max + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off[pd->log_max], 32, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  if (fetch_root) {
+    CK(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off[pd->log_max], 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return ZK_OK;
+}
+
+int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
+                            zk_pdata** out) {
+  zk_pdata* pd = new zk_pdata();
+  pd->ctx = c;
+  pd->n = 1;
+  pd->heights.assign(1, h);
+  pd->widths.assign(1, w);
+  pd->mats.assign(1, mat);
+  pd->owned.assign(1, take_ownership);
+  int32_t rc = mmcs_build(c, pd, fetch_root);
+  if (rc != ZK_OK) {
+    pd->owned[0] = false;
+    pdata_release(pd);
+    return rc;
+  }
+  *out = pd;
   return ZK_OK;
 }
 
@@ -518,10 +541,10 @@ extern "C" int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint3
   return ZK_OK;
 }
 
-int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t* d_opened,
-                       uint32_t* d_proofs) {
+int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t shift,
+                       uint32_t* d_opened, uint64_t opened_stride, uint32_t* d_proofs, uint64_t proofs_stride) {
   ZK_LAUNCH(open_gather_kernel, n_idx, 128, 0, c->stream, pd->d_desc, pd->n, pd->sum_w, pd->digests, pd->d_layer_off,
-                                                   pd->log_max, d_idx, d_opened, d_proofs);
+            pd->log_max, d_idx, shift, d_opened, opened_stride, d_proofs, proofs_stride);
   CK(cudaGetLastError());
   c->launches++;
   return ZK_OK;
@@ -545,7 +568,7 @@ extern "C" int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const
   if ((rc = dev_alloc(c, ob, (void**)&d_op))) return rc;
   if ((rc = dev_alloc(c, pb, (void**)&d_pr))) return rc;
   CK(cudaMemcpyAsync(d_idx, indices, n_idx * 8ull, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = pdata_open_dev(c, pd, n_idx, d_idx, d_op, d_pr))) return rc;
+  if ((rc = pdata_open_dev(c, pd, n_idx, d_idx, 0, d_op, pd->sum_w, d_pr, (uint64_t)pd->log_max * 8))) return rc;
   if (ob) CK(cudaMemcpyAsync(opened, d_op, ob, cudaMemcpyDeviceToHost, c->stream));
   if (pb) CK(cudaMemcpyAsync(proofs, d_pr, pb, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

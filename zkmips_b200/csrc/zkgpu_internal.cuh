@@ -11,8 +11,8 @@
 
 #include "../../include/zkgpu.h"
 #include "kb31_host.h"
+#include "launch.cuh"
 #include "merkle.cuh"
-#include "ntt.cuh"
 
 int32_t zk_fail(int32_t code, const std::string& msg);
 
@@ -29,7 +29,7 @@ struct zk_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::mutex mu;
-  uint32_t log_L = 22;                    // NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
+  uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
   uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
   bool prof = false;
   struct Rec {
@@ -76,7 +76,14 @@ int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out);
 int32_t dev_free(zk_ctx* c, void* p);
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
                 uint32_t* out);
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd);
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true);
+// Mmcs::commit of one device-resident matrix; with fetch_root == false nothing is copied to the host and the
+// stream is not synchronised (the root stays at pdata_root_dev()).
+int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
+                            zk_pdata** out);
+inline const uint32_t* pdata_root_dev(const zk_pdata* pd) { return pd->digests + pd->layer_off[pd->log_max]; }
 void pdata_release(zk_pdata* pd);
-int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t* d_opened,
-                       uint32_t* d_proofs);
+// open_batch gather for n_idx indices (each shifted right by `shift` first); query q writes its rows at
+// opened + q * opened_stride and its path at proofs + q * proofs_stride (strides in words).
+int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t shift,
+                       uint32_t* d_opened, uint64_t opened_stride, uint32_t* d_proofs, uint64_t proofs_stride);

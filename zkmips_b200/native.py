@@ -53,6 +53,13 @@ PROTOTYPES = {
     "zk_pdata_copy_lde": (i32, [vp, u32, u32p]),
     "zk_pdata_copy_layer": (i32, [vp, u32, u32p]),
     "zk_pdata_open_batch": (i32, [vp, u32, u64p, u32p, u32p]),
+    "zk_challenger_init": (i32, [vp]),
+    "zk_challenger_observe": (i32, [vp, vp, u32p, u32]),
+    "zk_challenger_sample_ext": (i32, [vp, vp, u32, u32p]),
+    "zk_challenger_sample_bits": (i32, [vp, vp, u32, u32, u64p]),
+    "zk_challenger_grind": (i32, [vp, vp, u32, u32p]),
+    "zk_pcs_proof_words": (u64, [u32, C.POINTER(vp), u32p, u32, u32]),
+    "zk_pcs_open": (i32, [vp, u32, C.POINTER(vp), u32p, u32p, u32, u32, u32, vp, C.c_int64, u32p, u64]),
 }
 
 
@@ -289,6 +296,51 @@ class Ctx:
         self.lib.check(self.d.zk_mmcs_commit(self.h, len(ms), ptrs, heights.ctypes.data_as(u64p), _p32(widths),
                                              _p32(root), C.byref(pd)))
         return root, PData(self, pd, root)
+
+
+class Challenger:
+    """Host image of a DuplexChallenger (34 words) whose operations run on the device."""
+
+    def __init__(self, ctx, words=None):
+        self.ctx = ctx
+        self.w = np.zeros(34, np.uint32) if words is None else np.ascontiguousarray(words, dtype=np.uint32).copy()
+
+    def _p(self):
+        return self.w.ctypes.data_as(vp)
+
+    def observe(self, vals):
+        v = _arr(vals, np.uint32).reshape(-1)
+        self.ctx.lib.check(self.ctx.d.zk_challenger_observe(self.ctx.h, self._p(), _p32(v), v.size))
+
+    def sample_ext(self, n=1):
+        out = np.empty((n, 4), np.uint32)
+        self.ctx.lib.check(self.ctx.d.zk_challenger_sample_ext(self.ctx.h, self._p(), n, _p32(out)))
+        return out[0] if n == 1 else out
+
+    def sample_bits(self, bits, n=1):
+        out = np.empty(n, np.uint64)
+        self.ctx.lib.check(self.ctx.d.zk_challenger_sample_bits(self.ctx.h, self._p(), bits, n, out.ctypes.data_as(u64p)))
+        return out
+
+    def grind(self, bits):
+        w = u32()
+        self.ctx.lib.check(self.ctx.d.zk_challenger_grind(self.ctx.h, self._p(), bits, C.byref(w)))
+        return w.value
+
+
+def pcs_open(ctx, rounds, points_per_mat, ch, log_blowup=1, num_queries=84, pow_bits=16, inject_witness=-1):
+    """TwoAdicFriPcs::open.  rounds: list of PData; points_per_mat: flat list (round-major) of lists of 4-word
+    points; ch: Challenger (advanced in place).  Returns the flat proof (layout: include/zkgpu.h)."""
+    handles = (vp * len(rounds))(*[r.h for r in rounds])
+    n_points = _arr([len(p) for p in points_per_mat], np.uint32)
+    pts = _arr([q for p in points_per_mat for q in p], np.uint32).reshape(-1)
+    if pts.size == 0:
+        pts = np.zeros(4, np.uint32)
+    words = ctx.d.zk_pcs_proof_words(len(rounds), handles, _p32(n_points), log_blowup, num_queries)
+    proof = np.zeros(words, np.uint32)
+    ctx.lib.check(ctx.d.zk_pcs_open(ctx.h, len(rounds), handles, _p32(n_points), _p32(pts), log_blowup, num_queries,
+                                    pow_bits, ch._p(), inject_witness, _p32(proof), words))
+    return proof
 
 
 _default = None
