@@ -1,6 +1,7 @@
 // zkgpu.cu -- libzkgpu.so: context, Pcs::commit path (coset LDE + Poseidon2 MMCS) and the C ABI of
 // include/zkgpu.h.  sm_100a only; no CPU fallback.
 #include "zkgpu_internal.cuh"
+#include "merkle.cuh"
 #include "ntt.cuh"
 
 thread_local std::string g_last_error;

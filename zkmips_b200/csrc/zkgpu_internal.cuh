@@ -12,7 +12,6 @@
 #include "../../include/zkgpu.h"
 #include "kb31_host.h"
 #include "launch.cuh"
-#include "merkle.cuh"
 
 int32_t zk_fail(int32_t code, const std::string& msg);
 
