@@ -116,6 +116,29 @@ int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out_ho
 int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const uint64_t* indices, uint32_t* opened_host,
                             uint32_t* proofs_host);
 
+/* ---- quotient (quotient_values, crates/stark/src/quotient.rs:19-171) ---------------------------------
+ * Chips are compiled into the library as generated kernels (zkmips_b200/air/codegen.py); a chip is
+ * addressed by the index of its name.  zk_quotient evaluates, for every point of the quotient domain
+ * (size 2^(log_degree + log_quotient_degree), shift GENERATOR), the folded constraints
+ * sum_k alpha^(n-1-k) C_k times inv_zeroifier, reading local/next rows directly from the committed LDEs
+ * (Pcs::get_evaluations_on_domain without the copy), and writes the 2^log_quotient_degree quotient chunks
+ * (split_evals, crates/stark/src/prover.rs:477-488) as N x 4 base matrices, back to back, into a device
+ * buffer the caller frees with zk_dev_free (after committing it with zk_commit_dev, domain shift of
+ * chunk c = GENERATOR * g_{n+lqd}^c).  The 11 data arguments mirror quotient_values' parameters. */
+typedef struct {
+  uint32_t main_width, prep_width, perm_width /* extension columns */, num_public_values, num_challenges;
+  uint32_t num_constraints, max_degree, num_kernels;
+} zk_air_desc;
+int32_t zk_air_count(void);
+const char* zk_air_name(int32_t id);
+int32_t zk_air_find(const char* name); /* -1 when unknown */
+int32_t zk_air_info(int32_t id, zk_air_desc* out);
+int32_t zk_quotient(zk_ctx* ctx, int32_t air_id, const zk_pdata* prep, uint32_t prep_idx, const zk_pdata* main_data,
+                    uint32_t main_idx, const zk_pdata* perm, uint32_t perm_idx, uint32_t log_degree,
+                    uint32_t log_quotient_degree, const uint32_t alpha[4], const uint32_t* perm_challenges,
+                    const uint32_t* public_values, uint32_t n_public_values, const uint32_t local_cumsum[4],
+                    const uint32_t global_cumsum[14], zk_dptr* out_chunks);
+
 /* ---- DuplexChallenger<Val, Perm, 16, 8> (crates/stark/src/kb31_poseidon2.rs:180; semantics restated at
  *      crates/recursion/circuit/src/challenger.rs:90-233) ------------------------------------------------
  * The 34-word image of a Plonky3 DuplexChallenger: sponge_state, input_buffer (+ length), output_buffer

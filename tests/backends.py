@@ -18,7 +18,9 @@ _gpu = None
 
 
 def build_emu(force=False):
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+    from zkmips_b200.air import codegen
+    codegen.write()
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "gen"] + [os.path.join(CSRC, "gen", "airs_gen.cuh")] + [
         os.path.join(EMU_DIR, "emu_runtime.cpp"), os.path.join(EMU_DIR, "include", "cuda_runtime.h"),
         os.path.join(ROOT, "include", "zkgpu.h")]
     if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in srcs):

@@ -1,0 +1,248 @@
+"""SSA constraint programs and the builder that records them.
+
+Node kinds (type 'b' = base field, 'e' = degree-4 extension):
+  const v            b   canonical constant
+  prep r c | main r c b  column c of the local (r=0) / next (r=1) row
+  perm r c           e   extension column c of the permutation trace (4 base columns in memory)
+  pv k | gcs k       b   public value k / coordinate k of the global cumulative sum (SepticDigest, 14 words)
+  lcs                e   local cumulative sum
+  chal k             e   permutation challenge k
+  first|last|trans   b   selectors of the trace domain on the quotient coset
+  add a b | sub a b | mul a b | neg a      (result is 'e' when any operand is 'e')
+
+`AirBuilder` mirrors the methods Ziren's chips call on p3 `AirBuilder` / `PairBuilder` /
+`PermutationAirBuilder` / `MultiTableAirBuilder` (crates/stark/src/folder.rs:52-149):
+main(), preprocessed(), permutation(), permutation_randomness(), public_values(), local_cumulative_sum(),
+global_cumulative_sum(), is_first_row(), is_last_row(), is_transition(), when(...), when_first_row(),
+when_last_row(), when_transition(), assert_zero(), assert_eq(), assert_one(), assert_bool(),
+assert_zero_ext(), assert_eq_ext().  Constraints keep their emission order: constraint k is folded with
+alpha^(n-1-k) (crates/stark/src/prover.rs:453-456).
+"""
+import json
+
+P = 0x7F000001
+
+
+class Expr:
+    __slots__ = ("air", "id")
+
+    def __init__(self, air, nid):
+        self.air, self.id = air, nid
+
+    @property
+    def ty(self):
+        return self.air.types[self.id]
+
+    def _lift(self, o):
+        if isinstance(o, Expr):
+            return o
+        return self.air.const(int(o))
+
+    def __add__(self, o):
+        return self.air.op("add", self, self._lift(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self.air.op("sub", self, self._lift(o))
+
+    def __rsub__(self, o):
+        return self.air.op("sub", self._lift(o), self)
+
+    def __mul__(self, o):
+        return self.air.op("mul", self, self._lift(o))
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self.air.op("neg", self)
+
+
+class Air:
+    """One chip's constraint program."""
+
+    def __init__(self, name, main_width, prep_width=0, perm_width=0, num_public_values=0, num_challenges=2):
+        self.name = name
+        self.main_width, self.prep_width, self.perm_width = main_width, prep_width, perm_width
+        self.num_public_values, self.num_challenges = num_public_values, num_challenges
+        self.nodes = []   # tuples
+        self.types = []   # 'b' / 'e'
+        self.constraints = []  # node ids, emission order
+        self._memo = {}
+
+    # ---- node construction with hash-consing
+    def _node(self, key, ty):
+        nid = self._memo.get(key)
+        if nid is None:
+            nid = len(self.nodes)
+            self.nodes.append(key)
+            self.types.append(ty)
+            self._memo[key] = nid
+        return Expr(self, nid)
+
+    def const(self, v):
+        return self._node(("const", int(v) % P), "b")
+
+    def leaf(self, kind, *args):
+        ty = "e" if kind in ("perm", "lcs", "chal") else "b"
+        return self._node((kind,) + tuple(int(a) for a in args), ty)
+
+    def op(self, kind, a, b=None):
+        if kind == "neg":
+            return self._node(("neg", a.id), a.ty)
+        ia, ib = a.id, b.id
+        # constant folding / identities keep generated kernels small
+        ka, kb_ = self.nodes[ia], self.nodes[ib]
+        if ka[0] == "const" and kb_[0] == "const":
+            va, vb = ka[1], kb_[1]
+            return self.const({"add": va + vb, "sub": va - vb, "mul": va * vb}[kind])
+        if kind == "add" and ka == ("const", 0):
+            return b
+        if kind in ("add", "sub") and kb_ == ("const", 0):
+            return a
+        if kind == "mul" and (ka == ("const", 1)):
+            return b
+        if kind == "mul" and (kb_ == ("const", 1)):
+            return a
+        if kind in ("add", "mul") and ia > ib and a.ty == b.ty:
+            ia, ib = ib, ia  # commutative canonical order
+        ty = "e" if "e" in (self.types[ia], self.types[ib]) else "b"
+        return self._node((kind, ia, ib), ty)
+
+    # ---- serialisation (the format a Rust-side recording builder would emit)
+    def to_json(self):
+        return json.dumps({
+            "name": self.name, "main_width": self.main_width, "prep_width": self.prep_width,
+            "perm_width": self.perm_width, "num_public_values": self.num_public_values,
+            "num_challenges": self.num_challenges, "nodes": [list(n) for n in self.nodes],
+            "constraints": self.constraints})
+
+    @classmethod
+    def from_json(cls, text):
+        d = json.loads(text)
+        a = cls(d["name"], d["main_width"], d["prep_width"], d["perm_width"], d["num_public_values"],
+                d.get("num_challenges", 2))
+        for n in d["nodes"]:
+            n = tuple(n)
+            if n[0] in ("add", "sub", "mul"):
+                ty = "e" if "e" in (a.types[n[1]], a.types[n[2]]) else "b"
+            elif n[0] == "neg":
+                ty = a.types[n[1]]
+            else:
+                ty = "e" if n[0] in ("perm", "lcs", "chal") else "b"
+            a.nodes.append(n)
+            a.types.append(ty)
+        a.constraints = list(d["constraints"])
+        return a
+
+    @property
+    def num_constraints(self):
+        return len(self.constraints)
+
+    def max_degree(self):
+        """Degree of the constraints in the trace polynomials (selectors count 1), as
+        crates/stark/src/chip.rs:81-87 computes it for log_quotient_degree."""
+        deg = []
+        for n in self.nodes:
+            k = n[0]
+            if k in ("prep", "main", "perm", "first", "last", "trans"):
+                deg.append(1)
+            elif k in ("add", "sub"):
+                deg.append(max(deg[n[1]], deg[n[2]]))
+            elif k == "mul":
+                deg.append(deg[n[1]] + deg[n[2]])
+            elif k == "neg":
+                deg.append(deg[n[1]])
+            else:
+                deg.append(0)
+        return max([deg[c] for c in self.constraints] or [0])
+
+
+class _Rows:
+    def __init__(self, air, kind, width):
+        self.air, self.kind, self.width = air, kind, width
+
+    def row_slice(self, r):
+        return [self.air.leaf(self.kind, r, c) for c in range(self.width)]
+
+    def local(self):
+        return self.row_slice(0)
+
+    def next(self):
+        return self.row_slice(1)
+
+
+class AirBuilder:
+    def __init__(self, air, cond=None):
+        self.air, self.cond = air, cond
+
+    # --- inputs
+    def main(self):
+        return _Rows(self.air, "main", self.air.main_width)
+
+    def preprocessed(self):
+        return _Rows(self.air, "prep", self.air.prep_width)
+
+    def permutation(self):
+        return _Rows(self.air, "perm", self.air.perm_width)
+
+    def permutation_randomness(self):
+        return [self.air.leaf("chal", k) for k in range(self.air.num_challenges)]
+
+    def public_values(self):
+        return [self.air.leaf("pv", k) for k in range(self.air.num_public_values)]
+
+    def local_cumulative_sum(self):
+        return self.air.leaf("lcs")
+
+    def global_cumulative_sum(self):
+        return [self.air.leaf("gcs", k) for k in range(14)]
+
+    def is_first_row(self):
+        return self.air.leaf("first")
+
+    def is_last_row(self):
+        return self.air.leaf("last")
+
+    def is_transition(self):
+        return self.air.leaf("trans")
+
+    def const(self, v):
+        return self.air.const(v)
+
+    # --- filtered builders
+    def when(self, cond):
+        c = cond if self.cond is None else self.cond * cond
+        return AirBuilder(self.air, c)
+
+    def when_first_row(self):
+        return self.when(self.is_first_row())
+
+    def when_last_row(self):
+        return self.when(self.is_last_row())
+
+    def when_transition(self):
+        return self.when(self.is_transition())
+
+    # --- constraints
+    def _lift(self, x):
+        return x if isinstance(x, Expr) else self.air.const(int(x))
+
+    def assert_zero(self, x):
+        x = self._lift(x)
+        if self.cond is not None:
+            x = self.cond * x
+        self.air.constraints.append(x.id)
+
+    def assert_eq(self, a, b):
+        self.assert_zero(self._lift(a) - self._lift(b))
+
+    def assert_one(self, x):
+        self.assert_zero(self._lift(x) - 1)
+
+    def assert_bool(self, x):
+        x = self._lift(x)
+        self.assert_zero(x * (x - 1))
+
+    assert_zero_ext = assert_zero
+    assert_eq_ext = assert_eq

@@ -53,6 +53,11 @@ PROTOTYPES = {
     "zk_pdata_copy_lde": (i32, [vp, u32, u32p]),
     "zk_pdata_copy_layer": (i32, [vp, u32, u32p]),
     "zk_pdata_open_batch": (i32, [vp, u32, u64p, u32p, u32p]),
+    "zk_air_count": (i32, []),
+    "zk_air_name": (C.c_char_p, [i32]),
+    "zk_air_find": (i32, [C.c_char_p]),
+    "zk_air_info": (i32, [i32, vp]),
+    "zk_quotient": (i32, [vp, i32, vp, u32, vp, u32, vp, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p, u64p]),
     "zk_challenger_init": (i32, [vp]),
     "zk_challenger_observe": (i32, [vp, vp, u32p, u32]),
     "zk_challenger_sample_ext": (i32, [vp, vp, u32, u32p]),
@@ -286,6 +291,31 @@ class Ctx:
                                             heights.ctypes.data_as(u64p), _p32(widths), _p32(shifts),
                                             log_blowup, _p32(root), C.byref(pd)))
         return root, PData(self, pd, root)
+
+    def quotient(self, air_name, main, log_degree, log_quotient_degree, alpha, prep=None, perm=None,
+                 perm_challenges=None, public_values=(), local_cumsum=None, global_cumsum=None):
+        """quotient_values for one chip.  main / prep / perm are (PData, matrix index) pairs.  Returns the device
+        pointer of the chunk matrices (2^lqd matrices of 2^log_degree x 4)."""
+        aid = self.d.zk_air_find(air_name.encode())
+        if aid < 0:
+            raise ZkError(f"unknown AIR {air_name}")
+        pv = _arr(public_values, np.uint32)
+        al = _arr(alpha, np.uint32)
+        ch = _arr(perm_challenges, np.uint32).reshape(-1) if perm_challenges is not None else None
+        lc = _arr(local_cumsum, np.uint32) if local_cumsum is not None else None
+        gc = _arr(global_cumsum, np.uint32) if global_cumsum is not None else None
+        out = u64()
+        self.lib.check(self.d.zk_quotient(
+            self.h, aid, prep[0].h if prep else None, prep[1] if prep else 0, main[0].h, main[1],
+            perm[0].h if perm else None, perm[1] if perm else 0, log_degree, log_quotient_degree, _p32(al),
+            _p32(ch) if ch is not None else None, _p32(pv) if pv.size else None, pv.size,
+            _p32(lc) if lc is not None else None, _p32(gc) if gc is not None else None, C.byref(out)))
+        return out.value
+
+    def download(self, dptr, shape):
+        out = np.empty(shape, np.uint32)
+        self.d2h(out, dptr)
+        return out
 
     def mmcs_commit(self, mats):
         ms = [_arr(m, np.uint32) for m in mats]
