@@ -74,9 +74,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def count_between(self, t0, t1):
+        return sum(1 for t, _ in self.lines if t0 <= t <= t1)
+
+    def stop(self, windows):
+        """windows: list of (t0, t1) host-clock intervals during which the GPU was under the benchmark load."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +91,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if not any(a <= t <= b for a, b in windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -238,23 +244,35 @@ def main():
             ms = float(t.item())
         return ms / steps, root
 
-    for _ in range(args.warmup):
-        root_dev = step_dev()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        root_dev = step_dev()
     ctx.prof_reset()
     ctx.prof_enable(True)
     l0 = ctx.launch_count()
+    windows = []
+    t0 = time.time()
     ms_dev, root_dev = timed(step_dev, args.steps)
+    windows.append((t0, time.time()))
     launches = ctx.launch_count() - l0
     ctx.prof_enable(False)
     recs = ctx.prof_records()
-    clocks = sampler.stop()
 
     for _ in range(2):
         root_host = step_host()
+    t0 = time.time()
     ms_host, root_host = timed(step_host, args.steps)
+    windows.append((t0, time.time()))
     assert (root_dev == root_host).all(), "device-resident and host-buffer commits disagree"
+    if sum(sampler.count_between(a, b) for a, b in windows) < 5:
+        # short runs: keep the same load going (untimed) until nvidia-smi has sampled it a few times
+        t0 = time.time()
+        while time.time() - t0 < 1.5:
+            step_dev()
+        torch.cuda.synchronize()
+        windows.append((t0, time.time()))
+    clocks = sampler.stop(windows)
 
     # per-stage device time (CUDA events recorded by the library on the same stream)
     stage = {}
