@@ -164,3 +164,22 @@ def test_bad_arguments(be):
         ctx.commit([np.zeros((3, 4), np.uint32)], [one], 1)  # height not a power of two
     with pytest.raises(ZkError):
         ctx.commit([np.zeros((4, 4), np.uint32)], [0], 1)  # zero shift
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_streaming_commit_multi_slab(be, monkeypatch):
+    """zk_commit streams column slabs (H2D || LDE || resumable sponge).  Force many small slabs and compare
+    with the oracle: solo tallest matrix (streamed leaves), ragged last slab, and a mixed batch."""
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_SLAB_COLS", "16")
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+    try:
+        _check_commit(ctx, [_mont(64, 40, seed=31)], [one], 1)          # slabs 16,16,8, leaves streamed
+        _check_commit(ctx, [_mont(32, 24, seed=32)], [one], 2)
+        _check_commit(ctx, [_mont(64, 35, seed=33)], [one], 1)          # width not a multiple of 8: LDE streamed only
+        _check_commit(ctx, [_mont(64, 48, seed=34), _mont(16, 20, seed=35), _mont(64, 3, seed=36)], [one] * 3, 1)
+    finally:
+        ctx.destroy()

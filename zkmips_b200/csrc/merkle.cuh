@@ -52,6 +52,43 @@ __global__ void __launch_bounds__(256) hash_rows_w8(const uint32_t* __restrict__
   store_digest(out + r * 8, s);
 }
 
+// Resumable leaf sponge for the streaming commit: absorbs columns [c0, c0 + 8*nchunk) of every row.  The full
+// 16-word sponge state of row r lives in state[k*h + r], k < 4 (coalesced uint4 per thread) between slabs.
+__global__ void __launch_bounds__(256) hash_rows_slab(const uint32_t* __restrict__ mat, uint32_t pitch, uint32_t c0,
+                                                      uint32_t nchunk, uint64_t h, uint4* __restrict__ state, int first,
+                                                      int last, uint32_t* __restrict__ out) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  const uint4* row = reinterpret_cast<const uint4*>(mat + r * pitch + c0);
+  uint32_t s[16];
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = 0;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint4 v = state[k * h + r];
+      s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
+    }
+  }
+  uint4 a = __ldg(row), b = __ldg(row + 1);
+  for (uint32_t c = 0; c < nchunk; c++) {
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if (c + 1 < nchunk) {
+      a = __ldg(row + 2 * (c + 1));
+      b = __ldg(row + 2 * (c + 1) + 1);
+    }
+    p2::permute(s);
+  }
+  if (last) {
+    store_digest(out + r * 8, s);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) state[k * h + r] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+  }
+}
+
 // General case: the row is the concatenation of the rows of several matrices of any widths.
 __global__ void __launch_bounds__(256) hash_rows_multi(const MatDesc* __restrict__ gm, uint32_t gn, uint64_t h,
                                                        uint32_t* __restrict__ out) {

@@ -43,7 +43,9 @@ struct PassArgs {
   uint32_t* dst;
   const uint32_t* tw;     // tw[e] = g_L^(+-e) for this direction, e < 2^(L-1)
   const uint32_t* scale;  // optional: element of natural row j is multiplied by scale[j] on load
-  uint32_t w;             // columns = row pitch in words
+  uint32_t ws, wd;        // row pitch (words) of src / dst
+  uint32_t c0s, c0d;      // first column inside src / dst
+  uint32_t nc;            // number of columns transformed
   uint32_t log_n;         // transform size
   uint32_t s0;            // stages done by earlier passes
   uint32_t log_L;         // size of the twiddle table's group
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_sme
   uint32_t* stw = sm + (ROWS + ROWS / 32) * C;
 
   const uint32_t cc = threadIdx.x & (C - 1), tau = threadIdx.x >> 4;
-  const uint32_t ncg = (A.w + C - 1) / C;
+  const uint32_t ncg = (A.nc + C - 1) / C;
   const uint32_t cg = blockIdx.x % ncg, tile = blockIdx.x / ncg;
   const uint32_t n = A.log_n, rem = n - A.s0 - K;
   const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
   const uint32_t col = cg * C + cc;
-  const bool ok = col < A.w;
+  const bool ok = col < A.nc;
   const uint32_t jbase = (hi << (n - A.s0)) + lo;
 
   for (uint32_t e = threadIdx.x; e < ROWS; e += NT) stw[e] = root_pow(A.tw, A.log_L, K, e);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_sme
     uint32_t i = ((uint32_t)q << B) + tau;
     uint32_t j = jbase + (i << rem);
     uint32_t srow = A.src_bitrev ? (__brev(j) >> (32 - n)) : j;
-    uint32_t x = ok ? __ldg(A.src + (size_t)srow * A.w + col) : 0u;
+    uint32_t x = ok ? __ldg(A.src + (size_t)srow * A.ws + A.c0s + col) : 0u;
     if (A.scale) x = kb::mul(x, __ldg(A.scale + j));
     v[q] = x;
   }
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_sme
       uint32_t E = (lo << A.s0) * (__brev(i) >> (32 - K));
       x = kb::mul(x, root_pow(A.tw, A.log_L, n, E));
     }
-    if (ok) A.dst[(size_t)(jbase + (i << rem)) * A.w + col] = x;
+    if (ok) A.dst[(size_t)(jbase + (i << rem)) * A.wd + A.c0d + col] = x;
   }
 }
 
@@ -152,8 +154,8 @@ template <int K, int DIR>
 __global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /* tiles * w */) {
   uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const uint32_t col = (uint32_t)(gid % A.w);
-  const uint32_t tile = (uint32_t)(gid / A.w);
+  const uint32_t col = (uint32_t)(gid % A.nc);
+  const uint32_t tile = (uint32_t)(gid / A.nc);
   const uint32_t n = A.log_n, rem = n - A.s0 - K;
   const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
   const uint32_t jbase = (hi << (n - A.s0)) + lo;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /
   for (int i = 0; i < R; i++) {
     uint32_t j = jbase + ((uint32_t)i << rem);
     uint32_t srow = (A.src_bitrev && n > 0) ? (__brev(j) >> (32 - n)) : j;
-    uint32_t x = __ldg(A.src + (size_t)srow * A.w + col);
+    uint32_t x = __ldg(A.src + (size_t)srow * A.ws + A.c0s + col);
     if (A.scale) x = kb::mul(x, __ldg(A.scale + j));
     v[i] = x;
   }
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /
       uint32_t E = (lo << A.s0) * (__brev((uint32_t)i) >> (32 - (K > 0 ? K : 1)));
       x = kb::mul(x, root_pow(A.tw, A.log_L, n, E));
     }
-    A.dst[(size_t)(jbase + ((uint32_t)i << rem)) * A.w + col] = x;
+    A.dst[(size_t)(jbase + ((uint32_t)i << rem)) * A.wd + A.c0d + col] = x;
   }
 }
 
@@ -190,7 +192,7 @@ inline cudaError_t launch_smem(const PassArgs& A, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  uint32_t ncg = (A.w + TILE_COLS - 1) / TILE_COLS;
+  uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
   uint64_t tiles = 1ull << (A.log_n - (5 + B));
   uint64_t blocks = tiles * ncg;
   auto kfn = ntt_pass_smem<B, DIR>;
@@ -199,7 +201,7 @@ inline cudaError_t launch_smem(const PassArgs& A, cudaStream_t st) {
 }
 template <int K, int DIR>
 inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
-  uint64_t total = (uint64_t)A.w << (A.log_n - K);
+  uint64_t total = (uint64_t)A.nc << (A.log_n - K);
   unsigned blocks = (unsigned)((total + 255) / 256);
   auto kfn = ntt_pass_reg<K, DIR>;
   ZK_LAUNCH(kfn, blocks, 256, 0, st, A, total);
@@ -224,24 +226,32 @@ inline cudaError_t launch_pass(const PassArgs& A, uint32_t k, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-// Full transform of every column of an (2^log_n x w) matrix: natural-order rows in (optionally
-// gathered through a bit reversal and scaled), bit-reversed rows out.  dst may equal src only when
-// src_bitrev == 0.
-inline cudaError_t transform(const uint32_t* src, uint32_t* dst, uint32_t log_n, uint32_t w, int dir,
-                             const uint32_t* tw, uint32_t log_L, const uint32_t* scale, bool src_bitrev,
-                             cudaStream_t st) {
-  if (w == 0) return cudaSuccess;
+// A column range of a row-major matrix: `nc` columns starting at column c0 of rows of pitch w words.
+struct Cols {
+  uint32_t* ptr;
+  uint32_t w, c0;
+};
+
+// Full transform of `nc` columns of a 2^log_n-row matrix: natural-order rows in (optionally gathered
+// through a bit reversal and scaled), bit-reversed rows out.  dst may alias src only when src_bitrev == 0.
+inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, int dir, const uint32_t* tw,
+                             uint32_t log_L, const uint32_t* scale, bool src_bitrev, cudaStream_t st) {
+  if (nc == 0) return cudaSuccess;
   uint32_t npass = log_n == 0 ? 1 : (log_n + 9) / 10;
   uint32_t k0 = log_n - 10 * (npass - 1);
   uint32_t s0 = 0;
   for (uint32_t p = 0; p < npass; p++) {
     uint32_t k = p == 0 ? k0 : 10;
     PassArgs A;
-    A.src = p == 0 ? src : dst;
-    A.dst = dst;
+    A.src = p == 0 ? src.ptr : dst.ptr;
+    A.ws = p == 0 ? src.w : dst.w;
+    A.c0s = p == 0 ? src.c0 : dst.c0;
+    A.dst = dst.ptr;
+    A.wd = dst.w;
+    A.c0d = dst.c0;
+    A.nc = nc;
     A.tw = tw;
     A.scale = p == 0 ? scale : nullptr;
-    A.w = w;
     A.log_n = log_n;
     A.s0 = s0;
     A.log_L = log_L;

@@ -63,6 +63,12 @@ static int32_t ctx_init(zk_ctx* c) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("ZK_SLAB_COLS")) {
+    int v = atoi(e);
+    if (v >= 16 && v % 16 == 0) c->slab_cols = (uint32_t)v;
+  }
+  if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, c->device));
   uint64_t thr = UINT64_MAX;
@@ -118,6 +124,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -234,35 +241,129 @@ static inline uint32_t num_passes(uint32_t log_n) { return log_n == 0 ? 1 : (log
 // coset_lde_batch(in, log_blowup, shift).bit_reverse_rows()  (SURVEY A.7).
 // Block t of the output (rows [t*h, (t+1)*h)) is the size-h DFT, bit-reversed, of the coefficients
 // scaled by (shift * g_{n+b}^bitrev_b(t))^i: 2^b independent coset transforms, no zero padding.
-int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                uint32_t* out) {
+
+// scale vectors sigma_t^i / h of the 2^b coset blocks (shared by every column of a matrix)
+static int32_t lde_scales(zk_ctx* c, uint64_t h, uint32_t log_blowup, uint32_t shift, std::vector<uint32_t*>& out) {
+  uint32_t n = kbh::log2_exact(h);
+  uint32_t gnb = kbh::two_adic_generator(n + log_blowup);
+  uint32_t hinv = kbh::inv(kbh::to_monty((uint32_t)(h % kbh::P)));
+  out.assign(1u << log_blowup, nullptr);
+  for (uint32_t t = 0; t < (1u << log_blowup); t++) {
+    int32_t rc = dev_alloc(c, h * 4ull, (void**)&out[t]);
+    if (rc) return rc;
+    uint32_t sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
+    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, out[t], h, sigma, hinv);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  return ZK_OK;
+}
+
+static int32_t check_lde_shape(zk_ctx* c, uint64_t h, uint32_t log_blowup) {
   if (h == 0 || (h & (h - 1))) return zk_fail(ZK_ERR_ARG, "height must be a power of two");
   uint32_t n = kbh::log2_exact(h);
   if (n > c->log_L) return zk_fail(ZK_ERR_ARG, "trace height above 2^22 is not supported");
   if (n + log_blowup > kbh::TWO_ADICITY) return zk_fail(ZK_ERR_ARG, "LDE height exceeds the two-adicity of the field");
-  if (w == 0) return ZK_OK;
-  uint32_t *coef = nullptr, *scale = nullptr;
-  int32_t rc;
-  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&coef))) return rc;
-  if ((rc = dev_alloc(c, h * 4ull, (void**)&scale))) return rc;
+  return ZK_OK;
+}
+
+// LDE of `nc` columns.  `coef` receives the (bit-reversed, unscaled) coefficients and may alias `in` (the
+// inverse transform then runs in place); the 2^b blocks go to out.ptr + t*h*out.w, columns [out.c0, out.c0+nc).
+static int32_t lde_cols(zk_ctx* c, ntt::Cols in, ntt::Cols coef, ntt::Cols out, uint32_t nc, uint64_t h,
+                        uint32_t log_blowup, const std::vector<uint32_t*>& scales) {
+  if (nc == 0) return ZK_OK;
+  uint32_t n = kbh::log2_exact(h);
   {
     ProfScope ps(c, "idft");
-    CK(ntt::transform(in, coef, n, w, ntt::DIR_INV, c->tw[1], c->log_L, nullptr, false, c->stream));
+    CK(ntt::transform(in, coef, nc, n, ntt::DIR_INV, c->tw[1], c->log_L, nullptr, false, c->stream));
     c->launches += num_passes(n);
   }
-  uint32_t gnb = kbh::two_adic_generator(n + log_blowup);
-  uint32_t hinv = kbh::inv(kbh::to_monty((uint32_t)(h % kbh::P)));
   for (uint32_t t = 0; t < (1u << log_blowup); t++) {
     ProfScope ps(c, "coset_dft");
-    uint32_t sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
-    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, scale, h, sigma, hinv);
-    CK(cudaGetLastError());
-    CK(ntt::transform(coef, out + (size_t)t * h * w, n, w, ntt::DIR_FWD, c->tw[0], c->log_L, scale, true, c->stream));
-    c->launches += 1 + num_passes(n);
+    ntt::Cols blk{out.ptr + (size_t)t * h * out.w, out.w, out.c0};
+    CK(ntt::transform(coef, blk, nc, n, ntt::DIR_FWD, c->tw[0], c->log_L, scales[t], true, c->stream));
+    c->launches += num_passes(n);
   }
-  if ((rc = dev_free(c, coef))) return rc;
-  if ((rc = dev_free(c, scale))) return rc;
   return ZK_OK;
+}
+
+int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                uint32_t* out) {
+  int32_t rc = check_lde_shape(c, h, log_blowup);
+  if (rc) return rc;
+  if (w == 0) return ZK_OK;
+  uint32_t* coef = nullptr;
+  std::vector<uint32_t*> scales;
+  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&coef))) return rc;
+  if ((rc = lde_scales(c, h, log_blowup, shift, scales))) return rc;
+  rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, w, 0}, ntt::Cols{out, w, 0}, w, h, log_blowup,
+                scales);
+  for (auto p : scales) dev_free(c, p);
+  dev_free(c, coef);
+  return rc;
+}
+
+// Streaming LDE of a HOST matrix: column slabs flow  H2D (copy stream)  ||  inverse + coset transforms  ||
+// resumable leaf sponge (compute stream), double buffered.  The slab buffer doubles as the coefficient
+// buffer (in-place inverse transform), so no full-size staging copy of the trace exists on the device.
+// When `leaves` is non-null the rows of the LDE are hashed slab by slab (w must be a multiple of 8).
+static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                               uint32_t* out, uint32_t* leaves) {
+  int32_t rc = check_lde_shape(c, h, log_blowup);
+  if (rc) return rc;
+  if (w == 0) return ZK_OK;
+  if (!host) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
+  const uint64_t H = h << log_blowup;
+  uint32_t slab = c->slab_cols;
+  if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
+  const uint32_t nslab = (w + slab - 1) / slab;
+  std::vector<uint32_t*> scales;
+  if ((rc = lde_scales(c, h, log_blowup, shift, scales))) return rc;
+  uint32_t* buf[2] = {nullptr, nullptr};
+  uint4* state = nullptr;
+  const uint32_t nbuf = nslab > 1 ? 2 : 1;
+  for (uint32_t b = 0; b < nbuf; b++)
+    if ((rc = dev_alloc(c, h * (uint64_t)slab * 4, (void**)&buf[b]))) return rc;
+  if (leaves && nslab > 1 && (rc = dev_alloc(c, H * 64, (void**)&state))) return rc;
+  cudaEvent_t up_done[2], buf_free[2], ready;
+  for (int b = 0; b < 2; b++) {
+    CK(cudaEventCreateWithFlags(&up_done[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&buf_free[b], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  CK(cudaEventRecord(ready, c->stream));  // allocations above are ordered on the compute stream
+  CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+  for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
+    const uint32_t b = k & 1, c0 = k * slab, nc = std::min(slab, w - c0);
+    if (k >= 2) CK(cudaStreamWaitEvent(c->copy_stream, buf_free[b], 0));
+    {
+      ProfScope ps(c, "h2d_enqueue");
+      CK(cudaMemcpy2DAsync(buf[b], (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+                           c->copy_stream));
+    }
+    CK(cudaEventRecord(up_done[b], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, up_done[b], 0));
+    ntt::Cols sl{buf[b], nc, 0};
+    rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
+    if (rc) break;
+    CK(cudaEventRecord(buf_free[b], c->stream));
+    if (leaves) {
+      ProfScope ps(c, "leaf_hash");
+      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + 255) / 256), 256, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
+                (int)(k + 1 == nslab), leaves);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  for (int b = 0; b < 2; b++) {
+    cudaEventDestroy(up_done[b]);
+    cudaEventDestroy(buf_free[b]);
+  }
+  cudaEventDestroy(ready);
+  for (auto p : scales) dev_free(c, p);
+  for (uint32_t b = 0; b < nbuf; b++) dev_free(c, buf[b]);
+  if (state) dev_free(c, state);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +388,9 @@ static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t
 }
 
 // Builds the digest layers over pd->mats (already on the device) and fills root.
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root) {
+// Layer geometry + digest buffer; separate from mmcs_build so that the streaming commit can hash leaves
+// while the LDE is still being produced.
+int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd) {
   uint32_t n = pd->n;
   pd->order.resize(n);
   for (uint32_t i = 0; i < n; i++) pd->order[i] = i;
@@ -301,8 +404,14 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root) {
     pd->layer_off[l] = words;
     words += (hmax >> l) * 8;
   }
+  return dev_alloc(c, words * 4, (void**)&pd->digests);
+}
+
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done) {
+  uint32_t n = pd->n;
   int32_t rc;
-  if ((rc = dev_alloc(c, words * 4, (void**)&pd->digests))) return rc;
+  if (!pd->digests && (rc = mmcs_alloc(c, pd))) return rc;
+  uint64_t hmax = pd->heights[pd->order[0]];
   uint32_t* inj = nullptr;
   uint32_t next = 0;
   auto take_group = [&](uint64_t height, std::vector<mk::MatDesc>& g) {
@@ -316,7 +425,7 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root) {
   {
     ProfScope ps(c, "leaf_hash");
     take_group(hmax, g);
-    if ((rc = hash_group(c, g, hmax, pd->digests))) return rc;
+    if (!leaves_done && (rc = hash_group(c, g, hmax, pd->digests))) return rc;
   }
   {
     ProfScope ps(c, "tree");
@@ -393,10 +502,11 @@ void pdata_release(zk_pdata* pd) {
   delete pd;
 }
 
-// common tail of the four commit entry points.  `src[i]` are DEVICE pointers to the input matrices.
-static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* src, const uint64_t* heights,
-                             const uint32_t* widths, const uint32_t* domain_shifts, bool do_lde, uint32_t log_blowup,
-                             uint32_t root[8], zk_pdata** out) {
+// common tail of the four commit entry points.  `src[i]` are DEVICE pointers to the input matrices, or HOST
+// pointers when src_is_host (LDE case only: the streaming commit uploads them slab by slab).
+static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* src, bool src_is_host,
+                             const uint64_t* heights, const uint32_t* widths, const uint32_t* domain_shifts, bool do_lde,
+                             uint32_t log_blowup, uint32_t root[8], zk_pdata** out) {
   zk_pdata* pd = new zk_pdata();
   pd->ctx = c;
   pd->n = n_mats;
@@ -405,24 +515,41 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
   pd->mats.assign(n_mats, nullptr);
   pd->owned.assign(n_mats, false);
   int32_t rc = ZK_OK;
-  for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
-    if (do_lde) {
+  bool leaves_done = false;
+  if (do_lde) {
+    uint64_t hmax = 0;
+    for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
       pd->heights[i] = heights[i] << log_blowup;
+      hmax = std::max(hmax, pd->heights[i]);
       pd->owned[i] = true;
       rc = dev_alloc(c, pd->heights[i] * widths[i] * 4ull, (void**)&pd->mats[i]);
-      if (rc) break;
-      if (domain_shifts[i] == 0) {
-        rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
-        break;
+      if (rc == ZK_OK && domain_shifts[i] == 0) rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
+    }
+    if (rc == ZK_OK) rc = mmcs_alloc(c, pd);
+    // the leaf sponge can be streamed with the LDE when one matrix alone forms the tallest class
+    int solo = -1, ntall = 0;
+    for (uint32_t i = 0; i < n_mats; i++)
+      if (pd->heights[i] == hmax) {
+        ntall++;
+        solo = (int)i;
       }
+    if (!(src_is_host && ntall == 1 && widths[solo] > 0 && widths[solo] % 8 == 0 && c->slab_cols % 8 == 0)) solo = -1;
+    for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
       uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
-      rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
-    } else {
+      if (src_is_host)
+        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i],
+                             (int)i == solo ? pd->digests : nullptr);
+      else
+        rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
+    }
+    leaves_done = solo >= 0;
+  } else {
+    for (uint32_t i = 0; i < n_mats; i++) {
       pd->heights[i] = heights[i];
       pd->mats[i] = const_cast<uint32_t*>(src[i]);
     }
   }
-  if (rc == ZK_OK) rc = mmcs_build(c, pd);
+  if (rc == ZK_OK) rc = mmcs_build(c, pd, true, leaves_done);
   if (rc != ZK_OK) {
     pdata_release(pd);
     return rc;
@@ -457,11 +584,9 @@ extern "C" int32_t zk_commit(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
   if (rc) return rc;
   std::lock_guard<std::mutex> g(c->mu);
   CK(cudaSetDevice(c->device));
-  std::vector<uint32_t*> dev;
-  rc = upload_all(c, n_mats, mats_host, heights, widths, dev);
-  if (rc == ZK_OK) rc = commit_common(c, n_mats, dev.data(), heights, widths, domain_shifts, true, log_blowup, root, out);
-  for (auto p : dev) dev_free(c, p);
-  return rc;
+  for (uint32_t i = 0; i < n_mats; i++)
+    if (!mats_host[i] && heights[i] * widths[i]) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
+  return commit_common(c, n_mats, mats_host, true, heights, widths, domain_shifts, true, log_blowup, root, out);
 }
 extern "C" int32_t zk_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
                                  const uint32_t* widths, const uint32_t* domain_shifts, uint32_t log_blowup,
@@ -473,7 +598,7 @@ extern "C" int32_t zk_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr* mats
   CK(cudaSetDevice(c->device));
   std::vector<const uint32_t*> src(n_mats);
   for (uint32_t i = 0; i < n_mats; i++) src[i] = (const uint32_t*)mats_dev[i];
-  return commit_common(c, n_mats, src.data(), heights, widths, domain_shifts, true, log_blowup, root, out);
+  return commit_common(c, n_mats, src.data(), false, heights, widths, domain_shifts, true, log_blowup, root, out);
 }
 extern "C" int32_t zk_mmcs_commit(zk_ctx* c, uint32_t n_mats, const uint32_t* const* mats_host, const uint64_t* heights,
                                   const uint32_t* widths, uint32_t root[8], zk_pdata** out) {
@@ -484,7 +609,7 @@ extern "C" int32_t zk_mmcs_commit(zk_ctx* c, uint32_t n_mats, const uint32_t* co
   CK(cudaSetDevice(c->device));
   std::vector<uint32_t*> dev;
   rc = upload_all(c, n_mats, mats_host, heights, widths, dev);
-  if (rc == ZK_OK) rc = commit_common(c, n_mats, dev.data(), heights, widths, nullptr, false, 0, root, out);
+  if (rc == ZK_OK) rc = commit_common(c, n_mats, dev.data(), false, heights, widths, nullptr, false, 0, root, out);
   if (rc == ZK_OK) {
     for (uint32_t i = 0; i < n_mats; i++) (*out)->owned[i] = true;  // the uploads now belong to the pdata
   } else {
@@ -501,7 +626,7 @@ extern "C" int32_t zk_mmcs_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr*
   CK(cudaSetDevice(c->device));
   std::vector<const uint32_t*> src(n_mats);
   for (uint32_t i = 0; i < n_mats; i++) src[i] = (const uint32_t*)mats_dev[i];
-  return commit_common(c, n_mats, src.data(), heights, widths, nullptr, false, 0, root, out);
+  return commit_common(c, n_mats, src.data(), false, heights, widths, nullptr, false, 0, root, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -676,7 +801,7 @@ extern "C" int32_t zk_dft_batch(zk_ctx* c, const uint32_t* in, uint64_t h, uint3
   if ((rc = dev_alloc(c, bytes, (void**)&d))) return rc;
   if ((rc = dev_alloc(c, bytes, (void**)&o))) return rc;
   CK(cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(ntt::transform(d, d, n, w, ntt::DIR_FWD, c->tw[0], c->log_L, nullptr, false, c->stream));
+  CK(ntt::transform(ntt::Cols{d, w, 0}, ntt::Cols{d, w, 0}, w, n, ntt::DIR_FWD, c->tw[0], c->log_L, nullptr, false, c->stream));
   uint64_t total = h * w;
   ZK_LAUNCH(bitrev_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, c->stream, d, o, n, w, total);
   CK(cudaGetLastError());

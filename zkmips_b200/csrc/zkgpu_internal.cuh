@@ -27,6 +27,9 @@ struct zk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
+  uint32_t slab_cols = 64;              // columns per slab of the streaming commit (multiple of 16; env ZK_SLAB_COLS)
+  uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
   uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
@@ -75,7 +78,8 @@ int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out);
 int32_t dev_free(zk_ctx* c, void* p);
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
                 uint32_t* out);
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true);
+int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd);
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true, bool leaves_done = false);
 // Mmcs::commit of one device-resident matrix; with fetch_root == false nothing is copied to the host and the
 // stream is not synchronised (the root stays at pdata_root_dev()).
 int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
