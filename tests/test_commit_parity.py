@@ -58,7 +58,7 @@ GPU_LOGS = EMU_LOGS + [13, 14, 15, 16, 17, 20, 21]
 def _dft_cases():
     out = []
     for n in GPU_LOGS:
-        w = 3 if n >= 9 else 20
+        w = (3 if n % 2 else 4) if n >= 9 else 20
         marks = [] if n in EMU_LOGS else [pytest.mark.gpu]
         out.append(pytest.param("emu", n, w, id=f"emu-2^{n}x{w}", marks=marks + ([pytest.mark.skip("gpu only size")] if n not in EMU_LOGS else [])))
         out.append(pytest.param("gpu", n, w, id=f"gpu-2^{n}x{w}", marks=[pytest.mark.gpu]))
@@ -183,3 +183,12 @@ def test_streaming_commit_multi_slab(be, monkeypatch):
         _check_commit(ctx, [_mont(64, 48, seed=34), _mont(16, 20, seed=35), _mont(64, 3, seed=36)], [one] * 3, 1)
     finally:
         ctx.destroy()
+
+
+def test_lde_two_pass_k10_emu():
+    """2^20 rows x 2 columns: both k=10 passes of the second-generation kernel (coset scale + bit-reversed
+    gather fused in the first, pass twiddles) on the emulator; the GPU twins are the 2^20 cases above."""
+    ctx = backends.emu()
+    m = _mont(1 << 20, 2, seed=77)
+    shift = ob.lib().ork_to_monty(3)
+    assert (ctx.coset_lde(m, 1, shift) == ob.coset_lde(m, 1, shift)).all()

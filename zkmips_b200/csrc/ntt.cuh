@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include "kb31.cuh"
+#include "kb31_host.h"
 #include "launch.cuh"
 
 namespace ntt {
@@ -149,6 +150,159 @@ __global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_sme
   }
 }
 
+// ---- pass with k = 10 stages, second generation ------------------------------------------------
+// Same tile and data flow as ntt_pass_smem<5> with the instruction count per element roughly halved:
+//   * two adjacent columns per thread (64-bit global and shared accesses, twiddles shared by both);
+//   * butterfly twiddles are compile-time constants multiplied with Shoup's method
+//     (x*w mod p = x*w - floor(x*w'/2^32)*p, w' = floor(w*2^32/p): IMAD.HI + 2 IMAD + VIADDMNMX, no
+//     Montgomery correction because the constant is kept in plain form);
+//   * the pass twiddle g_n^(base*bitrev_10(i)) is split as g^(base*bitrev_5(i>>5)) * g^(32*base*bitrev_5(i&31)):
+//     the first factor, the inner twiddle w_1024^(tau*kappa) and the coset scale sigma^(lo + tau*2^rem)/h are
+//     merged into ONE per-CTA shared-memory table F[tau][kappa]; the second factor is a 32-entry table G;
+//     the remaining coset factor sigma^(q*32*2^rem) comes from the kernel arguments (constant bank).
+//   No per-element global twiddle or scale loads remain.  Requires even pitches, offsets and column count.
+struct Tw32 {
+  uint32_t w[2][16];   // plain (non-Montgomery) w_32^(+-e)
+  uint32_t ws[2][16];  // floor(w * 2^32 / p)
+};
+constexpr Tw32 make_tw32() {
+  Tw32 t{};
+  uint32_t g5 = kbh::two_adic_generator(5);
+  uint32_t g[2] = {g5, kbh::inv(g5)};
+  for (int d = 0; d < 2; d++)
+    for (int e = 0; e < 16; e++) {
+      uint32_t w = kbh::from_monty(kbh::pow(g[d], e));
+      t.w[d][e] = w;
+      t.ws[d][e] = (uint32_t)(((uint64_t)w << 32) / kbh::P);
+    }
+  return t;
+}
+__device__ constexpr Tw32 TW32 = make_tw32();
+
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t ws) {
+  uint32_t q = __umulhi(x, ws);
+  uint32_t r = x * w - q * kb::P;  // in [0, 2p)
+  return min(r, r - kb::P);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dif32_shoup(uint32_t (&v)[32]) {
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    const int half = 16 >> t;
+#pragma unroll
+    for (int x = 0; x < 32; x++) {
+      if ((x & half) == 0) {
+        const int e = (x & (half - 1)) << t;
+        uint32_t u = v[x], z = v[x + half];
+        v[x] = kb::add(u, z);
+        if (e == 0)
+          v[x + half] = kb::sub(u, z);
+        else
+          v[x + half] = shoup_mul(u - z + kb::P, TW32.w[DIR][e], TW32.ws[DIR][e]);
+      }
+    }
+  }
+}
+
+struct Pass10Extra {
+  uint32_t dq[32];  // sigma^(q * 32 * 2^rem), Montgomery (FIRST passes only)
+  uint32_t sigma;   // coset shift of this block (Montgomery)
+  uint32_t hinv;    // 1 / n (Montgomery)
+};
+
+constexpr int P10_ROWS = 1024, P10_FSTRIDE = 33;
+constexpr size_t P10_SMEM = ((size_t)(P10_ROWS + P10_ROWS / 32) * TILE_COLS + 32 * P10_FSTRIDE + 96) * 4;
+
+template <int DIR, bool FIRST, bool PASSTW>
+__global__ void __launch_bounds__(256, 2) ntt_pass10(PassArgs A, Pass10Extra X) {
+  constexpr int C = TILE_COLS;
+  ZK_DYN_SMEM(sm);
+  uint32_t* sdat = sm;
+  uint32_t* F = sm + (P10_ROWS + P10_ROWS / 32) * C;
+  uint32_t* G = F + 32 * P10_FSTRIDE;
+  uint32_t* gk = G + 32;
+  uint32_t* ct = gk + 32;
+
+  const uint32_t cp = threadIdx.x & 7, tau = threadIdx.x >> 3;
+  const uint32_t ncg = (A.nc + C - 1) / C;
+  const uint32_t cg = blockIdx.x % ncg, tile = blockIdx.x / ncg;
+  const uint32_t n = A.log_n, rem = n - A.s0 - 10;
+  const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
+  const uint32_t col = cg * C + cp * 2;
+  const bool ok = col < A.nc;  // nc is even
+  const uint32_t jbase = (hi << (n - A.s0)) + lo;
+  const uint32_t base = lo << A.s0;
+
+  if (threadIdx.x < 32) {
+    gk[threadIdx.x] = PASSTW ? root_pow(A.tw, A.log_L, n, base * threadIdx.x) : kb::ONE;
+  } else if (threadIdx.x < 64) {
+    uint32_t k = threadIdx.x - 32;
+    G[k] = PASSTW ? root_pow(A.tw, A.log_L, n, (base * k) << 5) : kb::ONE;
+  } else if (threadIdx.x < 96) {
+    uint32_t t = threadIdx.x - 64;
+    ct[t] = FIRST ? kb::mul(kb::pow(X.sigma, jbase + (t << rem)), X.hinv) : kb::ONE;
+  }
+
+  uint32_t v0[32], v1[32];
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = ((uint32_t)q << 5) + tau;
+    uint32_t j = jbase + (i << rem);
+    uint32_t srow = FIRST ? (__brev(j) >> (32 - n)) : j;
+    uint2 x = make_uint2(0u, 0u);
+    if (ok) x = __ldg(reinterpret_cast<const uint2*>(A.src + (size_t)srow * A.ws + A.c0s + col));
+    if (FIRST && q > 0) {
+      x.x = kb::mul(x.x, X.dq[q]);
+      x.y = kb::mul(x.y, X.dq[q]);
+    }
+    v0[q] = x.x;
+    v1[q] = x.y;
+  }
+  __syncthreads();  // gk, ct ready
+  for (uint32_t e = threadIdx.x; e < 1024; e += 256) {
+    uint32_t t = e >> 5, k = e & 31;
+    uint32_t f = root_pow(A.tw, A.log_L, 10, t * k);
+    if (PASSTW) f = kb::mul(f, gk[k]);
+    if (FIRST) f = kb::mul(f, ct[t]);
+    F[t * P10_FSTRIDE + k] = f;
+  }
+  dif32_shoup<DIR>(v0);
+  dif32_shoup<DIR>(v1);
+  __syncthreads();  // F ready
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    if (q > 0 || FIRST || PASSTW) {
+      uint32_t f = F[tau * P10_FSTRIDE + brev5(q)];
+      v0[q] = kb::mul(v0[q], f);
+      v1[q] = kb::mul(v1[q], f);
+    }
+    uint32_t i = ((uint32_t)q << 5) + tau;
+    *reinterpret_cast<uint2*>(sdat + (i + (i >> 5)) * C + cp * 2) = make_uint2(v0[q], v1[q]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = tau * 32 + q;
+    uint2 x = *reinterpret_cast<const uint2*>(sdat + (i + (i >> 5)) * C + cp * 2);
+    v0[q] = x.x;
+    v1[q] = x.y;
+  }
+  dif32_shoup<DIR>(v0);
+  dif32_shoup<DIR>(v1);
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    uint32_t i = tau * 32 + q;
+    uint32_t a = v0[q], b = v1[q];
+    if (PASSTW && q > 0) {
+      uint32_t g = G[brev5(q)];
+      a = kb::mul(a, g);
+      b = kb::mul(b, g);
+    }
+    if (ok) *reinterpret_cast<uint2*>(A.dst + (size_t)(jbase + (i << rem)) * A.wd + A.c0d + col) = make_uint2(a, b);
+  }
+}
+
 // ---- pass with k <= 5 stages: registers only --------------------------------------------------
 template <int K, int DIR>
 __global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /* tiles * w */) {
@@ -208,6 +362,27 @@ inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int DIR, bool FIRST, bool PASSTW>
+inline cudaError_t launch_pass10(const PassArgs& A, const Pass10Extra& X, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)P10_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
+  uint64_t blocks = (1ull << (A.log_n - 10)) * ncg;
+  auto kfn = ntt_pass10<DIR, FIRST, PASSTW>;
+  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, 256, P10_SMEM, st, A, X);
+  return cudaGetLastError();
+}
+
+// the k = 10 pass can use the second-generation kernel when every access is 8-byte aligned
+inline bool pass10_ok(const PassArgs& A) {
+  return ((A.ws | A.wd | A.c0s | A.c0d | A.nc) & 1u) == 0 && ((uintptr_t)A.src % 8) == 0 && ((uintptr_t)A.dst % 8) == 0;
+}
+
 template <int DIR>
 inline cudaError_t launch_pass(const PassArgs& A, uint32_t k, cudaStream_t st) {
   switch (k) {
@@ -234,9 +409,15 @@ struct Cols {
 
 // Full transform of `nc` columns of a 2^log_n-row matrix: natural-order rows in (optionally gathered
 // through a bit reversal and scaled), bit-reversed rows out.  dst may alias src only when src_bitrev == 0.
+struct CosetScale {
+  const uint32_t* vec = nullptr;  // sigma^j / n for every natural row j (needed when the first pass is not a k=10 pass)
+  uint32_t sigma = 0, hinv = 0;   // the same as scalars (Montgomery)
+};
+
 inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, int dir, const uint32_t* tw,
-                             uint32_t log_L, const uint32_t* scale, bool src_bitrev, cudaStream_t st) {
+                             uint32_t log_L, const CosetScale* cs, bool src_bitrev, cudaStream_t st) {
   if (nc == 0) return cudaSuccess;
+  const uint32_t* scale = cs ? cs->vec : nullptr;
   uint32_t npass = log_n == 0 ? 1 : (log_n + 9) / 10;
   uint32_t k0 = log_n - 10 * (npass - 1);
   uint32_t s0 = 0;
@@ -256,7 +437,34 @@ inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, in
     A.s0 = s0;
     A.log_L = log_L;
     A.src_bitrev = (p == 0 && src_bitrev) ? 1u : 0u;
-    cudaError_t e = dir == DIR_FWD ? launch_pass<DIR_FWD>(A, k, st) : launch_pass<DIR_INV>(A, k, st);
+    cudaError_t e;
+    const bool first = p == 0 && cs != nullptr && src_bitrev;  // coset scale + bit-reversed gather come together
+    const bool plain = A.scale == nullptr && A.src_bitrev == 0;
+    if (k == 10 && pass10_ok(A) && (first || plain)) {
+      Pass10Extra X{};
+      const bool passtw = log_n - s0 - 10 > 0;
+      if (first) {
+        X.sigma = cs->sigma;
+        X.hinv = cs->hinv;
+        uint32_t d = kbh::pow(cs->sigma, 32ull << (log_n - 10)), acc = kbh::ONE;
+        for (int q = 0; q < 32; q++) {
+          X.dq[q] = acc;
+          acc = kbh::mul(acc, d);
+        }
+        A.scale = nullptr;
+        if (dir == DIR_FWD)
+          e = passtw ? launch_pass10<DIR_FWD, true, true>(A, X, st) : launch_pass10<DIR_FWD, true, false>(A, X, st);
+        else
+          e = passtw ? launch_pass10<DIR_INV, true, true>(A, X, st) : launch_pass10<DIR_INV, true, false>(A, X, st);
+      } else if (dir == DIR_FWD) {
+        e = passtw ? launch_pass10<DIR_FWD, false, true>(A, X, st) : launch_pass10<DIR_FWD, false, false>(A, X, st);
+      } else {
+        e = passtw ? launch_pass10<DIR_INV, false, true>(A, X, st) : launch_pass10<DIR_INV, false, false>(A, X, st);
+      }
+    } else {
+      if (p == 0 && cs != nullptr && A.scale == nullptr) return cudaErrorInvalidValue;  // scale vector was not prepared
+      e = dir == DIR_FWD ? launch_pass<DIR_FWD>(A, k, st) : launch_pass<DIR_INV>(A, k, st);
+    }
     if (e != cudaSuccess) return e;
     s0 += k;
   }

@@ -243,20 +243,29 @@ static inline uint32_t num_passes(uint32_t log_n) { return log_n == 0 ? 1 : (log
 // scaled by (shift * g_{n+b}^bitrev_b(t))^i: 2^b independent coset transforms, no zero padding.
 
 // scale vectors sigma_t^i / h of the 2^b coset blocks (shared by every column of a matrix)
-static int32_t lde_scales(zk_ctx* c, uint64_t h, uint32_t log_blowup, uint32_t shift, std::vector<uint32_t*>& out) {
+static int32_t lde_scales(zk_ctx* c, uint64_t h, uint32_t log_blowup, uint32_t shift, bool aligned,
+                          std::vector<ntt::CosetScale>& out) {
   uint32_t n = kbh::log2_exact(h);
   uint32_t gnb = kbh::two_adic_generator(n + log_blowup);
   uint32_t hinv = kbh::inv(kbh::to_monty((uint32_t)(h % kbh::P)));
-  out.assign(1u << log_blowup, nullptr);
+  out.assign(1u << log_blowup, ntt::CosetScale{});
   for (uint32_t t = 0; t < (1u << log_blowup); t++) {
-    int32_t rc = dev_alloc(c, h * 4ull, (void**)&out[t]);
+    out[t].sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
+    out[t].hinv = hinv;
+    if (aligned && n >= 10 && n % 10 == 0) continue;  // first pass = second-generation k=10 pass: derives the scale itself
+    uint32_t* v = nullptr;
+    int32_t rc = dev_alloc(c, h * 4ull, (void**)&v);
     if (rc) return rc;
-    uint32_t sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
-    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, out[t], h, sigma, hinv);
+    out[t].vec = v;
+    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, v, h, out[t].sigma, hinv);
     CK(cudaGetLastError());
     c->launches++;
   }
   return ZK_OK;
+}
+static void free_scales(zk_ctx* c, std::vector<ntt::CosetScale>& s) {
+  for (auto& x : s)
+    if (x.vec) dev_free(c, const_cast<uint32_t*>(x.vec));
 }
 
 static int32_t check_lde_shape(zk_ctx* c, uint64_t h, uint32_t log_blowup) {
@@ -270,7 +279,7 @@ static int32_t check_lde_shape(zk_ctx* c, uint64_t h, uint32_t log_blowup) {
 // LDE of `nc` columns.  `coef` receives the (bit-reversed, unscaled) coefficients and may alias `in` (the
 // inverse transform then runs in place); the 2^b blocks go to out.ptr + t*h*out.w, columns [out.c0, out.c0+nc).
 static int32_t lde_cols(zk_ctx* c, ntt::Cols in, ntt::Cols coef, ntt::Cols out, uint32_t nc, uint64_t h,
-                        uint32_t log_blowup, const std::vector<uint32_t*>& scales) {
+                        uint32_t log_blowup, const std::vector<ntt::CosetScale>& scales) {
   if (nc == 0) return ZK_OK;
   uint32_t n = kbh::log2_exact(h);
   {
@@ -281,7 +290,7 @@ static int32_t lde_cols(zk_ctx* c, ntt::Cols in, ntt::Cols coef, ntt::Cols out, 
   for (uint32_t t = 0; t < (1u << log_blowup); t++) {
     ProfScope ps(c, "coset_dft");
     ntt::Cols blk{out.ptr + (size_t)t * h * out.w, out.w, out.c0};
-    CK(ntt::transform(coef, blk, nc, n, ntt::DIR_FWD, c->tw[0], c->log_L, scales[t], true, c->stream));
+    CK(ntt::transform(coef, blk, nc, n, ntt::DIR_FWD, c->tw[0], c->log_L, &scales[t], true, c->stream));
     c->launches += num_passes(n);
   }
   return ZK_OK;
@@ -293,12 +302,13 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
   if (rc) return rc;
   if (w == 0) return ZK_OK;
   uint32_t* coef = nullptr;
-  std::vector<uint32_t*> scales;
+  std::vector<ntt::CosetScale> scales;
   if ((rc = dev_alloc(c, h * w * 4ull, (void**)&coef))) return rc;
-  if ((rc = lde_scales(c, h, log_blowup, shift, scales))) return rc;
+  const bool aligned = (w & 1u) == 0 && ((uintptr_t)in % 8) == 0 && ((uintptr_t)out % 8) == 0;
+  if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
   rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, w, 0}, ntt::Cols{out, w, 0}, w, h, log_blowup,
                 scales);
-  for (auto p : scales) dev_free(c, p);
+  free_scales(c, scales);
   dev_free(c, coef);
   return rc;
 }
@@ -317,8 +327,9 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   uint32_t slab = c->slab_cols;
   if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
   const uint32_t nslab = (w + slab - 1) / slab;
-  std::vector<uint32_t*> scales;
-  if ((rc = lde_scales(c, h, log_blowup, shift, scales))) return rc;
+  std::vector<ntt::CosetScale> scales;
+  const bool aligned = (w & 1u) == 0 && (slab & 1u) == 0 && ((uintptr_t)out % 8) == 0;
+  if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
   uint32_t* buf[2] = {nullptr, nullptr};
   uint4* state = nullptr;
   const uint32_t nbuf = nslab > 1 ? 2 : 1;
@@ -360,7 +371,7 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     cudaEventDestroy(buf_free[b]);
   }
   cudaEventDestroy(ready);
-  for (auto p : scales) dev_free(c, p);
+  free_scales(c, scales);
   for (uint32_t b = 0; b < nbuf; b++) dev_free(c, buf[b]);
   if (state) dev_free(c, state);
   return rc;

@@ -28,7 +28,7 @@ struct zk_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
-  uint32_t slab_cols = 64;              // columns per slab of the streaming commit (multiple of 16; env ZK_SLAB_COLS)
+  uint32_t slab_cols = 32;              // columns per slab of the streaming commit (multiple of 16; env ZK_SLAB_COLS)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
