@@ -24,6 +24,7 @@
 // scale vector (coset shift powers and 1/n).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "kb31.cuh"
@@ -214,9 +215,12 @@ struct Pass10Extra {
 constexpr int P10_ROWS = 1024, P10_FSTRIDE = 33;
 constexpr size_t P10_SMEM = ((size_t)(P10_ROWS + P10_ROWS / 32) * TILE_COLS + 32 * P10_FSTRIDE + 96) * 4;
 
-template <int DIR, bool FIRST, bool PASSTW>
-__global__ void __launch_bounds__(256, 2) ntt_pass10(PassArgs A, Pass10Extra X) {
+// CPT = columns per thread: 2 -> 256 threads, 64-bit accesses, 128 registers (16 warps/SM);
+//                            1 -> 512 threads, 32-bit accesses, 64 registers (32 warps/SM).
+template <int DIR, bool FIRST, bool PASSTW, int CPT>
+__global__ void __launch_bounds__(512 / CPT, 2) ntt_pass10(PassArgs A, Pass10Extra X) {
   constexpr int C = TILE_COLS;
+  constexpr uint32_t NT = 512 / CPT, CSH = CPT == 2 ? 3 : 4;  // threads, log2(threads per tau)
   ZK_DYN_SMEM(sm);
   uint32_t* sdat = sm;
   uint32_t* F = sm + (P10_ROWS + P10_ROWS / 32) * C;
@@ -224,13 +228,14 @@ __global__ void __launch_bounds__(256, 2) ntt_pass10(PassArgs A, Pass10Extra X) 
   uint32_t* gk = G + 32;
   uint32_t* ct = gk + 32;
 
-  const uint32_t cp = threadIdx.x & 7, tau = threadIdx.x >> 3;
+  const uint32_t cp = threadIdx.x & ((1u << CSH) - 1), tau = threadIdx.x >> CSH;
   const uint32_t ncg = (A.nc + C - 1) / C;
   const uint32_t cg = blockIdx.x % ncg, tile = blockIdx.x / ncg;
   const uint32_t n = A.log_n, rem = n - A.s0 - 10;
   const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
-  const uint32_t col = cg * C + cp * 2;
-  const bool ok = col < A.nc;  // nc is even
+  const uint32_t lc = cp * CPT;  // column inside the tile
+  const uint32_t col = cg * C + lc;
+  const bool ok = col < A.nc;  // nc is even when CPT == 2
   const uint32_t jbase = (hi << (n - A.s0)) + lo;
   const uint32_t base = lo << A.s0;
 
@@ -244,62 +249,81 @@ __global__ void __launch_bounds__(256, 2) ntt_pass10(PassArgs A, Pass10Extra X) 
     ct[t] = FIRST ? kb::mul(kb::pow(X.sigma, jbase + (t << rem)), X.hinv) : kb::ONE;
   }
 
-  uint32_t v0[32], v1[32];
+  uint32_t v[CPT][32];
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     uint32_t i = ((uint32_t)q << 5) + tau;
     uint32_t j = jbase + (i << rem);
     uint32_t srow = FIRST ? (__brev(j) >> (32 - n)) : j;
-    uint2 x = make_uint2(0u, 0u);
-    if (ok) x = __ldg(reinterpret_cast<const uint2*>(A.src + (size_t)srow * A.ws + A.c0s + col));
-    if (FIRST && q > 0) {
-      x.x = kb::mul(x.x, X.dq[q]);
-      x.y = kb::mul(x.y, X.dq[q]);
+    const uint32_t* sp = A.src + (size_t)srow * A.ws + A.c0s + col;
+    if constexpr (CPT == 2) {
+      uint2 x = make_uint2(0u, 0u);
+      if (ok) x = __ldg(reinterpret_cast<const uint2*>(sp));
+      v[0][q] = x.x;
+      v[1][q] = x.y;
+    } else {
+      v[0][q] = ok ? __ldg(sp) : 0u;
     }
-    v0[q] = x.x;
-    v1[q] = x.y;
+    if (FIRST && q > 0) {
+#pragma unroll
+      for (int c = 0; c < CPT; c++) v[c][q] = kb::mul(v[c][q], X.dq[q]);
+    }
   }
   __syncthreads();  // gk, ct ready
-  for (uint32_t e = threadIdx.x; e < 1024; e += 256) {
+  for (uint32_t e = threadIdx.x; e < 1024; e += NT) {
     uint32_t t = e >> 5, k = e & 31;
     uint32_t f = root_pow(A.tw, A.log_L, 10, t * k);
     if (PASSTW) f = kb::mul(f, gk[k]);
     if (FIRST) f = kb::mul(f, ct[t]);
     F[t * P10_FSTRIDE + k] = f;
   }
-  dif32_shoup<DIR>(v0);
-  dif32_shoup<DIR>(v1);
+#pragma unroll
+  for (int c = 0; c < CPT; c++) dif32_shoup<DIR>(v[c]);
   __syncthreads();  // F ready
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     if (q > 0 || FIRST || PASSTW) {
       uint32_t f = F[tau * P10_FSTRIDE + brev5(q)];
-      v0[q] = kb::mul(v0[q], f);
-      v1[q] = kb::mul(v1[q], f);
+#pragma unroll
+      for (int c = 0; c < CPT; c++) v[c][q] = kb::mul(v[c][q], f);
     }
     uint32_t i = ((uint32_t)q << 5) + tau;
-    *reinterpret_cast<uint2*>(sdat + (i + (i >> 5)) * C + cp * 2) = make_uint2(v0[q], v1[q]);
+    uint32_t* dp = sdat + (i + (i >> 5)) * C + lc;
+    if constexpr (CPT == 2)
+      *reinterpret_cast<uint2*>(dp) = make_uint2(v[0][q], v[1][q]);
+    else
+      *dp = v[0][q];
   }
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     uint32_t i = tau * 32 + q;
-    uint2 x = *reinterpret_cast<const uint2*>(sdat + (i + (i >> 5)) * C + cp * 2);
-    v0[q] = x.x;
-    v1[q] = x.y;
+    const uint32_t* dp = sdat + (i + (i >> 5)) * C + lc;
+    if constexpr (CPT == 2) {
+      uint2 x = *reinterpret_cast<const uint2*>(dp);
+      v[0][q] = x.x;
+      v[1][q] = x.y;
+    } else {
+      v[0][q] = *dp;
+    }
   }
-  dif32_shoup<DIR>(v0);
-  dif32_shoup<DIR>(v1);
+#pragma unroll
+  for (int c = 0; c < CPT; c++) dif32_shoup<DIR>(v[c]);
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     uint32_t i = tau * 32 + q;
-    uint32_t a = v0[q], b = v1[q];
     if (PASSTW && q > 0) {
       uint32_t g = G[brev5(q)];
-      a = kb::mul(a, g);
-      b = kb::mul(b, g);
+#pragma unroll
+      for (int c = 0; c < CPT; c++) v[c][q] = kb::mul(v[c][q], g);
     }
-    if (ok) *reinterpret_cast<uint2*>(A.dst + (size_t)(jbase + (i << rem)) * A.wd + A.c0d + col) = make_uint2(a, b);
+    uint32_t* op = A.dst + (size_t)(jbase + (i << rem)) * A.wd + A.c0d + col;
+    if (ok) {
+      if constexpr (CPT == 2)
+        *reinterpret_cast<uint2*>(op) = make_uint2(v[0][q], v[1][q]);
+      else
+        *op = v[0][q];
+    }
   }
 }
 
@@ -362,25 +386,38 @@ inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int DIR, bool FIRST, bool PASSTW>
-inline cudaError_t launch_pass10(const PassArgs& A, const Pass10Extra& X, cudaStream_t st) {
+template <int DIR, bool FIRST, bool PASSTW, int CPT>
+inline cudaError_t launch_pass10_cpt(const PassArgs& A, const Pass10Extra& X, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)P10_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
   uint64_t blocks = (1ull << (A.log_n - 10)) * ncg;
-  auto kfn = ntt_pass10<DIR, FIRST, PASSTW>;
-  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, 256, P10_SMEM, st, A, X);
+  auto kfn = ntt_pass10<DIR, FIRST, PASSTW, CPT>;
+  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, 512 / CPT, P10_SMEM, st, A, X);
   return cudaGetLastError();
 }
 
-// the k = 10 pass can use the second-generation kernel when every access is 8-byte aligned
-inline bool pass10_ok(const PassArgs& A) {
+// columns per thread of the k=10 pass: 2 needs every access 8-byte aligned
+inline bool pass10_aligned(const PassArgs& A) {
   return ((A.ws | A.wd | A.c0s | A.c0d | A.nc) & 1u) == 0 && ((uintptr_t)A.src % 8) == 0 && ((uintptr_t)A.dst % 8) == 0;
+}
+inline int& pass10_cpt_pref() {
+  static int pref = [] {
+    const char* e = getenv("ZK_NTT_CPT");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return pref;
+}
+
+template <int DIR, bool FIRST, bool PASSTW>
+inline cudaError_t launch_pass10(const PassArgs& A, const Pass10Extra& X, cudaStream_t st) {
+  if (pass10_cpt_pref() == 2 && pass10_aligned(A)) return launch_pass10_cpt<DIR, FIRST, PASSTW, 2>(A, X, st);
+  return launch_pass10_cpt<DIR, FIRST, PASSTW, 1>(A, X, st);
 }
 
 template <int DIR>
@@ -440,7 +477,7 @@ inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, in
     cudaError_t e;
     const bool first = p == 0 && cs != nullptr && src_bitrev;  // coset scale + bit-reversed gather come together
     const bool plain = A.scale == nullptr && A.src_bitrev == 0;
-    if (k == 10 && pass10_ok(A) && (first || plain)) {
+    if (k == 10 && (first || plain)) {
       Pass10Extra X{};
       const bool passtw = log_n - s0 - 10 > 0;
       if (first) {

@@ -252,7 +252,8 @@ static int32_t lde_scales(zk_ctx* c, uint64_t h, uint32_t log_blowup, uint32_t s
   for (uint32_t t = 0; t < (1u << log_blowup); t++) {
     out[t].sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
     out[t].hinv = hinv;
-    if (aligned && n >= 10 && n % 10 == 0) continue;  // first pass = second-generation k=10 pass: derives the scale itself
+    (void)aligned;
+    if (n >= 10 && n % 10 == 0) continue;  // first pass = second-generation k=10 pass: derives the scale itself
     uint32_t* v = nullptr;
     int32_t rc = dev_alloc(c, h * 4ull, (void**)&v);
     if (rc) return rc;
