@@ -190,7 +190,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
       uint32_t Li = S.log_max - i;
       uint64_t hh = 1ull << (Li - 1);
       zk_pdata* lp = nullptr;
-      RC(mmcs_commit_one_dev(c, cur, hh, 8, false, false, &lp));
+      RC(mmcs_commit_one_dev(c, cur, hh, 8, false, false, &lp, false));
       sc.pds.push_back(lp);
       layer_pd.push_back(lp);
       CK(cudaMemcpyAsync(commits + 8 * i, pdata_root_dev(lp), 32, cudaMemcpyDeviceToDevice, st));
@@ -241,7 +241,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
       }
       for (uint32_t i = 0; i < S.n_layers; i++) {
         const zk_pdata* lp = layer_pd[i];
-        ZK_LAUNCH(fri::fri_layer_query_kernel, num_queries, 64, 0, st, lp->mats[0], lp->digests, lp->d_layer_off, lp->log_max, i,
+        ZK_LAUNCH(fri::fri_layer_query_kernel, num_queries, 64, 0, st, lp->mats[0], lp->digests, lp->log_max, i,
                   d_idx, queries, S.query_words, S.layer_q_off[i]);
         c->launches++;
       }

@@ -16,6 +16,8 @@
 #include "launch.cuh"
 #include "poseidon2.cuh"
 
+__host__ __device__ inline uint64_t mmcs_layer_off(uint32_t L, uint32_t l);
+
 namespace fri {
 
 struct Chal {  // same 34-word image as zk_challenger in include/zkgpu.h
@@ -303,7 +305,7 @@ __global__ void final_poly_kernel(const uint32_t* __restrict__ folded, uint32_t 
 // answer_query for one commit-phase layer (p3_fri::prover::answer_query): block q = query q.
 // Writes sibling value (4 words) then the path of the pair leaf into proof[q * query_stride + off ...].
 __global__ void fri_layer_query_kernel(const uint32_t* __restrict__ leaves /* ext pairs */, const uint32_t* __restrict__ digests,
-                                       const uint64_t* __restrict__ layer_off, uint32_t log_h /* of the layer tree */,
+                                       uint32_t log_h /* of the layer tree */,
                                        uint32_t layer_i, const uint64_t* __restrict__ indices, uint32_t* __restrict__ proof,
                                        uint64_t query_stride, uint64_t off) {
   uint64_t index_i = indices[blockIdx.x] >> layer_i;
@@ -314,7 +316,7 @@ __global__ void fri_layer_query_kernel(const uint32_t* __restrict__ leaves /* ex
       o[t] = leaves[pair * 8 + 4 * ((index_i ^ 1) & 1) + t];
     } else {
       uint32_t l = (t - 4) >> 3, k = (t - 4) & 7;
-      o[t] = digests[layer_off[l] + (((pair >> l) ^ 1) << 3) + k];
+      o[t] = digests[mmcs_layer_off(log_h, l) + (((pair >> l) ^ 1) << 3) + k];
     }
   }
 }

@@ -140,6 +140,26 @@ __global__ void __launch_bounds__(256) compress_layer(const uint32_t* __restrict
   store_digest(cur + i * 8, s);
 }
 
+// Top of the tree in ONE launch: starting from a layer of `len0` <= 1024 digests at word offset off0 of the
+// digest buffer (layers stored back to back, halving), a single CTA compresses layer after layer down to
+// the root.  Replaces up to 10 launch-latency-bound compress_layer launches per tree (FRI commits 20 trees).
+__global__ void __launch_bounds__(512) compress_top(uint32_t* __restrict__ digests, uint64_t off0, uint32_t len0) {
+  uint64_t off = off0;
+  for (uint32_t len = len0; len > 1; len >>= 1) {
+    uint32_t half = len >> 1;
+    uint64_t nxt = off + (uint64_t)len * 8;
+    for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+      const uint4* p = reinterpret_cast<const uint4*>(digests + off + (uint64_t)i * 16);
+      uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+      uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      p2::permute(s);
+      store_digest(digests + nxt + (uint64_t)i * 8, s);
+    }
+    __syncthreads();
+    off = nxt;
+  }
+}
+
 // Raw permutation of n independent 16-word states (unit entry point / known-answer tests).
 __global__ void __launch_bounds__(256) permute_states(uint32_t* st, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

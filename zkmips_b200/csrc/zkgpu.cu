@@ -28,8 +28,7 @@ __global__ void bitrev_rows_kernel(const uint32_t* __restrict__ in, uint32_t* __
 
 // Mmcs::open_batch gather: block b = query index b
 __global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32_t n_mats, uint32_t sum_w,
-                                   const uint32_t* __restrict__ digests, const uint64_t* __restrict__ layer_off,
-                                   uint32_t log_max, const uint64_t* __restrict__ indices, uint32_t shift,
+                                   const uint32_t* __restrict__ digests, uint32_t log_max, const uint64_t* __restrict__ indices, uint32_t shift,
                                    uint32_t* __restrict__ opened, uint64_t opened_stride,
                                    uint32_t* __restrict__ proofs, uint64_t proofs_stride) {
   uint64_t index = indices[blockIdx.x] >> shift;
@@ -43,7 +42,7 @@ __global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32
   uint32_t* p = proofs + (size_t)blockIdx.x * proofs_stride;
   for (uint32_t t = threadIdx.x; t < log_max * 8; t += blockDim.x) {
     uint32_t l = t >> 3, k = t & 7;
-    p[t] = digests[layer_off[l] + (((index >> l) ^ 1) << 3) + k];
+    p[t] = digests[mmcs_layer_off(log_max, l) + (((index >> l) ^ 1) << 3) + k];
   }
 }
 
@@ -348,11 +347,8 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
     const uint32_t b = k & 1, c0 = k * slab, nc = std::min(slab, w - c0);
     if (k >= 2) CK(cudaStreamWaitEvent(c->copy_stream, buf_free[b], 0));
-    {
-      ProfScope ps(c, "h2d_enqueue");
-      CK(cudaMemcpy2DAsync(buf[b], (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
-                           c->copy_stream));
-    }
+    CK(cudaMemcpy2DAsync(buf[b], (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+                         c->copy_stream));
     CK(cudaEventRecord(up_done[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, up_done[b], 0));
     ntt::Cols sl{buf[b], nc, 0};
@@ -419,7 +415,7 @@ int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd) {
   return dev_alloc(c, words * 4, (void**)&pd->digests);
 }
 
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done) {
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, bool with_open_desc) {
   uint32_t n = pd->n;
   int32_t rc;
   if (!pd->digests && (rc = mmcs_alloc(c, pd))) return rc;
@@ -443,6 +439,13 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done) {
     ProfScope ps(c, "tree");
     for (uint32_t l = 1; l <= pd->log_max; l++) {
       uint64_t len = hmax >> l;
+      if (next == n && 2 * len <= 1024) {
+        // no matrix left to inject: one CTA finishes the tree from the layer of 2*len digests
+        ZK_LAUNCH_COOP(mk::compress_top, 1, 512, 0, c->stream, pd->digests, pd->layer_off[l - 1], (uint32_t)(2 * len));
+        CK(cudaGetLastError());
+        c->launches++;
+        break;
+      }
       take_group(len, g);
       const uint32_t* injp = nullptr;
       if (!g.empty()) {
@@ -457,18 +460,18 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done) {
     }
   }
   if (inj && (rc = dev_free(c, inj))) return rc;
-  // open_batch descriptors
-  std::vector<zk_open_desc> od(n);
-  uint32_t off = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
-    off += pd->widths[i];
+  if (with_open_desc) {
+    // open_batch descriptors
+    std::vector<zk_open_desc> od(n);
+    uint32_t off = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
+      off += pd->widths[i];
+    }
+    pd->sum_w = off;
+    if ((rc = dev_alloc(c, n * sizeof(zk_open_desc), (void**)&pd->d_desc))) return rc;
+    CK(cudaMemcpyAsync(pd->d_desc, od.data(), n * sizeof(zk_open_desc), cudaMemcpyHostToDevice, c->stream));
   }
-  pd->sum_w = off;
-  if ((rc = dev_alloc(c, n * sizeof(zk_open_desc), (void**)&pd->d_desc))) return rc;
-  CK(cudaMemcpyAsync(pd->d_desc, od.data(), n * sizeof(zk_open_desc), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = dev_alloc(c, (pd->log_max + 1) * 8, (void**)&pd->d_layer_off))) return rc;
-  CK(cudaMemcpyAsync(pd->d_layer_off, pd->layer_off.data(), (pd->log_max + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (fetch_root) {
     CK(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off[pd->log_max], 32, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -477,7 +480,7 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done) {
 }
 
 int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
-                            zk_pdata** out) {
+                            zk_pdata** out, bool with_open_desc) {
   zk_pdata* pd = new zk_pdata();
   pd->ctx = c;
   pd->n = 1;
@@ -485,7 +488,7 @@ int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bo
   pd->widths.assign(1, w);
   pd->mats.assign(1, mat);
   pd->owned.assign(1, take_ownership);
-  int32_t rc = mmcs_build(c, pd, fetch_root);
+  int32_t rc = mmcs_build(c, pd, fetch_root, false, with_open_desc);
   if (rc != ZK_OK) {
     pd->owned[0] = false;
     pdata_release(pd);
@@ -510,7 +513,6 @@ void pdata_release(zk_pdata* pd) {
     if (pd->owned[i] && pd->mats[i]) cudaFreeAsync(pd->mats[i], c->stream);
   if (pd->digests) cudaFreeAsync(pd->digests, c->stream);
   if (pd->d_desc) cudaFreeAsync(pd->d_desc, c->stream);
-  if (pd->d_layer_off) cudaFreeAsync(pd->d_layer_off, c->stream);
   delete pd;
 }
 
@@ -681,8 +683,7 @@ extern "C" int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint3
 
 int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t shift,
                        uint32_t* d_opened, uint64_t opened_stride, uint32_t* d_proofs, uint64_t proofs_stride) {
-  ZK_LAUNCH(open_gather_kernel, n_idx, 128, 0, c->stream, pd->d_desc, pd->n, pd->sum_w, pd->digests, pd->d_layer_off,
-            pd->log_max, d_idx, shift, d_opened, opened_stride, d_proofs, proofs_stride);
+  ZK_LAUNCH(open_gather_kernel, n_idx, 128, 0, c->stream, pd->d_desc, pd->n, pd->sum_w, pd->digests, pd->log_max, d_idx, shift, d_opened, opened_stride, d_proofs, proofs_stride);
   CK(cudaGetLastError());
   c->launches++;
   return ZK_OK;

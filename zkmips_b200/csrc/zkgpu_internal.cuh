@@ -50,6 +50,11 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// word offset of digest layer l in a tree whose leaf layer has 2^L digests (layers stored leaves first)
+__host__ __device__ inline uint64_t mmcs_layer_off(uint32_t L, uint32_t l) {
+  return 8ull * ((2ull << L) - (2ull << (L - l)));
+}
+
 struct zk_open_desc {
   const uint32_t* ptr;
   uint32_t w;
@@ -70,7 +75,6 @@ struct zk_pdata {
   uint32_t* digests = nullptr;    // all layers, leaves first
   std::vector<uint64_t> layer_off;  // word offset of each layer
   zk_open_desc* d_desc = nullptr;
-  uint64_t* d_layer_off = nullptr;
   uint32_t root[8] = {0};
 };
 
@@ -79,11 +83,13 @@ int32_t dev_free(zk_ctx* c, void* p);
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
                 uint32_t* out);
 int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd);
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true, bool leaves_done = false);
+// with_open_desc == false skips the open_batch descriptor upload (FRI layers are opened by their own kernel),
+// which keeps the build free of host->device copies and therefore fully asynchronous.
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true, bool leaves_done = false, bool with_open_desc = true);
 // Mmcs::commit of one device-resident matrix; with fetch_root == false nothing is copied to the host and the
 // stream is not synchronised (the root stays at pdata_root_dev()).
 int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
-                            zk_pdata** out);
+                            zk_pdata** out, bool with_open_desc = true);
 inline const uint32_t* pdata_root_dev(const zk_pdata* pd) { return pd->digests + pd->layer_off[pd->log_max]; }
 void pdata_release(zk_pdata* pd);
 // open_batch gather for n_idx indices (each shifted right by `shift` first); query q writes its rows at

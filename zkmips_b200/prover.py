@@ -69,6 +69,12 @@ class ShardProof:
 class GpuShardProver:
     def __init__(self, ctx, log_blowup=1, num_queries=84, pow_bits=16):
         self.ctx, self.log_blowup, self.num_queries, self.pow_bits = ctx, log_blowup, num_queries, pow_bits
+        self.phase_ms = {}  # host wall clock per phase of the last commit/open (each phase ends synchronised)
+
+    def _tick(self, name, t0):
+        import time
+        self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
 
     @staticmethod
     def order(chips):
@@ -85,13 +91,18 @@ class GpuShardProver:
 
     def commit(self, chips):
         """MachineProver::commit (prover.rs:258-292)."""
+        import time
+        t0 = time.perf_counter()
         chips = self.order(chips)
         root, pd = self.ctx.commit([c.main for c in chips], [MONTY_ONE] * len(chips), self.log_blowup)
+        self._tick("commit_main", t0)
         return chips, root, pd
 
     def open(self, chips, main_root, main_pd, challenger: Challenger, prep_root=None, prep_pd=None,
              inject_witness=-1):
         """MachineProver::open (prover.rs:298-653).  `chips` in commit order."""
+        import time
+        t0 = time.perf_counter()
         ctx = self.ctx
         pre_idx = {}
         for c in chips:
@@ -114,6 +125,7 @@ class GpuShardProver:
                 challenger.observe(lcs)
                 challenger.observe(c.global_cumsum)
         alpha = challenger.sample_ext()                                  # prover.rs:426
+        t0 = self._tick("permutation_and_challenges", t0)
         # quotient values per chip, written as chunk matrices (prover.rs:429-488)
         chunk_ptrs, chunk_shapes, chunk_shifts = [], [], []
         for c in chips:
@@ -130,11 +142,14 @@ class GpuShardProver:
                 chunk_shapes.append((1 << n, 4))
                 chunk_shifts.append(monty(3 * pow(g, k, P)))             # split_domains: shift * g^k
             c._chunks_dptr = dptr
+        ctx.sync()
+        t0 = self._tick("quotient", t0)
         q_root, q_pd = ctx.commit_dev(chunk_ptrs, chunk_shapes, chunk_shifts, self.log_blowup)   # prover.rs:496-497
         for c in chips:
             ctx.dev_free(c._chunks_dptr)
         challenger.observe(q_root)                                       # prover.rs:498
         zeta = challenger.sample_ext()                                   # prover.rs:501
+        t0 = self._tick("commit_quotient", t0)
         # opening points (prover.rs:503-544)
         rounds, points = [], []
 
@@ -156,6 +171,7 @@ class GpuShardProver:
         points += [[zeta] for _ in chunk_ptrs]
         proof = pcs_open(ctx, rounds, points, challenger, self.log_blowup, self.num_queries, self.pow_bits,
                          inject_witness)                                 # prover.rs:546-556
+        t0 = self._tick("pcs_open", t0)
         shapes = [[(r.height(i), r.width(i)) for i in range(r.num_matrices())] for r in rounds]
         sp = ShardProof(main_root, perm_root, q_root, prep_root, proof, cumsums, [c.name for c in chips], points, shapes)
         if perm_pd is not None:
