@@ -11,17 +11,16 @@
 //
 // Decomposition (decimation in frequency, natural order in, bit-reversed order out), "four-step" at
 // two levels so that almost all twiddles are compile-time constants:
-//   * the n stages are cut into passes of k <= 10 stages; a pass tile is 2^k rows (stride 2^(n-s0-k))
-//     x 16 columns; after its local size-2^k DFT each element is multiplied by the pass twiddle
-//     g_n^(lo * 2^s0 * bitrev_k(i)), which makes the remaining stages independent smaller DFTs;
-//   * inside a tile (k = 5 + B) each thread keeps 32 elements of one column in registers: a size-32
-//     DFT with constant twiddles (powers of w_32 from the constant bank), one twiddle multiply by
-//     w_{2^k}^(tau * bitrev_5(q)) from a shared-memory table, ONE shared-memory exchange, then
-//     2^(5-B) size-2^B DFTs with constant twiddles.  One HBM read + one HBM write per pass.
-//   * passes with k <= 5 need no shared memory at all (ntt_pass_reg).
+//   * the n stages are cut into passes: floor(n/10) passes of k = 10 stages (ntt_pass10) preceded by one
+//     or two register-only passes (k <= 5, ntt_pass_reg) for the remaining n mod 10 stages.  A pass tile is
+//     2^k rows of stride 2^(n-s0-k); after its local size-2^k DFT each element is multiplied by the pass
+//     twiddle g_n^(lo * 2^s0 * bitrev_k(i)), which makes the remaining stages independent smaller DFTs;
+//   * inside a k=10 tile each thread keeps 32 elements of a column in registers: a size-32 DFT with constant
+//     twiddles (Shoup multiplication by immediates), one twiddle multiply from a per-CTA shared-memory table,
+//     ONE shared-memory exchange, a second size-32 DFT.  One HBM read + one HBM write per pass.
 // Fused into the first pass of a transform: bit-reversed row gather (hands the bit-reversed output of
-// the inverse transform to the forward one without a separate permutation kernel) and a per-row
-// scale vector (coset shift powers and 1/n).
+// the inverse transform to the forward one without a separate permutation kernel) and the coset scale
+// sigma^j / n.
 #pragma once
 #include <cstdint>
 #include <cstdlib>
@@ -88,71 +87,11 @@ __host__ __device__ constexpr int brev5(int q) {
   return ((q & 1) << 4) | ((q & 2) << 2) | (q & 4) | ((q & 8) >> 2) | ((q & 16) >> 4);
 }
 
-// ---- pass with k = 5 + B stages (B in 1..5) -------------------------------------------------
-template <int B>
-constexpr size_t pass_smem_bytes() {
-  constexpr int ROWS = 1 << (5 + B);
-  return (size_t)(ROWS + ROWS / 32) * TILE_COLS * 4 + (size_t)ROWS * 4;
-}
-
-template <int B, int DIR>
-__global__ void __launch_bounds__(TILE_COLS << B, (B == 5 ? 2 : 1)) ntt_pass_smem(PassArgs A) {
-  constexpr int K = 5 + B, ROWS = 1 << K, C = TILE_COLS, NT = C << B;
-  ZK_DYN_SMEM(sm);
-  uint32_t* sdat = sm;
-  uint32_t* stw = sm + (ROWS + ROWS / 32) * C;
-
-  const uint32_t cc = threadIdx.x & (C - 1), tau = threadIdx.x >> 4;
-  const uint32_t ncg = (A.nc + C - 1) / C;
-  const uint32_t cg = blockIdx.x % ncg, tile = blockIdx.x / ncg;
-  const uint32_t n = A.log_n, rem = n - A.s0 - K;
-  const uint32_t lo = tile & ((1u << rem) - 1), hi = tile >> rem;
-  const uint32_t col = cg * C + cc;
-  const bool ok = col < A.nc;
-  const uint32_t jbase = (hi << (n - A.s0)) + lo;
-
-  for (uint32_t e = threadIdx.x; e < ROWS; e += NT) stw[e] = root_pow(A.tw, A.log_L, K, e);
-
-  uint32_t v[32];
-#pragma unroll
-  for (int q = 0; q < 32; q++) {
-    uint32_t i = ((uint32_t)q << B) + tau;
-    uint32_t j = jbase + (i << rem);
-    uint32_t srow = A.src_bitrev ? (__brev(j) >> (32 - n)) : j;
-    uint32_t x = ok ? __ldg(A.src + (size_t)srow * A.ws + A.c0s + col) : 0u;
-    if (A.scale) x = kb::mul(x, __ldg(A.scale + j));
-    v[q] = x;
-  }
-  dif_groups<5, DIR, 32>(v);
-  __syncthreads();  // stw complete
-#pragma unroll
-  for (int q = 1; q < 32; q++) v[q] = kb::mul(v[q], stw[tau * brev5(q)]);
-#pragma unroll
-  for (int q = 0; q < 32; q++) {
-    uint32_t i = ((uint32_t)q << B) + tau;
-    sdat[(i + (i >> 5)) * C + cc] = v[q];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 32; q++) {
-    uint32_t i = tau * 32 + q;
-    v[q] = sdat[(i + (i >> 5)) * C + cc];
-  }
-  dif_groups<B, DIR, 32>(v);
-#pragma unroll
-  for (int q = 0; q < 32; q++) {
-    uint32_t i = tau * 32 + q;
-    uint32_t x = v[q];
-    if (rem > 0) {
-      uint32_t E = (lo << A.s0) * (__brev(i) >> (32 - K));
-      x = kb::mul(x, root_pow(A.tw, A.log_L, n, E));
-    }
-    if (ok) A.dst[(size_t)(jbase + (i << rem)) * A.wd + A.c0d + col] = x;
-  }
-}
-
-// ---- pass with k = 10 stages, second generation ------------------------------------------------
-// Same tile and data flow as ntt_pass_smem<5> with the instruction count per element roughly halved:
+// ---- pass with k = 10 stages -------------------------------------------------------------------
+// Tile = 1024 rows (stride 2^rem) x 16 columns; each thread keeps 32 elements per column in registers:
+// size-32 DFT, twiddle, ONE shared-memory exchange (padded, conflict free), size-32 DFT, pass twiddle.
+// (The first version of this kernel, one column per thread with global twiddle/scale loads, needed 85-104
+// instructions per element; this one 51-69: profiles/README.md.)
 //   * two adjacent columns per thread (64-bit global and shared accesses, twiddles shared by both);
 //   * butterfly twiddles are compile-time constants multiplied with Shoup's method
 //     (x*w mod p = x*w - floor(x*w'/2^32)*p, w' = floor(w*2^32/p): IMAD.HI + 2 IMAD + VIADDMNMX, no
@@ -360,23 +299,6 @@ __global__ void __launch_bounds__(256) ntt_pass_reg(PassArgs A, uint64_t total /
 }
 
 // ---- host-side launch -------------------------------------------------------------------------
-template <int B, int DIR>
-inline cudaError_t launch_smem(const PassArgs& A, cudaStream_t st) {
-  static bool configured = false;
-  constexpr size_t bytes = pass_smem_bytes<B>();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
-  uint64_t tiles = 1ull << (A.log_n - (5 + B));
-  uint64_t blocks = tiles * ncg;
-  auto kfn = ntt_pass_smem<B, DIR>;
-  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, TILE_COLS << B, bytes, st, A);
-  return cudaGetLastError();
-}
 template <int K, int DIR>
 inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
   uint64_t total = (uint64_t)A.nc << (A.log_n - K);
@@ -429,11 +351,6 @@ inline cudaError_t launch_pass(const PassArgs& A, uint32_t k, cudaStream_t st) {
     case 3: return launch_reg<3, DIR>(A, st);
     case 4: return launch_reg<4, DIR>(A, st);
     case 5: return launch_reg<5, DIR>(A, st);
-    case 6: return launch_smem<1, DIR>(A, st);
-    case 7: return launch_smem<2, DIR>(A, st);
-    case 8: return launch_smem<3, DIR>(A, st);
-    case 9: return launch_smem<4, DIR>(A, st);
-    case 10: return launch_smem<5, DIR>(A, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -446,6 +363,24 @@ struct Cols {
 
 // Full transform of `nc` columns of a 2^log_n-row matrix: natural-order rows in (optionally gathered
 // through a bit reversal and scaled), bit-reversed rows out.  dst may alias src only when src_bitrev == 0.
+// Pass plan: as many k=10 passes (shared-memory kernel) as fit, preceded by one or two register-only passes
+// (k <= 5) for the remaining log_n mod 10 stages.  Register passes are plain streaming kernels.
+inline uint32_t plan_passes(uint32_t log_n, uint32_t* ks) {
+  uint32_t n10 = log_n / 10, r = log_n - 10 * n10, np = 0;
+  if (log_n == 0) {
+    ks[np++] = 0;
+    return np;
+  }
+  if (r > 5) {
+    ks[np++] = r - 5;
+    ks[np++] = 5;
+  } else if (r > 0) {
+    ks[np++] = r;
+  }
+  for (uint32_t i = 0; i < n10; i++) ks[np++] = 10;
+  return np;
+}
+
 struct CosetScale {
   const uint32_t* vec = nullptr;  // sigma^j / n for every natural row j (needed when the first pass is not a k=10 pass)
   uint32_t sigma = 0, hinv = 0;   // the same as scalars (Montgomery)
@@ -455,11 +390,11 @@ inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, in
                              uint32_t log_L, const CosetScale* cs, bool src_bitrev, cudaStream_t st) {
   if (nc == 0) return cudaSuccess;
   const uint32_t* scale = cs ? cs->vec : nullptr;
-  uint32_t npass = log_n == 0 ? 1 : (log_n + 9) / 10;
-  uint32_t k0 = log_n - 10 * (npass - 1);
+  uint32_t ks[8];
+  uint32_t npass = plan_passes(log_n, ks);
   uint32_t s0 = 0;
   for (uint32_t p = 0; p < npass; p++) {
-    uint32_t k = p == 0 ? k0 : 10;
+    uint32_t k = ks[p];
     PassArgs A;
     A.src = p == 0 ? src.ptr : dst.ptr;
     A.ws = p == 0 ? src.w : dst.w;

@@ -235,7 +235,10 @@ extern "C" int32_t zk_d2h(zk_ctx* c, void* dst, zk_dptr src, uint64_t bytes) {
 // ------------------------------------------------------------------------------------------------
 // LDE
 // ------------------------------------------------------------------------------------------------
-static inline uint32_t num_passes(uint32_t log_n) { return log_n == 0 ? 1 : (log_n + 9) / 10; }
+static inline uint32_t num_passes(uint32_t log_n) {
+  uint32_t ks[8];
+  return ntt::plan_passes(log_n, ks);
+}
 
 // coset_lde_batch(in, log_blowup, shift).bit_reverse_rows()  (SURVEY A.7).
 // Block t of the output (rows [t*h, (t+1)*h)) is the size-h DFT, bit-reversed, of the coefficients
