@@ -97,6 +97,10 @@ int32_t zk_mmcs_commit(zk_ctx* ctx, uint32_t n_mats, const uint32_t* const* mats
 int32_t zk_mmcs_commit_dev(zk_ctx* ctx, uint32_t n_mats, const zk_dptr* mats_dev, const uint64_t* heights,
                            const uint32_t* widths, uint32_t root[8], zk_pdata** out);
 
+/* When enabled, zk_commit keeps a device copy of every input trace in the prover data (zk_pdata_trace), so
+ * that stages between commits which read the trace itself (LogUp) need no second upload. */
+int32_t zk_ctx_keep_traces(zk_ctx* ctx, int32_t enable);
+
 /* ---- ProverData accessors -------------------------------------------------------------------------- */
 void zk_pdata_free(zk_pdata* pd);
 uint32_t zk_pdata_num_matrices(const zk_pdata* pd);
@@ -107,6 +111,8 @@ int32_t zk_pdata_root(const zk_pdata* pd, uint32_t root[8]);
 /* Pcs::get_evaluations_on_domain (crates/stark/src/prover.rs:437-445): the committed LDE, no copy.
  * Row r of the returned matrix is the evaluation at GENERATOR * g^bitrev(r). */
 zk_dptr zk_pdata_lde(const zk_pdata* pd, uint32_t i);
+/* the retained input trace (natural order, height >> log_blowup rows), or 0 when traces were not kept */
+zk_dptr zk_pdata_trace(const zk_pdata* pd, uint32_t i);
 /* Mmcs::get_matrices / Serialize support: copy an LDE matrix or a digest layer (0 = leaves) to the host. */
 int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* out_host);
 int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out_host);
@@ -127,7 +133,7 @@ int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const uint64_t* 
  * chunk c = GENERATOR * g_{n+lqd}^c).  The 11 data arguments mirror quotient_values' parameters. */
 typedef struct {
   uint32_t main_width, prep_width, perm_width /* extension columns */, num_public_values, num_challenges;
-  uint32_t num_constraints, max_degree, num_kernels;
+  uint32_t num_constraints, max_degree, num_kernels, num_lookups;
 } zk_air_desc;
 int32_t zk_air_count(void);
 const char* zk_air_name(int32_t id);
@@ -138,6 +144,14 @@ int32_t zk_quotient(zk_ctx* ctx, int32_t air_id, const zk_pdata* prep, uint32_t 
                     uint32_t log_quotient_degree, const uint32_t alpha[4], const uint32_t* perm_challenges,
                     const uint32_t* public_values, uint32_t n_public_values, const uint32_t local_cumsum[4],
                     const uint32_t global_cumsum[14], zk_dptr* out_chunks);
+
+/* generate_permutation_trace (crates/stark/src/permutation.rs:102-196; call site prover.rs:341-364) on the
+ * device: LogUp batch entries and the running sum for a chip with lookups.  Inputs are the natural-order
+ * traces on the device (zk_pdata_trace after zk_ctx_keep_traces(ctx, 1), or buffers uploaded with zk_h2d).
+ * out_trace: height x (4 * perm_width) base matrix (`flatten_to_base`, prover.rs:393), freed with zk_dev_free
+ * after it has been committed with zk_commit_dev. */
+int32_t zk_permutation_trace(zk_ctx* ctx, int32_t air_id, zk_dptr prep_trace, zk_dptr main_trace, uint64_t height,
+                             const uint32_t perm_challenges[8], zk_dptr* out_trace, uint32_t local_cumsum[4]);
 
 /* ---- DuplexChallenger<Val, Perm, 16, 8> (crates/stark/src/kb31_poseidon2.rs:180; semantics restated at
  *      crates/recursion/circuit/src/challenger.rs:90-233) ------------------------------------------------

@@ -42,6 +42,7 @@ def wide_chip(log_n, width=64, seed=1, name=None):
 
 
 def lookup_chip(log_n, seed=3, name="Lookup"):
+    """valid trace for library.lookup_pair (its LogUp permutation trace is generated on the device)"""
     n = 1 << log_n
     rng = np.random.default_rng(seed)
     pv0 = 7
@@ -54,22 +55,10 @@ def lookup_chip(log_n, seed=3, name="Lookup"):
     m[:, 2] = (m[:, 0] * m[:, 1] + p[:, 0]) % P
     m[:, 3] = rng.integers(0, 2, n)
     m[:, 4] = rng.integers(0, 5, n)
-
-    def permutation(chal_monty):
-        al, be = [[int(x) for x in ob.from_monty(c)] for c in chal_monty]
-        perm = np.zeros((n, 8), np.uint64)
-        phi = [0, 0, 0, 0]
-        for i in range(n):
-            send = ae.ext_add(ae.ext_add(al, [int(m[i, 0]), 0, 0, 0]), ae.ext_mul(be, [int(m[i, 1]), 0, 0, 0]))
-            recv = ae.ext_add(ae.ext_add(al, [int(p[i, 0]), 0, 0, 0]), ae.ext_mul(be, [int(p[i, 1]), 0, 0, 0]))
-            num = ae.ext_sub([int(m[i, 3]) * x % P for x in recv], [int(m[i, 4]) * x % P for x in send])
-            v = ae.ext_mul(num, ae.ext_inv(ae.ext_mul(send, recv)))
-            phi = ae.ext_add(phi, v)
-            perm[i, :4], perm[i, 4:] = v, phi
-        return M(perm), M(phi)
-
-    return Chip(name, "lookup_pair", M(m), preprocessed=M(p), permutation=permutation, public_values=M([pv0]),
-                global_cumsum=M(np.arange(1, 15)))
+    c = Chip(name, "lookup_pair", M(m), preprocessed=M(p), public_values=M([pv0]), global_cumsum=M(np.arange(1, 15)))
+    c.has_lookups = True
+    c.canon = (p, m)
+    return c
 
 
 def _ext_from(words_monty):
@@ -83,7 +72,7 @@ def verify_shard(sp, chips, challenger_words, log_blowup=1, num_queries=84, pow_
     ch = bf.Challenger.from_words(challenger_words)
     bf.observe(ch, sp.main_commit)
     chal = [bf.sample_ext(ch), bf.sample_ext(ch)]
-    perm_chips = [c for c in chips if c.permutation is not None]
+    perm_chips = [c for c in chips if c.permutation is not None or c.has_lookups]
     if sp.perm_commit is not None:
         bf.observe(ch, sp.perm_commit)
         for c, lcs in zip(perm_chips, sp.local_cumsums):
@@ -137,7 +126,7 @@ def verify_shard(sp, chips, challenger_words, log_blowup=1, num_queries=84, pow_
             op["prep"] = prep_round[ppi]
             ppi += 1
         lcs = (0, 0, 0, 0)
-        if c.permutation is not None:
+        if c.permutation is not None or c.has_lookups:
             # unflatten: ext column j = sum_e X^e * opened[4j+e]  (verifier.rs:365-371)
             rows = []
             for prow in perm_round[pi]:

@@ -44,8 +44,15 @@ def test_quotient_values_match_oracle(be, which):
         kw["prep"] = (prep_pd, 0)
         okw["prep_q"] = _natural(prep_pd.lde(0))
     lcs = None
-    if chip.permutation is not None:
-        tr, lcs = chip.permutation(chal)
+    if chip.has_lookups:
+        # device LogUp trace (zk_permutation_trace) against the numpy restatement of permutation.rs:102-196
+        from oracle import logup
+        p_c, m_c = chip.canon
+        exp_tr, exp_lcs = logup.generate_permutation_trace(air, p_c, m_c, ob.from_monty(chal[0]), ob.from_monty(chal[1]))
+        dptr, lcs = ctx.permutation_trace(chip.air, ctx.upload(chip.preprocessed), ctx.upload(chip.main), 1 << n, chal)
+        tr = ctx.download(dptr, exp_tr.shape)
+        assert (ob.from_monty(tr) == exp_tr).all()
+        assert list(ob.from_monty(lcs)) == exp_lcs
         _, perm_pd = ctx.commit([tr], [MONTY_ONE], 1)
         kw["perm"] = (perm_pd, 0)
         okw["perm_q"] = _natural(perm_pd.lde(0))
@@ -106,3 +113,24 @@ def test_invalid_trace_is_rejected(be):
     ok, why = su.verify_shard(sp, ordered, start, 1, 4, 4)
     assert not ok and "constraint identity" in why
     pd.free()
+
+
+@pytest.mark.parametrize("be,log_n", [pytest.param("emu", 11, id="emu-2^11"),
+                                      pytest.param("gpu", 11, id="gpu-2^11", marks=pytest.mark.gpu),
+                                      pytest.param("gpu", 16, id="gpu-2^16", marks=pytest.mark.gpu)])
+def test_permutation_trace_multi_block_scan(be, log_n):
+    """running-sum column over more rows than one scan block (1024): block scan + totals + add"""
+    from oracle import logup
+    ctx = _backend(be)
+    chip = su.lookup_chip(log_n, seed=9)
+    air = su.AIRS[chip.air]
+    chal = su.M(np.arange(20, 28).reshape(2, 4))
+    p_c, m_c = chip.canon
+    exp_tr, exp_lcs = logup.generate_permutation_trace(air, p_c, m_c, ob.from_monty(chal[0]), ob.from_monty(chal[1]))
+    pp, mp = ctx.upload(chip.preprocessed), ctx.upload(chip.main)
+    dptr, lcs = ctx.permutation_trace(chip.air, pp, mp, 1 << log_n, chal)
+    tr = ctx.download(dptr, exp_tr.shape)
+    for p in (pp, mp, dptr):
+        ctx.dev_free(p)
+    assert (ob.from_monty(tr) == exp_tr).all()
+    assert list(ob.from_monty(lcs)) == exp_lcs

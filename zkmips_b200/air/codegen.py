@@ -87,9 +87,62 @@ def _emit_node(air, n):
     return f"const kb::Ext {v} = kb::ext_neg(kb::ext_sub_base({b}, {a}));"  # a - b
 
 
+def _emit_linear(lf, name):
+    """VirtualPairCol::apply on the local row (base field), Montgomery constants as immediates"""
+    c, terms = lf
+    lines = [f"    uint32_t {name} = 0x{_monty(c):08x}u;"]
+    for (t, col, w) in terms:
+        src = "m" if t == "main" else "p"
+        if w % P == 1:
+            lines.append(f"    {name} = kb::add({name}, __ldg({src} + {col}));")
+        else:
+            lines.append(f"    {name} = kb::add({name}, kb::mul(__ldg({src} + {col}), 0x{_monty(w):08x}u));")
+    return lines
+
+
+def _emit_logup(air):
+    """generate_permutation_trace for one chip: one thread per row (crates/stark/src/permutation.rs:29-69)"""
+    fn = f"logup_{air.name}"
+    lookups = [(l, True) for l in air.sends] + [(l, False) for l in air.receives]
+    width, bs = air.permutation_width, air.batch_size
+    maxv = max(len(l["values"]) for l, _ in lookups)
+    o = [f"__global__ void __launch_bounds__(128) {fn}(logup::Args A) {{",
+         "  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;",
+         "  if (r >= A.h) return;",
+         "  const uint32_t* m = A.main + r * A.wm;",
+         "  const uint32_t* p = A.prep + r * A.wp;",
+         "  const kb::Ext alpha = logup::ld_ext(A.chal);",
+         "  kb::Ext bp[%d];" % max(maxv, 1),
+         "  bp[0] = logup::ld_ext(A.chal + 4);"]
+    for k in range(1, maxv):
+        o.append(f"  bp[{k}] = kb::ext_mul(bp[{k - 1}], bp[0]);")
+    o.append("  kb::Ext total = kb::ext_zero();")
+    for b in range(width - 1):
+        chunk = lookups[b * bs:(b + 1) * bs]
+        n = len(chunk)
+        o.append("  {")
+        o.append(f"    kb::Ext d[{n}];")
+        o.append(f"    uint32_t mu[{n}];")
+        for i, (l, is_send) in enumerate(chunk):
+            o.append(f"    d[{i}] = kb::ext_add_base(alpha, 0x{_monty(l['kind']):08x}u);")
+            for k, lf in enumerate(l["values"]):
+                o += _emit_linear(lf, f"v{i}_{k}")
+                o.append(f"    d[{i}] = kb::ext_add(d[{i}], kb::ext_mul_base(bp[{k}], v{i}_{k}));")
+            o += _emit_linear(l["mult"], f"mm{i}")
+            o.append(f"    mu[{i}] = {'mm%d' % i if is_send else 'kb::neg(mm%d)' % i};")
+        o.append(f"    kb::Ext e = logup::batch_entry<{n}>(d, mu);")
+        o.append(f"    logup::st_ext(A.perm + r * A.wq + {4 * b}, e);")
+        o.append("    total = kb::ext_add(total, e);")
+        o.append("  }")
+    o.append("  logup::st_ext(A.rowsum + 4 * r, total);")
+    o.append("}")
+    o.append("")
+    return fn, o
+
+
 def generate(airs):
-    out = ["// GENERATED by zkmips_b200/air/codegen.py -- do not edit.", "#pragma once", '#include "../quotient.cuh"', "",
-           "namespace quotgen {", ""]
+    out = ["// GENERATED by zkmips_b200/air/codegen.py -- do not edit.", "#pragma once", '#include "../quotient.cuh"',
+           '#include "../logup.cuh"', "", "namespace quotgen {", ""]
     table = []
     for ai, air in enumerate(airs):
         parts = _parts(air)
@@ -116,16 +169,23 @@ def generate(airs):
             out.append(f"  quot::epilogue(A, i, R, acc, {'true' if pi == 0 else 'false'});")
             out.append("}")
             out.append("")
-        table.append((air, names))
+        lfn = "nullptr"
+        if air.sends or air.receives:
+            lfn, code = _emit_logup(air)
+            out += code
+        table.append((air, names, lfn))
     out.append("struct Entry {")
     out.append("  const char* name;")
     out.append("  uint32_t main_w, prep_w, perm_w, n_pv, n_chal, n_constraints, max_degree, n_parts;")
-    out.append("  void (*parts[%d])(quot::Args);" % max(1, max(len(n) for _, n in table)))
+    out.append("  uint32_t n_lookups;")
+    out.append("  void (*logup)(logup::Args);")
+    out.append("  void (*parts[%d])(quot::Args);" % max(1, max(len(n) for _, n, _ in table)))
     out.append("};")
     out.append("static const Entry AIRS[] = {")
-    for air, names in table:
+    for air, names, lfn in table:
         out.append(f'  {{"{air.name}", {air.main_width}, {air.prep_width}, {air.perm_width}, {air.num_public_values}, '
-                   f"{air.num_challenges}, {air.num_constraints}, {air.max_degree()}, {len(names)}, {{{', '.join(names)}}}}},")
+                   f"{air.num_challenges}, {air.num_constraints}, {air.max_degree()}, {len(names)}, "
+                   f"{len(air.sends) + len(air.receives)}, {lfn}, {{{', '.join(names)}}}}},")
     out.append("};")
     out.append(f"static const int NUM_AIRS = {len(table)};")
     out.append("")

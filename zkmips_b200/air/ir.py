@@ -69,6 +69,12 @@ class Air:
         self.types = []   # 'b' / 'e'
         self.constraints = []  # node ids, emission order
         self._memo = {}
+        # LogUp lookups (crates/stark/src/lookup/lookup.rs:8-19), Local scope: dicts
+        #   {"kind": argument_index, "values": [linear form...], "mult": linear form}
+        # a linear form is (constant, [(table 'main'|'prep', column, weight), ...]) = p3 VirtualPairCol
+        self.sends, self.receives = [], []
+        self.batch_size = 2  # 2^log_quotient_degree (crates/stark/src/chip.rs:173-175)
+        self.lookups_finalized = False
 
     # ---- node construction with hash-consing
     def _node(self, key, ty):
@@ -109,13 +115,54 @@ class Air:
         ty = "e" if "e" in (self.types[ia], self.types[ib]) else "b"
         return self._node((kind, ia, ib), ty)
 
+    # ---- VirtualPairCol extraction: an Expr that is affine in the LOCAL row's columns
+    def linear_form(self, e):
+        def walk(nid):
+            n = self.nodes[nid]
+            k = n[0]
+            if k == "const":
+                return n[1], {}
+            if k in ("main", "prep"):
+                if n[1] != 0:
+                    raise ValueError("lookup values may only use the local row")
+                return 0, {(k, n[2]): 1}
+            if k == "neg":
+                c, t = walk(n[1])
+                return (-c) % P, {kk: (-v) % P for kk, v in t.items()}
+            if k in ("add", "sub"):
+                ca, ta = walk(n[1])
+                cb, tb = walk(n[2])
+                sg = 1 if k == "add" else -1
+                out = dict(ta)
+                for kk, v in tb.items():
+                    out[kk] = (out.get(kk, 0) + sg * v) % P
+                return (ca + sg * cb) % P, out
+            if k == "mul":
+                ca, ta = walk(n[1])
+                cb, tb = walk(n[2])
+                if ta and tb:
+                    raise ValueError("lookup values must be linear in the trace columns")
+                if not ta:
+                    return ca * cb % P, {kk: v * ca % P for kk, v in tb.items()}
+                return ca * cb % P, {kk: v * cb % P for kk, v in ta.items()}
+            raise ValueError(f"node kind {k} is not allowed in a lookup value")
+        c, terms = walk(e.id)
+        return (c % P, sorted((t, col, w) for (t, col), w in terms.items() if w % P))
+
+    @property
+    def permutation_width(self):
+        """local_permutation_trace_width (crates/stark/src/permutation.rs:18-23), in extension columns"""
+        nl = len(self.sends) + len(self.receives)
+        return 0 if nl == 0 else -(-nl // self.batch_size) + 1
+
     # ---- serialisation (the format a Rust-side recording builder would emit)
     def to_json(self):
         return json.dumps({
             "name": self.name, "main_width": self.main_width, "prep_width": self.prep_width,
             "perm_width": self.perm_width, "num_public_values": self.num_public_values,
             "num_challenges": self.num_challenges, "nodes": [list(n) for n in self.nodes],
-            "constraints": self.constraints})
+            "constraints": self.constraints, "sends": self.sends, "receives": self.receives,
+            "batch_size": self.batch_size})
 
     @classmethod
     def from_json(cls, text):
@@ -133,6 +180,12 @@ class Air:
             a.nodes.append(n)
             a.types.append(ty)
         a.constraints = list(d["constraints"])
+        fix = lambda lf: (lf[0], [tuple(t) for t in lf[1]])
+        for key in ("sends", "receives"):
+            setattr(a, key, [{"kind": l["kind"], "values": [fix(v) for v in l["values"]], "mult": fix(l["mult"])}
+                             for l in d.get(key, [])])
+        a.batch_size = d.get("batch_size", 2)
+        a.lookups_finalized = bool(a.sends or a.receives)
         return a
 
     @property
@@ -246,3 +299,66 @@ class AirBuilder:
 
     assert_zero_ext = assert_zero
     assert_eq_ext = assert_eq
+
+    # --- LogUp lookups (ZKMAirBuilder::send / receive -> Lookup, crates/stark/src/lookup/builder.rs)
+    def send(self, kind, values, multiplicity):
+        self.air.sends.append({"kind": int(kind), "values": [self.air.linear_form(self._lift(v)) for v in values],
+                               "mult": self.air.linear_form(self._lift(multiplicity))})
+
+    def receive(self, kind, values, multiplicity):
+        self.air.receives.append({"kind": int(kind), "values": [self.air.linear_form(self._lift(v)) for v in values],
+                                  "mult": self.air.linear_form(self._lift(multiplicity))})
+
+    def _apply(self, lf):
+        """VirtualPairCol::apply on the local row"""
+        c, terms = lf
+        acc = self.air.const(c)
+        for (t, col, w) in terms:
+            acc = acc + self.air.leaf(t, 0, col) * w
+        return acc
+
+    def eval_permutation_constraints(self, batch_size=2):
+        """Transliteration of eval_permutation_constraints (crates/stark/src/permutation.rs:205-347), appended
+        after the chip's own constraints exactly as Chip::eval does (crates/stark/src/chip.rs:259-270).  Local
+        scope only (the global-scope rows tie main columns to the septic digest and need no permutation trace)."""
+        air = self.air
+        assert not air.lookups_finalized
+        air.lookups_finalized = True
+        air.batch_size = batch_size
+        lookups = [(l, True) for l in air.sends] + [(l, False) for l in air.receives]
+        if not lookups:
+            return
+        air.perm_width = air.permutation_width
+        perm, permn = self.permutation().local(), self.permutation().next()
+        alpha, beta = self.permutation_randomness()[:2]
+        lcs = self.local_cumulative_sum()
+        width = air.perm_width
+        for b in range(width - 1):
+            chunk = lookups[b * batch_size:(b + 1) * batch_size]
+            rlcs, mults = [], []
+            for l, is_send in chunk:
+                rlc = alpha + l["kind"]           # betas.next() == 1 multiplies the argument index
+                bp = beta
+                for lf in l["values"]:
+                    rlc = rlc + bp * self._apply(lf)
+                    bp = bp * beta
+                rlcs.append(rlc)
+                m = self._apply(l["mult"])
+                mults.append(m if is_send else -m)
+            product, numerator = None, None
+            for i, (m, rlc) in enumerate(zip(mults, rlcs)):
+                product = rlc if product is None else product * rlc
+                others = None
+                for j, o in enumerate(rlcs):
+                    if j != i:
+                        others = o if others is None else others * o
+                term = m if others is None else others * m
+                numerator = term if numerator is None else numerator + term
+            self.assert_eq_ext(product * perm[b], numerator)
+        sum_local, sum_next = perm[0], permn[0]
+        for b in range(1, width - 1):
+            sum_local, sum_next = sum_local + perm[b], sum_next + permn[b]
+        phi_local, phi_next = perm[width - 1], permn[width - 1]
+        self.when_first_row().assert_eq_ext(phi_local, sum_local)
+        self.when_transition().assert_eq_ext(phi_next - phi_local, sum_next)
+        self.when_last_row().assert_eq_ext(phi_local, lcs)

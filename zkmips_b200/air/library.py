@@ -41,33 +41,21 @@ def wide_bitwise(width=256, name=None):
 
 
 def lookup_pair():
-    """Small chip with preprocessed columns and a LogUp-style permutation argument, exercising every
-    extension-field node kind the reference's eval_permutation_constraints uses
-    (crates/stark/src/permutation.rs:205-347): one send and one receive per row batched in one column,
-        perm[0] * (alpha + v0 + beta*v1) * (alpha + u0 + beta*u1) = m_s * (alpha + u..) - m_r * (alpha + v..)
-        phi' - phi = perm'[0] (transition), phi[first] = perm[0], phi[last] = local cumulative sum."""
-    air = Air("lookup_pair", main_width=5, prep_width=2, perm_width=2, num_public_values=1)
+    """Small chip with preprocessed columns and LogUp lookups, in the shape of Ziren's chips: its own
+    constraints, then three lookups (two sends, one receive; batch size 2 -> two batch columns + the running
+    sum) whose permutation constraints are appended by eval_permutation_constraints.
+    Columns: main (a, b, c, s, m), preprocessed (p0, p1)."""
+    air = Air("lookup_pair", main_width=5, prep_width=2, perm_width=0, num_public_values=1)
     b = AirBuilder(air)
     m, mn = b.main().local(), b.main().next()
     p = b.preprocessed().local()
-    perm, permn = b.permutation().local(), b.permutation().next()
-    alpha, beta = b.permutation_randomness()
-    lcs = b.local_cumulative_sum()
-    gcs = b.global_cumulative_sum()
-    # main constraints: m2 = m0 * m1 + p0 ; m3 boolean ; next.m0 = m0 + pv0 on transitions
     b.assert_eq(m[2], m[0] * m[1] + p[0])
     b.assert_bool(m[3])
     b.when_transition().assert_eq(mn[0], m[0] + b.public_values()[0])
-    # LogUp batch: send (m0, m1) with multiplicity m3, receive (p0, p1) with multiplicity m4
-    send = alpha + m[0] + beta * m[1]
-    recv = alpha + p[0] + beta * p[1]
-    b.assert_zero_ext(perm[0] * send * recv - (m[3] * recv - m[4] * send))
-    phi, phin = perm[1], permn[1]
-    b.when_transition().assert_eq_ext(phin - phi, permn[0])
-    b.when_first_row().assert_eq_ext(phi, perm[0])
-    b.when_last_row().assert_eq_ext(phi, lcs)
-    # global cumulative sum is only observed by this synthetic chip: tie coordinate 0 to a main column on the last row
-    b.when_last_row().assert_eq(m[4] * gcs[0], m[4] * gcs[0])
+    b.send(4, [m[0], m[1] + 2 * p[1], 7], m[3])            # Byte-kind lookup with a linear combination and a constant
+    b.send(1, [m[2] - p[0]], m[4])                         # Memory-kind
+    b.receive(4, [p[0], p[1], m[0] + 1], m[3] + m[4])      # Byte-kind receive
+    b.eval_permutation_constraints(batch_size=2)
     return air
 
 

@@ -23,6 +23,7 @@ extern "C" int32_t zk_air_info(int32_t id, zk_air_desc* out) {
   out->num_constraints = e.n_constraints;
   out->max_degree = e.max_degree;
   out->num_kernels = e.n_parts;
+  out->num_lookups = e.n_lookups;
   return ZK_OK;
 }
 
@@ -101,5 +102,53 @@ extern "C" int32_t zk_quotient(zk_ctx* c, int32_t air_id, const zk_pdata* prep, 
   if ((rc = dev_free(c, d_in))) return rc;
   if ((rc = dev_free(c, d_ap))) return rc;
   *out_chunks = (zk_dptr)d_out;
+  return ZK_OK;
+}
+
+// generate_permutation_trace on the device (crates/stark/src/permutation.rs:102-196; call site
+// crates/stark/src/prover.rs:341-364).  Traces are natural-order device matrices (zk_pdata_trace).
+extern "C" int32_t zk_permutation_trace(zk_ctx* c, int32_t air_id, zk_dptr prep_trace, zk_dptr main_trace, uint64_t height,
+                                        const uint32_t perm_challenges[8], zk_dptr* out_trace, uint32_t local_cumsum[4]) {
+  if (!c || !main_trace || !perm_challenges || !out_trace || !local_cumsum) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (air_id < 0 || air_id >= quotgen::NUM_AIRS) return zk_fail(ZK_ERR_ARG, "unknown air id");
+  const quotgen::Entry& e = quotgen::AIRS[air_id];
+  if (!e.logup) return zk_fail(ZK_ERR_ARG, "this AIR has no lookups");
+  if (e.prep_w && !prep_trace) return zk_fail(ZK_ERR_ARG, "preprocessed trace is required by this AIR");
+  if (height == 0 || (height & (height - 1))) return zk_fail(ZK_ERR_ARG, "height must be a power of two");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  ProfScope ps(c, "permutation_trace");
+  logup::Args A;
+  A.prep = (const uint32_t*)prep_trace;
+  A.main = (const uint32_t*)main_trace;
+  A.wp = e.prep_w;
+  A.wm = e.main_w;
+  A.wq = 4 * e.perm_w;
+  A.h = height;
+  uint32_t nblocks = (uint32_t)((height + logup::SCAN_T - 1) / logup::SCAN_T);
+  uint32_t *d_chal = nullptr, *d_perm = nullptr, *d_rowsum = nullptr, *d_bsum = nullptr;
+  int32_t rc;
+  if ((rc = dev_alloc(c, 48, (void**)&d_chal))) return rc;  // alpha, beta, [last]
+  if ((rc = dev_alloc(c, height * A.wq * 4ull, (void**)&d_perm))) return rc;
+  if ((rc = dev_alloc(c, height * 16, (void**)&d_rowsum))) return rc;
+  if ((rc = dev_alloc(c, nblocks * 16ull, (void**)&d_bsum))) return rc;
+  CK(cudaMemcpyAsync(d_chal, perm_challenges, 32, cudaMemcpyHostToDevice, c->stream));
+  A.chal = d_chal;
+  A.perm = d_perm;
+  A.rowsum = d_rowsum;
+  auto kfn = e.logup;
+  ZK_LAUNCH(kfn, (unsigned)((height + 127) / 128), 128, 0, c->stream, A);
+  const uint32_t col4 = A.wq - 4;
+  ZK_LAUNCH_COOP(logup::scan_block_kernel, nblocks, logup::SCAN_T, 0, c->stream, d_rowsum, height, d_perm, A.wq, col4, d_bsum);
+  ZK_LAUNCH_COOP(logup::scan_totals_kernel, 1, logup::SCAN_T, 0, c->stream, d_bsum, nblocks);
+  ZK_LAUNCH(logup::scan_add_kernel, nblocks, logup::SCAN_T, 0, c->stream, d_perm, height, A.wq, col4, d_bsum, d_chal + 8);
+  CK(cudaGetLastError());
+  c->launches += 4;
+  CK(cudaMemcpyAsync(local_cumsum, d_chal + 8, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  dev_free(c, d_chal);
+  dev_free(c, d_rowsum);
+  dev_free(c, d_bsum);
+  *out_trace = (zk_dptr)d_perm;
   return ZK_OK;
 }

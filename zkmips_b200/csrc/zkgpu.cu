@@ -67,6 +67,10 @@ static int32_t ctx_init(zk_ctx* c) {
     int v = atoi(e);
     if (v >= 16 && v % 16 == 0) c->slab_cols = (uint32_t)v;
   }
+  if (const char* e = getenv("ZK_SLAB_MB")) {
+    int v = atoi(e);
+    if (v >= 1) c->slab_bytes = (uint64_t)v << 20;
+  }
   if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -321,13 +325,19 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
 // buffer (in-place inverse transform), so no full-size staging copy of the trace exists on the device.
 // When `leaves` is non-null the rows of the LDE are hashed slab by slab (w must be a multiple of 8).
 static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                               uint32_t* out, uint32_t* leaves) {
+                               uint32_t* out, uint32_t* leaves, uint32_t* keep_trace) {
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
   if (w == 0) return ZK_OK;
   if (!host) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
   const uint64_t H = h << log_blowup;
+  // slab width: a fixed number of columns when ZK_SLAB_COLS is set, otherwise as many columns as make
+  // ~slab_bytes (a multiple of 16 columns, >= 32): short-and-wide traces must not be cut into tiny slabs
   uint32_t slab = c->slab_cols;
+  if (slab == 0) {
+    uint64_t cols = c->slab_bytes / (h * 4);
+    slab = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(32, cols / 16 * 16), 1u << 20);
+  }
   if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
   const uint32_t nslab = (w + slab - 1) / slab;
   std::vector<ntt::CosetScale> scales;
@@ -354,6 +364,9 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
                          c->copy_stream));
     CK(cudaEventRecord(up_done[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, up_done[b], 0));
+    if (keep_trace)  // retain the slab before the in-place inverse transform overwrites it
+      CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf[b], (size_t)nc * 4, (size_t)nc * 4, h, cudaMemcpyDeviceToDevice,
+                           c->stream));
     ntt::Cols sl{buf[b], nc, 0};
     rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
     if (rc) break;
@@ -514,6 +527,8 @@ void pdata_release(zk_pdata* pd) {
   cudaSetDevice(c->device);
   for (uint32_t i = 0; i < pd->mats.size(); i++)
     if (pd->owned[i] && pd->mats[i]) cudaFreeAsync(pd->mats[i], c->stream);
+  for (uint32_t i = 0; i < pd->traces.size(); i++)
+    if (pd->trace_owned[i] && pd->traces[i]) cudaFreeAsync(pd->traces[i], c->stream);
   if (pd->digests) cudaFreeAsync(pd->digests, c->stream);
   if (pd->d_desc) cudaFreeAsync(pd->d_desc, c->stream);
   delete pd;
@@ -531,6 +546,8 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
   pd->widths.assign(widths, widths + n_mats);
   pd->mats.assign(n_mats, nullptr);
   pd->owned.assign(n_mats, false);
+  pd->traces.assign(n_mats, nullptr);
+  pd->trace_owned.assign(n_mats, false);
   int32_t rc = ZK_OK;
   bool leaves_done = false;
   if (do_lde) {
@@ -550,12 +567,23 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
         ntall++;
         solo = (int)i;
       }
-    if (!(src_is_host && ntall == 1 && widths[solo] > 0 && widths[solo] % 8 == 0 && c->slab_cols % 8 == 0)) solo = -1;
+    if (!(src_is_host && ntall == 1 && widths[solo] > 0 && widths[solo] % 8 == 0)) solo = -1;
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
       uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
+      uint32_t* keep = nullptr;
+      if (c->keep_traces) {
+        if (src_is_host) {
+          rc = dev_alloc(c, heights[i] * widths[i] * 4ull, (void**)&keep);
+          if (rc) break;
+          pd->traces[i] = keep;
+          pd->trace_owned[i] = true;
+        } else {
+          pd->traces[i] = const_cast<uint32_t*>(src[i]);  // borrowed: the caller keeps it alive
+        }
+      }
       if (src_is_host)
         rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i],
-                             (int)i == solo ? pd->digests : nullptr);
+                             (int)i == solo ? pd->digests : nullptr, keep);
       else
         rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
     }
@@ -664,6 +692,15 @@ extern "C" int32_t zk_pdata_root(const zk_pdata* pd, uint32_t root[8]) {
   return ZK_OK;
 }
 extern "C" zk_dptr zk_pdata_lde(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? (zk_dptr)pd->mats[i] : 0; }
+extern "C" zk_dptr zk_pdata_trace(const zk_pdata* pd, uint32_t i) {
+  return pd && i < pd->traces.size() ? (zk_dptr)pd->traces[i] : 0;
+}
+extern "C" int32_t zk_ctx_keep_traces(zk_ctx* c, int32_t enable) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "ctx is null");
+  std::lock_guard<std::mutex> g(c->mu);
+  c->keep_traces = enable != 0;
+  return ZK_OK;
+}
 extern "C" int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* out) {
   if (!pd || i >= pd->n || !out) return zk_fail(ZK_ERR_ARG, "bad argument");
   zk_ctx* c = pd->ctx;

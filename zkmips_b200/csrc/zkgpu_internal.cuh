@@ -28,11 +28,13 @@ struct zk_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
-  uint32_t slab_cols = 32;              // columns per slab of the streaming commit (multiple of 16; env ZK_SLAB_COLS)
+  uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
+  uint64_t slab_bytes = 128ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
   uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
+  bool keep_traces = false;
   bool prof = false;
   struct Rec {
     std::string name;
@@ -69,6 +71,8 @@ struct zk_pdata {
   std::vector<uint32_t> widths;
   std::vector<uint32_t*> mats;    // device
   std::vector<bool> owned;
+  std::vector<uint32_t*> traces;  // retained input traces (zk_ctx_keep_traces), else empty
+  std::vector<bool> trace_owned;
   std::vector<uint32_t> order;    // indices by height descending, stable
   uint32_t log_max = 0;
   uint32_t sum_w = 0;

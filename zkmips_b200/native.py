@@ -57,6 +57,9 @@ PROTOTYPES = {
     "zk_air_name": (C.c_char_p, [i32]),
     "zk_air_find": (i32, [C.c_char_p]),
     "zk_air_info": (i32, [i32, vp]),
+    "zk_permutation_trace": (i32, [vp, i32, u64, u64, u64, u32p, u64p, u32p]),
+    "zk_ctx_keep_traces": (i32, [vp, i32]),
+    "zk_pdata_trace": (u64, [vp, u32]),
     "zk_quotient": (i32, [vp, i32, vp, u32, vp, u32, vp, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p, u64p]),
     "zk_challenger_init": (i32, [vp]),
     "zk_challenger_observe": (i32, [vp, vp, u32p, u32]),
@@ -148,6 +151,9 @@ class PData:
 
     def lde_ptr(self, i):
         return self.d.zk_pdata_lde(self.h, i)
+
+    def trace_ptr(self, i):
+        return self.d.zk_pdata_trace(self.h, i)
 
     def lde(self, i):
         out = np.empty((self.height(i), self.width(i)), np.uint32)
@@ -311,6 +317,32 @@ class Ctx:
             _p32(ch) if ch is not None else None, _p32(pv) if pv.size else None, pv.size,
             _p32(lc) if lc is not None else None, _p32(gc) if gc is not None else None, C.byref(out)))
         return out.value
+
+    def keep_traces(self, on=True):
+        self.lib.check(self.d.zk_ctx_keep_traces(self.h, 1 if on else 0))
+
+    def air_info(self, air_name):
+        aid = self.d.zk_air_find(air_name.encode())
+        if aid < 0:
+            raise ZkError(f"unknown AIR {air_name}")
+        buf = (u32 * 9)()
+        self.lib.check(self.d.zk_air_info(aid, C.cast(buf, vp)))
+        keys = ["main_width", "prep_width", "perm_width", "num_public_values", "num_challenges", "num_constraints",
+                "max_degree", "num_kernels", "num_lookups"]
+        return dict(zip(keys, list(buf)))
+
+    def permutation_trace(self, air_name, prep_trace, main_trace, height, perm_challenges):
+        """generate_permutation_trace on the device.  Returns (device pointer of the h x 4*perm_width matrix,
+        local cumulative sum[4])."""
+        aid = self.d.zk_air_find(air_name.encode())
+        if aid < 0:
+            raise ZkError(f"unknown AIR {air_name}")
+        ch = _arr(perm_challenges, np.uint32).reshape(-1)
+        out = u64()
+        lcs = np.empty(4, np.uint32)
+        self.lib.check(self.d.zk_permutation_trace(self.h, aid, prep_trace or 0, main_trace, height, _p32(ch),
+                                                   C.byref(out), _p32(lcs)))
+        return out.value, lcs
 
     def download(self, dptr, shape):
         out = np.empty(shape, np.uint32)

@@ -40,8 +40,10 @@ class Chip:
     air: str
     main: np.ndarray
     preprocessed: Optional[np.ndarray] = None
+    # host-side permutation trace generator (only for chips whose AIR was not compiled with lookups):
     # (perm_challenges (2,4) Montgomery) -> (permutation trace flattened to base (h, 4*perm_width), local_cumsum[4])
     permutation: Optional[Callable] = None
+    has_lookups: bool = False  # LogUp trace generated on the device (zk_permutation_trace)
     public_values: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint32))
     global_cumsum: np.ndarray = field(default_factory=lambda: np.zeros(14, np.uint32))
     log_quotient_degree: int = 1
@@ -69,6 +71,7 @@ class ShardProof:
 class GpuShardProver:
     def __init__(self, ctx, log_blowup=1, num_queries=84, pow_bits=16):
         self.ctx, self.log_blowup, self.num_queries, self.pow_bits = ctx, log_blowup, num_queries, pow_bits
+        ctx.keep_traces(True)  # LogUp reads the traces themselves between the commits
         self.phase_ms = {}  # host wall clock per phase of the last commit/open (each phase ends synchronised)
 
     def _tick(self, name, t0):
@@ -110,16 +113,28 @@ class GpuShardProver:
                 pre_idx[c.name] = len(pre_idx)
         challenger.observe(main_root)                                   # prover.rs:323
         perm_challenges = challenger.sample_ext(2)                       # prover.rs:326-329
-        perm_chips = [c for c in chips if c.permutation is not None]
+        for c in chips:
+            c.has_lookups = ctx.air_info(c.air)["num_lookups"] > 0
+        perm_chips = [c for c in chips if c.permutation is not None or c.has_lookups]
         perm_pd, perm_root, perm_idx, cumsums = None, None, {}, []
         if perm_chips:
-            traces = []
-            for c in perm_chips:
-                tr, lcs = c.permutation(perm_challenges)                # prover.rs:341-364 (host side today)
-                perm_idx[c.name] = len(traces)
-                traces.append(tr)
+            ptrs, shapes = [], []
+            for c in perm_chips:                                         # prover.rs:341-364
+                if c.has_lookups:
+                    ptr, lcs = ctx.permutation_trace(
+                        c.air, prep_pd.trace_ptr(pre_idx[c.name]) if c.name in pre_idx else 0,
+                        main_pd.trace_ptr(chips.index(c)), c.main.shape[0], perm_challenges)
+                    wq = 4 * ctx.air_info(c.air)["perm_width"]
+                else:
+                    tr, lcs = c.permutation(perm_challenges)
+                    ptr, wq = ctx.upload(tr), tr.shape[1]
+                perm_idx[c.name] = len(ptrs)
+                ptrs.append(ptr)
+                shapes.append((c.main.shape[0], wq))
                 cumsums.append(np.asarray(lcs, np.uint32))
-            perm_root, perm_pd = ctx.commit(traces, [MONTY_ONE] * len(traces), self.log_blowup)   # prover.rs:401-403
+            perm_root, perm_pd = ctx.commit_dev(ptrs, shapes, [MONTY_ONE] * len(ptrs), self.log_blowup)  # prover.rs:401-403
+            for ptr in ptrs:
+                ctx.dev_free(ptr)
             challenger.observe(perm_root)                                # prover.rs:406
             for c, lcs in zip(perm_chips, cumsums):                      # prover.rs:407-413
                 challenger.observe(lcs)
