@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="skip the shard-prove leg (commit + quotient + open)")
     ap.add_argument("--shard-steps", type=int, default=3)
+    ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -265,6 +266,12 @@ def main():
     lib = native.load()
     stream = torch.cuda.current_stream()
     ctx = lib.ctx_create(local, stream=stream.cuda_stream)
+    if args.shard_only:
+        res = shard_leg(ctx, torch, dist, world, rank, args)
+        if rank == 0:
+            print(json.dumps({"shard_prove": res}))
+        ctx.destroy()
+        return
 
     # synthetic shard of this rank: pinned host copy (e2e path) and a device-resident copy (value path)
     host = torch.from_numpy(synth_trace(log_rows, cols, rank).view(np.int32)).pin_memory()

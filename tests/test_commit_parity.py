@@ -181,6 +181,8 @@ def test_streaming_commit_multi_slab(be, monkeypatch):
         _check_commit(ctx, [_mont(32, 24, seed=32)], [one], 2)
         _check_commit(ctx, [_mont(64, 35, seed=33)], [one], 1)          # width not a multiple of 8: LDE streamed only
         _check_commit(ctx, [_mont(64, 48, seed=34), _mont(16, 20, seed=35), _mont(64, 3, seed=36)], [one] * 3, 1)
+        # single-matrix height classes: leaves AND injected digests hashed while streaming
+        _check_commit(ctx, [_mont(128, 32, seed=37), _mont(32, 24, seed=38), _mont(8, 40, seed=39)], [one] * 3, 1)
     finally:
         ctx.destroy()
 

@@ -465,9 +465,14 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, b
       take_group(len, g);
       const uint32_t* injp = nullptr;
       if (!g.empty()) {
-        if (!inj && (rc = dev_alloc(c, (hmax >> 1) * 32, (void**)&inj))) return rc;
-        if ((rc = hash_group(c, g, len, inj))) return rc;
-        injp = inj;
+        auto it = pd->class_digests.find(len);
+        if (it != pd->class_digests.end()) {
+          injp = it->second;  // already hashed while the LDE streamed in
+        } else {
+          if (!inj && (rc = dev_alloc(c, (hmax >> 1) * 32, (void**)&inj))) return rc;
+          if ((rc = hash_group(c, g, len, inj))) return rc;
+          injp = inj;
+        }
       }
       ZK_LAUNCH(mk::compress_layer, (unsigned)((len + 255) / 256), 256, 0, c->stream, 
           pd->digests + pd->layer_off[l - 1], pd->digests + pd->layer_off[l], len, injp);
@@ -476,6 +481,8 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, b
     }
   }
   if (inj && (rc = dev_free(c, inj))) return rc;
+  for (auto& kv : pd->class_digests) dev_free(c, kv.second);
+  pd->class_digests.clear();
   if (with_open_desc) {
     // open_batch descriptors
     std::vector<zk_open_desc> od(n);
@@ -529,6 +536,7 @@ void pdata_release(zk_pdata* pd) {
     if (pd->owned[i] && pd->mats[i]) cudaFreeAsync(pd->mats[i], c->stream);
   for (uint32_t i = 0; i < pd->traces.size(); i++)
     if (pd->trace_owned[i] && pd->traces[i]) cudaFreeAsync(pd->traces[i], c->stream);
+  for (auto& kv : pd->class_digests) cudaFreeAsync(kv.second, c->stream);
   if (pd->digests) cudaFreeAsync(pd->digests, c->stream);
   if (pd->d_desc) cudaFreeAsync(pd->d_desc, c->stream);
   delete pd;
@@ -560,14 +568,21 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       if (rc == ZK_OK && domain_shifts[i] == 0) rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
     }
     if (rc == ZK_OK) rc = mmcs_alloc(c, pd);
-    // the leaf sponge can be streamed with the LDE when one matrix alone forms the tallest class
-    int solo = -1, ntall = 0;
-    for (uint32_t i = 0; i < n_mats; i++)
+    // the row sponge of a height class can be streamed with the LDE when ONE matrix forms the class
+    // (leaf layer for the tallest class, injected digests for the others)
+    std::map<uint64_t, int> members;
+    for (uint32_t i = 0; i < n_mats; i++) members[pd->heights[i]]++;
+    std::vector<uint32_t*> stream_digests(n_mats, nullptr);
+    for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
+      if (!(src_is_host && members[pd->heights[i]] == 1 && widths[i] > 0 && widths[i] % 8 == 0)) continue;
       if (pd->heights[i] == hmax) {
-        ntall++;
-        solo = (int)i;
+        stream_digests[i] = pd->digests;
+        leaves_done = true;
+      } else {
+        rc = dev_alloc(c, pd->heights[i] * 32, (void**)&stream_digests[i]);
+        if (rc == ZK_OK) pd->class_digests[pd->heights[i]] = stream_digests[i];
       }
-    if (!(src_is_host && ntall == 1 && widths[solo] > 0 && widths[solo] % 8 == 0)) solo = -1;
+    }
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
       uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
       uint32_t* keep = nullptr;
@@ -582,12 +597,10 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
         }
       }
       if (src_is_host)
-        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i],
-                             (int)i == solo ? pd->digests : nullptr, keep);
+        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], stream_digests[i], keep);
       else
         rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
     }
-    leaves_done = solo >= 0;
   } else {
     for (uint32_t i = 0; i < n_mats; i++) {
       pd->heights[i] = heights[i];

@@ -1,6 +1,7 @@
 // zkgpu_internal.cuh -- shared declarations of the libzkgpu translation units (not part of the ABI).
 #pragma once
 #include <algorithm>
+#include <map>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -71,6 +72,7 @@ struct zk_pdata {
   std::vector<uint32_t> widths;
   std::vector<uint32_t*> mats;    // device
   std::vector<bool> owned;
+  std::map<uint64_t, uint32_t*> class_digests;  // row digests of a height class hashed while its LDE streamed in
   std::vector<uint32_t*> traces;  // retained input traces (zk_ctx_keep_traces), else empty
   std::vector<bool> trace_owned;
   std::vector<uint32_t> order;    // indices by height descending, stable
