@@ -97,7 +97,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   Scratch sc(c);
   ProfScope ps_all(c, "pcs_open");
 
-  uint32_t *d_proof, *d_pts, *d_alpha, *d_apow, *d_status, *d_found, *d_beta, *d_red, *d_aoff, *d_rowred, *d_wts, *d_partial;
+  uint32_t *d_proof, *d_pts, *d_alpha, *d_apow, *d_apow_split, *d_status, *d_found, *d_beta, *d_red, *d_aoff, *d_rowred, *d_wts, *d_partial;
   uint64_t* d_idx;
   fri::Chal* d_ch;
   uint64_t Hmax = 1ull << S.log_max;
@@ -106,13 +106,15 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   RC(sc.alloc(&d_pts, (uint64_t)std::max(total_pts, 1u) * 16));
   RC(sc.alloc(&d_alpha, 16));
   RC(sc.alloc(&d_apow, (uint64_t)std::max(S.max_w, 1u) * 16));
+  RC(sc.alloc(&d_apow_split, (uint64_t)std::max(S.max_w, 1u) * 32));
+  if (S.max_w > 65536) return zk_fail(ZK_ERR_ARG, "matrix width above 65536 is not supported by the opening reduction");
   RC(sc.alloc(&d_status, 4));
   RC(sc.alloc(&d_found, 4));
   RC(sc.alloc(&d_beta, 16));
   RC(sc.alloc(&d_red, 32));
   RC(sc.alloc(&d_aoff, 32));
   RC(sc.alloc(&d_rowred, Hmax * 16));
-  RC(sc.alloc(&d_wts, 2 * (Hmax >> log_blowup) * 16));
+  RC(sc.alloc(&d_wts, 2 * (Hmax >> log_blowup) * 32));
   RC(sc.alloc(&d_partial, (uint64_t)nchunks_max * 2 * std::max(S.max_w, 1u) * 16));
   RC(sc.alloc(&d_idx, (uint64_t)std::max(num_queries, 1u) * 8));
   RC(sc.alloc(&d_ch, sizeof(fri::Chal)));
@@ -123,7 +125,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
 
   // batch-combination challenge alpha and its powers
   ZK_LAUNCH(fri::ch_sample_ext_kernel, 1, 1, 0, st, d_ch, d_alpha, 1u);
-  if (S.max_w) ZK_LAUNCH(fri::ext_powers_kernel, (S.max_w + 127) / 128, 128, 0, st, d_alpha, d_apow, S.max_w);
+  if (S.max_w) ZK_LAUNCH(fri::ext_powers_kernel, (S.max_w + 127) / 128, 128, 0, st, d_alpha, d_apow, d_apow_split, S.max_w);
   CK(cudaGetLastError());
   c->launches += 2;
 
@@ -154,15 +156,20 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
           continue;
         }
         uint32_t gL = kbh::two_adic_generator(L), gn = kbh::two_adic_generator(n);
-        ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, d_apow, d_rowred);
+        ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, d_apow_split, d_rowred);
         c->launches++;
         for (uint32_t p0 = 0; p0 < n_points[k]; p0 += 2) {
           uint32_t np = std::min(2u, n_points[k] - p0);
           uint64_t N = 1ull << n;
           uint32_t nchunks = (uint32_t)((N + fri::BARY_ROWS - 1) / fri::BARY_ROWS);
-          uint32_t ntile = (w + 31) / 32;
           ZK_LAUNCH(fri::bary_weights_kernel, (unsigned)((N + 255) / 256), 256, 0, st, pt, np, n, gn, d_wts);
-          ZK_LAUNCH_COOP(fri::bary_partial_kernel, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, d_wts, np, d_partial);
+          if ((w & 1u) == 0 && ((uintptr_t)pd->mats[m] % 8) == 0) {
+            auto kfn = fri::bary_partial_kernel<2>;
+            ZK_LAUNCH_COOP(kfn, nchunks * ((w + 63) / 64), 256, 0, st, pd->mats[m], n, w, d_wts, np, d_partial);
+          } else {
+            auto kfn = fri::bary_partial_kernel<1>;
+            ZK_LAUNCH_COOP(kfn, nchunks * ((w + 31) / 32), 256, 0, st, pd->mats[m], n, w, d_wts, np, d_partial);
+          }
           ZK_LAUNCH(fri::bary_final_kernel, (w + 255) / 256, 256, 0, st, d_partial, nchunks, w, n, pt, np, out);
           ZK_LAUNCH_COOP(fri::reduce_ys_kernel, 1, 256, 0, st, out, d_apow, d_alpha, w, np, num_reduced[L], d_red, d_aoff);
           ZK_LAUNCH(fri::ro_accumulate_kernel, (unsigned)((H + 255) / 256), 256, 0, st, ro[L], d_rowred, L, gL, pt, np, d_red,
@@ -213,7 +220,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   {
     ProfScope ps(c, "grind");
     if (inject_witness < 0) {
-      const uint32_t batch = 1u << 22;
+      const uint32_t batch = 1u << 19;  // 8x the expected 2^16 tries: one batch suffices with probability 1 - e^-8
       for (uint64_t base = 0; base < kbh::P; base += batch) {
         ZK_LAUNCH(fri::grind_kernel, batch / 256, 256, 0, st, d_ch, pow_bits, (uint32_t)base, batch, d_found);
         c->launches++;

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "kb31_host.h"
 #include "launch.cuh"
 #include "poseidon2.cuh"
 
@@ -109,11 +110,43 @@ __device__ __forceinline__ void st_ext(uint32_t* p, kb::Ext e) {
   *reinterpret_cast<uint4*>(p) = make_uint4(e.c[0], e.c[1], e.c[2], e.c[3]);
 }
 
+// ---- lazy dot products --------------------------------------------------------------------------------
+// sum_i v_i * w_i with the weights split into 16-bit halves: acc_lo += v*lo(w), acc_hi += v*hi(w) are single
+// IMAD.WIDE accumulations (terms < 2^47, so 2^16 of them fit in 64 bits) instead of a Montgomery product
+// and a modular addition per term.  reduce_acc() returns (acc_hi * 2^16 + acc_lo) * R^-1 mod p, i.e. the sum
+// of the Montgomery products.
+__device__ __forceinline__ uint32_t reduce_acc(uint64_t lo, uint64_t hi) {
+  constexpr uint32_t TWO16 = kbh::to_monty(1u << 16);
+  uint64_t fl = (lo >> 32) * (uint64_t)kb::ONE + (lo & 0xffffffffull);  // == lo (mod p), < 2^58
+  uint64_t fh = (hi >> 32) * (uint64_t)kb::ONE + (hi & 0xffffffffull);
+  return kb::add(kb::mont_reduce64(fl), kb::mul(kb::mont_reduce64(fh), TWO16));
+}
+__device__ __forceinline__ void st_split(uint32_t* p, kb::Ext e) {  // 8 words: low halves, then high halves
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(e.c[0] & 0xffffu, e.c[1] & 0xffffu, e.c[2] & 0xffffu, e.c[3] & 0xffffu);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(e.c[0] >> 16, e.c[1] >> 16, e.c[2] >> 16, e.c[3] >> 16);
+}
+struct Acc4 {  // one extension accumulator: 4 coefficients x (lo, hi)
+  uint64_t lo[4], hi[4];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int k = 0; k < 4; k++) lo[k] = hi[k] = 0;
+  }
+  __device__ __forceinline__ void fma(uint4 wl, uint4 wh, uint32_t v) {
+    lo[0] += (uint64_t)wl.x * v; lo[1] += (uint64_t)wl.y * v; lo[2] += (uint64_t)wl.z * v; lo[3] += (uint64_t)wl.w * v;
+    hi[0] += (uint64_t)wh.x * v; hi[1] += (uint64_t)wh.y * v; hi[2] += (uint64_t)wh.z * v; hi[3] += (uint64_t)wh.w * v;
+  }
+  __device__ __forceinline__ kb::Ext reduce() const {
+    return kb::Ext{{reduce_acc(lo[0], hi[0]), reduce_acc(lo[1], hi[1]), reduce_acc(lo[2], hi[2]), reduce_acc(lo[3], hi[3])}};
+  }
+};
+
 // out[j] = alpha^j, j < n
-__global__ void ext_powers_kernel(const uint32_t* alpha, uint32_t* out, uint32_t n) {
+__global__ void ext_powers_kernel(const uint32_t* alpha, uint32_t* out, uint32_t* out_split, uint32_t n) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  st_ext(out + 4 * (size_t)j, kb::ext_pow(ld_ext(alpha), j));
+  kb::Ext e = kb::ext_pow(ld_ext(alpha), j);
+  st_ext(out + 4 * (size_t)j, e);
+  st_split(out_split + 8 * (size_t)j, e);
 }
 
 // x_r = GENERATOR * g_L^{bitrev_L(r)}: the point of row r of a bit-reversed LDE of height 2^L
@@ -121,36 +154,31 @@ __device__ __forceinline__ uint32_t lde_point(uint32_t r, uint32_t L, uint32_t g
   return kb::mul(kb::GEN, kb::pow(gL, kb::bitrev(r, L)));
 }
 
-// rowred[r] = sum_j alpha^j m[r][j]   (Matrix::dot_ext_powers).  One thread per row; alpha powers in smem.
+// rowred[r] = sum_j alpha^j m[r][j]   (Matrix::dot_ext_powers).  One thread per row; split alpha powers in smem.
 constexpr int RR_CHUNK = 512;  // alpha powers staged per pass
 __global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
-                                                         const uint32_t* __restrict__ apow, uint32_t* __restrict__ rowred) {
-  __shared__ uint32_t sp[RR_CHUNK * 4];
+                                                         const uint32_t* __restrict__ apow_split,
+                                                         uint32_t* __restrict__ rowred) {
+  __shared__ uint4 sp[RR_CHUNK * 2];
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t* row = mat + (r < H ? r : 0) * w;
-  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // sums of Montgomery-reduced products, < w * p
+  Acc4 acc;
+  acc.zero();
   for (uint32_t c0 = 0; c0 < w; c0 += RR_CHUNK) {
     uint32_t nc = min(w - c0, (uint32_t)RR_CHUNK);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nc * 4; i += blockDim.x) sp[i] = apow[(size_t)c0 * 4 + i];
+    for (uint32_t i = threadIdx.x; i < nc * 2; i += blockDim.x)
+      sp[i] = reinterpret_cast<const uint4*>(apow_split)[(size_t)c0 * 2 + i];
     __syncthreads();
     if (r < H) {
-      for (uint32_t j = 0; j < nc; j++) {
-        uint32_t v = __ldg(row + c0 + j);
-        a0 += kb::mul(sp[4 * j + 0], v);
-        a1 += kb::mul(sp[4 * j + 1], v);
-        a2 += kb::mul(sp[4 * j + 2], v);
-        a3 += kb::mul(sp[4 * j + 3], v);
-      }
+#pragma unroll 4
+      for (uint32_t j = 0; j < nc; j++) acc.fma(sp[2 * j], sp[2 * j + 1], __ldg(row + c0 + j));
     }
   }
-  if (r < H) {
-    kb::Ext e{{(uint32_t)(a0 % kb::P), (uint32_t)(a1 % kb::P), (uint32_t)(a2 % kb::P), (uint32_t)(a3 % kb::P)}};
-    st_ext(rowred + 4 * r, e);
-  }
+  if (r < H) st_ext(rowred + 4 * r, acc.reduce());
 }
 
-// Barycentric weights over the low coset: wts[p][r] = x_r / (z_p - x_r), r < N = 2^n
+// Barycentric weights over the low coset: wts[p][r] = x_r / (z_p - x_r), r < N = 2^n, stored split (8 words)
 __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __restrict__ pts, uint32_t npts, uint32_t n,
                                                            uint32_t gn, uint32_t* __restrict__ wts) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,49 +187,71 @@ __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __res
   for (uint32_t p = 0; p < npts; p++) {
     kb::Ext z = ld_ext(pts + 4 * p);
     kb::Ext d = kb::ext_inv(kb::ext_sub_base(z, x));
-    st_ext(wts + 4 * (((size_t)p << n) + r), kb::ext_mul_base(d, x));
+    st_split(wts + 8 * (((size_t)p << n) + r), kb::ext_mul_base(d, x));
   }
 }
 
 // partial[chunk][p][c] = sum over the rows of the chunk of wts[p][r] * m[r][c].
-// Block = 32 columns x 8 row lanes; rows of the chunk are strided over the 8 lanes, then reduced in smem.
+// Block = 32 lanes x 8 row lanes; a lane owns CPL adjacent columns (64-bit loads when CPL == 2); rows of the
+// chunk are strided over the 8 row lanes, then reduced in shared memory.
 constexpr int BARY_ROWS = 2048;  // rows per chunk
+template <int CPL>
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
                                                            const uint32_t* __restrict__ wts, uint32_t npts,
                                                            uint32_t* __restrict__ partial) {
-  __shared__ uint32_t red[8][2][4][32];
+  __shared__ uint32_t red[8][2][CPL][4][32];
   const uint32_t lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-  const uint32_t ntile = (w + 31) / 32;
+  const uint32_t ntile = (w + 32 * CPL - 1) / (32 * CPL);
   const uint32_t tile = blockIdx.x % ntile, chunk = blockIdx.x / ntile;
-  const uint32_t col = tile * 32 + lane;
+  const uint32_t col = (tile * 32 + lane) * CPL;
   const uint64_t N = 1ull << n;
   uint64_t r0 = (uint64_t)chunk * BARY_ROWS, r1 = min(N, r0 + BARY_ROWS);
-  uint64_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  Acc4 acc[2][CPL];
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int c = 0; c < CPL; c++) acc[p][c].zero();
+  const uint4* W = reinterpret_cast<const uint4*>(wts);
   if (col < w) {
     for (uint64_t r = r0 + sub; r < r1; r += 8) {
-      uint32_t v = __ldg(mat + r * w + col);
-      for (uint32_t p = 0; p < npts; p++) {
-        uint4 wt = __ldg(reinterpret_cast<const uint4*>(wts + 4 * (((size_t)p << n) + r)));
-        acc[p][0] += kb::mul(wt.x, v);
-        acc[p][1] += kb::mul(wt.y, v);
-        acc[p][2] += kb::mul(wt.z, v);
-        acc[p][3] += kb::mul(wt.w, v);
+      uint32_t v[CPL];
+      if constexpr (CPL == 2) {
+        uint2 x = __ldg(reinterpret_cast<const uint2*>(mat + r * w + col));
+        v[0] = x.x;
+        v[1] = x.y;
+      } else {
+        v[0] = __ldg(mat + r * w + col);
+      }
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        if ((uint32_t)p < npts) {
+          uint4 wl = __ldg(W + 2 * (((size_t)p << n) + r)), wh = __ldg(W + 2 * (((size_t)p << n) + r) + 1);
+#pragma unroll
+          for (int c = 0; c < CPL; c++) acc[p][c].fma(wl, wh, v[c]);
+        }
       }
     }
   }
+#pragma unroll
   for (int p = 0; p < 2; p++)
-    for (int k = 0; k < 4; k++) red[sub][p][k][lane] = (uint32_t)(acc[p][k] % kb::P);
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      kb::Ext e = acc[p][c].reduce();
+#pragma unroll
+      for (int k = 0; k < 4; k++) red[sub][p][c][k][lane] = e.c[k];
+    }
   __syncthreads();
   if (sub == 0 && col < w) {
-    for (uint32_t p = 0; p < npts; p++) {
-      kb::Ext e;
-      for (int k = 0; k < 4; k++) {
-        uint32_t s = 0;
-        for (int q = 0; q < 8; q++) s = kb::add(s, red[q][p][k][lane]);
-        e.c[k] = s;
+    for (uint32_t p = 0; p < npts; p++)
+      for (int c = 0; c < CPL; c++) {
+        kb::Ext e;
+        for (int k = 0; k < 4; k++) {
+          uint32_t s = 0;
+          for (int q = 0; q < 8; q++) s = kb::add(s, red[q][p][c][k][lane]);
+          e.c[k] = s;
+        }
+        st_ext(partial + 4 * (((size_t)chunk * npts + p) * w + col + c), e);
       }
-      st_ext(partial + 4 * (((size_t)chunk * npts + p) * w + col), e);
-    }
   }
 }
 
