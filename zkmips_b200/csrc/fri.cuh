@@ -115,8 +115,9 @@ __device__ __forceinline__ void st_ext(uint32_t* p, kb::Ext e) {
 // IMAD.WIDE accumulations (terms < 2^47, so 2^16 of them fit in 64 bits) instead of a Montgomery product
 // and a modular addition per term.  reduce_acc() returns (acc_hi * 2^16 + acc_lo) * R^-1 mod p, i.e. the sum
 // of the Montgomery products.
+constexpr uint32_t TWO16_MONTY = kbh::to_monty(1u << 16);
 __device__ __forceinline__ uint32_t reduce_acc(uint64_t lo, uint64_t hi) {
-  constexpr uint32_t TWO16 = kbh::to_monty(1u << 16);
+  constexpr uint32_t TWO16 = TWO16_MONTY;
   uint64_t fl = (lo >> 32) * (uint64_t)kb::ONE + (lo & 0xffffffffull);  // == lo (mod p), < 2^58
   uint64_t fh = (hi >> 32) * (uint64_t)kb::ONE + (hi & 0xffffffffull);
   return kb::add(kb::mont_reduce64(fl), kb::mul(kb::mont_reduce64(fh), TWO16));
