@@ -134,3 +134,44 @@ def test_permutation_trace_multi_block_scan(be, log_n):
         ctx.dev_free(p)
     assert (ob.from_monty(tr) == exp_tr).all()
     assert list(ob.from_monty(lcs)) == exp_lcs
+
+
+@pytest.mark.gpu
+def test_two_contexts_prove_concurrently():
+    """two shards in flight on one GPU (two contexts, two host threads, shared Chip objects): both proofs must
+    equal the proof computed alone -- guards the library's per-context state and the mirror's per-call state."""
+    import threading
+    from zkmips_b200 import native
+    lib = native.load()
+    chips = [su.fibonacci_chip(12), su.wide_chip(10, 64), su.lookup_chip(11)]
+    ctxs = [lib.ctx_create(0), lib.ctx_create(0)]
+    provers = [GpuShardProver(c, 1, 20, 8) for c in ctxs]
+    preps = [p.setup(chips) for p in provers]
+
+    def prove(k):
+        ch = Challenger(ctxs[k])
+        ordered, root, pd = provers[k].commit(chips)
+        sp = provers[k].open(ordered, root, pd, ch, *preps[k])
+        pd.free()
+        return sp
+
+    ref = prove(0)
+    out = [[], []]
+
+    def worker(k):
+        for _ in range(4):
+            out[k].append(prove(k))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(2):
+        assert len(out[k]) == 4
+        for sp in out[k]:
+            assert (sp.pcs_proof == ref.pcs_proof).all()
+            assert (sp.quotient_commit == ref.quotient_commit).all()
+    for k in range(2):
+        preps[k][1].free()
+        ctxs[k].destroy()

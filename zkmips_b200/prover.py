@@ -113,14 +113,13 @@ class GpuShardProver:
                 pre_idx[c.name] = len(pre_idx)
         challenger.observe(main_root)                                   # prover.rs:323
         perm_challenges = challenger.sample_ext(2)                       # prover.rs:326-329
-        for c in chips:
-            c.has_lookups = ctx.air_info(c.air)["num_lookups"] > 0
-        perm_chips = [c for c in chips if c.permutation is not None or c.has_lookups]
+        lookups = {c.name: ctx.air_info(c.air)["num_lookups"] > 0 for c in chips}
+        perm_chips = [c for c in chips if c.permutation is not None or lookups[c.name]]
         perm_pd, perm_root, perm_idx, cumsums = None, None, {}, []
         if perm_chips:
             ptrs, shapes = [], []
             for c in perm_chips:                                         # prover.rs:341-364
-                if c.has_lookups:
+                if lookups[c.name]:
                     ptr, lcs = ctx.permutation_trace(
                         c.air, prep_pd.trace_ptr(pre_idx[c.name]) if c.name in pre_idx else 0,
                         main_pd.trace_ptr(chips.index(c)), c.main.shape[0], perm_challenges)
@@ -142,7 +141,7 @@ class GpuShardProver:
         alpha = challenger.sample_ext()                                  # prover.rs:426
         t0 = self._tick("permutation_and_challenges", t0)
         # quotient values per chip, written as chunk matrices (prover.rs:429-488)
-        chunk_ptrs, chunk_shapes, chunk_shifts = [], [], []
+        chunk_ptrs, chunk_shapes, chunk_shifts, chunk_bufs = [], [], [], []
         for c in chips:
             n, lqd = c.log_degree, c.log_quotient_degree
             lcs = cumsums[perm_idx[c.name]] if c.name in perm_idx else None
@@ -156,12 +155,12 @@ class GpuShardProver:
                 chunk_ptrs.append(dptr + k * (1 << n) * 16)
                 chunk_shapes.append((1 << n, 4))
                 chunk_shifts.append(monty(3 * pow(g, k, P)))             # split_domains: shift * g^k
-            c._chunks_dptr = dptr
+            chunk_bufs.append(dptr)  # (per-call state: Chip objects may be shared between provers / threads)
         ctx.sync()
         t0 = self._tick("quotient", t0)
         q_root, q_pd = ctx.commit_dev(chunk_ptrs, chunk_shapes, chunk_shifts, self.log_blowup)   # prover.rs:496-497
-        for c in chips:
-            ctx.dev_free(c._chunks_dptr)
+        for dptr in chunk_bufs:
+            ctx.dev_free(dptr)
         challenger.observe(q_root)                                       # prover.rs:498
         zeta = challenger.sample_ext()                                   # prover.rs:501
         t0 = self._tick("commit_quotient", t0)
