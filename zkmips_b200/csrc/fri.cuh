@@ -179,6 +179,36 @@ __global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restr
   if (r < H) st_ext(rowred + 4 * r, acc.reduce());
 }
 
+// Same for wide matrices: one WARP per row, lanes stride the columns (coalesced), partial sums combined with
+// shuffles.  The thread-per-row form above leaves most of the machine idle when the LDE has few, long rows.
+__global__ void __launch_bounds__(256) row_reduce_warp_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
+                                                              const uint32_t* __restrict__ apow_split,
+                                                              uint32_t* __restrict__ rowred) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= H) return;
+  const uint32_t* row = mat + r * w;
+  const uint4* A = reinterpret_cast<const uint4*>(apow_split);
+  Acc4 acc;
+  acc.zero();
+  for (uint32_t j = lane; j < w; j += 32) acc.fma(__ldg(A + 2 * j), __ldg(A + 2 * j + 1), __ldg(row + j));
+  kb::Ext e = acc.reduce();
+#ifdef ZK_EMU  // the test-only emulator has no lock-step lanes: combine through shared memory instead
+  __shared__ uint32_t sh[256 * 4];
+  st_ext(sh + 4 * threadIdx.x, e);
+  __syncthreads();
+  if (lane == 0)
+    for (int l = 1; l < 32; l++) e = kb::ext_add(e, ld_ext(sh + 4 * (threadIdx.x + l)));
+#else
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) e.c[k] = kb::add(e.c[k], __shfl_xor_sync(0xffffffffu, e.c[k], off));
+  }
+#endif
+  if (lane == 0) st_ext(rowred + 4 * r, e);
+}
+
 // Barycentric weights over the low coset: wts[p][r] = x_r / (z_p - x_r), r < N = 2^n, stored split (8 words)
 __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __restrict__ pts, uint32_t npts, uint32_t n,
                                                            uint32_t gn, uint32_t* __restrict__ wts) {
@@ -193,18 +223,20 @@ __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __res
 }
 
 // partial[chunk][p][c] = sum over the rows of the chunk of wts[p][r] * m[r][c].
-// Block = 32 lanes x 8 row lanes; a lane owns CPL adjacent columns (64-bit loads when CPL == 2); rows of the
-// chunk are strided over the 8 row lanes, then reduced in shared memory.
+// Block = CW column lanes x (256 / CW) row lanes, CW = min(32, columns / CPL) rounded up to a power of two, so
+// narrow matrices (w = 2, 4: Fibonacci, quotient chunks) still use every thread; a lane owns CPL adjacent
+// columns (64-bit loads when CPL == 2); row lanes stride the chunk and are reduced in shared memory.
 constexpr int BARY_ROWS = 2048;  // rows per chunk
 template <int CPL>
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
-                                                           const uint32_t* __restrict__ wts, uint32_t npts,
+                                                           const uint32_t* __restrict__ wts, uint32_t npts, uint32_t log_cw,
                                                            uint32_t* __restrict__ partial) {
-  __shared__ uint32_t red[8][2][CPL][4][32];
-  const uint32_t lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-  const uint32_t ntile = (w + 32 * CPL - 1) / (32 * CPL);
+  __shared__ uint32_t red[2 * CPL * 4][256];
+  const uint32_t cw = 1u << log_cw, nrl = 256u >> log_cw;
+  const uint32_t lane = threadIdx.x & (cw - 1), rl = threadIdx.x >> log_cw;
+  const uint32_t ntile = (w + cw * CPL - 1) / (cw * CPL);
   const uint32_t tile = blockIdx.x % ntile, chunk = blockIdx.x / ntile;
-  const uint32_t col = (tile * 32 + lane) * CPL;
+  const uint32_t col = (tile * cw + lane) * CPL;
   const uint64_t N = 1ull << n;
   uint64_t r0 = (uint64_t)chunk * BARY_ROWS, r1 = min(N, r0 + BARY_ROWS);
   Acc4 acc[2][CPL];
@@ -214,7 +246,7 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
     for (int c = 0; c < CPL; c++) acc[p][c].zero();
   const uint4* W = reinterpret_cast<const uint4*>(wts);
   if (col < w) {
-    for (uint64_t r = r0 + sub; r < r1; r += 8) {
+    for (uint64_t r = r0 + rl; r < r1; r += nrl) {
       uint32_t v[CPL];
       if constexpr (CPL == 2) {
         uint2 x = __ldg(reinterpret_cast<const uint2*>(mat + r * w + col));
@@ -239,43 +271,60 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
     for (int c = 0; c < CPL; c++) {
       kb::Ext e = acc[p][c].reduce();
 #pragma unroll
-      for (int k = 0; k < 4; k++) red[sub][p][c][k][lane] = e.c[k];
+      for (int k = 0; k < 4; k++) red[(p * CPL + c) * 4 + k][threadIdx.x] = e.c[k];
     }
   __syncthreads();
-  if (sub == 0 && col < w) {
+  for (uint32_t s = nrl >> 1; s >= 1; s >>= 1) {
+    if (rl < s) {
+#pragma unroll
+      for (int q = 0; q < 2 * CPL * 4; q++)
+        red[q][threadIdx.x] = kb::add(red[q][threadIdx.x], red[q][threadIdx.x + (s << log_cw)]);
+    }
+    __syncthreads();
+  }
+  if (rl == 0 && col < w) {
     for (uint32_t p = 0; p < npts; p++)
       for (int c = 0; c < CPL; c++) {
+        if (col + c >= w) continue;
         kb::Ext e;
-        for (int k = 0; k < 4; k++) {
-          uint32_t s = 0;
-          for (int q = 0; q < 8; q++) s = kb::add(s, red[q][p][c][k][lane]);
-          e.c[k] = s;
-        }
+        for (int k = 0; k < 4; k++) e.c[k] = red[(p * CPL + c) * 4 + k][threadIdx.x];
         st_ext(partial + 4 * (((size_t)chunk * npts + p) * w + col + c), e);
       }
   }
 }
 
 // ys[p][c] = scale_p * sum_chunks partial;  scale_p = (z^N - s^N) / (N s^N), s = GENERATOR.
-// Writes the opened values into the proof (point-major, width ext each).
-__global__ void __launch_bounds__(256) bary_final_kernel(const uint32_t* __restrict__ partial, uint32_t nchunks,
+// One block per column: the chunk partials are summed by 128 threads.  Writes the opened values into the
+// proof (point-major, width ext each).
+__global__ void __launch_bounds__(128) bary_final_kernel(const uint32_t* __restrict__ partial, uint32_t nchunks,
                                                          uint32_t w, uint32_t n, const uint32_t* __restrict__ pts,
                                                          uint32_t npts, uint32_t* __restrict__ ys) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= w) return;
+  __shared__ uint32_t red[4][128];
+  const uint32_t c = blockIdx.x;
   for (uint32_t p = 0; p < npts; p++) {
     kb::Ext acc = kb::ext_zero();
-    for (uint32_t k = 0; k < nchunks; k++) acc = kb::ext_add(acc, ld_ext(partial + 4 * (((size_t)k * npts + p) * w + c)));
-    kb::Ext z = ld_ext(pts + 4 * p);
-    kb::Ext zN = z;
-    uint32_t sN = kb::GEN;
-    for (uint32_t i = 0; i < n; i++) {
-      zN = kb::ext_sqr(zN);
-      sN = kb::sqr(sN);
+    for (uint32_t k = threadIdx.x; k < nchunks; k += 128) acc = kb::ext_add(acc, ld_ext(partial + 4 * (((size_t)k * npts + p) * w + c)));
+    __syncthreads();
+    for (int k = 0; k < 4; k++) red[k][threadIdx.x] = acc.c[k];
+    __syncthreads();
+    for (uint32_t s = 64; s >= 1; s >>= 1) {
+      if (threadIdx.x < s)
+        for (int k = 0; k < 4; k++) red[k][threadIdx.x] = kb::add(red[k][threadIdx.x], red[k][threadIdx.x + s]);
+      __syncthreads();
     }
-    uint32_t Nm = kb::to_monty(1u << n);  // n <= 22
-    kb::Ext scale = kb::ext_mul_base(kb::ext_sub_base(zN, sN), kb::inv(kb::mul(Nm, sN)));
-    st_ext(ys + 4 * ((size_t)p * w + c), kb::ext_mul(acc, scale));
+    if (threadIdx.x == 0) {
+      acc = kb::Ext{{red[0][0], red[1][0], red[2][0], red[3][0]}};
+      kb::Ext z = ld_ext(pts + 4 * p);
+      kb::Ext zN = z;
+      uint32_t sN = kb::GEN;
+      for (uint32_t i = 0; i < n; i++) {
+        zN = kb::ext_sqr(zN);
+        sN = kb::sqr(sN);
+      }
+      uint32_t Nm = kb::to_monty(1u << n);  // n <= 22
+      kb::Ext scale = kb::ext_mul_base(kb::ext_sub_base(zN, sN), kb::inv(kb::mul(Nm, sN)));
+      st_ext(ys + 4 * ((size_t)p * w + c), kb::ext_mul(acc, scale));
+    }
   }
 }
 

@@ -72,10 +72,17 @@ static int32_t ctx_init(zk_ctx* c) {
     if (v >= 1) c->slab_bytes = (uint64_t)v << 20;
   }
   if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
-  cudaMemPool_t pool;
-  CK(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  // a private stream-ordered pool per context: contexts that prove shards concurrently on one GPU must not
+  // couple their streams through cross-stream reuse of freed blocks in the device's default pool
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof props);
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = c->device;
+  CK(cudaMemPoolCreate(&c->pool, &props));
   uint64_t thr = UINT64_MAX;
-  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   // constant twiddles of the size-32 DFT
   uint32_t w32[2][16];
   uint32_t g5 = kbh::two_adic_generator(5), g5i = kbh::inv(g5);
@@ -127,6 +134,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -197,7 +205,7 @@ ProfScope::~ProfScope() {
 // ------------------------------------------------------------------------------------------------
 int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out) {
   if (bytes == 0) bytes = 4;
-  CK(cudaMallocAsync(out, bytes, c->stream));
+  CK(cudaMallocFromPoolAsync(out, bytes, c->pool, c->stream));
   return ZK_OK;
 }
 int32_t dev_free(zk_ctx* c, void* p) {

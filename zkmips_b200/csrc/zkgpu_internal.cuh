@@ -28,6 +28,7 @@ struct zk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaMemPool_t pool = nullptr;         // private stream-ordered allocator of this context
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
   uint64_t slab_bytes = 128ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
