@@ -45,6 +45,15 @@ def leaf_hash_bytes(log_rows, cols, log_blowup):
     return 4 * H * cols + 32 * H
 
 
+def kernel_traffic(name):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (or None)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")) as fh:
+            return json.load(fh)[name]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -400,7 +409,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "mk::hash_rows_w8 (Poseidon2 leaf sponge)", "bound": "hbm", "achieved": ach,
-                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": kernel_traffic("mk::hash_rows_w8") if (log_rows, cols) == (LOG_ROWS, COLS) else None,
+                     "algorithmic_bytes": leaf_hash_bytes(log_rows, cols, LOG_BLOWUP),
+                     "int_pipes": "ncu: fmaheavy 76 %, alu 61 %, issue slots 61 % busy, 4378 warp instructions per permutation (profiles/r1_ncu_full_final.csv)",
                      "ms_per_launch": leaf_ms,
                      "note": "int-pipe bound kernel; HBM fraction reported as required, see DESIGN.md section 4"},
         "commit_roofline": {"algorithmic_bytes": A, "achieved": commit_gbs, "unit": "GB/s", "frac": commit_gbs / peak},
