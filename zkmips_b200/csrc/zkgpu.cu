@@ -134,6 +134,11 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
+  for (int b = 0; b < 2; b++) {
+    if (c->slab_buf[b]) cudaFree(c->slab_buf[b]);
+    if (c->slab_up[b]) cudaEventDestroy(c->slab_up[b]);
+    if (c->slab_free[b]) cudaEventDestroy(c->slab_free[b]);
+  }
   if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -328,6 +333,25 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
   return rc;
 }
 
+// (Re)allocates the context's two slab buffers when a larger slab is needed (rare; synchronises).
+static int32_t ensure_slab_bufs(zk_ctx* c, uint64_t bytes) {
+  if (bytes <= c->slab_cap) return ZK_OK;
+  CK(cudaStreamSynchronize(c->copy_stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < 2; b++) {
+    if (c->slab_buf[b]) CK(cudaFree(c->slab_buf[b]));
+    c->slab_buf[b] = nullptr;
+    CK(cudaMalloc(&c->slab_buf[b], bytes));
+    c->slab_used[b] = false;
+    if (!c->slab_up[b]) {
+      CK(cudaEventCreateWithFlags(&c->slab_up[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->slab_free[b], cudaEventDisableTiming));
+    }
+  }
+  c->slab_cap = bytes;
+  return ZK_OK;
+}
+
 // Streaming LDE of a HOST matrix: column slabs flow  H2D (copy stream)  ||  inverse + coset transforms  ||
 // resumable leaf sponge (compute stream), double buffered.  The slab buffer doubles as the coefficient
 // buffer (in-place inverse transform), so no full-size staging copy of the trace exists on the device.
@@ -343,42 +367,38 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // ~slab_bytes (a multiple of 16 columns, >= 32): short-and-wide traces must not be cut into tiny slabs
   uint32_t slab = c->slab_cols;
   if (slab == 0) {
-    uint64_t cols = c->slab_bytes / (h * 4);
-    slab = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(32, cols / 16 * 16), 1u << 20);
+    // rows of a 2-D copy narrower than 256 B lose PCIe efficiency (measured: 64 B rows 43 ms, 128 B 24.8 ms,
+    // 256 B 24.4 ms, 512 B 28.8 ms per GiB-sized trace), a trace should still be cut into >= 4 slabs to overlap
+    uint64_t by_bytes = std::max<uint64_t>(64, c->slab_bytes / (h * 4) / 16 * 16);
+    uint64_t quarter = std::max<uint64_t>(64, (w / 4 + 15) / 16 * 16);
+    slab = (uint32_t)std::min(by_bytes, quarter);
   }
   if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
   const uint32_t nslab = (w + slab - 1) / slab;
   std::vector<ntt::CosetScale> scales;
   const bool aligned = (w & 1u) == 0 && (slab & 1u) == 0 && ((uintptr_t)out % 8) == 0;
   if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
-  uint32_t* buf[2] = {nullptr, nullptr};
+  // the two slab buffers and their events live in the context and are shared by every matrix and every call:
+  // the copy stream can therefore run ahead into the NEXT matrix while this one is still being transformed
+  if ((rc = ensure_slab_bufs(c, h * (uint64_t)slab * 4))) return rc;
   uint4* state = nullptr;
-  const uint32_t nbuf = nslab > 1 ? 2 : 1;
-  for (uint32_t b = 0; b < nbuf; b++)
-    if ((rc = dev_alloc(c, h * (uint64_t)slab * 4, (void**)&buf[b]))) return rc;
   if (leaves && nslab > 1 && (rc = dev_alloc(c, H * 64, (void**)&state))) return rc;
-  cudaEvent_t up_done[2], buf_free[2], ready;
-  for (int b = 0; b < 2; b++) {
-    CK(cudaEventCreateWithFlags(&up_done[b], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&buf_free[b], cudaEventDisableTiming));
-  }
-  CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  CK(cudaEventRecord(ready, c->stream));  // allocations above are ordered on the compute stream
-  CK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
-    const uint32_t b = k & 1, c0 = k * slab, nc = std::min(slab, w - c0);
-    if (k >= 2) CK(cudaStreamWaitEvent(c->copy_stream, buf_free[b], 0));
-    CK(cudaMemcpy2DAsync(buf[b], (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+    const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = k * slab, nc = std::min(slab, w - c0);
+    uint32_t* buf = c->slab_buf[b];
+    if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
+    CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
                          c->copy_stream));
-    CK(cudaEventRecord(up_done[b], c->copy_stream));
-    CK(cudaStreamWaitEvent(c->stream, up_done[b], 0));
+    CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
     if (keep_trace)  // retain the slab before the in-place inverse transform overwrites it
-      CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf[b], (size_t)nc * 4, (size_t)nc * 4, h, cudaMemcpyDeviceToDevice,
+      CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h, cudaMemcpyDeviceToDevice,
                            c->stream));
-    ntt::Cols sl{buf[b], nc, 0};
+    ntt::Cols sl{buf, nc, 0};
     rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
     if (rc) break;
-    CK(cudaEventRecord(buf_free[b], c->stream));
+    CK(cudaEventRecord(c->slab_free[b], c->stream));
+    c->slab_used[b] = true;
     if (leaves) {
       ProfScope ps(c, "leaf_hash");
       ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + 255) / 256), 256, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
@@ -387,13 +407,7 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
       c->launches++;
     }
   }
-  for (int b = 0; b < 2; b++) {
-    cudaEventDestroy(up_done[b]);
-    cudaEventDestroy(buf_free[b]);
-  }
-  cudaEventDestroy(ready);
   free_scales(c, scales);
-  for (uint32_t b = 0; b < nbuf; b++) dev_free(c, buf[b]);
   if (state) dev_free(c, state);
   return rc;
 }

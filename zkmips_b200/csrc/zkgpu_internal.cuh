@@ -30,8 +30,13 @@ struct zk_ctx {
   bool own_stream = false;
   cudaMemPool_t pool = nullptr;         // private stream-ordered allocator of this context
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
+  uint32_t* slab_buf[2] = {nullptr, nullptr};  // double-buffered upload slabs, shared by all matrices / calls
+  uint64_t slab_cap = 0;
+  uint64_t slab_seq = 0;
+  bool slab_used[2] = {false, false};
+  cudaEvent_t slab_up[2] = {nullptr, nullptr}, slab_free[2] = {nullptr, nullptr};
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
-  uint64_t slab_bytes = 128ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
+  uint64_t slab_bytes = 256ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
