@@ -175,3 +175,24 @@ def test_two_contexts_prove_concurrently():
     for k in range(2):
         preps[k][1].free()
         ctxs[k].destroy()
+
+
+@pytest.mark.gpu
+def test_one_process_two_devices():
+    """INTEGRATION.md's dispatch keeps one context per GPU inside ONE process: per-device state (constant
+    twiddles, function attributes, pools) must be set up for every device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from zkmips_b200 import native
+    lib = native.load()
+    roots = []
+    m = su.M(np.arange(1 << 14 * 1).reshape(-1, 1) % 1000 + np.arange(24))  # 2^14 x 24
+    for dev in (0, 1, 0):
+        ctx = lib.ctx_create(dev)
+        root, pd = ctx.commit([m], [MONTY_ONE], 1)
+        roots.append(root)
+        pd.free()
+        ctx.destroy()
+    assert (roots[0] == roots[1]).all() and (roots[0] == roots[2]).all()
+    assert (roots[0] == ob.pcs_commit([m], 1).root).all()

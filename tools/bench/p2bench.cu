@@ -11,6 +11,15 @@ __device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
 __device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
 constexpr uint32_t P = kb::P;
 
+// forced-ALU add: a 3-input add with an opaque zero cannot be turned into IMAD.IADD (fmaheavy pipe) by ptxas,
+// so it must issue as IADD3 on the alu pipe; used to rebalance the two integer pipes
+__device__ uint32_t g_zero_dev;  // 0 at run time, unknown at compile time
+__device__ __forceinline__ uint32_t add3z(uint32_t a, uint32_t b, uint32_t z) {
+  uint32_t s;
+  asm("add.u32 %0, %1, %2;\n\tadd.u32 %0, %0, %3;" : "=r"(s) : "r"(a), "r"(b), "r"(z));
+  return min(s, s - P);
+}
+
 // MUL variants -------------------------------------------------------------
 struct MulSub {  // product code: subtractive form, umulhi
   static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return kb::mul(a, b); }
@@ -46,14 +55,20 @@ __device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uin
   uint32_t n0 = kb::add(t01123, t01), n2 = kb::add(t01233, t23);
   x0 = n0; x1 = n1; x2 = n2; x3 = n3;
 }
-__device__ __forceinline__ void external_layer(uint32_t (&s)[16]) {
+template <int FA>
+__device__ __forceinline__ void external_layer(uint32_t (&s)[16], uint32_t z) {
 #pragma unroll
   for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
   uint32_t sums[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) sums[k] = kb::add(kb::add(s[k], s[4 + k]), kb::add(s[8 + k], s[12 + k]));
+  for (int k = 0; k < 4; k++) {
+    if (FA >= 2)
+      sums[k] = add3z(add3z(s[k], s[4 + k], z), add3z(s[8 + k], s[12 + k], z), z);
+    else
+      sums[k] = kb::add(kb::add(s[k], s[4 + k]), kb::add(s[8 + k], s[12 + k]));
+  }
 #pragma unroll
-  for (int j = 0; j < 16; j++) s[j] = kb::add(s[j], sums[j & 3]);
+  for (int j = 0; j < 16; j++) s[j] = FA >= 1 ? add3z(s[j], sums[j & 3], z) : kb::add(s[j], sums[j & 3]);
 }
 // x * 2^-k mod p = (x >> k) - (x & (2^k-1)) * ((p-1) >> k)   since 2^-k = -(p-1)/2^k  (p = 127*2^24 + 1)
 template <int K> __device__ __forceinline__ uint32_t div2k(uint32_t x) {
@@ -94,13 +109,13 @@ template <class M, int DIAG> __device__ __forceinline__ void internal_layer(uint
     s[15] = kb::sub(sum, div2k<24>(s[15]));
   }
 }
-template <class M, int DIAG> __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
-  external_layer(s);
+template <class M, int DIAG, int FA = 0> __device__ __forceinline__ void permute(uint32_t (&s)[16], uint32_t z = 0) {
+  external_layer<FA>(s, z);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = cube<M>(kb::add(s[i], EXT_RC[r][i]));
-    external_layer(s);
+    for (int i = 0; i < 16; i++) s[i] = cube<M>(FA >= 3 ? add3z(s[i], EXT_RC[r][i], z) : kb::add(s[i], EXT_RC[r][i]));
+    external_layer<FA>(s, z);
   }
 #pragma unroll
   for (int r = 0; r < 13; r++) {
@@ -110,13 +125,14 @@ template <class M, int DIAG> __device__ __forceinline__ void permute(uint32_t (&
 #pragma unroll
   for (int r = 4; r < 8; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = cube<M>(kb::add(s[i], EXT_RC[r][i]));
-    external_layer(s);
+    for (int i = 0; i < 16; i++) s[i] = cube<M>(FA >= 3 ? add3z(s[i], EXT_RC[r][i], z) : kb::add(s[i], EXT_RC[r][i]));
+    external_layer<FA>(s, z);
   }
 }
 
-template <class M, int DIAG, int ILP, int MINB>
+template <class M, int DIAG, int ILP, int MINB, int FA = 0>
 __global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
+  const uint32_t z = g_zero_dev;
   uint32_t s[ILP][16];
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
@@ -125,7 +141,7 @@ __global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
     for (int i = 0; i < 16; i++) s[k][i] = (tid * 2654435761u + i * 40503u + k * 977u) % P;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int k = 0; k < ILP; k++) permute<M, DIAG>(s[k]);
+    for (int k = 0; k < ILP; k++) permute<M, DIAG, FA>(s[k], z);
   }
   uint32_t acc = 0;
 #pragma unroll
@@ -136,22 +152,22 @@ __global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
   if (ILP > 1) out[tid * ILP + 1] = s[ILP - 1][3];
 }
 
-template <class M, int DIAG, int ILP, int MINB>
+template <class M, int DIAG, int ILP, int MINB, int FA = 0>
 void run(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
   int blocks = sms * 8, iters = 128;
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, bench<M, DIAG, ILP, MINB>);
+  cudaFuncGetAttributes(&fa, bench<M, DIAG, ILP, MINB, FA>);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench<M, DIAG, ILP, MINB>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench<M, DIAG, ILP, MINB, FA>, 256, 0);
   blocks = sms * occ;
-  bench<M, DIAG, ILP, MINB><<<blocks, 256>>>(d_out, 4);
+  bench<M, DIAG, ILP, MINB, FA><<<blocks, 256>>>(d_out, 4);
   cudaDeviceSynchronize();
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   float best = 1e9;
   for (int rep = 0; rep < 3; rep++) {
     cudaEventRecord(a);
-    bench<M, DIAG, ILP, MINB><<<blocks, 256>>>(d_out, iters);
+    bench<M, DIAG, ILP, MINB, FA><<<blocks, 256>>>(d_out, iters);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
@@ -175,6 +191,9 @@ int main() {
   uint32_t ref[1] = {0xffffffffu};
   run<MulSub, 0, 1, 1>("sub/diagmul", d, ref, sms);
   run<MulSub, 1, 1, 1>("sub/diagshift", d, ref, sms);
+  run<MulSub, 1, 1, 1, 1>("sub/diagshift forceALU1", d, ref, sms);
+  run<MulSub, 1, 1, 1, 2>("sub/diagshift forceALU2", d, ref, sms);
+  run<MulSub, 1, 1, 1, 3>("sub/diagshift forceALU3", d, ref, sms);
   run<MulAdd, 0, 1, 1>("add/diagmul", d, ref, sms);
   run<MulAdd, 1, 1, 1>("add/diagshift", d, ref, sms);
   run<MulLea, 1, 1, 1>("lea/diagshift", d, ref, sms);

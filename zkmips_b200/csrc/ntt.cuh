@@ -310,18 +310,31 @@ inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
 
 template <int DIR, bool FIRST, bool PASSTW, int CPT>
 inline cudaError_t launch_pass10_cpt(const PassArgs& A, const Pass10Extra& X, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)P10_SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
   uint64_t blocks = (1ull << (A.log_n - 10)) * ncg;
   auto kfn = ntt_pass10<DIR, FIRST, PASSTW, CPT>;
   ZK_LAUNCH_COOP(kfn, (unsigned)blocks, 512 / CPT, P10_SMEM, st, A, X);
   return cudaGetLastError();
+}
+
+// Function attributes are per device: every context calls this once for its device (a process may drive
+// several GPUs, one context each), so nothing is cached in process-wide statics.
+template <int DIR, bool FIRST, bool PASSTW>
+inline cudaError_t configure_pass10() {
+  cudaError_t e = cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P10_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ntt_pass10<DIR, FIRST, PASSTW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P10_SMEM);
+}
+inline cudaError_t configure_device() {
+  cudaError_t e;
+  if ((e = configure_pass10<DIR_FWD, false, false>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_FWD, false, true>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_FWD, true, false>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_FWD, true, true>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_INV, false, false>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_INV, false, true>()) != cudaSuccess) return e;
+  if ((e = configure_pass10<DIR_INV, true, false>()) != cudaSuccess) return e;
+  return configure_pass10<DIR_INV, true, true>();
 }
 
 // columns per thread of the k=10 pass: 2 needs every access 8-byte aligned

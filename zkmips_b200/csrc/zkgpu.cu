@@ -83,6 +83,7 @@ static int32_t ctx_init(zk_ctx* c) {
   CK(cudaMemPoolCreate(&c->pool, &props));
   uint64_t thr = UINT64_MAX;
   CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CK(ntt::configure_device());
   // constant twiddles of the size-32 DFT
   uint32_t w32[2][16];
   uint32_t g5 = kbh::two_adic_generator(5), g5i = kbh::inv(g5);
