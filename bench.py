@@ -184,14 +184,18 @@ def run_reference(args):
 def shard_leg(ctx, torch, dist, world, rank, args):
     """Second BASELINE metric: shard prove ms = MachineProver::commit + open (quotient, quotient commit, Pcs::open
     with 84 queries / 16 PoW bits) for one synthetic shard per GPU, traces in host memory, proof back on the host.
-    Chips: wide_bitwise_1024 at 2^16 rows (keccak-precompile-like), wide_bitwise_64 at 2^18, Fibonacci at 2^20."""
+    Chips (default): wide_bitwise_1024 at 2^16 rows, wide_bitwise_64 at 2^18, Fibonacci at 2^20; --shard-config keccak:
+    the BASELINE config-3 shape, wide_bitwise_4096 at 2^16 rows (6144 constraints)."""
     import numpy as np
 
     from tests import shard_util as su
     from zkmips_b200 import Challenger
     from zkmips_b200.prover import GpuShardProver
 
-    chips = [su.wide_chip(16, 1024, seed=11 + rank), su.wide_chip(18, 64, seed=12 + rank), su.fibonacci_chip(20, 1 + rank, 1)]
+    if args.shard_config == "keccak":
+        chips = [su.wide_chip(16, 4096, seed=11 + rank), su.fibonacci_chip(16, 1 + rank, 1)]
+    else:
+        chips = [su.wide_chip(16, 1024, seed=11 + rank), su.wide_chip(18, 64, seed=12 + rank), su.fibonacci_chip(20, 1 + rank, 1)]
     for c in chips:  # the host-side trace buffers are pinned, as the bench contract's e2e path allows
         c.main = torch.from_numpy(c.main.view(np.int32)).pin_memory().numpy().view(np.uint32)
     cells = sum(c.main.size for c in chips)
@@ -257,7 +261,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt2 = float(tt.item())
     ctx2.destroy()
-    res = {"ms_per_shard": dt * 1e3, "shards_per_s": world / dt, "shards_per_s_two_in_flight": world / dt2,
+    res = {"config": args.shard_config, "ms_per_shard": dt * 1e3, "shards_per_s": world / dt, "shards_per_s_two_in_flight": world / dt2,
            "trace_cells_per_shard": int(cells),
            "chips": [f"{c.name}: 2^{c.log_degree} x {c.main.shape[1]}" for c in ordered],
            "params": "log_blowup 1, 84 queries, 16 PoW bits", "timing": "host wall clock around commit+open, max over ranks",
@@ -283,6 +287,9 @@ def main():
     ap.add_argument("--no-shard", action="store_true", help="skip the shard-prove leg (commit + quotient + open)")
     ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
+    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak"],
+                    help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 (86 M cells); keccak: BASELINE config 3, one "
+                         "2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

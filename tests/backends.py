@@ -20,12 +20,14 @@ _gpu = None
 def build_emu(force=False):
     from zkmips_b200.air import codegen
     codegen.write()
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "gen"] + [os.path.join(CSRC, "gen", "airs_gen.cuh")] + [
+    gen = os.path.join(CSRC, "gen")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "gen"] + [os.path.join(gen, f) for f in os.listdir(gen)] + [
         os.path.join(EMU_DIR, "emu_runtime.cpp"), os.path.join(EMU_DIR, "include", "cuda_runtime.h"),
         os.path.join(ROOT, "include", "zkgpu.h")]
     if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in srcs):
         return EMU_SO
-    cu = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    cu = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")) + sorted(
+        os.path.join("gen", f) for f in os.listdir(gen) if f.endswith(".cu"))
     cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(EMU_DIR, "include")]
     for f in cu:
         cmd += ["-x", "c++", os.path.join(CSRC, f)]

@@ -19,7 +19,7 @@
 #include <vector>
 
 #define ZK_EMU 1
-#define __global__ inline
+#define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline

@@ -140,16 +140,28 @@ def _emit_logup(air):
     return fn, o
 
 
+N_KERNEL_FILES = 8
+
+
 def generate(airs):
-    out = ["// GENERATED by zkmips_b200/air/codegen.py -- do not edit.", "#pragma once", '#include "../quotient.cuh"',
+    """Returns {relative file name: text}: N_KERNEL_FILES translation units with the quotient kernels (compiled
+    in parallel; ptxas time grows faster than linearly with the size of one unit) and airs_gen.cuh with the
+    declarations, the LogUp kernels and the registry."""
+    files = [["// GENERATED by zkmips_b200/air/codegen.py -- do not edit.", '#include "../quotient.cuh"', "",
+              "namespace quotgen {", ""] for _ in range(N_KERNEL_FILES)]
+    hdr = ["// GENERATED by zkmips_b200/air/codegen.py -- do not edit.", "#pragma once", '#include "../quotient.cuh"',
            '#include "../logup.cuh"', "", "namespace quotgen {", ""]
     table = []
+    nk = 0
     for ai, air in enumerate(airs):
         parts = _parts(air)
         names = []
         for pi, part in enumerate(parts):
             fn = f"quot_{air.name}_p{pi}"
             names.append(fn)
+            hdr.append(f"__global__ void {fn}(quot::Args A);")
+            out = files[nk % N_KERNEL_FILES]
+            nk += 1
             out.append(f"__global__ void __launch_bounds__(128) {fn}(quot::Args A) {{")
             out.append("  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;")
             out.append("  if (i >= (1u << (A.log_n + A.lqd))) return;")
@@ -172,38 +184,45 @@ def generate(airs):
         lfn = "nullptr"
         if air.sends or air.receives:
             lfn, code = _emit_logup(air)
-            out += code
+            hdr += code
         table.append((air, names, lfn))
-    out.append("struct Entry {")
-    out.append("  const char* name;")
-    out.append("  uint32_t main_w, prep_w, perm_w, n_pv, n_chal, n_constraints, max_degree, n_parts;")
-    out.append("  uint32_t n_lookups;")
-    out.append("  void (*logup)(logup::Args);")
-    out.append("  void (*parts[%d])(quot::Args);" % max(1, max(len(n) for _, n, _ in table)))
-    out.append("};")
-    out.append("static const Entry AIRS[] = {")
+    hdr.append("")
+    hdr.append("struct Entry {")
+    hdr.append("  const char* name;")
+    hdr.append("  uint32_t main_w, prep_w, perm_w, n_pv, n_chal, n_constraints, max_degree, n_parts;")
+    hdr.append("  uint32_t n_lookups;")
+    hdr.append("  void (*logup)(logup::Args);")
+    hdr.append("  void (*parts[%d])(quot::Args);" % max(1, max(len(n) for _, n, _ in table)))
+    hdr.append("};")
+    hdr.append("static const Entry AIRS[] = {")
     for air, names, lfn in table:
-        out.append(f'  {{"{air.name}", {air.main_width}, {air.prep_width}, {air.perm_width}, {air.num_public_values}, '
+        hdr.append(f'  {{"{air.name}", {air.main_width}, {air.prep_width}, {air.perm_width}, {air.num_public_values}, '
                    f"{air.num_challenges}, {air.num_constraints}, {air.max_degree()}, {len(names)}, "
                    f"{len(air.sends) + len(air.receives)}, {lfn}, {{{', '.join(names)}}}}},")
-    out.append("};")
-    out.append(f"static const int NUM_AIRS = {len(table)};")
-    out.append("")
-    out.append("}  // namespace quotgen")
-    return "\n".join(out) + "\n"
+    hdr.append("};")
+    hdr.append(f"static const int NUM_AIRS = {len(table)};")
+    hdr.append("")
+    hdr.append("}  // namespace quotgen")
+    out = {"airs_gen.cuh": "\n".join(hdr) + "\n"}
+    for i, f in enumerate(files):
+        f.append("}  // namespace quotgen")
+        out[f"airs_kernels_{i}.cu"] = "\n".join(f) + "\n"
+    return out
 
 
-def write(path=None):
+def write(gen_dir=None):
+    """Writes csrc/gen/ (files are only rewritten when their text changes, so make-style staleness works)."""
     from . import library
     here = os.path.dirname(os.path.abspath(__file__))
-    path = path or os.path.join(os.path.dirname(here), "csrc", "gen", "airs_gen.cuh")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    text = generate(library.all_airs())
-    old = open(path).read() if os.path.exists(path) else None
-    if old != text:
-        with open(path, "w") as fh:
-            fh.write(text)
-    return path
+    gen_dir = gen_dir or os.path.join(os.path.dirname(here), "csrc", "gen")
+    os.makedirs(gen_dir, exist_ok=True)
+    for name, text in generate(library.all_airs()).items():
+        path = os.path.join(gen_dir, name)
+        old = open(path).read() if os.path.exists(path) else None
+        if old != text:
+            with open(path, "w") as fh:
+                fh.write(text)
+    return gen_dir
 
 
 if __name__ == "__main__":

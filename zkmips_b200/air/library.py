@@ -60,4 +60,5 @@ def lookup_pair():
 
 
 def all_airs():
-    return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(1024, "wide_bitwise_1024")]
+    return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(1024, "wide_bitwise_1024"),
+            wide_bitwise(4096, "wide_bitwise_4096")]

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libzkgpu.so")
-SOURCES = ["zkgpu.cu", "fri.cu", "quotient.cu"]
+SOURCES = ["zkgpu.cu", "fri.cu", "quotient.cu"]  # + csrc/gen/airs_kernels_*.cu (generated)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--compiler-options", "-fPIC", "-Xptxas", "-v",
@@ -39,14 +39,16 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
 
+    sources = SOURCES + sorted(os.path.join("gen", f) for f in os.listdir(os.path.join(CSRC, "gen")) if f.endswith(".cu"))
+
     def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, sources))
     log = "".join(r[3] for r in results)
     rc = max(r[2] for r in results)
     if rc == 0:

@@ -2,6 +2,21 @@
 #include "zkgpu_internal.cuh"
 #include "gen/airs_gen.cuh"
 
+namespace quot {
+// alpha_pows[k] = alpha^(n-1-k)  (powers_of_alpha reversed, crates/stark/src/prover.rs:453-456)
+__global__ void alpha_pows_rev_kernel(const uint32_t* alpha, uint32_t n, uint32_t* out) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  kb::Ext a{{alpha[0], alpha[1], alpha[2], alpha[3]}};
+  kb::Ext r = kb::ext_pow(a, n - 1 - k);
+  out[4 * k + 0] = r.c[0];
+  out[4 * k + 1] = r.c[1];
+  out[4 * k + 2] = r.c[2];
+  out[4 * k + 3] = r.c[3];
+}
+
+}  // namespace quot
+
 extern "C" int32_t zk_air_count(void) { return quotgen::NUM_AIRS; }
 extern "C" const char* zk_air_name(int32_t id) {
   return (id >= 0 && id < quotgen::NUM_AIRS) ? quotgen::AIRS[id].name : nullptr;

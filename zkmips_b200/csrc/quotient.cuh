@@ -89,16 +89,4 @@ __device__ __forceinline__ void epilogue(const Args& A, uint32_t i, const Row& R
   *o = make_uint4(q.c[0], q.c[1], q.c[2], q.c[3]);
 }
 
-// alpha_pows[k] = alpha^(n-1-k)  (powers_of_alpha reversed, crates/stark/src/prover.rs:453-456)
-__global__ void alpha_pows_rev_kernel(const uint32_t* alpha, uint32_t n, uint32_t* out) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  kb::Ext a{{alpha[0], alpha[1], alpha[2], alpha[3]}};
-  kb::Ext r = kb::ext_pow(a, n - 1 - k);
-  out[4 * k + 0] = r.c[0];
-  out[4 * k + 1] = r.c[1];
-  out[4 * k + 2] = r.c[2];
-  out[4 * k + 3] = r.c[3];
-}
-
 }  // namespace quot
