@@ -36,8 +36,32 @@ constexpr int DIR_FWD = 0;
 constexpr int DIR_INV = 1;
 constexpr int TILE_COLS = 16;
 
-// c_w32[dir][e] = w_32^(+e) / w_32^(-e), e < 16, Montgomery form; filled by zk_ctx_create.
-__constant__ uint32_t c_w32[2][16];
+// Butterfly twiddles are compile-time constants: plain (non-Montgomery) powers of w_64 with their Shoup
+// companions floor(w * 2^32 / p), so x*w mod p = x*w - floor(x*w'/2^32)*p costs IMAD.HI + 2 IMAD + VIADDMNMX
+// and needs no Montgomery correction (the data stays in Montgomery form: (xR)*w = (xw)R).
+struct Tw64 {
+  uint32_t w[2][32];   // w_64^(+-e), e < 32
+  uint32_t ws[2][32];  // floor(w * 2^32 / p)
+};
+constexpr Tw64 make_tw64() {
+  Tw64 t{};
+  uint32_t g6 = kbh::two_adic_generator(6);
+  uint32_t g[2] = {g6, kbh::inv(g6)};
+  for (int d = 0; d < 2; d++)
+    for (int e = 0; e < 32; e++) {
+      uint32_t w = kbh::from_monty(kbh::pow(g[d], e));
+      t.w[d][e] = w;
+      t.ws[d][e] = (uint32_t)(((uint64_t)w << 32) / kbh::P);
+    }
+  return t;
+}
+__device__ constexpr Tw64 TW64 = make_tw64();
+
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t ws) {
+  uint32_t q = __umulhi(x, ws);
+  uint32_t r = x * w - q * kb::P;  // in [0, 2p)
+  return min(r, r - kb::P);
+}
 
 struct PassArgs {
   const uint32_t* src;
@@ -62,7 +86,7 @@ __device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ tw, ui
   return __ldg(tw + idx);
 }
 
-// N / 2^LG independent size-2^LG DIF transforms on consecutive groups of v, twiddles from c_w32.
+// N / 2^LG independent size-2^LG DIF transforms (LG <= 6) on consecutive groups of v.
 template <int LG, int DIR, int N>
 __device__ __forceinline__ void dif_groups(uint32_t (&v)[N]) {
 #pragma unroll
@@ -71,13 +95,13 @@ __device__ __forceinline__ void dif_groups(uint32_t (&v)[N]) {
 #pragma unroll
     for (int x = 0; x < N; x++) {
       if ((x & half) == 0) {
-        const int e32 = ((x & (half - 1)) << t) << (5 - LG);
+        const int e64 = ((x & (half - 1)) << t) << (6 - LG);
         uint32_t u = v[x], z = v[x + half];
         v[x] = kb::add(u, z);
-        if (e32 == 0)
+        if (e64 == 0)
           v[x + half] = kb::sub(u, z);
         else
-          v[x + half] = kb::mul(u - z + kb::P, c_w32[DIR][e32]);
+          v[x + half] = shoup_mul(u - z + kb::P, TW64.w[DIR][e64], TW64.ws[DIR][e64]);
       }
     }
   }
@@ -93,58 +117,12 @@ __host__ __device__ constexpr int brev5(int q) {
 // (The first version of this kernel, one column per thread with global twiddle/scale loads, needed 85-104
 // instructions per element; this one 51-69: profiles/README.md.)
 //   * two adjacent columns per thread (64-bit global and shared accesses, twiddles shared by both);
-//   * butterfly twiddles are compile-time constants multiplied with Shoup's method
-//     (x*w mod p = x*w - floor(x*w'/2^32)*p, w' = floor(w*2^32/p): IMAD.HI + 2 IMAD + VIADDMNMX, no
-//     Montgomery correction because the constant is kept in plain form);
+//   * butterfly twiddles are compile-time constants multiplied with Shoup's method (TW64 above);
 //   * the pass twiddle g_n^(base*bitrev_10(i)) is split as g^(base*bitrev_5(i>>5)) * g^(32*base*bitrev_5(i&31)):
 //     the first factor, the inner twiddle w_1024^(tau*kappa) and the coset scale sigma^(lo + tau*2^rem)/h are
 //     merged into ONE per-CTA shared-memory table F[tau][kappa]; the second factor is a 32-entry table G;
 //     the remaining coset factor sigma^(q*32*2^rem) comes from the kernel arguments (constant bank).
 //   No per-element global twiddle or scale loads remain.  Requires even pitches, offsets and column count.
-struct Tw32 {
-  uint32_t w[2][16];   // plain (non-Montgomery) w_32^(+-e)
-  uint32_t ws[2][16];  // floor(w * 2^32 / p)
-};
-constexpr Tw32 make_tw32() {
-  Tw32 t{};
-  uint32_t g5 = kbh::two_adic_generator(5);
-  uint32_t g[2] = {g5, kbh::inv(g5)};
-  for (int d = 0; d < 2; d++)
-    for (int e = 0; e < 16; e++) {
-      uint32_t w = kbh::from_monty(kbh::pow(g[d], e));
-      t.w[d][e] = w;
-      t.ws[d][e] = (uint32_t)(((uint64_t)w << 32) / kbh::P);
-    }
-  return t;
-}
-__device__ constexpr Tw32 TW32 = make_tw32();
-
-__device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t ws) {
-  uint32_t q = __umulhi(x, ws);
-  uint32_t r = x * w - q * kb::P;  // in [0, 2p)
-  return min(r, r - kb::P);
-}
-
-template <int DIR>
-__device__ __forceinline__ void dif32_shoup(uint32_t (&v)[32]) {
-#pragma unroll
-  for (int t = 0; t < 5; t++) {
-    const int half = 16 >> t;
-#pragma unroll
-    for (int x = 0; x < 32; x++) {
-      if ((x & half) == 0) {
-        const int e = (x & (half - 1)) << t;
-        uint32_t u = v[x], z = v[x + half];
-        v[x] = kb::add(u, z);
-        if (e == 0)
-          v[x + half] = kb::sub(u, z);
-        else
-          v[x + half] = shoup_mul(u - z + kb::P, TW32.w[DIR][e], TW32.ws[DIR][e]);
-      }
-    }
-  }
-}
-
 struct Pass10Extra {
   uint32_t dq[32];  // sigma^(q * 32 * 2^rem), Montgomery (FIRST passes only)
   uint32_t sigma;   // coset shift of this block (Montgomery)
@@ -217,7 +195,7 @@ __global__ void __launch_bounds__(512 / CPT, 2) ntt_pass10(PassArgs A, Pass10Ext
     F[t * P10_FSTRIDE + k] = f;
   }
 #pragma unroll
-  for (int c = 0; c < CPT; c++) dif32_shoup<DIR>(v[c]);
+  for (int c = 0; c < CPT; c++) dif_groups<5, DIR, 32>(v[c]);
   __syncthreads();  // F ready
 #pragma unroll
   for (int q = 0; q < 32; q++) {
@@ -247,7 +225,7 @@ __global__ void __launch_bounds__(512 / CPT, 2) ntt_pass10(PassArgs A, Pass10Ext
     }
   }
 #pragma unroll
-  for (int c = 0; c < CPT; c++) dif32_shoup<DIR>(v[c]);
+  for (int c = 0; c < CPT; c++) dif_groups<5, DIR, 32>(v[c]);
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     uint32_t i = tau * 32 + q;
@@ -364,6 +342,7 @@ inline cudaError_t launch_pass(const PassArgs& A, uint32_t k, cudaStream_t st) {
     case 3: return launch_reg<3, DIR>(A, st);
     case 4: return launch_reg<4, DIR>(A, st);
     case 5: return launch_reg<5, DIR>(A, st);
+    case 6: return launch_reg<6, DIR>(A, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -377,14 +356,14 @@ struct Cols {
 // Full transform of `nc` columns of a 2^log_n-row matrix: natural-order rows in (optionally gathered
 // through a bit reversal and scaled), bit-reversed rows out.  dst may alias src only when src_bitrev == 0.
 // Pass plan: as many k=10 passes (shared-memory kernel) as fit, preceded by one or two register-only passes
-// (k <= 5) for the remaining log_n mod 10 stages.  Register passes are plain streaming kernels.
+// (k <= 6) for the remaining log_n mod 10 stages.  Register passes are plain streaming kernels.
 inline uint32_t plan_passes(uint32_t log_n, uint32_t* ks) {
   uint32_t n10 = log_n / 10, r = log_n - 10 * n10, np = 0;
   if (log_n == 0) {
     ks[np++] = 0;
     return np;
   }
-  if (r > 5) {
+  if (r > 6) {
     ks[np++] = r - 5;
     ks[np++] = 5;
   } else if (r > 0) {

@@ -84,14 +84,6 @@ static int32_t ctx_init(zk_ctx* c) {
   uint64_t thr = UINT64_MAX;
   CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CK(ntt::configure_device());
-  // constant twiddles of the size-32 DFT
-  uint32_t w32[2][16];
-  uint32_t g5 = kbh::two_adic_generator(5), g5i = kbh::inv(g5);
-  for (int e = 0; e < 16; e++) {
-    w32[0][e] = kbh::pow(g5, e);
-    w32[1][e] = kbh::pow(g5i, e);
-  }
-  CK(cudaMemcpyToSymbolAsync(ntt::c_w32, w32, sizeof w32, 0, cudaMemcpyHostToDevice, c->stream));
   // global tables of g_L^(+-e)
   uint64_t half = 1ull << (c->log_L - 1);
   uint32_t gL = kbh::two_adic_generator(c->log_L);
@@ -402,7 +394,8 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     c->slab_used[b] = true;
     if (leaves) {
       ProfScope ps(c, "leaf_hash");
-      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + 255) / 256), 256, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
+      const unsigned bs = H < (1ull << 19) ? 128 : 256;
+      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + bs - 1) / bs), bs, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
                 (int)(k + 1 == nslab), leaves);
       CK(cudaGetLastError());
       c->launches++;
@@ -417,15 +410,17 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
 // MMCS
 // ------------------------------------------------------------------------------------------------
 static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t h, uint32_t* out) {
-  unsigned blocks = (unsigned)((h + 255) / 256);
+  // fewer than ~3 resident CTAs of 256 threads per SM: use 128-thread CTAs so the rows spread evenly over the SMs
+  const unsigned bs = h < (1ull << 19) ? 128 : 256;
+  unsigned blocks = (unsigned)((h + bs - 1) / bs);
   if (g.size() == 1 && g[0].w % 8 == 0 && g[0].w > 0 && ((uintptr_t)g[0].ptr % 32) == 0) {
-    ZK_LAUNCH(mk::hash_rows_w8, blocks, 256, 0, c->stream, g[0].ptr, g[0].w, h, out);
+    ZK_LAUNCH(mk::hash_rows_w8, blocks, bs, 0, c->stream, g[0].ptr, g[0].w, h, out);
   } else {
     mk::MatDesc* d = nullptr;
     int32_t rc;
     if ((rc = dev_alloc(c, g.size() * sizeof(mk::MatDesc), (void**)&d))) return rc;
     CK(cudaMemcpyAsync(d, g.data(), g.size() * sizeof(mk::MatDesc), cudaMemcpyHostToDevice, c->stream));
-    ZK_LAUNCH(mk::hash_rows_multi, blocks, 256, 0, c->stream, d, (uint32_t)g.size(), h, out);
+    ZK_LAUNCH(mk::hash_rows_multi, blocks, bs, 0, c->stream, d, (uint32_t)g.size(), h, out);
     CK(cudaGetLastError());
     if ((rc = dev_free(c, d))) return rc;
   }
