@@ -2,6 +2,7 @@
 // include/zkgpu.h.  sm_100a only; no CPU fallback.
 #include "zkgpu_internal.cuh"
 #include "merkle.cuh"
+#include "kb31.cuh"
 #include "ntt.cuh"
 
 thread_local std::string g_last_error;
@@ -15,6 +16,21 @@ int32_t zk_fail(int32_t code, const std::string& msg) {
 // small kernels local to this file
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// tw[e] = base^e for e < count (base = g_L or its inverse); one thread per entry, square-and-multiply.
+__global__ void powers_kernel(uint32_t* out, uint64_t count, uint32_t base, uint32_t init) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  uint32_t r = init, b = base;
+  uint64_t k = e;
+  while (k) {
+    if (k & 1) r = kb::mul(r, b);
+    b = kb::mul(b, b);
+    k >>= 1;
+  }
+  out[e] = r;
+}
+
 
 // out row r = in row bitrev(r)  (natural <-> bit-reversed order), one thread per word
 __global__ void bitrev_rows_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t log_h,
@@ -89,7 +105,7 @@ static int32_t ctx_init(zk_ctx* c) {
   uint32_t gL = kbh::two_adic_generator(c->log_L);
   for (int d = 0; d < 2; d++) {
     CK(cudaMalloc(&c->tw[d], half * 4));
-    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((half + 255) / 256), 256, 0, c->stream, c->tw[d], half,
+    ZK_LAUNCH(powers_kernel, (unsigned)((half + 255) / 256), 256, 0, c->stream, c->tw[d], half,
                                                                               d == 0 ? gL : kbh::inv(gL), kbh::ONE);
     CK(cudaGetLastError());
     c->launches++;
@@ -265,12 +281,12 @@ static int32_t lde_scales(zk_ctx* c, uint64_t h, uint32_t log_blowup, uint32_t s
     out[t].sigma = kbh::mul(shift, kbh::pow(gnb, kbh::bitrev(t, log_blowup)));
     out[t].hinv = hinv;
     (void)aligned;
-    if (n >= 10 && n % 10 == 0) continue;  // first pass = second-generation k=10 pass: derives the scale itself
+    if (ntt::first_pass_is_smem(n)) continue;  // a shared-memory first pass derives the scale itself
     uint32_t* v = nullptr;
     int32_t rc = dev_alloc(c, h * 4ull, (void**)&v);
     if (rc) return rc;
     out[t].vec = v;
-    ZK_LAUNCH(ntt::powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, v, h, out[t].sigma, hinv);
+    ZK_LAUNCH(powers_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, v, h, out[t].sigma, hinv);
     CK(cudaGetLastError());
     c->launches++;
   }
