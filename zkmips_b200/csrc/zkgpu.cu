@@ -79,8 +79,6 @@ static int32_t ctx_init(zk_ctx* c) {
     c->own_stream = true;
   }
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->hash_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&c->hash_done, cudaEventDisableTiming));
   if (const char* e = getenv("ZK_SLAB_COLS")) {
     int v = atoi(e);
     if (v >= 16 && v % 16 == 0) c->slab_cols = (uint32_t)v;
@@ -151,8 +149,6 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
     if (c->slab_free[b]) cudaEventDestroy(c->slab_free[b]);
   }
   if (c->pool) cudaMemPoolDestroy(c->pool);
-  if (c->hash_stream) cudaStreamDestroy(c->hash_stream);
-  if (c->hash_done) cudaEventDestroy(c->hash_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -200,7 +196,7 @@ extern "C" int32_t zk_prof_get(zk_ctx* c, int32_t i, char* name, int32_t cap, fl
 }
 extern "C" uint64_t zk_launch_count(zk_ctx* c) { return c ? c->launches : 0; }
 
-ProfScope::ProfScope(zk_ctx* c, const char* name, cudaStream_t stream) : c(c), st(stream ? stream : c->stream) {
+ProfScope::ProfScope(zk_ctx* c, const char* name) : c(c) {
   if (!c->prof) return;
   idx = (int)c->recs.size();
   zk_ctx::Rec r;
@@ -208,13 +204,13 @@ ProfScope::ProfScope(zk_ctx* c, const char* name, cudaStream_t stream) : c(c), s
   r.launches = c->launches;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
-  cudaEventRecord(r.a, st);
+  cudaEventRecord(r.a, c->stream);
   c->recs.push_back(r);
 }
 ProfScope::~ProfScope() {
   if (idx < 0) return;
   auto& r = c->recs[idx];
-  cudaEventRecord(r.b, st);
+  cudaEventRecord(r.b, c->stream);
   r.launches = c->launches - r.launches;
 }
 
@@ -369,10 +365,8 @@ static int32_t ensure_slab_bufs(zk_ctx* c, uint64_t bytes) {
 // resumable leaf sponge (compute stream), double buffered.  The slab buffer doubles as the coefficient
 // buffer (in-place inverse transform), so no full-size staging copy of the trace exists on the device.
 // When `leaves` is non-null the rows of the LDE are hashed slab by slab (w must be a multiple of 8).
-// With a DEVICE source the same slab loop runs without the upload (the inverse transform reads the source
-// columns and writes the slab buffer), which still lets the sponge of slab k overlap the transforms of k+1.
-static int32_t lde_stream(zk_ctx* c, const uint32_t* host, bool src_is_host, uint64_t h, uint32_t w, uint32_t log_blowup,
-                          uint32_t shift, uint32_t* out, uint32_t* leaves, uint32_t* keep_trace) {
+static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
+                               uint32_t* out, uint32_t* leaves, uint32_t* keep_trace) {
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
   if (w == 0) return ZK_OK;
@@ -401,48 +395,31 @@ static int32_t lde_stream(zk_ctx* c, const uint32_t* host, bool src_is_host, uin
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
     const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = k * slab, nc = std::min(slab, w - c0);
     uint32_t* buf = c->slab_buf[b];
+    if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
+    CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+                         c->copy_stream));
+    CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
+    if (keep_trace)  // retain the slab before the in-place inverse transform overwrites it
+      CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h, cudaMemcpyDeviceToDevice,
+                           c->stream));
     ntt::Cols sl{buf, nc, 0};
-    if (src_is_host) {
-      if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
-      CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
-                           c->copy_stream));
-      CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
-      CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
-      if (keep_trace)  // retain the slab before the in-place inverse transform overwrites it
-        CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h,
-                             cudaMemcpyDeviceToDevice, c->stream));
-      rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
-    } else {
-      rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(host), w, c0}, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
-    }
+    rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
     if (rc) break;
     CK(cudaEventRecord(c->slab_free[b], c->stream));
     c->slab_used[b] = true;
     if (leaves) {
-      // the sponge runs on its own stream: it only needs this slab's LDE columns, so the next slab's transforms
-      // (compute stream) fill the SM capacity the register-bound sponge leaves idle
-      CK(cudaStreamWaitEvent(c->hash_stream, c->slab_free[b], 0));
-      ProfScope ps(c, "leaf_hash", c->hash_stream);
+      ProfScope ps(c, "leaf_hash");
       const unsigned bs = H < (1ull << 19) ? 128 : 256;
-      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + bs - 1) / bs), bs, 0, c->hash_stream, out, w, c0, nc >> 3, H, state,
-                (int)(k == 0), (int)(k + 1 == nslab), leaves);
+      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + bs - 1) / bs), bs, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
+                (int)(k + 1 == nslab), leaves);
       CK(cudaGetLastError());
       c->launches++;
-      c->hash_pending = true;
     }
   }
   free_scales(c, scales);
-  if (state) CK(cudaFreeAsync(state, c->hash_stream));  // ordered after the last sponge that used it
+  if (state) dev_free(c, state);
   return rc;
-}
-
-// the compute stream continues (tree building, frees) only after every sponge enqueued on the hash stream
-static int32_t join_hash_stream(zk_ctx* c) {
-  if (!c->hash_pending) return ZK_OK;
-  CK(cudaEventRecord(c->hash_done, c->hash_stream));
-  CK(cudaStreamWaitEvent(c->stream, c->hash_done, 0));
-  c->hash_pending = false;
-  return ZK_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,7 +608,7 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
     for (uint32_t i = 0; i < n_mats; i++) members[pd->heights[i]]++;
     std::vector<uint32_t*> stream_digests(n_mats, nullptr);
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
-      if (!(members[pd->heights[i]] == 1 && widths[i] > 0 && widths[i] % 8 == 0)) continue;
+      if (!(src_is_host && members[pd->heights[i]] == 1 && widths[i] > 0 && widths[i] % 8 == 0)) continue;
       if (pd->heights[i] == hmax) {
         stream_digests[i] = pd->digests;
         leaves_done = true;
@@ -653,7 +630,10 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
           pd->traces[i] = const_cast<uint32_t*>(src[i]);  // borrowed: the caller keeps it alive
         }
       }
-      rc = lde_stream(c, src[i], src_is_host, heights[i], widths[i], log_blowup, shift, pd->mats[i], stream_digests[i], keep);
+      if (src_is_host)
+        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], stream_digests[i], keep);
+      else
+        rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
     }
   } else {
     for (uint32_t i = 0; i < n_mats; i++) {
@@ -661,8 +641,6 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       pd->mats[i] = const_cast<uint32_t*>(src[i]);
     }
   }
-  int32_t rcj = join_hash_stream(c);
-  if (rc == ZK_OK) rc = rcj;
   if (rc == ZK_OK) rc = mmcs_build(c, pd, true, leaves_done);
   if (rc != ZK_OK) {
     pdata_release(pd);

@@ -28,9 +28,6 @@ struct zk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaStream_t hash_stream = nullptr;   // row sponges of finished slabs, concurrent with the next slab's transforms
-  cudaEvent_t hash_done = nullptr;      // last sponge enqueued on hash_stream
-  bool hash_pending = false;
   cudaMemPool_t pool = nullptr;         // private stream-ordered allocator of this context
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
   uint32_t* slab_buf[2] = {nullptr, nullptr};  // double-buffered upload slabs, shared by all matrices / calls
@@ -58,8 +55,7 @@ struct zk_ctx {
 struct ProfScope {
   zk_ctx* c;
   int idx = -1;
-  cudaStream_t st;
-  ProfScope(zk_ctx* c, const char* name, cudaStream_t stream = nullptr);  // default: the context's compute stream
+  ProfScope(zk_ctx* c, const char* name);
   ~ProfScope();
 };
 
