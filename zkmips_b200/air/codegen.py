@@ -167,8 +167,7 @@ def generate(airs):
             out.append("  if (i >= (1u << (A.log_n + A.lqd))) return;")
             out.append("  quot::Row R;")
             out.append("  quot::prologue(A, i, R);")
-            out.append("  quot::Fold acc;")
-            out.append("  quot::fold_init(acc);")
+            out.append("  kb::Ext acc = kb::ext_zero();")
             # demand-driven emission: a node is materialised right before the first constraint that needs
             # it, which keeps live ranges (registers) short for wide chips
             done = set()
@@ -178,7 +177,7 @@ def generate(airs):
                         done.add(n)
                         out.append("  " + _emit_node(air, n))
                 f = "fold_b" if air.types[c] == "b" else "fold_e"
-                out.append(f"  quot::{f}(acc, A.alpha_pows + {8 * k}, n{c});")
+                out.append(f"  acc = quot::{f}(acc, A.alpha_pows + {4 * k}, n{c});")
             out.append(f"  quot::epilogue(A, i, R, acc, {'true' if pi == 0 else 'false'});")
             out.append("}")
             out.append("")

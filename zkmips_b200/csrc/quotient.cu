@@ -9,11 +9,10 @@ __global__ void alpha_pows_rev_kernel(const uint32_t* alpha, uint32_t n, uint32_
   if (k >= n) return;
   kb::Ext a{{alpha[0], alpha[1], alpha[2], alpha[3]}};
   kb::Ext r = kb::ext_pow(a, n - 1 - k);
-#pragma unroll
-  for (int e = 0; e < 4; e++) {  // split layout: low 16 bits of the 4 coefficients, then the high bits
-    out[8 * k + e] = r.c[e] & 0xffffu;
-    out[8 * k + 4 + e] = r.c[e] >> 16;
-  }
+  out[4 * k + 0] = r.c[0];
+  out[4 * k + 1] = r.c[1];
+  out[4 * k + 2] = r.c[2];
+  out[4 * k + 3] = r.c[3];
 }
 
 }  // namespace quot
@@ -95,7 +94,7 @@ extern "C" int32_t zk_quotient(zk_ctx* c, int32_t air_id, const zk_pdata* prep, 
   if (n_public_values) memcpy(host.data() + 22 + 4 * n_chal, public_values, 4ull * n_public_values);
   uint32_t *d_in = nullptr, *d_ap = nullptr, *d_out = nullptr;
   if ((rc = dev_alloc(c, host.size() * 4, (void**)&d_in))) return rc;
-  if ((rc = dev_alloc(c, std::max(e.n_constraints, 1u) * 32ull, (void**)&d_ap))) return rc;
+  if ((rc = dev_alloc(c, std::max(e.n_constraints, 1u) * 16ull, (void**)&d_ap))) return rc;
   if ((rc = dev_alloc(c, qsize * 16, (void**)&d_out))) return rc;
   CK(cudaMemcpyAsync(d_in, host.data(), host.size() * 4, cudaMemcpyHostToDevice, c->stream));
   if (e.n_constraints) {

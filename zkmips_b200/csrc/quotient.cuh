@@ -14,7 +14,6 @@
 #include <cuda_runtime.h>
 
 #include "kb31.cuh"
-#include "kb31_host.h"
 
 namespace quot {
 
@@ -22,8 +21,7 @@ struct Args {
   const uint32_t* prep;
   const uint32_t* main;
   const uint32_t* perm;
-  const uint32_t* alpha_pows;  // alpha_pows[k] = alpha^(n_constraints-1-k), 8 words each: the 4 coefficients'
-                               // low 16 bits, then their high bits (lazy dot product, see fold_b)
+  const uint32_t* alpha_pows;  // alpha_pows[k] = alpha^(n_constraints-1-k), 4 words each
   const uint32_t* chal;        // permutation challenges, 4 words each
   const uint32_t* pvs;         // public values
   const uint32_t* lcs;         // local cumulative sum (4)
@@ -71,45 +69,17 @@ __device__ __forceinline__ void prologue(const Args& A, uint32_t i, Row& R) {
   R.is_trans = b;
 }
 
-// ProverConstraintFolder::assert_zero / assert_zero_ext (folder.rs:79-84,94-102).
-// Base-field constraints (almost all of them) are folded LAZILY: with alpha^k split into 16-bit halves,
-// acc_lo += lo(alpha^k) * C and acc_hi += hi(alpha^k) * C are single 64-bit IMAD.WIDE accumulations (terms
-// < 2^47, a part has far fewer than 2^16 constraints), 8 per constraint instead of 4 Montgomery products and
-// 4 modular additions; one reduction per point at the end.  Extension constraints use a full product.
-struct Fold {
-  uint64_t lo[4], hi[4];
-  kb::Ext ext;
-};
-__device__ __forceinline__ void fold_init(Fold& f) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) f.lo[k] = f.hi[k] = 0;
-  f.ext = kb::ext_zero();
+// ProverConstraintFolder::assert_zero / assert_zero_ext (folder.rs:79-84,94-102)
+__device__ __forceinline__ kb::Ext fold_b(kb::Ext acc, const uint32_t* ap, uint32_t c) {
+  return kb::ext_add(acc, kb::ext_mul_base(ld_ext(ap), c));
 }
-__device__ __forceinline__ void fold_b(Fold& f, const uint32_t* ap, uint32_t c) {
-  uint4 wl = __ldg(reinterpret_cast<const uint4*>(ap)), wh = __ldg(reinterpret_cast<const uint4*>(ap) + 1);
-  f.lo[0] += (uint64_t)wl.x * c; f.lo[1] += (uint64_t)wl.y * c; f.lo[2] += (uint64_t)wl.z * c; f.lo[3] += (uint64_t)wl.w * c;
-  f.hi[0] += (uint64_t)wh.x * c; f.hi[1] += (uint64_t)wh.y * c; f.hi[2] += (uint64_t)wh.z * c; f.hi[3] += (uint64_t)wh.w * c;
-}
-__device__ __forceinline__ void fold_e(Fold& f, const uint32_t* ap, kb::Ext c) {
-  uint4 wl = __ldg(reinterpret_cast<const uint4*>(ap)), wh = __ldg(reinterpret_cast<const uint4*>(ap) + 1);
-  kb::Ext a{{wl.x | (wh.x << 16), wl.y | (wh.y << 16), wl.z | (wh.z << 16), wl.w | (wh.w << 16)}};
-  f.ext = kb::ext_add(f.ext, kb::ext_mul(a, c));
-}
-constexpr uint32_t QUOT_TWO16_MONTY = kbh::to_monty(1u << 16);
-__device__ __forceinline__ uint32_t fold_reduce1(uint64_t lo, uint64_t hi) {  // (hi * 2^16 + lo) * R^-1 mod p
-  uint64_t fl = (lo >> 32) * (uint64_t)kb::ONE + (lo & 0xffffffffull);
-  uint64_t fh = (hi >> 32) * (uint64_t)kb::ONE + (hi & 0xffffffffull);
-  return kb::add(kb::mont_reduce64(fl), kb::mul(kb::mont_reduce64(fh), QUOT_TWO16_MONTY));
-}
-__device__ __forceinline__ kb::Ext fold_finish(const Fold& f) {
-  kb::Ext e{{fold_reduce1(f.lo[0], f.hi[0]), fold_reduce1(f.lo[1], f.hi[1]), fold_reduce1(f.lo[2], f.hi[2]),
-             fold_reduce1(f.lo[3], f.hi[3])}};
-  return kb::ext_add(e, f.ext);
+__device__ __forceinline__ kb::Ext fold_e(kb::Ext acc, const uint32_t* ap, kb::Ext c) {
+  return kb::ext_add(acc, kb::ext_mul(ld_ext(ap), c));
 }
 
 // quotient = accumulator * inv_zeroifier (quotient.rs:160), written into chunk i mod 2^lqd (prover.rs:477-488)
-__device__ __forceinline__ void epilogue(const Args& A, uint32_t i, const Row& R, const Fold& f, bool first_part) {
-  kb::Ext q = kb::ext_mul_base(fold_finish(f), R.inv_zh);
+__device__ __forceinline__ void epilogue(const Args& A, uint32_t i, const Row& R, kb::Ext acc, bool first_part) {
+  kb::Ext q = kb::ext_mul_base(acc, R.inv_zh);
   uint32_t c = i & ((1u << A.lqd) - 1), j = i >> A.lqd;
   uint4* o = reinterpret_cast<uint4*>(A.out + (((size_t)c << A.log_n) + j) * 4);
   if (!first_part) {
