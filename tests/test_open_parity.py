@@ -133,3 +133,36 @@ def test_open_large_default_params():
     ctx = backends.gpu()
     mats = [[_mont(1 << 12, 7, 1)], [_mont(1 << 14, 64, 2), _mont(1 << 10, 19, 3)], [_mont(1 << 14, 8, 4)]]
     _run(ctx, mats, 1, lambda m: 2, nq=84, pow_bits=16)
+
+
+@pytest.mark.gpu
+def test_reference_pcs_inner_inputs():
+    """The deterministic inputs of the reference's own PCS test, `test_verify_two_adic_pcs_inner`
+    (crates/recursion/circuit/src/fri.rs:817-871): two 2^19 x 100 matrices with entries from_canonical_u32(i),
+    inner_fri_config (blowup 2, 84 queries, 16 PoW bits), transcript = observe(commit), zeta = sample_ext,
+    every matrix opened at zeta.  The commitment must equal the oracle's and the proof must be accepted by the
+    transliterated verifier (the reference asserts exactly `pcs.verify(...).unwrap()`)."""
+    ctx = backends.gpu()
+    h, w = 1 << 19, 100
+    canon = (np.arange(h * w, dtype=np.uint64) % P).astype(np.uint32).reshape(h, w)
+    mat = ob.to_monty(canon)
+    one = ob.lib().ork_to_monty(1)
+    root, pd = ctx.commit([mat, mat], [one, one], 1)
+    tree = ob.pcs_commit([mat, mat], 1)
+    assert (root == tree.root).all()
+    och = bf.new_challenger()
+    bf.observe(och, root)
+    zeta = bf.sample_ext(och)
+    ch_v = bf.Challenger.from_words(och.words())
+    dch = Challenger(ctx, och.words())
+    pts = [[zeta], [zeta]]
+    proof = pcs_open(ctx, [pd], pts, dch, 1, 84, 16)
+    n_mats, hs, ws = bf.shapes_of([tree])
+    assert bf.pcs_verify([root], n_mats, hs, ws, pts, ch_v, proof, 1, 84, 16) == 1
+    assert (dch.w == ch_v.words()).all()
+    # opened values = p_j(zeta): spot-check column 0 against the oracle's own opening of the same commitment
+    och2 = bf.Challenger.from_words(och.words())
+    wit = int(proof[2 * w * 4 + 20 * 8 + 4])
+    proof_o = bf.pcs_open([tree], pts, och2, 1, 84, 16, inject_witness=wit)
+    assert (proof_o == proof).all()
+    pd.free()
