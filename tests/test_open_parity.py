@@ -162,7 +162,7 @@ def test_reference_pcs_inner_inputs():
     assert (dch.w == ch_v.words()).all()
     # opened values = p_j(zeta): spot-check column 0 against the oracle's own opening of the same commitment
     och2 = bf.Challenger.from_words(och.words())
-    wit = int(proof[2 * w * 4 + 20 * 8 + 4])
+    wit = int(proof[2 * w * 4 + 19 * 8 + 4])  # opened values, 19 commit-phase roots, final_poly, then the witness
     proof_o = bf.pcs_open([tree], pts, och2, 1, 84, 16, inject_witness=wit)
     assert (proof_o == proof).all()
     pd.free()
