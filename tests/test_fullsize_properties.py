@@ -43,6 +43,12 @@ def test_full_size_commit_properties():
     assert lde.shape == (1 << (log_n + 1), w)
     # Montgomery form is linear, so the identity holds on the Montgomery words as well
     assert (_colsum(lde) == (2 * _colsum(tr)) % P).all()
+    # pinned host memory takes the streaming path (slabs, resumable sponge), pageable the contiguous one
+    import torch
+    pinned = torch.from_numpy(tr.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    root_p, pd_p = ctx.commit([pinned], [ONE], 1)
+    assert (root_p == root).all()
+    pd_p.free()
     # device-resident commit gives the same root
     dptr = ctx.upload(tr)
     root2, pd2 = ctx.commit_dev([dptr], [tr.shape], [ONE], 1)

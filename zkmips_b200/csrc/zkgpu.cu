@@ -342,6 +342,8 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
   return rc;
 }
 
+static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t h, uint32_t* out);
+
 // (Re)allocates the context's two slab buffers when a larger slab is needed (rare; synchronises).
 static int32_t ensure_slab_bufs(zk_ctx* c, uint64_t bytes) {
   if (bytes <= c->slab_cap) return ZK_OK;
@@ -372,6 +374,24 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   if (w == 0) return ZK_OK;
   if (!host) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
   const uint64_t H = h << log_blowup;
+  // Pageable host memory (a plain Rust Vec): strided 2-D copies from it crawl (measured 4 GB/s), so the trace goes
+  // up in ONE contiguous copy and the device-resident path takes over.  Pinned / registered buffers stream.
+  cudaPointerAttributes pa;
+  bool pinned = cudaPointerGetAttributes(&pa, host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // unregistered pointers may leave a sticky-less error code behind on old drivers
+  if (!pinned && (uint64_t)h * w * 4 >= c->stream_min_bytes && c->slab_cols == 0) {
+    uint32_t* stage = keep_trace;
+    if (!stage && (rc = dev_alloc(c, h * w * 4ull, (void**)&stage))) return rc;
+    CK(cudaMemcpyAsync(stage, host, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
+    rc = lde_dev(c, stage, h, w, log_blowup, shift, out);
+    if (rc == ZK_OK && leaves) {
+      ProfScope ps(c, "leaf_hash");
+      std::vector<mk::MatDesc> grp{mk::MatDesc{out, w}};
+      rc = hash_group(c, grp, H, leaves);
+    }
+    if (!keep_trace) dev_free(c, stage);
+    return rc;
+  }
   // slab width: a fixed number of columns when ZK_SLAB_COLS is set, otherwise as many columns as make
   // ~slab_bytes (a multiple of 16 columns, >= 32): short-and-wide traces must not be cut into tiny slabs
   uint32_t slab = c->slab_cols;
