@@ -308,6 +308,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libzkgpu has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     log_rows, cols = args.log_rows, args.cols

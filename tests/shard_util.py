@@ -41,6 +41,17 @@ def wide_chip(log_n, width=64, seed=1, name=None):
     return Chip(name or f"Wide{width}", f"wide_bitwise_{width}", M(t))
 
 
+def quintic_chip(log_n, seed=5, name="Quintic"):
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    a = (np.arange(n, dtype=np.uint64) + 3) % P
+    b = rng.integers(0, P, n).astype(np.uint64)
+    b[0] = 1
+    a2 = a * a % P
+    d = a2 * a2 % P * b % P
+    return Chip(name, "quintic", M(np.stack([a, b, d], axis=1)), log_quotient_degree=2)
+
+
 def lookup_chip(log_n, seed=3, name="Lookup"):
     """valid trace for library.lookup_pair (its LogUp permutation trace is generated on the device)"""
     n = 1 << log_n

@@ -196,3 +196,34 @@ def test_one_process_two_devices():
         ctx.destroy()
     assert (roots[0] == roots[1]).all() and (roots[0] == roots[2]).all()
     assert (roots[0] == ob.pcs_commit([m], 1).root).all()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_quotient_degree_four_chunks(be):
+    """log_quotient_degree = 2 with blowup 4 (the shrink configuration): four quotient chunks on shifted domains,
+    quotient values against the numpy restatement and the whole proof against the verifier identity
+    (recompute_quotient with four chunk domains, crates/stark/src/verifier.rs:400-435)."""
+    ctx = _backend(be)
+    chip = su.quintic_chip(5)
+    air = su.AIRS[chip.air]
+    assert air.max_degree() == 5
+    n = chip.log_degree
+    _, main_pd = ctx.commit([chip.main], [MONTY_ONE], 2)
+    alpha = su.M([9, 8, 7, 6])
+    dptr = ctx.quotient(chip.air, (main_pd, 0), n, 2, alpha)
+    got = ob.from_monty(ctx.download(dptr, (4, 1 << n, 4)))
+    ctx.dev_free(dptr)
+    lde_nat = _natural(main_pd.lde(0))  # quotient domain = the whole LDE here (n + 2 bits)
+    exp = ae.quotient_values(air, n, 2, lde_nat, ob.from_monty(alpha))
+    for c in range(4):
+        assert (got[c] == exp[c::4]).all()
+    main_pd.free()
+    nq, pw = (6, 4) if be == "emu" else (42, 16)
+    prover = GpuShardProver(ctx, 2, nq, pw)
+    ch = Challenger(ctx)
+    start = ch.w.copy()
+    ordered, root, pd = prover.commit([chip, su.fibonacci_chip(4)])
+    sp = prover.open(ordered, root, pd, ch)
+    ok, why = su.verify_shard(sp, ordered, start, 2, nq, pw)
+    assert ok, why
+    pd.free()

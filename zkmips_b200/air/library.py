@@ -59,6 +59,20 @@ def lookup_pair():
     return air
 
 
+def quintic():
+    """Degree-5 chip: log_quotient_degree = 2 (four quotient chunks; needs log_blowup >= 2, the shrink configuration
+    crates/stark/src/kb31_poseidon2.rs:217-227).  Columns (a, b, d): d = a^4 * b, next.a = a + 1 on transitions,
+    b boolean on the first row."""
+    air = Air("quintic", main_width=3)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    a2 = m[0] * m[0]
+    b.assert_eq(m[2], a2 * a2 * m[1])
+    b.when_transition().assert_eq(mn[0], m[0] + 1)
+    b.when_first_row().assert_bool(m[1])
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(1024, "wide_bitwise_1024"),
-            wide_bitwise(4096, "wide_bitwise_4096")]
+            wide_bitwise(4096, "wide_bitwise_4096"), quintic()]
