@@ -136,6 +136,68 @@ class ProverData {
   std::shared_ptr<zk_pdata> p_;
 };
 
+// TwoAdicSubgroupDft (the trait `Radix2DitParallel` implements; type alias crates/stark/src/kb31_poseidon2.rs:179)
+class GpuDft {
+ public:
+  explicit GpuDft(Context& c) : c_(c) {}
+  // dft_batch: natural-order DFT of every column
+  std::vector<Val> dft_batch(const RowMajorMatrixView& m) const {
+    std::vector<Val> out(m.height * m.width);
+    check(zk_dft_batch(c_.raw(), m.values, m.height, m.width, out.data()));
+    return out;
+  }
+  // coset_lde_batch(mat, added_bits, shift).bit_reverse_rows(): (height << added_bits) rows
+  std::vector<Val> coset_lde_batch(const RowMajorMatrixView& m, uint32_t added_bits, Val shift) const {
+    std::vector<Val> out((m.height << added_bits) * m.width);
+    check(zk_coset_lde(c_.raw(), m.values, m.height, m.width, added_bits, shift, out.data()));
+    return out;
+  }
+
+ private:
+  Context& c_;
+};
+
+// MerkleTreeMmcs<_, _, MyHash, MyCompress, 8> (crates/stark/src/kb31_poseidon2.rs:176-177): commit / open_batch.
+// (verify_batch stays on the CPU side of the caller, as in the reference's verifier.)
+class MerkleTreeMmcs {
+ public:
+  explicit MerkleTreeMmcs(Context& c) : c_(c) {}
+  std::pair<Digest, ProverData> commit(const std::vector<RowMajorMatrixView>& mats) const {
+    std::vector<const Val*> ptrs;
+    std::vector<uint64_t> hs;
+    std::vector<uint32_t> ws;
+    for (auto& m : mats) {
+      ptrs.push_back(m.values);
+      hs.push_back(m.height);
+      ws.push_back(m.width);
+    }
+    Digest root;
+    zk_pdata* pd = nullptr;
+    check(zk_mmcs_commit(c_.raw(), (uint32_t)mats.size(), ptrs.data(), hs.data(), ws.data(), root.data(), &pd));
+    return {root, ProverData(pd)};
+  }
+  // open_batch(index, data) -> (opened rows per matrix, sibling digests bottom-up)
+  std::pair<std::vector<std::vector<Val>>, std::vector<Digest>> open_batch(uint64_t index, const ProverData& pd) const {
+    uint32_t sum_w = 0;
+    for (uint32_t i = 0; i < pd.num_matrices(); i++) sum_w += pd.width(i);
+    std::vector<Val> flat(sum_w ? sum_w : 1), path((size_t)pd.log_max_height() * 8 + 8);
+    check(zk_pdata_open_batch(pd.raw(), 1, &index, flat.data(), path.data()));
+    std::vector<std::vector<Val>> rows;
+    const Val* p = flat.data();
+    for (uint32_t i = 0; i < pd.num_matrices(); i++) {
+      rows.emplace_back(p, p + pd.width(i));
+      p += pd.width(i);
+    }
+    std::vector<Digest> proof(pd.log_max_height());
+    for (uint32_t l = 0; l < pd.log_max_height(); l++)
+      for (int k = 0; k < 8; k++) proof[l][k] = path[8 * l + k];
+    return {rows, proof};
+  }
+
+ private:
+  Context& c_;
+};
+
 // DuplexChallenger whose permutations run on the device
 class DuplexChallenger {
  public:

@@ -64,7 +64,17 @@ int main(int argc, char** argv) {
     };
     auto [opened, proof] = pcs.open(rounds, ch);
 
+    // trait-level pieces: TwoAdicSubgroupDft::coset_lde_batch and Mmcs::{commit, open_batch}
+    GpuDft dft(ctx);
+    std::vector<Val> lde = dft.coset_lde_batch(RowMajorMatrixView{trace.data(), n, 2}, 1, field::GENERATOR);
+    MerkleTreeMmcs mmcs(ctx);
+    auto [mmcs_root, mmcs_data] = mmcs.commit({RowMajorMatrixView{lde.data(), 2 * n, 2}});
+    auto [rows, path] = mmcs.open_batch(5, mmcs_data);
+
     printf("{\n");
+    print_words("mmcs_root_of_lde", mmcs_root.data(), 8);
+    print_words("opened_row_5", rows[0].data(), rows[0].size());
+    printf("\"path_len\": %zu,\n", path.size());
     print_words("main_commit", main_commit.data(), 8);
     print_words("quotient_commit", quotient_commit.data(), 8);
     print_words("alpha", alpha.data(), 4);

@@ -30,6 +30,10 @@ def _run_and_check(exe, log_n, nq, pw):
     chip = su.fibonacci_chip(log_n)
     tree = ob.pcs_commit([chip.main], 1)
     assert got["main_commit"] == [int(x) for x in tree.root]
+    # Dft + Mmcs used separately give the same tree as Pcs::commit
+    assert got["mmcs_root_of_lde"] == [int(x) for x in tree.root]
+    assert got["opened_row_5"] == [int(x) for x in tree.matrix(0)[5]]
+    assert got["path_len"] == log_n + 1
     ch = bf.new_challenger()
     bf.observe(ch, chip.public_values)
     bf.observe(ch, tree.root)
