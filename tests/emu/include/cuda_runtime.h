@@ -51,6 +51,7 @@ static inline void __syncwarp() {}
 static inline void __threadfence() {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int32_t __mulhi(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * b) >> 32); }
 static inline uint32_t __brev(uint32_t x) {
   uint32_t r = 0;
   for (int i = 0; i < 32; i++) { r = (r << 1) | (x & 1); x >>= 1; }

@@ -187,6 +187,32 @@ def test_streaming_commit_multi_slab(be, monkeypatch):
         ctx.destroy()
 
 
+@pytest.mark.parametrize("be", BACKENDS)
+def test_streaming_commit_tapered_slabs(be, monkeypatch):
+    """Default slab schedule of the streaming commit: the last full slab is cut in halves so that the tail
+    after the last upload is short (256 columns -> slabs of 64, 64, 64, 32, 32 columns).  Pinned host memory
+    on the GPU (pageable traces take the one-copy path), forced streaming for small matrices."""
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    monkeypatch.delenv("ZK_SLAB_COLS", raising=False)
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+
+    def pin(m):
+        if be != "gpu":
+            return m
+        import torch
+        return torch.from_numpy(m.view(np.int32)).pin_memory().numpy().view(np.uint32)
+
+    try:
+        _check_commit(ctx, [pin(_mont(64, 256, seed=41))], [one], 1)      # 64, 64, 64, 32, 32
+        _check_commit(ctx, [pin(_mont(32, 320, seed=42))], [one], 2)      # 80, 80, 80, 80 (80 is not cut: 40 % 8 != 0 is avoided)
+        _check_commit(ctx, [pin(_mont(64, 512, seed=43)), pin(_mont(16, 24, seed=44))], [one] * 2, 1)  # 128 x 3, 64, 64
+    finally:
+        ctx.destroy()
+
+
 def test_lde_two_pass_k10_emu():
     """2^20 rows x 2 columns: both k=10 passes of the second-generation kernel (coset scale + bit-reversed
     gather fused in the first, pass twiddles) on the emulator; the GPU twins are the 2^20 cases above."""

@@ -2,6 +2,7 @@
 // traffic) to pick the instruction mix that best balances the fmaheavy (IMAD*) and alu pipes on sm_100a.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bench/p2bench tools/bench/p2bench.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../zkmips_b200/csrc/kb31.cuh"
@@ -10,16 +11,24 @@
 __device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
 __device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
 constexpr uint32_t P = kb::P;
+// rolled-loop variants index the round constants at run time: constant bank (uniform LDC / ULDC)
+__constant__ uint32_t C_EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
+__constant__ uint32_t C_INT_RC[13] = ZK_P2_INT_RC_MONTY;
 
 // forced-ALU add: a 3-input add with an opaque zero cannot be turned into IMAD.IADD (fmaheavy pipe) by ptxas,
 // so it must issue as IADD3 on the alu pipe; used to rebalance the two integer pipes
 __device__ uint32_t g_zero_dev;  // 0 at run time, unknown at compile time
 __device__ __forceinline__ uint32_t add3z(uint32_t a, uint32_t b, uint32_t z) {
-  uint32_t s;
-  asm("add.u32 %0, %1, %2;\n\tadd.u32 %0, %0, %3;" : "=r"(s) : "r"(a), "r"(b), "r"(z));
+  uint32_t s = a + b + z;  // z is 0 at run time, unknown to the compiler: a true three-input add -> IADD3 (alu pipe)
   return min(s, s - P);
 }
-
+// forced-ALU modular add for operands that are not shared with other adds (so a - p cannot be hoisted):
+// t = a + b - p is a three-input add (IADD3, alu pipe only); correction min(t, t + p).
+__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b) {
+  uint32_t t;
+  asm("{\n\t.reg .u32 q;\n\tadd.u32 q, %1, %2;\n\tadd.u32 %0, q, %3;\n\t}" : "=r"(t) : "r"(a), "r"(b), "n"(0u - P));
+  return min(t, t + P);
+}
 // MUL variants -------------------------------------------------------------
 struct MulSub {  // product code: subtractive form, umulhi
   static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return kb::mul(a, b); }
@@ -47,18 +56,40 @@ struct MulLea {  // subtractive form, m = lo * MU through shifts (alu pipe) inst
 };
 
 template <class M> __device__ __forceinline__ uint32_t cube(uint32_t a) { return M::mul(M::lazy(a, a), a); }
+// S-box with the round constant folded in.  Default: modular add, then two Montgomery products.
+template <class M> struct Sbox {
+  static __device__ __forceinline__ uint32_t f(uint32_t x, uint32_t rc) { return cube<M>(kb::add(x, rc)); }
+};
+// Signed form: t = x + rc - p in [-p, p) needs no correction before it is squared; x2 = t*t*R^-1 stays in
+// (-p, p/2) uncorrected; the second product uses the signed Montgomery reduction (signed m, signed mulhi), whose
+// result is in (-p, p): ONE correction for the whole S-box (10 instructions instead of 11).
+struct MulSigned : MulSub {};
+template <> struct Sbox<MulSigned> {
+  static __device__ __forceinline__ uint32_t f(uint32_t x, uint32_t rc) {
+    int32_t t = (int32_t)(x + (rc - P));
+    int64_t T = (int64_t)t * t;
+    uint32_t m = (uint32_t)T * kb::MU;
+    int32_t x2 = (int32_t)((uint64_t)T >> 32) - (int32_t)__umulhi(m, P);
+    int64_t T2 = (int64_t)x2 * t;
+    int32_t m2 = (int32_t)((uint32_t)T2 * kb::MU);
+    int32_t r = (int32_t)(T2 >> 32) - __mulhi(m2, (int32_t)P);
+    return min((uint32_t)r, (uint32_t)r + P);
+  }
+};
 
-__device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
-  uint32_t t01 = kb::add(x0, x1), t23 = kb::add(x2, x3), t0123 = kb::add(t01, t23);
+template <int FM = 0>
+__device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t z) {
+  uint32_t t01 = FM >= 1 ? add3z(x0, x1, z) : kb::add(x0, x1), t23 = FM >= 1 ? add3z(x2, x3, z) : kb::add(x2, x3);
+  uint32_t t0123 = FM >= 2 ? add3z(t01, t23, z) : kb::add(t01, t23);
   uint32_t t01123 = kb::add(t0123, x1), t01233 = kb::add(t0123, x3);
   uint32_t n3 = kb::add(t01233, kb::dbl(x0)), n1 = kb::add(t01123, kb::dbl(x2));
-  uint32_t n0 = kb::add(t01123, t01), n2 = kb::add(t01233, t23);
+  uint32_t n0 = FM >= 3 ? add3z(t01123, t01, z) : kb::add(t01123, t01), n2 = FM >= 3 ? add3z(t01233, t23, z) : kb::add(t01233, t23);
   x0 = n0; x1 = n1; x2 = n2; x3 = n3;
 }
 template <int FA>
 __device__ __forceinline__ void external_layer(uint32_t (&s)[16], uint32_t z) {
 #pragma unroll
-  for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+  for (int i = 0; i < 16; i += 4) m4<(FA >= 4 ? FA - 3 : 0)>(s[i], s[i + 1], s[i + 2], s[i + 3], z);
   uint32_t sums[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -114,19 +145,82 @@ template <class M, int DIAG, int FA = 0> __device__ __forceinline__ void permute
 #pragma unroll
   for (int r = 0; r < 4; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = cube<M>(FA >= 3 ? add3z(s[i], EXT_RC[r][i], z) : kb::add(s[i], EXT_RC[r][i]));
+    for (int i = 0; i < 16; i++) s[i] = FA >= 3 ? cube<M>(add3z(s[i], EXT_RC[r][i], z)) : Sbox<M>::f(s[i], EXT_RC[r][i]);
     external_layer<FA>(s, z);
   }
 #pragma unroll
   for (int r = 0; r < 13; r++) {
-    s[0] = cube<M>(kb::add(s[0], INT_RC[r]));
+    s[0] = Sbox<M>::f(s[0], INT_RC[r]);
     internal_layer<M, DIAG>(s);
   }
 #pragma unroll
   for (int r = 4; r < 8; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = cube<M>(FA >= 3 ? add3z(s[i], EXT_RC[r][i], z) : kb::add(s[i], EXT_RC[r][i]));
+    for (int i = 0; i < 16; i++) s[i] = FA >= 3 ? cube<M>(add3z(s[i], EXT_RC[r][i], z)) : Sbox<M>::f(s[i], EXT_RC[r][i]);
     external_layer<FA>(s, z);
+  }
+}
+
+// Rolled variants: the fully unrolled permutation is ~4500 instructions = 72 KB of straight-line code, far more
+// than the instruction caches hold, and every warp streams it once per permutation (ncu: icc hit rate 57 %,
+// 44 % of stall cycles "no instruction").  ROLL 1: internal rounds in a loop; 2: external rounds too (two loops);
+// 3: one copy of the external-round body (phase loop); EU = unroll factor of the external-round loop.
+template <class M, int DIAG, int ROLL, int EU, int FA = 0>
+__device__ __forceinline__ void permute_rolled(uint32_t (&s)[16], uint32_t z = 0) {
+  external_layer<FA>(s, z);
+  if (ROLL == 3) {
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ph++) {
+#pragma unroll 1
+      for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = Sbox<M>::f(s[i], C_EXT_RC[ph * 4 + r][i]);
+        external_layer<FA>(s, z);
+      }
+      if (ph == 0) {
+#pragma unroll 1
+        for (int r = 0; r < 13; r++) {
+          s[0] = Sbox<M>::f(s[0], C_INT_RC[r]);
+          internal_layer<M, DIAG>(s);
+        }
+      }
+    }
+    return;
+  }
+  if (ROLL >= 2) {
+#pragma unroll EU
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) s[i] = Sbox<M>::f(s[i], C_EXT_RC[r][i]);
+      external_layer<FA>(s, z);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) s[i] = Sbox<M>::f(s[i], EXT_RC[r][i]);
+      external_layer<FA>(s, z);
+    }
+  }
+#pragma unroll 1
+  for (int r = 0; r < 13; r++) {
+    s[0] = Sbox<M>::f(s[0], C_INT_RC[r]);
+    internal_layer<M, DIAG>(s);
+  }
+  if (ROLL >= 2) {
+#pragma unroll EU
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) s[i] = Sbox<M>::f(s[i], C_EXT_RC[r][i]);
+      external_layer<FA>(s, z);
+    }
+  } else {
+#pragma unroll
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) s[i] = Sbox<M>::f(s[i], EXT_RC[r][i]);
+      external_layer<FA>(s, z);
+    }
   }
 }
 
@@ -141,7 +235,10 @@ __global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
     for (int i = 0; i < 16; i++) s[k][i] = (tid * 2654435761u + i * 40503u + k * 977u) % P;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int k = 0; k < ILP; k++) permute<M, DIAG, FA>(s[k], z);
+    for (int k = 0; k < ILP; k++) {
+      if (FA >= 10) permute_rolled<M, DIAG, (FA % 100 - 10) / 10, FA % 10 ? FA % 10 : 1, FA / 100>(s[k], z);   // FA = 100*forceALU + 10*(ROLL+1) + EU
+      else permute<M, DIAG, FA>(s[k], z);
+    }
   }
   uint32_t acc = 0;
 #pragma unroll
@@ -183,25 +280,51 @@ void run(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
          perms / best / 1e6, best * 1e-3 * 1.9e9 * sms / perms, ok, cudaGetErrorString(cudaGetLastError()));
 }
 
-int main() {
+int main(int argc, char** argv) {
+  int only = argc > 1 ? atoi(argv[1]) : -1;  // run a single variant (for ncu captures)
+  int idx = 0;
+#define RUN(...) if (idx++, only < 0 || only == idx - 1) run<__VA_ARGS__>
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int sms = p.multiProcessorCount;
   printf("%s, %d SMs\n", p.name, sms);
   uint32_t* d; cudaMalloc(&d, (size_t)sms * 16 * 256 * 2 * 4);
   uint32_t ref[1] = {0xffffffffu};
-  run<MulSub, 0, 1, 1>("sub/diagmul", d, ref, sms);
-  run<MulSub, 1, 1, 1>("sub/diagshift", d, ref, sms);
-  run<MulSub, 1, 1, 1, 1>("sub/diagshift forceALU1", d, ref, sms);
-  run<MulSub, 1, 1, 1, 2>("sub/diagshift forceALU2", d, ref, sms);
-  run<MulSub, 1, 1, 1, 3>("sub/diagshift forceALU3", d, ref, sms);
-  run<MulAdd, 0, 1, 1>("add/diagmul", d, ref, sms);
-  run<MulAdd, 1, 1, 1>("add/diagshift", d, ref, sms);
-  run<MulLea, 1, 1, 1>("lea/diagshift", d, ref, sms);
-  run<MulSub, 1, 1, 6>("sub/diagshift minb6", d, ref, sms);
-  run<MulAdd, 1, 1, 6>("add/diagshift minb6", d, ref, sms);
-  run<MulAdd, 1, 1, 8>("add/diagshift minb8", d, ref, sms);
-  run<MulSub, 1, 2, 1>("sub/diagshift ilp2", d, ref, sms);
-  run<MulAdd, 1, 2, 1>("add/diagshift ilp2", d, ref, sms);
-  run<MulAdd, 1, 2, 3>("add/diagshift ilp2 minb3", d, ref, sms);
+  RUN(MulSub, 0, 1, 1)("sub/diagmul", d, ref, sms);
+  RUN(MulSub, 1, 1, 1)("sub/diagshift", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1)("signed-sbox/diagshift", d, ref, sms);
+  RUN(MulSigned, 1, 1, 6)("signed-sbox/diagshift minb6", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 20)("sub roll-int", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 31)("sub roll-int roll-ext", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 32)("sub roll-int ext-unroll2", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 41)("sub roll-all one-ext-body", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 20)("signed roll-int", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 31)("signed roll-int roll-ext", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 32)("signed roll-int ext-unroll2", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 41)("signed roll-all one-ext-body", d, ref, sms);
+  RUN(MulSigned, 1, 1, 6, 31)("signed roll-int roll-ext minb6", d, ref, sms);
+  RUN(MulSigned, 1, 1, 6, 41)("signed roll-all one-ext minb6", d, ref, sms);
+  RUN(MulSigned, 1, 1, 8, 31)("signed roll-int roll-ext minb8", d, ref, sms);
+  RUN(MulSigned, 1, 2, 1, 31)("signed roll-int roll-ext ilp2", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 131)("signed roll2 forceALU1", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 231)("signed roll2 forceALU2", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 141)("signed roll3 forceALU1", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 241)("signed roll3 forceALU2", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 441)("signed roll3 m4-alu1 (72)", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 541)("signed roll3 m4-alu2 (108)", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 641)("signed roll3 m4-alu3 (180)", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 131)("sub roll2 forceALU1", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 231)("sub roll2 forceALU2", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 1)("sub/diagshift forceALU1", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 2)("sub/diagshift forceALU2", d, ref, sms);
+  RUN(MulSub, 1, 1, 1, 3)("sub/diagshift forceALU3", d, ref, sms);
+  RUN(MulAdd, 0, 1, 1)("add/diagmul", d, ref, sms);
+  RUN(MulAdd, 1, 1, 1)("add/diagshift", d, ref, sms);
+  RUN(MulLea, 1, 1, 1)("lea/diagshift", d, ref, sms);
+  RUN(MulSub, 1, 1, 6)("sub/diagshift minb6", d, ref, sms);
+  RUN(MulAdd, 1, 1, 6)("add/diagshift minb6", d, ref, sms);
+  RUN(MulAdd, 1, 1, 8)("add/diagshift minb8", d, ref, sms);
+  RUN(MulSub, 1, 2, 1)("sub/diagshift ilp2", d, ref, sms);
+  RUN(MulAdd, 1, 2, 1)("add/diagshift ilp2", d, ref, sms);
+  RUN(MulAdd, 1, 2, 3)("add/diagshift ilp2 minb3", d, ref, sms);
   return 0;
 }

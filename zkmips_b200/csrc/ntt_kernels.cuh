@@ -89,7 +89,7 @@ constexpr size_t pass_smem_bytes() {
 }
 
 template <int B, int DIR, bool FIRST, bool PASSTW, int CPT>
-__global__ void __launch_bounds__((16 / CPT) << B, (CPT == 2 ? 512 : 1024) / ((16 / CPT) << B)) ntt_pass_smem(PassArgs A,
+__global__ void __launch_bounds__((16 / CPT) << B, (CPT == 2 ? 768 : 1024) / ((16 / CPT) << B)) ntt_pass_smem(PassArgs A,
                                                                                                            PassExtra X) {
   constexpr int K = 5 + B, ROWS = 1 << K, C = TILE_COLS;
   constexpr uint32_t NTAU = 1u << B, NT = NTAU * (16 / CPT), CSH = CPT == 2 ? 3 : 4;

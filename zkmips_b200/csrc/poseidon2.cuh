@@ -8,17 +8,38 @@
 // TruncatedPermutation<2,8,16> (crates/stark/src/kb31_poseidon2.rs:173-177; semantics
 // crates/recursion/circuit/src/hash.rs:40-49,76-81).
 //
-// The state lives in 16 registers; every loop is fully unrolled so round constants become immediates
-// of the IADD3 that adds them (no constant-bank or shared-memory traffic).  The kernel is bound by the
-// integer pipes (fma: IMAD*, alu: IADD3/VIADDMNMX), not by memory -- see DESIGN.md.
+// The state lives in 16 registers.  The ROUND loops are rolled (one copy of the external-round body, one of the
+// internal-round body, ~760 instructions = 12 KB): the fully unrolled permutation is ~4500 instructions = 72 KB
+// of straight-line code that every warp streams once per permutation, and that version was bound by instruction
+// fetch, not by the integer pipes (ncu on B200: instruction-cache hit rate 57 %, 44 % of stall cycles
+// "no instruction", 55.6 clk/perm/SM; rolled: hit rate 99.99 %, fmaheavy pipe 85 % busy, 47.8 clk/perm/SM --
+// profiles/r1_p2bench_variants.txt).  Round constants come from the constant bank (uniform LDC per round).
+// Within a round everything is unrolled over the 16 lanes.  Bound by the integer pipes (fma: IMAD*, alu:
+// IADD3/VIADDMNMX; IMAD.WIDE and IMAD.HI occupy the fma pipe for 4 cycles, the rest for 2:
+// profiles/r1_pipebench.txt), not by memory -- see DESIGN.md.
 #pragma once
 #include "kb31.cuh"
 #include "../../include/zk_poseidon2_rc.h"
 
 namespace p2 {
 
-__device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
-__device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
+static __constant__ uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
+static __constant__ uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
+
+// S-box with the round constant folded in: (x + rc)^3.  t = x + rc - p lies in [-p, p) and is squared as a signed
+// number, so the modular add needs no correction; x2 = t*t/R stays uncorrected in (-p, p/2); the second product
+// uses the signed Montgomery reduction (signed m, signed mulhi), whose result lies in (-p, p): one correction
+// for the whole S-box -- 10 instructions instead of 11 (IADD3, 2x {IMAD.WIDE, IMAD, IMAD.HI, IADD3}, VIADDMNMX).
+__device__ __forceinline__ uint32_t sbox(uint32_t x, uint32_t rc) {
+  int32_t t = (int32_t)(x + (rc - kb::P));
+  int64_t T = (int64_t)t * t;  // < p^2
+  uint32_t m = (uint32_t)T * kb::MU;
+  int32_t x2 = (int32_t)((uint64_t)T >> 32) - (int32_t)__umulhi(m, kb::P);
+  int64_t T2 = (int64_t)x2 * t;  // |T2| < p^2
+  int32_t m2 = (int32_t)((uint32_t)T2 * kb::MU);
+  int32_t r = (int32_t)(T2 >> 32) - __mulhi(m2, (int32_t)kb::P);  // low words cancel exactly; r in (-p, p)
+  return min((uint32_t)r, (uint32_t)r + kb::P);
+}
 
 // x * 2^-k mod p without a multiplication by a Montgomery constant: p = 127 * 2^24 + 1, so
 // 2^-k = -(p-1)/2^k (k <= 24) and  x / 2^k = (x >> k) - (x mod 2^k) * ((p-1) >> k)  (mod p).
@@ -81,22 +102,21 @@ __device__ __forceinline__ void internal_layer(uint32_t (&s)[16]) {
 
 __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
   external_layer(s);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = kb::cube(kb::add(s[i], EXT_RC[r][i]));
-    external_layer(s);
-  }
-#pragma unroll
-  for (int r = 0; r < 13; r++) {
-    s[0] = kb::cube(kb::add(s[0], INT_RC[r]));
-    internal_layer(s);
-  }
-#pragma unroll
-  for (int r = 4; r < 8; r++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = kb::cube(kb::add(s[i], EXT_RC[r][i]));
-    external_layer(s);
+      for (int i = 0; i < 16; i++) s[i] = sbox(s[i], EXT_RC[half * 4 + r][i]);
+      external_layer(s);
+    }
+    if (half == 0) {
+#pragma unroll 1
+      for (int r = 0; r < 13; r++) {
+        s[0] = sbox(s[0], INT_RC[r]);
+        internal_layer(s);
+      }
+    }
   }
 }
 

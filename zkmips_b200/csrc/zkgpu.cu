@@ -403,7 +403,22 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     slab = (uint32_t)std::min(by_bytes, quarter);
   }
   if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
-  const uint32_t nslab = (w + slab - 1) / slab;
+  // Slab schedule.  The copy stream is the critical path (compute per slab is shorter than its upload), so what
+  // is left after the LAST upload -- the transforms and the sponge of the last slab -- is pure tail.  The last
+  // full slab is therefore cut in halves, down to 32 columns (128 B rows still copy at full PCIe rate, 64 B rows
+  // do not): 256 columns go up as 64, 64, 64, 32, 32 and the tail is a 32-column slab instead of a 64-column one.
+  std::vector<uint32_t> cuts;  // first column of every slab, then w
+  {
+    uint32_t c0 = 0;
+    while (c0 < w) {
+      cuts.push_back(c0);
+      uint32_t nc = std::min(slab, w - c0);
+      if (c->slab_cols == 0 && slab < w && w - c0 <= slab && nc >= 64 && nc % 32 == 0) nc /= 2;
+      c0 += nc;
+    }
+    cuts.push_back(w);
+  }
+  const uint32_t nslab = (uint32_t)cuts.size() - 1;
   std::vector<ntt::CosetScale> scales;
   const bool aligned = (w & 1u) == 0 && (slab & 1u) == 0 && ((uintptr_t)out % 8) == 0;
   if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
@@ -413,7 +428,7 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   uint4* state = nullptr;
   if (leaves && nslab > 1 && (rc = dev_alloc(c, H * 64, (void**)&state))) return rc;
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
-    const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = k * slab, nc = std::min(slab, w - c0);
+    const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = cuts[k], nc = cuts[k + 1] - c0;
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
     CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
