@@ -431,13 +431,20 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = cuts[k], nc = cuts[k + 1] - c0;
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
-    CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
-                         c->copy_stream));
+    if (nc == w)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
+      CK(cudaMemcpyAsync(buf, host, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    else
+      CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+                           c->copy_stream));
     CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
-    if (keep_trace)  // retain the slab before the in-place inverse transform overwrites it
-      CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h, cudaMemcpyDeviceToDevice,
-                           c->stream));
+    if (keep_trace) {  // retain the slab before the in-place inverse transform overwrites it
+      if (nc == w)  // one slab: a plain copy (a 2-D copy of 2^20 rows of 8 bytes is issued row by row: 100 ms)
+        CK(cudaMemcpyAsync(keep_trace, buf, (size_t)h * w * 4, cudaMemcpyDeviceToDevice, c->stream));
+      else
+        CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h,
+                             cudaMemcpyDeviceToDevice, c->stream));
+    }
     ntt::Cols sl{buf, nc, 0};
     rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
     if (rc) break;
@@ -500,56 +507,90 @@ int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd) {
   return dev_alloc(c, words * 4, (void**)&pd->digests);
 }
 
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, bool with_open_desc) {
+// Advances the digest layers as far as the available matrices allow.  `pending` maps a committed height to the
+// number of its matrices whose LDE has not been enqueued yet (nullptr: everything is available).  The streaming
+// commit calls this after every matrix, so the row digests of complete height classes and every tree layer that
+// does not wait for a later (shorter) class run while the remaining traces are still being uploaded; what is
+// left after the last upload is the last slab, the injection of its class and the layers above it.
+int32_t mmcs_advance(zk_ctx* c, zk_pdata* pd, TreeProgress& tp, const std::map<uint64_t, int>* pending) {
+  const uint32_t n = pd->n;
+  int32_t rc;
+  const uint64_t hmax = pd->heights[pd->order[0]], hmin = pd->heights[pd->order[n - 1]];
+  auto avail = [&](uint64_t h) {
+    if (!pending) return true;
+    auto it = pending->find(h);
+    return it == pending->end() || it->second == 0;
+  };
+  std::vector<mk::MatDesc> g;
+  auto group = [&](uint64_t height) {
+    g.clear();
+    for (uint32_t k = 0; k < n; k++) {
+      uint32_t m = pd->order[k];
+      if (pd->heights[m] == height) g.push_back(mk::MatDesc{pd->mats[m], pd->widths[m]});
+    }
+  };
+  if (!tp.leaves) {
+    if (!avail(hmax)) return ZK_OK;
+    if (!tp.leaves_streamed) {
+      ProfScope ps(c, "leaf_hash");
+      group(hmax);
+      if ((rc = hash_group(c, g, hmax, pd->digests))) return rc;
+    }
+    tp.leaves = true;
+  }
+  if (tp.next_l > pd->log_max) return ZK_OK;
+  {
+    group(hmax >> tp.next_l);
+    if (!g.empty() && !avail(hmax >> tp.next_l)) return ZK_OK;  // nothing can be done yet: no empty profile record
+  }
+  ProfScope ps(c, "tree");
+  while (tp.next_l <= pd->log_max) {
+    const uint32_t l = tp.next_l;
+    const uint64_t len = hmax >> l;
+    if (hmin > len && 2 * len <= 1024) {
+      // no matrix left to inject: one CTA finishes the tree from the layer of 2*len digests
+      ZK_LAUNCH_COOP(mk::compress_top, 1, 512, 0, c->stream, pd->digests, pd->layer_off[l - 1], (uint32_t)(2 * len));
+      CK(cudaGetLastError());
+      c->launches++;
+      tp.next_l = pd->log_max + 1;
+      break;
+    }
+    group(len);
+    const uint32_t* injp = nullptr;
+    if (!g.empty()) {
+      if (!avail(len)) break;
+      auto it = pd->class_digests.find(len);
+      if (it != pd->class_digests.end()) {
+        injp = it->second;  // already hashed while the LDE streamed in
+      } else {
+        if (!tp.inj && (rc = dev_alloc(c, (hmax >> 1) * 32, (void**)&tp.inj))) return rc;
+        if ((rc = hash_group(c, g, len, tp.inj))) return rc;
+        injp = tp.inj;
+      }
+    }
+    ZK_LAUNCH(mk::compress_layer, (unsigned)((len + 255) / 256), 256, 0, c->stream, pd->digests + pd->layer_off[l - 1],
+              pd->digests + pd->layer_off[l], len, injp);
+    CK(cudaGetLastError());
+    c->launches++;
+    tp.next_l++;
+  }
+  return ZK_OK;
+}
+
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, bool with_open_desc, TreeProgress* resume) {
   uint32_t n = pd->n;
   int32_t rc;
   if (!pd->digests && (rc = mmcs_alloc(c, pd))) return rc;
-  uint64_t hmax = pd->heights[pd->order[0]];
-  uint32_t* inj = nullptr;
-  uint32_t next = 0;
-  auto take_group = [&](uint64_t height, std::vector<mk::MatDesc>& g) {
-    g.clear();
-    while (next < n && pd->heights[pd->order[next]] == height) {
-      uint32_t m = pd->order[next++];
-      g.push_back(mk::MatDesc{pd->mats[m], pd->widths[m]});
-    }
-  };
-  std::vector<mk::MatDesc> g;
-  {
-    ProfScope ps(c, "leaf_hash");
-    take_group(hmax, g);
-    if (!leaves_done && (rc = hash_group(c, g, hmax, pd->digests))) return rc;
+  TreeProgress local;
+  TreeProgress& tp = resume ? *resume : local;
+  if (!resume) tp.leaves_streamed = leaves_done;
+  rc = mmcs_advance(c, pd, tp, nullptr);
+  if (tp.inj) {
+    int32_t rc2 = dev_free(c, tp.inj);
+    tp.inj = nullptr;
+    if (rc == ZK_OK) rc = rc2;
   }
-  {
-    ProfScope ps(c, "tree");
-    for (uint32_t l = 1; l <= pd->log_max; l++) {
-      uint64_t len = hmax >> l;
-      if (next == n && 2 * len <= 1024) {
-        // no matrix left to inject: one CTA finishes the tree from the layer of 2*len digests
-        ZK_LAUNCH_COOP(mk::compress_top, 1, 512, 0, c->stream, pd->digests, pd->layer_off[l - 1], (uint32_t)(2 * len));
-        CK(cudaGetLastError());
-        c->launches++;
-        break;
-      }
-      take_group(len, g);
-      const uint32_t* injp = nullptr;
-      if (!g.empty()) {
-        auto it = pd->class_digests.find(len);
-        if (it != pd->class_digests.end()) {
-          injp = it->second;  // already hashed while the LDE streamed in
-        } else {
-          if (!inj && (rc = dev_alloc(c, (hmax >> 1) * 32, (void**)&inj))) return rc;
-          if ((rc = hash_group(c, g, len, inj))) return rc;
-          injp = inj;
-        }
-      }
-      ZK_LAUNCH(mk::compress_layer, (unsigned)((len + 255) / 256), 256, 0, c->stream, 
-          pd->digests + pd->layer_off[l - 1], pd->digests + pd->layer_off[l], len, injp);
-      CK(cudaGetLastError());
-      c->launches++;
-    }
-  }
-  if (inj && (rc = dev_free(c, inj))) return rc;
+  if (rc) return rc;
   for (auto& kv : pd->class_digests) dev_free(c, kv.second);
   pd->class_digests.clear();
   if (with_open_desc) {
@@ -627,6 +668,7 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
   pd->trace_owned.assign(n_mats, false);
   int32_t rc = ZK_OK;
   bool leaves_done = false;
+  TreeProgress tp;
   if (do_lde) {
     uint64_t hmax = 0;
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
@@ -652,6 +694,8 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
         if (rc == ZK_OK) pd->class_digests[pd->heights[i]] = stream_digests[i];
       }
     }
+    std::map<uint64_t, int> pending = members;
+    tp.leaves_streamed = leaves_done;
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
       uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
       uint32_t* keep = nullptr;
@@ -669,6 +713,10 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
         rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], stream_digests[i], keep);
       else
         rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
+      pending[pd->heights[i]]--;
+      // host traces: hash complete height classes and build every tree layer that is already determined while
+      // the copy stream is still uploading the remaining matrices
+      if (rc == ZK_OK && src_is_host && i + 1 < n_mats) rc = mmcs_advance(c, pd, tp, &pending);
     }
   } else {
     for (uint32_t i = 0; i < n_mats; i++) {
@@ -676,7 +724,8 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       pd->mats[i] = const_cast<uint32_t*>(src[i]);
     }
   }
-  if (rc == ZK_OK) rc = mmcs_build(c, pd, true, leaves_done);
+  if (rc == ZK_OK) rc = mmcs_build(c, pd, true, leaves_done, true, &tp);
+  if (tp.inj) dev_free(c, tp.inj);
   if (rc != ZK_OK) {
     pdata_release(pd);
     return rc;

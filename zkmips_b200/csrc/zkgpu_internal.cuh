@@ -97,7 +97,16 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
 int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd);
 // with_open_desc == false skips the open_batch descriptor upload (FRI layers are opened by their own kernel),
 // which keeps the build free of host->device copies and therefore fully asynchronous.
-int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true, bool leaves_done = false, bool with_open_desc = true);
+// progress of an incrementally built tree (streaming commit): next layer to compute, leaf state, injection scratch
+struct TreeProgress {
+  uint32_t next_l = 1;
+  bool leaves = false;           // leaf layer complete
+  bool leaves_streamed = false;  // the leaf digests are written by the streaming sponge, not by mmcs_advance
+  uint32_t* inj = nullptr;
+};
+int32_t mmcs_advance(zk_ctx* c, zk_pdata* pd, TreeProgress& tp, const std::map<uint64_t, int>* pending);
+int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root = true, bool leaves_done = false, bool with_open_desc = true,
+                   TreeProgress* resume = nullptr);
 // Mmcs::commit of one device-resident matrix; with fetch_root == false nothing is copied to the host and the
 // stream is not synchronised (the root stays at pdata_root_dev()).
 int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bool take_ownership, bool fetch_root,
