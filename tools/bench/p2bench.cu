@@ -79,11 +79,12 @@ template <> struct Sbox<MulSigned> {
 
 template <int FM = 0>
 __device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t z) {
-  uint32_t t01 = FM >= 1 ? add3z(x0, x1, z) : kb::add(x0, x1), t23 = FM >= 1 ? add3z(x2, x3, z) : kb::add(x2, x3);
-  uint32_t t0123 = FM >= 2 ? add3z(t01, t23, z) : kb::add(t01, t23);
-  uint32_t t01123 = kb::add(t0123, x1), t01233 = kb::add(t0123, x3);
-  uint32_t n3 = kb::add(t01233, kb::dbl(x0)), n1 = kb::add(t01123, kb::dbl(x2));
-  uint32_t n0 = FM >= 3 ? add3z(t01123, t01, z) : kb::add(t01123, t01), n2 = FM >= 3 ? add3z(t01233, t23, z) : kb::add(t01233, t23);
+  auto A = [&](uint32_t a, uint32_t b, int lvl) { return FM >= lvl ? add3z(a, b, z) : kb::add(a, b); };
+  uint32_t t01 = A(x0, x1, 1), t23 = A(x2, x3, 1);
+  uint32_t t0123 = A(t01, t23, 2);
+  uint32_t t01123 = A(t0123, x1, 4), t01233 = A(t0123, x3, 4);
+  uint32_t n3 = A(t01233, kb::dbl(x0), 4), n1 = A(t01123, kb::dbl(x2), 4);
+  uint32_t n0 = A(t01123, t01, 3), n2 = A(t01233, t23, 3);
   x0 = n0; x1 = n1; x2 = n2; x3 = n3;
 }
 template <int FA>
@@ -93,13 +94,13 @@ __device__ __forceinline__ void external_layer(uint32_t (&s)[16], uint32_t z) {
   uint32_t sums[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    if (FA >= 2)
+    if (FA == 2 || FA >= 7)
       sums[k] = add3z(add3z(s[k], s[4 + k], z), add3z(s[8 + k], s[12 + k], z), z);
     else
       sums[k] = kb::add(kb::add(s[k], s[4 + k]), kb::add(s[8 + k], s[12 + k]));
   }
 #pragma unroll
-  for (int j = 0; j < 16; j++) s[j] = FA >= 1 ? add3z(s[j], sums[j & 3], z) : kb::add(s[j], sums[j & 3]);
+  for (int j = 0; j < 16; j++) s[j] = (FA >= 1 && FA <= 3) || FA >= 7 ? add3z(s[j], sums[j & 3], z) : kb::add(s[j], sums[j & 3]);
 }
 // x * 2^-k mod p = (x >> k) - (x & (2^k-1)) * ((p-1) >> k)   since 2^-k = -(p-1)/2^k  (p = 127*2^24 + 1)
 template <int K> __device__ __forceinline__ uint32_t div2k(uint32_t x) {
@@ -108,10 +109,11 @@ template <int K> __device__ __forceinline__ uint32_t div2k(uint32_t x) {
   uint32_t d = q - r * c;
   return min(d, d + P);
 }
-template <class M, int DIAG> __device__ __forceinline__ void internal_layer(uint32_t (&s)[16]) {
-  uint32_t a0 = kb::add(s[0], s[1]), a1 = kb::add(s[2], s[3]), a2 = kb::add(s[4], s[5]), a3 = kb::add(s[6], s[7]);
-  uint32_t a4 = kb::add(s[8], s[9]), a5 = kb::add(s[10], s[11]), a6 = kb::add(s[12], s[13]), a7 = kb::add(s[14], s[15]);
-  uint32_t sum = kb::add(kb::add(kb::add(a0, a1), kb::add(a2, a3)), kb::add(kb::add(a4, a5), kb::add(a6, a7)));
+template <class M, int DIAG, int FI = 0> __device__ __forceinline__ void internal_layer(uint32_t (&s)[16], uint32_t z = 0) {
+  auto A = [&](uint32_t a, uint32_t b) { return FI >= 1 ? add3z(a, b, z) : kb::add(a, b); };
+  uint32_t a0 = A(s[0], s[1]), a1 = A(s[2], s[3]), a2 = A(s[4], s[5]), a3 = A(s[6], s[7]);
+  uint32_t a4 = A(s[8], s[9]), a5 = A(s[10], s[11]), a6 = A(s[12], s[13]), a7 = A(s[14], s[15]);
+  uint32_t sum = A(A(A(a0, a1), A(a2, a3)), A(A(a4, a5), A(a6, a7)));
   uint32_t d;
   s[0] = kb::sub(sum, kb::dbl(s[0]));
   s[1] = kb::add(sum, s[1]);
@@ -181,7 +183,7 @@ __device__ __forceinline__ void permute_rolled(uint32_t (&s)[16], uint32_t z = 0
 #pragma unroll 1
         for (int r = 0; r < 13; r++) {
           s[0] = Sbox<M>::f(s[0], C_INT_RC[r]);
-          internal_layer<M, DIAG>(s);
+          internal_layer<M, DIAG, (FA >= 8 ? 1 : 0)>(s, z);
         }
       }
     }
@@ -205,7 +207,7 @@ __device__ __forceinline__ void permute_rolled(uint32_t (&s)[16], uint32_t z = 0
 #pragma unroll 1
   for (int r = 0; r < 13; r++) {
     s[0] = Sbox<M>::f(s[0], C_INT_RC[r]);
-    internal_layer<M, DIAG>(s);
+    internal_layer<M, DIAG, (FA >= 8 ? 1 : 0)>(s, z);
   }
   if (ROLL >= 2) {
 #pragma unroll EU
@@ -312,6 +314,8 @@ int main(int argc, char** argv) {
   RUN(MulSigned, 1, 1, 1, 441)("signed roll3 m4-alu1 (72)", d, ref, sms);
   RUN(MulSigned, 1, 1, 1, 541)("signed roll3 m4-alu2 (108)", d, ref, sms);
   RUN(MulSigned, 1, 1, 1, 641)("signed roll3 m4-alu3 (180)", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 741)("signed roll3 ext-all-alu (648)", d, ref, sms);
+  RUN(MulSigned, 1, 1, 1, 841)("signed roll3 ext-all+intsum (843)", d, ref, sms);
   RUN(MulSub, 1, 1, 1, 131)("sub roll2 forceALU1", d, ref, sms);
   RUN(MulSub, 1, 1, 1, 231)("sub roll2 forceALU2", d, ref, sms);
   RUN(MulSub, 1, 1, 1, 1)("sub/diagshift forceALU1", d, ref, sms);

@@ -79,6 +79,8 @@ __host__ __device__ constexpr int brev5(int q) {
 //   round B: 2^(5-B) size-2^B DFTs on the thread's 32 consecutive rows;
 //   second factor of the pass twiddle G[bitrev_5(i&31)] = g^(base*2^B*...), store.
 // CPT = columns per thread: 2 -> 64-bit accesses, 128 registers; 1 -> any alignment, 64 registers.
+// (Three resident CTAs per SM instead of two -- __launch_bounds__(256, 3): 80 registers, 48 B of spill -- were
+// measured slower on B200: inverse transform 1.44 -> 1.66 ms, coset transforms 3.17 -> 3.27 ms per 2^20 x 256 LDE.)
 // No per-element global twiddle or scale loads.  (First version of this kernel: 85-104 instructions per
 // element; this one 49-62: profiles/README.md.)
 constexpr int FSTRIDE = 33;
@@ -89,7 +91,7 @@ constexpr size_t pass_smem_bytes() {
 }
 
 template <int B, int DIR, bool FIRST, bool PASSTW, int CPT>
-__global__ void __launch_bounds__((16 / CPT) << B, (CPT == 2 ? 768 : 1024) / ((16 / CPT) << B)) ntt_pass_smem(PassArgs A,
+__global__ void __launch_bounds__((16 / CPT) << B, (CPT == 2 ? 512 : 1024) / ((16 / CPT) << B)) ntt_pass_smem(PassArgs A,
                                                                                                            PassExtra X) {
   constexpr int K = 5 + B, ROWS = 1 << K, C = TILE_COLS;
   constexpr uint32_t NTAU = 1u << B, NT = NTAU * (16 / CPT), CSH = CPT == 2 ? 3 : 4;
