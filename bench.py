@@ -45,6 +45,19 @@ def leaf_hash_bytes(log_rows, cols, log_blowup):
     return 4 * H * cols + 32 * H
 
 
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """the bench line: to the process's ORIGINAL stdout (see main), everything else went to stderr"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def kernel_traffic(name):
     """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (or None)"""
     try:
@@ -184,14 +197,14 @@ def run_reference(args):
     dt = (time.perf_counter() - t) / args.steps
     v = (1 << log) * COLS / dt / 1e9
     sample = f"each step = one commit of 2^{log} x {COLS} (1/{1 << (LOG_ROWS - log)} of the workload rows)"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (KoalaBear Montgomery)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def shard_leg(ctx, torch, dist, world, rank, args):
@@ -305,6 +318,12 @@ def main():
                     help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 (86 M cells); keccak: BASELINE config 3, one "
                          "2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells)")
     args = ap.parse_args()
+    # Exactly ONE line on stdout: native libraries print there too (NCCL's version banner goes through printf), so
+    # file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -322,7 +341,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libzkgpu has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     log_rows, cols = args.log_rows, args.cols
@@ -333,7 +351,7 @@ def main():
     if args.shard_only:
         res = shard_leg(ctx, torch, dist, world, rank, args)
         if rank == 0:
-            print(json.dumps({"shard_prove": res}))
+            emit_json({"shard_prove": res})
         ctx.destroy()
         return
 
@@ -486,7 +504,7 @@ def main():
         v, cores, sample, _, _ = cpu_commit_sample()
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(out))
+        emit_json(out)
     ctx.destroy()
     if world > 1:
         dist.destroy_process_group()
