@@ -340,6 +340,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libzkgpu has no CPU fallback")
     torch.cuda.set_device(local)
+    from zkmips_b200.dispatch import bind_to_gpu_numa
+    all_cpus = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa(local)  # before the pinned trace buffers are allocated (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -478,6 +481,7 @@ def main():
         "dtype": "u32 (KoalaBear Montgomery)", "data": "synthetic",
         "config": {"workload": WORKLOAD if (log_rows, cols) == (LOG_ROWS, COLS) else f"2^{log_rows} x {cols}, blowup 2",
                    "shards_per_gpu_per_step": 1, "parallelism": f"one shard per GPU x{world}, no data-path collective",
+                   "host_affinity": f"rank 0 bound to {len(cpus)} CPUs next to its GPU (NVML)" if cpus else "unbound",
                    "l2": "inputs (1 GiB trace, 2 GiB LDE) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_host, "h2d_bytes_per_step": 4 * n_elems,
                 "d2h_bytes_per_step": 32, "commits_in_flight": 1},
@@ -501,6 +505,7 @@ def main():
     if not args.no_shard:
         out["shard_prove"] = shard_leg(ctx, torch, dist, world, rank, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
         v, cores, sample, _, _ = cpu_commit_sample()
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:

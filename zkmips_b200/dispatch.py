@@ -10,6 +10,28 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs next to GPU `device_index` (NVML's ideal affinity) BEFORE it allocates
+    its pinned trace buffers: first-touch then puts them on the GPU's own NUMA node, so that with one process per
+    GPU the uploads do not all read one socket's memory.  (The 8-GPU pool box is a 32-vCPU guest with a single NUMA
+    node, so the binding changes nothing there: its aggregate upload rate tops out at ~176 GB/s = 44 Gelem/s for
+    4 and for 8 GPUs, profiles/r1_bench_8gpu.json.)  Returns the CPU list it bound to, or None when NVML / the
+    affinity call is unavailable."""
+    try:
+        import os
+
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            device_index = int(vis.split(",")[device_index])  # NVML enumerates the physical devices
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def shards_for_rank(n_shards, world, rank):
     """round-robin placement: shard i -> rank i mod world"""
     return list(range(rank, n_shards, world))
