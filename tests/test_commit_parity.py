@@ -213,6 +213,33 @@ def test_streaming_commit_tapered_slabs(be, monkeypatch):
         ctx.destroy()
 
 
+@pytest.mark.parametrize("be", BACKENDS)
+def test_streaming_commit_multi_member_classes(be, monkeypatch):
+    """Height classes of SEVERAL matrices are streamed too: the class sponge is resumed matrix after matrix at any
+    alignment (a 2-column matrix in front shifts every later chunk boundary by 2), slabs of 16 columns, zero-width
+    members first / in the middle / last, classes interleaved in input order."""
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_SLAB_COLS", "16")
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+    try:
+        # keccak-like: narrow + wide chip of the same height (BASELINE config 3 shape)
+        _check_commit(ctx, [_mont(64, 2, seed=51), _mont(64, 72, seed=52)], [one] * 2, 1)
+        # three members, widths 5 + 40 + 3 (partial block carried across two matrix boundaries), shorter classes between
+        _check_commit(ctx, [_mont(64, 5, seed=53), _mont(16, 3, seed=54), _mont(64, 40, seed=55), _mont(16, 13, seed=56),
+                            _mont(64, 3, seed=57), _mont(4, 8, seed=58)], [one] * 6, 1)
+        # zero-width members: first, middle and LAST of their class (the last one must still finalise the digests)
+        _check_commit(ctx, [_mont(32, 0, seed=59), _mont(32, 9, seed=60), _mont(32, 0, seed=61), _mont(8, 24, seed=62),
+                            _mont(8, 0, seed=63)], [one] * 5, 2)
+        # exactly block-aligned members use the vector kernel, the misaligned ones after them the general one
+        _check_commit(ctx, [_mont(64, 16, seed=64), _mont(64, 8, seed=65), _mont(64, 6, seed=66), _mont(64, 32, seed=67)],
+                      [one] * 4, 1)
+    finally:
+        ctx.destroy()
+
+
 def test_lde_two_pass_k10_emu():
     """2^20 rows x 2 columns: both k=10 passes of the second-generation kernel (coset scale + bit-reversed
     gather fused in the first, pass twiddles) on the emulator; the GPU twins are the 2^20 cases above."""

@@ -227,3 +227,30 @@ def test_quotient_degree_four_chunks(be):
     ok, why = su.verify_shard(sp, ordered, start, 2, nq, pw)
     assert ok, why
     pd.free()
+
+
+@pytest.mark.parametrize("name,log_blowup,num_queries", [("default", 1, 84), ("compressed", 2, 42), ("ultra_compressed", 3, 28)])
+@pytest.mark.parametrize("be", BACKENDS)
+def test_reference_fri_configs(be, name, log_blowup, num_queries):
+    """The three FRI configurations of the reference (crates/stark/src/kb31_poseidon2.rs:203-241: default_fri_config
+    for core shards, compressed_fri_config for compress, ultra_compressed_fri_config for shrink/wrap; 16 proof-of-work
+    bits each): a shard with chips of different heights, lookups and a preprocessed trace proves and verifies under
+    every one of them, and the main commitment equals the oracle's for that blowup."""
+    ctx = _backend(be)
+    nq, pw = (min(num_queries, 6), 5) if be == "emu" else (num_queries, 16)
+    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), su.lookup_chip(5)]
+    prover = GpuShardProver(ctx, log_blowup, nq, pw)
+    prep_root, prep_pd = prover.setup(chips)
+    ch = Challenger(ctx)
+    ch.observe(prep_root)
+    start = ch.w.copy()
+    ordered, root, pd = prover.commit(chips)
+    assert (root == ob.pcs_commit([c.main for c in ordered], log_blowup).root).all()
+    sp = prover.open(ordered, root, pd, ch, prep_root, prep_pd)
+    ok, why = su.verify_shard(sp, ordered, start, log_blowup, nq, pw)
+    assert ok, f"{name}: {why}"
+    # a proof made for one configuration must not verify under another blowup
+    other = 1 if log_blowup != 1 else 2
+    assert not su.verify_shard(sp, ordered, start, other, nq, pw)[0]
+    pd.free()
+    prep_pd.free()

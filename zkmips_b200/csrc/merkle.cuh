@@ -89,6 +89,51 @@ __global__ void __launch_bounds__(256) hash_rows_slab(const uint32_t* __restrict
   }
 }
 
+// Resumable sponge at ANY alignment: absorbs columns [c0, c0 + nc) of every row of one matrix into the sponge of
+// the row's height class, which may already hold k0 = (words absorbed so far) mod 8 pending words in its rate
+// (a class of several matrices is the concatenation of their rows in input order, so a matrix of width 2 in front
+// shifts every later chunk boundary by 2).  State layout as hash_rows_slab.  `last` finalises: a pending partial
+// block is permuted once (PaddingFreeSponge) and the digest written.  nc == 0 is allowed (zero-width member).
+__global__ void __launch_bounds__(256) hash_rows_slab_any(const uint32_t* __restrict__ mat, uint32_t pitch, uint32_t c0,
+                                                          uint32_t nc, uint64_t h, uint4* __restrict__ state, uint32_t k0,
+                                                          int first, int last, uint32_t* __restrict__ out) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  const uint32_t* row = mat + r * pitch + c0;
+  uint32_t s[16];
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = 0;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint4 v = state[k * h + r];
+      s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
+    }
+  }
+  uint32_t c = 0, k = k0;  // k0 is uniform over the grid: the branches below do not diverge
+  do {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i >= (int)k && c < nc) {
+        s[i] = __ldg(row + c);
+        c++;
+        k = i + 1;
+      }
+    }
+    if (k == 8 || (last && c == nc && k > 0)) {
+      p2::permute(s);
+      k = 0;
+    }
+  } while (c < nc);
+  if (last) {
+    store_digest(out + r * 8, s);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; q++) state[q * h + r] = make_uint4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+  }
+}
+
 // General case: the row is the concatenation of the rows of several matrices of any widths.
 __global__ void __launch_bounds__(256) hash_rows_multi(const MatDesc* __restrict__ gm, uint32_t gn, uint64_t h,
                                                        uint32_t* __restrict__ out) {

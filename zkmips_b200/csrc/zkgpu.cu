@@ -366,12 +366,48 @@ static int32_t ensure_slab_bufs(zk_ctx* c, uint64_t bytes) {
 // Streaming LDE of a HOST matrix: column slabs flow  H2D (copy stream)  ||  inverse + coset transforms  ||
 // resumable leaf sponge (compute stream), double buffered.  The slab buffer doubles as the coefficient
 // buffer (in-place inverse transform), so no full-size staging copy of the trace exists on the device.
-// When `leaves` is non-null the rows of the LDE are hashed slab by slab (w must be a multiple of 8).
+// When `cs` is non-null the rows of the LDE are absorbed slab by slab into the sponge of the matrix's height class
+// (`last_member`: this is the last matrix of the class, so its last slab finalises the digests).
+
+// Sponge of one height class of a streaming commit: the rows of the class are the concatenation of the rows of its
+// matrices in input order; `pos` words of every row have been absorbed so far.
+struct ClassStream {
+  uint32_t* digests = nullptr;  // H x 8 words: the leaf layer or the injected digests of the class
+  uint4* state = nullptr;       // H x 16 words between two absorb calls (allocated on demand)
+  uint64_t pos = 0;
+  int remaining = 0;            // matrices of the class not absorbed yet
+  bool any = false;
+};
+
+static int32_t absorb_slab(zk_ctx* c, const uint32_t* lde, uint32_t pitch, uint32_t c0, uint32_t nc, uint64_t H,
+                           ClassStream& cs, bool last) {
+  ProfScope ps(c, "leaf_hash");
+  const bool first = !cs.any;
+  int32_t rc;
+  if (!(first && last) && !cs.state && (rc = dev_alloc(c, H * 64, (void**)&cs.state))) return rc;
+  const uint32_t k0 = (uint32_t)(cs.pos & 7);
+  // fewer than ~3 resident CTAs of 256 threads per SM: 128-thread CTAs spread the rows evenly over the SMs
+  const unsigned bs = H < (1ull << 19) ? 128 : 256;
+  const unsigned blocks = (unsigned)((H + bs - 1) / bs);
+  const bool aligned = k0 == 0 && nc > 0 && nc % 8 == 0 && pitch % 8 == 0 && c0 % 8 == 0 && ((uintptr_t)lde % 32) == 0;
+  if (aligned)
+    ZK_LAUNCH(mk::hash_rows_slab, blocks, bs, 0, c->stream, lde, pitch, c0, nc >> 3, H, cs.state, (int)first, (int)last,
+              cs.digests);
+  else
+    ZK_LAUNCH(mk::hash_rows_slab_any, blocks, bs, 0, c->stream, lde, pitch, c0, nc, H, cs.state, k0, (int)first, (int)last,
+              cs.digests);
+  CK(cudaGetLastError());
+  c->launches++;
+  cs.any = true;
+  cs.pos += nc;
+  return ZK_OK;
+}
+
 static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                               uint32_t* out, uint32_t* leaves, uint32_t* keep_trace) {
+                               uint32_t* out, ClassStream* cs, bool last_member, uint32_t* keep_trace) {
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
-  if (w == 0) return ZK_OK;
+  if (w == 0) return (cs && last_member) ? absorb_slab(c, nullptr, 0, 0, 0, h << log_blowup, *cs, true) : ZK_OK;
   if (!host) return zk_fail(ZK_ERR_ARG, "null matrix pointer");
   const uint64_t H = h << log_blowup;
   // Pageable host memory (a plain Rust Vec): strided 2-D copies from it crawl (measured 4 GB/s), so the trace goes
@@ -384,11 +420,7 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     if (!stage && (rc = dev_alloc(c, h * w * 4ull, (void**)&stage))) return rc;
     CK(cudaMemcpyAsync(stage, host, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
     rc = lde_dev(c, stage, h, w, log_blowup, shift, out);
-    if (rc == ZK_OK && leaves) {
-      ProfScope ps(c, "leaf_hash");
-      std::vector<mk::MatDesc> grp{mk::MatDesc{out, w}};
-      rc = hash_group(c, grp, H, leaves);
-    }
+    if (rc == ZK_OK && cs) rc = absorb_slab(c, out, w, 0, w, H, *cs, last_member);
     if (!keep_trace) dev_free(c, stage);
     return rc;
   }
@@ -425,8 +457,6 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // the two slab buffers and their events live in the context and are shared by every matrix and every call:
   // the copy stream can therefore run ahead into the NEXT matrix while this one is still being transformed
   if ((rc = ensure_slab_bufs(c, h * (uint64_t)slab * 4))) return rc;
-  uint4* state = nullptr;
-  if (leaves && nslab > 1 && (rc = dev_alloc(c, H * 64, (void**)&state))) return rc;
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
     const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = cuts[k], nc = cuts[k + 1] - c0;
     uint32_t* buf = c->slab_buf[b];
@@ -450,17 +480,9 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     if (rc) break;
     CK(cudaEventRecord(c->slab_free[b], c->stream));
     c->slab_used[b] = true;
-    if (leaves) {
-      ProfScope ps(c, "leaf_hash");
-      const unsigned bs = H < (1ull << 19) ? 128 : 256;
-      ZK_LAUNCH(mk::hash_rows_slab, (unsigned)((H + bs - 1) / bs), bs, 0, c->stream, out, w, c0, nc >> 3, H, state, (int)(k == 0),
-                (int)(k + 1 == nslab), leaves);
-      CK(cudaGetLastError());
-      c->launches++;
-    }
+    if (cs && (rc = absorb_slab(c, out, w, c0, nc, H, *cs, last_member && k + 1 == nslab))) break;
   }
   free_scales(c, scales);
-  if (state) dev_free(c, state);
   return rc;
 }
 
@@ -679,19 +701,28 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       if (rc == ZK_OK && domain_shifts[i] == 0) rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
     }
     if (rc == ZK_OK) rc = mmcs_alloc(c, pd);
-    // the row sponge of a height class can be streamed with the LDE when ONE matrix forms the class
-    // (leaf layer for the tallest class, injected digests for the others)
+    // Host traces: the row sponge of every height class is streamed with the LDE (leaf layer for the tallest class,
+    // injected digests for the others); a class of several matrices is absorbed matrix after matrix, in input order.
     std::map<uint64_t, int> members;
-    for (uint32_t i = 0; i < n_mats; i++) members[pd->heights[i]]++;
-    std::vector<uint32_t*> stream_digests(n_mats, nullptr);
-    for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
-      if (!(src_is_host && members[pd->heights[i]] == 1 && widths[i] > 0 && widths[i] % 8 == 0)) continue;
-      if (pd->heights[i] == hmax) {
-        stream_digests[i] = pd->digests;
-        leaves_done = true;
-      } else {
-        rc = dev_alloc(c, pd->heights[i] * 32, (void**)&stream_digests[i]);
-        if (rc == ZK_OK) pd->class_digests[pd->heights[i]] = stream_digests[i];
+    std::map<uint64_t, uint64_t> class_w;
+    for (uint32_t i = 0; i < n_mats; i++) {
+      members[pd->heights[i]]++;
+      class_w[pd->heights[i]] += widths[i];
+    }
+    std::map<uint64_t, ClassStream> cls;
+    if (src_is_host) {
+      for (auto& kv : class_w) {
+        if (rc != ZK_OK || kv.second == 0) continue;
+        ClassStream st;
+        st.remaining = members[kv.first];
+        if (kv.first == hmax) {
+          st.digests = pd->digests;
+          leaves_done = true;
+        } else {
+          rc = dev_alloc(c, kv.first * 32, (void**)&st.digests);
+          if (rc == ZK_OK) pd->class_digests[kv.first] = st.digests;
+        }
+        if (rc == ZK_OK) cls[kv.first] = st;
       }
     }
     std::map<uint64_t, int> pending = members;
@@ -709,15 +740,21 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
           pd->traces[i] = const_cast<uint32_t*>(src[i]);  // borrowed: the caller keeps it alive
         }
       }
-      if (src_is_host)
-        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], stream_digests[i], keep);
-      else
+      if (src_is_host) {
+        auto it = cls.find(pd->heights[i]);
+        ClassStream* st = it == cls.end() ? nullptr : &it->second;
+        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], st, st && st->remaining == 1,
+                             keep);
+        if (st) st->remaining--;
+      } else
         rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
       pending[pd->heights[i]]--;
       // host traces: hash complete height classes and build every tree layer that is already determined while
       // the copy stream is still uploading the remaining matrices
       if (rc == ZK_OK && src_is_host && i + 1 < n_mats) rc = mmcs_advance(c, pd, tp, &pending);
     }
+    for (auto& kv : cls)
+      if (kv.second.state) dev_free(c, kv.second.state);
   } else {
     for (uint32_t i = 0; i < n_mats; i++) {
       pd->heights[i] = heights[i];
