@@ -207,6 +207,53 @@ def run_reference(args):
     })
 
 
+# A maximal log-21 execution shard (crates/core/executor/src/artifacts/maximal_shapes.json): chip -> log2
+# height, with the committed columns per row of each chip from mips_costs.json (`Chip::cost`, crates/stark/src/chip.rs:
+# 151-162: preprocessed + main + 4 * permutation + 4 * quotient columns).
+EXEC21_SHAPE = {"Cpu": (21, 119), "AddSub": (21, 47), "Global": (21, 115), "MemoryInstrs": (20, 115), "Lt": (19, 56),
+                "MemoryLocal": (18, 100), "Branch": (18, 90), "ShiftLeft": (17, 68), "Bitwise": (5, 42), "Jump": (4, 82),
+                "MovCond": (2, 48)}
+
+
+def exec_shard_leg(ctx, torch, args):
+    """Commit of ALL committed columns of a maximal log-21 execution shard in one MachineProver::commit call from
+    pinned host memory: eleven chips, three of them at 2^21 rows (one height class of three matrices whose widths are
+    not multiples of 8, so the class sponge resumes at every alignment), 8.0e8 cells = 3.2 GB of traces."""
+    import numpy as np
+    order = sorted(EXEC21_SHAPE.items(), key=lambda kv: (-kv[1][0], kv[0]))  # prover.rs:264
+    mats = []
+    for k, (name, (lg, w)) in enumerate(order):
+        m = synth_trace(lg, w, 100 + k)
+        mats.append(torch.from_numpy(m.view(np.int32)).pin_memory().numpy().view(np.uint32))
+    cells = sum(m.size for m in mats)
+    one = 0x01FFFFFE
+
+    def commit():
+        root, pd = ctx.commit(mats, [one] * len(mats), LOG_BLOWUP)
+        pd.free()
+        return root
+
+    for _ in range(2):  # the context's memory pool grows to this shard's 10 GB working set (0.1-0.8 s, once)
+        commit()
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    torch.cuda.synchronize()
+    steps = 3
+    t = time.perf_counter()
+    for _ in range(steps):
+        root = commit()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t) / steps
+    ctx.prof_enable(False)
+    stage = {}
+    for name, ms, _ in ctx.prof_records():
+        stage[name] = stage.get(name, 0.0) + ms / steps
+    return {"shape": "maximal log-21 execution shard: " + ", ".join(f"{n} 2^{lg}x{w}" for n, (lg, w) in order),
+            "cells": int(cells), "h2d_bytes": int(4 * cells), "ms_per_commit": dt * 1e3, "Gelem_per_s": cells / dt / 1e9,
+            "pcie_floor_ms": 4 * cells / 55.4e6, "device_stage_ms": {k: round(v, 3) for k, v in stage.items()},
+            "root": [int(x) for x in root], "timing": "host wall clock around zk_commit (pinned host traces in, root out)"}
+
+
 def shard_leg(ctx, torch, dist, world, rank, args):
     """Second BASELINE metric: shard prove ms = MachineProver::commit + open (quotient, quotient commit, Pcs::open
     with 84 queries / 16 PoW bits) for one synthetic shard per GPU, traces in host memory, proof back on the host.
@@ -504,6 +551,8 @@ def main():
     }
     if not args.no_shard:
         out["shard_prove"] = shard_leg(ctx, torch, dist, world, rank, args)
+    if not args.no_shard and world == 1:
+        out["exec_shard_commit"] = exec_shard_leg(ctx, torch, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
         v, cores, sample, _, _ = cpu_commit_sample()

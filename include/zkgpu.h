@@ -56,6 +56,8 @@ int32_t zk_prof_enable(zk_ctx* ctx, int32_t enable);
 int32_t zk_prof_reset(zk_ctx* ctx);
 int32_t zk_prof_count(zk_ctx* ctx);
 int32_t zk_prof_get(zk_ctx* ctx, int32_t i, char* name, int32_t name_cap, float* ms, uint64_t* launches);
+/* start of record i on the ctx stream, in ms after the start of record 0 (timeline of the stages) */
+int32_t zk_prof_start(zk_ctx* ctx, int32_t i, float* ms_after_first);
 /* number of kernels of this library launched on the ctx since creation */
 uint64_t zk_launch_count(zk_ctx* ctx);
 

@@ -240,6 +240,50 @@ def test_streaming_commit_multi_member_classes(be, monkeypatch):
         ctx.destroy()
 
 
+@pytest.mark.parametrize("be", BACKENDS)
+def test_commit_execution_shard_shape(be, monkeypatch):
+    """The chips of a maximal log-21 execution shard (bench.py EXEC21_SHAPE: heights from maximal_shapes.json, widths
+    from mips_costs.json), scaled down by 2^9 rows so the oracle finishes in seconds: eleven matrices, a three-member
+    tallest class with widths 47 + 119 + 115, in the prover's (-height, name) order, streamed from host memory."""
+    import bench
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    monkeypatch.setenv("ZK_SLAB_COLS", "32")
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+    order = sorted(bench.EXEC21_SHAPE.items(), key=lambda kv: (-kv[1][0], kv[0]))
+    down = 13 if be == "emu" else 9
+    mats = [_mont(1 << max(lg - down, 0), w, seed=70 + k) for k, (name, (lg, w)) in enumerate(order)]
+    try:
+        _check_commit(ctx, mats, [one] * len(mats), 1)
+    finally:
+        ctx.destroy()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_streaming_commit_retained_traces(be, monkeypatch):
+    """zk_ctx_keep_traces: the slabs are uploaded straight into the retained trace (strided) and transformed from
+    there.  The retained trace must equal the input and the commitment the oracle's, for several slabs per matrix,
+    a ragged last slab, an odd width and a one-slab matrix."""
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_SLAB_COLS", "16")
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    ctx.keep_traces(True)
+    one = ob.lib().ork_to_monty(1)
+    try:
+        mats = [_mont(64, 40, seed=81), _mont(64, 35, seed=82), _mont(16, 8, seed=83), _mont(64, 2, seed=84)]
+        root, pd = ctx.commit(mats, [one] * len(mats), 1)
+        assert (root == ob.pcs_commit(mats, 1, [one] * len(mats)).root).all()
+        for i, m in enumerate(mats):
+            assert (ctx.download(pd.trace_ptr(i), m.shape) == m).all(), f"retained trace {i} differs from the input"
+        pd.free()
+    finally:
+        ctx.destroy()
+
+
 def test_lde_two_pass_k10_emu():
     """2^20 rows x 2 columns: both k=10 passes of the second-generation kernel (coset scale + bit-reversed
     gather fused in the first, pass twiddles) on the emulator; the GPU twins are the 2^20 cases above."""

@@ -143,7 +143,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < zk_ctx::NSLAB; b++) {
     if (c->slab_buf[b]) cudaFree(c->slab_buf[b]);
     if (c->slab_up[b]) cudaEventDestroy(c->slab_up[b]);
     if (c->slab_free[b]) cudaEventDestroy(c->slab_free[b]);
@@ -192,6 +192,13 @@ extern "C" int32_t zk_prof_get(zk_ctx* c, int32_t i, char* name, int32_t cap, fl
     strncpy(name, r.name.c_str(), cap - 1);
     name[cap - 1] = 0;
   }
+  return ZK_OK;
+}
+// start of record i on the ctx stream, in ms after the start of record 0 (a timeline of the stages)
+extern "C" int32_t zk_prof_start(zk_ctx* c, int32_t i, float* ms_after_first) {
+  if (!c || !ms_after_first || i < 0 || i >= (int32_t)c->recs.size()) return zk_fail(ZK_ERR_ARG, "bad profile record index");
+  CK(cudaEventSynchronize(c->recs[i].a));
+  CK(cudaEventElapsedTime(ms_after_first, c->recs[0].a, c->recs[i].a));
   return ZK_OK;
 }
 extern "C" uint64_t zk_launch_count(zk_ctx* c) { return c ? c->launches : 0; }
@@ -344,12 +351,23 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
 
 static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t h, uint32_t* out);
 
-// (Re)allocates the context's two slab buffers when a larger slab is needed (rare; synchronises).
+// dst[r * dpitch + j] = src[r * nc + j], j < nc: a column slab back into its place in the row-major retained trace
+template <class T>
+__global__ void __launch_bounds__(256) scatter_cols_kernel(const T* __restrict__ src, T* __restrict__ dst, uint32_t nc,
+                                                           uint32_t dpitch, uint64_t total) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = i / nc;
+    uint32_t j = (uint32_t)(i - r * nc);
+    dst[r * dpitch + j] = src[i];
+  }
+}
+
+// (Re)allocates the context's slab buffers when a larger slab is needed (rare; synchronises).
 static int32_t ensure_slab_bufs(zk_ctx* c, uint64_t bytes) {
   if (bytes <= c->slab_cap) return ZK_OK;
   CK(cudaStreamSynchronize(c->copy_stream));
   CK(cudaStreamSynchronize(c->stream));
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < zk_ctx::NSLAB; b++) {
     if (c->slab_buf[b]) CK(cudaFree(c->slab_buf[b]));
     c->slab_buf[b] = nullptr;
     CK(cudaMalloc(&c->slab_buf[b], bytes));
@@ -440,16 +458,22 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // full slab is therefore cut in halves, down to 32 columns (128 B rows still copy at full PCIe rate, 64 B rows
   // do not): 256 columns go up as 64, 64, 64, 32, 32 and the tail is a 32-column slab instead of a 64-column one.
   std::vector<uint32_t> cuts;  // first column of every slab, then w
-  {
-    uint32_t c0 = 0;
-    while (c0 < w) {
-      cuts.push_back(c0);
-      uint32_t nc = std::min(slab, w - c0);
-      if (c->slab_cols == 0 && slab < w && w - c0 <= slab && nc >= 64 && nc % 32 == 0) nc /= 2;
+  if (c->slab_cols != 0 || slab >= w) {  // fixed slab width (ZK_SLAB_COLS), or one slab
+    for (uint32_t c0 = 0; c0 < w; c0 += slab) cuts.push_back(c0);
+  } else {
+    // about w / slab slabs of EQUAL width (a multiple of 8 columns), never a narrow remainder: 68 columns cut as
+    // 64 + 4 made the second upload a 2-D copy of 2^17 rows of 16 bytes -- 7.8 ms for 2 MB
+    const uint32_t ns = std::max(1u, (w + slab / 2) / slab);
+    const uint32_t base = ns > 1 ? std::max(8u, w / ns / 8 * 8) : w;
+    for (uint32_t k = 0; k < ns; k++) cuts.push_back(k * base);
+    uint32_t c0 = (ns - 1) * base, nc = w - c0;
+    while (ns > 1 && nc >= 64 && nc % 32 == 0) {  // taper the last slab: halves, down to 32 columns
+      nc /= 2;
       c0 += nc;
+      cuts.push_back(c0);
     }
-    cuts.push_back(w);
   }
+  cuts.push_back(w);
   const uint32_t nslab = (uint32_t)cuts.size() - 1;
   std::vector<ntt::CosetScale> scales;
   const bool aligned = (w & 1u) == 0 && (slab & 1u) == 0 && ((uintptr_t)out % 8) == 0;
@@ -458,7 +482,7 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // the copy stream can therefore run ahead into the NEXT matrix while this one is still being transformed
   if ((rc = ensure_slab_bufs(c, h * (uint64_t)slab * 4))) return rc;
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
-    const uint32_t b = (uint32_t)(c->slab_seq++ & 1), c0 = cuts[k], nc = cuts[k + 1] - c0;
+    const uint32_t b = (uint32_t)(c->slab_seq++ % zk_ctx::NSLAB), c0 = cuts[k], nc = cuts[k + 1] - c0;
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
     if (nc == w)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
@@ -469,11 +493,22 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
     if (keep_trace) {  // retain the slab before the in-place inverse transform overwrites it
-      if (nc == w)  // one slab: a plain copy (a 2-D copy of 2^20 rows of 8 bytes is issued row by row: 100 ms)
+      if (nc == w) {
         CK(cudaMemcpyAsync(keep_trace, buf, (size_t)h * w * 4, cudaMemcpyDeviceToDevice, c->stream));
-      else
-        CK(cudaMemcpy2DAsync(keep_trace + c0, (size_t)w * 4, buf, (size_t)nc * 4, (size_t)nc * 4, h,
-                             cudaMemcpyDeviceToDevice, c->stream));
+      } else {
+        // a kernel, not cudaMemcpy2DAsync: 2-D copies are issued row by row (2^20 rows of 8 bytes: 100 ms; the slabs
+        // of a 3.2 GB execution shard: 22 ms), and uploading straight into the strided destination is slower still
+        const bool v4 = ((nc | w | c0) & 3u) == 0;
+        const uint64_t total = (uint64_t)h * (v4 ? nc / 4 : nc);
+        const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32);
+        if (v4)
+          ZK_LAUNCH(scatter_cols_kernel<uint4>, blocks, 256, 0, c->stream, reinterpret_cast<const uint4*>(buf),
+                    reinterpret_cast<uint4*>(keep_trace + c0), nc / 4, w / 4, total);
+        else
+          ZK_LAUNCH(scatter_cols_kernel<uint32_t>, blocks, 256, 0, c->stream, buf, keep_trace + c0, nc, w, total);
+        CK(cudaGetLastError());
+        c->launches++;
+      }
     }
     ntt::Cols sl{buf, nc, 0};
     rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);

@@ -30,11 +30,14 @@ struct zk_ctx {
   bool own_stream = false;
   cudaMemPool_t pool = nullptr;         // private stream-ordered allocator of this context
   cudaStream_t copy_stream = nullptr;   // H2D of trace slabs, overlapped with compute on `stream`
-  uint32_t* slab_buf[2] = {nullptr, nullptr};  // double-buffered upload slabs, shared by all matrices / calls
+  // upload slabs, shared by all matrices / calls (a third buffer was measured: no gain, the copy stream is not
+  // held back by buffer reuse but by the PCIe rate of odd-pitch rows)
+  static constexpr int NSLAB = 2;
+  uint32_t* slab_buf[NSLAB] = {nullptr, nullptr};
   uint64_t slab_cap = 0;
   uint64_t slab_seq = 0;
-  bool slab_used[2] = {false, false};
-  cudaEvent_t slab_up[2] = {nullptr, nullptr}, slab_free[2] = {nullptr, nullptr};
+  bool slab_used[NSLAB] = {false, false};
+  cudaEvent_t slab_up[NSLAB] = {nullptr, nullptr}, slab_free[NSLAB] = {nullptr, nullptr};
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
   uint64_t slab_bytes = 256ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "zk_prof_reset": (i32, [vp]),
     "zk_prof_count": (i32, [vp]),
     "zk_prof_get": (i32, [vp, i32, C.c_char_p, i32, C.POINTER(C.c_float), u64p]),
+    "zk_prof_start": (i32, [vp, i32, C.POINTER(C.c_float)]),
     "zk_launch_count": (u64, [vp]),
     "zk_dev_alloc": (i32, [vp, u64, u64p]),
     "zk_dev_free": (i32, [vp, u64]),
@@ -210,6 +211,15 @@ class Ctx:
         for i in range(self.d.zk_prof_count(self.h)):
             self.lib.check(self.d.zk_prof_get(self.h, i, buf, 64, C.byref(ms), C.byref(nl)))
             out.append((buf.value.decode(), ms.value, nl.value))
+        return out
+
+    def prof_timeline(self):
+        """(name, start ms after the first record, duration ms) of every record: a timeline of the ctx stream"""
+        out = []
+        t0 = C.c_float()
+        for i, (name, ms, _) in enumerate(self.prof_records()):
+            self.lib.check(self.d.zk_prof_start(self.h, i, C.byref(t0)))
+            out.append((name, t0.value, ms))
         return out
 
     # ---- device memory
