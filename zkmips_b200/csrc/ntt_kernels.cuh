@@ -245,7 +245,10 @@ inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// columns per thread: 2 needs every access 8-byte aligned (env ZK_NTT_CPT=1 forces the scalar variant)
+// columns per thread: 2 needs every access 8-byte aligned (env ZK_NTT_CPT=1 forces the scalar variant).  Letting the
+// two-column kernel fall back to 32-bit accesses per side at run time (for odd chip widths) was measured: the extra
+// uniform branches in the 32-deep load / store loops cost the ALIGNED case 1.44 -> 1.71 ms (inverse) and 3.17 -> 5.0 ms
+// (coset) per 2^20 x 256 LDE, and the odd-width execution shard got slower too (NTT 20.3 -> 28.6 ms): reverted.
 inline bool pass_aligned(const PassArgs& A) {
   return ((A.ws | A.wd | A.c0s | A.c0d | A.nc) & 1u) == 0 && ((uintptr_t)A.src % 8) == 0 && ((uintptr_t)A.dst % 8) == 0;
 }
