@@ -248,7 +248,9 @@ inline cudaError_t launch_reg(const PassArgs& A, cudaStream_t st) {
 // columns per thread: 2 needs every access 8-byte aligned (env ZK_NTT_CPT=1 forces the scalar variant).  Letting the
 // two-column kernel fall back to 32-bit accesses per side at run time (for odd chip widths) was measured: the extra
 // uniform branches in the 32-deep load / store loops cost the ALIGNED case 1.44 -> 1.71 ms (inverse) and 3.17 -> 5.0 ms
-// (coset) per 2^20 x 256 LDE, and the odd-width execution shard got slower too (NTT 20.3 -> 28.6 ms): reverted.
+// (coset) per 2^20 x 256 LDE, and the odd-width execution shard got slower too (NTT 20.3 -> 28.6 ms): reverted.  A
+// compile-time two-column variant with 32-bit global accesses (no run-time branches) left the aligned case untouched but
+// was still slower than one column per thread on the odd widths (20.3 -> 22.0 ms): it is the 64-bit accesses that pay.
 inline bool pass_aligned(const PassArgs& A) {
   return ((A.ws | A.wd | A.c0s | A.c0d | A.nc) & 1u) == 0 && ((uintptr_t)A.src % 8) == 0 && ((uintptr_t)A.dst % 8) == 0;
 }
