@@ -1,4 +1,5 @@
-"""Timeline (start, duration) of the stage records of one execution-shard commit from pinned host memory."""
+"""Timeline (start, duration, gap) of the stage records of one commit from pinned host memory.
+usage: python tools/bench/commit_timeline.py [exec|keccak|headline] [keep]   (exec: bench.EXEC21_SHAPE; keccak: 2^16 x 2 + 2^16 x 4096; headline: 2^20 x 256)"""
 import time, sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
@@ -6,8 +7,10 @@ import bench
 from zkmips_b200 import native
 lib = native.load()
 ctx = lib.ctx_create(0)
-if len(sys.argv) > 1: ctx.keep_traces(True)
-order = sorted(bench.EXEC21_SHAPE.items(), key=lambda kv: (-kv[1][0], kv[0]))
+which = sys.argv[1] if len(sys.argv) > 1 else "exec"
+if "keep" in sys.argv[1:]: ctx.keep_traces(True)
+shape = {"exec": bench.EXEC21_SHAPE, "keccak": {"Fibonacci": (16, 2), "Wide4096": (16, 4096)}, "headline": {"Trace": (20, 256)}}[which if which in ("exec", "keccak", "headline") else "exec"]
+order = sorted(shape.items(), key=lambda kv: (-kv[1][0], kv[0]))
 mats = [torch.from_numpy(bench.synth_trace(lg, w, 100 + k).view(np.int32)).pin_memory().numpy().view(np.uint32) for k, (n, (lg, w)) in enumerate(order)]
 one = 0x01FFFFFE
 for _ in range(2):
