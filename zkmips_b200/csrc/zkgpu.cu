@@ -88,6 +88,7 @@ static int32_t ctx_init(zk_ctx* c) {
     if (v >= 1) c->slab_bytes = (uint64_t)v << 20;
   }
   if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
+  if (const char* e = getenv("ZK_HASH_VEC_MIN_ROWS")) c->hash_vec_min_rows = strtoull(e, nullptr, 10);
   // a private stream-ordered pool per context: contexts that prove shards concurrently on one GPU must not
   // couple their streams through cross-stream reuse of freed blocks in the device's default pool
   cudaMemPoolProps props;
@@ -407,7 +408,10 @@ static int32_t absorb_slab(zk_ctx* c, const uint32_t* lde, uint32_t pitch, uint3
   // fewer than ~3 resident CTAs of 256 threads per SM: 128-thread CTAs spread the rows evenly over the SMs
   const unsigned bs = H < (1ull << 19) ? 128 : 256;
   const unsigned blocks = (unsigned)((H + bs - 1) / bs);
-  const bool aligned = k0 == 0 && nc > 0 && nc % 8 == 0 && pitch % 8 == 0 && c0 % 8 == 0 && ((uintptr_t)lde % 32) == 0;
+  // the vector-load kernel needs block alignment; below 2^19 rows the scalar-load kernel is the faster one anyway
+  // (5.58 vs 5.75 ms of leaf hashing on the 86 M-cell shard: fewer live registers across the permutation)
+  const bool aligned = H >= c->hash_vec_min_rows && k0 == 0 && nc > 0 && nc % 8 == 0 && pitch % 8 == 0 && c0 % 8 == 0 &&
+                       ((uintptr_t)lde % 32) == 0;
   if (aligned)
     ZK_LAUNCH(mk::hash_rows_slab, blocks, bs, 0, c->stream, lde, pitch, c0, nc >> 3, H, cs.state, (int)first, (int)last,
               cs.digests);

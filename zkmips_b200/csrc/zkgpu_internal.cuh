@@ -40,6 +40,7 @@ struct zk_ctx {
   cudaEvent_t slab_up[NSLAB] = {nullptr, nullptr}, slab_free[NSLAB] = {nullptr, nullptr};
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
   uint64_t slab_bytes = 256ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
+  uint64_t hash_vec_min_rows = 1ull << 19;  // streamed sponge: vector-load kernel from this many rows (env ZK_HASH_VEC_MIN_ROWS)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
