@@ -212,6 +212,16 @@ def test_streaming_commit_tapered_slabs(be, monkeypatch):
         _check_commit(ctx, [pin(_mont(64, 512, seed=43)), pin(_mont(16, 24, seed=44))], [one] * 2, 1)  # 128 x 3, 64, 64
     finally:
         ctx.destroy()
+    # Uneven cuts: the widest slab of the schedule can exceed the nominal slab width -- 68 and 90 columns
+    # round to ONE slab of the whole width, 300 columns are cut 72, 72, 72, 84 (nominal 80), 119 is odd.  Each in a FRESH
+    # context, so the slab buffers are sized by this matrix alone (a larger earlier matrix would hide an overflow).
+    for k, w in enumerate((68, 90, 119, 300, 1000)):
+        ctx = lib.ctx_create(0)
+        try:
+            _check_commit(ctx, [pin(_mont(64, w, seed=45 + k))], [one], 1)
+            _check_commit(ctx, [pin(_mont(32, w, seed=145 + k)), pin(_mont(32, 3, seed=245 + k))], [one] * 2, 2)
+        finally:
+            ctx.destroy()
 
 
 @pytest.mark.parametrize("be", BACKENDS)
@@ -244,7 +254,8 @@ def test_streaming_commit_multi_member_classes(be, monkeypatch):
 @pytest.mark.parametrize("be", BACKENDS)
 def test_commit_execution_shard_shape(be, monkeypatch):
     """The chips of a maximal log-21 execution shard (bench.py EXEC21_SHAPE: heights from maximal_shapes.json, widths
-    from mips_costs.json), scaled down by 2^9 rows so the oracle finishes in seconds: eleven matrices, a three-member
+    from mips_costs.json), scaled down by 2^5 rows on the GPU (2^13 on the emulator) so the oracle finishes in seconds:
+    eleven matrices, a three-member
     tallest class with widths 47 + 119 + 115, in the prover's (-height, name) order, streamed from host memory."""
     import bench
     from zkmips_b200 import native
@@ -254,7 +265,7 @@ def test_commit_execution_shard_shape(be, monkeypatch):
     ctx = lib.ctx_create(0)
     one = ob.lib().ork_to_monty(1)
     order = sorted(bench.EXEC21_SHAPE.items(), key=lambda kv: (-kv[1][0], kv[0]))
-    down = 13 if be == "emu" else 9
+    down = 13 if be == "emu" else 5
     mats = [_mont(1 << max(lg - down, 0), w, seed=70 + k) for k, (name, (lg, w)) in enumerate(order)]
     try:
         _check_commit(ctx, mats, [one] * len(mats), 1)

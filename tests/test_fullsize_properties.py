@@ -98,3 +98,34 @@ def test_max_height_and_two_adicity_limit():
     pd.free()
     with pytest.raises(ZkError):
         ctx.commit([tr], [ONE], 3)
+
+
+@pytest.mark.parametrize("kind", ["a", "b"])
+def test_config2_commit_bit_exact_with_oracle(kind):
+    """BASELINE config 2 at FULL size (2^20 x 256, blowup 2), both inputs of SURVEY 8(d): (a) (r*W + c) mod p,
+    (b) splitmix64(0x5A4B4D49).  The oracle's Pcs::commit of the same trace takes seconds on the box's host cores,
+    so the headline configuration is pinned bit for bit: root, three sampled digest layers (leaves, middle, near
+    the top), and LDE rows + Merkle paths at sampled indices -- from pinned host memory (streaming commit) and from
+    a device-resident trace (zk_commit_dev), which is the path bench.py's `value` times."""
+    import torch
+    ctx = backends.gpu()
+    tr = util.config2_trace(kind)
+    tree = ob.pcs_commit([tr], 1)
+    pinned = torch.from_numpy(tr.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    root, pd = ctx.commit([pinned], [ONE], 1)
+    assert (root == tree.root).all(), "streaming commit: root differs from the oracle"
+    for layer in (0, 9, 17):
+        assert (pd.layer(layer) == tree.layer(layer)).all(), f"digest layer {layer} differs from the oracle"
+    idx = [0, 1, (1 << 21) - 1, 1 << 20, 1234567, 777777]
+    opened, proofs = pd.open_batch(idx)
+    for k, i in enumerate(idx):
+        rows, proof = tree.open(i)
+        assert (opened[k] == rows[0]).all(), f"LDE row {i} differs from the oracle"
+        assert (proofs[k] == proof).all(), f"Merkle path {i} differs from the oracle"
+    pd.free()
+    dptr = ctx.upload(tr)
+    root2, pd2 = ctx.commit_dev([dptr], [tr.shape], [ONE], 1)
+    assert (root2 == tree.root).all(), "device-resident commit: root differs from the oracle"
+    assert (pd2.layer(0)[::4099] == tree.layer(0)[::4099]).all()
+    pd2.free()
+    ctx.dev_free(dptr)

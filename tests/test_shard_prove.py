@@ -26,11 +26,17 @@ def _natural(lde_bitrev):
 
 
 @pytest.mark.parametrize("be", BACKENDS)
-@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup"])
+@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096"])
 def test_quotient_values_match_oracle(be, which):
+    """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
+    constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
+    quotient buffer (quotient.cuh accumulate path), which the small chips never reach."""
     ctx = _backend(be)
     chip = {"fibonacci": lambda: su.fibonacci_chip(5), "wide": lambda: su.wide_chip(4, 64),
-            "lookup": lambda: su.lookup_chip(4)}[which]()
+            "lookup": lambda: su.lookup_chip(4), "wide1024": lambda: su.wide_chip(10, 1024, seed=21),
+            "wide4096": lambda: su.wide_chip(8, 4096, seed=22)}[which]()
+    if which in ("wide1024", "wide4096"):
+        assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
     air = su.AIRS[chip.air]
     n = chip.log_degree
     _, main_pd = ctx.commit([chip.main], [MONTY_ONE], 1)

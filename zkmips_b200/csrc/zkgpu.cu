@@ -484,7 +484,15 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
   // the two slab buffers and their events live in the context and are shared by every matrix and every call:
   // the copy stream can therefore run ahead into the NEXT matrix while this one is still being transformed
-  if ((rc = ensure_slab_bufs(c, h * (uint64_t)slab * 4))) return rc;
+  // sized by the WIDEST slab of the schedule, not by the nominal `slab`: equal-width cuts round down to a multiple of
+  // 8 columns and hand the remainder to the last slab (300 columns -> 72, 72, 72, 84 with slab = 80), and a matrix
+  // whose width rounds to one slab goes up whole (68 or 90 columns with slab = 64)
+  uint32_t widest = 0;
+  for (uint32_t k = 0; k < nslab; k++) widest = std::max(widest, cuts[k + 1] - cuts[k]);
+  if ((rc = ensure_slab_bufs(c, h * (uint64_t)widest * 4))) {
+    free_scales(c, scales);
+    return rc;
+  }
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
     const uint32_t b = (uint32_t)(c->slab_seq++ % zk_ctx::NSLAB), c0 = cuts[k], nc = cuts[k + 1] - c0;
     uint32_t* buf = c->slab_buf[b];
