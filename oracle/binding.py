@@ -88,6 +88,7 @@ def lib():
         L.ork_mmcs_verify.restype = C.c_int32
         L.ork_mmcs_verify.argtypes = [_u32p, C.c_uint32, _u64p, _u64p, C.c_uint64, _u32p, _u32p, C.c_uint32]
         L.ork_num_threads.restype = C.c_int32
+        L.ork_set_num_threads.argtypes = [C.c_int32]
         _bind_fri(L)
         _lib = L
     return _lib
@@ -283,3 +284,11 @@ def pcs_commit(mats, log_blowup=1, domain_shifts=None):
     if rc != 0:
         raise ValueError(f"ork_pcs_commit failed: {rc}")
     return Tree(h, root)
+
+
+def use_all_cores():
+    """OpenMP thread count = the cores this process may run on, whatever OMP_NUM_THREADS says (torch.distributed.run
+    exports OMP_NUM_THREADS=1 to its workers).  Returns the count."""
+    n = len(os.sched_getaffinity(0))
+    lib().ork_set_num_threads(n)
+    return lib().ork_num_threads()

@@ -40,6 +40,14 @@ int32_t ork_num_threads(void) {
   return 1;
 #endif
 }
+/* overrides OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers) */
+void ork_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* Poseidon2 width 16, x^3, 8 external + 13 internal rounds                                   */

@@ -80,6 +80,7 @@ int32_t ork_pcs_commit(uint32_t n_mats, const uint32_t* const* mats, const uint6
                        uint32_t root[8], ork_tree** out);
 
 int32_t ork_num_threads(void);
+void ork_set_num_threads(int32_t n);
 
 /* ---- DuplexChallenger<Val, Perm, 16, 8> ---- */
 typedef struct {

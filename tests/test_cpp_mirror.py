@@ -35,7 +35,7 @@ def _run_and_check(exe, log_n, nq, pw):
     assert got["opened_row_5"] == [int(x) for x in tree.matrix(0)[5]]
     assert got["path_len"] == log_n + 1
     ch = bf.new_challenger()
-    bf.observe(ch, chip.public_values)
+    bf.observe(ch, su.M(chip.pvs))
     bf.observe(ch, tree.root)
     bf.sample_ext(ch)
     bf.sample_ext(ch)

@@ -26,7 +26,7 @@ def _natural(lde_bitrev):
 
 
 @pytest.mark.parametrize("be", BACKENDS)
-@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096"])
+@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -34,7 +34,8 @@ def test_quotient_values_match_oracle(be, which):
     ctx = _backend(be)
     chip = {"fibonacci": lambda: su.fibonacci_chip(5), "wide": lambda: su.wide_chip(4, 64),
             "lookup": lambda: su.lookup_chip(4), "wide1024": lambda: su.wide_chip(10, 1024, seed=21),
-            "wide4096": lambda: su.wide_chip(8, 4096, seed=22)}[which]()
+            "wide4096": lambda: su.wide_chip(8, 4096, seed=22), "global": lambda: su.global_chip(5),
+            "local_bool": lambda: su.local_bool_chip(4)}[which]()
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
     air = su.AIRS[chip.air]
@@ -50,7 +51,7 @@ def test_quotient_values_match_oracle(be, which):
         kw["prep"] = (prep_pd, 0)
         okw["prep_q"] = _natural(prep_pd.lde(0))
     lcs = None
-    if chip.has_lookups:
+    if air.sends or air.receives:
         # device LogUp trace (zk_permutation_trace) against the numpy restatement of permutation.rs:102-196
         from oracle import logup
         p_c, m_c = chip.canon
@@ -63,12 +64,14 @@ def test_quotient_values_match_oracle(be, which):
         kw["perm"] = (perm_pd, 0)
         okw["perm_q"] = _natural(perm_pd.lde(0))
         okw["lcs"] = ob.from_monty(lcs)
-    dptr = ctx.quotient(chip.air, (main_pd, 0), n, 1, alpha, perm_challenges=chal, public_values=chip.public_values,
-                        local_cumsum=lcs, global_cumsum=chip.global_cumsum, **kw)
+    pvs = su.public_values_for([chip])
+    gcs = su.M(np.arange(1, 15))
+    dptr = ctx.quotient(chip.air, (main_pd, 0), n, 1, alpha, perm_challenges=chal, public_values=pvs,
+                        local_cumsum=lcs, global_cumsum=gcs, **kw)
     got = ob.from_monty(ctx.download(dptr, (2, 1 << n, 4)))
     ctx.dev_free(dptr)
     exp = ae.quotient_values(air, n, 1, _natural(main_pd.lde(0)), ob.from_monty(alpha), chal=ob.from_monty(chal),
-                             gcs=ob.from_monty(chip.global_cumsum), pvs=ob.from_monty(chip.public_values), **okw)
+                             gcs=ob.from_monty(gcs), pvs=ob.from_monty(pvs), **okw)
     # chunk c holds the rows i = c (mod 2)
     assert (got[0] == exp[0::2]).all() and (got[1] == exp[1::2]).all()
     # the quotient of a valid trace is a polynomial of degree < 2N: its top half of coefficients vanish, which
@@ -76,31 +79,167 @@ def test_quotient_values_match_oracle(be, which):
     assert exp.any()
 
 
+NUM_PV = 8  # StarkMachine::num_pv_elts of the synthetic machine
+
+
+def _machine(chips):
+    return {c.name: c for c in chips}
+
+
+def _prove(ctx, chips, log_blowup, nq, pw, pc_start=0x1234, mutate=None):
+    """setup + the machine-level challenger (pk.observe_into) + prove one shard; returns what the verifier needs"""
+    prover = GpuShardProver(ctx, log_blowup, nq, pw, num_pv_elts=NUM_PV)
+    pk = prover.setup(chips, pc_start=su.M([pc_start])[0], initial_global_cumulative_sum=su.M(np.arange(101, 115)))
+    ch = Challenger(ctx)
+    pk.observe_into(ch)                                  # machine.rs:79-86, once per proof; shards get a clone
+    pvs = su.public_values_for(chips, NUM_PV)
+    data = prover.commit(chips, pvs)
+    if mutate:
+        mutate(prover, pk, data)
+    sp = prover.open(pk, data, Challenger(ctx, ch.w))
+    return prover, pk, data, sp
+
+
 @pytest.mark.parametrize("be", BACKENDS)
 def test_shard_proof_verifies(be):
-    """multi-chip shard (BASELINE config 1 stand-in): Fibonacci + wide + lookup chips of different heights."""
+    """multi-chip shard (BASELINE config 1 stand-in) proven with the reference's transcript and checked by the
+    verifier written from crates/stark/src/verifier.rs alone: Fibonacci (public values), a wide chip, a balanced LogUp
+    pair (`local_only`, so their main traces open at zeta only), a Global-scope chip whose cumulative sum is read
+    from its last 14 main columns, a `local_only` chip without lookups and a chip with a preprocessed trace."""
     ctx = _backend(be)
     nq, pw = (8, 6) if be == "emu" else (84, 16)
-    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), su.lookup_chip(5), su.fibonacci_chip(3, 2, 5, name="Fib2")]
-    prover = GpuShardProver(ctx, 1, nq, pw)
-    prep_root, prep_pd = prover.setup(chips)
-    ch = Challenger(ctx)
-    ch.observe(prep_root)  # stands in for the vk/pc_start observations of machine.rs:79-86
-    start = ch.w.copy()
-    ordered, root, pd = prover.commit(chips)
-    assert [c.name for c in ordered] == ["Fibonacci", "Lookup", "Wide64", "Fib2"]
+    send, recv = su.lookup_side_chips(5)
+    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), send, recv, su.global_chip(3), su.local_bool_chip(4)]
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
+    assert [c.name for c in data.chips] == ["Fibonacci", "LookupRecv", "LookupSend", "LocalBool", "Wide64", "GlobalTail"]
     # commitment parity with the oracle PCS
-    assert (root == ob.pcs_commit([c.main for c in ordered], 1).root).all()
-    sp = prover.open(ordered, root, pd, ch, prep_root, prep_pd)
-    ok, why = su.verify_shard(sp, ordered, start, 1, nq, pw)
+    assert (data.main_commit == ob.pcs_commit([c.main for c in data.chips], 1).root).all()
+    vk = su.vk_of(pk)
+    ok, why = su.machine_verify(vk, _machine(chips), [sp], NUM_PV, 1, nq, pw)
     assert ok, why
-    # tampering with an opened value or a commitment must be rejected
-    bad = sp.pcs_proof.copy()
-    bad[3] ^= 1
-    sp_bad = type(sp)(**{**sp.__dict__, "pcs_proof": bad})
-    assert not su.verify_shard(sp_bad, ordered, start, 1, nq, pw)[0]
-    pd.free()
-    prep_pd.free()
+    # every chip has a permutation matrix (width 0 without lookups) and the Global chip's sum is its last 14 columns
+    gi = sp.chip_ordering["GlobalTail"]
+    assert (sp.opened_values[gi].global_cumulative_sum == data.chips[gi].main.reshape(-1)[-14:]).all()
+    assert all(v.permutation.local.shape[0] == 4 * su.AIRS[c.air].perm_width for v, c in zip(sp.opened_values, data.chips))
+    li = sp.chip_ordering["LookupSend"]
+    assert not sp.opened_values[li].main.next.any() and sp.opened_values[li].main.local.any()   # local_only: next = 0
+    assert sp.opened_values[li].local_cumulative_sum.any() and not sp.local_cumulative_sum().any()
+    # tampering with an opened value, a commitment, a cumulative sum or a public value must be rejected
+    import copy
+    for what in ("opened", "commit", "lcs", "pv"):
+        bad = copy.deepcopy(sp)
+        if what == "opened":
+            bad.opened_values[0].main.local[0, 0] ^= 1
+        elif what == "commit":
+            bad.commitment.quotient_commit[3] ^= 1
+        elif what == "lcs":
+            bad.opened_values[li].local_cumulative_sum[1] ^= 1
+        else:
+            bad.public_values[5] ^= 1
+        assert not su.machine_verify(vk, _machine(chips), [bad], NUM_PV, 1, nq, pw)[0], what
+    # the wire format round-trips and the decoded proof verifies
+    from zkmips_b200 import proof as pf
+    blob = pf.to_bincode(sp)
+    sp2 = pf.from_bincode(blob)
+    assert pf.to_bincode(sp2) == blob
+    ok, why = su.machine_verify(vk, _machine(chips), [sp2], NUM_PV, 1, nq, pw)
+    assert ok, why
+    data.main_data.free()
+    pk.data and pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_shard_proof_bit_exact_with_oracle_prover(be):
+    """north_star: "identical Merkle roots, quotient commitments, FRI query openings".  The CPU restatement of the
+    reference prover (oracle/shard_prover.py: C oracle commits and Pcs::open, numpy LogUp and quotient) and the GPU
+    path prove the same shard from the same challenger; the two `ShardProof`s must have the same bincode image --
+    every commitment, opened value, cumulative sum, FRI layer root, the pow witness (both take the smallest) and every
+    query opening and Merkle path."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (8, 6) if be == "emu" else (84, 16)
+    send, recv = su.lookup_side_chips(5)
+    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), send, recv, su.global_chip(3), su.local_bool_chip(4),
+             su.lookup_chip(5)]
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=NUM_PV)
+    opk = op.setup(chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    assert (opk.commit == pk.commit).all()
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    osp_proof = op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))
+    assert (osp_proof.commitment.main_commit == sp.commitment.main_commit).all()
+    assert (osp_proof.commitment.permutation_commit == sp.commitment.permutation_commit).all()
+    assert (osp_proof.commitment.quotient_commit == sp.commitment.quotient_commit).all()
+    assert osp_proof.opening_proof.pow_witness == sp.opening_proof.pow_witness
+    assert pf.to_bincode(osp_proof) == pf.to_bincode(sp)
+    data.main_data.free()
+    pk.data.free()
+
+
+@pytest.mark.parametrize("drop", ["public_values", "vk", "local_sum", "global_sum", "perm_commit", "local_only"])
+@pytest.mark.parametrize("be", BACKENDS)
+def test_dropped_observation_fails_verification(be, drop, monkeypatch):
+    """VERDICT round 1, task 2: a prover that skips any one transcript step of prover.rs:322,406-413 -- or opens a
+    `local_only` chip at two points -- must produce a proof the (independent) verifier rejects."""
+    ctx = _backend(be)
+    nq, pw = 6, 4
+    send, recv = su.lookup_side_chips(4)
+    chips = [su.fibonacci_chip(5), send, recv, su.global_chip(3)]
+    prover = GpuShardProver(ctx, 1, nq, pw, num_pv_elts=NUM_PV)
+    pk = prover.setup(chips, pc_start=su.M([77])[0])
+    ch = Challenger(ctx)
+    if drop != "vk":
+        pk.observe_into(ch)
+    pvs = su.public_values_for(chips, NUM_PV)
+    data = prover.commit(chips, pvs)
+    if drop == "public_values":
+        prover.num_pv_elts = 0                       # skips prover.rs:322
+    if drop == "local_only":
+        for c in data.chips:
+            c.local_only = False                     # opens [zeta, zeta*g] where the verifier expects [zeta]
+    real_observe = Challenger.observe
+    seen = {"n": 0}
+
+    def observe(self, vals):
+        v = np.asarray(vals, np.uint32).reshape(-1)
+        seen["n"] += 1
+        # inside open(): call 1 = public values, 2 = main commit, 3 = permutation commit, then per chip (local sum,
+        # global x, global y)
+        if drop == "perm_commit" and seen["n"] == 3:
+            return
+        if drop == "local_sum" and seen["n"] == 4:
+            return
+        if drop == "global_sum" and seen["n"] == 5:
+            return
+        real_observe(self, v)
+
+    monkeypatch.setattr(Challenger, "observe", observe)
+    sp = prover.open(pk, data, Challenger(ctx, ch.w))
+    monkeypatch.setattr(Challenger, "observe", real_observe)
+    if drop == "local_only":
+        for c in chips:
+            c.local_only = su.AIRS[c.air].local_only
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 1, nq, pw)
+    assert not ok, f"dropping {drop} went unnoticed"
+    data.main_data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_unbalanced_lookups_are_rejected(be):
+    """lookup_pair's sends and receives do not cancel: every per-chip check passes (PCS, constraint identity with the
+    permutation constraints) and the verifier's LAST check -- the shard's local cumulative sum is zero,
+    verifier.rs:236-244 -- rejects the proof, as the reference would."""
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    chips = [su.fibonacci_chip(5), su.lookup_chip(4)]
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 1, nq, pw)
+    assert not ok and why.endswith("local cumulative sum is not zero"), why
+    data.main_data.free()
+    pk.data.free()
 
 
 @pytest.mark.parametrize("be", BACKENDS)
@@ -111,14 +250,10 @@ def test_invalid_trace_is_rejected(be):
     chip = su.fibonacci_chip(5)
     chip.main = chip.main.copy()
     chip.main[7, 1] = (int(chip.main[7, 1]) + 1) % su.P
-    prover = GpuShardProver(ctx, 1, 4, 4)
-    ch = Challenger(ctx)
-    start = ch.w.copy()
-    ordered, root, pd = prover.commit([chip])
-    sp = prover.open(ordered, root, pd, ch)
-    ok, why = su.verify_shard(sp, ordered, start, 1, 4, 4)
-    assert not ok and "constraint identity" in why
-    pd.free()
+    prover, pk, data, sp = _prove(ctx, [chip], 1, 4, 4)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine([chip]), [sp], NUM_PV, 1, 4, 4)
+    assert not ok and "OodEvaluationMismatch" in why
+    data.main_data.free()
 
 
 @pytest.mark.parametrize("be,log_n", [pytest.param("emu", 11, id="emu-2^11"),
@@ -151,15 +286,18 @@ def test_two_contexts_prove_concurrently():
     lib = native.load()
     chips = [su.fibonacci_chip(12), su.wide_chip(10, 64), su.lookup_chip(11)]
     ctxs = [lib.ctx_create(0), lib.ctx_create(0)]
-    provers = [GpuShardProver(c, 1, 20, 8) for c in ctxs]
-    preps = [p.setup(chips) for p in provers]
+    provers = [GpuShardProver(c, 1, 20, 8, num_pv_elts=NUM_PV) for c in ctxs]
+    pks = [p.setup(chips) for p in provers]
+    pvs = su.public_values_for(chips, NUM_PV)
+    from zkmips_b200 import proof as pf
 
     def prove(k):
         ch = Challenger(ctxs[k])
-        ordered, root, pd = provers[k].commit(chips)
-        sp = provers[k].open(ordered, root, pd, ch, *preps[k])
-        pd.free()
-        return sp
+        pks[k].observe_into(ch)
+        data = provers[k].commit(chips, pvs)
+        sp = provers[k].open(pks[k], data, ch)
+        data.main_data.free()
+        return pf.to_bincode(sp)
 
     ref = prove(0)
     out = [[], []]
@@ -175,11 +313,10 @@ def test_two_contexts_prove_concurrently():
         t.join()
     for k in range(2):
         assert len(out[k]) == 4
-        for sp in out[k]:
-            assert (sp.pcs_proof == ref.pcs_proof).all()
-            assert (sp.quotient_commit == ref.quotient_commit).all()
+        for blob in out[k]:
+            assert blob == ref
     for k in range(2):
-        preps[k][1].free()
+        pks[k].data.free()
         ctxs[k].destroy()
 
 
@@ -225,14 +362,11 @@ def test_quotient_degree_four_chunks(be):
         assert (got[c] == exp[c::4]).all()
     main_pd.free()
     nq, pw = (6, 4) if be == "emu" else (42, 16)
-    prover = GpuShardProver(ctx, 2, nq, pw)
-    ch = Challenger(ctx)
-    start = ch.w.copy()
-    ordered, root, pd = prover.commit([chip, su.fibonacci_chip(4)])
-    sp = prover.open(ordered, root, pd, ch)
-    ok, why = su.verify_shard(sp, ordered, start, 2, nq, pw)
+    chips = [chip, su.fibonacci_chip(4)]
+    prover, pk, data, sp = _prove(ctx, chips, 2, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 2, nq, pw)
     assert ok, why
-    pd.free()
+    data.main_data.free()
 
 
 @pytest.mark.parametrize("name,log_blowup,num_queries", [("default", 1, 84), ("compressed", 2, 42), ("ultra_compressed", 3, 28)])
@@ -244,19 +378,21 @@ def test_reference_fri_configs(be, name, log_blowup, num_queries):
     every one of them, and the main commitment equals the oracle's for that blowup."""
     ctx = _backend(be)
     nq, pw = (min(num_queries, 6), 5) if be == "emu" else (num_queries, 16)
-    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), su.lookup_chip(5)]
-    prover = GpuShardProver(ctx, log_blowup, nq, pw)
-    prep_root, prep_pd = prover.setup(chips)
-    ch = Challenger(ctx)
-    ch.observe(prep_root)
-    start = ch.w.copy()
-    ordered, root, pd = prover.commit(chips)
-    assert (root == ob.pcs_commit([c.main for c in ordered], log_blowup).root).all()
-    sp = prover.open(ordered, root, pd, ch, prep_root, prep_pd)
-    ok, why = su.verify_shard(sp, ordered, start, log_blowup, nq, pw)
+    send, recv = su.lookup_side_chips(5)
+    chips = [su.fibonacci_chip(6), su.wide_chip(4, 64), send, recv, su.lookup_chip(3)]
+    prover, pk, data, sp = _prove(ctx, chips, log_blowup, nq, pw)
+    assert (data.main_commit == ob.pcs_commit([c.main for c in data.chips], log_blowup).root).all()
+    vk = su.vk_of(pk)
+    ok, why = su.machine_verify(vk, _machine(chips), [sp], NUM_PV, log_blowup, nq, pw)
+    # lookup_pair is unbalanced on purpose: everything up to the last check (shard sum == 0) must pass
+    assert not ok and why.endswith("local cumulative sum is not zero"), f"{name}: {why}"
+    chips2 = chips[:4]
+    prover, pk2, data2, sp2 = _prove(ctx, chips2, log_blowup, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk2), _machine(chips2), [sp2], NUM_PV, log_blowup, nq, pw)
     assert ok, f"{name}: {why}"
     # a proof made for one configuration must not verify under another blowup
     other = 1 if log_blowup != 1 else 2
-    assert not su.verify_shard(sp, ordered, start, other, nq, pw)[0]
-    pd.free()
-    prep_pd.free()
+    assert not su.machine_verify(su.vk_of(pk2), _machine(chips2), [sp2], NUM_PV, other, nq, pw)[0]
+    data.main_data.free()
+    data2.main_data.free()
+    pk.data.free()

@@ -5,19 +5,7 @@ P = 0x7F000001
 R = 1 << 32
 
 
-def splitmix64(seed, n, offset=0):
-    """Uniform canonical field elements < p from splitmix64: outputs
-    offset .. offset + n - 1 of the stream (counter based, so a large matrix can be produced in chunks)."""
-    out = np.empty(n, dtype=np.uint64)
-    x = np.uint64(seed)
-    with np.errstate(over="ignore"):
-        idx = np.arange(offset + 1, offset + n + 1, dtype=np.uint64)
-        z = x + idx * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    out[:] = z % np.uint64(P)
-    return out.astype(np.uint32)
+from zkmips_b200.synth import config2_trace, splitmix64  # noqa: E402,F401
 
 
 def canon_matrix(h, w, kind="rand", seed=0x5A4B4D49):
@@ -26,23 +14,6 @@ def canon_matrix(h, w, kind="rand", seed=0x5A4B4D49):
     if kind == "index":
         return (np.arange(h * w, dtype=np.uint64) % P).astype(np.uint32).reshape(h, w)
     return splitmix64(seed + 7919 * h + w, h * w).reshape(h, w)
-
-
-def config2_trace(kind, log_rows=20, cols=256):
-    """BASELINE config 2 inputs in Montgomery form, numpy only:
-    'a' = from_canonical((r * W + c) mod p)  (mirrors recursion/circuit/src/fri.rs:832-835),
-    'b' = uniform canonical values from splitmix64(seed = 0x5A4B4D49)."""
-    n = (1 << log_rows) * cols
-    out = np.empty(n, np.uint32)
-    step = 1 << 24
-    for off in range(0, n, step):
-        m = min(step, n - off)
-        if kind == "a":
-            canon = (np.arange(off, off + m, dtype=np.uint64) % P).astype(np.uint32)
-        else:
-            canon = splitmix64(0x5A4B4D49, m, off)
-        out[off:off + m] = monty(canon)
-    return out.reshape(1 << log_rows, cols)
 
 
 def monty(a):

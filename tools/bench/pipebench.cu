@@ -11,7 +11,8 @@ constexpr uint32_t P = 0x7f000001u;
 constexpr int CH = 8;      // independent chains per thread
 constexpr int UNROLL = 16; // ops per chain per loop iteration
 
-enum Op { IADD3, VMNMX, IMAD, WIDE, HI, HIS, LOP, SHF, MIX_ADD_MAD, MIX_MNMX_MAD, MIX_MONT, MIX_ADD_MNMX, MODADD, MONTMUL };
+enum Op { IADD3, VMNMX, IMAD, WIDE, HI, HIS, LOP, SHF, MIX_ADD_MAD, MIX_MNMX_MAD, MIX_MONT, MIX_ADD_MNMX, MODADD, MONTMUL,
+          DFMA, DADD, MIX_DFMA_IMAD, MIX_DFMA_IADD, MIX_DFMA_IMAD_IADD, MIX_DFMA_WIDE, FFMA, MIX_FFMA_IMAD, MIX_FFMA_IMAD_IADD };
 
 template <int OP>
 __device__ __forceinline__ void step(uint32_t& x, uint32_t& y, uint32_t k) {
@@ -45,6 +46,17 @@ __device__ __forceinline__ void step(uint32_t& x, uint32_t& y, uint32_t k) {
     uint32_t t;
     asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(x) : "r"(y), "r"(k));
     asm volatile("add.u32 %0, %1, %2;\n\tmin.u32 %1, %1, %0;" : "=r"(t), "+r"(x) : "r"(k));
+  } else if (OP == DFMA || OP == DADD || OP == MIX_DFMA_IMAD || OP == MIX_DFMA_IADD || OP == MIX_DFMA_IMAD_IADD || OP == MIX_DFMA_WIDE) {
+    // the double lives in the (x, y) register pair of the chain for the pure tests; the mixes keep a separate integer op
+    // on k-derived values so that the FP64 pipe and the integer pipes run side by side
+    double d = __hiloint2double((int)y, (int)x);
+    if (OP == DADD) asm volatile("add.f64 %0, %0, %1;" : "+d"(d) : "d"(1.5));
+    else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d) : "d"(1.0000001), "d"(0.5));
+    x = (uint32_t)__double2loint(d); y = (uint32_t)__double2hiint(d);
+  } else if (OP == FFMA || OP == MIX_FFMA_IMAD || OP == MIX_FFMA_IMAD_IADD) {
+    float f = __uint_as_float(x);
+    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0000001f), "f"(0.5f));
+    x = __float_as_uint(f);
   } else if (OP == MODADD) {  // what the compiler makes of kb::add (it may pick IMAD.IADD)
     uint32_t s = x + y;
     x = min(s, s - P);
@@ -61,27 +73,44 @@ __device__ __forceinline__ void step(uint32_t& x, uint32_t& y, uint32_t k) {
     }
   }
 }
+// integer companion of the FP64 / FP32 mixes, on its own registers (z, u)
+template <int OP>
+__device__ __forceinline__ void step2(uint32_t& z, uint32_t& u, uint32_t k) {
+  if (OP == MIX_DFMA_IMAD || OP == MIX_DFMA_IMAD_IADD || OP == MIX_FFMA_IMAD || OP == MIX_FFMA_IMAD_IADD)
+    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(z) : "r"(k), "r"(k));
+  if (OP == MIX_DFMA_IADD || OP == MIX_DFMA_IMAD_IADD || OP == MIX_FFMA_IMAD_IADD)
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(u) : "r"(k), "r"(k));
+  if (OP == MIX_DFMA_WIDE) {
+    uint64_t w;
+    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(z), "r"(u));
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(z), "=r"(u) : "l"(w));
+  }
+}
 template <int OP> constexpr int sass_per_step() {
+  if (OP == MIX_DFMA_IMAD || OP == MIX_DFMA_IADD || OP == MIX_DFMA_WIDE || OP == MIX_FFMA_IMAD) return 2;
+  if (OP == MIX_DFMA_IMAD_IADD || OP == MIX_FFMA_IMAD_IADD) return 3;
   return OP == MIX_ADD_MAD || OP == MIX_MNMX_MAD || OP == MIX_ADD_MNMX || OP == MODADD ? 2 : OP == MONTMUL ? 5 : OP == MIX_MONT ? 11 : 1;
 }
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cyc, int iters, const uint32_t* kp) {
   const uint32_t k = kp[0];  // in a register, not a constant-bank operand
-  uint32_t x[CH], y[CH];
+  uint32_t x[CH], y[CH], z[CH], u[CH];
 #pragma unroll
-  for (int c = 0; c < CH; c++) { x[c] = threadIdx.x * 2654435761u + c * 40503u + 1; y[c] = (blockIdx.x + c) * 977u + 3; if (OP == MIX_MONT || OP >= MODADD) { x[c] %= P; y[c] %= P; } }
+  for (int c = 0; c < CH; c++) { z[c] = threadIdx.x + 77u * c; u[c] = blockIdx.x + 3u * c; }
+#pragma unroll
+  for (int c = 0; c < CH; c++) { x[c] = threadIdx.x * 2654435761u + c * 40503u + 1; y[c] = (blockIdx.x + c) * 977u + 3; if (OP == MIX_MONT || OP == MODADD || OP == MONTMUL) { x[c] %= P; y[c] %= P; } if (OP >= DFMA && OP <= MIX_DFMA_WIDE) { y[c] = 0x40000000u | (y[c] & 0xfffffu); } }
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++)
+    for (int un = 0; un < UNROLL; un++)
 #pragma unroll
-      for (int c = 0; c < CH; c++) step<OP>(x[c], y[c], k);
+      for (int c = 0; c < CH; c++) { step<OP>(x[c], y[c], k); step2<OP>(z[c], u[c], k); }
   }
   long long t1 = clock64();
   uint32_t acc = 0;
 #pragma unroll
-  for (int c = 0; c < CH; c++) acc ^= x[c] + y[c];
+  for (int c = 0; c < CH; c++) acc ^= x[c] + y[c] + z[c] + u[c];
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -124,5 +153,14 @@ int main() {
   run<MODADD>("kb::add as compiled", d, c, sms);
   run<MONTMUL>("kb::mul as compiled", d, c, sms);
   run<MIX_MONT>("kb::mul + 3 kb::add", d, c, sms);
+  run<DFMA>("DFMA", d, c, sms);
+  run<DADD>("DADD", d, c, sms);
+  run<MIX_DFMA_IMAD>("DFMA + IMAD", d, c, sms);
+  run<MIX_DFMA_IADD>("DFMA + IADD3", d, c, sms);
+  run<MIX_DFMA_IMAD_IADD>("DFMA + IMAD + IADD3", d, c, sms);
+  run<MIX_DFMA_WIDE>("DFMA + IMAD.WIDE", d, c, sms);
+  run<FFMA>("FFMA", d, c, sms);
+  run<MIX_FFMA_IMAD>("FFMA + IMAD", d, c, sms);
+  run<MIX_FFMA_IMAD_IADD>("FFMA + IMAD + IADD3", d, c, sms);
   return 0;
 }

@@ -61,8 +61,13 @@ class Expr:
 class Air:
     """One chip's constraint program."""
 
-    def __init__(self, name, main_width, prep_width=0, perm_width=0, num_public_values=0, num_challenges=2):
+    def __init__(self, name, main_width, prep_width=0, perm_width=0, num_public_values=0, num_challenges=2,
+                 commit_scope="local", local_only=False):
         self.name = name
+        # MachineAir::commit_scope (LookupScope::Local / Global, crates/stark/src/air/machine.rs) and
+        # MachineAir::local_only (no constraint reads the next row: opened at zeta only, prover.rs:503-531)
+        assert commit_scope in ("local", "global")
+        self.commit_scope, self.local_only = commit_scope, bool(local_only)
         self.main_width, self.prep_width, self.perm_width = main_width, prep_width, perm_width
         self.num_public_values, self.num_challenges = num_public_values, num_challenges
         self.nodes = []   # tuples
@@ -162,13 +167,13 @@ class Air:
             "perm_width": self.perm_width, "num_public_values": self.num_public_values,
             "num_challenges": self.num_challenges, "nodes": [list(n) for n in self.nodes],
             "constraints": self.constraints, "sends": self.sends, "receives": self.receives,
-            "batch_size": self.batch_size})
+            "batch_size": self.batch_size, "commit_scope": self.commit_scope, "local_only": self.local_only})
 
     @classmethod
     def from_json(cls, text):
         d = json.loads(text)
         a = cls(d["name"], d["main_width"], d["prep_width"], d["perm_width"], d["num_public_values"],
-                d.get("num_challenges", 2))
+                d.get("num_challenges", 2), d.get("commit_scope", "local"), d.get("local_only", False))
         for n in d["nodes"]:
             n = tuple(n)
             if n[0] in ("add", "sub", "mul"):
@@ -185,8 +190,23 @@ class Air:
             setattr(a, key, [{"kind": l["kind"], "values": [fix(v) for v in l["values"]], "mult": fix(l["mult"])}
                              for l in d.get(key, [])])
         a.batch_size = d.get("batch_size", 2)
-        a.lookups_finalized = bool(a.sends or a.receives)
+        a.lookups_finalized = True
         return a
+
+    def uses_next_row(self):
+        """does any constraint read the next row of the preprocessed / main trace?  (a `local_only` chip must not)"""
+        need, stack = set(), list(self.constraints)
+        while stack:
+            n = stack.pop()
+            if n in need:
+                continue
+            need.add(n)
+            node = self.nodes[n]
+            if node[0] in ("add", "sub", "mul"):
+                stack += [node[1], node[2]]
+            elif node[0] == "neg":
+                stack.append(node[1])
+        return any(self.nodes[n][0] in ("main", "prep") and self.nodes[n][1] == 1 for n in need)
 
     @property
     def num_constraints(self):
@@ -319,15 +339,30 @@ class AirBuilder:
 
     def eval_permutation_constraints(self, batch_size=2):
         """Transliteration of eval_permutation_constraints (crates/stark/src/permutation.rs:205-347), appended
-        after the chip's own constraints exactly as Chip::eval does (crates/stark/src/chip.rs:259-270).  Local
-        scope only (the global-scope rows tie main columns to the septic digest and need no permutation trace)."""
+        after the chip's own constraints exactly as Chip::eval does (crates/stark/src/chip.rs:259-270) -- for EVERY
+        chip: without local lookups and with Local scope it adds nothing (count_permutation_constraints,
+        permutation.rs:355-388)."""
         air = self.air
         assert not air.lookups_finalized
         air.lookups_finalized = True
         air.batch_size = batch_size
         lookups = [(l, True) for l in air.sends] + [(l, False) for l in air.receives]
-        if not lookups:
-            return
+        if lookups:
+            self._eval_local_lookups(lookups, batch_size)
+        # Global scope (permutation.rs:333-346): the last row's final 14 main columns are the chip's contribution to
+        # the shard's global cumulative sum (a SepticDigest: x[7], y[7]); 14 constraints, x_i and y_i interleaved
+        if air.commit_scope == "global":
+            main_local = self.main().local()
+            gcs = self.global_cumulative_sum()
+            w = air.main_width
+            for i in range(7):
+                self.when_last_row().assert_eq(main_local[w - 14 + i], gcs[i])
+                self.when_last_row().assert_eq(main_local[w - 7 + i], gcs[7 + i])
+        if air.local_only:
+            assert not air.uses_next_row(), f"{air.name} is declared local_only but reads the next row"
+
+    def _eval_local_lookups(self, lookups, batch_size):
+        air = self.air
         air.perm_width = air.permutation_width
         perm, permn = self.permutation().local(), self.permutation().next()
         alpha, beta = self.permutation_randomness()[:2]
