@@ -145,50 +145,49 @@ class ClockSampler:
 
 
 def synth_trace(log_rows, cols, seed):
-    """config 2(b): uniform canonical values from splitmix64, converted to Montgomery form (numpy only)."""
-    import numpy as np
-    from tests import util
-    n = (1 << log_rows) * cols
-    out = np.empty(n, np.uint32)
-    step = 1 << 24
-    for off in range(0, n, step):
-        m = min(step, n - off)
-        out[off:off + m] = util.monty(util.splitmix64(0x5A4B4D49 + seed + 1000003 * (off // step), m))
-    return out.reshape(1 << log_rows, cols)
+    """config 2(b): uniform canonical values from splitmix64(0x5A4B4D49 + seed), Montgomery form (numpy only)."""
+    from zkmips_b200 import synth
+    return synth.config2_trace("b", log_rows, cols, seed=0x5A4B4D49 + seed)
 
 
-def cpu_commit_sample(target_s=15.0, max_log=LOG_ROWS):
-    """Times the oracle's Pcs::commit on a bounded sample of the workload; returns (Gelem/s, cores, sample)."""
+def cpu_commit_sample(trace, target_s=30.0):
+    """Times the oracle's Pcs::commit on the bench trace itself (all host cores) when a probe predicts it fits in
+    target_s, else on a row prefix of it.  Returns (Gelem/s, cores, sample text, seconds, log rows, oracle root)."""
     from oracle import binding as ob
-    cores = ob.lib().ork_num_threads()
-    probe_log = 14
-    m = synth_trace(probe_log, COLS, 1)
-    ob.pcs_commit([m], LOG_BLOWUP)  # warm up threads / page in
+    cores = ob.use_all_cores()
+    full_log = int(trace.shape[0]).bit_length() - 1
+    cols = trace.shape[1]
+    probe_log = min(14, full_log)
+    ob.pcs_commit([trace[:1 << probe_log]], LOG_BLOWUP)  # warm up threads / page in
     t = time.perf_counter()
-    ob.pcs_commit([m], LOG_BLOWUP)
+    ob.pcs_commit([trace[:1 << probe_log]], LOG_BLOWUP)
     dt = time.perf_counter() - t
     log = probe_log
-    while log < max_log and dt * (1 << (log + 1 - probe_log)) * 1.1 <= target_s:
+    while log < full_log and dt * (1 << (log + 1 - probe_log)) * 1.1 <= target_s:
         log += 1
-    m = synth_trace(log, COLS, 2)
+    m = trace[:1 << log]
     t = time.perf_counter()
     tree = ob.pcs_commit([m], LOG_BLOWUP)
     dt = time.perf_counter() - t
+    root = tree.root.copy()
     del tree
-    return (1 << log) * COLS / dt / 1e9, cores, f"one commit of 2^{log} x {COLS} (1/{1 << (LOG_ROWS - log)} of the workload rows), {dt:.2f} s", dt, log
+    return ((1 << log) * cols / dt / 1e9, cores,
+            f"one commit of 2^{log} x {cols} (1/{1 << (full_log - log)} of the workload rows), {dt:.2f} s", dt, log, root)
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm on the host CPU (oracle port)."""
+    """`--impl reference`: the reference algorithm on the host CPU (oracle port) with every
+    core this process may use -- torch.distributed.run exports OMP_NUM_THREADS=1, which the oracle overrides."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import binding as ob
-    cores = ob.lib().ork_num_threads()
+    cores = ob.use_all_cores()
     # bounded sample per step so that steps+warmup end within a few minutes
     budget = 150.0 / max(1, args.steps + args.warmup)
-    _, _, _, dt_probe, log = cpu_commit_sample(target_s=min(20.0, budget))
-    m = synth_trace(log, COLS, 3)
+    trace = synth_trace(LOG_ROWS, COLS, 0)
+    _, _, _, _, log, _ = cpu_commit_sample(trace, target_s=min(20.0, budget))
+    m = trace[:1 << log]
     for _ in range(args.warmup):
         ob.pcs_commit([m], LOG_BLOWUP)
     t = time.perf_counter()
@@ -259,36 +258,72 @@ def exec_shard_leg(ctx, torch, args):
             "root": [int(x) for x in root], "timing": "host wall clock around zk_commit (pinned host traces in, root out)"}
 
 
-def shard_leg(ctx, torch, dist, world, rank, args):
-    """Second BASELINE metric: shard prove ms = MachineProver::commit + open (quotient, quotient commit, Pcs::open
-    with 84 queries / 16 PoW bits) for one synthetic shard per GPU, traces in host memory, proof back on the host.
-    Chips (default): wide_bitwise_1024 at 2^16 rows, wide_bitwise_64 at 2^18, Fibonacci at 2^20; --shard-config keccak:
-    the BASELINE config-3 shape, wide_bitwise_4096 at 2^16 rows (6144 constraints)."""
+NUM_PV = 8  # StarkMachine::num_pv_elts of the synthetic machine
+
+
+def shard_chips(config, rank=0, scale=0):
+    """The synthetic shard of metric 2 (heights scaled down by 2^scale for the CPU leg's bounded sample).
+    mixed : wide_bitwise_1024 2^16, wide_bitwise_64 2^18, Fibonacci 2^20 and a balanced LogUp pair at 2^18 (88 M cells:
+            between a maximal log-17 and log-18 execution shard, SURVEY A.11);
+    keccak: BASELINE config 3, wide_bitwise_4096 at 2^16 rows (6144 degree-3 constraints) + Fibonacci 2^16;
+    large : wide_bitwise_1024 2^19, wide_bitwise_64 2^21, Fibonacci 2^21, LogUp pair 2^20 (6.8e8 cells: a maximal
+            log-21 execution shard's size)."""
+    from zkmips_b200 import synth
+    d = scale
+    if config == "keccak":
+        return [synth.wide_chip(16 - d, 4096, seed=11 + rank), synth.fibonacci_chip(16 - d, 1 + rank, 1)]
+    if config == "large":
+        send, recv = synth.lookup_side_chips(20 - d, seed=9 + rank)
+        return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
+                synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
+    send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
+    return [synth.wide_chip(16 - d, 1024, seed=11 + rank), synth.wide_chip(18 - d, 64, seed=12 + rank),
+            synth.fibonacci_chip(20 - d, 1 + rank, 1), send, recv]
+
+
+def _pin(torch, chips):
     import numpy as np
-
-    from tests import shard_util as su
-    from zkmips_b200 import Challenger
-    from zkmips_b200.prover import GpuShardProver
-
-    if args.shard_config == "keccak":
-        chips = [su.wide_chip(16, 4096, seed=11 + rank), su.fibonacci_chip(16, 1 + rank, 1)]
-    else:
-        chips = [su.wide_chip(16, 1024, seed=11 + rank), su.wide_chip(18, 64, seed=12 + rank), su.fibonacci_chip(20, 1 + rank, 1)]
     for c in chips:  # the host-side trace buffers are pinned, as the bench contract's e2e path allows
         c.main = torch.from_numpy(c.main.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    return chips
+
+
+class ShardWorker:
+    """One in-flight shard slot of a GPU: its own context (stream, pool, slab buffers) and prover; the proving key is
+    committed ONCE per context (pk_to_device, prover.rs:63) and every shard gets a clone of the machine challenger."""
+
+    def __init__(self, ctx, chips):
+        from zkmips_b200 import Challenger, synth
+        from zkmips_b200.prover import GpuShardProver
+        self.ctx = ctx
+        self.prover = GpuShardProver(ctx, 1, 84, 16, num_pv_elts=NUM_PV)
+        self.pk = self.prover.setup(chips)
+        ch = Challenger(ctx)
+        self.pk.observe_into(ch)
+        self.start = ch.w.copy()
+        self.pvs = synth.public_values_for(chips, NUM_PV)
+        self.Challenger = Challenger
+
+    def prove(self, chips):
+        data = self.prover.commit(chips, self.pvs)
+        sp = self.prover.open(self.pk, data, self.Challenger(self.ctx, self.start))
+        data.main_data.free()
+        return sp
+
+
+def shard_leg(ctx, torch, dist, world, rank, args):
+    """Second BASELINE metric: shard prove ms = MachineProver::commit + open (permutation traces + commit, quotient,
+    quotient commit, Pcs::open with 84 queries / 16 PoW bits, repackaging into a ShardProof) for one synthetic shard
+    per GPU, traces in pinned host memory, proof back on the host.  Then the multi-shard workload of BASELINE configs
+    4/5: S shards from a host queue, two in flight per GPU, shard i -> rank i mod N."""
+    import queue
+    import threading
+
+    chips = _pin(torch, shard_chips(args.shard_config, rank))
     cells = sum(c.main.size for c in chips)
-    prover = GpuShardProver(ctx, 1, 84, 16)
-    start = Challenger(ctx).w.copy()
-
-    def one():
-        ch = Challenger(ctx, start)
-        ordered, root, pd = prover.commit(chips)
-        sp = prover.open(ordered, root, pd, ch)
-        pd.free()
-        return ordered, sp
-
-    ordered, sp = one()  # warm-up (also pages the generated quotient kernels in)
-    prover.phase_ms = {}  # host phase clocks of the timed steps only
+    w1 = ShardWorker(ctx, chips)
+    sp = w1.prove(chips)  # warm-up (also pages the generated quotient kernels in)
+    w1.prover.phase_ms = {}  # host phase clocks of the timed steps only
     ctx.prof_reset()
     ctx.prof_enable(True)
     if world > 1:
@@ -296,11 +331,11 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     torch.cuda.synchronize()
     t = time.perf_counter()
     for _ in range(args.shard_steps):
-        ordered, sp = one()
+        sp = w1.prove(chips)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t) / args.shard_steps
     ctx.prof_enable(False)
-    phases = {k: round(v / args.shard_steps, 3) for k, v in prover.phase_ms.items()}
+    phases = {k: round(v / args.shard_steps, 3) for k, v in w1.prover.phase_ms.items()}
     stage = {}
     for name, ms, _ in ctx.prof_records():
         stage[name] = stage.get(name, 0.0) + ms / args.shard_steps
@@ -308,50 +343,107 @@ def shard_leg(ctx, torch, dist, world, rank, args):
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    # throughput with two shards in flight per GPU (the reference keeps shard_batch_size shards in flight,
-    # crates/core/machine/src/utils/prove.rs:487-521): a second context on its own stream, driven by a second
-    # host thread, fills the latency-bound phases (FRI commit chain, top of the Merkle trees) of the first
-    import threading
+
+    # ---- multi-shard program (BASELINE configs 4/5; crates/core/machine/src/utils/prove.rs:480-526): S shards in a host
+    # queue, shard i on rank i mod N, TWO shards in flight per GPU (the reference keeps shard_batch_size shards in
+    # flight, prove.rs:487-521): a second context on its own stream, driven by a second host thread, uploads and
+    # commits shard i+1 while shard i is in its latency-bound open phase.  Strong scaling: S is fixed as N grows.
     ctx2 = ctx.lib.ctx_create(torch.cuda.current_device())
-    prover2 = GpuShardProver(ctx2, 1, 84, 16)
+    w2 = ShardWorker(ctx2, chips)
+    w2.prove(chips)  # warm-up of the second context
+    S = args.multi_shards
+    mine = list(range(rank, S, world))
+    jobs = queue.Queue()
+    for i in mine:
+        jobs.put(i)
+    proofs = {}
 
-    def worker(pv, cx, n):
-        for _ in range(n):
-            chx = Challenger(cx, start)
-            o, r, p = pv.commit(chips)
-            pv.open(o, r, p, chx)
-            p.free()
+    def worker(w):
+        while True:
+            try:
+                i = jobs.get_nowait()
+            except queue.Empty:
+                return
+            proofs[i] = w.prove(chips)
 
-    worker(prover2, ctx2, 1)  # warm-up of the second context
-    n_each = max(2, args.shard_steps)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t = time.perf_counter()
-    th = [threading.Thread(target=worker, args=(prover, ctx, n_each)), threading.Thread(target=worker, args=(prover2, ctx2, n_each))]
+    th = [threading.Thread(target=worker, args=(w,)) for w in (w1, w2)]
     for x in th:
         x.start()
     for x in th:
         x.join()
     torch.cuda.synchronize()
-    dt2 = (time.perf_counter() - t) / (2 * n_each)
+    dtm = time.perf_counter() - t
     if world > 1:
-        tt = torch.tensor([dt2], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([dtm], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt2 = float(tt.item())
+        dtm = float(tt.item())
+    from zkmips_b200 import proof as pf
+    blob = pf.to_bincode(sp)
+    assert all(pf.to_bincode(p) == blob for p in proofs.values()), "shards of the queue differ from the serial proof"
+    w2.pk.data and w2.pk.data.free()
     ctx2.destroy()
-    res = {"config": args.shard_config, "ms_per_shard": dt * 1e3, "shards_per_s": world / dt, "shards_per_s_two_in_flight": world / dt2,
+    res = {"config": args.shard_config, "ms_per_shard": dt * 1e3, "shards_per_s": world / dt,
            "trace_cells_per_shard": int(cells),
-           "chips": [f"{c.name}: 2^{c.log_degree} x {c.main.shape[1]}" for c in ordered],
-           "params": "log_blowup 1, 84 queries, 16 PoW bits", "timing": "host wall clock around commit+open, max over ranks",
-           "proof_words": int(sp.pcs_proof.size), "host_phase_ms": phases,
-           "device_stage_ms": {k: round(v, 3) for k, v in stage.items()}}
-    if rank == 0:
-        ok, why = su.verify_shard(sp, ordered, start, 1, 84, 16)
-        res["verified_by_oracle_verifier"] = bool(ok)
-        if not ok:
-            res["verify_error"] = why
+           "chips": [f"{c.name}: 2^{c.log_degree} x {c.main.shape[1]}" for c in w1.prover.order(chips)],
+           "params": "log_blowup 1, 84 queries, 16 PoW bits; reference transcript (prover.rs:298-653)",
+           "timing": "host wall clock around commit+open, max over ranks",
+           "proof_bytes_bincode": len(blob), "host_phase_ms": phases,
+           "device_stage_ms": {k: round(v, 3) for k, v in stage.items()},
+           "multi_shard": {"shards": S, "shards_in_flight_per_gpu": 2, "placement": "shard i -> rank i mod N",
+                           "seconds": dtm, "shards_per_s": S / dtm, "cells_per_s": S * cells / dtm, "scaling": "strong",
+                           "h2d_bytes_per_shard": int(4 * cells)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res["cpu_baseline"] = shard_cpu_leg(args, ctx, torch, cells)
     return res
+
+
+def shard_cpu_leg(args, ctx, torch, full_cells):
+    """CPU leg of metric 2: the oracle's shard prover (oracle/shard_prover.py: C oracle for the commits and Pcs::open on
+    every host core, numpy for LogUp and the quotient) on the same shard scaled down by 2^k rows so that it ends in
+    ~10-30 s.  The GPU proves the SAME sample and the two proofs are compared byte for byte."""
+    from oracle import binding as ob
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    from zkmips_b200.air import library
+    os.sched_setaffinity(0, ALL_CPUS)
+    cores = ob.use_all_cores()
+    airs = {a.name: a for a in library.all_airs()}
+    scale = 4
+    while True:
+        chips = shard_chips(args.shard_config, 0, scale)
+        op = osp.OracleShardProver(airs, 1, 84, 16, num_pv_elts=NUM_PV)
+        from zkmips_b200 import synth
+        pvs = synth.public_values_for(chips, NUM_PV)
+        opk = op.setup(chips)
+        och = bf.new_challenger()
+        opk.observe_into(och)
+        t = time.perf_counter()
+        osp_proof = op.prove(opk, chips, och, pvs)
+        dt = time.perf_counter() - t
+        if dt > 6.0 or scale == 0:
+            break
+        scale -= 1 if dt > 2.0 else 2
+        scale = max(scale, 0)
+    cells = sum(c.main.size for c in chips)
+    w = ShardWorker(ctx, chips)
+    t = time.perf_counter()
+    sp = w.prove(chips)
+    gpu_dt = time.perf_counter() - t
+    same = pf.to_bincode(sp) == pf.to_bincode(osp_proof)
+    return {"value": cells / dt / 1e6, "unit": "Mcell/s", "cores": cores, "kind": "port",
+            "sample": f"one shard of the same chips with heights / 2^{scale} ({cells} cells), {dt:.2f} s; "
+                      f"phases {dict((k, round(v, 2)) for k, v in op.phase_s.items())}",
+            "seconds": dt, "cells": int(cells), "gpu_ms_same_sample": gpu_dt * 1e3,
+            "proof_matches_oracle": bool(same),
+            "extrapolated_ms_per_full_shard": dt * 1e3 * full_cells / cells}
+
+
+ALL_CPUS = os.sched_getaffinity(0)
 
 
 def main():
@@ -366,9 +458,11 @@ def main():
     ap.add_argument("--no-shard", action="store_true", help="skip the shard-prove leg (commit + quotient + open)")
     ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
-    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak"],
-                    help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 (86 M cells); keccak: BASELINE config 3, one "
-                         "2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells)")
+    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large"],
+                    help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 + LogUp pair 2^18 (88 M cells); keccak: BASELINE "
+                         "config 3, one 2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells); "
+                         "large: 6.8e8 cells, the size of a maximal log-21 execution shard")
+    ap.add_argument("--multi-shards", type=int, default=16, help="shards of the multi-shard leg (fixed total, all GPUs)")
     args = ap.parse_args()
     # Exactly ONE line on stdout: native libraries print there too (NCCL's version banner goes through printf), so
     # file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
@@ -393,7 +487,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libzkgpu has no CPU fallback")
     torch.cuda.set_device(local)
     from zkmips_b200.dispatch import bind_to_gpu_numa
-    all_cpus = os.sched_getaffinity(0)
     cpus = bind_to_gpu_numa(local)  # before the pinned trace buffers are allocated (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -559,9 +652,17 @@ def main():
     if not args.no_shard and world == 1:
         out["exec_shard_commit"] = exec_shard_leg(ctx, torch, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
-        v, cores, sample, _, _ = cpu_commit_sample()
+        os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host core again
+        v, cores, sample, _, slog, oroot = cpu_commit_sample(host_np)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        # the oracle committed (a row prefix of) the bench trace: the GPU root of the same rows must equal it
+        if slog == log_rows:
+            groot = root_dev
+        else:
+            groot, gpd = ctx.commit([host_np[:1 << slog]], [one], LOG_BLOWUP)
+            gpd.free()
+        out["root_matches_oracle"] = bool((groot == oroot).all())
+        out["root_checked_on"] = sample
     if rank == 0:
         emit_json(out)
     ctx.destroy()

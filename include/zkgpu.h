@@ -17,6 +17,8 @@
  *     library (or handed in by the caller for the `_dev` variants);
  *   - a zk_ctx is bound to one GPU and one CUDA stream; calls on the same ctx are serialised by an
  *     internal mutex, so rayon workers may share it (crates/core/machine/src/utils/prove.rs:487-497).
+ *   - zk_pdata handles point into their context: zk_ctx_destroy with handles still alive is DEFERRED until the
+ *     last of them is freed (bindings drop handles from destructors in any order).
  *   - there is NO CPU fallback: without a CUDA device zk_ctx_create fails with ZK_ERR_CUDA.
  */
 #ifndef ZKGPU_H
@@ -118,6 +120,15 @@ zk_dptr zk_pdata_trace(const zk_pdata* pd, uint32_t i);
 /* Mmcs::get_matrices / Serialize support: copy an LDE matrix or a digest layer (0 = leaves) to the host. */
 int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* out_host);
 int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out_host);
+/* Deserialize support (`PcsProverData<SC>: Serialize + DeserializeOwned`, crates/stark/src/prover.rs:221,
+ * crates/stark/src/machine.rs:56-57: the proving key holds the preprocessed round's ProverData and is serialised):
+ * the inverse of zk_pdata_copy_lde / zk_pdata_copy_layer.  heights are COMMITTED heights; layers_host[l] is digest layer
+ * l (0 = leaves), n_layers = log2(max height) + 1.  traces_host (nullable, entries nullable) restores the retained
+ * input traces of zk_ctx_keep_traces (height >> log_blowup rows each; `StarkProvingKey::traces`).  Nothing is
+ * re-hashed: like serde, it restores exactly what was exported. */
+int32_t zk_pdata_import(zk_ctx* ctx, uint32_t n_mats, const uint32_t* const* ldes_host, const uint64_t* heights,
+                        const uint32_t* widths, const uint32_t* const* layers_host, uint32_t n_layers,
+                        const uint32_t* const* traces_host, uint32_t log_blowup, zk_pdata** out);
 /* Mmcs::open_batch for n_idx indices at once (crates/recursion/circuit/src/fri.rs:383-387):
  * opened: for each index, the rows of all matrices back to back in matrix order (sum of widths words);
  * proofs: for each index, log_max_height siblings of 8 words, bottom-up. */

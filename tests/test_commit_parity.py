@@ -303,3 +303,38 @@ def test_lde_two_pass_k10_emu():
     m = _mont(1 << 20, 2, seed=77)
     shift = ob.lib().ork_to_monty(3)
     assert (ctx.coset_lde(m, 1, shift) == ob.coset_lde(m, 1, shift)).all()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_prover_data_export_import_round_trip(be):
+    """`PcsProverData: Serialize + DeserializeOwned` (crates/stark/src/prover.rs:221, machine.rs:56-57): the host image
+    of a mixed-height commitment (LDE matrices + digest layers) is imported into a fresh handle, which must answer
+    open_batch exactly like the original (rows and Merkle paths) and carry the same root; with the retained traces
+    restored, the handle also serves the LogUp stage (`pk.traces`).  The context is destroyed while the imported handle
+    is still alive: destruction is deferred to the last zk_pdata_free."""
+    from zkmips_b200 import native
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    ctx = lib.ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+    mats = [_mont(64, 12, seed=301), _mont(16, 5, seed=302), _mont(64, 0, seed=303), _mont(4, 9, seed=304)]
+    root, pd = ctx.commit(mats, [one] * len(mats), 1)
+    image = pd.export()
+    idx = [0, 1, 77, 127]
+    opened, proofs = pd.open_batch(idx)
+    pd.free()
+    pd2 = ctx.import_pdata(image, traces=mats, log_blowup=1)
+    assert (pd2.root == root).all()
+    assert pd2.num_matrices() == 4 and pd2.log_max_height() == 7
+    o2, p2 = pd2.open_batch(idx)
+    assert (o2 == opened).all() and (p2 == proofs).all()
+    for i, m in enumerate(mats):
+        assert (pd2.lde(i) == image["ldes"][i]).all()
+        if m.size:
+            assert (ctx.download(pd2.trace_ptr(i), m.shape) == m).all()
+    tree = ob.pcs_commit(mats, 1, [one] * len(mats))
+    dims = [tree.dims(i) for i in range(4)]
+    rows = [o2[2, :12], o2[2, 12:17], o2[2, 17:17], o2[2, 17:26]]
+    assert ob.mmcs_verify(root, dims, 77, rows, p2[2])
+    ctx.destroy()      # deferred: pd2 is still alive
+    assert pd2.num_matrices() == 4
+    pd2.free()         # the last handle tears the context down

@@ -93,9 +93,10 @@ extern "C" int32_t zk_quotient(zk_ctx* c, int32_t air_id, const zk_pdata* prep, 
   if (global_cumsum) memcpy(host.data() + 8 + 4 * n_chal, global_cumsum, 56);
   if (n_public_values) memcpy(host.data() + 22 + 4 * n_chal, public_values, 4ull * n_public_values);
   uint32_t *d_in = nullptr, *d_ap = nullptr, *d_out = nullptr;
-  if ((rc = dev_alloc(c, host.size() * 4, (void**)&d_in))) return rc;
-  if ((rc = dev_alloc(c, std::max(e.n_constraints, 1u) * 16ull, (void**)&d_ap))) return rc;
-  if ((rc = dev_alloc(c, qsize * 16, (void**)&d_out))) return rc;
+  DevScope ds(c);  // frees on every return path; the output is released to the caller at the end
+  if ((rc = ds.alloc(&d_in, host.size() * 4))) return rc;
+  if ((rc = ds.alloc(&d_ap, std::max(e.n_constraints, 1u) * 16ull))) return rc;
+  if ((rc = ds.alloc(&d_out, qsize * 16))) return rc;
   CK(cudaMemcpyAsync(d_in, host.data(), host.size() * 4, cudaMemcpyHostToDevice, c->stream));
   if (e.n_constraints) {
     ZK_LAUNCH(quot::alpha_pows_rev_kernel, (e.n_constraints + 127) / 128, 128, 0, c->stream, d_in, e.n_constraints, d_ap);
@@ -114,8 +115,7 @@ extern "C" int32_t zk_quotient(zk_ctx* c, int32_t air_id, const zk_pdata* prep, 
     CK(cudaGetLastError());
     c->launches++;
   }
-  if ((rc = dev_free(c, d_in))) return rc;
-  if ((rc = dev_free(c, d_ap))) return rc;
+  ds.release(d_out);
   *out_chunks = (zk_dptr)d_out;
   return ZK_OK;
 }
@@ -143,10 +143,11 @@ extern "C" int32_t zk_permutation_trace(zk_ctx* c, int32_t air_id, zk_dptr prep_
   uint32_t nblocks = (uint32_t)((height + logup::SCAN_T - 1) / logup::SCAN_T);
   uint32_t *d_chal = nullptr, *d_perm = nullptr, *d_rowsum = nullptr, *d_bsum = nullptr;
   int32_t rc;
-  if ((rc = dev_alloc(c, 48, (void**)&d_chal))) return rc;  // alpha, beta, [last]
-  if ((rc = dev_alloc(c, height * A.wq * 4ull, (void**)&d_perm))) return rc;
-  if ((rc = dev_alloc(c, height * 16, (void**)&d_rowsum))) return rc;
-  if ((rc = dev_alloc(c, nblocks * 16ull, (void**)&d_bsum))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d_chal, 48))) return rc;  // alpha, beta, [last]
+  if ((rc = ds.alloc(&d_perm, height * A.wq * 4ull))) return rc;
+  if ((rc = ds.alloc(&d_rowsum, height * 16))) return rc;
+  if ((rc = ds.alloc(&d_bsum, nblocks * 16ull))) return rc;
   CK(cudaMemcpyAsync(d_chal, perm_challenges, 32, cudaMemcpyHostToDevice, c->stream));
   A.chal = d_chal;
   A.perm = d_perm;
@@ -161,9 +162,7 @@ extern "C" int32_t zk_permutation_trace(zk_ctx* c, int32_t air_id, zk_dptr prep_
   c->launches += 4;
   CK(cudaMemcpyAsync(local_cumsum, d_chal + 8, 16, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d_chal);
-  dev_free(c, d_rowsum);
-  dev_free(c, d_bsum);
+  ds.release(d_perm);
   *out_trace = (zk_dptr)d_perm;
   return ZK_OK;
 }

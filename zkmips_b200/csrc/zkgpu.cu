@@ -67,6 +67,7 @@ __global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+extern "C" void zk_ctx_destroy(zk_ctx* c);
 static int32_t ctx_init(zk_ctx* c) {
   CK(cudaSetDevice(c->device));
   cudaDeviceProp prop;
@@ -127,7 +128,9 @@ extern "C" int32_t zk_ctx_create_on_stream(int32_t device, void* stream, zk_ctx*
   c->stream = (cudaStream_t)stream;
   int32_t rc = ctx_init(c);
   if (rc != ZK_OK) {
-    delete c;
+    std::string why = g_last_error;
+    zk_ctx_destroy(c);  // releases whatever ctx_init got as far as creating
+    g_last_error = why;
     return rc;
   }
   *out = c;
@@ -135,15 +138,28 @@ extern "C" int32_t zk_ctx_create_on_stream(int32_t device, void* stream, zk_ctx*
 }
 extern "C" int32_t zk_ctx_create(int32_t device, zk_ctx** out) { return zk_ctx_create_on_stream(device, nullptr, out); }
 
+static void ctx_teardown(zk_ctx* c);
 extern "C" void zk_ctx_destroy(zk_ctx* c) {
   if (!c) return;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (c->live_pdata) {  // deferred: the last zk_pdata_free finishes the job
+      c->destroy_requested = true;
+      return;
+    }
+  }
+  ctx_teardown(c);
+}
+static void ctx_teardown(zk_ctx* c) {
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& r : c->recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
-  for (int d = 0; d < 2; d++) cudaFree(c->tw[d]);
+  for (int d = 0; d < 2; d++)
+    if (c->tw[d]) cudaFree(c->tw[d]);
   for (int b = 0; b < zk_ctx::NSLAB; b++) {
     if (c->slab_buf[b]) cudaFree(c->slab_buf[b]);
     if (c->slab_up[b]) cudaEventDestroy(c->slab_up[b]);
@@ -151,7 +167,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* c) {
   }
   if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 extern "C" int32_t zk_ctx_sync(zk_ctx* c) {
@@ -338,15 +354,16 @@ int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t 
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
   if (w == 0) return ZK_OK;
+  DevScope ds(c);
   uint32_t* coef = nullptr;
   std::vector<ntt::CosetScale> scales;
-  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&coef))) return rc;
+  if ((rc = ds.alloc(&coef, h * w * 4ull))) return rc;
   const bool aligned = (w & 1u) == 0 && ((uintptr_t)in % 8) == 0 && ((uintptr_t)out % 8) == 0;
-  if ((rc = lde_scales(c, h, log_blowup, shift, aligned, scales))) return rc;
-  rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, w, 0}, ntt::Cols{out, w, 0}, w, h, log_blowup,
-                scales);
-  free_scales(c, scales);
-  dev_free(c, coef);
+  rc = lde_scales(c, h, log_blowup, shift, aligned, scales);
+  if (rc == ZK_OK)
+    rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, w, 0}, ntt::Cols{out, w, 0}, w, h,
+                  log_blowup, scales);
+  free_scales(c, scales);  // also after a partial failure of lde_scales
   return rc;
 }
 
@@ -711,6 +728,7 @@ static int32_t check_shapes(uint32_t n_mats, const void* ptrs, const uint64_t* h
 void pdata_release(zk_pdata* pd) {
   zk_ctx* c = pd->ctx;
   cudaSetDevice(c->device);
+  if (pd->counted) c->live_pdata--;
   for (uint32_t i = 0; i < pd->mats.size(); i++)
     if (pd->owned[i] && pd->mats[i]) cudaFreeAsync(pd->mats[i], c->stream);
   for (uint32_t i = 0; i < pd->traces.size(); i++)
@@ -815,6 +833,8 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
     return rc;
   }
   if (root) memcpy(root, pd->root, 32);
+  pd->counted = true;
+  c->live_pdata++;
   *out = pd;
   return ZK_OK;
 }
@@ -894,8 +914,14 @@ extern "C" int32_t zk_mmcs_commit_dev(zk_ctx* c, uint32_t n_mats, const zk_dptr*
 // ------------------------------------------------------------------------------------------------
 extern "C" void zk_pdata_free(zk_pdata* pd) {
   if (!pd) return;
-  std::lock_guard<std::mutex> g(pd->ctx->mu);
-  pdata_release(pd);
+  zk_ctx* c = pd->ctx;
+  bool teardown = false;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    pdata_release(pd);
+    teardown = c->destroy_requested && c->live_pdata == 0;
+  }
+  if (teardown) ctx_teardown(c);
 }
 extern "C" uint32_t zk_pdata_num_matrices(const zk_pdata* pd) { return pd ? pd->n : 0; }
 extern "C" uint64_t zk_pdata_height(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? pd->heights[i] : 0; }
@@ -936,6 +962,73 @@ extern "C" int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint3
   return ZK_OK;
 }
 
+// Mmcs::ProverData: Serialize + DeserializeOwned (crates/stark/src/prover.rs:221, machine.rs:56-57): the inverse of
+// zk_pdata_copy_lde / zk_pdata_copy_layer.  Nothing is hashed -- like serde, it restores what was exported.
+extern "C" int32_t zk_pdata_import(zk_ctx* c, uint32_t n_mats, const uint32_t* const* ldes_host, const uint64_t* heights,
+                                   const uint32_t* widths, const uint32_t* const* layers_host, uint32_t n_layers,
+                                   const uint32_t* const* traces_host, uint32_t log_blowup, zk_pdata** out) {
+  if (!c || !out || !layers_host) return zk_fail(ZK_ERR_ARG, "null argument");
+  int32_t rc = check_shapes(n_mats, ldes_host, heights, widths);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  zk_pdata* pd = new zk_pdata();
+  pd->ctx = c;
+  pd->n = n_mats;
+  pd->heights.assign(heights, heights + n_mats);
+  pd->widths.assign(widths, widths + n_mats);
+  pd->mats.assign(n_mats, nullptr);
+  pd->owned.assign(n_mats, true);
+  pd->traces.assign(n_mats, nullptr);
+  pd->trace_owned.assign(n_mats, false);
+  auto fail = [&](int32_t code) {
+    pdata_release(pd);
+    return code;
+  };
+  for (uint32_t i = 0; i < n_mats; i++) {
+    const uint64_t bytes = heights[i] * widths[i] * 4ull;
+    if (bytes && !ldes_host[i]) return fail(zk_fail(ZK_ERR_ARG, "null matrix pointer"));
+    if ((rc = dev_alloc(c, bytes, (void**)&pd->mats[i]))) return fail(rc);
+    if (bytes && cudaMemcpyAsync(pd->mats[i], ldes_host[i], bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      return fail(zk_fail(ZK_ERR_CUDA, "upload of an LDE matrix failed"));
+    if (traces_host && traces_host[i]) {
+      if (heights[i] >> log_blowup == 0) return fail(zk_fail(ZK_ERR_ARG, "committed height below the blowup"));
+      const uint64_t tb = (heights[i] >> log_blowup) * widths[i] * 4ull;
+      if ((rc = dev_alloc(c, tb, (void**)&pd->traces[i]))) return fail(rc);
+      pd->trace_owned[i] = true;
+      if (tb && cudaMemcpyAsync(pd->traces[i], traces_host[i], tb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        return fail(zk_fail(ZK_ERR_CUDA, "upload of a retained trace failed"));
+    }
+  }
+  if ((rc = mmcs_alloc(c, pd))) return fail(rc);
+  if (n_layers != pd->log_max + 1) return fail(zk_fail(ZK_ERR_ARG, "expected log_max_height + 1 digest layers"));
+  const uint64_t hmax = pd->heights[pd->order[0]];
+  for (uint32_t l = 0; l <= pd->log_max; l++) {
+    if (!layers_host[l]) return fail(zk_fail(ZK_ERR_ARG, "null digest layer"));
+    if (cudaMemcpyAsync(pd->digests + pd->layer_off[l], layers_host[l], (hmax >> l) * 32, cudaMemcpyHostToDevice,
+                        c->stream) != cudaSuccess)
+      return fail(zk_fail(ZK_ERR_CUDA, "upload of a digest layer failed"));
+  }
+  // open_batch descriptors and root, as mmcs_build's tail
+  std::vector<zk_open_desc> od(n_mats);
+  uint32_t off = 0;
+  for (uint32_t i = 0; i < n_mats; i++) {
+    od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
+    off += pd->widths[i];
+  }
+  pd->sum_w = off;
+  if ((rc = dev_alloc(c, n_mats * sizeof(zk_open_desc), (void**)&pd->d_desc))) return fail(rc);
+  if (cudaMemcpyAsync(pd->d_desc, od.data(), n_mats * sizeof(zk_open_desc), cudaMemcpyHostToDevice, c->stream) !=
+          cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return fail(zk_fail(ZK_ERR_CUDA, "upload of the open_batch descriptors failed"));
+  memcpy(pd->root, layers_host[pd->log_max], 32);
+  pd->counted = true;
+  c->live_pdata++;
+  *out = pd;
+  return ZK_OK;
+}
+
 int32_t pdata_open_dev(zk_ctx* c, const zk_pdata* pd, uint32_t n_idx, const uint64_t* d_idx, uint32_t shift,
                        uint32_t* d_opened, uint64_t opened_stride, uint32_t* d_proofs, uint64_t proofs_stride) {
   ZK_LAUNCH(open_gather_kernel, n_idx, 128, 0, c->stream, pd->d_desc, pd->n, pd->sum_w, pd->digests, pd->log_max, d_idx, shift, d_opened, opened_stride, d_proofs, proofs_stride);
@@ -957,18 +1050,16 @@ extern "C" int32_t zk_pdata_open_batch(const zk_pdata* pd, uint32_t n_idx, const
   uint64_t* d_idx = nullptr;
   uint32_t *d_op = nullptr, *d_pr = nullptr;
   int32_t rc;
+  DevScope ds(c);
   uint64_t ob = (uint64_t)n_idx * pd->sum_w * 4, pb = (uint64_t)n_idx * pd->log_max * 32;
-  if ((rc = dev_alloc(c, n_idx * 8ull, (void**)&d_idx))) return rc;
-  if ((rc = dev_alloc(c, ob, (void**)&d_op))) return rc;
-  if ((rc = dev_alloc(c, pb, (void**)&d_pr))) return rc;
+  if ((rc = ds.alloc(&d_idx, n_idx * 8ull))) return rc;
+  if ((rc = ds.alloc(&d_op, ob))) return rc;
+  if ((rc = ds.alloc(&d_pr, pb))) return rc;
   CK(cudaMemcpyAsync(d_idx, indices, n_idx * 8ull, cudaMemcpyHostToDevice, c->stream));
   if ((rc = pdata_open_dev(c, pd, n_idx, d_idx, 0, d_op, pd->sum_w, d_pr, (uint64_t)pd->log_max * 8))) return rc;
   if (ob) CK(cudaMemcpyAsync(opened, d_op, ob, cudaMemcpyDeviceToHost, c->stream));
   if (pb) CK(cudaMemcpyAsync(proofs, d_pr, pb, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d_idx);
-  dev_free(c, d_op);
-  dev_free(c, d_pr);
   return ZK_OK;
 }
 
@@ -982,14 +1073,15 @@ extern "C" int32_t zk_poseidon2_permute(zk_ctx* c, uint32_t* states, uint64_t n)
   CK(cudaSetDevice(c->device));
   uint32_t* d = nullptr;
   int32_t rc;
-  if ((rc = dev_alloc(c, n * 64, (void**)&d))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d, n * 64))) return rc;
   CK(cudaMemcpyAsync(d, states, n * 64, cudaMemcpyHostToDevice, c->stream));
   ZK_LAUNCH(mk::permute_states, (unsigned)((n + 255) / 256), 256, 0, c->stream, d, n);
   CK(cudaGetLastError());
   c->launches++;
   CK(cudaMemcpyAsync(states, d, n * 64, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  return dev_free(c, d);
+  return ZK_OK;
 }
 
 extern "C" int32_t zk_hash_rows(zk_ctx* c, const uint32_t* mat, uint64_t h, uint32_t w, uint32_t* digests) {
@@ -999,15 +1091,15 @@ extern "C" int32_t zk_hash_rows(zk_ctx* c, const uint32_t* mat, uint64_t h, uint
   CK(cudaSetDevice(c->device));
   uint32_t *d = nullptr, *o = nullptr;
   int32_t rc;
-  if ((rc = dev_alloc(c, h * w * 4ull, (void**)&d))) return rc;
-  if ((rc = dev_alloc(c, h * 32, (void**)&o))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d, h * w * 4ull))) return rc;
+  if ((rc = ds.alloc(&o, h * 32))) return rc;
   if (h * w) CK(cudaMemcpyAsync(d, mat, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
   std::vector<mk::MatDesc> grp{mk::MatDesc{d, w}};
   if ((rc = hash_group(c, grp, h, o))) return rc;
   CK(cudaMemcpyAsync(digests, o, h * 32, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d);
-  return dev_free(c, o);
+  return ZK_OK;
 }
 
 extern "C" int32_t zk_compress_layer(zk_ctx* c, const uint32_t* prev, uint64_t n_out, uint32_t* out) {
@@ -1017,16 +1109,16 @@ extern "C" int32_t zk_compress_layer(zk_ctx* c, const uint32_t* prev, uint64_t n
   CK(cudaSetDevice(c->device));
   uint32_t *d = nullptr, *o = nullptr;
   int32_t rc;
-  if ((rc = dev_alloc(c, n_out * 64, (void**)&d))) return rc;
-  if ((rc = dev_alloc(c, n_out * 32, (void**)&o))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d, n_out * 64))) return rc;
+  if ((rc = ds.alloc(&o, n_out * 32))) return rc;
   CK(cudaMemcpyAsync(d, prev, n_out * 64, cudaMemcpyHostToDevice, c->stream));
   ZK_LAUNCH(mk::compress_layer, (unsigned)((n_out + 255) / 256), 256, 0, c->stream, d, o, n_out, nullptr);
   CK(cudaGetLastError());
   c->launches++;
   CK(cudaMemcpyAsync(out, o, n_out * 32, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d);
-  return dev_free(c, o);
+  return ZK_OK;
 }
 
 extern "C" int32_t zk_coset_lde_dev(zk_ctx* c, zk_dptr in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
@@ -1045,14 +1137,14 @@ extern "C" int32_t zk_coset_lde(zk_ctx* c, const uint32_t* in, uint64_t h, uint3
   uint32_t *d = nullptr, *o = nullptr;
   int32_t rc;
   uint64_t ib = h * w * 4ull, obytes = ib << log_blowup;
-  if ((rc = dev_alloc(c, ib, (void**)&d))) return rc;
-  if ((rc = dev_alloc(c, obytes, (void**)&o))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d, ib))) return rc;
+  if ((rc = ds.alloc(&o, obytes))) return rc;
   CK(cudaMemcpyAsync(d, in, ib, cudaMemcpyHostToDevice, c->stream));
   if ((rc = lde_dev(c, d, h, w, log_blowup, shift, o))) return rc;
   CK(cudaMemcpyAsync(out, o, obytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d);
-  return dev_free(c, o);
+  return ZK_OK;
 }
 
 extern "C" int32_t zk_dft_batch(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t* out) {
@@ -1066,8 +1158,9 @@ extern "C" int32_t zk_dft_batch(zk_ctx* c, const uint32_t* in, uint64_t h, uint3
   uint32_t *d = nullptr, *o = nullptr;
   int32_t rc;
   uint64_t bytes = h * w * 4ull;
-  if ((rc = dev_alloc(c, bytes, (void**)&d))) return rc;
-  if ((rc = dev_alloc(c, bytes, (void**)&o))) return rc;
+  DevScope ds(c);
+  if ((rc = ds.alloc(&d, bytes))) return rc;
+  if ((rc = ds.alloc(&o, bytes))) return rc;
   CK(cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(ntt::transform(ntt::Cols{d, w, 0}, ntt::Cols{d, w, 0}, w, n, ntt::DIR_FWD, c->tw[0], c->log_L, nullptr, false, c->stream));
   uint64_t total = h * w;
@@ -1076,6 +1169,5 @@ extern "C" int32_t zk_dft_batch(zk_ctx* c, const uint32_t* in, uint64_t h, uint3
   c->launches += num_passes(n) + 1;
   CK(cudaMemcpyAsync(out, o, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  dev_free(c, d);
-  return dev_free(c, o);
+  return ZK_OK;
 }

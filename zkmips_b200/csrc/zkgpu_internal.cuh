@@ -54,6 +54,24 @@ struct zk_ctx {
   };
   std::vector<Rec> recs;
   uint64_t launches = 0;
+  // prover data handles hold a pointer to their context: zk_ctx_destroy with handles still alive only marks the
+  // context and the LAST zk_pdata_free tears it down (bindings free handles from destructors in any order)
+  uint64_t live_pdata = 0;
+  bool destroy_requested = false;
+};
+
+// device allocations of one entry point, freed (stream-ordered) on every return path
+struct DevScope {
+  zk_ctx* c;
+  std::vector<void*> ptrs;
+  explicit DevScope(zk_ctx* c) : c(c) {}
+  template <class T>
+  int32_t alloc(T** p, uint64_t bytes);
+  void release(void* p) {  // hand a pointer over to the caller
+    for (auto& q : ptrs)
+      if (q == p) q = nullptr;
+  }
+  ~DevScope();
 };
 
 struct ProfScope {
@@ -92,10 +110,23 @@ struct zk_pdata {
   std::vector<uint64_t> layer_off;  // word offset of each layer
   zk_open_desc* d_desc = nullptr;
   uint32_t root[8] = {0};
+  bool counted = false;  // handed to the caller (counts towards ctx->live_pdata)
 };
 
 int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out);
 int32_t dev_free(zk_ctx* c, void* p);
+template <class T>
+int32_t DevScope::alloc(T** p, uint64_t bytes) {
+  void* q = nullptr;
+  int32_t rc = dev_alloc(c, bytes, &q);
+  if (rc == ZK_OK) ptrs.push_back(q);
+  *p = (T*)q;
+  return rc;
+}
+inline DevScope::~DevScope() {
+  for (auto p : ptrs)
+    if (p) cudaFreeAsync(p, c->stream);
+}
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
                 uint32_t* out);
 int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd);

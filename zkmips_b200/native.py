@@ -53,6 +53,7 @@ PROTOTYPES = {
     "zk_pdata_lde": (u64, [vp, u32]),
     "zk_pdata_copy_lde": (i32, [vp, u32, u32p]),
     "zk_pdata_copy_layer": (i32, [vp, u32, u32p]),
+    "zk_pdata_import": (i32, [vp, u32, C.POINTER(vp), u64p, u32p, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp)]),
     "zk_pdata_open_batch": (i32, [vp, u32, u64p, u32p, u32p]),
     "zk_air_count": (i32, []),
     "zk_air_name": (C.c_char_p, [i32]),
@@ -165,6 +166,11 @@ class PData:
         out = np.empty(((1 << self.log_max_height()) >> l, 8), np.uint32)
         self.ctx.lib.check(self.d.zk_pdata_copy_layer(self.h, l, _p32(out)))
         return out
+
+    def export(self):
+        """host image of the prover data (what `Serialize` writes): LDE matrices + every digest layer"""
+        n = self.num_matrices()
+        return {"ldes": [self.lde(i) for i in range(n)], "layers": [self.layer(l) for l in range(self.log_max_height() + 1)]}
 
     def open_batch(self, indices):
         idx = _arr(indices, np.uint64)
@@ -358,6 +364,24 @@ class Ctx:
         out = np.empty(shape, np.uint32)
         self.d2h(out, dptr)
         return out
+
+    def import_pdata(self, image, traces=None, log_blowup=1):
+        """`DeserializeOwned` for Mmcs::ProverData: rebuild device-resident prover data from PData.export()'s image
+        (optionally with the retained input traces, e.g. `StarkProvingKey::traces`)."""
+        ldes = [_arr(m, np.uint32) for m in image["ldes"]]
+        layers = [_arr(l, np.uint32) for l in image["layers"]]
+        heights, widths = self._shape_args([m.shape for m in ldes])
+        lp = (vp * len(ldes))(*[m.ctypes.data_as(vp) for m in ldes])
+        yp = (vp * len(layers))(*[l.ctypes.data_as(vp) for l in layers])
+        tp = None
+        keep = []
+        if traces is not None:
+            keep = [None if t is None else _arr(t, np.uint32) for t in traces]
+            tp = (vp * len(ldes))(*[None if t is None else t.ctypes.data_as(vp) for t in keep])
+        pd = vp()
+        self.lib.check(self.d.zk_pdata_import(self.h, len(ldes), lp, heights.ctypes.data_as(u64p), _p32(widths), yp,
+                                              len(layers), tp, log_blowup, C.byref(pd)))
+        return PData(self, pd, layers[-1].reshape(-1)[:8].copy())
 
     def mmcs_commit(self, mats):
         ms = [_arr(m, np.uint32) for m in mats]

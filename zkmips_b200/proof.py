@@ -127,7 +127,7 @@ class RoundShape:
 
 def split_flat_proof(flat, rounds: List[RoundShape], log_blowup, num_queries):
     """-> (opened[round][matrix][point] = (width, 4) array, FriProof)"""
-    flat = np.asarray(flat, np.uint32)
+    flat = np.asarray(flat, np.uint32)  # the structured proof holds VIEWS into this buffer
     off = 0
     opened = []
     for r in rounds:
@@ -135,15 +135,15 @@ def split_flat_proof(flat, rounds: List[RoundShape], log_blowup, num_queries):
         for w, npts in zip(r.widths, r.n_points):
             mat = []
             for _ in range(npts):
-                mat.append(flat[off:off + 4 * w].reshape(w, 4).copy())
+                mat.append(flat[off:off + 4 * w].reshape(w, 4))
                 off += 4 * w
             rnd.append(mat)
         opened.append(rnd)
     log_max = max(r.log_max for r in rounds)
     n_layers = max(log_max - log_blowup, 0)
-    commits = flat[off:off + 8 * n_layers].reshape(n_layers, 8).copy()
+    commits = flat[off:off + 8 * n_layers].reshape(n_layers, 8)
     off += 8 * n_layers
-    final_poly = flat[off:off + 4].copy()
+    final_poly = flat[off:off + 4]
     off += 4
     pow_witness = int(flat[off])
     off += 1
@@ -153,17 +153,17 @@ def split_flat_proof(flat, rounds: List[RoundShape], log_blowup, num_queries):
         for r in rounds:
             rows = []
             for w in r.widths:
-                rows.append(flat[off:off + w].copy())
+                rows.append(flat[off:off + w])
                 off += w
-            path = flat[off:off + 8 * r.log_max].reshape(r.log_max, 8).copy()
+            path = flat[off:off + 8 * r.log_max].reshape(r.log_max, 8)
             off += 8 * r.log_max
             inp.append(BatchOpening(rows, path))
         steps = []
         for i in range(n_layers):
-            sib = flat[off:off + 4].copy()
+            sib = flat[off:off + 4]
             off += 4
             d = log_max - i - 1
-            steps.append(CommitPhaseProofStep(sib, flat[off:off + 8 * d].reshape(d, 8).copy()))
+            steps.append(CommitPhaseProofStep(sib, flat[off:off + 8 * d].reshape(d, 8)))
             off += 8 * d
         queries.append(QueryProof(inp, steps))
     assert off == flat.size, f"flat proof has {flat.size} words, layout accounts for {off}"
