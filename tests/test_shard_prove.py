@@ -8,7 +8,7 @@ import pytest
 from oracle import air_eval as ae
 from oracle import binding as ob
 from tests import backends, shard_util as su
-from zkmips_b200 import Challenger
+from zkmips_b200 import Challenger, synth
 from zkmips_b200.prover import MONTY_ONE, GpuShardProver
 
 BACKENDS = [pytest.param("emu", id="emu"), pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)]
@@ -26,7 +26,8 @@ def _natural(lde_bitrev):
 
 
 @pytest.mark.parametrize("be", BACKENDS)
-@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool"])
+@pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
+                                   "Lt", "Bitwise"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -35,7 +36,10 @@ def test_quotient_values_match_oracle(be, which):
     chip = {"fibonacci": lambda: su.fibonacci_chip(5), "wide": lambda: su.wide_chip(4, 64),
             "lookup": lambda: su.lookup_chip(4), "wide1024": lambda: su.wide_chip(10, 1024, seed=21),
             "wide4096": lambda: su.wide_chip(8, 4096, seed=22), "global": lambda: su.global_chip(5),
-            "local_bool": lambda: su.local_bool_chip(4)}[which]()
+            "local_bool": lambda: su.local_bool_chip(4),
+            # real Ziren chips transcribed from their Air::eval (library.add_sub / lt / bitwise), real lookups
+            "AddSub": lambda: synth.add_sub_chip(6), "Lt": lambda: synth.lt_chip(6),
+            "Bitwise": lambda: synth.bitwise_chip(5)}[which]()
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
     air = su.AIRS[chip.air]
@@ -56,7 +60,8 @@ def test_quotient_values_match_oracle(be, which):
         from oracle import logup
         p_c, m_c = chip.canon
         exp_tr, exp_lcs = logup.generate_permutation_trace(air, p_c, m_c, ob.from_monty(chal[0]), ob.from_monty(chal[1]))
-        dptr, lcs = ctx.permutation_trace(chip.air, ctx.upload(chip.preprocessed), ctx.upload(chip.main), 1 << n, chal)
+        dptr, lcs = ctx.permutation_trace(chip.air, ctx.upload(chip.preprocessed) if chip.preprocessed is not None else 0,
+                                          ctx.upload(chip.main), 1 << n, chal)
         tr = ctx.download(dptr, exp_tr.shape)
         assert (ob.from_monty(tr) == exp_tr).all()
         assert list(ob.from_monty(lcs)) == exp_lcs
@@ -177,6 +182,34 @@ def test_shard_proof_bit_exact_with_oracle_prover(be):
     assert pf.to_bincode(osp_proof) == pf.to_bincode(sp)
     data.main_data.free()
     pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_real_alu_chips_shard(be):
+    """SURVEY f2: a shard of three REAL Ziren chips -- AddSub, Lt, Bitwise, transcribed from their Air::eval with their
+    real byte-table sends and instruction-bus receives -- proven on the GPU path: the proof is byte-identical to the CPU
+    restatement's, and the verifier accepts every per-chip check (PCS openings at [zeta] only: all three are
+    local_only; constraint identity including the LogUp constraints).  Their lookups are answered by the Cpu and Byte
+    chips, which are not in this shard, so the final shard-sum check must be the one that fails."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    logs = (7, 6, 5) if be == "emu" else (12, 11, 10)
+    chips = [synth.add_sub_chip(logs[0]), synth.lt_chip(logs[1]), synth.bitwise_chip(logs[2])]
+    for c in chips:
+        air = su.AIRS[c.air]
+        assert c.main.shape[1] + 4 * air.perm_width + 8 == {"AddSub": 47, "Lt": 56, "Bitwise": 42}[c.air]  # mips_costs.json
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 1, nq, pw)
+    assert not ok and why.endswith("local cumulative sum is not zero"), why
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=NUM_PV)
+    opk = op.setup(chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))) == pf.to_bincode(sp)
+    data.main_data.free()
 
 
 @pytest.mark.parametrize("drop", ["public_values", "vk", "local_sum", "global_sum", "perm_commit", "local_only"])

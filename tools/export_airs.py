@@ -1,0 +1,19 @@
+#!/usr/bin/env python3
+"""Writes the constraint programs of the real Ziren chips as JSON (zkmips_b200/air/exported/<Chip>.json): the format a
+Rust-side recording builder (ZKMAirBuilder + PairBuilder + MultiTableAirBuilder running `Chip::eval` once,
+crates/stark/src/chip.rs:253-272, the way the reference already runs it symbolically to count constraints,
+crates/stark/src/machine.rs:357-369) has to emit.  tests/test_air_ir.py checks that loading these files reproduces the
+generated CUDA text."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from zkmips_b200.air import library  # noqa: E402
+
+OUT = os.path.join(ROOT, "zkmips_b200", "air", "exported")
+os.makedirs(OUT, exist_ok=True)
+for air in (library.add_sub(), library.lt(), library.bitwise()):
+    with open(os.path.join(OUT, air.name + ".json"), "w") as fh:
+        fh.write(air.to_json() + "\n")
+    print(air.name, air.num_constraints, "constraints,", len(air.nodes), "nodes")

@@ -288,6 +288,10 @@ class AirBuilder:
         c = cond if self.cond is None else self.cond * cond
         return AirBuilder(self.air, c)
 
+    def when_not(self, cond):
+        """p3 AirBuilder::when_not: filter by (1 - cond)"""
+        return self.when(1 - self._lift(cond))
+
     def when_first_row(self):
         return self.when(self.is_first_row())
 

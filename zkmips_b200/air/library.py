@@ -120,7 +120,169 @@ def local_bool(width=8):
     return air
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Real Ziren chips, transcribed by hand from their `Air::eval` (the Rust-side exporter of SURVEY f2 would emit exactly
+# these programs as JSON: `Air.to_json`).  Column order = the `#[repr(C)]` column structs; constraint and lookup
+# emission order = the order of the builder calls in `eval`, which fixes the powers of alpha and the LogUp batches.
+# Committed columns per row (main + 4 * permutation + 4 * 2 quotient) match `mips_costs.json`: AddSub 47, Lt 56,
+# Bitwise 42.
+# ------------------------------------------------------------------------------------------------------------------
+LOOKUP_MEMORY, LOOKUP_PROGRAM, LOOKUP_INSTRUCTION, LOOKUP_BYTE = 1, 2, 3, 4   # LookupKind, stark/src/lookup/lookup.rs:23-44
+BYTE_AND, BYTE_OR, BYTE_XOR, BYTE_U8RANGE, BYTE_LTU, BYTE_NOR = 0, 1, 2, 4, 6, 9  # ByteOpcode, executor/src/opcode.rs:184-205
+OP_ADD, OP_SUB, OP_SLT, OP_SLTU, OP_AND, OP_OR, OP_XOR, OP_NOR = 0, 1, 13, 14, 15, 16, 17, 18  # Opcode, opcode.rs:15-35
+
+
+def _send_byte(b, opcode, a, bb, c, mult):
+    """ZKMAirBuilder::send_byte -> send_byte_pair(opcode, a1, 0, b, c) (stark/src/air/builder.rs:120-150)"""
+    b.send(LOOKUP_BYTE, [opcode, a, 0, bb, c], mult)
+
+
+def _slice_range_check_u8(b, xs, mult):
+    """WordAirBuilder::slice_range_check_u8 (core/machine/src/air/word.rs:55-80): bytes are checked in pairs"""
+    i = 0
+    while i + 1 < len(xs):
+        _send_byte(b, BYTE_U8RANGE, 0, xs[i], xs[i + 1], mult)
+        i += 2
+    if i < len(xs):
+        _send_byte(b, BYTE_U8RANGE, 0, xs[i], 0, mult)
+
+
+def _receive_instruction(b, pc, next_pc, opcode, a, bb, c, mult):
+    """ZKMAirBuilder::receive_instruction as the ALU chips call it (stark/src/air/builder.rs:237-279): shard = clk = 0,
+    next_next_pc = next_pc + 4, num_extra_cycles = 0, hi = 0, op_a_immutable = is_rw_a = is_check_memory = is_halt = 0,
+    is_sequential = 1."""
+    vals = [0, 0, pc, next_pc, next_pc + 4, 0, opcode] + list(a) + list(bb) + list(c) + [0, 0, 0, 0] + [0, 0, 0, 0, 1]
+    b.receive(LOOKUP_INSTRUCTION, vals, mult)
+
+
+def add_sub():
+    """AddSubChip (crates/core/machine/src/alu/add_sub/mod.rs:42-62 columns, :180-249 eval) with AddOperation
+    (crates/core/machine/src/operations/add.rs:14-99).  19 main columns, 14 constraints + 6 byte sends + 2 instruction
+    receives; `local_only`."""
+    air = Air("AddSub", main_width=19, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    value, carry = m[2:6], m[6:9]
+    op1, op2 = m[9:13], m[13:17]
+    is_add, is_sub = m[17], m[18]
+    # AddOperation::eval(builder, operand_1, operand_2, add_operation, is_add + is_sub)
+    is_real = is_add + is_sub
+    r = b.when(is_real)
+    base = 256
+    o0 = op1[0] + op2[0] - value[0]
+    o1 = op1[1] + op2[1] - value[1] + carry[0]
+    o2 = op1[2] + op2[2] - value[2] + carry[1]
+    o3 = op1[3] + op2[3] - value[3] + carry[2]
+    r.assert_zero(o3 * (o3 - base))
+    r.assert_zero(carry[0] * (o0 - base))
+    r.assert_zero(carry[1] * (o1 - base))
+    r.assert_zero(carry[2] * (o2 - base))
+    r.assert_zero((carry[0] - 1) * o0)
+    r.assert_zero((carry[1] - 1) * o1)
+    r.assert_zero((carry[2] - 1) * o2)
+    r.assert_bool(carry[0])
+    r.assert_bool(carry[1])
+    r.assert_bool(carry[2])
+    r.assert_bool(is_real)
+    _slice_range_check_u8(b, op1, is_real)
+    _slice_range_check_u8(b, op2, is_real)
+    _slice_range_check_u8(b, value, is_real)
+    _receive_instruction(b, pc, next_pc, OP_ADD, value, op1, op2, is_add)
+    _receive_instruction(b, pc, next_pc, OP_SUB, op1, value, op2, is_sub)
+    b.assert_bool(is_add)
+    b.assert_bool(is_sub)
+    b.assert_bool(is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+def bitwise():
+    """BitwiseChip (crates/core/machine/src/alu/bitwise/mod.rs:33-58 columns, :179-234 eval): 18 main columns, 4 byte
+    sends + 1 instruction receive, 5 constraints (the reference asserts `is_xor` boolean twice and never `is_nor`;
+    transcribed as written)."""
+    air = Air("Bitwise", main_width=18, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    a, bb, c = m[2:6], m[6:10], m[10:14]
+    is_nor, is_xor, is_or, is_and = m[14], m[15], m[16], m[17]
+    opcode = is_xor * BYTE_XOR + is_or * BYTE_OR + is_and * BYTE_AND + is_nor * BYTE_NOR
+    mult = is_xor + is_or + is_and + is_nor
+    for i in range(4):
+        _send_byte(b, opcode, a[i], bb[i], c[i], mult)
+    cpu_opcode = is_xor * OP_XOR + is_or * OP_OR + is_and * OP_AND + is_nor * OP_NOR
+    _receive_instruction(b, pc, next_pc, cpu_opcode, a, bb, c, mult)
+    b.assert_bool(is_xor)
+    b.assert_bool(is_or)
+    b.assert_bool(is_and)
+    b.assert_bool(is_xor)
+    b.assert_bool(mult)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+def lt():
+    """LtChip (crates/core/machine/src/alu/lt/mod.rs:36-85 columns, :274-468 eval): 36 main columns, 3 byte sends + 1
+    instruction receive."""
+    air = Air("Lt", main_width=36, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc, is_slt, is_sltu = m[0], m[1], m[2], m[3]
+    a, bw, cw = m[4:8], m[8:12], m[12:16]
+    byte_flags = m[16:20]
+    b_masked, c_masked, not_eq_inv = m[20], m[21], m[22]
+    msb_b, msb_c, bit_b, bit_c = m[23], m[24], m[25], m[26]
+    sltu, is_comp_eq, is_sign_eq = m[27], m[28], m[29]
+    comparison_bytes = m[30:32]
+    # m[32:36] = byte_equality_check: allocated by the reference, never constrained
+    is_real = is_slt + is_sltu
+    b_comp = list(bw)
+    c_comp = list(cw)
+    b_comp[3] = bw[3] * is_sltu + b_masked * is_slt
+    c_comp[3] = cw[3] * is_sltu + c_masked * is_slt
+    _send_byte(b, BYTE_AND, b_masked, bw[3], 0x7F, is_real)
+    _send_byte(b, BYTE_AND, c_masked, cw[3], 0x7F, is_real)
+    b.assert_eq(bit_b, msb_b * is_slt)
+    b.assert_eq(bit_c, msb_c * is_slt)
+    inv_128 = pow(128, -1, 0x7F000001)
+    b.assert_eq(msb_b, (bw[3] - b_masked) * inv_128)
+    b.assert_eq(msb_c, (cw[3] - c_masked) * inv_128)
+    b.assert_bool(is_sign_eq)
+    b.when(is_sign_eq).assert_eq(bit_b, bit_c)
+    b.when(is_real).when_not(is_sign_eq).assert_one(bit_b + bit_c)
+    b.assert_eq(a[0], bit_b * (1 - bit_c) + is_sign_eq * sltu)
+    b.assert_zero(a[1])
+    b.assert_zero(a[2])
+    b.assert_zero(a[3])
+    sum_flags = byte_flags[0] + byte_flags[1] + byte_flags[2] + byte_flags[3]
+    for f in byte_flags:
+        b.assert_bool(f)
+    b.assert_bool(sum_flags)
+    b.when(is_real).assert_eq(1 - is_comp_eq, sum_flags)
+    b.assert_bool(is_comp_eq)
+    visited = None
+    b_byte_sel = c_byte_sel = None
+    for k in (3, 2, 1, 0):
+        flag = byte_flags[k]
+        visited = flag if visited is None else visited + flag
+        b_byte_sel = b_comp[k] * flag if b_byte_sel is None else b_byte_sel + b_comp[k] * flag
+        c_byte_sel = c_comp[k] * flag if c_byte_sel is None else c_byte_sel + c_comp[k] * flag
+        b.when_not(visited).assert_eq(b_comp[k], c_comp[k])
+        b.when(is_comp_eq).assert_zero(visited)
+    b.assert_eq(comparison_bytes[0], b_byte_sel)
+    b.assert_eq(comparison_bytes[1], c_byte_sel)
+    b.when_not(is_comp_eq).assert_eq(not_eq_inv * (comparison_bytes[0] - comparison_bytes[1]), is_real)
+    _send_byte(b, BYTE_LTU, sltu, comparison_bytes[0], comparison_bytes[1], is_real)
+    b.assert_bool(is_slt)
+    b.assert_bool(is_sltu)
+    b.assert_bool(is_slt + is_sltu)
+    _receive_instruction(b, pc, next_pc, is_slt * OP_SLT + is_sltu * OP_SLTU, a, bw, cw, is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
-            local_bool()]
+            local_bool(), add_sub(), lt(), bitwise()]

@@ -148,3 +148,105 @@ def public_values_for(chips, n=8):
     return M(pv)
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Real Ziren ALU chips (library.add_sub / lt / bitwise): numpy restatements of their `event_to_row` on random events.
+# `fill` of the 2^log_n rows are real events, the rest is the zero padding the reference leaves (is_real = 0).
+# ------------------------------------------------------------------------------------------------------------------
+def _bytes(x):
+    x = np.asarray(x, np.uint64)
+    return np.stack([(x >> np.uint64(8 * k)) & np.uint64(0xFF) for k in range(4)], axis=1)
+
+
+def _events(log_n, seed, fill):
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    real = max(1, int(n * fill)) if n > 1 else 1
+    pc = (0x1000 + 4 * np.arange(real, dtype=np.uint64)) % P
+    b = rng.integers(0, 1 << 32, real, dtype=np.uint64)
+    c = rng.integers(0, 1 << 32, real, dtype=np.uint64)
+    return n, real, rng, pc, b, c
+
+
+def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub"):
+    """AddSubChip::event_to_row + AddOperation::populate (alu/add_sub/mod.rs:150-172, operations/add.rs:26-60)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    is_add = rng.integers(0, 2, real).astype(np.uint64)
+    mask = np.uint64(0xFFFFFFFF)
+    a = np.where(is_add == 1, (b + c) & mask, (b - c) & mask)       # ADD: a = b + c;  SUB: a = b - c
+    op1 = np.where(is_add == 1, b, a)                               # operand_1: b for ADD, a for SUB
+    op2 = c
+    value = (op1 + op2) & mask
+    x, y = _bytes(op1), _bytes(op2)
+    carry = np.zeros((real, 3), np.uint64)
+    carry[:, 0] = (x[:, 0] + y[:, 0]) > 255
+    carry[:, 1] = (x[:, 1] + y[:, 1] + carry[:, 0]) > 255
+    carry[:, 2] = (x[:, 2] + y[:, 2] + carry[:, 1]) > 255
+    t = np.zeros((n, 19), np.uint64)
+    t[:real, 0], t[:real, 1] = pc, (pc + 4) % P
+    t[:real, 2:6], t[:real, 6:9] = _bytes(value), carry
+    t[:real, 9:13], t[:real, 13:17] = x, y
+    t[:real, 17], t[:real, 18] = is_add, 1 - is_add
+    ch = Chip(name, "AddSub", M(t), local_only=True)
+    ch.canon = (None, t)
+    return ch
+
+
+def bitwise_chip(log_n, seed=22, fill=0.75, name="Bitwise"):
+    """BitwiseChip::event_to_row (alu/bitwise/mod.rs:141-170)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    op = rng.integers(0, 4, real)  # 0 nor, 1 xor, 2 or, 3 and
+    mask = np.uint64(0xFFFFFFFF)
+    a = np.select([op == 0, op == 1, op == 2], [~(b | c) & mask, b ^ c, b | c], b & c)
+    t = np.zeros((n, 18), np.uint64)
+    t[:real, 0], t[:real, 1] = pc, (pc + 4) % P
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(a), _bytes(b), _bytes(c)
+    for k in range(4):
+        t[:real, 14 + k] = op == k
+    ch = Chip(name, "Bitwise", M(t), local_only=True)
+    ch.canon = (None, t)
+    return ch
+
+
+def lt_chip(log_n, seed=23, fill=0.75, name="Lt"):
+    """LtChip::event_to_row (alu/lt/mod.rs:179-262)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    eq = rng.integers(0, 8, real) == 0
+    c = np.where(eq, b, c)                                          # some equal operands (is_comp_eq = 1)
+    near = rng.integers(0, 4, real) == 0
+    c = np.where(near & ~eq, (b & np.uint64(0xFFFF0000)) | (c & np.uint64(0xFFFF)), c)  # differ in a LOW byte only
+    is_slt = rng.integers(0, 2, real).astype(np.uint64)
+    bb, cb = _bytes(b), _bytes(c)
+    b_masked, c_masked = bb[:, 3] & np.uint64(0x7F), cb[:, 3] & np.uint64(0x7F)
+    b_comp, c_comp = bb.copy(), cb.copy()
+    b_comp[:, 3] = np.where(is_slt == 1, b_masked, bb[:, 3])
+    c_comp[:, 3] = np.where(is_slt == 1, c_masked, cb[:, 3])
+    t = np.zeros((n, 36), np.uint64)
+    flags = np.zeros((real, 4), np.uint64)
+    sltu = np.zeros(real, np.uint64)
+    inv = np.zeros(real, np.uint64)
+    cmp_bytes = np.zeros((real, 2), np.uint64)
+    done = np.zeros(real, bool)
+    for k in (3, 2, 1, 0):                                          # most significant differing byte
+        hit = ~done & (b_comp[:, k] != c_comp[:, k])
+        flags[hit, k] = 1
+        sltu[hit] = b_comp[hit, k] < c_comp[hit, k]
+        cmp_bytes[hit, 0], cmp_bytes[hit, 1] = b_comp[hit, k], c_comp[hit, k]
+        done |= hit
+    diff = (cmp_bytes[:, 0] + np.uint64(P) - cmp_bytes[:, 1]) % np.uint64(P)
+    inv[done] = [pow(int(d), P - 2, P) for d in diff[done]]
+    msb_b, msb_c = bb[:, 3] >> np.uint64(7), cb[:, 3] >> np.uint64(7)
+    is_sign_eq = np.where(is_slt == 1, msb_b == msb_c, 1).astype(np.uint64)
+    bit_b, bit_c = msb_b * is_slt, msb_c * is_slt
+    a0 = bit_b * (1 - bit_c) + is_sign_eq * sltu
+    t[:real, 0], t[:real, 1], t[:real, 2], t[:real, 3] = pc, (pc + 4) % P, is_slt, 1 - is_slt
+    t[:real, 4] = a0
+    t[:real, 8:12], t[:real, 12:16], t[:real, 16:20] = bb, cb, flags
+    t[:real, 20], t[:real, 21], t[:real, 22] = b_masked, c_masked, inv
+    t[:real, 23], t[:real, 24], t[:real, 25], t[:real, 26] = msb_b, msb_c, bit_b, bit_c
+    t[:real, 27], t[:real, 28], t[:real, 29] = sltu, ~done, is_sign_eq
+    t[:real, 30:32] = cmp_bytes
+    ch = Chip(name, "Lt", M(t), local_only=True)
+    ch.canon = (None, t)
+    return ch
