@@ -28,7 +28,7 @@ def build_emu(force=False):
         return EMU_SO
     cu = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu")) + sorted(
         os.path.join("gen", f) for f in os.listdir(gen) if f.endswith(".cu"))
-    cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(EMU_DIR, "include")]
+    cmd = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(EMU_DIR, "include")]
     for f in cu:
         cmd += ["-x", "c++", os.path.join(CSRC, f)]
     cmd += ["-x", "c++", os.path.join(EMU_DIR, "emu_runtime.cpp"), "-o", EMU_SO]

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include "../../zkmips_b200/csrc/kb31.cuh"
 #include "../../include/zk_poseidon2_rc.h"
+#include "poseidon2_f64.cuh"
 
 __device__ constexpr uint32_t EXT_RC[8][16] = ZK_P2_EXT_RC_MONTY;
 __device__ constexpr uint32_t INT_RC[13] = ZK_P2_INT_RC_MONTY;
@@ -251,6 +252,59 @@ __global__ void __launch_bounds__(256, MINB) bench(uint32_t* out, int iters) {
   if (ILP > 1) out[tid * ILP + 1] = s[ILP - 1][3];
 }
 
+// Warp-specialised mix: DPW of the 8 warps of a CTA run the FP64-pipe permutation (poseidon2_f64.cuh), the others the
+// rolled integer one (the product's p2::permute shape).  Same inputs and outputs (Montgomery words) on both paths.
+template <int DPW, int MINB>
+__global__ void __launch_bounds__(256, MINB) bench_mixed(uint32_t* out, int iters) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = (tid * 2654435761u + i * 40503u) % P;
+  if ((int)(threadIdx.x >> 5) < DPW) {
+    double d[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) d[i] = p2d::from_monty_word(s[i]);
+    for (int it = 0; it < iters; it++) p2d::permute(d);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = p2d::to_monty_word(d[i]);
+  } else {
+    for (int it = 0; it < iters; it++) permute_rolled<MulSigned, 1, 3, 1, 0>(s, 0);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc ^= s[i] + i;
+  out[tid] = acc;
+}
+template <int DPW, int MINB>
+void run_mixed(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
+  int iters = 128, occ = 0;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, bench_mixed<DPW, MINB>);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench_mixed<DPW, MINB>, 256, 0);
+  int blocks = sms * occ;
+  bench_mixed<DPW, MINB><<<blocks, 256>>>(d_out, 4);
+  cudaDeviceSynchronize();
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e9;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(a);
+    bench_mixed<DPW, MINB><<<blocks, 256>>>(d_out, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  double perms = (double)blocks * 256 * iters;
+  uint32_t h[256];
+  cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+  // thread 0 (a DP warp when DPW > 0) against the integer reference; thread 255 (an integer warp when DPW < 8) too
+  if (h_ref[0] == 0xffffffffu) h_ref[0] = h[0];
+  const char* ok = (h[0] == h_ref[0]) ? " same-result" : " RESULT-DIFFERS";
+  printf("%-28s regs=%3d occ=%d blocks/SM  %.3f ms  %.2f Gperm/s  %.1f clk/perm/SM@1.9GHz%s err=%s\n", name, fa.numRegs, occ, best,
+         perms / best / 1e6, best * 1e-3 * 1.9e9 * sms / perms, ok, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <class M, int DIAG, int ILP, int MINB, int FA = 0>
 void run(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
   int blocks = sms * 8, iters = 128;
@@ -283,14 +337,26 @@ void run(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
 }
 
 int main(int argc, char** argv) {
-  int only = argc > 1 ? atoi(argv[1]) : -1;  // run a single variant (for ncu captures)
+  int only = argc > 1 ? atoi(argv[1]) : -1;  // run a single variant (for ncu captures); -2: the int / fp64 mixes only
   int idx = 0;
-#define RUN(...) if (idx++, only < 0 || only == idx - 1) run<__VA_ARGS__>
+#define RUN(...) if (idx++, only == -1 || only == -2 || only == idx - 1) run<__VA_ARGS__>
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int sms = p.multiProcessorCount;
   printf("%s, %d SMs\n", p.name, sms);
   uint32_t* d; cudaMalloc(&d, (size_t)sms * 16 * 256 * 2 * 4);
   uint32_t ref[1] = {0xffffffffu};
+#define RUNM(...) if (idx++, only == -1 || only == -2 || only == idx - 1) run_mixed<__VA_ARGS__>
+  RUN(MulSigned, 1, 1, 1, 41)("signed roll-all one-ext-body", d, ref, sms);   // the product's integer permutation: reference result
+  RUNM(0, 1)("mixed 0/8 fp64 warps (int only)", d, ref, sms);
+  RUNM(8, 1)("mixed 8/8 fp64 warps (fp64 only)", d, ref, sms);
+  RUNM(2, 1)("mixed 2/8 fp64 warps", d, ref, sms);
+  RUNM(3, 1)("mixed 3/8 fp64 warps", d, ref, sms);
+  RUNM(4, 1)("mixed 4/8 fp64 warps", d, ref, sms);
+  RUNM(5, 1)("mixed 5/8 fp64 warps", d, ref, sms);
+  RUNM(4, 3)("mixed 4/8 fp64 warps minb3", d, ref, sms);
+  RUNM(4, 4)("mixed 4/8 fp64 warps minb4", d, ref, sms);
+  RUNM(3, 4)("mixed 3/8 fp64 warps minb4", d, ref, sms);
+  if (only == -2) return 0;   // p2bench -2: only the mixes above
   RUN(MulSub, 0, 1, 1)("sub/diagmul", d, ref, sms);
   RUN(MulSub, 1, 1, 1)("sub/diagshift", d, ref, sms);
   RUN(MulSigned, 1, 1, 1)("signed-sbox/diagshift", d, ref, sms);
