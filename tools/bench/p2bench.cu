@@ -275,6 +275,54 @@ __global__ void __launch_bounds__(256, MINB) bench_mixed(uint32_t* out, int iter
   for (int i = 0; i < 16; i++) acc ^= s[i] + i;
   out[tid] = acc;
 }
+// Cleaner mix: whole CTAs are of one kind (blockIdx % 8 < DPB -> FP64), a grid of many waves with few iterations per
+// CTA, so that the two kinds stream through the SMs at their own rates and no CTA waits for its slower half.
+template <int DPB, int MINB>
+__global__ void __launch_bounds__(256, MINB) bench_mixed_cta(uint32_t* out, int iters) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = ((tid & 0xffffu) * 2654435761u + i * 40503u) % P;
+  if ((int)(blockIdx.x & 7u) < DPB) {
+    double d[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) d[i] = p2d::from_monty_word(s[i]);
+    for (int it = 0; it < iters; it++) p2d::permute(d);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = p2d::to_monty_word(d[i]);
+  } else {
+    for (int it = 0; it < iters; it++) permute_rolled<MulSigned, 1, 3, 1, 0>(s, 0);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc ^= s[i] + i;
+  out[tid & 0xfffffu] = acc;
+}
+template <int DPB, int MINB>
+void run_mixed_cta(const char* name, uint32_t* d_out, int sms) {
+  int iters = 8, occ = 0, waves = 48;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, bench_mixed_cta<DPB, MINB>);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench_mixed_cta<DPB, MINB>, 256, 0);
+  int blocks = sms * occ * waves;
+  bench_mixed_cta<DPB, MINB><<<blocks, 256>>>(d_out, 1);
+  cudaDeviceSynchronize();
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e9;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(a);
+    bench_mixed_cta<DPB, MINB><<<blocks, 256>>>(d_out, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  double perms = (double)blocks * 256 * iters;
+  printf("%-28s regs=%3d occ=%d blocks/SM  %.3f ms  %.2f Gperm/s  %.1f clk/perm/SM@1.9GHz err=%s\n", name, fa.numRegs, occ, best,
+         perms / best / 1e6, best * 1e-3 * 1.9e9 * sms / perms, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int DPW, int MINB>
 void run_mixed(const char* name, uint32_t* d_out, uint32_t* h_ref, int sms) {
   int iters = 128, occ = 0;
@@ -343,7 +391,7 @@ int main(int argc, char** argv) {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int sms = p.multiProcessorCount;
   printf("%s, %d SMs\n", p.name, sms);
-  uint32_t* d; cudaMalloc(&d, (size_t)sms * 16 * 256 * 2 * 4);
+  uint32_t* d; cudaMalloc(&d, (size_t)(1u << 20) * 4 + (size_t)sms * 16 * 256 * 2 * 4);
   uint32_t ref[1] = {0xffffffffu};
 #define RUNM(...) if (idx++, only == -1 || only == -2 || only == idx - 1) run_mixed<__VA_ARGS__>
   RUN(MulSigned, 1, 1, 1, 41)("signed roll-all one-ext-body", d, ref, sms);   // the product's integer permutation: reference result
@@ -356,6 +404,17 @@ int main(int argc, char** argv) {
   RUNM(4, 3)("mixed 4/8 fp64 warps minb3", d, ref, sms);
   RUNM(4, 4)("mixed 4/8 fp64 warps minb4", d, ref, sms);
   RUNM(3, 4)("mixed 3/8 fp64 warps minb4", d, ref, sms);
+#define RUNC(...) if (idx++, only == -1 || only == -2 || only == idx - 1) run_mixed_cta<__VA_ARGS__>
+  RUNC(0, 4)("cta-mix 0/8 fp64 CTAs minb4", d, sms);
+  RUNC(8, 4)("cta-mix 8/8 fp64 CTAs minb4", d, sms);
+  RUNC(2, 4)("cta-mix 2/8 fp64 CTAs minb4", d, sms);
+  RUNC(3, 4)("cta-mix 3/8 fp64 CTAs minb4", d, sms);
+  RUNC(4, 4)("cta-mix 4/8 fp64 CTAs minb4", d, sms);
+  RUNC(5, 4)("cta-mix 5/8 fp64 CTAs minb4", d, sms);
+  RUNC(3, 3)("cta-mix 3/8 fp64 CTAs minb3", d, sms);
+  RUNC(4, 3)("cta-mix 4/8 fp64 CTAs minb3", d, sms);
+  RUNC(3, 5)("cta-mix 3/8 fp64 CTAs minb5", d, sms);
+  RUNC(4, 5)("cta-mix 4/8 fp64 CTAs minb5", d, sms);
   if (only == -2) return 0;   // p2bench -2: only the mixes above
   RUN(MulSub, 0, 1, 1)("sub/diagmul", d, ref, sms);
   RUN(MulSub, 1, 1, 1)("sub/diagshift", d, ref, sms);
