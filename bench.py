@@ -261,13 +261,20 @@ def exec_shard_leg(ctx, torch, args):
 NUM_PV = 8  # StarkMachine::num_pv_elts of the synthetic machine
 
 
+FRI_PARAMS = {"recursion": (2, 42, 16)}  # compressed_fri_config (kb31_poseidon2.rs:216-227); default (1, 84, 16)
+
+
 def shard_chips(config, rank=0, scale=0):
     """The synthetic shard of metric 2 (heights scaled down by 2^scale for the CPU leg's bounded sample).
     mixed : wide_bitwise_1024 2^16, wide_bitwise_64 2^18, Fibonacci 2^20 and a balanced LogUp pair at 2^18 (88 M cells:
             between a maximal log-17 and log-18 execution shard, SURVEY A.11);
     keccak: BASELINE config 3, wide_bitwise_4096 at 2^16 rows (6144 degree-3 constraints) + Fibonacci 2^16;
     large : wide_bitwise_1024 2^19, wide_bitwise_64 2^21, Fibonacci 2^21, LogUp pair 2^20 (6.8e8 cells: a maximal
-            log-21 execution shard's size)."""
+            log-21 execution shard's size);
+    recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:93-103: 2^18, 2^18,
+            2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries), with
+            this library's AIRs standing in for the RecursionAir chips (the real AddSub / Lt / Bitwise chips among them):
+            many small matrices, latency-bound."""
     from zkmips_b200 import synth
     d = scale
     if config == "keccak":
@@ -276,6 +283,15 @@ def shard_chips(config, rank=0, scale=0):
         send, recv = synth.lookup_side_chips(20 - d, seed=9 + rank)
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
+    if config == "recursion":
+        send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
+        send.name, recv.name = "MemoryVar", "Select"
+        return [send, recv, synth.local_bool_chip(16 - d, seed=3 + rank, name="MemoryConst"),
+                synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI"), synth.add_sub_chip(15 - d, seed=5 + rank, name="BaseAlu"),
+                synth.bitwise_chip(15 - d, seed=6 + rank, name="ExtAlu"),
+                synth.wide_chip(17 - d, 64, seed=7 + rank, name="ExpReverseBitsLen"),
+                synth.wide_chip(16 - d, 256, seed=8 + rank, name="Poseidon2Wide"),
+                synth.fibonacci_chip(max(4 - d, 2), 1 + rank, 1, name="PublicValues")]
     send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
     return [synth.wide_chip(16 - d, 1024, seed=11 + rank), synth.wide_chip(18 - d, 64, seed=12 + rank),
             synth.fibonacci_chip(20 - d, 1 + rank, 1), send, recv]
@@ -292,11 +308,11 @@ class ShardWorker:
     """One in-flight shard slot of a GPU: its own context (stream, pool, slab buffers) and prover; the proving key is
     committed ONCE per context (pk_to_device, prover.rs:63) and every shard gets a clone of the machine challenger."""
 
-    def __init__(self, ctx, chips):
+    def __init__(self, ctx, chips, fri=(1, 84, 16)):
         from zkmips_b200 import Challenger, synth
         from zkmips_b200.prover import GpuShardProver
         self.ctx = ctx
-        self.prover = GpuShardProver(ctx, 1, 84, 16, num_pv_elts=NUM_PV)
+        self.prover = GpuShardProver(ctx, fri[0], fri[1], fri[2], num_pv_elts=NUM_PV)
         self.pk = self.prover.setup(chips)
         ch = Challenger(ctx)
         self.pk.observe_into(ch)
@@ -321,7 +337,8 @@ def shard_leg(ctx, torch, dist, world, rank, args):
 
     chips = _pin(torch, shard_chips(args.shard_config, rank))
     cells = sum(c.main.size for c in chips)
-    w1 = ShardWorker(ctx, chips)
+    fri = FRI_PARAMS.get(args.shard_config, (1, 84, 16))
+    w1 = ShardWorker(ctx, chips, fri)
     sp = w1.prove(chips)  # warm-up (also pages the generated quotient kernels in)
     w1.prover.phase_ms = {}  # host phase clocks of the timed steps only
     ctx.prof_reset()
@@ -348,9 +365,12 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     # queue, shard i on rank i mod N, TWO shards in flight per GPU (the reference keeps shard_batch_size shards in
     # flight, prove.rs:487-521): a second context on its own stream, driven by a second host thread, uploads and
     # commits shard i+1 while shard i is in its latency-bound open phase.  Strong scaling: S is fixed as N grows.
-    ctx2 = ctx.lib.ctx_create(torch.cuda.current_device())
-    w2 = ShardWorker(ctx2, chips)
-    w2.prove(chips)  # warm-up of the second context
+    workers = [w1]
+    for _ in range(args.in_flight - 1):
+        cx = ctx.lib.ctx_create(torch.cuda.current_device())
+        wk = ShardWorker(cx, chips, fri)
+        wk.prove(chips)  # warm-up of the extra context
+        workers.append(wk)
     S = args.multi_shards
     mine = list(range(rank, S, world))
     jobs = queue.Queue()
@@ -370,7 +390,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
         dist.barrier()
     torch.cuda.synchronize()
     t = time.perf_counter()
-    th = [threading.Thread(target=worker, args=(w,)) for w in (w1, w2)]
+    th = [threading.Thread(target=worker, args=(w,)) for w in workers]
     for x in th:
         x.start()
     for x in th:
@@ -384,16 +404,17 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     from zkmips_b200 import proof as pf
     blob = pf.to_bincode(sp)
     assert all(pf.to_bincode(p) == blob for p in proofs.values()), "shards of the queue differ from the serial proof"
-    w2.pk.data and w2.pk.data.free()
-    ctx2.destroy()
+    for wk in workers[1:]:
+        wk.pk.data and wk.pk.data.free()
+        wk.ctx.destroy()
     res = {"config": args.shard_config, "ms_per_shard": dt * 1e3, "shards_per_s": world / dt,
            "trace_cells_per_shard": int(cells),
            "chips": [f"{c.name}: 2^{c.log_degree} x {c.main.shape[1]}" for c in w1.prover.order(chips)],
-           "params": "log_blowup 1, 84 queries, 16 PoW bits; reference transcript (prover.rs:298-653)",
+           "params": f"log_blowup {fri[0]}, {fri[1]} queries, {fri[2]} PoW bits; reference transcript (prover.rs:298-653)",
            "timing": "host wall clock around commit+open, max over ranks",
            "proof_bytes_bincode": len(blob), "host_phase_ms": phases,
            "device_stage_ms": {k: round(v, 3) for k, v in stage.items()},
-           "multi_shard": {"shards": S, "shards_in_flight_per_gpu": 2, "placement": "shard i -> rank i mod N",
+           "multi_shard": {"shards": S, "shards_in_flight_per_gpu": args.in_flight, "placement": "shard i -> rank i mod N",
                            "seconds": dtm, "shards_per_s": S / dtm, "cells_per_s": S * cells / dtm, "scaling": "strong",
                            "h2d_bytes_per_shard": int(4 * cells)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -416,7 +437,8 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
     scale = 4
     while True:
         chips = shard_chips(args.shard_config, 0, scale)
-        op = osp.OracleShardProver(airs, 1, 84, 16, num_pv_elts=NUM_PV)
+        fri = FRI_PARAMS.get(args.shard_config, (1, 84, 16))
+        op = osp.OracleShardProver(airs, fri[0], fri[1], fri[2], num_pv_elts=NUM_PV)
         from zkmips_b200 import synth
         pvs = synth.public_values_for(chips, NUM_PV)
         opk = op.setup(chips)
@@ -430,7 +452,7 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
         scale -= 1 if dt > 2.0 else 2
         scale = max(scale, 0)
     cells = sum(c.main.size for c in chips)
-    w = ShardWorker(ctx, chips)
+    w = ShardWorker(ctx, chips, fri)
     t = time.perf_counter()
     sp = w.prove(chips)
     gpu_dt = time.perf_counter() - t
@@ -458,7 +480,8 @@ def main():
     ap.add_argument("--no-shard", action="store_true", help="skip the shard-prove leg (commit + quotient + open)")
     ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
-    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large"],
+    ap.add_argument("--in-flight", type=int, default=2, help="shards in flight per GPU in the multi-shard leg (contexts)")
+    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion"],
                     help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 + LogUp pair 2^18 (88 M cells); keccak: BASELINE "
                          "config 3, one 2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells); "
                          "large: 6.8e8 cells, the size of a maximal log-21 execution shard")

@@ -283,6 +283,7 @@ def lt():
 
 
 def all_airs():
-    return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(1024, "wide_bitwise_1024"),
+    return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
+            wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise()]
