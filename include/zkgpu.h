@@ -115,6 +115,9 @@ int32_t zk_pdata_root(const zk_pdata* pd, uint32_t root[8]);
 /* Pcs::get_evaluations_on_domain (crates/stark/src/prover.rs:437-445): the committed LDE, no copy.
  * Row r of the returned matrix is the evaluation at GENERATOR * g^bitrev(r). */
 zk_dptr zk_pdata_lde(const zk_pdata* pd, uint32_t i);
+/* row stride of that matrix in WORDS: the width rounded up to even (rows of a committed LDE start 8-byte aligned, so
+ * that 47-, 115-, 119-column chips take the same vector paths as even widths); columns >= width are padding. */
+uint32_t zk_pdata_pitch(const zk_pdata* pd, uint32_t i);
 /* the retained input trace (natural order, height >> log_blowup rows), or 0 when traces were not kept */
 zk_dptr zk_pdata_trace(const zk_pdata* pd, uint32_t i);
 /* Mmcs::get_matrices / Serialize support: copy an LDE matrix or a digest layer (0 = leaves) to the host. */

@@ -131,6 +131,8 @@ class ProverData {
   }
   // Pcs::get_evaluations_on_domain: device view of the LDE, no copy
   zk_dptr evaluations_on_domain(uint32_t i) const { return zk_pdata_lde(raw(), i); }
+  // row stride of that view in words (odd widths are padded to even)
+  uint32_t pitch(uint32_t i) const { return zk_pdata_pitch(raw(), i); }
 
  private:
   std::shared_ptr<zk_pdata> p_;

@@ -85,6 +85,7 @@ extern "C-unwind" {
     pub fn zk_pdata_log_max_height(pd: *const ZkPdata) -> u32;
     pub fn zk_pdata_root(pd: *const ZkPdata, root: *mut u32) -> i32;
     pub fn zk_pdata_lde(pd: *const ZkPdata, i: u32) -> ZkDptr;
+    pub fn zk_pdata_pitch(pd: *const ZkPdata, i: u32) -> u32;
     pub fn zk_pdata_trace(pd: *const ZkPdata, i: u32) -> ZkDptr;
     pub fn zk_pdata_copy_lde(pd: *const ZkPdata, i: u32, out_host: *mut u32) -> i32;
     pub fn zk_pdata_copy_layer(pd: *const ZkPdata, layer: u32, out_host: *mut u32) -> i32;

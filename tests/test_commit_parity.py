@@ -338,3 +338,43 @@ def test_prover_data_export_import_round_trip(be):
     ctx.destroy()      # deferred: pd2 is still alive
     assert pd2.num_matrices() == 4
     pd2.free()         # the last handle tears the context down
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_even_pitch_of_odd_width_ldes(be, monkeypatch):
+    """Committed LDEs of odd width carry one padding column (rows start 8-byte aligned: the two-column NTT kernels and
+    64-bit loads then apply to 47-, 115-, 119-column chips).  The padding is invisible: same root, same digest layers,
+    same exported LDE and same openings as the dense layout (ZK_EVEN_PITCH=0) and as the oracle -- from host memory
+    (streamed slabs, retained traces) and from device-resident traces."""
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    lib = native.load() if be == "gpu" else native.load(backends.build_emu())
+    one = ob.lib().ork_to_monty(1)
+    logs = (6, 6, 4) if be == "emu" else (12, 12, 9)
+    mats = [_mont(1 << logs[0], 47, seed=401), _mont(1 << logs[1], 119, seed=402), _mont(1 << logs[2], 5, seed=403),
+            _mont(1 << logs[2], 8, seed=404)]
+    tree = ob.pcs_commit(mats, 1, [one] * len(mats))
+    results = []
+    for even in ("1", "0"):
+        monkeypatch.setenv("ZK_EVEN_PITCH", even)
+        ctx = lib.ctx_create(0)
+        ctx.keep_traces(True)
+        try:
+            root, pd = ctx.commit(mats, [one] * len(mats), 1)
+            assert [pd.pitch(i) for i in range(4)] == ([48, 120, 6, 8] if even == "1" else [47, 119, 5, 8])
+            assert (root == tree.root).all()
+            for i, m in enumerate(mats):
+                assert (pd.lde(i) == tree.matrix(i)).all()
+                assert (ctx.download(pd.trace_ptr(i), m.shape) == m).all()
+            idx = [0, 3, (1 << (logs[0] + 1)) - 1]
+            results.append(pd.open_batch(idx))
+            pd.free()
+            dptrs = [ctx.upload(m) for m in mats]
+            root2, pd2 = ctx.commit_dev(dptrs, [m.shape for m in mats], [one] * len(mats), 1)
+            assert (root2 == tree.root).all() and (pd2.lde(1) == tree.matrix(1)).all()
+            pd2.free()
+            for p in dptrs:
+                ctx.dev_free(p)
+        finally:
+            ctx.destroy()
+    assert (results[0][0] == results[1][0]).all() and (results[0][1] == results[1][1]).all()

@@ -145,7 +145,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
       const zk_pdata* pd = rounds[r];
       for (uint32_t m = 0; m < pd->n; m++, k++) {
         uint64_t H = pd->heights[m];
-        uint32_t w = pd->widths[m];
+        uint32_t w = pd->widths[m], pitch = pd->pitches[m];
         uint32_t L = kbh::log2_exact(H), n = L - log_blowup;
         if (!ro[L]) {
           RC(sc.alloc(&ro[L], H * 16));
@@ -157,10 +157,11 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
         }
         uint32_t gL = kbh::two_adic_generator(L), gn = kbh::two_adic_generator(n);
         if (w >= 64)
-          ZK_LAUNCH_COOP(fri::row_reduce_warp_kernel, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, d_apow_split,
-                         d_rowred);
+          ZK_LAUNCH_COOP(fri::row_reduce_warp_kernel, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch,
+                         d_apow_split, d_rowred);
         else
-          ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, d_apow_split, d_rowred);
+          ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split,
+                         d_rowred);
         c->launches++;
         for (uint32_t p0 = 0; p0 < n_points[k]; p0 += 2) {
           uint32_t np = std::min(2u, n_points[k] - p0);
@@ -168,16 +169,18 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
           uint32_t nchunks = (uint32_t)((N + fri::BARY_ROWS - 1) / fri::BARY_ROWS);
           ZK_LAUNCH(fri::bary_weights_kernel, (unsigned)((N + 255) / 256), 256, 0, st, pt, np, n, gn, d_wts);
           {
-            const uint32_t cpl = ((w & 1u) == 0 && ((uintptr_t)pd->mats[m] % 8) == 0) ? 2 : 1;
+            // two columns per lane need 8-byte aligned rows: an even PITCH (odd widths are padded), the lane past the
+            // last column accumulates the padding column and drops it
+            const uint32_t cpl = ((pitch & 1u) == 0 && ((uintptr_t)pd->mats[m] % 8) == 0) ? 2 : 1;
             uint32_t log_cw = 0;
             while (log_cw < 5 && (cpl << log_cw) < w) log_cw++;
             const uint32_t ntile = (w + (cpl << log_cw) - 1) / (cpl << log_cw);
             if (cpl == 2) {
               auto kfn = fri::bary_partial_kernel<2>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, d_wts, np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, d_wts, np, log_cw, d_partial);
             } else {
               auto kfn = fri::bary_partial_kernel<1>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, d_wts, np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, d_wts, np, log_cw, d_partial);
             }
           }
           ZK_LAUNCH_COOP(fri::bary_final_kernel, w, 128, 0, st, d_partial, nchunks, w, n, pt, np, out);

@@ -158,11 +158,11 @@ __device__ __forceinline__ uint32_t lde_point(uint32_t r, uint32_t L, uint32_t g
 // rowred[r] = sum_j alpha^j m[r][j]   (Matrix::dot_ext_powers).  One thread per row; split alpha powers in smem.
 constexpr int RR_CHUNK = 512;  // alpha powers staged per pass
 __global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
-                                                         const uint32_t* __restrict__ apow_split,
+                                                         uint32_t pitch, const uint32_t* __restrict__ apow_split,
                                                          uint32_t* __restrict__ rowred) {
   __shared__ uint4 sp[RR_CHUNK * 2];
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t* row = mat + (r < H ? r : 0) * w;
+  const uint32_t* row = mat + (r < H ? r : 0) * pitch;
   Acc4 acc;
   acc.zero();
   for (uint32_t c0 = 0; c0 < w; c0 += RR_CHUNK) {
@@ -182,12 +182,12 @@ __global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restr
 // Same for wide matrices: one WARP per row, lanes stride the columns (coalesced), partial sums combined with
 // shuffles.  The thread-per-row form above leaves most of the machine idle when the LDE has few, long rows.
 __global__ void __launch_bounds__(256) row_reduce_warp_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
-                                                              const uint32_t* __restrict__ apow_split,
+                                                              uint32_t pitch, const uint32_t* __restrict__ apow_split,
                                                               uint32_t* __restrict__ rowred) {
   const uint32_t lane = threadIdx.x & 31;
   uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= H) return;
-  const uint32_t* row = mat + r * w;
+  const uint32_t* row = mat + r * pitch;
   const uint4* A = reinterpret_cast<const uint4*>(apow_split);
   Acc4 acc;
   acc.zero();
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __res
 constexpr int BARY_ROWS = 2048;  // rows per chunk
 template <int CPL>
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
-                                                           const uint32_t* __restrict__ wts, uint32_t npts, uint32_t log_cw,
-                                                           uint32_t* __restrict__ partial) {
+                                                           uint32_t pitch, const uint32_t* __restrict__ wts, uint32_t npts,
+                                                           uint32_t log_cw, uint32_t* __restrict__ partial) {
   __shared__ uint32_t red[2 * CPL * 4][256];
   const uint32_t cw = 1u << log_cw, nrl = 256u >> log_cw;
   const uint32_t lane = threadIdx.x & (cw - 1), rl = threadIdx.x >> log_cw;
@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
     for (uint64_t r = r0 + rl; r < r1; r += nrl) {
       uint32_t v[CPL];
       if constexpr (CPL == 2) {
-        uint2 x = __ldg(reinterpret_cast<const uint2*>(mat + r * w + col));
+        uint2 x = __ldg(reinterpret_cast<const uint2*>(mat + r * pitch + col));
         v[0] = x.x;
         v[1] = x.y;
       } else {
-        v[0] = __ldg(mat + r * w + col);
+        v[0] = __ldg(mat + r * pitch + col);
       }
 #pragma unroll
       for (int p = 0; p < 2; p++) {

@@ -21,6 +21,7 @@ namespace mk {
 struct MatDesc {
   const uint32_t* ptr;
   uint32_t w;
+  uint32_t pitch;  // row stride in words
 };
 
 __device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&s)[16]) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) hash_rows_multi(const MatDesc* __restrict
   for (int i = 0; i < 16; i++) s[i] = 0;
   uint32_t mi = 0, c = 0;
   while (mi < gn && gm[mi].w == 0) mi++;
-  const uint32_t* row = mi < gn ? gm[mi].ptr + r * gm[mi].w : nullptr;
+  const uint32_t* row = mi < gn ? gm[mi].ptr + r * gm[mi].pitch : nullptr;
   while (mi < gn) {
     uint32_t got = 0;
 #pragma unroll
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) hash_rows_multi(const MatDesc* __restrict
           c = 0;
           mi++;
           while (mi < gn && gm[mi].w == 0) mi++;
-          if (mi < gn) row = gm[mi].ptr + r * gm[mi].w;
+          if (mi < gn) row = gm[mi].ptr + r * gm[mi].pitch;
         }
       }
     }

@@ -43,13 +43,15 @@ extern "C" int32_t zk_air_info(int32_t id, zk_air_desc* out) {
 }
 
 static int32_t lde_of(const zk_pdata* pd, uint32_t idx, uint32_t want_w, uint64_t want_h, const char* what,
-                      const uint32_t** ptr) {
+                      const uint32_t** ptr, uint32_t* pitch) {
   *ptr = nullptr;
+  *pitch = want_w;
   if (want_w == 0) return ZK_OK;
   if (!pd || idx >= pd->n) return zk_fail(ZK_ERR_ARG, std::string(what) + " trace is required by this AIR");
   if (pd->widths[idx] != want_w) return zk_fail(ZK_ERR_ARG, std::string(what) + " trace has the wrong width");
   if (pd->heights[idx] < want_h) return zk_fail(ZK_ERR_ARG, std::string(what) + " LDE is shorter than the quotient domain");
   *ptr = pd->mats[idx];
+  *pitch = pd->pitches[idx];
   return ZK_OK;
 }
 
@@ -68,12 +70,9 @@ extern "C" int32_t zk_quotient(zk_ctx* c, int32_t air_id, const zk_pdata* prep, 
   quot::Args A;
   memset(&A, 0, sizeof A);
   int32_t rc;
-  if ((rc = lde_of(prep, prep_idx, e.prep_w, qsize, "preprocessed", &A.prep))) return rc;
-  if ((rc = lde_of(main_pd, main_idx, e.main_w, qsize, "main", &A.main))) return rc;
-  if ((rc = lde_of(perm, perm_idx, 4 * e.perm_w, qsize, "permutation", &A.perm))) return rc;
-  A.wp = e.prep_w;
-  A.wm = e.main_w;
-  A.wq = 4 * e.perm_w;
+  if ((rc = lde_of(prep, prep_idx, e.prep_w, qsize, "preprocessed", &A.prep, &A.wp))) return rc;
+  if ((rc = lde_of(main_pd, main_idx, e.main_w, qsize, "main", &A.main, &A.wm))) return rc;
+  if ((rc = lde_of(perm, perm_idx, 4 * e.perm_w, qsize, "permutation", &A.perm, &A.wq))) return rc;
   A.log_n = log_degree;
   A.lqd = log_quotient_degree;
   A.g_q = kbh::two_adic_generator(log_degree + log_quotient_degree);

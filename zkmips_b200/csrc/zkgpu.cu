@@ -52,7 +52,7 @@ __global__ void open_gather_kernel(const zk_open_desc* __restrict__ mats, uint32
   for (uint32_t m = 0; m < n_mats; m++) {
     zk_open_desc d = mats[m];
     uint64_t r = index >> (log_max - d.log_h);
-    const uint32_t* row = d.ptr + r * d.w;
+    const uint32_t* row = d.ptr + r * d.pitch;
     for (uint32_t c = threadIdx.x; c < d.w; c += blockDim.x) o[d.off + c] = row[c];
   }
   uint32_t* p = proofs + (size_t)blockIdx.x * proofs_stride;
@@ -89,6 +89,7 @@ static int32_t ctx_init(zk_ctx* c) {
     if (v >= 1) c->slab_bytes = (uint64_t)v << 20;
   }
   if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
+  if (const char* e = getenv("ZK_EVEN_PITCH")) c->even_pitch = atoi(e) != 0;  // 0: dense LDEs (A/B measurements)
   if (const char* e = getenv("ZK_HASH_VEC_MIN_ROWS")) c->hash_vec_min_rows = strtoull(e, nullptr, 10);
   // a private stream-ordered pool per context: contexts that prove shards concurrently on one GPU must not
   // couple their streams through cross-stream reuse of freed blocks in the device's default pool
@@ -329,15 +330,24 @@ static int32_t check_lde_shape(zk_ctx* c, uint64_t h, uint32_t log_blowup) {
   return ZK_OK;
 }
 
+// dst[r * pitch + col] = 0 for every row: the padding column of an odd-width matrix
+__global__ void __launch_bounds__(256) zero_col_kernel(uint32_t* __restrict__ dst, uint32_t pitch, uint32_t col, uint64_t h) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < h) dst[r * pitch + col] = 0u;
+}
+
 // LDE of `nc` columns.  `coef` receives the (bit-reversed, unscaled) coefficients and may alias `in` (the
 // inverse transform then runs in place); the 2^b blocks go to out.ptr + t*h*out.w, columns [out.c0, out.c0+nc).
+// The inverse transform covers nc_inv columns and the coset transforms nc columns (nc_inv < nc when the caller has
+// zeroed padding columns of `coef` itself).
 static int32_t lde_cols(zk_ctx* c, ntt::Cols in, ntt::Cols coef, ntt::Cols out, uint32_t nc, uint64_t h,
-                        uint32_t log_blowup, const std::vector<ntt::CosetScale>& scales) {
+                        uint32_t log_blowup, const std::vector<ntt::CosetScale>& scales, uint32_t nc_inv = ~0u) {
   if (nc == 0) return ZK_OK;
+  if (nc_inv == ~0u) nc_inv = nc;
   uint32_t n = kbh::log2_exact(h);
   {
     ProfScope ps(c, "idft");
-    CK(ntt::transform(in, coef, nc, n, ntt::DIR_INV, c->tw[1], c->log_L, nullptr, false, c->stream));
+    CK(ntt::transform(in, coef, nc_inv, n, ntt::DIR_INV, c->tw[1], c->log_L, nullptr, false, c->stream));
     c->launches += num_passes(n);
   }
   for (uint32_t t = 0; t < (1u << log_blowup); t++) {
@@ -350,33 +360,42 @@ static int32_t lde_cols(zk_ctx* c, ntt::Cols in, ntt::Cols coef, ntt::Cols out, 
 }
 
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                uint32_t* out) {
+                uint32_t* out, uint32_t out_pitch) {
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
   if (w == 0) return ZK_OK;
+  if (out_pitch < w) return zk_fail(ZK_ERR_ARG, "output pitch below the width");
   DevScope ds(c);
   uint32_t* coef = nullptr;
   std::vector<ntt::CosetScale> scales;
-  if ((rc = ds.alloc(&coef, h * w * 4ull))) return rc;
-  const bool aligned = (w & 1u) == 0 && ((uintptr_t)in % 8) == 0 && ((uintptr_t)out % 8) == 0;
-  rc = lde_scales(c, h, log_blowup, shift, aligned, scales);
+  // the coefficient buffer takes the output's pitch: with an odd width the inverse transform reads the caller's dense
+  // (odd-pitch) matrix one column per thread, but the 2^b coset transforms -- two thirds of the work -- run on even
+  // pitches, padding column included (zero coefficients in, zeros out)
+  const uint32_t ncf = std::min(out_pitch, lde_pitch(w));
+  if ((rc = ds.alloc(&coef, h * (uint64_t)ncf * 4))) return rc;
+  if (ncf > w) {
+    ZK_LAUNCH(zero_col_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, coef, ncf, w, h);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  rc = lde_scales(c, h, log_blowup, shift, true, scales);
   if (rc == ZK_OK)
-    rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, w, 0}, ntt::Cols{out, w, 0}, w, h,
-                  log_blowup, scales);
+    rc = lde_cols(c, ntt::Cols{const_cast<uint32_t*>(in), w, 0}, ntt::Cols{coef, ncf, 0}, ntt::Cols{out, out_pitch, 0}, ncf,
+                  h, log_blowup, scales, w);
   free_scales(c, scales);  // also after a partial failure of lde_scales
   return rc;
 }
 
 static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t h, uint32_t* out);
 
-// dst[r * dpitch + j] = src[r * nc + j], j < nc: a column slab back into its place in the row-major retained trace
+// dst[r * dpitch + j] = src[r * spitch + j], j < nc: a column slab back into its place in the row-major retained trace
 template <class T>
 __global__ void __launch_bounds__(256) scatter_cols_kernel(const T* __restrict__ src, T* __restrict__ dst, uint32_t nc,
-                                                           uint32_t dpitch, uint64_t total) {
+                                                           uint32_t spitch, uint32_t dpitch, uint64_t total) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t r = i / nc;
     uint32_t j = (uint32_t)(i - r * nc);
-    dst[r * dpitch + j] = src[i];
+    dst[r * dpitch + j] = src[r * spitch + j];
   }
 }
 
@@ -443,7 +462,7 @@ static int32_t absorb_slab(zk_ctx* c, const uint32_t* lde, uint32_t pitch, uint3
 }
 
 static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                               uint32_t* out, ClassStream* cs, bool last_member, uint32_t* keep_trace) {
+                               uint32_t* out, uint32_t out_pitch, ClassStream* cs, bool last_member, uint32_t* keep_trace) {
   int32_t rc = check_lde_shape(c, h, log_blowup);
   if (rc) return rc;
   if (w == 0) return (cs && last_member) ? absorb_slab(c, nullptr, 0, 0, 0, h << log_blowup, *cs, true) : ZK_OK;
@@ -458,8 +477,8 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     uint32_t* stage = keep_trace;
     if (!stage && (rc = dev_alloc(c, h * w * 4ull, (void**)&stage))) return rc;
     CK(cudaMemcpyAsync(stage, host, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
-    rc = lde_dev(c, stage, h, w, log_blowup, shift, out);
-    if (rc == ZK_OK && cs) rc = absorb_slab(c, out, w, 0, w, H, *cs, last_member);
+    rc = lde_dev(c, stage, h, w, log_blowup, shift, out, out_pitch);
+    if (rc == ZK_OK && cs) rc = absorb_slab(c, out, out_pitch, 0, w, H, *cs, last_member);
     if (!keep_trace) dev_free(c, stage);
     return rc;
   }
@@ -504,47 +523,55 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // sized by the WIDEST slab of the schedule, not by the nominal `slab`: equal-width cuts round down to a multiple of
   // 8 columns and hand the remainder to the last slab (300 columns -> 72, 72, 72, 84 with slab = 80), and a matrix
   // whose width rounds to one slab goes up whole (68 or 90 columns with slab = 64)
+  // (cuts are multiples of 8 columns, so only the LAST slab of an odd-width matrix has an odd width; it gets one
+  // padding column in the slab buffer -- zeroed, transformed along -- which lands in the padding column of the LDE)
   uint32_t widest = 0;
-  for (uint32_t k = 0; k < nslab; k++) widest = std::max(widest, cuts[k + 1] - cuts[k]);
+  for (uint32_t k = 0; k < nslab; k++) widest = std::max(widest, lde_pitch(cuts[k + 1] - cuts[k]));
   if ((rc = ensure_slab_bufs(c, h * (uint64_t)widest * 4))) {
     free_scales(c, scales);
     return rc;
   }
   for (uint32_t k = 0; k < nslab && rc == ZK_OK; k++) {
     const uint32_t b = (uint32_t)(c->slab_seq++ % zk_ctx::NSLAB), c0 = cuts[k], nc = cuts[k + 1] - c0;
+    const uint32_t ncp = (c0 + lde_pitch(nc) <= out_pitch) ? lde_pitch(nc) : nc;  // slab pitch = columns transformed
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
-    if (nc == w)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
+    if (nc == w && ncp == nc)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
       CK(cudaMemcpyAsync(buf, host, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
     else
-      CK(cudaMemcpy2DAsync(buf, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+      CK(cudaMemcpy2DAsync(buf, (size_t)ncp * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
                            c->copy_stream));
     CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
+    if (ncp > nc) {
+      ZK_LAUNCH(zero_col_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, buf, ncp, nc, h);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
     if (keep_trace) {  // retain the slab before the in-place inverse transform overwrites it
-      if (nc == w) {
+      if (nc == w && ncp == nc) {
         CK(cudaMemcpyAsync(keep_trace, buf, (size_t)h * w * 4, cudaMemcpyDeviceToDevice, c->stream));
       } else {
         // a kernel, not cudaMemcpy2DAsync: 2-D copies are issued row by row (2^20 rows of 8 bytes: 100 ms; the slabs
         // of a 3.2 GB execution shard: 22 ms), and uploading straight into the strided destination is slower still
-        const bool v4 = ((nc | w | c0) & 3u) == 0;
+        const bool v4 = ((nc | w | c0 | ncp) & 3u) == 0;
         const uint64_t total = (uint64_t)h * (v4 ? nc / 4 : nc);
         const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32);
         if (v4)
           ZK_LAUNCH(scatter_cols_kernel<uint4>, blocks, 256, 0, c->stream, reinterpret_cast<const uint4*>(buf),
-                    reinterpret_cast<uint4*>(keep_trace + c0), nc / 4, w / 4, total);
+                    reinterpret_cast<uint4*>(keep_trace + c0), nc / 4, ncp / 4, w / 4, total);
         else
-          ZK_LAUNCH(scatter_cols_kernel<uint32_t>, blocks, 256, 0, c->stream, buf, keep_trace + c0, nc, w, total);
+          ZK_LAUNCH(scatter_cols_kernel<uint32_t>, blocks, 256, 0, c->stream, buf, keep_trace + c0, nc, ncp, w, total);
         CK(cudaGetLastError());
         c->launches++;
       }
     }
-    ntt::Cols sl{buf, nc, 0};
-    rc = lde_cols(c, sl, sl, ntt::Cols{out, w, c0}, nc, h, log_blowup, scales);
+    ntt::Cols sl{buf, ncp, 0};
+    rc = lde_cols(c, sl, sl, ntt::Cols{out, out_pitch, c0}, ncp, h, log_blowup, scales);
     if (rc) break;
     CK(cudaEventRecord(c->slab_free[b], c->stream));
     c->slab_used[b] = true;
-    if (cs && (rc = absorb_slab(c, out, w, c0, nc, H, *cs, last_member && k + 1 == nslab))) break;
+    if (cs && (rc = absorb_slab(c, out, out_pitch, c0, nc, H, *cs, last_member && k + 1 == nslab))) break;
   }
   free_scales(c, scales);
   return rc;
@@ -557,7 +584,7 @@ static int32_t hash_group(zk_ctx* c, const std::vector<mk::MatDesc>& g, uint64_t
   // fewer than ~3 resident CTAs of 256 threads per SM: use 128-thread CTAs so the rows spread evenly over the SMs
   const unsigned bs = h < (1ull << 19) ? 128 : 256;
   unsigned blocks = (unsigned)((h + bs - 1) / bs);
-  if (g.size() == 1 && g[0].w % 8 == 0 && g[0].w > 0 && ((uintptr_t)g[0].ptr % 32) == 0) {
+  if (g.size() == 1 && g[0].w % 8 == 0 && g[0].w > 0 && g[0].pitch == g[0].w && ((uintptr_t)g[0].ptr % 32) == 0) {
     ZK_LAUNCH(mk::hash_rows_w8, blocks, bs, 0, c->stream, g[0].ptr, g[0].w, h, out);
   } else {
     mk::MatDesc* d = nullptr;
@@ -612,7 +639,7 @@ int32_t mmcs_advance(zk_ctx* c, zk_pdata* pd, TreeProgress& tp, const std::map<u
     g.clear();
     for (uint32_t k = 0; k < n; k++) {
       uint32_t m = pd->order[k];
-      if (pd->heights[m] == height) g.push_back(mk::MatDesc{pd->mats[m], pd->widths[m]});
+      if (pd->heights[m] == height) g.push_back(mk::MatDesc{pd->mats[m], pd->widths[m], pd->pitches[m]});
     }
   };
   if (!tp.leaves) {
@@ -684,7 +711,7 @@ int32_t mmcs_build(zk_ctx* c, zk_pdata* pd, bool fetch_root, bool leaves_done, b
     std::vector<zk_open_desc> od(n);
     uint32_t off = 0;
     for (uint32_t i = 0; i < n; i++) {
-      od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
+      od[i] = zk_open_desc{pd->mats[i], pd->widths[i], pd->pitches[i], kbh::log2_exact(pd->heights[i]), off};
       off += pd->widths[i];
     }
     pd->sum_w = off;
@@ -705,6 +732,7 @@ int32_t mmcs_commit_one_dev(zk_ctx* c, uint32_t* mat, uint64_t h, uint32_t w, bo
   pd->n = 1;
   pd->heights.assign(1, h);
   pd->widths.assign(1, w);
+  pd->pitches.assign(1, w);
   pd->mats.assign(1, mat);
   pd->owned.assign(1, take_ownership);
   int32_t rc = mmcs_build(c, pd, fetch_root, false, with_open_desc);
@@ -749,6 +777,7 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
   pd->n = n_mats;
   pd->heights.resize(n_mats);
   pd->widths.assign(widths, widths + n_mats);
+  pd->pitches.assign(widths, widths + n_mats);
   pd->mats.assign(n_mats, nullptr);
   pd->owned.assign(n_mats, false);
   pd->traces.assign(n_mats, nullptr);
@@ -762,7 +791,8 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       pd->heights[i] = heights[i] << log_blowup;
       hmax = std::max(hmax, pd->heights[i]);
       pd->owned[i] = true;
-      rc = dev_alloc(c, pd->heights[i] * widths[i] * 4ull, (void**)&pd->mats[i]);
+      pd->pitches[i] = c->even_pitch ? lde_pitch(widths[i]) : widths[i];
+      rc = dev_alloc(c, pd->heights[i] * pd->pitches[i] * 4ull, (void**)&pd->mats[i]);
       if (rc == ZK_OK && domain_shifts[i] == 0) rc = zk_fail(ZK_ERR_ARG, "domain shift must be non-zero");
     }
     if (rc == ZK_OK) rc = mmcs_alloc(c, pd);
@@ -808,11 +838,11 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
       if (src_is_host) {
         auto it = cls.find(pd->heights[i]);
         ClassStream* st = it == cls.end() ? nullptr : &it->second;
-        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], st, st && st->remaining == 1,
-                             keep);
+        rc = lde_stream_host(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], pd->pitches[i], st,
+                             st && st->remaining == 1, keep);
         if (st) st->remaining--;
       } else
-        rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i]);
+        rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], pd->pitches[i]);
       pending[pd->heights[i]]--;
       // host traces: hash complete height classes and build every tree layer that is already determined while
       // the copy stream is still uploading the remaining matrices
@@ -947,10 +977,15 @@ extern "C" int32_t zk_pdata_copy_lde(const zk_pdata* pd, uint32_t i, uint32_t* o
   zk_ctx* c = pd->ctx;
   std::lock_guard<std::mutex> g(c->mu);
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(out, pd->mats[i], pd->heights[i] * pd->widths[i] * 4ull, cudaMemcpyDeviceToHost, c->stream));
+  if (pd->pitches[i] == pd->widths[i])
+    CK(cudaMemcpyAsync(out, pd->mats[i], pd->heights[i] * pd->widths[i] * 4ull, cudaMemcpyDeviceToHost, c->stream));
+  else if (pd->widths[i])  // padded rows: the host image is dense
+    CK(cudaMemcpy2DAsync(out, (size_t)pd->widths[i] * 4, pd->mats[i], (size_t)pd->pitches[i] * 4, (size_t)pd->widths[i] * 4,
+                         pd->heights[i], cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ZK_OK;
 }
+extern "C" uint32_t zk_pdata_pitch(const zk_pdata* pd, uint32_t i) { return pd && i < pd->n ? pd->pitches[i] : 0; }
 extern "C" int32_t zk_pdata_copy_layer(const zk_pdata* pd, uint32_t layer, uint32_t* out) {
   if (!pd || layer > pd->log_max || !out) return zk_fail(ZK_ERR_ARG, "bad argument");
   zk_ctx* c = pd->ctx;
@@ -977,6 +1012,7 @@ extern "C" int32_t zk_pdata_import(zk_ctx* c, uint32_t n_mats, const uint32_t* c
   pd->n = n_mats;
   pd->heights.assign(heights, heights + n_mats);
   pd->widths.assign(widths, widths + n_mats);
+  pd->pitches.assign(widths, widths + n_mats);  // imported matrices are dense
   pd->mats.assign(n_mats, nullptr);
   pd->owned.assign(n_mats, true);
   pd->traces.assign(n_mats, nullptr);
@@ -1013,7 +1049,7 @@ extern "C" int32_t zk_pdata_import(zk_ctx* c, uint32_t n_mats, const uint32_t* c
   std::vector<zk_open_desc> od(n_mats);
   uint32_t off = 0;
   for (uint32_t i = 0; i < n_mats; i++) {
-    od[i] = zk_open_desc{pd->mats[i], pd->widths[i], kbh::log2_exact(pd->heights[i]), off};
+    od[i] = zk_open_desc{pd->mats[i], pd->widths[i], pd->pitches[i], kbh::log2_exact(pd->heights[i]), off};
     off += pd->widths[i];
   }
   pd->sum_w = off;
@@ -1095,7 +1131,7 @@ extern "C" int32_t zk_hash_rows(zk_ctx* c, const uint32_t* mat, uint64_t h, uint
   if ((rc = ds.alloc(&d, h * w * 4ull))) return rc;
   if ((rc = ds.alloc(&o, h * 32))) return rc;
   if (h * w) CK(cudaMemcpyAsync(d, mat, h * w * 4ull, cudaMemcpyHostToDevice, c->stream));
-  std::vector<mk::MatDesc> grp{mk::MatDesc{d, w}};
+  std::vector<mk::MatDesc> grp{mk::MatDesc{d, w, w}};
   if ((rc = hash_group(c, grp, h, o))) return rc;
   CK(cudaMemcpyAsync(digests, o, h * 32, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1126,7 +1162,7 @@ extern "C" int32_t zk_coset_lde_dev(zk_ctx* c, zk_dptr in, uint64_t h, uint32_t 
   if (!c || !in || !out) return zk_fail(ZK_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
   CK(cudaSetDevice(c->device));
-  return lde_dev(c, (const uint32_t*)in, h, w, log_blowup, shift, (uint32_t*)out);
+  return lde_dev(c, (const uint32_t*)in, h, w, log_blowup, shift, (uint32_t*)out, w);
 }
 
 extern "C" int32_t zk_coset_lde(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup,
@@ -1141,7 +1177,7 @@ extern "C" int32_t zk_coset_lde(zk_ctx* c, const uint32_t* in, uint64_t h, uint3
   if ((rc = ds.alloc(&d, ib))) return rc;
   if ((rc = ds.alloc(&o, obytes))) return rc;
   CK(cudaMemcpyAsync(d, in, ib, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = lde_dev(c, d, h, w, log_blowup, shift, o))) return rc;
+  if ((rc = lde_dev(c, d, h, w, log_blowup, shift, o, w))) return rc;
   CK(cudaMemcpyAsync(out, o, obytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ZK_OK;

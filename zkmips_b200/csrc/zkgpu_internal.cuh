@@ -41,6 +41,7 @@ struct zk_ctx {
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
   uint64_t slab_bytes = 256ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
   uint64_t hash_vec_min_rows = 1ull << 19;  // streamed sponge: vector-load kernel from this many rows (env ZK_HASH_VEC_MIN_ROWS)
+  bool even_pitch = true;                   // committed LDEs of odd width get a padding column (env ZK_EVEN_PITCH=0: dense)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
@@ -89,15 +90,22 @@ __host__ __device__ inline uint64_t mmcs_layer_off(uint32_t L, uint32_t l) {
 struct zk_open_desc {
   const uint32_t* ptr;
   uint32_t w;
+  uint32_t pitch;  // row stride in words (>= w)
   uint32_t log_h;
   uint32_t off;
 };
+
+// Row pitch of a committed LDE: odd widths get one padding column, so that every row starts 8-byte aligned and the
+// two-column NTT kernels, 64-bit loads of the opening reduction and >= 8-byte-aligned uploads apply to the 47-, 115-
+// and 119-column chips of a real execution shard.  The padding column holds the transform of zeros (zeros).
+inline uint32_t lde_pitch(uint32_t w) { return (w + 1u) & ~1u; }
 
 struct zk_pdata {
   zk_ctx* ctx = nullptr;
   uint32_t n = 0;
   std::vector<uint64_t> heights;  // committed heights
   std::vector<uint32_t> widths;
+  std::vector<uint32_t> pitches;  // row stride of mats[i] in words: lde_pitch(w) for committed LDEs, w otherwise
   std::vector<uint32_t*> mats;    // device
   std::vector<bool> owned;
   std::map<uint64_t, uint32_t*> class_digests;  // row digests of a height class hashed while its LDE streamed in
@@ -127,8 +135,9 @@ inline DevScope::~DevScope() {
   for (auto p : ptrs)
     if (p) cudaFreeAsync(p, c->stream);
 }
+// `out` has row pitch out_pitch >= w words (even when w is odd: see lde_pitch); `in` is dense (pitch w)
 int32_t lde_dev(zk_ctx* c, const uint32_t* in, uint64_t h, uint32_t w, uint32_t log_blowup, uint32_t shift,
-                uint32_t* out);
+                uint32_t* out, uint32_t out_pitch);
 int32_t mmcs_alloc(zk_ctx* c, zk_pdata* pd);
 // with_open_desc == false skips the open_batch descriptor upload (FRI layers are opened by their own kernel),
 // which keeps the build free of host->device copies and therefore fully asynchronous.

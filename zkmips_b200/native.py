@@ -51,6 +51,7 @@ PROTOTYPES = {
     "zk_pdata_log_max_height": (u32, [vp]),
     "zk_pdata_root": (i32, [vp, u32p]),
     "zk_pdata_lde": (u64, [vp, u32]),
+    "zk_pdata_pitch": (u32, [vp, u32]),
     "zk_pdata_copy_lde": (i32, [vp, u32, u32p]),
     "zk_pdata_copy_layer": (i32, [vp, u32, u32p]),
     "zk_pdata_import": (i32, [vp, u32, C.POINTER(vp), u64p, u32p, C.POINTER(vp), u32, C.POINTER(vp), u32, C.POINTER(vp)]),
@@ -153,6 +154,10 @@ class PData:
 
     def lde_ptr(self, i):
         return self.d.zk_pdata_lde(self.h, i)
+
+    def pitch(self, i):
+        """row stride of LDE matrix i on the device, in words (>= width: odd widths are padded to even)"""
+        return self.d.zk_pdata_pitch(self.h, i)
 
     def trace_ptr(self, i):
         return self.d.zk_pdata_trace(self.h, i)
