@@ -336,6 +336,14 @@ __global__ void __launch_bounds__(256) zero_col_kernel(uint32_t* __restrict__ ds
   if (r < h) dst[r * pitch + col] = 0u;
 }
 
+// dst[r * dpitch + j] = j < nc ? src[r * nc + j] : 0: dense rows of an odd slab spread to the even pitch (one warp per row)
+__global__ void __launch_bounds__(256) spread_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                          uint32_t nc, uint32_t dpitch, uint64_t h) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < h; r += (uint64_t)gridDim.x * 8)
+    for (uint32_t j = lane; j < dpitch; j += 32) dst[r * dpitch + j] = j < nc ? src[r * nc + j] : 0u;
+}
+
 // LDE of `nc` columns.  `coef` receives the (bit-reversed, unscaled) coefficients and may alias `in` (the
 // inverse transform then runs in place); the 2^b blocks go to out.ptr + t*h*out.w, columns [out.c0, out.c0+nc).
 // The inverse transform covers nc_inv columns and the coset transforms nc columns (nc_inv < nc when the caller has
@@ -525,9 +533,18 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
   // whose width rounds to one slab goes up whole (68 or 90 columns with slab = 64)
   // (cuts are multiples of 8 columns, so only the LAST slab of an odd-width matrix has an odd width; it gets one
   // padding column in the slab buffer -- zeroed, transformed along -- which lands in the padding column of the LDE)
-  uint32_t widest = 0;
-  for (uint32_t k = 0; k < nslab; k++) widest = std::max(widest, lde_pitch(cuts[k + 1] - cuts[k]));
-  if ((rc = ensure_slab_bufs(c, h * (uint64_t)widest * 4))) {
+  // An odd slab is uploaded DENSE into a staging region behind the slab (linear copy for whole rows, 2-D copy with a
+  // dense destination otherwise -- the copy geometries whose PCIe rates are known, profiles/r1_h2d_probe.txt) and spread
+  // to the even pitch by a kernel: a 2-D copy straight into the padded pitch (2^21 rows of 188 B into 192 B) is issued
+  // row by row and took the execution-shard commit from 82 to 332 ms.
+  uint32_t widest = 0, widest_odd = 0;
+  for (uint32_t k = 0; k < nslab; k++) {
+    const uint32_t nck = cuts[k + 1] - cuts[k];
+    widest = std::max(widest, lde_pitch(nck));
+    if (cuts[k] + lde_pitch(nck) <= out_pitch && lde_pitch(nck) > nck) widest_odd = std::max(widest_odd, nck);
+  }
+  const uint64_t stage_off = (h * (uint64_t)widest + 63) / 64 * 64;  // words; keeps the staging region 256-byte aligned
+  if ((rc = ensure_slab_bufs(c, (stage_off + h * (uint64_t)widest_odd) * 4))) {
     free_scales(c, scales);
     return rc;
   }
@@ -536,15 +553,17 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     const uint32_t ncp = (c0 + lde_pitch(nc) <= out_pitch) ? lde_pitch(nc) : nc;  // slab pitch = columns transformed
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
-    if (nc == w && ncp == nc)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
-      CK(cudaMemcpyAsync(buf, host, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    uint32_t* up = ncp > nc ? buf + stage_off : buf;  // dense upload target
+    if (nc == w)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
+      CK(cudaMemcpyAsync(up, host, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
     else
-      CK(cudaMemcpy2DAsync(buf, (size_t)ncp * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+      CK(cudaMemcpy2DAsync(up, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
                            c->copy_stream));
     CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
-    if (ncp > nc) {
-      ZK_LAUNCH(zero_col_kernel, (unsigned)((h + 255) / 256), 256, 0, c->stream, buf, ncp, nc, h);
+    if (ncp > nc) {  // dense rows -> even pitch, padding column zeroed
+      const unsigned blocks = (unsigned)std::min<uint64_t>((h + 7) / 8, 148 * 16);
+      ZK_LAUNCH(spread_rows_kernel, blocks, 256, 0, c->stream, up, buf, nc, ncp, h);
       CK(cudaGetLastError());
       c->launches++;
     }
