@@ -90,7 +90,7 @@ class Lib:
     """One loaded libzkgpu.so.  Methods are 1:1 with the C ABI, with numpy arrays for host buffers."""
 
     def __init__(self, path=None):
-        path = path or DEFAULT_SO
+        path = path or os.environ.get("ZK_LIB") or DEFAULT_SO  # ZK_LIB: A/B builds of the same sources (tools only)
         if not os.path.exists(path):
             raise ZkError(f"{path} is missing: build it with `python -m zkmips_b200.build` "
                           "(there is no CPU fallback)")
