@@ -62,6 +62,8 @@ int32_t zk_prof_get(zk_ctx* ctx, int32_t i, char* name, int32_t name_cap, float*
 int32_t zk_prof_start(zk_ctx* ctx, int32_t i, float* ms_after_first);
 /* number of kernels of this library launched on the ctx since creation */
 uint64_t zk_launch_count(zk_ctx* ctx);
+/* NTT passes this process has run on the persistent TMA-fed kernel (csrc/ntt_tma.cuh) -- tests assert the path was taken */
+uint64_t zk_ntt_tma_passes(void);
 
 /* ---- device memory plumbing --------------------------------------------------------------------- */
 int32_t zk_dev_alloc(zk_ctx* ctx, uint64_t bytes, zk_dptr* out);

@@ -63,6 +63,7 @@ extern "C-unwind" {
     pub fn zk_prof_get(ctx: *mut ZkCtx, i: i32, name: *mut core::ffi::c_char, name_cap: i32, ms: *mut f32, launches: *mut u64) -> i32;
     pub fn zk_prof_start(ctx: *mut ZkCtx, i: i32, ms_after_first: *mut f32) -> i32;
     pub fn zk_launch_count(ctx: *mut ZkCtx) -> u64;
+    pub fn zk_ntt_tma_passes() -> u64;
     pub fn zk_dev_alloc(ctx: *mut ZkCtx, bytes: u64, out: *mut ZkDptr) -> i32;
     pub fn zk_dev_free(ctx: *mut ZkCtx, p: ZkDptr) -> i32;
     pub fn zk_h2d(ctx: *mut ZkCtx, dst: ZkDptr, src_host: *const core::ffi::c_void, bytes: u64) -> i32;

@@ -26,3 +26,13 @@ void launch(unsigned grid, unsigned block, const std::function<void()>& f, bool 
   }
 }
 }  // namespace zkemu
+
+// The persistent TMA-fed NTT pass (zkmips_b200/csrc/ntt_tma*.cu) is not part of the emulator build: it never handles a
+// pass here, so ntt::transform falls through to the plain shared-memory kernel.
+#include "../../zkmips_b200/csrc/ntt.cuh"
+namespace ntt {
+cudaError_t run_pass_tma_fwd(const PassArgs&, uint32_t, bool, const PassExtra&, cudaStream_t, bool* handled) { *handled = false; return cudaSuccess; }
+cudaError_t run_pass_tma_inv(const PassArgs&, uint32_t, bool, const PassExtra&, cudaStream_t, bool* handled) { *handled = false; return cudaSuccess; }
+cudaError_t configure_tma_fwd() { return cudaSuccess; }
+cudaError_t configure_tma_inv() { return cudaSuccess; }
+}  // namespace ntt

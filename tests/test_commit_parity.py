@@ -83,6 +83,32 @@ def test_coset_lde(be, n, w, log_blowup):
     assert (ctx.coset_lde(m, log_blowup, shift) == ob.coset_lde(m, log_blowup, shift)).all()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21])
+def test_ntt_tma_path(n, monkeypatch):
+    """The persistent TMA-fed pass (csrc/ntt_tma.cuh) for every tile shape k = 6..10, first / middle / last passes,
+    both directions, a ragged last column group (20 = 16 + 4 columns) and a full-width one: forced on for small
+    matrices, compared with the oracle and with the plain shared-memory kernels (ZK_NTT_TMA=0)."""
+    ctx = _backend("gpu")
+    shift = ob.lib().ork_to_monty(3)
+    w = 20 if n < 20 else 8
+    m = _mont(1 << n, w, seed=700 + n)
+    monkeypatch.setenv("ZK_NTT_TMA_MIN_TILES", "1")
+    monkeypatch.setenv("ZK_NTT_TMA", "1")
+    t0 = ctx.lib.dll.zk_ntt_tma_passes()
+    d_tma = ctx.dft_batch(m)
+    lde_tma = ctx.coset_lde(m, 1 if n >= 20 else 2, shift)
+    npass = 1 if n <= 11 else 2 if n <= 20 else 3  # passes of >= 6 stages (11 = 6 + a register pass)
+    assert ctx.lib.dll.zk_ntt_tma_passes() - t0 == npass * (1 + 1 + (2 if n >= 20 else 4)), "the TMA path was not taken"
+    monkeypatch.setenv("ZK_NTT_TMA", "0")
+    d_plain = ctx.dft_batch(m)
+    lde_plain = ctx.coset_lde(m, 1 if n >= 20 else 2, shift)
+    assert (d_tma == d_plain).all() and (lde_tma == lde_plain).all()
+    if n <= 17:
+        assert (d_tma == ob.dft_batch(m)).all()
+        assert (lde_tma == ob.coset_lde(m, 2, shift)).all()
+
+
 @pytest.mark.parametrize("be", BACKENDS)
 def test_coset_lde_other_shift_and_wide(be):
     ctx = _backend(be)

@@ -95,9 +95,19 @@ cudaError_t run_pass_fwd(const PassArgs& A, uint32_t k, bool first, const PassEx
 cudaError_t run_pass_inv(const PassArgs& A, uint32_t k, bool first, const PassExtra& X, cudaStream_t st);
 cudaError_t configure_fwd();
 cudaError_t configure_inv();
+// persistent TMA-fed variant of the shared-memory pass (ntt_tma.cuh; ntt_tma_fwd.cu / ntt_tma_inv.cu): sets *handled when
+// the pass qualified (size, alignment, enough tiles to stream) and was launched
+cudaError_t run_pass_tma_fwd(const PassArgs& A, uint32_t k, bool first, const PassExtra& X, cudaStream_t st, bool* handled);
+cudaError_t run_pass_tma_inv(const PassArgs& A, uint32_t k, bool first, const PassExtra& X, cudaStream_t st, bool* handled);
+uint64_t& tma_pass_counter();  // defined in zkgpu.cu (the emulator build never increments it)
+cudaError_t configure_tma_fwd();
+cudaError_t configure_tma_inv();
 inline cudaError_t configure_device() {
   cudaError_t e = configure_fwd();
-  return e != cudaSuccess ? e : configure_inv();
+  if (e == cudaSuccess) e = configure_inv();
+  if (e == cudaSuccess) e = configure_tma_fwd();
+  if (e == cudaSuccess) e = configure_tma_inv();
+  return e;
 }
 
 // Full transform of `nc` columns of a 2^log_n-row matrix: natural-order rows in (optionally gathered
@@ -143,7 +153,10 @@ inline cudaError_t transform(Cols src, Cols dst, uint32_t nc, uint32_t log_n, in
     } else if (p == 0 && src_bitrev) {
       return cudaErrorInvalidValue;  // gather without scale is not used
     }
-    cudaError_t e = dir == DIR_FWD ? run_pass_fwd(A, k, first, X, st) : run_pass_inv(A, k, first, X, st);
+    bool handled = false;
+    cudaError_t e = cudaSuccess;
+    if (k >= 6) e = dir == DIR_FWD ? run_pass_tma_fwd(A, k, first, X, st, &handled) : run_pass_tma_inv(A, k, first, X, st, &handled);
+    if (e == cudaSuccess && !handled) e = dir == DIR_FWD ? run_pass_fwd(A, k, first, X, st) : run_pass_inv(A, k, first, X, st);
     if (e != cudaSuccess) return e;
     s0 += k;
   }

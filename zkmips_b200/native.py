@@ -30,6 +30,7 @@ PROTOTYPES = {
     "zk_prof_get": (i32, [vp, i32, C.c_char_p, i32, C.POINTER(C.c_float), u64p]),
     "zk_prof_start": (i32, [vp, i32, C.POINTER(C.c_float)]),
     "zk_launch_count": (u64, [vp]),
+    "zk_ntt_tma_passes": (u64, []),
     "zk_dev_alloc": (i32, [vp, u64, u64p]),
     "zk_dev_free": (i32, [vp, u64]),
     "zk_h2d": (i32, [vp, u64, vp, u64]),
