@@ -32,7 +32,7 @@ constexpr int TMA_REGS_COMPUTE = 112, TMA_REGS_PRODUCER = 24;  // the CTA keeps 
 constexpr int TMA_NBUF = 3;
 constexpr uint32_t TMA_TILE_WORDS = 1024 * TILE_COLS;     // 64 KB
 constexpr uint32_t TMA_TAB_WORDS = 32 * FSTRIDE + 16 * 32 + 32 + 32;  // F, G (per sub-tile), gk, ct
-constexpr size_t TMA_SMEM_BYTES = (size_t)TMA_NBUF * TMA_TILE_WORDS * 4 + (size_t)TMA_NGROUP * TMA_TAB_WORDS * 4 + 64 + 128;
+constexpr size_t TMA_SMEM_BYTES = (size_t)TMA_NBUF * TMA_TILE_WORDS * 4 + (size_t)TMA_NGROUP * TMA_TAB_WORDS * 4 + 64;
 
 struct TmaArgs {
   uint32_t total;    // super-tiles = 2^(n-10) * column groups
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     ntt_pass_tma(const __grid_constant__ CUtensorMap tmap, PassArgs A, PassExtra X, TmaArgs T) {
   constexpr int K = 5 + B, LS = 5 - B;
   constexpr uint32_t NTAU = 1u << B, S = 1u << LS, C = TILE_COLS;
-  extern __shared__ __align__(128) uint32_t sm_raw[];
-  // 128-byte aligned base for the TMA destinations
-  uint32_t* sm = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 127) & ~(uintptr_t)127);
+  // TMA destinations need 128-byte alignment: the declaration's alignment is honoured for the dynamic window (no static
+  // shared memory in this kernel).  No integer round trip on the pointer: that loses the shared address space and every
+  // access turns into a generic LD.E / ST.E (seen in the first ncu capture: long-scoreboard and lg-throttle stalls).
+  extern __shared__ __align__(1024) uint32_t sm[];
   uint32_t* bufs = sm;
   uint32_t* tabs = sm + TMA_NBUF * TMA_TILE_WORDS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tabs + TMA_NGROUP * TMA_TAB_WORDS);  // full[3], empty[3]

@@ -17,6 +17,9 @@ cudaError_t run_pass_tma_inv(const PassArgs& A, uint32_t k, bool first, const Pa
   const long min_tiles = env ? atol(env) : -1L;
   const uint64_t tiles = (uint64_t)((A.nc + TILE_COLS - 1) / TILE_COLS) << (A.log_n - 10);
   if (tiles < (min_tiles >= 0 ? (uint64_t)min_tiles : 2ull * sms)) return cudaSuccess;
+  // measured on the log-21 execution shard (7 + 7 + 7 stages, 56..64-column slabs): the tables are rebuilt every few
+  // tiles and the short passes are HBM-bound anyway -- the plain kernel is 5 % faster there; wide, deep passes only
+  if (min_tiles < 0 && (A.nc < 8 * TILE_COLS || k < 8)) return cudaSuccess;
   cudaError_t e = run_pass_tma_dir<DIR_INV>(A, k, first, X, st, sms);
   if (e == cudaErrorNotSupported) return cudaSuccess;
   *handled = true;
