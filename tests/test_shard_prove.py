@@ -233,25 +233,21 @@ def test_dropped_observation_fails_verification(be, drop, monkeypatch):
     if drop == "local_only":
         for c in data.chips:
             c.local_only = False                     # opens [zeta, zeta*g] where the verifier expects [zeta]
-    real_observe = Challenger.observe
+    real_many = Challenger.observe_many
     seen = {"n": 0}
 
-    def observe(self, vals):
-        v = np.asarray(vals, np.uint32).reshape(-1)
+    def observe_many(self, parts):
+        parts = list(parts)
         seen["n"] += 1
-        # inside open(): call 1 = public values, 2 = main commit, 3 = permutation commit, then per chip (local sum,
-        # global x, global y)
-        if drop == "perm_commit" and seen["n"] == 3:
-            return
-        if drop == "local_sum" and seen["n"] == 4:
-            return
-        if drop == "global_sum" and seen["n"] == 5:
-            return
-        real_observe(self, v)
+        # inside open(): call 1 = [public values, main commit]; call 2 = [permutation commit, then per chip local sum,
+        # global x, global y]
+        if seen["n"] == 2 and drop in ("perm_commit", "local_sum", "global_sum"):
+            parts.pop({"perm_commit": 0, "local_sum": 1, "global_sum": 2}[drop])
+        real_many(self, parts)
 
-    monkeypatch.setattr(Challenger, "observe", observe)
+    monkeypatch.setattr(Challenger, "observe_many", observe_many)
     sp = prover.open(pk, data, Challenger(ctx, ch.w))
-    monkeypatch.setattr(Challenger, "observe", real_observe)
+    monkeypatch.setattr(Challenger, "observe_many", real_many)
     if drop == "local_only":
         for c in chips:
             c.local_only = su.AIRS[c.air].local_only

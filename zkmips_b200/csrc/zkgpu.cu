@@ -508,6 +508,12 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     slab = (uint32_t)std::min(by_bytes, quarter);
   }
   if ((uint64_t)h * w * 4 < c->stream_min_bytes || w <= slab) slab = w;  // small matrices: one slab
+  // Rows whose pitch is not a multiple of 128 bytes (47-, 115-, 119-column chips) make poor column slabs: the strided
+  // copy of 224..256-byte rows out of a 476-byte pitch reaches 42 GB/s, and the log-21 execution shard spent 74 ms on
+  // uploads that take 58 ms as linear copies (profiles/r2_timeline_exec_shard.txt).  Such a matrix goes up WHOLE, in one
+  // linear copy, and the pipeline runs at matrix granularity instead (the two slab buffers belong to the context, so the
+  // copy stream is already uploading the next matrix while this one is transformed and hashed).
+  if (c->slab_cols == 0 && ((uint64_t)w * 4) % 128 != 0) slab = w;
   // Slab schedule.  The copy stream is the critical path (compute per slab is shorter than its upload), so what
   // is left after the LAST upload -- the transforms and the sponge of the last slab -- is pure tail.  The last
   // full slab is therefore cut in halves, down to 32 columns (128 B rows still copy at full PCIe rate, 64 B rows

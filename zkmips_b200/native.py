@@ -414,6 +414,13 @@ class Challenger:
         v = _arr(vals, np.uint32).reshape(-1)
         self.ctx.lib.check(self.ctx.d.zk_challenger_observe(self.ctx.h, self._p(), _p32(v), v.size))
 
+    def observe_many(self, parts):
+        """Consecutive observe / observe_slice calls in ONE device round trip: observing slices one after the other is
+        observing their concatenation (DuplexChallenger::observe_slice, challenger.rs)."""
+        parts = [np.asarray(p, np.uint32).reshape(-1) for p in parts]
+        if parts:
+            self.observe(np.concatenate(parts))
+
     def sample_ext(self, n=1):
         out = np.empty((n, 4), np.uint32)
         self.ctx.lib.check(self.ctx.d.zk_challenger_sample_ext(self.ctx.h, self._p(), n, _p32(out)))

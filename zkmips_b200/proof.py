@@ -125,6 +125,46 @@ class RoundShape:
         return max(int(h).bit_length() - 1 for h in self.heights)
 
 
+class _QueryView:
+    """Sequence of QueryProof records backed by the flat proof buffer (built when indexed)."""
+
+    def __init__(self, flat, off0, stride, n, rounds, log_max, n_layers):
+        self.flat, self.off0, self.stride, self.n = flat, off0, stride, n
+        self.rounds, self.log_max, self.n_layers = rounds, log_max, n_layers
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return (self[k] for k in range(self.n))
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(self.n))]
+        if k < 0:
+            k += self.n
+        if not 0 <= k < self.n:
+            raise IndexError(k)
+        flat, off = self.flat, self.off0 + k * self.stride
+        inp = []
+        for r in self.rounds:
+            rows = []
+            for w in r.widths:
+                rows.append(flat[off:off + w])
+                off += w
+            path = flat[off:off + 8 * r.log_max].reshape(r.log_max, 8)
+            off += 8 * r.log_max
+            inp.append(BatchOpening(rows, path))
+        steps = []
+        for i in range(self.n_layers):
+            sib = flat[off:off + 4]
+            off += 4
+            d = self.log_max - i - 1
+            steps.append(CommitPhaseProofStep(sib, flat[off:off + 8 * d].reshape(d, 8)))
+            off += 8 * d
+        return QueryProof(inp, steps)
+
+
 def split_flat_proof(flat, rounds: List[RoundShape], log_blowup, num_queries):
     """-> (opened[round][matrix][point] = (width, 4) array, FriProof)"""
     flat = np.asarray(flat, np.uint32)  # the structured proof holds VIEWS into this buffer
@@ -147,26 +187,12 @@ def split_flat_proof(flat, rounds: List[RoundShape], log_blowup, num_queries):
     off += 4
     pow_witness = int(flat[off])
     off += 1
-    queries = []
-    for _ in range(num_queries):
-        inp = []
-        for r in rounds:
-            rows = []
-            for w in r.widths:
-                rows.append(flat[off:off + w])
-                off += w
-            path = flat[off:off + 8 * r.log_max].reshape(r.log_max, 8)
-            off += 8 * r.log_max
-            inp.append(BatchOpening(rows, path))
-        steps = []
-        for i in range(n_layers):
-            sib = flat[off:off + 4]
-            off += 4
-            d = log_max - i - 1
-            steps.append(CommitPhaseProofStep(sib, flat[off:off + 8 * d].reshape(d, 8)))
-            off += 8 * d
-        queries.append(QueryProof(inp, steps))
-    assert off == flat.size, f"flat proof has {flat.size} words, layout accounts for {off}"
+    # query records are fixed-size: sliced on demand (84 queries x (rounds x matrices + layers) views cost 2 ms when
+    # built eagerly -- more than the device spends on the query phase)
+    per_query = sum(sum(r.widths) + 8 * r.log_max for r in rounds) + sum(4 + 8 * (log_max - i - 1) for i in range(n_layers))
+    assert off + num_queries * per_query == flat.size, \
+        f"flat proof has {flat.size} words, layout accounts for {off + num_queries * per_query}"
+    queries = _QueryView(flat, off, per_query, num_queries, rounds, log_max, n_layers)
     return opened, FriProof(commits, queries, final_poly, pow_witness)
 
 

@@ -141,8 +141,9 @@ class GpuShardProver:
         main_pd = data.main_data
         pvs = data.public_values
         log_degrees = [c.log_degree for c in chips]
-        challenger.observe(pvs[:self.num_pv_elts])                       # prover.rs:322
-        challenger.observe(data.main_commit)                             # prover.rs:323
+        # prover.rs:322-323: observe_slice(public_values), observe(main_commit) -- consecutive observations are one
+        # device round trip (observing slices one after the other = observing their concatenation)
+        challenger.observe_many([pvs[:self.num_pv_elts], data.main_commit])
         perm_challenges = challenger.sample_ext(2)                       # prover.rs:326-329
         # permutation trace of every chip (prover.rs:341-364): generated on the device from the retained traces
         ptrs, shapes, local_sums, global_sums = [], [], [], []
@@ -162,11 +163,11 @@ class GpuShardProver:
         for ptr in ptrs:
             if ptr:
                 ctx.dev_free(ptr)
-        challenger.observe(perm_root)                                    # prover.rs:406
-        for lcs, gcs in zip(local_sums, global_sums):                    # prover.rs:407-413
-            challenger.observe(lcs)
-            challenger.observe(gcs[:7])
-            challenger.observe(gcs[7:])
+        # prover.rs:406-413: observe(perm_root); per chip observe_slice(local sum), observe_slice(global sum x, y)
+        parts = [perm_root]
+        for lcs, gcs in zip(local_sums, global_sums):
+            parts += [lcs, gcs[:7], gcs[7:]]
+        challenger.observe_many(parts)
         alpha = challenger.sample_ext()                                  # prover.rs:426
         t0 = self._tick("permutation_and_challenges", t0)
         # quotient values per chip, written as chunk matrices (prover.rs:429-488)
