@@ -50,6 +50,7 @@ static inline void __syncwarp() {}
 // NOTE: warp shuffles need lock-step lanes; kernels that use them provide an emulator path (ZK_EMU)
 static inline void __threadfence() {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int32_t __mulhi(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * b) >> 32); }
 static inline uint32_t __brev(uint32_t x) {

@@ -203,16 +203,23 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   uint32_t* witness_slot = final_slot + 4;
   uint32_t* queries = witness_slot + 1;
   uint32_t* cur = ro[S.log_max];
-  std::vector<zk_pdata*> layer_pd;
+  struct LayerRec {  // what the query phase needs of a committed layer
+    const uint32_t* leaves;
+    const uint32_t* digests;
+    uint32_t log_h;
+  };
+  std::vector<LayerRec> layer_rec;
   {
     ProfScope ps(c, "fri_commit_phase");
-    for (uint32_t i = 0; i < S.n_layers; i++) {
+    // layers whose input still has more than 2^FRI_TAIL_MAX_LOG elements: one MMCS commit + transcript + fold each
+    uint32_t i = 0;
+    for (; i < S.n_layers && S.log_max - i > (uint32_t)fri::FRI_TAIL_MAX_LOG; i++) {
       uint32_t Li = S.log_max - i;
       uint64_t hh = 1ull << (Li - 1);
       zk_pdata* lp = nullptr;
       RC(mmcs_commit_one_dev(c, cur, hh, 8, false, false, &lp, false));
       sc.pds.push_back(lp);
-      layer_pd.push_back(lp);
+      layer_rec.push_back(LayerRec{lp->mats[0], lp->digests, lp->log_max});
       CK(cudaMemcpyAsync(commits + 8 * i, pdata_root_dev(lp), 32, cudaMemcpyDeviceToDevice, st));
       ZK_LAUNCH(fri::ch_observe_kernel, 1, 1, 0, st, d_ch, pdata_root_dev(lp), 8u);
       ZK_LAUNCH(fri::ch_sample_ext_kernel, 1, 1, 0, st, d_ch, d_beta, 1u);
@@ -224,9 +231,37 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
       c->launches += 3;
       cur = nxt;
     }
-    ZK_LAUNCH(fri::final_poly_kernel, 1, 1, 0, st, cur, 1u << (S.log_max - S.n_layers), final_slot, d_status);
-    ZK_LAUNCH(fri::ch_observe_kernel, 1, 1, 0, st, d_ch, final_slot, 4u);
-    c->launches += 2;
+    if (i < S.n_layers) {
+      // the remaining layers, the final-polynomial check and its observation: ONE launch (fri::fri_tail_kernel)
+      std::vector<fri::TailLayer> tl;
+      for (; i < S.n_layers; i++) {
+        uint32_t Li = S.log_max - i;
+        uint64_t hh = 1ull << (Li - 1);
+        fri::TailLayer t;
+        t.cur = cur;
+        RC(sc.alloc(&t.nxt, hh * 16));
+        RC(sc.alloc(&t.digests, (2 * hh - 1) * 32));
+        t.ro_next = ro[Li - 1];
+        t.commit_slot = commits + 8 * i;
+        t.L = Li;
+        t.gL_inv = kbh::inv(kbh::two_adic_generator(Li));
+        tl.push_back(t);
+        layer_rec.push_back(LayerRec{t.cur, t.digests, Li - 1});
+        cur = t.nxt;
+      }
+      fri::TailLayer* d_tl;
+      RC(sc.alloc(&d_tl, tl.size() * sizeof(fri::TailLayer)));
+      CK(cudaMemcpyAsync(d_tl, tl.data(), tl.size() * sizeof(fri::TailLayer), cudaMemcpyHostToDevice, st));
+      ZK_LAUNCH_COOP(fri::fri_tail_kernel, 1, 1024, 0, st, d_tl, (uint32_t)tl.size(), d_ch, 1u << (S.log_max - S.n_layers),
+                     final_slot, d_status);
+      CK(cudaGetLastError());
+      c->launches++;
+    } else {
+      ZK_LAUNCH(fri::final_poly_kernel, 1, 1, 0, st, cur, 1u << (S.log_max - S.n_layers), final_slot, d_status);
+      ZK_LAUNCH(fri::ch_observe_kernel, 1, 1, 0, st, d_ch, final_slot, 4u);
+      CK(cudaGetLastError());
+      c->launches += 2;
+    }
   }
 
   // ---- proof of work ---------------------------------------------------------------------------
@@ -260,8 +295,8 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
                           S.query_words));
       }
       for (uint32_t i = 0; i < S.n_layers; i++) {
-        const zk_pdata* lp = layer_pd[i];
-        ZK_LAUNCH(fri::fri_layer_query_kernel, num_queries, 64, 0, st, lp->mats[0], lp->digests, lp->log_max, i,
+        const LayerRec& lp = layer_rec[i];
+        ZK_LAUNCH(fri::fri_layer_query_kernel, num_queries, 64, 0, st, lp.leaves, lp.digests, lp.log_h, i,
                   d_idx, queries, S.query_words, S.layer_q_off[i]);
         c->launches++;
       }

@@ -402,6 +402,93 @@ __global__ void final_poly_kernel(const uint32_t* __restrict__ folded, uint32_t 
   st_ext(slot, f0);
 }
 
+// The LAST layers of the commit phase in ONE launch.  A layer of <= 1024 leaf rows is a chain of single-permutation-deep
+// steps -- leaf hash, log2 tree levels, observe the root, sample beta, fold -- that cost 5 launches and ~100 us each as
+// separate kernels (profiles/r2_launches_shard_prove.csv); one CTA walks all of them with block barriers instead, then
+// checks that the last folded vector is constant, writes final_poly and observes it.  Same transcript order as the
+// per-layer path: commit -> observe -> sample beta -> fold (fri.rs:308-351 mirror).
+__device__ __forceinline__ void st_digest(uint32_t* out, const uint32_t (&s)[16]) {
+  reinterpret_cast<uint4*>(out)[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  reinterpret_cast<uint4*>(out)[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+struct TailLayer {
+  uint32_t* cur;           // 2^L extension elements = 2^(L-1) leaf rows of 8 words
+  uint32_t* nxt;           // 2^(L-1) extension elements
+  uint32_t* digests;       // 8 * (2^L - 1) words, leaves first (mmcs_layer_off(L - 1, l))
+  const uint32_t* ro_next; // reduced openings of height 2^(L-1) rolled in with beta^2, or null
+  uint32_t* commit_slot;   // 8 words in the proof
+  uint32_t L, gL_inv;
+};
+constexpr int FRI_TAIL_MAX_LOG = 11;  // layers whose input has <= 2^11 elements (<= 1024 leaf rows)
+__global__ void __launch_bounds__(1024) fri_tail_kernel(const TailLayer* __restrict__ layers, uint32_t n_layers, Chal* ch,
+                                                        uint32_t final_len, uint32_t* __restrict__ final_slot,
+                                                        uint32_t* __restrict__ status) {
+  __shared__ uint32_t s_beta[4];
+  Chal c;
+  if (threadIdx.x == 0) c = *ch;
+  const uint32_t* last = nullptr;
+  for (uint32_t li = 0; li < n_layers; li++) {
+    const TailLayer ly = layers[li];
+    const uint32_t hh = 1u << (ly.L - 1);
+    // leaf layer: digest of row r = sponge of its 8 words (one permutation)
+    for (uint32_t r = threadIdx.x; r < hh; r += blockDim.x) {
+      const uint4* p = reinterpret_cast<const uint4*>(ly.cur + 8 * (size_t)r);
+      uint4 a = p[0], b = p[1];
+      uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
+      p2::permute(s);
+      st_digest(ly.digests + 8 * (size_t)r, s);
+    }
+    __syncthreads();
+    uint64_t off = 0;
+    for (uint32_t len = hh; len > 1; len >>= 1) {
+      const uint32_t half = len >> 1;
+      const uint64_t nx = off + (uint64_t)len * 8;
+      for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(ly.digests + off + (uint64_t)i * 16);
+        uint4 a = p[0], b = p[1], cc = p[2], d = p[3];
+        uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z, d.w};
+        p2::permute(s);
+        st_digest(ly.digests + nx + (uint64_t)i * 8, s);
+      }
+      __syncthreads();
+      off = nx;
+    }
+    if (threadIdx.x == 0) {
+      const uint32_t* root = ly.digests + off;
+      for (int k = 0; k < 8; k++) {
+        const uint32_t v = root[k];
+        ly.commit_slot[k] = v;
+        ch_observe(c, v);
+      }
+      for (int k = 0; k < 4; k++) s_beta[k] = ch_sample(c);
+    }
+    __syncthreads();
+    const kb::Ext b = kb::Ext{{s_beta[0], s_beta[1], s_beta[2], s_beta[3]}};
+    for (uint32_t k = threadIdx.x; k < hh; k += blockDim.x) {
+      uint32_t inv_x = kb::pow(ly.gL_inv, kb::bitrev(k, ly.L - 1));
+      kb::Ext pw = kb::ext_mul_base(b, kb::mul(kb::HALF, inv_x));
+      kb::Ext ca = kb::ext_add_base(pw, kb::HALF);
+      kb::Ext cb = kb::ext_neg(kb::ext_sub_base(pw, kb::HALF));
+      kb::Ext e0 = ld_ext(ly.cur + 8 * (size_t)k), e1 = ld_ext(ly.cur + 8 * (size_t)k + 4);
+      kb::Ext f = kb::ext_add(kb::ext_mul(ca, e0), kb::ext_mul(cb, e1));
+      if (ly.ro_next) f = kb::ext_add(f, kb::ext_mul(kb::ext_sqr(b), ld_ext(ly.ro_next + 4 * (size_t)k)));
+      st_ext(ly.nxt + 4 * (size_t)k, f);
+    }
+    __syncthreads();
+    last = ly.nxt;
+  }
+  if (threadIdx.x == 0) {
+    kb::Ext f0 = ld_ext(last);
+    for (uint32_t k = 1; k < final_len; k++) {
+      kb::Ext f = ld_ext(last + 4 * k);
+      if (f.c[0] != f0.c[0] || f.c[1] != f0.c[1] || f.c[2] != f0.c[2] || f.c[3] != f0.c[3]) status[0] |= 4u;
+    }
+    st_ext(final_slot, f0);
+    for (int k = 0; k < 4; k++) ch_observe(c, f0.c[k]);
+    *ch = c;
+  }
+}
+
 // answer_query for one commit-phase layer (p3_fri::prover::answer_query): block q = query q.
 // Writes sibling value (4 words) then the path of the pair leaf into proof[q * query_stride + off ...].
 __global__ void fri_layer_query_kernel(const uint32_t* __restrict__ leaves /* ext pairs */, const uint32_t* __restrict__ digests,

@@ -206,6 +206,57 @@ __global__ void __launch_bounds__(512) compress_top(uint32_t* __restrict__ diges
   }
 }
 
+// Tail of a tree in ONE launch for up to 2^16 digests: CTA b compresses its segment of 1024 digests down to one (ten
+// layers, written to their places in the back-to-back layer buffer), and the CTA that finishes LAST (device counter)
+// compresses the gridDim.x remaining digests down to the root.  A tree of 2^16 leaves used to cost six compress_layer
+// launches of 11-13 us each (one permutation deep, launch-latency bound) plus compress_top; every FRI layer commits a tree.
+__global__ void __launch_bounds__(512) compress_tail(uint32_t* __restrict__ digests, uint64_t off0, uint32_t len0,
+                                                     unsigned int* __restrict__ counter) {
+  __shared__ unsigned int s_last;
+  const uint32_t seg = len0 < 1024u ? len0 : 1024u;
+  uint64_t off = off0;
+  uint32_t len = len0, cnt = seg, base = blockIdx.x * seg;
+  while (cnt > 1) {
+    const uint32_t half = cnt >> 1;
+    const uint64_t nxt = off + (uint64_t)len * 8;
+    for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+      const uint4* p = reinterpret_cast<const uint4*>(digests + off + (uint64_t)(base + 2 * i) * 8);
+      uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+      uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      p2::permute(s);
+      store_digest(digests + nxt + (uint64_t)((base >> 1) + i) * 8, s);
+    }
+    __syncthreads();
+    off = nxt;
+    len >>= 1;
+    cnt = half;
+    base >>= 1;
+  }
+  if (gridDim.x == 1) return;
+  __threadfence();  // this CTA's digest is visible device-wide before its ticket is
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) *counter = 0u;  // ready for the next tree on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (len = gridDim.x; len > 1; len >>= 1) {
+    const uint32_t half = len >> 1;
+    const uint64_t nxt = off + (uint64_t)len * 8;
+    for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+      const uint4* p = reinterpret_cast<const uint4*>(digests + off + (uint64_t)i * 16);
+      uint4 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2), d = __ldcg(p + 3);  // written by other SMs: not through L1
+      uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      p2::permute(s);
+      store_digest(digests + nxt + (uint64_t)i * 8, s);
+    }
+    __syncthreads();
+    off = nxt;
+  }
+}
+
 // Raw permutation of n independent 16-word states (unit entry point / known-answer tests).
 __global__ void __launch_bounds__(256) permute_states(uint32_t* st, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -113,6 +113,8 @@ static int32_t ctx_init(zk_ctx* c) {
     CK(cudaGetLastError());
     c->launches++;
   }
+  CK(cudaMalloc(&c->tail_counter, 64));  // ticket counters of the single-launch tree tails (reset by their last CTA)
+  CK(cudaMemsetAsync(c->tail_counter, 0, 64, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ZK_OK;
 }
@@ -161,6 +163,7 @@ static void ctx_teardown(zk_ctx* c) {
   }
   for (int d = 0; d < 2; d++)
     if (c->tw[d]) cudaFree(c->tw[d]);
+  if (c->tail_counter) cudaFree(c->tail_counter);
   for (int b = 0; b < zk_ctx::NSLAB; b++) {
     if (c->slab_buf[b]) cudaFree(c->slab_buf[b]);
     if (c->slab_up[b]) cudaEventDestroy(c->slab_up[b]);
@@ -692,9 +695,11 @@ int32_t mmcs_advance(zk_ctx* c, zk_pdata* pd, TreeProgress& tp, const std::map<u
   while (tp.next_l <= pd->log_max) {
     const uint32_t l = tp.next_l;
     const uint64_t len = hmax >> l;
-    if (hmin > len && 2 * len <= 1024) {
-      // no matrix left to inject: one CTA finishes the tree from the layer of 2*len digests
-      ZK_LAUNCH_COOP(mk::compress_top, 1, 512, 0, c->stream, pd->digests, pd->layer_off[l - 1], (uint32_t)(2 * len));
+    if (hmin > len && 2 * len <= (1u << 16)) {
+      // no matrix left to inject: ONE launch finishes the tree from the layer of 2*len digests (segments of 1024 per
+      // CTA, the last CTA to finish does the top)
+      ZK_LAUNCH_COOP(mk::compress_tail, (unsigned)std::max<uint64_t>(1, (2 * len) >> 10), 512, 0, c->stream, pd->digests,
+                     pd->layer_off[l - 1], (uint32_t)(2 * len), c->tail_counter);
       CK(cudaGetLastError());
       c->launches++;
       tp.next_l = pd->log_max + 1;

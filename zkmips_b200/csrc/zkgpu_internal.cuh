@@ -46,6 +46,7 @@ struct zk_ctx {
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
   uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
+  unsigned int* tail_counter = nullptr;   // mk::compress_tail / fri tail kernels: "last CTA finishes" tickets
   bool keep_traces = false;
   bool prof = false;
   struct Rec {
