@@ -80,6 +80,37 @@ def int_pipe_note(name, log_rows, cols):
         return None
 
 
+def int_pipe_roofline(log_rows, cols, leaf_ms, sm_mhz):
+    """Second roofline of the leaf sponge, against the pipes that actually bound it: pipe-cycles the permutations of one
+    launch occupy on the fma and alu pipes (per-permutation budget read off the SASS of THIS build by
+    zkmips_b200/build.py -> pipe_model.json; cost model calibrated by tools/bench/pipebench.cu: 2 cycles per warp
+    instruction, 4 for IMAD.WIDE / IMAD.HI) over what 148 SMs x 4 sub-partitions x 2 pipes supply at the sampled clock."""
+    try:
+        with open(os.path.join(ROOT, "zkmips_b200", "pipe_model.json")) as fh:
+            m = json.load(fh)
+        src = "SASS of this build (zkmips_b200/pipe_model.json)"
+    except Exception:
+        m = {"fma_pipe_cycles": 5532, "alu_pipe_cycles": 4322, "warp_instructions": 4500}
+        src = "profiles/README.md (round-1 SASS count)"
+    warp_perms = (1 << (log_rows + LOG_BLOWUP)) * (cols // 8) / 32
+    hz = (sm_mhz or 1965.0) * 1e6
+    sms = 148
+    supply_per_pipe = sms * 4 * hz           # pipe-cycles per second of ONE pipe over the GPU
+    t = leaf_ms * 1e-3
+    fma, alu = m["fma_pipe_cycles"], m["alu_pipe_cycles"]
+    ach = warp_perms * (fma + alu) / t
+    return {"kernel": "mk::hash_rows_w8 (Poseidon2 leaf sponge)", "bound": "int-pipe", "unit": "Tpipe-cycle/s",
+            "achieved": ach / 1e12, "peak": 2 * supply_per_pipe / 1e12, "frac": ach / (2 * supply_per_pipe),
+            "binding_pipe": {"name": "fma" if fma >= alu else "alu",
+                             "frac": warp_perms * max(fma, alu) / t / supply_per_pipe},
+            "issue_frac": warp_perms * m["warp_instructions"] / t / supply_per_pipe,
+            "per_warp_permutation": {"fma_pipe_cycles": fma, "alu_pipe_cycles": alu,
+                                     "warp_instructions": m["warp_instructions"]},
+            "sm_mhz": hz / 1e6, "source": src,
+            "note": "frac = both pipes full; binding_pipe.frac = the busier pipe alone (ncu fmaheavy 83.9 %); moving "
+                    "adds between the pipes at SASS level was measured slower both ways (profiles/r2_p2bench_sass_sweep.txt)"}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -665,7 +696,9 @@ def main():
                      "algorithmic_bytes": leaf_hash_bytes(log_rows, cols, LOG_BLOWUP),
                      "int_pipes": int_pipe_note("mk::hash_rows_w8", log_rows, cols),
                      "ms_per_launch": leaf_ms,
-                     "note": "int-pipe bound kernel; HBM fraction reported as required, see DESIGN.md section 4"},
+                     "note": "HBM fraction as the bench contract asks; the kernel is bound by the integer pipes -- see "
+                             "roofline_int beside this object and DESIGN.md section 4"},
+        "roofline_int": int_pipe_roofline(log_rows, cols, leaf_ms, (clocks or {}).get("sm_mhz")),
         "commit_roofline": {"algorithmic_bytes": A, "achieved": commit_gbs, "unit": "GB/s", "frac": commit_gbs / peak},
         "stages_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
         "root": [int(x) for x in root_dev],

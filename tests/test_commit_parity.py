@@ -84,6 +84,18 @@ def test_coset_lde(be, n, w, log_blowup):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,w", [(17, 4), (18, 4), (18, 2), (19, 4), (20, 2)])
+def test_ntt_narrow_tiles(n, w):
+    """4-column tiles for matrices of <= 4 columns (tiles of 512 and 1024 rows: passes of 9 and 10 stages), first,
+    middle and last passes, against the oracle."""
+    ctx = _backend("gpu")
+    shift = ob.lib().ork_to_monty(3)
+    m = _mont(1 << n, w, seed=900 + n + w)
+    assert (ctx.dft_batch(m) == ob.dft_batch(m)).all()
+    assert (ctx.coset_lde(m, 1, shift) == ob.coset_lde(m, 1, shift)).all()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21])
 def test_ntt_tma_path(n, monkeypatch):
     """The persistent TMA-fed pass (csrc/ntt_tma.cuh) for every tile shape k = 6..10, first / middle / last passes,

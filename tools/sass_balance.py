@@ -224,6 +224,32 @@ def patch_function(blob, sec_off, cubin, fun, per_ext, log):
     return len(patched), patched
 
 
+def perm_pipe_model(obj, fun="_ZN2mk12hash_rows_w8EPKjjmPj"):
+    """Integer-pipe budget of one Poseidon2 permutation inside kernel `fun` of a cubin / object file, from its SASS:
+    cycles the fma pipe (IMAD* 2, IMAD.WIDE / IMAD.HI 4) and the alu pipe (2 each) are occupied per WARP-permutation,
+    weighting the external-round body x8 and the internal-round body x13 (cost model: profiles/r1_pipebench.txt)."""
+    ins = disasm(obj, fun)
+    loops = []
+    for a, text in ins:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", text)
+        if m and int(m.group(1), 16) < a:
+            loops.append((int(m.group(1), 16), a))
+    stats = {l: body_stats(ins, *l) for l in loops}
+    count = {l: sum(1 for a, _ in ins if l[0] <= a <= l[1]) for l in loops}
+    ext = [l for l in loops if stats[l][2] == 32]
+    itl = [l for l in loops if stats[l][2] == 2]
+    if not ext or not itl:
+        return None
+    e, i = min(ext, key=lambda l: count[l]), min(itl, key=lambda l: count[l])
+    outer = max(loops, key=lambda l: count[l])  # the per-chunk loop: absorb + first linear layer + both bodies
+    fma = stats[outer][0] - stats[e][0] - stats[i][0] + 8 * stats[e][0] + 13 * stats[i][0]
+    alu = stats[outer][1] - stats[e][1] - stats[i][1] + 8 * stats[e][1] + 13 * stats[i][1]
+    n = count[outer] - count[e] - count[i] + 8 * count[e] + 13 * count[i]
+    return {"kernel": fun, "fma_pipe_cycles": fma, "alu_pipe_cycles": alu, "warp_instructions": n,
+            "external_body": {"instructions": count[e], "fma": stats[e][0], "alu": stats[e][1]},
+            "internal_body": {"instructions": count[i], "fma": stats[i][0], "alu": stats[i][1]}}
+
+
 IADD3_RR = re.compile(r"^IADD3 R(\d+), PT, PT, R(\d+)(\.reuse)?, (-?)R(\d+)(\.reuse)?, RZ$")
 
 

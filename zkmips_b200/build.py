@@ -111,6 +111,20 @@ def build(force=False, verbose=False, balance=None, so=None):
         rc = res.returncode
     with open(os.path.join(HERE, "build.log" if so == SO else "build_ab.log"), "w") as fh:
         fh.write(log)
+    if rc == 0 and so == SO:
+        # integer-pipe budget of one permutation of the leaf sponge as compiled (bench.py: roofline_int)
+        try:
+            import importlib.util
+            import json
+            spec = importlib.util.spec_from_file_location("sass_balance", os.path.join(os.path.dirname(HERE), "tools", "sass_balance.py"))
+            sb = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(sb)
+            model = sb.perm_pipe_model(os.path.join(objdir, "zkgpu.o"))
+            if model:
+                with open(os.path.join(HERE, "pipe_model.json"), "w") as fh:
+                    json.dump(model, fh, indent=1)
+        except Exception as e:  # the model is reporting only
+            log += f"pipe model not written: {e}\n"
     if verbose or rc:
         print(log)
     if rc:

@@ -84,17 +84,21 @@ __host__ __device__ constexpr int brev5(int q) {
 // No per-element global twiddle or scale loads.  (First version of this kernel: 85-104 instructions per
 // element; this one 49-62: profiles/README.md.)
 constexpr int FSTRIDE = 33;
-template <int B>
+template <int B, int C = TILE_COLS>
 constexpr size_t pass_smem_bytes() {
   constexpr int ROWS = 1 << (5 + B);
-  return ((size_t)(ROWS + ROWS / 32) * TILE_COLS + (size_t)(1 << B) * FSTRIDE + 96) * 4;
+  return ((size_t)(ROWS + ROWS / 32) * C + (size_t)(1 << B) * FSTRIDE + 96) * 4;
 }
+// Narrow matrices (<= 4 columns: Fibonacci-like chips, permutation traces and quotient chunks, which are 4 base-field
+// columns each) use 4-column tiles: with 16-column tiles three quarters of every CTA's lanes carried zeros, and the
+// eighteen 4-column transforms of a shard proof cost as much as its 1024-column one.
+constexpr int NARROW_COLS = 4;
 
-template <int B, int DIR, bool FIRST, bool PASSTW, int CPT>
-__global__ void __launch_bounds__((16 / CPT) << B, (CPT == 2 ? 512 : 1024) / ((16 / CPT) << B)) ntt_pass_smem(PassArgs A,
-                                                                                                           PassExtra X) {
-  constexpr int K = 5 + B, ROWS = 1 << K, C = TILE_COLS;
-  constexpr uint32_t NTAU = 1u << B, NT = NTAU * (16 / CPT), CSH = CPT == 2 ? 3 : 4;
+template <int B, int DIR, bool FIRST, bool PASSTW, int CPT, int C = TILE_COLS>
+__global__ void __launch_bounds__((C / CPT) << B, (CPT == 2 ? 512 : 1024) / ((C / CPT) << B)) ntt_pass_smem(PassArgs A,
+                                                                                                          PassExtra X) {
+  constexpr int K = 5 + B, ROWS = 1 << K;
+  constexpr uint32_t NTAU = 1u << B, NT = NTAU * (C / CPT), CSH = (C / CPT) == 8 ? 3 : (C / CPT) == 16 ? 4 : (C / CPT) == 2 ? 1 : 2;
   ZK_DYN_SMEM(sm);
   uint32_t* sdat = sm;
   uint32_t* F = sm + (ROWS + ROWS / 32) * C;
@@ -262,21 +266,26 @@ inline int cpt_pref() {
   return pref;
 }
 
-template <int B, int DIR, bool FIRST, bool PASSTW, int CPT>
+template <int B, int DIR, bool FIRST, bool PASSTW, int CPT, int C = TILE_COLS>
 inline cudaError_t launch_smem_cpt(const PassArgs& A, const PassExtra& X, cudaStream_t st) {
-  uint32_t ncg = (A.nc + TILE_COLS - 1) / TILE_COLS;
+  uint32_t ncg = (A.nc + C - 1) / C;
   uint64_t blocks = (1ull << (A.log_n - (5 + B))) * ncg;
-  auto kfn = ntt_pass_smem<B, DIR, FIRST, PASSTW, CPT>;
-  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, (16 / CPT) << B, pass_smem_bytes<B>(), st, A, X);
+  auto kfn = ntt_pass_smem<B, DIR, FIRST, PASSTW, CPT, C>;
+  ZK_LAUNCH_COOP(kfn, (unsigned)blocks, (C / CPT) << B, (pass_smem_bytes<B, C>()), st, A, X);
   return cudaGetLastError();
 }
 template <int B, int DIR>
 inline cudaError_t launch_smem(const PassArgs& A, bool first, const PassExtra& X, cudaStream_t st) {
   const bool passtw = A.log_n - A.s0 - (5 + B) > 0;
   const bool two = cpt_pref() == 2 && pass_aligned(A);
+  // (tiles of >= 512 rows only: below that a 4-column CTA is less than a warp, and such matrices are tiny anyway)
+  const bool narrow = two && A.nc <= NARROW_COLS && B >= 4;
 #define ZK_NTT_CASE(F, T)                                                               \
-  if (first == F && passtw == T)                                                        \
-    return two ? launch_smem_cpt<B, DIR, F, T, 2>(A, X, st) : launch_smem_cpt<B, DIR, F, T, 1>(A, X, st);
+  if (first == F && passtw == T) {                                                      \
+    if constexpr (B >= 4)                                                               \
+      if (narrow) return launch_smem_cpt<B, DIR, F, T, 2, NARROW_COLS>(A, X, st);       \
+    return two ? launch_smem_cpt<B, DIR, F, T, 2>(A, X, st) : launch_smem_cpt<B, DIR, F, T, 1>(A, X, st); \
+  }
   ZK_NTT_CASE(false, false)
   ZK_NTT_CASE(false, true)
   ZK_NTT_CASE(true, false)
@@ -311,7 +320,11 @@ inline cudaError_t configure_b() {
 #define ZK_NTT_ATTR(F, T, CPTV)                                                                                   \
   if (e == cudaSuccess)                                                                                           \
     e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR, F, T, CPTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                             (int)pass_smem_bytes<B>());
+                             (int)pass_smem_bytes<B>());                                                          \
+  if constexpr (B >= 4 && CPTV == 2)                                                                              \
+    if (e == cudaSuccess)                                                                                         \
+      e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR, F, T, 2, NARROW_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)pass_smem_bytes<B, NARROW_COLS>());
   ZK_NTT_ATTR(false, false, 1) ZK_NTT_ATTR(false, true, 1) ZK_NTT_ATTR(true, false, 1) ZK_NTT_ATTR(true, true, 1)
   ZK_NTT_ATTR(false, false, 2) ZK_NTT_ATTR(false, true, 2) ZK_NTT_ATTR(true, false, 2) ZK_NTT_ATTR(true, true, 2)
 #undef ZK_NTT_ATTR
