@@ -97,7 +97,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   Scratch sc(c);
   ProfScope ps_all(c, "pcs_open");
 
-  uint32_t *d_proof, *d_pts, *d_alpha, *d_apow, *d_apow_split, *d_status, *d_found, *d_beta, *d_red, *d_aoff, *d_rowred, *d_wts, *d_partial;
+  uint32_t *d_proof, *d_pts, *d_alpha, *d_apow, *d_apow_split, *d_status, *d_found, *d_beta, *d_red, *d_aoff, *d_rowred, *d_partial;
   uint64_t* d_idx;
   fri::Chal* d_ch;
   uint64_t Hmax = 1ull << S.log_max;
@@ -114,7 +114,6 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   RC(sc.alloc(&d_red, 32));
   RC(sc.alloc(&d_aoff, 32));
   RC(sc.alloc(&d_rowred, Hmax * 16));
-  RC(sc.alloc(&d_wts, 2 * (Hmax >> log_blowup) * 32));
   RC(sc.alloc(&d_partial, (uint64_t)nchunks_max * 2 * std::max(S.max_w, 1u) * 16));
   RC(sc.alloc(&d_idx, (uint64_t)std::max(num_queries, 1u) * 8));
   RC(sc.alloc(&d_ch, sizeof(fri::Chal)));
@@ -136,6 +135,15 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
     ro[i] = nullptr;
     num_reduced[i] = 0;
   }
+  struct DenKey {
+    uint32_t L;
+    uint32_t z[4];
+    bool operator<(const DenKey& o) const { return L != o.L ? L < o.L : memcmp(z, o.z, 16) < 0; }
+  };
+  struct DenBuf {
+    uint32_t *inv, *wts;
+  };
+  std::map<DenKey, DenBuf> dens;  // per (LDE height, opening point): fri::inv_den_kernel
   {
     ProfScope ps(c, "open_reduce");
     uint32_t* out = d_proof;
@@ -155,7 +163,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
           pt += 4 * n_points[k];
           continue;
         }
-        uint32_t gL = kbh::two_adic_generator(L), gn = kbh::two_adic_generator(n);
+        uint32_t gL = kbh::two_adic_generator(L);
         if (w >= 64)
           ZK_LAUNCH_COOP(fri::row_reduce_warp_kernel, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch,
                          d_apow_split, d_rowred);
@@ -167,7 +175,24 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
           uint32_t np = std::min(2u, n_points[k] - p0);
           uint64_t N = 1ull << n;
           uint32_t nchunks = (uint32_t)((N + fri::BARY_ROWS - 1) / fri::BARY_ROWS);
-          ZK_LAUNCH(fri::bary_weights_kernel, (unsigned)((N + 255) / 256), 256, 0, st, pt, np, n, gn, d_wts);
+          // 1 / (z - x_r) over the LDE domain and the barycentric weights over its low coset: once per (height, point)
+          const uint32_t *invp[2] = {nullptr, nullptr}, *wtsp[2] = {nullptr, nullptr};
+          for (uint32_t q = 0; q < np; q++) {
+            const uint32_t* hz = points + 4 * (size_t)((pt - d_pts) / 4 + q);
+            DenKey key{L, {hz[0], hz[1], hz[2], hz[3]}};
+            auto it = dens.find(key);
+            if (it == dens.end()) {
+              DenBuf b;
+              RC(sc.alloc(&b.inv, H * 16));
+              RC(sc.alloc(&b.wts, N * 32));
+              ZK_LAUNCH(fri::inv_den_kernel, (unsigned)((H / fri::INV_BATCH + 255) / 256 + 1), 256, 0, st, pt + 4 * q, L, n, gL,
+                        b.inv, b.wts);
+              c->launches++;
+              it = dens.emplace(key, b).first;
+            }
+            invp[q] = it->second.inv;
+            wtsp[q] = it->second.wts;
+          }
           {
             // two columns per lane need 8-byte aligned rows: an even PITCH (odd widths are padded), the lane past the
             // last column accumulates the padding column and drops it
@@ -177,18 +202,18 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
             const uint32_t ntile = (w + (cpl << log_cw) - 1) / (cpl << log_cw);
             if (cpl == 2) {
               auto kfn = fri::bary_partial_kernel<2>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, d_wts, np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, d_partial);
             } else {
               auto kfn = fri::bary_partial_kernel<1>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, d_wts, np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, d_partial);
             }
           }
           ZK_LAUNCH_COOP(fri::bary_final_kernel, w, 128, 0, st, d_partial, nchunks, w, n, pt, np, out);
           ZK_LAUNCH_COOP(fri::reduce_ys_kernel, 1, 256, 0, st, out, d_apow, d_alpha, w, np, num_reduced[L], d_red, d_aoff);
-          ZK_LAUNCH(fri::ro_accumulate_kernel, (unsigned)((H + 255) / 256), 256, 0, st, ro[L], d_rowred, L, gL, pt, np, d_red,
-                    d_aoff);
+          ZK_LAUNCH(fri::ro_accumulate_kernel, (unsigned)((H + 255) / 256), 256, 0, st, ro[L], d_rowred, L, invp[0], invp[1], np,
+                    d_red, d_aoff);
           CK(cudaGetLastError());
-          c->launches += 5;
+          c->launches += 4;
           num_reduced[L] += (uint64_t)np * w;
           out += (uint64_t)np * w * 4;
           pt += 4 * np;

@@ -209,16 +209,44 @@ __global__ void __launch_bounds__(256) row_reduce_warp_kernel(const uint32_t* __
   if (lane == 0) st_ext(rowred + 4 * r, e);
 }
 
-// Barycentric weights over the low coset: wts[p][r] = x_r / (z_p - x_r), r < N = 2^n, stored split (8 words)
-__global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __restrict__ pts, uint32_t npts, uint32_t n,
-                                                           uint32_t gn, uint32_t* __restrict__ wts) {
-  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= (1u << n)) return;
-  uint32_t x = lde_point(r, n, gn);
-  for (uint32_t p = 0; p < npts; p++) {
-    kb::Ext z = ld_ext(pts + 4 * p);
-    kb::Ext d = kb::ext_inv(kb::ext_sub_base(z, x));
-    st_split(wts + 8 * (((size_t)p << n) + r), kb::ext_mul_base(d, x));
+// Denominators of one opening point over a whole LDE domain, computed ONCE per (height, point) and shared by every
+// matrix of that height opened there (a chip's main trace, permutation trace and quotient chunks all open at zeta; the
+// per-matrix kernels used to redo a 22-step pow and a 31-squaring inversion per row and point):
+//   inv[r] = 1 / (z - x_r),  x_r = GENERATOR * g_L^{bitrev_L(r)},  r < 2^L;
+//   wts[r] = x_r / (z - x_r) in split form for the rows of the low coset, r < 2^n (its points are the first 2^n of the LDE's).
+// A thread walks INV_BATCH consecutive exponents e (x advances by one multiplication) and inverts its batch with
+// Montgomery's trick: three extension products per element and one extension inversion per batch.
+constexpr int INV_BATCH = 8;
+__global__ void __launch_bounds__(256) inv_den_kernel(const uint32_t* __restrict__ pt, uint32_t L, uint32_t n, uint32_t gL,
+                                                      uint32_t* __restrict__ inv, uint32_t* __restrict__ wts) {
+  const uint64_t H = 1ull << L;
+  const uint64_t e0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * INV_BATCH;
+  if (e0 >= H) return;
+  const uint32_t cnt = (uint32_t)min((uint64_t)INV_BATCH, H - e0);
+  const kb::Ext z = ld_ext(pt);
+  uint32_t x = kb::mul(kb::GEN, kb::pow(gL, e0));
+  uint32_t xs[INV_BATCH];
+  kb::Ext d[INV_BATCH], pre[INV_BATCH], run = kb::ext_one();
+#pragma unroll
+  for (int i = 0; i < INV_BATCH; i++) {
+    if ((uint32_t)i < cnt) {
+      xs[i] = x;
+      d[i] = kb::ext_sub_base(z, x);
+      run = i == 0 ? d[0] : kb::ext_mul(run, d[i]);
+      pre[i] = run;
+      x = kb::mul(x, gL);
+    }
+  }
+  kb::Ext acc = kb::ext_inv(run);
+#pragma unroll
+  for (int i = INV_BATCH - 1; i >= 0; i--) {
+    if ((uint32_t)i < cnt) {
+      kb::Ext v = i == 0 ? acc : kb::ext_mul(acc, pre[i - 1]);
+      if (i > 0) acc = kb::ext_mul(acc, d[i]);
+      const uint64_t r = kb::bitrev((uint32_t)(e0 + i), L);
+      st_ext(inv + 4 * r, v);
+      if (r < (1ull << n)) st_split(wts + 8 * r, kb::ext_mul_base(v, xs[i]));
+    }
   }
 }
 
@@ -229,7 +257,8 @@ __global__ void __launch_bounds__(256) bary_weights_kernel(const uint32_t* __res
 constexpr int BARY_ROWS = 2048;  // rows per chunk
 template <int CPL>
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
-                                                           uint32_t pitch, const uint32_t* __restrict__ wts, uint32_t npts,
+                                                           uint32_t pitch, const uint32_t* __restrict__ wts0,
+                                                           const uint32_t* __restrict__ wts1, uint32_t npts,
                                                            uint32_t log_cw, uint32_t* __restrict__ partial) {
   __shared__ uint32_t red[2 * CPL * 4][256];
   const uint32_t cw = 1u << log_cw, nrl = 256u >> log_cw;
@@ -244,7 +273,7 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
   for (int p = 0; p < 2; p++)
 #pragma unroll
     for (int c = 0; c < CPL; c++) acc[p][c].zero();
-  const uint4* W = reinterpret_cast<const uint4*>(wts);
+  const uint4* W[2] = {reinterpret_cast<const uint4*>(wts0), reinterpret_cast<const uint4*>(wts1)};  // per point: N x 8 words
   if (col < w) {
     for (uint64_t r = r0 + rl; r < r1; r += nrl) {
       uint32_t v[CPL];
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
 #pragma unroll
       for (int p = 0; p < 2; p++) {
         if ((uint32_t)p < npts) {
-          uint4 wl = __ldg(W + 2 * (((size_t)p << n) + r)), wh = __ldg(W + 2 * (((size_t)p << n) + r) + 1);
+          uint4 wl = __ldg(W[p] + 2 * r), wh = __ldg(W[p] + 2 * r + 1);
 #pragma unroll
           for (int c = 0; c < CPL; c++) acc[p][c].fma(wl, wh, v[c]);
         }
@@ -352,19 +381,18 @@ __global__ void __launch_bounds__(256) reduce_ys_kernel(const uint32_t* __restri
   }
 }
 
-// ro[r] += sum_p aoff[p] * (rowred[r] - red_ys[p]) / (x_r - z_p)
+// ro[r] += sum_p aoff[p] * (rowred[r] - red_ys[p]) / (x_r - z_p);  inv_p[r] = 1 / (z_p - x_r) from inv_den_kernel
 __global__ void __launch_bounds__(256) ro_accumulate_kernel(uint32_t* __restrict__ ro, const uint32_t* __restrict__ rowred,
-                                                            uint32_t L, uint32_t gL, const uint32_t* __restrict__ pts,
-                                                            uint32_t npts, const uint32_t* __restrict__ red_ys,
+                                                            uint32_t L, const uint32_t* __restrict__ inv0,
+                                                            const uint32_t* __restrict__ inv1, uint32_t npts,
+                                                            const uint32_t* __restrict__ red_ys,
                                                             const uint32_t* __restrict__ aoff) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= (1u << L)) return;
-  uint32_t x = lde_point(r, L, gL);
   kb::Ext rr = ld_ext(rowred + 4 * (size_t)r);
   kb::Ext acc = ld_ext(ro + 4 * (size_t)r);
   for (uint32_t p = 0; p < npts; p++) {
-    kb::Ext z = ld_ext(pts + 4 * p);
-    kb::Ext inv_den = kb::ext_inv(kb::ext_neg(kb::ext_sub_base(z, x)));  // 1 / (x - z)
+    kb::Ext inv_den = kb::ext_neg(ld_ext((p == 0 ? inv0 : inv1) + 4 * (size_t)r));  // 1 / (x - z)
     kb::Ext t = kb::ext_mul(kb::ext_sub(rr, ld_ext(red_ys + 4 * p)), inv_den);
     acc = kb::ext_add(acc, kb::ext_mul(ld_ext(aoff + 4 * p), t));
   }

@@ -22,6 +22,7 @@
 // the inverse transform to the forward one without a separate permutation kernel) and the coset scale
 // sigma^j / n.  Kernels live in ntt_kernels.cuh, instantiated per direction in ntt_fwd.cu / ntt_inv.cu.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -99,7 +100,7 @@ cudaError_t configure_inv();
 // the pass qualified (size, alignment, enough tiles to stream) and was launched
 cudaError_t run_pass_tma_fwd(const PassArgs& A, uint32_t k, bool first, const PassExtra& X, cudaStream_t st, bool* handled);
 cudaError_t run_pass_tma_inv(const PassArgs& A, uint32_t k, bool first, const PassExtra& X, cudaStream_t st, bool* handled);
-uint64_t& tma_pass_counter();  // defined in zkgpu.cu (the emulator build never increments it)
+std::atomic<uint64_t>& tma_pass_counter();  // defined in zkgpu.cu (the emulator build never increments it)
 cudaError_t configure_tma_fwd();
 cudaError_t configure_tma_inv();
 inline cudaError_t configure_device() {

@@ -182,12 +182,12 @@ extern "C" int32_t zk_ctx_sync(zk_ctx* c) {
 }
 extern "C" const char* zk_last_error(void) { return g_last_error.c_str(); }
 namespace ntt {
-uint64_t& tma_pass_counter() {
-  static uint64_t n = 0;  // diagnostics only (not synchronised)
+std::atomic<uint64_t>& tma_pass_counter() {
+  static std::atomic<uint64_t> n{0};  // diagnostics; contexts on several host threads bump it
   return n;
 }
 }  // namespace ntt
-extern "C" uint64_t zk_ntt_tma_passes(void) { return ntt::tma_pass_counter(); }
+extern "C" uint64_t zk_ntt_tma_passes(void) { return ntt::tma_pass_counter().load(); }
 extern "C" const char* zk_build_info(void) { return "libzkgpu sm_100a " __DATE__ " " __TIME__; }
 
 extern "C" int32_t zk_prof_enable(zk_ctx* c, int32_t enable) {
