@@ -111,6 +111,29 @@ def int_pipe_roofline(log_rows, cols, leaf_ms, sm_mhz):
                     "adds between the pipes at SASS level was measured slower both ways (profiles/r2_p2bench_sass_sweep.txt)"}
 
 
+def upload_helper_for(torch, world, local):
+    """An idle GPU of this node whose PCIe link may carry half of this rank's uploads (forwarded over NVLink,
+    zk_ctx_set_upload_helper): rank r of N borrows GPU G - 1 - r when the node exposes G >= 2 N GPUs -- from the far end,
+    because neighbouring GPUs can share a host-side cap (GPUs 0-3 of the pool's 8-GPU box deliver 115 GB/s together,
+    GPUs 4-7 219 GB/s: profiles/r2_h2d_multi_probe.txt).  Only for N >= 2: the single-GPU line stays what one GPU with one
+    link does, identical to a run on a one-GPU box."""
+    if os.environ.get("ZK_UPLOAD_HELPER", "1") == "0" or world < 2:
+        return None
+    n = torch.cuda.device_count()
+    return n - 1 - local if n >= 2 * world else None
+
+
+def attach_helper(ctx, helper):
+    if helper is None:
+        return False
+    try:
+        ctx.set_upload_helper(helper)
+        return True
+    except Exception as e:  # no peer access: uploads stay on the rank's own link
+        sys.stderr.write(f"upload helper GPU {helper} not used: {e}\n")
+        return False
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -399,6 +422,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     workers = [w1]
     for _ in range(args.in_flight - 1):
         cx = ctx.lib.ctx_create(torch.cuda.current_device())
+        attach_helper(cx, getattr(args, "upload_helper", None))
         wk = ShardWorker(cx, chips, fri)
         wk.prove(chips)  # warm-up of the extra context
         workers.append(wk)
@@ -550,6 +574,9 @@ def main():
     lib = native.load()
     stream = torch.cuda.current_stream()
     ctx = lib.ctx_create(local, stream=stream.cuda_stream)
+    helper = upload_helper_for(torch, world, local)
+    helper_on = attach_helper(ctx, helper)
+    args.upload_helper = helper if helper_on else None
     if args.shard_only:
         res = shard_leg(ctx, torch, dist, world, rank, args)
         if rank == 0:
@@ -622,6 +649,7 @@ def main():
     # still does its own H2D of the trace and D2H of the root inside the timed region; PCIe is the shared resource.
     import threading
     ctx2 = lib.ctx_create(local)
+    attach_helper(ctx2, args.upload_helper)
     roots2 = []
 
     def commit_worker(cx, n):
@@ -683,7 +711,9 @@ def main():
                    "host_affinity": f"rank 0 bound to {len(cpus)} CPUs next to its GPU (NVML)" if cpus else "unbound",
                    "l2": "inputs (1 GiB trace, 2 GiB LDE) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_host, "h2d_bytes_per_step": 4 * n_elems,
-                "d2h_bytes_per_step": 32, "commits_in_flight": 1},
+                "d2h_bytes_per_step": 32, "commits_in_flight": 1,
+                "upload_helper": ("rank r also uses the PCIe link of idle GPU G-1-r: half of every slab lands there and is "
+                                  "forwarded over NVLink (zk_ctx_set_upload_helper)") if args.upload_helper is not None else None},
         "e2e_two_in_flight": {"value": world * n_elems / (ms_pipe * 1e-3) / 1e9, "unit": UNIT, "ms_per_commit": ms_pipe,
                               "h2d_bytes_per_commit": 4 * n_elems, "d2h_bytes_per_commit": 32, "commits_in_flight": 2,
                               "note": "two contexts / host threads per GPU, as the reference's concurrent shard workers; "

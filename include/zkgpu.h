@@ -106,6 +106,11 @@ int32_t zk_mmcs_commit_dev(zk_ctx* ctx, uint32_t n_mats, const zk_dptr* mats_dev
 /* When enabled, zk_commit keeps a device copy of every input trace in the prover data (zk_pdata_trace), so
  * that stages between commits which read the trace itself (LogUp) need no second upload. */
 int32_t zk_ctx_keep_traces(zk_ctx* ctx, int32_t enable);
+/* Upload helper: `device` is an IDLE peer GPU of the same node (NVLink peer access required).  From then on zk_commit
+ * sends the second half of the rows of every trace slab over THAT GPU's PCIe link into a staging buffer there and
+ * forwards it over NVLink, so a rank on a partly used node gets two links' worth of host bandwidth (measured 109 vs
+ * 55.6 GB/s, profiles/r2_h2d_multi_probe.txt).  device < 0 turns it off.  Host buffers must be pinned. */
+int32_t zk_ctx_set_upload_helper(zk_ctx* ctx, int32_t device);
 
 /* ---- ProverData accessors -------------------------------------------------------------------------- */
 void zk_pdata_free(zk_pdata* pd);

@@ -79,6 +79,7 @@ extern "C-unwind" {
     pub fn zk_mmcs_commit(ctx: *mut ZkCtx, n_mats: u32, mats_host: *const *const u32, heights: *const u64, widths: *const u32, root: *mut u32, out: *mut *mut ZkPdata) -> i32;
     pub fn zk_mmcs_commit_dev(ctx: *mut ZkCtx, n_mats: u32, mats_dev: *const ZkDptr, heights: *const u64, widths: *const u32, root: *mut u32, out: *mut *mut ZkPdata) -> i32;
     pub fn zk_ctx_keep_traces(ctx: *mut ZkCtx, enable: i32) -> i32;
+    pub fn zk_ctx_set_upload_helper(ctx: *mut ZkCtx, device: i32) -> i32;
     pub fn zk_pdata_free(pd: *mut ZkPdata);
     pub fn zk_pdata_num_matrices(pd: *const ZkPdata) -> u32;
     pub fn zk_pdata_height(pd: *const ZkPdata, i: u32) -> u64;

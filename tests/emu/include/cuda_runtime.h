@@ -68,7 +68,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p 
 
 // ---- runtime API subset ------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef void* cudaStream_t;
 struct zkemu_event { std::chrono::steady_clock::time_point t; };
 typedef zkemu_event* cudaEvent_t;
@@ -123,6 +123,10 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
   for (size_t r = 0; r < rows; r++) memcpy((char*)d + r * dp, (const char*)s + r * sp, wbytes);
   return cudaSuccess;
 }
+// no peer devices in the emulator: zk_ctx_set_upload_helper reports an argument error
+static inline cudaError_t cudaDeviceCanAccessPeer(int* a, int, int) { *a = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaErrorInvalidValue; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -84,6 +84,42 @@ def test_coset_lde(be, n, w, log_blowup):
 
 
 @pytest.mark.gpu
+def test_upload_helper_commit(monkeypatch):
+    """zk_ctx_set_upload_helper: half of the rows of every slab travel over an idle peer GPU's PCIe link and NVLink.
+    Column slabs, uneven cuts, a whole-matrix odd-width upload and retained traces, against the oracle; needs 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs a second (idle) GPU")
+    from zkmips_b200 import native
+    monkeypatch.setenv("ZK_STREAM_MIN_BYTES", "0")
+    ctx = native.load().ctx_create(0)
+    one = ob.lib().ork_to_monty(1)
+
+    def pin(m):
+        return torch.from_numpy(m.view(np.int32)).pin_memory().numpy().view(np.uint32)
+
+    try:
+        ctx.set_upload_helper(1)
+        ctx.keep_traces(True)
+        mats = [pin(_mont(1 << 16, 300, seed=801)), pin(_mont(1 << 17, 47, seed=802)), pin(_mont(1 << 15, 256, seed=803))]
+        root, pd = ctx.commit(mats, [one] * 3, 1)
+        tree = ob.pcs_commit(mats, 1, [one] * 3)
+        assert (root == tree.root).all()
+        for i, m in enumerate(mats):
+            assert (pd.lde(i) == tree.matrix(i)).all()
+            assert (ctx.download(pd.trace_ptr(i), m.shape) == m).all()
+        pd.free()
+        ctx.set_upload_helper(-1)
+        root2, pd2 = ctx.commit(mats, [one] * 3, 1)
+        assert (root2 == root).all()
+        pd2.free()
+        with pytest.raises(Exception):
+            ctx.set_upload_helper(0)  # the context's own GPU is not a helper
+    finally:
+        ctx.destroy()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,w", [(17, 4), (18, 4), (18, 2), (19, 4), (20, 2)])
 def test_ntt_narrow_tiles(n, w):
     """4-column tiles for matrices of <= 4 columns (tiles of 512 and 1024 rows: passes of 9 and 10 stages), first,

@@ -142,6 +142,79 @@ extern "C" int32_t zk_ctx_create_on_stream(int32_t device, void* stream, zk_ctx*
 extern "C" int32_t zk_ctx_create(int32_t device, zk_ctx** out) { return zk_ctx_create_on_stream(device, nullptr, out); }
 
 static void ctx_teardown(zk_ctx* c);
+
+// ---- upload helper -------------------------------------------------------------------------------------------
+static void helper_release(zk_ctx* c) {
+  if (c->helper_dev < 0) return;
+  cudaSetDevice(c->helper_dev);
+  for (int b = 0; b < zk_ctx::NSLAB; b++) {
+    if (c->helper_stream[b]) {
+      cudaStreamSynchronize(c->helper_stream[b]);
+      cudaStreamDestroy(c->helper_stream[b]);
+    }
+    if (c->helper_done[b]) cudaEventDestroy(c->helper_done[b]);
+    if (c->helper_stage[b]) cudaFree(c->helper_stage[b]);
+    c->helper_stream[b] = nullptr;
+    c->helper_done[b] = nullptr;
+    c->helper_stage[b] = nullptr;
+  }
+  c->helper_cap = 0;
+  c->helper_dev = -1;
+  cudaSetDevice(c->device);
+}
+extern "C" int32_t zk_ctx_set_upload_helper(zk_ctx* c, int32_t device) {
+  if (!c) return zk_fail(ZK_ERR_ARG, "ctx is null");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->copy_stream));
+  CK(cudaStreamSynchronize(c->stream));
+  helper_release(c);
+  if (device < 0) return ZK_OK;
+  int ndev = 0, a = 0, b = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device >= ndev || device == c->device) return zk_fail(ZK_ERR_ARG, "upload helper must be another visible GPU");
+  CK(cudaDeviceCanAccessPeer(&a, c->device, device));
+  CK(cudaDeviceCanAccessPeer(&b, device, c->device));
+  if (!a || !b) return zk_fail(ZK_ERR_ARG, "no peer access between the context's GPU and the upload helper");
+  cudaError_t e = cudaDeviceEnablePeerAccess(device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+  cudaGetLastError();
+  CK(cudaSetDevice(device));
+  e = cudaDeviceEnablePeerAccess(c->device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+    cudaSetDevice(c->device);
+    CK(e);
+  }
+  cudaGetLastError();
+  for (int k = 0; k < zk_ctx::NSLAB; k++) {
+    cudaError_t e1 = cudaStreamCreateWithFlags(&c->helper_stream[k], cudaStreamNonBlocking);
+    cudaError_t e2 = cudaEventCreateWithFlags(&c->helper_done[k], cudaEventDisableTiming);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      c->helper_dev = device;
+      helper_release(c);
+      return zk_fail(ZK_ERR_CUDA, "could not create the upload helper's streams");
+    }
+  }
+  c->helper_dev = device;
+  CK(cudaSetDevice(c->device));
+  return ZK_OK;
+}
+// staging buffers on the helper GPU (grown on demand; synchronises the helper's streams)
+static int32_t helper_ensure(zk_ctx* c, uint64_t bytes) {
+  if (bytes <= c->helper_cap) return ZK_OK;
+  cudaError_t e = cudaSetDevice(c->helper_dev);
+  for (int b = 0; b < zk_ctx::NSLAB && e == cudaSuccess; b++) {
+    e = cudaStreamSynchronize(c->helper_stream[b]);
+    if (e == cudaSuccess && c->helper_stage[b]) e = cudaFree(c->helper_stage[b]);
+    c->helper_stage[b] = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&c->helper_stage[b], bytes);
+  }
+  cudaSetDevice(c->device);
+  CK(e);
+  c->helper_cap = bytes;
+  return ZK_OK;
+}
+
 extern "C" void zk_ctx_destroy(zk_ctx* c) {
   if (!c) return;
   {
@@ -169,6 +242,7 @@ static void ctx_teardown(zk_ctx* c) {
     if (c->slab_up[b]) cudaEventDestroy(c->slab_up[b]);
     if (c->slab_free[b]) cudaEventDestroy(c->slab_free[b]);
   }
+  helper_release(c);
   if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -570,13 +644,38 @@ static int32_t lde_stream_host(zk_ctx* c, const uint32_t* host, uint64_t h, uint
     uint32_t* buf = c->slab_buf[b];
     if (c->slab_used[b]) CK(cudaStreamWaitEvent(c->copy_stream, c->slab_free[b], 0));  // last reader of this buffer
     uint32_t* up = ncp > nc ? buf + stage_off : buf;  // dense upload target
+    // With an upload helper the second half of the rows travels over the helper GPU's PCIe link into a staging buffer
+    // there and is forwarded over NVLink; both halves are dense row ranges of the same slab buffer.
+    uint64_t h_direct = h;
+    const bool via_helper = c->helper_dev >= 0 && (uint64_t)h * nc * 4 >= c->helper_min_bytes;
+    if (via_helper) {
+      h_direct = h / 2;
+      const uint64_t hr = h - h_direct, bytes = hr * nc * 4;
+      if ((rc = helper_ensure(c, bytes))) break;
+      cudaStream_t hs = c->helper_stream[b];
+      uint32_t* stg = c->helper_stage[b];
+      cudaError_t e = cudaSetDevice(c->helper_dev);
+      if (e == cudaSuccess) {
+        if (nc == w)
+          e = cudaMemcpyAsync(stg, host + h_direct * w, bytes, cudaMemcpyHostToDevice, hs);
+        else
+          e = cudaMemcpy2DAsync(stg, (size_t)nc * 4, host + h_direct * w + c0, (size_t)w * 4, (size_t)nc * 4, hr,
+                                cudaMemcpyHostToDevice, hs);
+      }
+      if (e == cudaSuccess && c->slab_used[b]) e = cudaStreamWaitEvent(hs, c->slab_free[b], 0);  // last reader of the slab buffer
+      if (e == cudaSuccess) e = cudaMemcpyPeerAsync(up + h_direct * nc, c->device, stg, c->helper_dev, bytes, hs);
+      if (e == cudaSuccess) e = cudaEventRecord(c->helper_done[b], hs);
+      cudaSetDevice(c->device);
+      CK(e);
+    }
     if (nc == w)  // whole rows: one linear copy (a 2-D copy is issued row by row: 2^20 rows of 8 bytes take 2.7 ms)
-      CK(cudaMemcpyAsync(up, host, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
+      CK(cudaMemcpyAsync(up, host, (size_t)h_direct * w * 4, cudaMemcpyHostToDevice, c->copy_stream));
     else
-      CK(cudaMemcpy2DAsync(up, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h, cudaMemcpyHostToDevice,
+      CK(cudaMemcpy2DAsync(up, (size_t)nc * 4, host + c0, (size_t)w * 4, (size_t)nc * 4, h_direct, cudaMemcpyHostToDevice,
                            c->copy_stream));
     CK(cudaEventRecord(c->slab_up[b], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->slab_up[b], 0));
+    if (via_helper) CK(cudaStreamWaitEvent(c->stream, c->helper_done[b], 0));
     if (ncp > nc) {  // dense rows -> even pitch, padding column zeroed
       const unsigned blocks = (unsigned)std::min<uint64_t>((h + 7) / 8, 148 * 16);
       ZK_LAUNCH(spread_rows_kernel, blocks, 256, 0, c->stream, up, buf, nc, ncp, h);

@@ -38,6 +38,14 @@ struct zk_ctx {
   uint64_t slab_seq = 0;
   bool slab_used[NSLAB] = {false, false};
   cudaEvent_t slab_up[NSLAB] = {nullptr, nullptr}, slab_free[NSLAB] = {nullptr, nullptr};
+  // Upload helper (zk_ctx_set_upload_helper): an IDLE peer GPU whose PCIe link carries the second half of the rows of
+  // every slab; the half lands in a staging buffer there and is forwarded over NVLink (cudaMemcpyPeerAsync).
+  int helper_dev = -1;
+  cudaStream_t helper_stream[NSLAB] = {nullptr, nullptr};
+  cudaEvent_t helper_done[NSLAB] = {nullptr, nullptr};
+  uint32_t* helper_stage[NSLAB] = {nullptr, nullptr};
+  uint64_t helper_cap = 0;
+  uint64_t helper_min_bytes = 16ull << 20;  // smaller slabs go up directly
   uint32_t slab_cols = 0;               // fixed columns per slab (multiple of 16; env ZK_SLAB_COLS); 0 = by size
   uint64_t slab_bytes = 256ull << 20;   // target slab size of the streaming commit (env ZK_SLAB_MB)
   uint64_t hash_vec_min_rows = 1ull << 19;  // streamed sponge: vector-load kernel from this many rows (env ZK_HASH_VEC_MIN_ROWS)

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "zk_air_info": (i32, [i32, vp]),
     "zk_permutation_trace": (i32, [vp, i32, u64, u64, u64, u32p, u64p, u32p]),
     "zk_ctx_keep_traces": (i32, [vp, i32]),
+    "zk_ctx_set_upload_helper": (i32, [vp, i32]),
     "zk_pdata_trace": (u64, [vp, u32]),
     "zk_quotient": (i32, [vp, i32, vp, u32, vp, u32, vp, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p, u64p]),
     "zk_challenger_init": (i32, [vp]),
@@ -342,6 +343,10 @@ class Ctx:
 
     def keep_traces(self, on=True):
         self.lib.check(self.d.zk_ctx_keep_traces(self.h, 1 if on else 0))
+
+    def set_upload_helper(self, device):
+        """An idle peer GPU whose PCIe link carries half of every trace slab (forwarded over NVLink); -1: off."""
+        self.lib.check(self.d.zk_ctx_set_upload_helper(self.h, int(device)))
 
     def air_info(self, air_name):
         aid = self.d.zk_air_find(air_name.encode())
