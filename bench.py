@@ -61,7 +61,7 @@ def emit_json(obj):
 def kernel_traffic(name):
     """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (or None)"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")) as fh:
             return json.load(fh)[name]["dram_bytes_per_launch"]
     except Exception:
         return None
@@ -70,12 +70,12 @@ def kernel_traffic(name):
 def int_pipe_note(name, log_rows, cols):
     """integer-pipe utilisation of the kernel from the committed ncu --set full capture (the kernel's real bound)"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")) as fh:
             k = json.load(fh)[name]
         perms = (1 << (log_rows + LOG_BLOWUP)) * (cols // 8)
         return (f"ncu: fmaheavy {k['fmaheavy_pct']} %, alu {k['alu_pct']} %, issue slots {k['issue_pct']} % busy, "
                 f"{32 * k['warp_instructions'] / perms:.0f} thread instructions per permutation, instruction-cache hit rate "
-                f"{k['icc_hit_pct']} % (profiles/r1_ncu_full_final.csv)")
+                f"{k['icc_hit_pct']} % (profiles/r2_ncu_full_final.csv)")
     except Exception:
         return None
 
