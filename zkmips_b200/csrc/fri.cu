@@ -164,10 +164,15 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
           continue;
         }
         uint32_t gL = kbh::two_adic_generator(L);
-        if (w >= 64)
-          ZK_LAUNCH_COOP(fri::row_reduce_warp_kernel, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch,
-                         d_apow_split, d_rowred);
-        else
+        if (w >= 64) {
+          if (H % 4 == 0) {  // one warp per four rows
+            auto kfn = fri::row_reduce_warp_kernel<4>;
+            ZK_LAUNCH_COOP(kfn, (unsigned)((H / 4 * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split, d_rowred);
+          } else {
+            auto kfn = fri::row_reduce_warp_kernel<1>;
+            ZK_LAUNCH_COOP(kfn, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split, d_rowred);
+          }
+        } else
           ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split,
                          d_rowred);
         c->launches++;

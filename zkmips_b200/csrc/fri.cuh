@@ -179,34 +179,51 @@ __global__ void __launch_bounds__(256) row_reduce_kernel(const uint32_t* __restr
   if (r < H) st_ext(rowred + 4 * r, acc.reduce());
 }
 
-// Same for wide matrices: one WARP per row, lanes stride the columns (coalesced), partial sums combined with
-// shuffles.  The thread-per-row form above leaves most of the machine idle when the LDE has few, long rows.
+// Same for wide matrices: one WARP per R consecutive rows, lanes stride the columns (coalesced), partial sums combined
+// with shuffles.  The thread-per-row form above leaves most of the machine idle when the LDE has few, long rows.
+// R = 4: the split alpha powers of a column (two 16-byte loads) are fetched once and used for four rows, whose four
+// data loads are in flight together -- with one row per warp the kernel had 128 bytes in flight per warp and as much
+// L1 traffic for the powers as eight times its data (1.7 TB/s); 16-byte data loads with a lane owning four adjacent
+// columns were tried and are 3x SLOWER (every load of the powers then touches 32 lines instead of 8).
+template <int R>
 __global__ void __launch_bounds__(256) row_reduce_warp_kernel(const uint32_t* __restrict__ mat, uint64_t H, uint32_t w,
                                                               uint32_t pitch, const uint32_t* __restrict__ apow_split,
                                                               uint32_t* __restrict__ rowred) {
   const uint32_t lane = threadIdx.x & 31;
-  uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= H) return;
-  const uint32_t* row = mat + r * pitch;
+  const uint64_t r0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
+  if (r0 >= H) return;
+  const uint32_t* row = mat + r0 * pitch;
   const uint4* A = reinterpret_cast<const uint4*>(apow_split);
-  Acc4 acc;
-  acc.zero();
-  for (uint32_t j = lane; j < w; j += 32) acc.fma(__ldg(A + 2 * j), __ldg(A + 2 * j + 1), __ldg(row + j));
-  kb::Ext e = acc.reduce();
+  Acc4 acc[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) acc[k].zero();
+  for (uint32_t j = lane; j < w; j += 32) {
+    uint32_t v[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) v[k] = __ldg(row + (size_t)k * pitch + j);
+    const uint4 al = __ldg(A + 2 * j), ah = __ldg(A + 2 * j + 1);
+#pragma unroll
+    for (int k = 0; k < R; k++) acc[k].fma(al, ah, v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    kb::Ext e = acc[k].reduce();
 #ifdef ZK_EMU  // the test-only emulator has no lock-step lanes: combine through shared memory instead
-  __shared__ uint32_t sh[256 * 4];
-  st_ext(sh + 4 * threadIdx.x, e);
-  __syncthreads();
-  if (lane == 0)
-    for (int l = 1; l < 32; l++) e = kb::ext_add(e, ld_ext(sh + 4 * (threadIdx.x + l)));
+    __shared__ uint32_t sh[256 * 4];
+    __syncthreads();
+    st_ext(sh + 4 * threadIdx.x, e);
+    __syncthreads();
+    if (lane == 0)
+      for (int l = 1; l < 32; l++) e = kb::ext_add(e, ld_ext(sh + 4 * (threadIdx.x + l)));
 #else
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) e.c[k] = kb::add(e.c[k], __shfl_xor_sync(0xffffffffu, e.c[k], off));
-  }
+      for (int c = 0; c < 4; c++) e.c[c] = kb::add(e.c[c], __shfl_xor_sync(0xffffffffu, e.c[c], off));
+    }
 #endif
-  if (lane == 0) st_ext(rowred + 4 * r, e);
+    if (lane == 0) st_ext(rowred + 4 * (r0 + k), e);
+  }
 }
 
 // Denominators of one opening point over a whole LDE domain, computed ONCE per (height, point) and shared by every
@@ -255,12 +272,17 @@ __global__ void __launch_bounds__(256) inv_den_kernel(const uint32_t* __restrict
 // narrow matrices (w = 2, 4: Fibonacci, quotient chunks) still use every thread; a lane owns CPL adjacent
 // columns (64-bit loads when CPL == 2); row lanes stride the chunk and are reduced in shared memory.
 constexpr int BARY_ROWS = 2048;  // rows per chunk
+constexpr int BARY_STAGE = 128;  // rows of weights staged in shared memory at a time
 template <int CPL>
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __restrict__ mat, uint32_t n, uint32_t w,
                                                            uint32_t pitch, const uint32_t* __restrict__ wts0,
                                                            const uint32_t* __restrict__ wts1, uint32_t npts,
                                                            uint32_t log_cw, uint32_t* __restrict__ partial) {
+  // The weights of a row are the same for every column: they are staged through shared memory (coalesced loads, then
+  // broadcast reads) instead of four 16-byte global loads per row and thread, and the matrix loads of four rows are
+  // issued before their products -- the first version had one 8-byte load in flight per thread and ran at 0.5 TB/s.
   __shared__ uint32_t red[2 * CPL * 4][256];
+  __shared__ uint4 sw[2][BARY_STAGE * 2];
   const uint32_t cw = 1u << log_cw, nrl = 256u >> log_cw;
   const uint32_t lane = threadIdx.x & (cw - 1), rl = threadIdx.x >> log_cw;
   const uint32_t ntile = (w + cw * CPL - 1) / (cw * CPL);
@@ -274,23 +296,58 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t* __res
 #pragma unroll
     for (int c = 0; c < CPL; c++) acc[p][c].zero();
   const uint4* W[2] = {reinterpret_cast<const uint4*>(wts0), reinterpret_cast<const uint4*>(wts1)};  // per point: N x 8 words
-  if (col < w) {
-    for (uint64_t r = r0 + rl; r < r1; r += nrl) {
-      uint32_t v[CPL];
-      if constexpr (CPL == 2) {
-        uint2 x = __ldg(reinterpret_cast<const uint2*>(mat + r * pitch + col));
-        v[0] = x.x;
-        v[1] = x.y;
-      } else {
-        v[0] = __ldg(mat + r * pitch + col);
-      }
+  const bool active = col < w;
+  for (uint64_t s0 = r0; s0 < r1; s0 += BARY_STAGE) {
+    const uint32_t ns = (uint32_t)min((uint64_t)BARY_STAGE, r1 - s0);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2 * ns * npts; i += 256) {
+      const uint32_t p = i / (2 * ns), k = i - p * 2 * ns;
+      sw[p][k] = __ldg(W[p] + 2 * s0 + k);
+    }
+    __syncthreads();
+    if (active) {
+      // this thread's rows of the stage: rl, rl + nrl, ... ; four at a time
+      uint32_t t = rl;
+      for (; t + 3 * nrl < ns; t += 4 * nrl) {
+        uint32_t v[4][CPL];
 #pragma unroll
-      for (int p = 0; p < 2; p++) {
-        if ((uint32_t)p < npts) {
-          uint4 wl = __ldg(W[p] + 2 * r), wh = __ldg(W[p] + 2 * r + 1);
-#pragma unroll
-          for (int c = 0; c < CPL; c++) acc[p][c].fma(wl, wh, v[c]);
+        for (int u = 0; u < 4; u++) {
+          const uint32_t* src = mat + (s0 + t + u * nrl) * pitch + col;
+          if constexpr (CPL == 2) {
+            uint2 x = __ldg(reinterpret_cast<const uint2*>(src));
+            v[u][0] = x.x;
+            v[u][1] = x.y;
+          } else {
+            v[u][0] = __ldg(src);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int p = 0; p < 2; p++)
+            if ((uint32_t)p < npts) {
+              const uint4 wl = sw[p][2 * (t + u * nrl)], wh = sw[p][2 * (t + u * nrl) + 1];
+#pragma unroll
+              for (int c = 0; c < CPL; c++) acc[p][c].fma(wl, wh, v[u][c]);
+            }
+      }
+      for (; t < ns; t += nrl) {
+        uint32_t v[CPL];
+        const uint32_t* src = mat + (s0 + t) * pitch + col;
+        if constexpr (CPL == 2) {
+          uint2 x = __ldg(reinterpret_cast<const uint2*>(src));
+          v[0] = x.x;
+          v[1] = x.y;
+        } else {
+          v[0] = __ldg(src);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+          if ((uint32_t)p < npts) {
+            const uint4 wl = sw[p][2 * t], wh = sw[p][2 * t + 1];
+#pragma unroll
+            for (int c = 0; c < CPL; c++) acc[p][c].fma(wl, wh, v[c]);
+          }
       }
     }
   }
