@@ -176,6 +176,40 @@ int32_t zk_quotient(zk_ctx* ctx, int32_t air_id, const zk_pdata* prep, uint32_t 
 int32_t zk_permutation_trace(zk_ctx* ctx, int32_t air_id, zk_dptr prep_trace, zk_dptr main_trace, uint64_t height,
                              const uint32_t perm_challenges[8], zk_dptr* out_trace, uint32_t local_cumsum[4]);
 
+/* ---- device trace generation ---------------------------------------------------------------------------------------
+ * Batched device twins of the per-row trace fillers the reference calls through its own C FFI:
+ *   poseidon2_wide_event_to_row_koalabear / poseidon2_wide_instr_to_row_koalabear (crates/recursion/core/src/sys.rs:104-112,
+ *     C++ crates/recursion/core/include/poseidon2_wide.hpp:148-208; callers chips/poseidon2_wide/trace.rs:76-108,183-262),
+ *   add_sub_event_to_row_koalabear (crates/core/machine/src/sys.rs:23; C++ crates/core/machine/include/add_sub.hpp:24-39),
+ * and of the Rust `event_to_row` of BitwiseChip and LtChip (crates/core/machine/src/alu/bitwise/mod.rs:141-170,
+ * alu/lt/mod.rs:179-262).  One call fills the whole padded trace (rows = power of two >= n_events; padding exactly as
+ * `generate_trace` pads: zero rows for the ALU chips, the row of the all-zero input for Poseidon2) in a device buffer
+ * that goes straight into zk_commit_dev and is freed with zk_dev_free: only the events cross PCIe.
+ * The `_dev` variants read events already on the device. */
+typedef struct { /* AluEvent, #[repr(C)]: crates/core/executor/src/events/instr.rs:10-26 */
+  uint32_t pc, next_pc;
+  uint8_t opcode; /* crates/core/executor/src/opcode.rs:14-76 */
+  uint8_t pad_[3];
+  uint32_t hi, a, b, c;
+} zk_alu_event;
+enum { ZK_CHIP_ADD_SUB = 0, ZK_CHIP_BITWISE = 1, ZK_CHIP_LT = 2 };
+uint32_t zk_tracegen_alu_width(int32_t chip); /* 19 / 18 / 36 main columns; 0 for an unknown chip */
+int32_t zk_tracegen_alu(zk_ctx* ctx, int32_t chip, const zk_alu_event* events_host, uint64_t n_events, uint64_t rows,
+                        zk_dptr* out_trace);
+int32_t zk_tracegen_alu_dev(zk_ctx* ctx, int32_t chip, zk_dptr events_dev, uint64_t n_events, uint64_t rows,
+                            zk_dptr* out_trace);
+/* Poseidon2WideChip<DEGREE>: inputs = n_events x 16 Montgomery words (Poseidon2Event::input); sbox_state = 1 for
+ * DEGREE 3 (313 columns), 0 for DEGREE 9 (172 columns). */
+uint32_t zk_tracegen_poseidon2_wide_width(int32_t sbox_state);
+int32_t zk_tracegen_poseidon2_wide(zk_ctx* ctx, const uint32_t* inputs_host, uint64_t n_events, uint64_t rows,
+                                   int32_t sbox_state, zk_dptr* out_trace);
+int32_t zk_tracegen_poseidon2_wide_dev(zk_ctx* ctx, zk_dptr inputs_dev, uint64_t n_events, uint64_t rows,
+                                       int32_t sbox_state, zk_dptr* out_trace);
+/* preprocessed trace: instrs = n x 48 words (Poseidon2SkinnyInstr: input addrs[16], output addrs[16], mults[16]) ->
+ * rows x 49 (Poseidon2PreprocessedColsWide); padding rows are zero */
+int32_t zk_tracegen_poseidon2_wide_prep(zk_ctx* ctx, const uint32_t* instrs_host, uint64_t n, uint64_t rows,
+                                        zk_dptr* out_trace);
+
 /* ---- DuplexChallenger<Val, Perm, 16, 8> (crates/stark/src/kb31_poseidon2.rs:180; semantics restated at
  *      crates/recursion/circuit/src/challenger.rs:90-233) ------------------------------------------------
  * The 34-word image of a Plonky3 DuplexChallenger: sponge_state, input_buffer (+ length), output_buffer

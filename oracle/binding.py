@@ -60,6 +60,9 @@ def lib():
         L.ork_from_monty_vec.argtypes = [_u32p, _u32p, C.c_uint64]
         L.ork_poseidon2_permute.argtypes = [_u32p]
         L.ork_poseidon2_permute_canonical.argtypes = [_u32p]
+        L.ork_poseidon2_wide_trace.argtypes = [_u32p, C.c_uint64, C.c_uint64, C.c_int32, _u32p]
+        L.ork_poseidon2_wide_prep.argtypes = [_u32p, C.c_uint64, C.c_uint64, _u32p]
+        L.ork_add_sub_trace.argtypes = [_u32p, C.c_uint64, C.c_uint64, _u32p]
         L.ork_hash.argtypes = [_u32p, C.c_uint64, _u32p]
         L.ork_compress.argtypes = [_u32p, _u32p, _u32p]
         L.ork_hash_rows.argtypes = [_u32p, C.c_uint64, C.c_uint64, _u32p]
@@ -120,6 +123,10 @@ def ref():
             getattr(R, f).restype = C.c_uint32
             getattr(R, f).argtypes = [C.c_uint32]
         R.ref_poseidon2_permute.argtypes = [_u32p]
+        if hasattr(R, "ref_poseidon2_wide_event_to_row"):
+            R.ref_poseidon2_wide_event_to_row.argtypes = [_u32p, _u32p, C.c_int]
+            R.ref_poseidon2_wide_instr_to_row.argtypes = [_u32p, _u32p]
+            R.ref_add_sub_event_to_row.argtypes = [_u32p, _u32p]
         _ref = R
     return _ref
 
@@ -150,6 +157,28 @@ def permute_canonical(state):
     s = np.ascontiguousarray(state, dtype=np.uint32).copy()
     lib().ork_poseidon2_permute_canonical(_ptr(s))
     return s
+
+
+def poseidon2_wide_trace(inputs, rows, sbox=True):
+    """Poseidon2WideChip<3|9> main trace (rows x 313 | 172) from [n, 16] Montgomery inputs; padding = zero-input row"""
+    x = np.ascontiguousarray(inputs, dtype=np.uint32).reshape(-1, 16)
+    out = np.empty((rows, 313 if sbox else 172), np.uint32)
+    lib().ork_poseidon2_wide_trace(_ptr(x), len(x), rows, int(sbox), _ptr(out))
+    return out
+
+
+def poseidon2_wide_prep(instrs, rows):
+    x = np.ascontiguousarray(instrs, dtype=np.uint32).reshape(-1, 48)
+    out = np.empty((rows, 49), np.uint32)
+    lib().ork_poseidon2_wide_prep(_ptr(x), len(x), rows, _ptr(out))
+    return out
+
+
+def add_sub_trace(events, rows):
+    x = np.ascontiguousarray(events, dtype=np.uint32).reshape(-1, 7)
+    out = np.empty((rows, 19), np.uint32)
+    lib().ork_add_sub_trace(_ptr(x), len(x), rows, _ptr(out))
+    return out
 
 
 def hash_slice(x):

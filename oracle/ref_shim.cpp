@@ -32,3 +32,21 @@ void ref_poseidon2_permute(uint32_t state[16]) {
   for (size_t i = 0; i < WIDTH; i++) state[i] = out[i].val;
 }
 }
+
+// ---- trace fillers (the functions crates/recursion/core/src/sys.rs:104-113 binds) ---------------------------------
+extern "C" {
+// poseidon2_wide::event_to_row (poseidon2_wide.hpp:148-197): one main-trace row of Poseidon2WideChip<DEGREE>
+// (313 words with the S-box columns = DEGREE 3, 172 without = DEGREE 9) from the 16-word permutation input.
+void ref_poseidon2_wide_event_to_row(const uint32_t input[16], uint32_t* row, int sbox_state) {
+  kb31_t in[WIDTH];
+  for (size_t i = 0; i < WIDTH; i++) in[i] = kb31_t(input[i]);
+  poseidon2_wide::event_to_row<kb31_t>(in, reinterpret_cast<kb31_t*>(row), 0, 1, sbox_state != 0);
+}
+// poseidon2_wide::instr_to_row (poseidon2_wide.hpp:199-208): instr = input addrs[16], output addrs[16], mults[16]
+// (Poseidon2SkinnyInstr); cols = input[16], output[16] x {addr, mult}, is_real_neg (49 words).
+void ref_poseidon2_wide_instr_to_row(const uint32_t instr[48], uint32_t cols[49]) {
+  static_assert(sizeof(Poseidon2SkinnyInstr<kb31_t>) == 48 * 4 && sizeof(Poseidon2PreprocessedColsWide<kb31_t>) == 49 * 4);
+  poseidon2_wide::instr_to_row<kb31_t>(*reinterpret_cast<const Poseidon2SkinnyInstr<kb31_t>*>(instr),
+                                       *reinterpret_cast<Poseidon2PreprocessedColsWide<kb31_t>*>(cols));
+}
+}

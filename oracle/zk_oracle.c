@@ -109,6 +109,98 @@ void ork_poseidon2_permute(uint32_t* s) {
     p2_external(s);
   }
 }
+/* ------------------------------------------------------------------------------------------ */
+/* Trace fillers (restated; checked row for row against the reference's own C++ in oracle/_ref) */
+/* ------------------------------------------------------------------------------------------ */
+/* Poseidon2WideChip<DEGREE>::populate_perm (crates/recursion/core/src/chips/poseidon2_wide/trace.rs:271-330,
+ * populate_external_round :332-379, populate_internal_rounds :381-420; C++ twin poseidon2_wide.hpp:10-197).
+ * Row layout = PermutationState then PermutationSBoxState (columns/permutation.rs:20-35):
+ *   external_rounds_state[8][16] | internal_rounds_state[16] | internal_rounds_s0[12] | output_state[16]
+ *   | external_rounds_sbox[8][16] | internal_rounds_sbox[13]           (172 words, 313 with the S-box columns) */
+static void p2_wide_row(const kb_t in[16], kb_t* row, int sbox) {
+  kb_t diag[16], st[16];
+  for (int i = 0; i < 16; i++) diag[i] = kb_to_monty(P2_DIAG_CANON[i]);
+  kb_t* ext = row;             /* [8][16] */
+  kb_t* ist = row + 128;       /* [16]    */
+  kb_t* s0 = row + 144;        /* [12]    */
+  kb_t* out = row + 156;       /* [16]    */
+  kb_t* xsb = row + 172;       /* [8][16] */
+  kb_t* isb = row + 300;       /* [13]    */
+  memcpy(ext, in, 64);
+  for (int r = 0; r < 8; r++) {
+    memcpy(st, ext + 16 * r, 64);
+    if (r == 0) p2_external(st);
+    for (int i = 0; i < 16; i++) {
+      st[i] = p2_cube(kb_add(st[i], P2_EXT_RC[r][i]));
+      if (sbox) xsb[16 * r + i] = st[i];
+    }
+    p2_external(st);
+    if (r == 3) {
+      memcpy(ist, st, 64);
+      for (int k = 0; k < 13; k++) {
+        st[0] = p2_cube(kb_add(st[0], P2_INT_RC[k]));
+        if (sbox) isb[k] = st[0];
+        p2_internal(st, diag);
+        if (k < 12) s0[k] = st[0];
+      }
+      memcpy(ext + 64, st, 64);
+    } else if (r == 7) {
+      memcpy(out, st, 64);
+    } else {
+      memcpy(ext + 16 * (r + 1), st, 64);
+    }
+  }
+}
+/* generate_trace (trace.rs:76-108): one row per event, padding rows = the row of the all-zero input */
+void ork_poseidon2_wide_trace(const uint32_t* inputs, uint64_t n_events, uint64_t rows, int32_t sbox, uint32_t* out) {
+  uint64_t w = sbox ? 313 : 172;
+  kb_t zero[16];
+  memset(zero, 0, sizeof zero);
+#pragma omp parallel for schedule(static)
+  for (uint64_t r = 0; r < rows; r++) p2_wide_row(r < n_events ? inputs + 16 * r : zero, out + r * w, sbox);
+}
+/* generate_preprocessed_trace (trace.rs:183-216): instr = input addrs[16], output addrs[16], mults[16] ->
+ * input[16], output[16] x {addr, mult}, is_real_neg = -1; padding rows are zero */
+void ork_poseidon2_wide_prep(const uint32_t* instrs, uint64_t n, uint64_t rows, uint32_t* out) {
+  memset(out, 0, rows * 49 * sizeof(uint32_t));
+  for (uint64_t r = 0; r < n; r++) {
+    const uint32_t* in = instrs + 48 * r;
+    uint32_t* o = out + 49 * r;
+    for (int i = 0; i < 16; i++) {
+      o[i] = in[i];
+      o[16 + 2 * i] = in[16 + i];
+      o[17 + 2 * i] = in[32 + i];
+    }
+    o[48] = kb_neg(KB_ONE);
+  }
+}
+/* AddSubChip::event_to_row + AddOperation::populate (crates/core/machine/src/alu/add_sub/mod.rs:150-172,
+ * operations/add.rs:26-60; C++ twin crates/core/machine/include/add_sub.hpp).  event = AluEvent #[repr(C)]
+ * {pc, next_pc, opcode:u8 (+3 pad), hi, a, b, c} = 7 words; row = AddSubCols (19 words); padding rows zero. */
+void ork_add_sub_trace(const uint32_t* events, uint64_t n_events, uint64_t rows, uint32_t* out) {
+  memset(out, 0, rows * 19 * sizeof(uint32_t));
+  for (uint64_t r = 0; r < n_events; r++) {
+    const uint32_t* e = events + 7 * r;
+    uint32_t* o = out + 19 * r;
+    int is_add = (e[2] & 0xFF) == 0; /* Opcode::ADD = 0 */
+    uint32_t op1 = is_add ? e[5] : e[4], op2 = e[6], val = op1 + op2;
+    o[0] = kb_from_u32(e[0]);
+    o[1] = kb_from_u32(e[1]);
+    uint32_t carry = 0;
+    for (int k = 0; k < 4; k++) {
+      o[2 + k] = kb_to_monty((val >> (8 * k)) & 0xFF);
+      o[9 + k] = kb_to_monty((op1 >> (8 * k)) & 0xFF);
+      o[13 + k] = kb_to_monty((op2 >> (8 * k)) & 0xFF);
+      if (k < 3) {
+        carry = (((op1 >> (8 * k)) & 0xFF) + ((op2 >> (8 * k)) & 0xFF) + carry) > 0xFF;
+        o[6 + k] = carry ? KB_ONE : 0;
+      }
+    }
+    o[17] = is_add ? KB_ONE : 0;
+    o[18] = is_add ? 0 : KB_ONE;
+  }
+}
+
 void ork_poseidon2_permute_canonical(uint32_t* s) {
   for (int i = 0; i < 16; i++) s[i] = kb_from_u32(s[i]);
   ork_poseidon2_permute(s);

@@ -42,6 +42,10 @@ void ork_from_monty_vec(const uint32_t* m, uint32_t* out, uint64_t n);
 /* ---- Poseidon2 ---- */
 void ork_poseidon2_permute(uint32_t state[16]);                          /* Montgomery in/out */
 void ork_poseidon2_permute_canonical(uint32_t state[16]);                /* canonical in/out (the guest syscall form) */
+/* trace fillers: Poseidon2WideChip<3|9> main / preprocessed trace, AddSubChip main trace (see zk_oracle.c) */
+void ork_poseidon2_wide_trace(const uint32_t* inputs, uint64_t n_events, uint64_t rows, int32_t sbox, uint32_t* out);
+void ork_poseidon2_wide_prep(const uint32_t* instrs, uint64_t n, uint64_t rows, uint32_t* out);
+void ork_add_sub_trace(const uint32_t* events, uint64_t n_events, uint64_t rows, uint32_t* out);
 void ork_hash(const uint32_t* in, uint64_t n, uint32_t out[8]);          /* PaddingFreeSponge<16,8,8> */
 void ork_compress(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]); /* TruncatedPermutation<2,8,16> */
 void ork_hash_rows(const uint32_t* mat, uint64_t h, uint64_t w, uint32_t* digests /* h*8 */);

@@ -1,0 +1,152 @@
+"""Device trace generation (csrc/tracegen.cuh) against the oracle, and the oracle against the REFERENCE's own C++ row
+fillers compiled into oracle/_ref (poseidon2_wide.hpp event_to_row / instr_to_row, add_sub.hpp event_to_row).
+
+The reference's tests for these fillers compare the FFI rows with the Rust rows (crates/recursion/core/src/chips/
+poseidon2_wide/trace.rs tests `generate_trace_deg_3` / `generate_trace_deg_9` / `generate_preprocessed_trace`,
+crates/core/machine/src/alu/add_sub/mod.rs `test_generate_trace_ffi_eq_rust`); here the oracle plays the Rust side."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from zkmips_b200 import synth
+from zkmips_b200.proof import to_monty
+from . import backends
+
+P = 0x7F000001
+
+
+def _inputs(n, seed=1):
+    rng = np.random.default_rng(seed)
+    x = to_monty(rng.integers(0, P, (n, 16), dtype=np.uint64))
+    if n:
+        x[0] = 0                 # the padding row's input as a real event
+    if n > 1:
+        x[1] = to_monty(np.full(16, P - 1, np.uint64))
+    return x
+
+
+def _instrs(n, seed=2):
+    rng = np.random.default_rng(seed)
+    return to_monty(rng.integers(0, P, (n, 48), dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs reference
+@pytest.mark.parametrize("sbox", [True, False])
+def test_oracle_poseidon2_wide_rows_match_reference_cpp(sbox):
+    R = ob.ref()
+    if R is None or not hasattr(R, "ref_poseidon2_wide_event_to_row"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    x = _inputs(40)
+    got = ob.poseidon2_wide_trace(x, 64, sbox)
+    w = got.shape[1]
+    zero = np.zeros(16, np.uint32)
+    for r in range(64):
+        row = np.zeros(w, np.uint32)
+        inp = np.ascontiguousarray(x[r] if r < 40 else zero)
+        R.ref_poseidon2_wide_event_to_row(ob._ptr(inp), ob._ptr(row), int(sbox))
+        assert np.array_equal(row, got[r]), r
+    # output_state is the permutation of the input (poseidon2_wide/trace.rs:311-318 asserts the same)
+    assert np.array_equal(got[5, 156:172], ob.permute(x[5]))
+
+
+def test_oracle_poseidon2_wide_prep_matches_reference_cpp():
+    R = ob.ref()
+    if R is None or not hasattr(R, "ref_poseidon2_wide_instr_to_row"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    ins = _instrs(11)
+    got = ob.poseidon2_wide_prep(ins, 16)
+    for r in range(11):
+        row = np.zeros(49, np.uint32)
+        R.ref_poseidon2_wide_instr_to_row(ob._ptr(np.ascontiguousarray(ins[r])), ob._ptr(row))
+        assert np.array_equal(row, got[r])
+    assert not got[11:].any()
+
+
+def test_oracle_add_sub_rows_match_reference_cpp_and_numpy():
+    ev, n = synth.add_sub_events(7)
+    got = ob.add_sub_trace(ev, n)
+    assert np.array_equal(got, to_monty(synth.add_sub_rows(ev, n)))
+    R = ob.ref()
+    if R is None or not hasattr(R, "ref_add_sub_event_to_row"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    for r in range(len(ev)):
+        row = np.zeros(19, np.uint32)
+        R.ref_add_sub_event_to_row(ob._ptr(np.ascontiguousarray(ev[r])), ob._ptr(row))
+        assert np.array_equal(row, got[r]), r
+
+
+# ------------------------------------------------------------------------------------------------ device vs oracle
+def _check_poseidon2_wide(ctx, n_events, rows, sbox):
+    x = _inputs(n_events, seed=rows + n_events)
+    dptr, w = ctx.tracegen_poseidon2_wide(x, rows, sbox)
+    got = ctx.download(dptr, (rows, w))
+    ctx.dev_free(dptr)
+    assert np.array_equal(got, ob.poseidon2_wide_trace(x, rows, sbox))
+
+
+def _check_alu(ctx, chip, log_n, fill):
+    events_of = {"AddSub": synth.add_sub_events, "Bitwise": synth.bitwise_events, "Lt": synth.lt_events}[chip]
+    rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows}[chip]
+    ev, n = events_of(log_n, fill=fill)
+    dptr, w = ctx.tracegen_alu(chip, ev, n)
+    got = ctx.download(dptr, (n, w))
+    ctx.dev_free(dptr)
+    assert np.array_equal(got, to_monty(rows_of(ev, n)))
+
+
+def _check_prep(ctx, n, rows):
+    ins = _instrs(n)
+    dptr, w = ctx.tracegen_poseidon2_wide_prep(ins, rows)
+    got = ctx.download(dptr, (rows, w))
+    ctx.dev_free(dptr)
+    assert np.array_equal(got, ob.poseidon2_wide_prep(ins, rows))
+
+
+def test_tracegen_emu():
+    """kernel index math on the CPU emulator (test-only build of the same sources)"""
+    ctx = backends.emu()
+    _check_poseidon2_wide(ctx, 100, 256, True)
+    _check_poseidon2_wide(ctx, 3, 8, False)
+    for chip in ("AddSub", "Bitwise", "Lt"):
+        _check_alu(ctx, chip, 8, 0.7)
+    _check_prep(ctx, 5, 8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sbox", [True, False])
+@pytest.mark.parametrize("n_events,rows", [(0, 1), (1, 1), (5, 8), (127, 128), (129, 256), (40000, 1 << 16), (1 << 14, 1 << 14)])
+def test_tracegen_poseidon2_wide_gpu(n_events, rows, sbox):
+    _check_poseidon2_wide(backends.gpu(), n_events, rows, sbox)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chip", ["AddSub", "Bitwise", "Lt"])
+@pytest.mark.parametrize("log_n,fill", [(0, 1.0), (3, 0.5), (7, 1.0), (12, 0.75), (17, 0.9)])
+def test_tracegen_alu_gpu(chip, log_n, fill):
+    _check_alu(backends.gpu(), chip, log_n, fill)
+
+
+@pytest.mark.gpu
+def test_tracegen_prep_and_commit_gpu():
+    """the generated trace goes straight into zk_commit_dev: root equals the oracle's commit of the oracle's trace"""
+    ctx = backends.gpu()
+    _check_prep(ctx, 1000, 1024)
+    x = _inputs(3000)
+    rows = 4096
+    dptr, w = ctx.tracegen_poseidon2_wide(x, rows, True)
+    one = int(to_monty(np.array([1]))[0])  # trace-domain shift 1
+    root, pd = ctx.commit_dev([dptr], [(rows, w)], [one], 1)
+    tree = ob.pcs_commit([ob.poseidon2_wide_trace(x, rows, True)], 1)
+    assert np.array_equal(root, tree.root)
+    pd.free()
+    ctx.dev_free(dptr)
+
+
+@pytest.mark.gpu
+def test_tracegen_errors_gpu():
+    from zkmips_b200.native import ZkError
+    ctx = backends.gpu()
+    with pytest.raises(ZkError):
+        ctx.tracegen_poseidon2_wide(_inputs(9), 8, True)     # more events than rows
+    with pytest.raises(ZkError):
+        ctx.tracegen_alu("AddSub", synth.add_sub_events(4)[0], 12)  # not a power of two

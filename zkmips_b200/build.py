@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libzkgpu.so")
-SOURCES = ["zkgpu.cu", "ntt_fwd.cu", "ntt_inv.cu", "ntt_tma_fwd.cu", "ntt_tma_inv.cu", "fri.cu", "quotient.cu"]  # + csrc/gen/airs_kernels_*.cu (generated)
+SOURCES = ["zkgpu.cu", "ntt_fwd.cu", "ntt_inv.cu", "ntt_tma_fwd.cu", "ntt_tma_inv.cu", "fri.cu", "quotient.cu", "tracegen.cu"]  # + csrc/gen/airs_kernels_*.cu (generated)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--compiler-options", "-fPIC", "-Xptxas", "-v",

@@ -1,0 +1,228 @@
+// tracegen.cuh -- main / preprocessed trace rows filled on the device from event records: batched twins of the per-row
+// fillers the reference calls through its own C FFI (crates/recursion/core/src/sys.rs:20-113 ->
+// crates/recursion/core/include/*.hpp, crates/core/machine/src/sys.rs:14-42 -> crates/core/machine/include/*.hpp) and
+// of the Rust `event_to_row` of three ALU chips.  The reference fills rows on the CPU and the prover then uploads the
+// whole trace; here only the events cross PCIe (64 B per Poseidon2 permutation instead of a 1252-byte row, 28 B per ALU
+// event instead of 76..144 B) and the rows are written straight into the buffer zk_commit_dev reads.
+//
+// All kernels: one thread per row, 128 rows per CTA; rows are staged in shared memory and leave the CTA as contiguous
+// runs (a 128-row block of a dense row-major matrix is one contiguous range), so HBM sees full-sector writes whatever
+// the row width.  HBM-bound by construction (a row of 313 words costs ONE permutation; hashing it costs 40).
+#pragma once
+#include "kb31.cuh"
+#include "poseidon2.cuh"
+
+namespace tg {
+
+constexpr int ROWS = 128;  // rows (= threads) per CTA
+
+// ---- Poseidon2WideChip<DEGREE>::generate_trace (crates/recursion/core/src/chips/poseidon2_wide/trace.rs:76-108,
+//      populate_perm :271-330; C++ twin poseidon2_wide.hpp:96-197).  Row layout (columns/permutation.rs:20-35):
+//      external_rounds_state[8][16] | internal_rounds_state[16] | internal_rounds_s0[12] | output_state[16]
+//      | external_rounds_sbox[8][16] | internal_rounds_sbox[13]       -- 172 words (DEGREE 9), 313 with S-boxes (DEGREE 3)
+//      Padding rows are the row of the all-zero input (trace.rs:97-103), not zeros.
+constexpr uint32_t P2W_INT_STATE = 128, P2W_S0 = 144, P2W_OUT = 156, P2W_EXT_SBOX = 172, P2W_INT_SBOX = 300;
+constexpr uint32_t P2W_WIDTH_NO_SBOX = 172, P2W_WIDTH_SBOX = 313;
+
+template <bool SBOX>
+__global__ void __launch_bounds__(ROWS) poseidon2_wide_rows(const uint32_t* __restrict__ inputs, uint64_t n_events,
+                                                            uint64_t rows, uint32_t* __restrict__ out) {
+  constexpr uint32_t W = SBOX ? P2W_WIDTH_SBOX : P2W_WIDTH_NO_SBOX;
+  __shared__ uint32_t tile[ROWS][17];
+  __shared__ uint32_t s0t[ROWS][13];
+  __shared__ uint32_t sbt[ROWS][13];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
+  // 16 words of each of the CTA's rows -> columns [col, col + 16) of the trace, 64 contiguous bytes per row
+  auto emit = [&](const uint32_t (&v)[16], uint32_t col) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; i++) tile[tid][i] = v[i];
+    __syncthreads();
+    for (uint32_t idx = tid; idx < ROWS * 16; idx += ROWS) {
+      uint32_t r = idx >> 4, c = idx & 15;
+      if (row0 + r < rows) out[(row0 + r) * W + col + c] = tile[r][c];
+    }
+  };
+  for (uint32_t idx = tid; idx < ROWS * 16; idx += ROWS) {
+    uint32_t r = idx >> 4, c = idx & 15;
+    tile[r][c] = row0 + r < n_events ? inputs[(row0 + r) * 16 + c] : 0u;
+  }
+  __syncthreads();
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = tile[tid][i];
+  emit(s, 0);  // external_rounds_state[0] = input
+  p2::external_layer(s);
+#pragma unroll 1
+  for (int r = 0; r < 8; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = p2::sbox(s[i], p2::EXT_RC[r][i]);
+    if (SBOX) emit(s, P2W_EXT_SBOX + 16 * r);
+    p2::external_layer(s);
+    if (r == 3) {
+      emit(s, P2W_INT_STATE);
+#pragma unroll 1
+      for (int k = 0; k < 13; k++) {
+        s[0] = p2::sbox(s[0], p2::INT_RC[k]);
+        sbt[tid][k] = s[0];
+        p2::internal_layer(s);
+        s0t[tid][k] = s[0];  // k = 12 is not a column (it is external_rounds_state[4][0])
+      }
+      __syncthreads();
+      for (uint32_t idx = tid; idx < ROWS * 12; idx += ROWS) {
+        uint32_t rr = idx / 12, c = idx % 12;
+        if (row0 + rr < rows) out[(row0 + rr) * W + P2W_S0 + c] = s0t[rr][c];
+      }
+      if (SBOX)
+        for (uint32_t idx = tid; idx < ROWS * 13; idx += ROWS) {
+          uint32_t rr = idx / 13, c = idx % 13;
+          if (row0 + rr < rows) out[(row0 + rr) * W + P2W_INT_SBOX + c] = sbt[rr][c];
+        }
+      emit(s, 16 * 4);  // external_rounds_state[4] = state after the internal rounds
+    } else if (r == 7) {
+      emit(s, P2W_OUT);
+    } else {
+      emit(s, 16 * (r + 1));
+    }
+  }
+}
+
+// ---- generate_preprocessed_trace (trace.rs:183-216; instr_to_row poseidon2_wide.hpp:199-208):
+//      instr = input addrs[16], output addrs[16], mults[16]  ->  input[16], output[16] x {addr, mult}, is_real_neg = -1
+__global__ void poseidon2_wide_prep_rows(const uint32_t* __restrict__ instrs, uint64_t n, uint64_t rows,
+                                         uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 49) return;
+  uint64_t r = i / 49;
+  uint32_t c = (uint32_t)(i % 49);
+  uint32_t v = 0;
+  if (r < n) {
+    const uint32_t* in = instrs + r * 48;
+    if (c < 16) v = in[c];
+    else if (c < 48) v = ((c - 16) & 1) ? in[32 + ((c - 16) >> 1)] : in[16 + ((c - 16) >> 1)];
+    else v = kb::P - kb::ONE;
+  }
+  out[i] = v;
+}
+
+// ---- ALU chips from `AluEvent` records (#[repr(C)], crates/core/executor/src/events/instr.rs:10-26: 7 words, the
+//      opcode in the low byte of word 2).  Each filler writes CANONICAL values into its zeroed staging row; the flush
+//      converts to Montgomery form.  Padding rows (>= n_events) stay zero, as the reference pads.
+struct AluEv {
+  uint32_t pc, next_pc, opcode, hi, a, b, c;
+};
+
+// AddSubChip::event_to_row + AddOperation::populate (crates/core/machine/src/alu/add_sub/mod.rs:150-172,
+// operations/add.rs:26-60; C++ twin crates/core/machine/include/add_sub.hpp:8-39)
+struct AddSub {
+  static constexpr uint32_t W = 19;
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    bool is_add = e.opcode == 0;  // Opcode::ADD
+    uint32_t op1 = is_add ? e.b : e.a, op2 = e.c, val = op1 + op2, carry = 0;
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = (op1 >> (8 * k)) & 0xFF, y = (op2 >> (8 * k)) & 0xFF;
+      t[2 + k] = (val >> (8 * k)) & 0xFF;
+      t[9 + k] = x;
+      t[13 + k] = y;
+      carry = (x + y + carry) > 0xFF;
+      if (k < 3) t[6 + k] = carry;
+    }
+    t[17] = is_add;
+    t[18] = !is_add;
+  }
+};
+
+// BitwiseChip::event_to_row (crates/core/machine/src/alu/bitwise/mod.rs:141-170)
+struct Bitwise {
+  static constexpr uint32_t W = 18;
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      t[2 + k] = (e.a >> (8 * k)) & 0xFF;
+      t[6 + k] = (e.b >> (8 * k)) & 0xFF;
+      t[10 + k] = (e.c >> (8 * k)) & 0xFF;
+    }
+    t[14] = e.opcode == 18;  // NOR
+    t[15] = e.opcode == 17;  // XOR
+    t[16] = e.opcode == 16;  // OR
+    t[17] = e.opcode == 15;  // AND
+  }
+};
+
+// LtChip::event_to_row (crates/core/machine/src/alu/lt/mod.rs:179-262)
+struct Lt {
+  static constexpr uint32_t W = 36;
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    const uint32_t is_slt = e.opcode == 13;  // Opcode::SLT (SLTU = 14)
+    uint32_t bb[4], cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      bb[k] = (e.b >> (8 * k)) & 0xFF;
+      cb[k] = (e.c >> (8 * k)) & 0xFF;
+      t[8 + k] = bb[k];
+      t[12 + k] = cb[k];
+    }
+    uint32_t b_masked = bb[3] & 0x7F, c_masked = cb[3] & 0x7F;
+    uint32_t bc3 = is_slt ? b_masked : bb[3], cc3 = is_slt ? c_masked : cb[3];
+    uint32_t x = 0, y = 0, sltu = 0, found = 0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {  // most significant differing byte
+      uint32_t bk = k == 3 ? bc3 : bb[k], ck = k == 3 ? cc3 : cb[k];
+      uint32_t hit = !found && bk != ck;
+      t[16 + k] = hit;
+      if (hit) { x = bk; y = ck; sltu = bk < ck; found = 1; }
+    }
+    uint32_t msb_b = bb[3] >> 7, msb_c = cb[3] >> 7;
+    uint32_t is_sign_eq = is_slt ? (msb_b == msb_c) : 1u;
+    uint32_t bit_b = msb_b & is_slt, bit_c = msb_c & is_slt;
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+    t[2] = is_slt;
+    t[3] = !is_slt;
+    t[4] = bit_b * (1 - bit_c) + is_sign_eq * sltu;  // a[0]; a[1..3] = 0
+    t[20] = b_masked;
+    t[21] = c_masked;
+    // not_eq_inv = 1 / (comparison_bytes[0] - comparison_bytes[1]) when they differ
+    t[22] = found ? kb::from_monty(kb::inv(kb::to_monty(x >= y ? x - y : x + kb::P - y))) : 0u;
+    t[23] = msb_b;
+    t[24] = msb_c;
+    t[25] = bit_b;
+    t[26] = bit_c;
+    t[27] = sltu;
+    t[28] = !found;  // is_comp_eq
+    t[29] = is_sign_eq;
+    t[30] = x;
+    t[31] = y;
+    // t[32..36] = byte_equality_check: allocated by the reference, never written
+  }
+};
+
+template <class CHIP>
+__global__ void __launch_bounds__(ROWS) alu_rows(const uint32_t* __restrict__ events, uint64_t n_events, uint64_t rows,
+                                                 uint32_t* __restrict__ out) {
+  constexpr uint32_t W = CHIP::W;
+  __shared__ uint32_t ev[ROWS * 7];
+  __shared__ uint32_t tile[ROWS][W + 1];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
+  for (uint32_t idx = tid; idx < ROWS * 7; idx += ROWS) ev[idx] = row0 * 7 + idx < n_events * 7 ? events[row0 * 7 + idx] : 0u;
+  for (uint32_t c = 0; c < W; c++) tile[tid][c] = 0u;
+  __syncthreads();
+  if (row0 + tid < n_events) {
+    const uint32_t* e = ev + 7 * tid;
+    AluEv a{e[0], e[1], e[2] & 0xFFu, e[3], e[4], e[5], e[6]};
+    CHIP::fill(a, tile[tid]);
+  }
+  __syncthreads();
+  uint64_t base = row0 * W, end = rows * W;
+  for (uint32_t idx = tid; idx < ROWS * W; idx += ROWS)
+    if (base + idx < end) out[base + idx] = kb::to_monty(tile[idx / W][idx % W]);
+}
+
+}  // namespace tg

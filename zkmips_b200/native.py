@@ -66,6 +66,13 @@ PROTOTYPES = {
     "zk_ctx_set_upload_helper": (i32, [vp, i32]),
     "zk_pdata_trace": (u64, [vp, u32]),
     "zk_quotient": (i32, [vp, i32, vp, u32, vp, u32, vp, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p, u64p]),
+    "zk_tracegen_alu_width": (u32, [i32]),
+    "zk_tracegen_alu": (i32, [vp, i32, vp, u64, u64, u64p]),
+    "zk_tracegen_alu_dev": (i32, [vp, i32, u64, u64, u64, u64p]),
+    "zk_tracegen_poseidon2_wide_width": (u32, [i32]),
+    "zk_tracegen_poseidon2_wide": (i32, [vp, u32p, u64, u64, i32, u64p]),
+    "zk_tracegen_poseidon2_wide_dev": (i32, [vp, u64, u64, u64, i32, u64p]),
+    "zk_tracegen_poseidon2_wide_prep": (i32, [vp, u32p, u64, u64, u64p]),
     "zk_challenger_init": (i32, [vp]),
     "zk_challenger_observe": (i32, [vp, vp, u32p, u32]),
     "zk_challenger_sample_ext": (i32, [vp, vp, u32, u32p]),
@@ -370,6 +377,41 @@ class Ctx:
         self.lib.check(self.d.zk_permutation_trace(self.h, aid, prep_trace or 0, main_trace, height, _p32(ch),
                                                    C.byref(out), _p32(lcs)))
         return out.value, lcs
+
+    # ---- device trace generation (csrc/tracegen.cuh)
+    ALU_CHIPS = {"AddSub": 0, "Bitwise": 1, "Lt": 2}
+
+    def tracegen_alu(self, chip, events, rows):
+        """`AluEvent` records ([n, 7] uint32, host array or device pointer + count) -> device pointer of the padded
+        rows x width main trace of AddSubChip / BitwiseChip / LtChip, and its width."""
+        cid = self.ALU_CHIPS[chip]
+        out = u64()
+        if isinstance(events, tuple):
+            dptr, n = events
+            self.lib.check(self.d.zk_tracegen_alu_dev(self.h, cid, dptr, n, rows, C.byref(out)))
+        else:
+            ev = _arr(events, np.uint32).reshape(-1, 7)
+            self.lib.check(self.d.zk_tracegen_alu(self.h, cid, ev.ctypes.data_as(vp), len(ev), rows, C.byref(out)))
+        return out.value, self.d.zk_tracegen_alu_width(cid)
+
+    def tracegen_poseidon2_wide(self, inputs, rows, sbox_state=True):
+        """Poseidon2WideChip<3 | 9> main trace from the permutation inputs ([n, 16] Montgomery words, host array or
+        (device pointer, n)); returns (device pointer, width)."""
+        out = u64()
+        if isinstance(inputs, tuple):
+            dptr, n = inputs
+            self.lib.check(self.d.zk_tracegen_poseidon2_wide_dev(self.h, dptr, n, rows, int(sbox_state), C.byref(out)))
+        else:
+            x = _arr(inputs, np.uint32).reshape(-1, 16)
+            self.lib.check(self.d.zk_tracegen_poseidon2_wide(self.h, _p32(x), len(x), rows, int(sbox_state), C.byref(out)))
+        return out.value, self.d.zk_tracegen_poseidon2_wide_width(int(sbox_state))
+
+    def tracegen_poseidon2_wide_prep(self, instrs, rows):
+        """Poseidon2WideChip preprocessed trace from [n, 48] instruction words; returns (device pointer, 49)."""
+        x = _arr(instrs, np.uint32).reshape(-1, 48)
+        out = u64()
+        self.lib.check(self.d.zk_tracegen_poseidon2_wide_prep(self.h, _p32(x), len(x), rows, C.byref(out)))
+        return out.value, 49
 
     def download(self, dptr, shape):
         out = np.empty(shape, np.uint32)

@@ -169,14 +169,33 @@ def _events(log_n, seed, fill):
     return n, real, rng, pc, b, c
 
 
-def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub"):
-    """AddSubChip::event_to_row + AddOperation::populate (alu/add_sub/mod.rs:150-172, operations/add.rs:26-60)"""
+def _alu_event_array(pc, opcode, a, b, c):
+    """`AluEvent` records in their #[repr(C)] layout (crates/core/executor/src/events/instr.rs:10-26): u32 pc, next_pc,
+    u8 opcode (+ 3 padding bytes), u32 hi, a, b, c = 7 words -- what `zk_tracegen_alu` takes."""
+    ev = np.zeros((len(pc), 7), np.uint32)
+    ev[:, 0], ev[:, 1], ev[:, 2] = pc, (np.asarray(pc, np.uint64) + 4) % P, opcode
+    ev[:, 4], ev[:, 5], ev[:, 6] = a, b, c
+    return ev
+
+
+def add_sub_events(log_n, seed=21, fill=0.75):
+    """random ADD / SUB events: (events [real, 7], padded height)"""
     n, real, rng, pc, b, c = _events(log_n, seed, fill)
     is_add = rng.integers(0, 2, real).astype(np.uint64)
     mask = np.uint64(0xFFFFFFFF)
     a = np.where(is_add == 1, (b + c) & mask, (b - c) & mask)       # ADD: a = b + c;  SUB: a = b - c
-    op1 = np.where(is_add == 1, b, a)                               # operand_1: b for ADD, a for SUB
-    op2 = c
+    return _alu_event_array(pc, np.where(is_add == 1, 0, 1), a, b, c), n
+
+
+def add_sub_rows(events, n):
+    """AddSubChip::event_to_row + AddOperation::populate (alu/add_sub/mod.rs:150-172, operations/add.rs:26-60):
+    canonical rows, zero padding"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    is_add = (ev[:, 2] & np.uint64(0xFF)) == 0
+    mask = np.uint64(0xFFFFFFFF)
+    op1 = np.where(is_add, ev[:, 5], ev[:, 4])                      # operand_1: b for ADD, a for SUB
+    op2 = ev[:, 6]
     value = (op1 + op2) & mask
     x, y = _bytes(op1), _bytes(op2)
     carry = np.zeros((real, 3), np.uint64)
@@ -184,39 +203,68 @@ def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub"):
     carry[:, 1] = (x[:, 1] + y[:, 1] + carry[:, 0]) > 255
     carry[:, 2] = (x[:, 2] + y[:, 2] + carry[:, 1]) > 255
     t = np.zeros((n, 19), np.uint64)
-    t[:real, 0], t[:real, 1] = pc, (pc + 4) % P
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
     t[:real, 2:6], t[:real, 6:9] = _bytes(value), carry
     t[:real, 9:13], t[:real, 13:17] = x, y
-    t[:real, 17], t[:real, 18] = is_add, 1 - is_add
+    t[:real, 17], t[:real, 18] = is_add, ~is_add
+    return t
+
+
+def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub"):
+    ev, n = add_sub_events(log_n, seed, fill)
+    t = add_sub_rows(ev, n)
     ch = Chip(name, "AddSub", M(t), local_only=True)
-    ch.canon = (None, t)
+    ch.canon, ch.events = (None, t), ev
     return ch
 
 
-def bitwise_chip(log_n, seed=22, fill=0.75, name="Bitwise"):
-    """BitwiseChip::event_to_row (alu/bitwise/mod.rs:141-170)"""
+def bitwise_events(log_n, seed=22, fill=0.75):
     n, real, rng, pc, b, c = _events(log_n, seed, fill)
     op = rng.integers(0, 4, real)  # 0 nor, 1 xor, 2 or, 3 and
     mask = np.uint64(0xFFFFFFFF)
     a = np.select([op == 0, op == 1, op == 2], [~(b | c) & mask, b ^ c, b | c], b & c)
+    return _alu_event_array(pc, np.array([18, 17, 16, 15])[op], a, b, c), n   # Opcode::NOR / XOR / OR / AND
+
+
+def bitwise_rows(events, n):
+    """BitwiseChip::event_to_row (alu/bitwise/mod.rs:141-170)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
     t = np.zeros((n, 18), np.uint64)
-    t[:real, 0], t[:real, 1] = pc, (pc + 4) % P
-    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(a), _bytes(b), _bytes(c)
-    for k in range(4):
-        t[:real, 14 + k] = op == k
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(ev[:, 4]), _bytes(ev[:, 5]), _bytes(ev[:, 6])
+    for k, opc in enumerate((18, 17, 16, 15)):                      # is_nor, is_xor, is_or, is_and
+        t[:real, 14 + k] = (ev[:, 2] & np.uint64(0xFF)) == opc
+    return t
+
+
+def bitwise_chip(log_n, seed=22, fill=0.75, name="Bitwise"):
+    ev, n = bitwise_events(log_n, seed, fill)
+    t = bitwise_rows(ev, n)
     ch = Chip(name, "Bitwise", M(t), local_only=True)
-    ch.canon = (None, t)
+    ch.canon, ch.events = (None, t), ev
     return ch
 
 
-def lt_chip(log_n, seed=23, fill=0.75, name="Lt"):
-    """LtChip::event_to_row (alu/lt/mod.rs:179-262)"""
+def lt_events(log_n, seed=23, fill=0.75):
     n, real, rng, pc, b, c = _events(log_n, seed, fill)
     eq = rng.integers(0, 8, real) == 0
     c = np.where(eq, b, c)                                          # some equal operands (is_comp_eq = 1)
     near = rng.integers(0, 4, real) == 0
     c = np.where(near & ~eq, (b & np.uint64(0xFFFF0000)) | (c & np.uint64(0xFFFF)), c)  # differ in a LOW byte only
     is_slt = rng.integers(0, 2, real).astype(np.uint64)
+    bs = np.where(b >= (1 << 31), b.astype(np.int64) - (1 << 32), b.astype(np.int64))
+    cs = np.where(c >= (1 << 31), c.astype(np.int64) - (1 << 32), c.astype(np.int64))
+    a = np.where(is_slt == 1, bs < cs, b < c).astype(np.uint64)
+    return _alu_event_array(pc, np.where(is_slt == 1, 13, 14), a, b, c), n   # Opcode::SLT / SLTU
+
+
+def lt_rows(events, n):
+    """LtChip::event_to_row (alu/lt/mod.rs:179-262)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    b, c = ev[:, 5], ev[:, 6]
+    is_slt = ((ev[:, 2] & np.uint64(0xFF)) == 13).astype(np.uint64)
     bb, cb = _bytes(b), _bytes(c)
     b_masked, c_masked = bb[:, 3] & np.uint64(0x7F), cb[:, 3] & np.uint64(0x7F)
     b_comp, c_comp = bb.copy(), cb.copy()
@@ -240,13 +288,20 @@ def lt_chip(log_n, seed=23, fill=0.75, name="Lt"):
     is_sign_eq = np.where(is_slt == 1, msb_b == msb_c, 1).astype(np.uint64)
     bit_b, bit_c = msb_b * is_slt, msb_c * is_slt
     a0 = bit_b * (1 - bit_c) + is_sign_eq * sltu
-    t[:real, 0], t[:real, 1], t[:real, 2], t[:real, 3] = pc, (pc + 4) % P, is_slt, 1 - is_slt
+    t[:real, 0], t[:real, 1], t[:real, 2], t[:real, 3] = ev[:, 0], ev[:, 1], is_slt, 1 - is_slt
     t[:real, 4] = a0
     t[:real, 8:12], t[:real, 12:16], t[:real, 16:20] = bb, cb, flags
     t[:real, 20], t[:real, 21], t[:real, 22] = b_masked, c_masked, inv
     t[:real, 23], t[:real, 24], t[:real, 25], t[:real, 26] = msb_b, msb_c, bit_b, bit_c
     t[:real, 27], t[:real, 28], t[:real, 29] = sltu, ~done, is_sign_eq
     t[:real, 30:32] = cmp_bytes
+    return t
+
+
+def lt_chip(log_n, seed=23, fill=0.75, name="Lt"):
+    ev, n = lt_events(log_n, seed, fill)
+    t = lt_rows(ev, n)
+    assert np.array_equal(t[:len(ev), 4], np.asarray(ev[:, 4], np.uint64)), "LtChip row disagrees with the event's a"
     ch = Chip(name, "Lt", M(t), local_only=True)
-    ch.canon = (None, t)
+    ch.canon, ch.events = (None, t), ev
     return ch
