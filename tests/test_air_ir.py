@@ -13,7 +13,8 @@ EXPORTED = os.path.join(ROOT, "zkmips_b200", "air", "exported")
 def test_exported_json_reproduces_the_generated_kernels():
     """Loading zkmips_b200/air/exported/<Chip>.json (what a recording-builder exporter would write) must give the same
     program as the hand transcription: identical JSON again, and byte-identical generated CUDA."""
-    for make in (library.add_sub, library.lt, library.bitwise):
+    for make in (library.add_sub, library.lt, library.bitwise, lambda: library.poseidon2_wide(3),
+                 lambda: library.poseidon2_wide(9)):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -38,3 +39,66 @@ def test_real_chip_shapes_match_mips_costs():
         assert air.num_constraints == own + (air.perm_width - 1) + 3
         assert air.local_only and air.commit_scope == "local"
         assert air.max_degree() == 3  # log_quotient_degree 1
+
+
+def _constraints_on_trace(air, main, prep=None, seed=5):
+    """every constraint of `air` (own + LogUp) on the trace domain itself: rows local / next, selectors as indicator
+    vectors, permutation trace from the numpy LogUp restatement.  All must vanish on a valid trace."""
+    import numpy as np
+    from oracle import air_eval as ae, logup
+    rng = np.random.default_rng(seed)
+    n = main.shape[0]
+    chal = [[int(x) for x in rng.integers(1, ae.P, 4)] for _ in range(2)]
+    perm, lcs = logup.generate_permutation_trace(air, prep, main, chal[0], chal[1])
+    nxt = (np.arange(n) + 1) % n
+    rows = {"main": (main, main[nxt]), "perm": (perm, perm[nxt])}
+    if prep is not None:
+        rows["prep"] = (prep, prep[nxt])
+    first, last = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    first[0], last[n - 1] = 1, 1
+    sel = {"first": first, "last": last, "trans": 1 - last}
+    out = []
+    for c in ae.eval_rows(air, rows, sel, chal, lcs, (0,) * 14, ()):
+        out.append(np.stack(c.c) if isinstance(c, ae.VExt) else np.asarray(c))
+    return out
+
+
+def test_poseidon2_wide_air_vanishes_on_the_reference_fillers_rows():
+    """Poseidon2WideChip<3> / <9> as transcribed (library.poseidon2_wide) against rows produced by the oracle filler,
+    which is itself checked against the reference's C++ filler (tests/test_tracegen.py): a valid trace satisfies every
+    constraint, a corrupted cell breaks at least one.  Shapes: 313 / 172 main columns, 49 preprocessed columns
+    (chips/poseidon2_wide/columns), 32 memory lookups."""
+    import numpy as np
+    from oracle import binding as ob
+    from zkmips_b200.proof import to_monty
+    rng = np.random.default_rng(11)
+    n_ev, rows = 13, 16
+    x = to_monty(rng.integers(0, ae_P, (n_ev, 16), dtype=np.uint64))
+    instrs = to_monty(rng.integers(0, ae_P, (n_ev, 48), dtype=np.uint64))
+    prep = ob.from_monty(ob.poseidon2_wide_prep(instrs, rows)).astype(np.uint64)
+    for degree, width, own in ((3, 313, 298), (9, 172, 157)):
+        air = library.poseidon2_wide(degree)
+        assert (air.main_width, air.prep_width, len(air.sends), len(air.receives)) == (width, 49, 32, 0)
+        assert air.max_degree() == degree and air.local_only
+        bs = 2 if degree == 3 else 8
+        assert air.perm_width == 32 // bs + 1 and air.num_constraints == own + (air.perm_width - 1) + 3
+        main = ob.from_monty(ob.poseidon2_wide_trace(x, rows, degree == 3)).astype(np.uint64)
+        vals = _constraints_on_trace(air, main, prep)
+        assert len(vals) == air.num_constraints and all(not v.any() for v in vals)
+        bad = main.copy()
+        bad[3, 130] = (bad[3, 130] + 1) % ae_P           # one cell of internal_rounds_state
+        assert any(v.any() for v in _constraints_on_trace(air, bad, prep)[:own])
+
+
+def test_alu_airs_vanish_on_their_fillers_rows():
+    from zkmips_b200 import synth
+    import numpy as np
+    for make, events, rows in ((library.add_sub, synth.add_sub_events, synth.add_sub_rows),
+                               (library.lt, synth.lt_events, synth.lt_rows),
+                               (library.bitwise, synth.bitwise_events, synth.bitwise_rows)):
+        ev, n = events(5)
+        vals = _constraints_on_trace(make(), rows(ev, n))
+        assert all(not v.any() for v in vals)
+
+
+ae_P = 0x7F000001

@@ -25,9 +25,18 @@ def _natural(lde_bitrev):
     return ob.from_monty(lde_bitrev[idx])
 
 
+def p2w_host_chip(log_n, degree, **kw):
+    """Poseidon2WideDeg{3,9} with a HOST main trace from the oracle filler (the CPU provers and the quotient oracle need
+    one; the product fills these rows on the device)"""
+    c = synth.poseidon2_wide_chip(log_n, degree, **kw)
+    c.main = ob.poseidon2_wide_trace(c.events, c.rows, degree == 3)
+    c.canon = (ob.from_monty(c.preprocessed).astype(np.uint64), ob.from_monty(c.main).astype(np.uint64))
+    return c
+
+
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
-                                   "Lt", "Bitwise"])
+                                   "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -39,19 +48,23 @@ def test_quotient_values_match_oracle(be, which):
             "local_bool": lambda: su.local_bool_chip(4),
             # real Ziren chips transcribed from their Air::eval (library.add_sub / lt / bitwise), real lookups
             "AddSub": lambda: synth.add_sub_chip(6), "Lt": lambda: synth.lt_chip(6),
-            "Bitwise": lambda: synth.bitwise_chip(5)}[which]()
+            "Bitwise": lambda: synth.bitwise_chip(5),
+            # recursion chip (library.poseidon2_wide): 313 / 172 main + 49 preprocessed columns, 32 memory sends;
+            # DEGREE 9 has log_quotient_degree 3 (8 chunks, LogUp batches of 8)
+            "Poseidon2WideDeg3": lambda: p2w_host_chip(5, 3), "Poseidon2WideDeg9": lambda: p2w_host_chip(3, 9)}[which]()
+    lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
     air = su.AIRS[chip.air]
     n = chip.log_degree
-    _, main_pd = ctx.commit([chip.main], [MONTY_ONE], 1)
+    _, main_pd = ctx.commit([chip.main], [MONTY_ONE], lqd)
     prep_pd = perm_pd = None
     chal = su.M(np.arange(10, 18).reshape(2, 4))
     alpha = su.M([3, 1, 4, 1])
     kw = {}
     okw = {}
     if chip.preprocessed is not None:
-        _, prep_pd = ctx.commit([chip.preprocessed], [MONTY_ONE], 1)
+        _, prep_pd = ctx.commit([chip.preprocessed], [MONTY_ONE], lqd)
         kw["prep"] = (prep_pd, 0)
         okw["prep_q"] = _natural(prep_pd.lde(0))
     lcs = None
@@ -65,20 +78,21 @@ def test_quotient_values_match_oracle(be, which):
         tr = ctx.download(dptr, exp_tr.shape)
         assert (ob.from_monty(tr) == exp_tr).all()
         assert list(ob.from_monty(lcs)) == exp_lcs
-        _, perm_pd = ctx.commit([tr], [MONTY_ONE], 1)
+        _, perm_pd = ctx.commit([tr], [MONTY_ONE], lqd)
         kw["perm"] = (perm_pd, 0)
         okw["perm_q"] = _natural(perm_pd.lde(0))
         okw["lcs"] = ob.from_monty(lcs)
     pvs = su.public_values_for([chip])
     gcs = su.M(np.arange(1, 15))
-    dptr = ctx.quotient(chip.air, (main_pd, 0), n, 1, alpha, perm_challenges=chal, public_values=pvs,
+    dptr = ctx.quotient(chip.air, (main_pd, 0), n, lqd, alpha, perm_challenges=chal, public_values=pvs,
                         local_cumsum=lcs, global_cumsum=gcs, **kw)
-    got = ob.from_monty(ctx.download(dptr, (2, 1 << n, 4)))
+    got = ob.from_monty(ctx.download(dptr, (1 << lqd, 1 << n, 4)))
     ctx.dev_free(dptr)
-    exp = ae.quotient_values(air, n, 1, _natural(main_pd.lde(0)), ob.from_monty(alpha), chal=ob.from_monty(chal),
+    exp = ae.quotient_values(air, n, lqd, _natural(main_pd.lde(0)), ob.from_monty(alpha), chal=ob.from_monty(chal),
                              gcs=ob.from_monty(gcs), pvs=ob.from_monty(pvs), **okw)
-    # chunk c holds the rows i = c (mod 2)
-    assert (got[0] == exp[0::2]).all() and (got[1] == exp[1::2]).all()
+    # chunk c holds the rows i = c (mod 2^lqd)
+    for c in range(1 << lqd):
+        assert (got[c] == exp[c::1 << lqd]).all(), c
     # the quotient of a valid trace is a polynomial of degree < 2N: its top half of coefficients vanish, which
     # the FRI low-degree test checks in test_shard_proof_verifies; here: not identically zero
     assert exp.any()
@@ -210,6 +224,41 @@ def test_real_alu_chips_shard(be):
     opk.observe_into(och)
     assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))) == pf.to_bincode(sp)
     data.main_data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_recursion_chips_from_events_shard(be):
+    """a compress-shaped shard of Poseidon2WideDeg3 (the recursion machine's widest chip) and the ALU
+    chips, whose main traces never exist on the host: the prover gets EVENTS (16-word permutation inputs, 7-word
+    AluEvents), fills the rows on the device (zk_tracegen_*) and commits them from HBM.  The proof must be byte-identical
+    to the CPU prover's, which is given the rows the oracle fillers produce (those are checked against the reference's
+    own C++ fillers in tests/test_tracegen.py)."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    logs = (5, 6, 4) if be == "emu" else (12, 13, 11)
+    dev_chips = [synth.poseidon2_wide_chip(logs[0]), synth.add_sub_chip(logs[1], device=True),
+                 synth.lt_chip(logs[2], device=True), su.fibonacci_chip(4)]
+    assert all(c.main is None for c in dev_chips[:3])
+    host_chips = [p2w_host_chip(logs[0], 3), synth.add_sub_chip(logs[1]), synth.lt_chip(logs[2]), su.fibonacci_chip(4)]
+    prover, pk, data, sp = _prove(ctx, dev_chips, 1, nq, pw)
+    assert len(data.device_traces) == 4
+    assert (data.main_commit == ob.pcs_commit([c.main for c in prover.order(host_chips)], 1).root).all()
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=NUM_PV)
+    opk = op.setup(host_chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    assert (opk.commit == pk.commit).all()
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    want = op.prove(opk, host_chips, och, su.public_values_for(host_chips, NUM_PV))
+    assert pf.to_bincode(want) == pf.to_bincode(sp)
+    # every per-chip check of the verifier passes (the memory / byte / instruction buses are answered by chips that are
+    # not in this shard, so only the final sum check can fail)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(host_chips), [sp], NUM_PV, 1, nq, pw)
+    assert not ok and why.endswith("local cumulative sum is not zero"), why
+    data.free()
+    pk.data.free()
 
 
 @pytest.mark.parametrize("drop", ["public_values", "vk", "local_sum", "global_sum", "perm_commit", "local_only"])

@@ -282,8 +282,126 @@ def lt():
     return air
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Recursion chip: Poseidon2WideChip<DEGREE> (crates/recursion/core/src/chips/poseidon2_wide/air.rs:34-178), the widest
+# chip of the compress / shrink provers (RecursionAir<F, 3> / <F, 9>, crates/recursion/core/src/machine.rs).  Columns:
+# chips/poseidon2_wide/columns/permutation.rs:20-35 (main), columns/preprocessed.rs:8-14 (preprocessed).
+# ------------------------------------------------------------------------------------------------------------------
+def _poseidon2_round_constants():
+    """canonical RC_16_30_U32 rows as the chip indexes them (crates/primitives/src/lib.rs:563-1104): 8 external rounds
+    (round r < 4 -> row r, else row r + 13) and column 0 of the 13 internal rows, read from the generated header the
+    CUDA kernels and the oracle use"""
+    import os
+    import re
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "include",
+                             "zk_poseidon2_rc.h")).read().replace("\\\n", " ")
+    def table(name):
+        body = re.search(r"#define " + name + r"\s+(.*)", text).group(1)
+        return [int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)u", body)]
+    ext = table("ZK_P2_EXT_RC_CANON")
+    return [ext[16 * r:16 * r + 16] for r in range(8)], table("ZK_P2_INT_RC_CANON")
+
+
+P = 0x7F000001
+P2_DIAG = [P - 2, 1, 2, (P + 1) >> 1, 3, 4, (P - 1) >> 1, P - 3, P - 4, P - ((P - 1) >> 8), P - ((P - 1) >> 3), P - 127,
+           (P - 1) >> 8, (P - 1) >> 3, (P - 1) >> 4, 127]  # chips/poseidon2_wide/mod.rs:85-102
+
+
+def _apply_m_4(x):
+    """chips/poseidon2_wide/mod.rs:46-60"""
+    t01 = x[0] + x[1]
+    t23 = x[2] + x[3]
+    t0123 = t01 + t23
+    t01123 = t0123 + x[1]
+    t01233 = t0123 + x[3]
+    return [t01123 + t01, t01123 + (x[2] + x[2]), t01233 + t23, t01233 + (x[0] + x[0])]
+
+
+def _external_linear_layer(state):
+    """chips/poseidon2_wide/mod.rs:63-74"""
+    st = []
+    for j in range(0, 16, 4):
+        st += _apply_m_4(state[j:j + 4])
+    sums = [st[k] + st[4 + k] + st[8 + k] + st[12 + k] for k in range(4)]
+    return [st[j] + sums[j % 4] for j in range(16)]
+
+
+def _internal_linear_layer(state):
+    """chips/poseidon2_wide/mod.rs:104-114 -> p3_poseidon2::matmul_internal: state[i] * diag[i] + sum"""
+    total = state[0]
+    for x in state[1:]:
+        total = total + x
+    return [state[i] * P2_DIAG[i] + total for i in range(16)]
+
+
+def poseidon2_wide(degree=3):
+    """Poseidon2WideChip<DEGREE>::eval, statement by statement.  DEGREE 3 carries the S-box columns (313 main columns),
+    DEGREE 9 does not (172); 49 preprocessed columns; 32 memory sends; 1 + 8 * 16 (+ 8 * 16) + 12 + 16 (+ 13)
+    constraints before the permutation argument; `local_only`."""
+    assert degree in (3, 9)
+    sbox_cols = degree == 3
+    ext_rc, int_rc = _poseidon2_round_constants()
+    air = Air(f"Poseidon2WideDeg{degree}", main_width=313 if sbox_cols else 172, prep_width=49, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    p = b.preprocessed().local()
+    ext_state = [m[16 * r:16 * r + 16] for r in range(8)]
+    int_state, s0, out = m[128:144], m[144:156], m[156:172]
+    ext_sbox = [m[172 + 16 * r:188 + 16 * r] for r in range(8)] if sbox_cols else None
+    int_sbox = m[300:313] if sbox_cols else None
+    prep_input = p[0:16]
+    prep_output = [(p[16 + 2 * i], p[17 + 2 * i]) for i in range(16)]   # MemoryAccessColsChips {addr, mult}
+    is_real_neg = p[48]
+    # air.rs:45-52: dummy constraint that normalises the chip to DEGREE
+    x00 = ext_state[0][0]
+    lhs = x00
+    for _ in range(degree - 1):
+        lhs = lhs * x00
+    b.assert_eq(lhs, lhs)
+    # air.rs:55-69: memory lookups, send_single(addr, val, mult) = send(Memory, [addr, val, 0, 0, 0], mult)
+    # (crates/recursion/core/src/builder.rs:19-44)
+    for i in range(16):
+        b.send(LOOKUP_MEMORY, [prep_input[i], ext_state[0][i], 0, 0, 0], is_real_neg)
+    for i in range(16):
+        b.send(LOOKUP_MEMORY, [prep_output[i][0], out[i], 0, 0, 0], prep_output[i][1])
+    # air.rs:72-74, eval_external_round :83-139
+    for r in range(8):
+        state = list(ext_state[r])
+        if r == 0:
+            state = _external_linear_layer(state)
+        add_rc = [state[i] + ext_rc[r][i] for i in range(16)]
+        sb = []
+        for i in range(16):
+            cube = add_rc[i] * add_rc[i] * add_rc[i]
+            if sbox_cols:
+                b.assert_eq(ext_sbox[r][i], cube)
+                sb.append(ext_sbox[r][i])
+            else:
+                sb.append(cube)
+        state = _external_linear_layer(sb)
+        nxt = int_state if r == 3 else out if r == 7 else ext_state[r + 1]
+        for i in range(16):
+            b.assert_eq(nxt[i], state[i])
+    # eval_internal_rounds, air.rs:142-177
+    state = list(int_state)
+    for r in range(13):
+        add_rc = (state[0] if r == 0 else s0[r - 1]) + int_rc[r]
+        cube = add_rc * add_rc * add_rc
+        if sbox_cols:
+            b.assert_eq(int_sbox[r], cube)
+            cube = int_sbox[r]
+        state[0] = cube
+        state = _internal_linear_layer(state)
+        if r < 12:
+            b.assert_eq(s0[r], state[0])
+    for i in range(16):
+        b.assert_eq(ext_state[4][i], state[i])
+    b.eval_permutation_constraints(batch_size=2 if degree == 3 else 8)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
-            local_bool(), add_sub(), lt(), bitwise()]
+            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9)]

@@ -47,15 +47,24 @@ class Chip:
     are properties of the chip's AIR (MachineAir::local_only / commit_scope) and must agree with the compiled AIR."""
     name: str
     air: str
-    main: np.ndarray
+    main: Optional[np.ndarray]           # None: the main trace is generated on the device from `events` (see below)
     preprocessed: Optional[np.ndarray] = None
     local_only: bool = False
     commit_scope: str = "local"          # "local" | "global" (LookupScope)
     log_quotient_degree: int = 1
+    # device trace generation (MachineAir::generate_trace on the GPU, csrc/tracegen.cuh): the event records of the
+    # shard's ExecutionRecord for this chip, the filler's name and the padded height (MachineAir::num_rows)
+    events: Optional[np.ndarray] = None
+    tracegen: Optional[str] = None       # "AddSub" | "Bitwise" | "Lt" | "Poseidon2WideDeg3" | "Poseidon2WideDeg9"
+    rows: Optional[int] = None
+
+    @property
+    def height(self):
+        return int(self.main.shape[0]) if self.main is not None else int(self.rows)
 
     @property
     def log_degree(self):
-        return int(self.main.shape[0]).bit_length() - 1
+        return self.height.bit_length() - 1
 
     def global_cumulative_sum(self):
         """prover.rs:353-361: zero for Local-scope chips, else the last 14 words of the main trace"""
@@ -94,6 +103,18 @@ class ShardMainData:
     main_data: object                 # PData
     chip_ordering: Dict[str, int]
     public_values: np.ndarray
+    global_sums: List[np.ndarray] = field(default_factory=list)   # per chip, prover.rs:353-361
+    device_traces: List[int] = field(default_factory=list)        # device buffers the prover data borrows (commit_dev)
+    ctx: object = None
+
+    def free(self):
+        """drop the prover data and the device traces it points into"""
+        if self.main_data is not None:
+            self.main_data.free()
+            self.main_data = None
+        for p in self.device_traces:
+            self.ctx.dev_free(p)
+        self.device_traces = []
 
 
 class GpuShardProver:
@@ -110,7 +131,16 @@ class GpuShardProver:
     @staticmethod
     def order(chips):
         """sort by (-height, name): prover.rs:264"""
-        return sorted(chips, key=lambda c: (-c.main.shape[0], c.name))
+        return sorted(chips, key=lambda c: (-c.height, c.name))
+
+    def generate_trace(self, chip):
+        """MachineAir::generate_trace on the device: (device pointer, width) of the padded main trace of a chip given by
+        its event records (zk_tracegen_*, the batched twins of the reference's per-row FFI fillers)."""
+        if chip.tracegen in self.ctx.ALU_CHIPS:
+            return self.ctx.tracegen_alu(chip.tracegen, chip.events, chip.height)
+        if chip.tracegen in ("Poseidon2WideDeg3", "Poseidon2WideDeg9"):
+            return self.ctx.tracegen_poseidon2_wide(chip.events, chip.height, chip.tracegen.endswith("3"))
+        raise ValueError(f"{chip.name}: no device trace filler named {chip.tracegen!r}")
 
     def setup(self, chips, pc_start=0, initial_global_cumulative_sum=None):
         """StarkMachine::setup (machine.rs:330-440): commit to the preprocessed traces of every chip that has one,
@@ -129,10 +159,31 @@ class GpuShardProver:
         """MachineProver::commit (prover.rs:258-292)."""
         t0 = time.perf_counter()
         chips = self.order(chips)
-        root, pd = self.ctx.commit([c.main for c in chips], [MONTY_ONE] * len(chips), self.log_blowup)
+        dev = []
+        if all(c.main is not None for c in chips):
+            root, pd = self.ctx.commit([c.main for c in chips], [MONTY_ONE] * len(chips), self.log_blowup)
+            gsums = [c.global_cumulative_sum() for c in chips]
+        else:
+            # at least one chip's rows are filled on the device from its events: everything is committed from HBM
+            # (zk_commit_dev borrows the buffers; they are released with the ShardMainData)
+            shapes, gsums = [], []
+            for c in chips:
+                if c.main is None:
+                    ptr, w = self.generate_trace(c)
+                else:
+                    ptr, w = self.ctx.upload(c.main), c.main.shape[1]
+                dev.append(ptr)
+                shapes.append((c.height, w))
+                if c.commit_scope == "local":
+                    gsums.append(np.zeros(14, np.uint32))
+                elif c.main is not None:
+                    gsums.append(c.global_cumulative_sum())
+                else:
+                    gsums.append(self.ctx.download(ptr + 4 * (c.height * w - 14), (14,)))
+            root, pd = self.ctx.commit_dev(dev, shapes, [MONTY_ONE] * len(chips), self.log_blowup)
         self._tick("commit_main", t0)
         return ShardMainData(chips, root, pd, {c.name: i for i, c in enumerate(chips)},
-                             np.asarray(public_values, np.uint32).reshape(-1))
+                             np.asarray(public_values, np.uint32).reshape(-1), gsums, dev, self.ctx)
 
     def open(self, pk: ProvingKey, data: ShardMainData, challenger: Challenger, inject_witness=-1) -> pf.ShardProof:
         """MachineProver::open (prover.rs:298-653)."""
@@ -152,13 +203,13 @@ class GpuShardProver:
             wq = 4 * info["perm_width"]                                  # flatten_to_base, prover.rs:393
             if info["num_lookups"] > 0:
                 prep = pk.data.trace_ptr(pk.chip_ordering[c.name]) if c.name in pk.chip_ordering else 0
-                ptr, lcs = ctx.permutation_trace(c.air, prep, main_pd.trace_ptr(i), c.main.shape[0], perm_challenges)
+                ptr, lcs = ctx.permutation_trace(c.air, prep, main_pd.trace_ptr(i), c.height, perm_challenges)
             else:
                 ptr, lcs = 0, np.zeros(4, np.uint32)                     # width 0: generate_permutation_trace's empty matrix
             ptrs.append(ptr)
-            shapes.append((c.main.shape[0], wq))
+            shapes.append((c.height, wq))
             local_sums.append(np.asarray(lcs, np.uint32))
-            global_sums.append(c.global_cumulative_sum())                # prover.rs:353-361
+            global_sums.append(data.global_sums[i] if data.global_sums else c.global_cumulative_sum())  # prover.rs:353-361
         perm_root, perm_pd = ctx.commit_dev(ptrs, shapes, [MONTY_ONE] * len(ptrs), self.log_blowup)  # prover.rs:401-403
         for ptr in ptrs:
             if ptr:
@@ -253,5 +304,5 @@ class GpuShardProver:
         """MachineProver::prove for one shard (prover.rs:660-693); `challenger` is the per-shard clone."""
         data = self.commit(chips, public_values)
         sp = self.open(pk, data, challenger)
-        data.main_data.free()
+        data.free()
         return sp

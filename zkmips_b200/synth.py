@@ -210,8 +210,12 @@ def add_sub_rows(events, n):
     return t
 
 
-def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub"):
+def add_sub_chip(log_n, seed=21, fill=0.75, name="AddSub", device=False):
+    """`device=True`: no host trace -- the chip carries its AluEvent records and the prover fills the rows on the GPU
+    (zk_tracegen_alu), so only 28 bytes per event cross PCIe."""
     ev, n = add_sub_events(log_n, seed, fill)
+    if device:
+        return Chip(name, "AddSub", None, local_only=True, events=ev, tracegen="AddSub", rows=n)
     t = add_sub_rows(ev, n)
     ch = Chip(name, "AddSub", M(t), local_only=True)
     ch.canon, ch.events = (None, t), ev
@@ -238,8 +242,12 @@ def bitwise_rows(events, n):
     return t
 
 
-def bitwise_chip(log_n, seed=22, fill=0.75, name="Bitwise"):
+def bitwise_chip(log_n, seed=22, fill=0.75, name="Bitwise", device=False):
+    """`device=True`: no host trace -- the chip carries its AluEvent records and the prover fills the rows on the GPU
+    (zk_tracegen_alu), so only 28 bytes per event cross PCIe."""
     ev, n = bitwise_events(log_n, seed, fill)
+    if device:
+        return Chip(name, "Bitwise", None, local_only=True, events=ev, tracegen="Bitwise", rows=n)
     t = bitwise_rows(ev, n)
     ch = Chip(name, "Bitwise", M(t), local_only=True)
     ch.canon, ch.events = (None, t), ev
@@ -298,10 +306,49 @@ def lt_rows(events, n):
     return t
 
 
-def lt_chip(log_n, seed=23, fill=0.75, name="Lt"):
+def lt_chip(log_n, seed=23, fill=0.75, name="Lt", device=False):
+    """`device=True`: no host trace -- the chip carries its AluEvent records and the prover fills the rows on the GPU
+    (zk_tracegen_alu), so only 28 bytes per event cross PCIe."""
     ev, n = lt_events(log_n, seed, fill)
+    if device:
+        return Chip(name, "Lt", None, local_only=True, events=ev, tracegen="Lt", rows=n)
     t = lt_rows(ev, n)
     assert np.array_equal(t[:len(ev), 4], np.asarray(ev[:, 4], np.uint64)), "LtChip row disagrees with the event's a"
     ch = Chip(name, "Lt", M(t), local_only=True)
     ch.canon, ch.events = (None, t), ev
     return ch
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
+# The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
+# preprocessed trace (addresses and multiplicities of the program's Poseidon2 instructions) is a plain scatter.
+# ------------------------------------------------------------------------------------------------------------------
+def poseidon2_wide_events(log_n, seed=31, fill=0.75):
+    """(inputs [real, 16] Montgomery, instrs [real, 48] Montgomery: input addrs, output addrs, mults; padded height)"""
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    real = max(1, int(n * fill)) if n > 1 else 1
+    inputs = to_monty(rng.integers(0, P, (real, 16), dtype=np.uint64))
+    addrs = rng.integers(0, 1 << 24, (real, 32), dtype=np.uint64)
+    mults = rng.integers(0, 4, (real, 16), dtype=np.uint64)
+    return inputs, to_monty(np.concatenate([addrs, mults], axis=1)), n
+
+
+def poseidon2_wide_prep_rows(instrs, n):
+    """Poseidon2WideChip::generate_preprocessed_trace (chips/poseidon2_wide/trace.rs:183-216), Montgomery in / out"""
+    ins = np.asarray(instrs, np.uint32)
+    t = np.zeros((n, 49), np.uint32)
+    real = len(ins)
+    t[:real, 0:16] = ins[:, 0:16]
+    t[:real, 16:48:2] = ins[:, 16:32]
+    t[:real, 17:48:2] = ins[:, 32:48]
+    t[:real, 48] = to_monty(np.array([P - 1], np.uint64))[0]
+    return t
+
+
+def poseidon2_wide_chip(log_n, degree=3, seed=31, fill=0.75, name=None):
+    inputs, instrs, n = poseidon2_wide_events(log_n, seed, fill)
+    air = f"Poseidon2WideDeg{degree}"
+    return Chip(name or air, air, None, preprocessed=poseidon2_wide_prep_rows(instrs, n), local_only=True,
+                log_quotient_degree=1 if degree == 3 else 3, events=inputs, tracegen=air, rows=n)
