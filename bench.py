@@ -325,10 +325,13 @@ def shard_chips(config, rank=0, scale=0):
     keccak: BASELINE config 3, wide_bitwise_4096 at 2^16 rows (6144 degree-3 constraints) + Fibonacci 2^16;
     large : wide_bitwise_1024 2^19, wide_bitwise_64 2^21, Fibonacci 2^21, LogUp pair 2^20 (6.8e8 cells: a maximal
             log-21 execution shard's size);
-    recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:93-103: 2^18, 2^18,
-            2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries), with
-            this library's AIRs standing in for the RecursionAir chips (the real AddSub / Lt / Bitwise chips among them):
-            many small matrices, latency-bound."""
+    recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
+            2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
+            Poseidon2Wide is the REAL chip (library.poseidon2_wide(3): 313 + 49 columns, 32 memory sends) and its rows
+            are filled on the device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide); the ALU
+            stand-ins of BatchFRI / BaseAlu / ExtAlu are the real AddSub / Lt / Bitwise chips, also filled on the device
+            from their AluEvent records; the other RecursionAir chips are this library's synthetic AIRs at the
+            reference's heights.  Many small matrices, latency-bound."""
     from zkmips_b200 import synth
     d = scale
     if config == "keccak":
@@ -341,10 +344,11 @@ def shard_chips(config, rank=0, scale=0):
         send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
         send.name, recv.name = "MemoryVar", "Select"
         return [send, recv, synth.local_bool_chip(16 - d, seed=3 + rank, name="MemoryConst"),
-                synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI"), synth.add_sub_chip(15 - d, seed=5 + rank, name="BaseAlu"),
-                synth.bitwise_chip(15 - d, seed=6 + rank, name="ExtAlu"),
+                synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI", device=True),
+                synth.add_sub_chip(15 - d, seed=5 + rank, name="BaseAlu", device=True),
+                synth.bitwise_chip(15 - d, seed=6 + rank, name="ExtAlu", device=True),
                 synth.wide_chip(17 - d, 64, seed=7 + rank, name="ExpReverseBitsLen"),
-                synth.wide_chip(16 - d, 256, seed=8 + rank, name="Poseidon2Wide"),
+                synth.poseidon2_wide_chip(16 - d, 3, seed=8 + rank, name="Poseidon2Wide"),
                 synth.fibonacci_chip(max(4 - d, 2), 1 + rank, 1, name="PublicValues")]
     send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
     return [synth.wide_chip(16 - d, 1024, seed=11 + rank), synth.wide_chip(18 - d, 64, seed=12 + rank),
@@ -353,9 +357,52 @@ def shard_chips(config, rank=0, scale=0):
 
 def _pin(torch, chips):
     import numpy as np
-    for c in chips:  # the host-side trace buffers are pinned, as the bench contract's e2e path allows
-        c.main = torch.from_numpy(c.main.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).pin_memory().numpy().view(np.uint32)
+    for c in chips:  # the host-side trace (or event) buffers are pinned, as the bench contract's e2e path allows
+        if c.main is not None:
+            c.main = pin(c.main)
+        else:
+            c.events = pin(c.events)
     return chips
+
+
+def chip_width(c):
+    from zkmips_b200.air import library
+    if c.main is not None:
+        return c.main.shape[1]
+    global _AIR_WIDTHS
+    if "_AIR_WIDTHS" not in globals():
+        _AIR_WIDTHS = {a.name: a.main_width for a in library.all_airs()}
+    return _AIR_WIDTHS[c.air]
+
+
+def shard_cells(chips):
+    return sum(c.height * chip_width(c) for c in chips)
+
+
+def shard_h2d_bytes(chips):
+    """bytes that cross PCIe per shard: host traces, or only the events of chips whose rows are filled on the device"""
+    return int(sum(c.main.nbytes if c.main is not None else c.events.nbytes for c in chips))
+
+
+def with_host_traces(chips):
+    """CPU legs only: chips given by events get the rows the ORACLE fillers produce (the reference fills rows on the
+    CPU, crates/recursion/core/src/chips/poseidon2_wide/trace.rs:76-108)"""
+    import copy
+    from oracle import binding as ob
+    from zkmips_b200 import synth
+    from zkmips_b200.proof import to_monty
+    out = []
+    for c in chips:
+        if c.main is None:
+            c = copy.copy(c)
+            if c.tracegen.startswith("Poseidon2Wide"):
+                c.main = ob.poseidon2_wide_trace(c.events, c.rows, c.tracegen.endswith("3"))
+            else:
+                rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows}[c.tracegen]
+                c.main = to_monty(rows_of(c.events, c.rows))
+        out.append(c)
+    return out
 
 
 class ShardWorker:
@@ -377,7 +424,7 @@ class ShardWorker:
     def prove(self, chips):
         data = self.prover.commit(chips, self.pvs)
         sp = self.prover.open(self.pk, data, self.Challenger(self.ctx, self.start))
-        data.main_data.free()
+        data.free()
         return sp
 
 
@@ -390,7 +437,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     import threading
 
     chips = _pin(torch, shard_chips(args.shard_config, rank))
-    cells = sum(c.main.size for c in chips)
+    cells = shard_cells(chips)
     fri = FRI_PARAMS.get(args.shard_config, (1, 84, 16))
     w1 = ShardWorker(ctx, chips, fri)
     sp = w1.prove(chips)  # warm-up (also pages the generated quotient kernels in)
@@ -464,14 +511,15 @@ def shard_leg(ctx, torch, dist, world, rank, args):
         wk.ctx.destroy()
     res = {"config": args.shard_config, "ms_per_shard": dt * 1e3, "shards_per_s": world / dt,
            "trace_cells_per_shard": int(cells),
-           "chips": [f"{c.name}: 2^{c.log_degree} x {c.main.shape[1]}" for c in w1.prover.order(chips)],
+           "chips": [f"{c.name}: 2^{c.log_degree} x {chip_width(c)}" + (" (rows filled on the device from events)" if c.main is None else "")
+                     for c in w1.prover.order(chips)],
            "params": f"log_blowup {fri[0]}, {fri[1]} queries, {fri[2]} PoW bits; reference transcript (prover.rs:298-653)",
            "timing": "host wall clock around commit+open, max over ranks",
            "proof_bytes_bincode": len(blob), "host_phase_ms": phases,
            "device_stage_ms": {k: round(v, 3) for k, v in stage.items()},
            "multi_shard": {"shards": S, "shards_in_flight_per_gpu": args.in_flight, "placement": "shard i -> rank i mod N",
                            "seconds": dtm, "shards_per_s": S / dtm, "cells_per_s": S * cells / dtm, "scaling": "strong",
-                           "h2d_bytes_per_shard": int(4 * cells)}}
+                           "h2d_bytes_per_shard": shard_h2d_bytes(chips)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = shard_cpu_leg(args, ctx, torch, cells)
     return res
@@ -496,17 +544,20 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
         op = osp.OracleShardProver(airs, fri[0], fri[1], fri[2], num_pv_elts=NUM_PV)
         from zkmips_b200 import synth
         pvs = synth.public_values_for(chips, NUM_PV)
-        opk = op.setup(chips)
+        t = time.perf_counter()
+        host_chips = with_host_traces(chips)      # generate_trace on the CPU, as the reference does
+        tracegen_s = time.perf_counter() - t
+        opk = op.setup(host_chips)
         och = bf.new_challenger()
         opk.observe_into(och)
         t = time.perf_counter()
-        osp_proof = op.prove(opk, chips, och, pvs)
-        dt = time.perf_counter() - t
+        osp_proof = op.prove(opk, host_chips, och, pvs)
+        dt = time.perf_counter() - t + tracegen_s
         if dt > 6.0 or scale == 0:
             break
         scale -= 1 if dt > 2.0 else 2
         scale = max(scale, 0)
-    cells = sum(c.main.size for c in chips)
+    cells = shard_cells(chips)
     w = ShardWorker(ctx, chips, fri)
     t = time.perf_counter()
     sp = w.prove(chips)
@@ -518,6 +569,72 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
             "seconds": dt, "cells": int(cells), "gpu_ms_same_sample": gpu_dt * 1e3,
             "proof_matches_oracle": bool(same),
             "extrapolated_ms_per_full_shard": dt * 1e3 * full_cells / cells}
+
+
+def tracegen_leg(ctx, torch, args):
+    """Device trace generation of the recursion machine's widest chip (Poseidon2WideDeg3, 313 columns) at the
+    Poseidon2Wide height of the largest compress shape (2^18 rows, crates/recursion/core/src/shape.rs:160-170):
+    (a) the kernel alone, inputs resident in HBM -- HBM-bound: 64 B read + 1252 B written per row;
+    (b) end to end from pinned host events through zk_tracegen_poseidon2_wide + zk_commit_dev, beside
+    (c) the reference's data flow: the 313-column rows uploaded through zk_commit (rows filled on the CPU beforehand,
+        not timed)."""
+    import numpy as np
+    from zkmips_b200 import synth
+    from zkmips_b200.prover import MONTY_ONE
+    log_n = 18
+    rows = 1 << log_n
+    inputs, _, _ = synth.poseidon2_wide_events(log_n, seed=77, fill=0.9)
+    inputs = torch.from_numpy(inputs.view(np.int32)).pin_memory().numpy().view(np.uint32)
+    n_ev = len(inputs)
+    d_in = ctx.upload(inputs)
+    reps = 5
+    for _ in range(2):
+        ptr, w = ctx.tracegen_poseidon2_wide((d_in, n_ev), rows, True)
+        ctx.dev_free(ptr)
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    for _ in range(reps):
+        ptr, w = ctx.tracegen_poseidon2_wide((d_in, n_ev), rows, True)
+        ctx.dev_free(ptr)
+    ctx.sync()
+    ctx.prof_enable(False)
+    ms = sum(m for name, m, _ in ctx.prof_records() if name == "tracegen") / reps
+    bytes_per_launch = n_ev * 64 + rows * w * 4
+    peak, peak_kind = measured_peaks()
+
+    def e2e_events():
+        ptr, _ = ctx.tracegen_poseidon2_wide(inputs, rows, True)
+        root, pd = ctx.commit_dev([ptr], [(rows, w)], [MONTY_ONE], 1)
+        pd.free()
+        ctx.dev_free(ptr)
+        return root
+
+    host_rows = torch.from_numpy(ctx.download(ctx.tracegen_poseidon2_wide((d_in, n_ev), rows, True)[0], (rows, w)).view(np.int32)
+                                 ).pin_memory().numpy().view(np.uint32)
+
+    def e2e_rows():
+        root, pd = ctx.commit([host_rows], [MONTY_ONE], 1)
+        pd.free()
+        return root
+
+    out = {}
+    for name, fn in (("events_to_commit", e2e_events), ("host_rows_to_commit", e2e_rows)):
+        fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            root = fn()
+        torch.cuda.synchronize()
+        out[name + "_ms"] = (time.perf_counter() - t) / reps * 1e3
+        out[name + "_root"] = [int(x) for x in root]
+    ctx.dev_free(d_in)
+    return {"chip": f"Poseidon2WideDeg3 2^{log_n} x {w}", "events": int(n_ev),
+            "kernel_ms": ms, "algorithmic_bytes": int(bytes_per_launch),
+            "roofline": {"kernel": "tg::poseidon2_wide_rows<true>", "bound": "hbm", "achieved": bytes_per_launch / ms / 1e6,
+                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": bytes_per_launch / ms / 1e6 / peak},
+            "h2d_bytes_events": int(inputs.nbytes), "h2d_bytes_rows": int(host_rows.nbytes),
+            "events_to_commit_ms": out["events_to_commit_ms"], "host_rows_to_commit_ms": out["host_rows_to_commit_ms"],
+            "roots_equal": out["events_to_commit_root"] == out["host_rows_to_commit_root"]}
 
 
 ALL_CPUS = os.sched_getaffinity(0)
@@ -737,6 +854,7 @@ def main():
         out["shard_prove"] = shard_leg(ctx, torch, dist, world, rank, args)
     if not args.no_shard and world == 1:
         out["exec_shard_commit"] = exec_shard_leg(ctx, torch, args)
+        out["tracegen"] = tracegen_leg(ctx, torch, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host core again
         v, cores, sample, _, slog, oroot = cpu_commit_sample(host_np)

@@ -23,6 +23,24 @@ pub const ZK_ERR_CUDA: i32 = -2;
 pub const ZK_ERR_STATE: i32 = -3;
 pub const ZK_ERR_VERIFY: i32 = -4;
 
+/// `zk_alu_event`: the layout of `zkm_core_executor::events::AluEvent` (#[repr(C)], events/instr.rs:10-26), so a
+/// `&[AluEvent]` can be handed over as `*const ZkAluEvent` without a copy.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct ZkAluEvent {
+    pub pc: u32,
+    pub next_pc: u32,
+    pub opcode: u8,
+    pub pad_: [u8; 3],
+    pub hi: u32,
+    pub a: u32,
+    pub b: u32,
+    pub c: u32,
+}
+pub const ZK_CHIP_ADD_SUB: i32 = 0;
+pub const ZK_CHIP_BITWISE: i32 = 1;
+pub const ZK_CHIP_LT: i32 = 2;
+
 /// 34-word image of a Plonky3 `DuplexChallenger<KoalaBear, Perm, 16, 8>`: `sponge_state`, `input_buffer` (+ length),
 /// `output_buffer` (+ length; samples pop from the END).
 #[repr(C)]
@@ -99,6 +117,13 @@ extern "C-unwind" {
     pub fn zk_air_info(id: i32, out: *mut ZkAirDesc) -> i32;
     pub fn zk_quotient(ctx: *mut ZkCtx, air_id: i32, prep: *const ZkPdata, prep_idx: u32, main_data: *const ZkPdata, main_idx: u32, perm: *const ZkPdata, perm_idx: u32, log_degree: u32, log_quotient_degree: u32, alpha: *const u32, perm_challenges: *const u32, public_values: *const u32, n_public_values: u32, local_cumsum: *const u32, global_cumsum: *const u32, out_chunks: *mut ZkDptr) -> i32;
     pub fn zk_permutation_trace(ctx: *mut ZkCtx, air_id: i32, prep_trace: ZkDptr, main_trace: ZkDptr, height: u64, perm_challenges: *const u32, out_trace: *mut ZkDptr, local_cumsum: *mut u32) -> i32;
+    pub fn zk_tracegen_alu_width(chip: i32) -> u32;
+    pub fn zk_tracegen_alu(ctx: *mut ZkCtx, chip: i32, events_host: *const ZkAluEvent, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_alu_dev(ctx: *mut ZkCtx, chip: i32, events_dev: ZkDptr, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_wide_width(sbox_state: i32) -> u32;
+    pub fn zk_tracegen_poseidon2_wide(ctx: *mut ZkCtx, inputs_host: *const u32, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_wide_dev(ctx: *mut ZkCtx, inputs_dev: ZkDptr, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_wide_prep(ctx: *mut ZkCtx, instrs_host: *const u32, n: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_challenger_init(ch: *mut ZkChallenger) -> i32;
     pub fn zk_challenger_observe(ctx: *mut ZkCtx, ch: *mut ZkChallenger, vals: *const u32, n: u32) -> i32;
     pub fn zk_challenger_sample_ext(ctx: *mut ZkCtx, ch: *mut ZkChallenger, n_ext: u32, out: *mut u32) -> i32;
