@@ -27,6 +27,7 @@
 #define __launch_bounds__(...)
 #define __constant__
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };

@@ -31,9 +31,9 @@ int32_t poseidon2_wide(zk_ctx* c, const uint32_t* host, zk_dptr dev, uint64_t n_
   const uint32_t w = sbox ? tg::P2W_WIDTH_SBOX : tg::P2W_WIDTH_NO_SBOX;
   uint32_t* out = nullptr;
   if ((rc = scope.alloc(&out, rows * w * 4ull))) return rc;
-  unsigned grid = (unsigned)((rows + tg::ROWS - 1) / tg::ROWS);
-  if (sbox) ZK_LAUNCH_COOP(tg::poseidon2_wide_rows<true>, grid, tg::ROWS, 0, c->stream, ev, n_events, rows, out);
-  else ZK_LAUNCH_COOP(tg::poseidon2_wide_rows<false>, grid, tg::ROWS, 0, c->stream, ev, n_events, rows, out);
+  unsigned grid = (unsigned)((rows + tg::P2W_ROWS - 1) / tg::P2W_ROWS);
+  if (sbox) ZK_LAUNCH_COOP(tg::poseidon2_wide_rows<true>, grid, tg::P2W_ROWS, 0, c->stream, ev, n_events, rows, out);
+  else ZK_LAUNCH_COOP(tg::poseidon2_wide_rows<false>, grid, tg::P2W_ROWS, 0, c->stream, ev, n_events, rows, out);
   CK(cudaGetLastError());
   c->launches++;
   scope.release(out);

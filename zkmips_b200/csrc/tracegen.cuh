@@ -5,9 +5,9 @@
 // whole trace; here only the events cross PCIe (64 B per Poseidon2 permutation instead of a 1252-byte row, 28 B per ALU
 // event instead of 76..144 B) and the rows are written straight into the buffer zk_commit_dev reads.
 //
-// All kernels: one thread per row, 128 rows per CTA; rows are staged in shared memory and leave the CTA as contiguous
-// runs (a 128-row block of a dense row-major matrix is one contiguous range), so HBM sees full-sector writes whatever
-// the row width.  HBM-bound by construction (a row of 313 words costs ONE permutation; hashing it costs 40).
+// All kernels: one thread per row; whole rows are staged in shared memory and leave the CTA as ONE contiguous run (a
+// block of consecutive rows of a dense row-major matrix is one contiguous range), so HBM sees full-sector writes
+// whatever the row width.  HBM-bound (a row of 313 words costs ONE permutation; hashing it costs 40).
 #pragma once
 #include "kb31.cuh"
 #include "poseidon2.cuh"
@@ -24,67 +24,73 @@ constexpr int ROWS = 128;  // rows (= threads) per CTA
 constexpr uint32_t P2W_INT_STATE = 128, P2W_S0 = 144, P2W_OUT = 156, P2W_EXT_SBOX = 172, P2W_INT_SBOX = 300;
 constexpr uint32_t P2W_WIDTH_NO_SBOX = 172, P2W_WIDTH_SBOX = 313;
 
+// One WARP per CTA, one row per lane, and the CTA's 32 whole rows staged in shared memory (40 KB with the S-box columns:
+// five CTAs per SM) before they leave as ONE contiguous, 16-byte aligned run of 128-bit stores -- every 32-byte sector
+// of the trace is written exactly once, completely.  The first version flushed each 16-column group of 128 rows as it
+// was produced: rows are 1252 bytes, so seven rows in eight start inside a sector and every group wrote two partial
+// sectors per row; ncu: 44 % of warp samples in MIO throttle behind the store path, 116 MB of DRAM reads (sector fills)
+// for a kernel that reads 15 MB, 0.24 ms for 2^18 rows (profiles/r2_ncu_tracegen.txt).
+constexpr int P2W_ROWS = 32;
+
 template <bool SBOX>
-__global__ void __launch_bounds__(ROWS) poseidon2_wide_rows(const uint32_t* __restrict__ inputs, uint64_t n_events,
-                                                            uint64_t rows, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(P2W_ROWS) poseidon2_wide_rows(const uint32_t* __restrict__ inputs, uint64_t n_events,
+                                                                uint64_t rows, uint32_t* __restrict__ out) {
   constexpr uint32_t W = SBOX ? P2W_WIDTH_SBOX : P2W_WIDTH_NO_SBOX;
-  __shared__ uint32_t tile[ROWS][17];
-  __shared__ uint32_t s0t[ROWS][13];
-  __shared__ uint32_t sbt[ROWS][13];
-  const uint32_t tid = threadIdx.x;
-  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
-  // 16 words of each of the CTA's rows -> columns [col, col + 16) of the trace, 64 contiguous bytes per row
-  auto emit = [&](const uint32_t (&v)[16], uint32_t col) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 16; i++) tile[tid][i] = v[i];
-    __syncthreads();
-    for (uint32_t idx = tid; idx < ROWS * 16; idx += ROWS) {
-      uint32_t r = idx >> 4, c = idx & 15;
-      if (row0 + r < rows) out[(row0 + r) * W + col + c] = tile[r][c];
-    }
-  };
-  for (uint32_t idx = tid; idx < ROWS * 16; idx += ROWS) {
-    uint32_t r = idx >> 4, c = idx & 15;
-    tile[r][c] = row0 + r < n_events ? inputs[(row0 + r) * 16 + c] : 0u;
-  }
-  __syncthreads();
+  // W = 313: lanes hit distinct banks per column; W = 172: 4-way conflicts on the 172 staging stores (noise beside
+  // the permutation)
+  __shared__ __align__(16) uint32_t tile[P2W_ROWS * W];
+  const uint32_t lane = threadIdx.x;
+  const uint64_t row0 = (uint64_t)blockIdx.x * P2W_ROWS;
+  uint32_t* const t = tile + lane * W;
   uint32_t s[16];
+  if (row0 + lane < n_events) {
+    const uint4* in = reinterpret_cast<const uint4*>(inputs + (row0 + lane) * 16);
 #pragma unroll
-  for (int i = 0; i < 16; i++) s[i] = tile[tid][i];
-  emit(s, 0);  // external_rounds_state[0] = input
+    for (int q = 0; q < 4; q++) {
+      uint4 v = in[q];
+      s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = 0u;  // padding rows: the row of the all-zero input
+  }
+  auto put = [&](uint32_t col) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[col + i] = s[i];
+  };
+  put(0);  // external_rounds_state[0] = input
   p2::external_layer(s);
 #pragma unroll 1
   for (int r = 0; r < 8; r++) {
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = p2::sbox(s[i], p2::EXT_RC[r][i]);
-    if (SBOX) emit(s, P2W_EXT_SBOX + 16 * r);
+    if (SBOX) put(P2W_EXT_SBOX + 16 * r);
     p2::external_layer(s);
     if (r == 3) {
-      emit(s, P2W_INT_STATE);
+      put(P2W_INT_STATE);
 #pragma unroll 1
       for (int k = 0; k < 13; k++) {
         s[0] = p2::sbox(s[0], p2::INT_RC[k]);
-        sbt[tid][k] = s[0];
+        if (SBOX) t[P2W_INT_SBOX + k] = s[0];
         p2::internal_layer(s);
-        s0t[tid][k] = s[0];  // k = 12 is not a column (it is external_rounds_state[4][0])
+        if (k < 12) t[P2W_S0 + k] = s[0];
       }
-      __syncthreads();
-      for (uint32_t idx = tid; idx < ROWS * 12; idx += ROWS) {
-        uint32_t rr = idx / 12, c = idx % 12;
-        if (row0 + rr < rows) out[(row0 + rr) * W + P2W_S0 + c] = s0t[rr][c];
-      }
-      if (SBOX)
-        for (uint32_t idx = tid; idx < ROWS * 13; idx += ROWS) {
-          uint32_t rr = idx / 13, c = idx % 13;
-          if (row0 + rr < rows) out[(row0 + rr) * W + P2W_INT_SBOX + c] = sbt[rr][c];
-        }
-      emit(s, 16 * 4);  // external_rounds_state[4] = state after the internal rounds
+      put(16 * 4);  // external_rounds_state[4] = state after the internal rounds
     } else if (r == 7) {
-      emit(s, P2W_OUT);
+      put(P2W_OUT);
     } else {
-      emit(s, 16 * (r + 1));
+      put(16 * (r + 1));
     }
+  }
+  __syncthreads();
+  if (row0 + P2W_ROWS <= rows) {
+    // 32 rows x W words = a multiple of 4 words, starting 16-byte aligned (32 * W * 4 bytes per CTA)
+    uint4* o = reinterpret_cast<uint4*>(out + row0 * W);
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+#pragma unroll 4
+    for (uint32_t k = lane; k < P2W_ROWS * W / 4; k += P2W_ROWS) o[k] = src[k];
+  } else {  // a trace shorter than one CTA
+    for (uint64_t k = lane; k < (rows - row0) * W; k += P2W_ROWS) out[row0 * W + k] = tile[k];
   }
 }
 
