@@ -327,10 +327,11 @@ def shard_chips(config, rank=0, scale=0):
             log-21 execution shard's size);
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
-            Poseidon2Wide is the REAL chip (library.poseidon2_wide(3): 313 + 49 columns, 32 memory sends) and its rows
-            are filled on the device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide); the ALU
-            stand-ins of BatchFRI / BaseAlu / ExtAlu are the real AddSub / Lt / Bitwise chips, also filled on the device
-            from their AluEvent records; the other RecursionAir chips are this library's synthetic AIRs at the
+            MemoryConst, BaseAlu and Poseidon2Wide are the REAL chips running a toy program whose memory bus balances
+            (synth.recursion_program_chips); the Poseidon2 rows (313 + 49 columns, 32 memory sends) are filled on the
+            device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide).  The stand-ins of BatchFRI / ExtAlu
+            are the real Lt / Bitwise chips of the core machine, also filled on the device from their AluEvent
+            records; MemoryVar / Select / ExpReverseBitsLen / PublicValues are this library's synthetic AIRs at the
             reference's heights.  Many small matrices, latency-bound."""
     from zkmips_b200 import synth
     d = scale
@@ -343,12 +344,12 @@ def shard_chips(config, rank=0, scale=0):
     if config == "recursion":
         send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
         send.name, recv.name = "MemoryVar", "Select"
-        return [send, recv, synth.local_bool_chip(16 - d, seed=3 + rank, name="MemoryConst"),
+        mem, alu, p2 = synth.recursion_program_chips(16 - d, 15 - d, 16 - d, 3, seed=41 + rank,
+                                                     names=("MemoryConst", "BaseAlu", "Poseidon2Wide"))
+        return [send, recv, mem, alu, p2,
                 synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI", device=True),
-                synth.add_sub_chip(15 - d, seed=5 + rank, name="BaseAlu", device=True),
                 synth.bitwise_chip(15 - d, seed=6 + rank, name="ExtAlu", device=True),
                 synth.wide_chip(17 - d, 64, seed=7 + rank, name="ExpReverseBitsLen"),
-                synth.poseidon2_wide_chip(16 - d, 3, seed=8 + rank, name="Poseidon2Wide"),
                 synth.fibonacci_chip(max(4 - d, 2), 1 + rank, 1, name="PublicValues")]
     send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
     return [synth.wide_chip(16 - d, 1024, seed=11 + rank), synth.wide_chip(18 - d, 64, seed=12 + rank),

@@ -400,8 +400,48 @@ def poseidon2_wide(degree=3):
     return air
 
 
+def memory_const():
+    """MemoryConstChip (crates/recursion/core/src/chips/mem/constant.rs:16-41 columns, :141-154 eval): one unused main
+    column, 12 preprocessed columns = 2 x (Block value[4], addr, mult); each entry WRITES its block:
+    send_block(addr, value, mult) = send(Memory, [addr, v0, v1, v2, v3], mult) (builder.rs:30-44)."""
+    air = Air("MemoryConst", main_width=1, prep_width=12, local_only=True)
+    b = AirBuilder(air)
+    p = b.preprocessed().local()
+    for e in range(2):
+        value, addr, mult = p[6 * e:6 * e + 4], p[6 * e + 4], p[6 * e + 5]
+        b.send(LOOKUP_MEMORY, [addr] + list(value), mult)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+def base_alu():
+    """BaseAluChip (crates/recursion/core/src/chips/alu_base.rs:27-62 columns, :266-297 eval): 4 operations per row.
+    Main: 4 x BaseAluIo {out, in1, in2}; preprocessed: 4 x {addrs {out, in1, in2}, is_add, is_sub, is_mul, is_div, mult}.
+    Per operation 5 constraints, two memory reads (receive_single, multiplicity is_real) and one write (send_single,
+    multiplicity mult).  Lookups are recorded in call order: receive in1, receive in2, send out."""
+    air = Air("BaseAlu", main_width=12, prep_width=32, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    p = b.preprocessed().local()
+    for e in range(4):
+        out, in1, in2 = m[3 * e], m[3 * e + 1], m[3 * e + 2]
+        a_out, a_in1, a_in2 = p[8 * e], p[8 * e + 1], p[8 * e + 2]
+        is_add, is_sub, is_mul, is_div, mult = p[8 * e + 3:8 * e + 8]
+        is_real = is_add + is_sub + is_mul + is_div
+        b.assert_bool(is_real)
+        b.when(is_add).assert_eq(in1 + in2, out)
+        b.when(is_sub).assert_eq(in1, in2 + out)
+        b.when(is_mul).assert_eq(out, in1 * in2)
+        b.when(is_div).assert_eq(in2 * out, in1)
+        b.receive(LOOKUP_MEMORY, [a_in1, in1, 0, 0, 0], is_real)
+        b.receive(LOOKUP_MEMORY, [a_in2, in2, 0, 0, 0], is_real)
+        b.send(LOOKUP_MEMORY, [a_out, out, 0, 0, 0], mult)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
-            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9)]
+            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu()]

@@ -352,3 +352,64 @@ def poseidon2_wide_chip(log_n, degree=3, seed=31, fill=0.75, name=None):
     air = f"Poseidon2WideDeg{degree}"
     return Chip(name or air, air, None, preprocessed=poseidon2_wide_prep_rows(instrs, n), local_only=True,
                 log_quotient_degree=1 if degree == 3 else 3, events=inputs, tracegen=air, rows=n)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A toy recursion PROGRAM over three real RecursionAir chips whose memory bus balances, so that the shard's cumulative
+# sum is zero and a verifier accepts the proof completely: MemoryConst writes constants c_j to addresses j; Poseidon2
+# permutation k reads addresses k .. k + 15 and writes its 16 outputs to fresh addresses (never read: multiplicity 0);
+# BaseAlu operation t reads two constants and writes its result to a fresh address.  Every constant's write
+# multiplicity is the number of times it is read (crates/recursion/core/src/chips/mem/mod.rs:14-22: positive = write).
+# ------------------------------------------------------------------------------------------------------------------
+def _inv_mod(x):
+    return np.array([pow(int(v), P - 2, P) for v in x], np.uint64)
+
+
+def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, fill=0.75, names=None):
+    """(MemoryConst, BaseAlu, Poseidon2WideDeg<degree>) chips of the toy program; the Poseidon2 rows are filled on the
+    device from the permutation inputs, the other two chips' traces are a few columns and stay host arrays."""
+    rng = np.random.default_rng(seed)
+    n_perm = max(1, int((1 << log_p2) * fill))
+    n_alu = max(1, int((4 << log_alu) * fill))
+    n_const = n_perm + 15
+    assert n_const <= (2 << log_mem), "MemoryConst too short for the constants of this program"
+    consts = rng.integers(1, P, n_const, dtype=np.uint64)              # non-zero: BaseAlu divides by them
+    reads = np.zeros(n_const, np.uint64)
+    # Poseidon2 instructions
+    win = np.arange(n_perm)[:, None] + np.arange(16)[None, :]          # addresses read by permutation k
+    np.add.at(reads, win.ravel(), 1)
+    out_base = 1 << 22
+    p2_instrs = np.concatenate([win, out_base + 16 * np.arange(n_perm)[:, None] + np.arange(16)[None, :],
+                                np.zeros((n_perm, 16), np.int64)], axis=1).astype(np.uint64)
+    p2_inputs = to_monty(consts[win])
+    # BaseAlu instructions
+    a1 = rng.integers(0, n_const, n_alu)
+    a2 = rng.integers(0, n_const, n_alu)
+    np.add.at(reads, a1, 1)
+    np.add.at(reads, a2, 1)
+    op = rng.integers(0, 4, n_alu)                                     # 0 add, 1 sub, 2 mul, 3 div
+    x, y = consts[a1], consts[a2]
+    res = np.select([op == 0, op == 1, op == 2], [(x + y) % P, (x + P - y) % P, x * y % P], x * _inv_mod(y) % P)
+    alu_rows = 1 << log_alu
+    alu_main = np.zeros((alu_rows * 4, 3), np.uint64)
+    alu_main[:n_alu] = np.stack([res, x, y], axis=1)                   # BaseAluIo {out, in1, in2}
+    alu_prep = np.zeros((alu_rows * 4, 8), np.uint64)
+    alu_prep[:n_alu, 0] = (1 << 23) + np.arange(n_alu)                 # fresh output addresses
+    alu_prep[:n_alu, 1], alu_prep[:n_alu, 2] = a1, a2
+    alu_prep[np.arange(n_alu), 3 + op] = 1                             # is_add / is_sub / is_mul / is_div; mult = 0
+    # MemoryConst: entries (value block, addr, mult), two per row
+    mem_rows = 1 << log_mem
+    mem_prep = np.zeros((mem_rows * 2, 6), np.uint64)
+    mem_prep[:n_const, 0], mem_prep[:n_const, 4], mem_prep[:n_const, 5] = consts, np.arange(n_const), reads
+    names = names or ("MemoryConst", "BaseAlu", f"Poseidon2WideDeg{degree}")
+    mem = Chip(names[0], "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
+               local_only=True)
+    alu = Chip(names[1], "BaseAlu", M(alu_main.reshape(alu_rows, 12)), preprocessed=M(alu_prep.reshape(alu_rows, 32)),
+               local_only=True)
+    mem.canon = (mem_prep.reshape(mem_rows, 12), np.zeros((mem_rows, 1), np.uint64))
+    alu.canon = (alu_prep.reshape(alu_rows, 32), alu_main.reshape(alu_rows, 12))
+    air = f"Poseidon2WideDeg{degree}"
+    p2 = Chip(names[2], air, None, preprocessed=poseidon2_wide_prep_rows(to_monty(p2_instrs), 1 << log_p2),
+              local_only=True, log_quotient_degree=1 if degree == 3 else 3, events=p2_inputs, tracegen=air,
+              rows=1 << log_p2)
+    return [mem, alu, p2]
