@@ -327,12 +327,12 @@ def shard_chips(config, rank=0, scale=0):
             log-21 execution shard's size);
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
-            MemoryConst, BaseAlu and Poseidon2Wide are the REAL chips running a toy program whose memory bus balances
-            (synth.recursion_program_chips); the Poseidon2 rows (313 + 49 columns, 32 memory sends) are filled on the
-            device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide).  The stand-ins of BatchFRI / ExtAlu
-            are the real Lt / Bitwise chips of the core machine, also filled on the device from their AluEvent
-            records; MemoryVar / Select / ExpReverseBitsLen / PublicValues are this library's synthetic AIRs at the
-            reference's heights.  Many small matrices, latency-bound."""
+            MemoryVar, Select, MemoryConst, BaseAlu, ExtAlu and Poseidon2Wide are the REAL chips running a toy program
+            whose memory bus balances (synth.recursion_program_chips); the Poseidon2 rows (313 + 49 columns, 32 memory
+            sends) are filled on the device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide).  The
+            stand-in of BatchFRI is the real Lt chip of the core machine, filled on the device from its AluEvent
+            records; ExpReverseBitsLen / PublicValues are this library's synthetic AIRs at the reference's heights.
+            Many small matrices, latency-bound."""
     from zkmips_b200 import synth
     d = scale
     if config == "keccak":
@@ -342,13 +342,11 @@ def shard_chips(config, rank=0, scale=0):
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
     if config == "recursion":
-        send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
-        send.name, recv.name = "MemoryVar", "Select"
-        mem, alu, p2 = synth.recursion_program_chips(16 - d, 15 - d, 16 - d, 3, seed=41 + rank,
-                                                     names=("MemoryConst", "BaseAlu", "Poseidon2Wide"))
-        return [send, recv, mem, alu, p2,
+        mem, alu, p2, sel, var, ext = synth.recursion_program_chips(
+            16 - d, 15 - d, 16 - d, 3, seed=41 + rank, names=("MemoryConst", "BaseAlu", "Poseidon2Wide"),
+            log_var=18 - d, log_ext=15 - d, log_sel=18 - d)
+        return [var, sel, mem, alu, ext, p2,
                 synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI", device=True),
-                synth.bitwise_chip(15 - d, seed=6 + rank, name="ExtAlu", device=True),
                 synth.wide_chip(17 - d, 64, seed=7 + rank, name="ExpReverseBitsLen"),
                 synth.fibonacci_chip(max(4 - d, 2), 1 + rank, 1, name="PublicValues")]
     send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)

@@ -14,7 +14,8 @@ def test_exported_json_reproduces_the_generated_kernels():
     """Loading zkmips_b200/air/exported/<Chip>.json (what a recording-builder exporter would write) must give the same
     program as the hand transcription: identical JSON again, and byte-identical generated CUDA."""
     for make in (library.add_sub, library.lt, library.bitwise, lambda: library.poseidon2_wide(3),
-                 lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu):
+                 lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
+                 library.ext_alu, library.select):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -105,11 +106,14 @@ ae_P = 0x7F000001
 
 
 def test_recursion_program_chips_satisfy_their_airs():
-    """MemoryConst (1 + 12 columns, 2 block writes per row) and BaseAlu (12 + 32 columns, 4 operations per row: 5
-    constraints, 2 reads and 1 write each) as transcribed, on the toy program of synth.recursion_program_chips"""
+    """MemoryConst (1 + 12 columns, 2 block writes per row), BaseAlu (12 + 32 columns, 4 operations per row: 5
+    constraints, 2 reads and 1 write each), MemoryVar (8 + 4), ExtAlu (48 + 32: 17 constraints per operation, block
+    reads / writes) and Select (5 + 8) as transcribed, on the toy program of synth.recursion_program_chips"""
     from zkmips_b200 import synth
-    mem, alu, _ = synth.recursion_program_chips(5, 4, 5)
-    for chip, air, shape in ((mem, library.memory_const(), (1, 12, 2, 0, 0)), (alu, library.base_alu(), (12, 32, 4, 8, 20))):
+    mem, alu, _, sel, var, ext = synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)
+    for chip, air, shape in ((mem, library.memory_const(), (1, 12, 2, 0, 0)), (alu, library.base_alu(), (12, 32, 4, 8, 20)),
+                             (var, library.memory_var(), (8, 4, 2, 0, 0)), (ext, library.ext_alu(), (48, 32, 4, 8, 68)),
+                             (sel, library.select(), (5, 8, 2, 3, 2))):
         assert (air.main_width, air.prep_width, len(air.sends), len(air.receives)) == shape[:4]
         assert air.num_constraints == shape[4] + ((air.perm_width - 1) + 3 if air.perm_width else 0)
         vals = _constraints_on_trace(air, chip.canon[1], chip.canon[0])

@@ -36,7 +36,8 @@ def p2w_host_chip(log_n, degree, **kw):
 
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
-                                   "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu"])
+                                   "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
+                                   "MemoryVar", "ExtAlu", "Select"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -53,7 +54,10 @@ def test_quotient_values_match_oracle(be, which):
             # DEGREE 9 has log_quotient_degree 3 (8 chunks, LogUp batches of 8)
             "Poseidon2WideDeg3": lambda: p2w_host_chip(5, 3), "Poseidon2WideDeg9": lambda: p2w_host_chip(3, 9),
             "MemoryConst": lambda: synth.recursion_program_chips(5, 4, 5)[0],
-            "BaseAlu": lambda: synth.recursion_program_chips(5, 4, 5)[1]}[which]()
+            "BaseAlu": lambda: synth.recursion_program_chips(5, 4, 5)[1],
+            "Select": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[3],
+            "MemoryVar": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[4],
+            "ExtAlu": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[5]}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
@@ -265,8 +269,9 @@ def test_recursion_chips_from_events_shard(be):
 
 @pytest.mark.parametrize("be", BACKENDS)
 def test_recursion_program_shard_verifies_completely(be):
-    """A toy recursion PROGRAM over three real RecursionAir chips -- MemoryConst (constants written to memory), BaseAlu
-    and Poseidon2WideDeg3 (both reading them) -- whose memory bus balances: the verifier restatement accepts the proof
+    """A toy recursion PROGRAM over six real RecursionAir chips -- MemoryConst (constants written to memory), BaseAlu,
+    Select and Poseidon2WideDeg3 (reading them), MemoryVar (extension operands) and ExtAlu (reading those) -- whose
+    memory bus balances: the verifier restatement accepts the proof
     COMPLETELY (PCS openings, constraint identity of every chip including LogUp, and the zero shard sum), and it is
     byte-identical with the CPU prover's.  Dropping one read from the program unbalances the bus and is rejected."""
     from oracle import binding_fri as bf
@@ -275,7 +280,9 @@ def test_recursion_program_shard_verifies_completely(be):
     ctx = _backend(be)
     nq, pw = (6, 4) if be == "emu" else (84, 16)
     logs = (5, 4, 5) if be == "emu" else (12, 11, 11)
-    chips = synth.recursion_program_chips(*logs) + [su.fibonacci_chip(4)]
+    more = dict(log_var=6, log_ext=4, log_sel=5) if be == "emu" else dict(log_var=13, log_ext=11, log_sel=12)
+    chips = synth.recursion_program_chips(*logs, **more) + [su.fibonacci_chip(4)]
+    assert [c.air for c in chips[:6]] == ["MemoryConst", "BaseAlu", "Poseidon2WideDeg3", "Select", "MemoryVar", "ExtAlu"]
     prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
     host = list(chips)
     host[2] = p2w_host_chip(logs[0], 3)                                # same events (same seed / fill), rows from the oracle
@@ -284,7 +291,7 @@ def test_recursion_program_shard_verifies_completely(be):
     ok, why = su.machine_verify(su.vk_of(pk), _machine(host), [sp], NUM_PV, 1, nq, pw)
     assert ok, why
     assert not sp.local_cumulative_sum().any()
-    assert all(sp.opened_values[sp.chip_ordering[c.name]].local_cumulative_sum.any() for c in chips[:3])
+    assert all(sp.opened_values[sp.chip_ordering[c.name]].local_cumulative_sum.any() for c in chips[:6])
     op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=NUM_PV)
     opk = op.setup(host, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
     och = bf.new_challenger()
@@ -293,7 +300,7 @@ def test_recursion_program_shard_verifies_completely(be):
     data.free()
     pk.data.free()
     # one multiplicity off by one: every per-chip check still passes, the shard sum does not
-    bad = synth.recursion_program_chips(*logs) + [su.fibonacci_chip(4)]
+    bad = synth.recursion_program_chips(*logs, **more) + [su.fibonacci_chip(4)]
     pre = ob.from_monty(bad[0].preprocessed).astype(np.uint64)
     pre[0, 5] = (pre[0, 5] + 1) % ae.P
     bad[0].preprocessed = ob.to_monty(pre.astype(np.uint32))

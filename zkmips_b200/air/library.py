@@ -440,8 +440,80 @@ def base_alu():
     return air
 
 
+def memory_var():
+    """MemoryVarChip (crates/recursion/core/src/chips/mem/variable.rs:15-38 columns, :148-159 eval): hint / witness
+    values written to memory: 2 entries per row, main = 2 x Block value[4], preprocessed = 2 x {addr, mult};
+    send_block(addr, value, mult) per entry."""
+    air = Air("MemoryVar", main_width=8, prep_width=4, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    p = b.preprocessed().local()
+    for e in range(2):
+        b.send(LOOKUP_MEMORY, [p[2 * e]] + list(m[4 * e:4 * e + 4]), p[2 * e + 1])
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+def _ext_mul(a, c):
+    """BinomialExtension<Expr> * BinomialExtension<Expr>, X^4 = 3 (crates/stark/src/air/extension.rs:55-75)"""
+    res = [None] * 4
+    for i in range(4):
+        for j in range(4):
+            k = i + j
+            term = 3 * a[i] * c[j] if k >= 4 else a[i] * c[j]
+            k %= 4
+            res[k] = term if res[k] is None else res[k] + term
+    return res
+
+
+def ext_alu():
+    """ExtAluChip (crates/recursion/core/src/chips/alu_ext.rs:18-57 columns, :268-302 eval): 4 extension-field operations
+    per row.  Main: 4 x ExtAluIo<Block> {out[4], in1[4], in2[4]}; preprocessed: 4 x {addrs {out, in1, in2}, is_add,
+    is_sub, is_mul, is_div, mult}.  assert_ext_eq = one assert_eq per coefficient (stark/src/air/builder.rs:400-408)."""
+    air = Air("ExtAlu", main_width=48, prep_width=32, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    p = b.preprocessed().local()
+    for e in range(4):
+        out, in1, in2 = m[12 * e:12 * e + 4], m[12 * e + 4:12 * e + 8], m[12 * e + 8:12 * e + 12]
+        a_out, a_in1, a_in2 = p[8 * e], p[8 * e + 1], p[8 * e + 2]
+        is_add, is_sub, is_mul, is_div, mult = p[8 * e + 3:8 * e + 8]
+        is_real = is_add + is_sub + is_mul + is_div
+        b.assert_bool(is_real)
+        for flag, lhs, rhs in ((is_add, [x + y for x, y in zip(in1, in2)], out),
+                               (is_sub, in1, [y + z for y, z in zip(in2, out)]),
+                               (is_mul, _ext_mul(in1, in2), out),
+                               (is_div, in1, _ext_mul(in2, out))):
+            for l, r in zip(lhs, rhs):
+                b.when(flag).assert_eq(l, r)
+        b.receive(LOOKUP_MEMORY, [a_in1] + list(in1), is_real)
+        b.receive(LOOKUP_MEMORY, [a_in2] + list(in2), is_real)
+        b.send(LOOKUP_MEMORY, [a_out] + list(out), mult)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+def select():
+    """SelectChip (crates/recursion/core/src/chips/select.rs:16-35 columns, :229-250 eval): main = SelectIo {bit, out1,
+    out2, in1, in2}; preprocessed = {is_real, addrs {bit, out1, out2, in1, in2}, mult1, mult2}."""
+    air = Air("Select", main_width=5, prep_width=8, local_only=True)
+    b = AirBuilder(air)
+    bit, out1, out2, in1, in2 = b.main().local()
+    p = b.preprocessed().local()
+    is_real, a_bit, a_out1, a_out2, a_in1, a_in2, mult1, mult2 = p
+    b.receive(LOOKUP_MEMORY, [a_bit, bit, 0, 0, 0], is_real)
+    b.receive(LOOKUP_MEMORY, [a_in1, in1, 0, 0, 0], is_real)
+    b.receive(LOOKUP_MEMORY, [a_in2, in2, 0, 0, 0], is_real)
+    b.send(LOOKUP_MEMORY, [a_out1, out1, 0, 0, 0], mult1)
+    b.send(LOOKUP_MEMORY, [a_out2, out2, 0, 0, 0], mult2)
+    b.assert_eq(out1, bit * in2 + (1 - bit) * in1)
+    b.assert_eq(out2, bit * in1 + (1 - bit) * in2)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
-            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu()]
+            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select()]

@@ -365,15 +365,20 @@ def _inv_mod(x):
     return np.array([pow(int(v), P - 2, P) for v in x], np.uint64)
 
 
-def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, fill=0.75, names=None):
+def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, fill=0.75, names=None, log_var=None,
+                            log_ext=None, log_sel=None):
     """(MemoryConst, BaseAlu, Poseidon2WideDeg<degree>) chips of the toy program; the Poseidon2 rows are filled on the
-    device from the permutation inputs, the other two chips' traces are a few columns and stay host arrays."""
+    device from the permutation inputs, the other two chips' traces are a few columns and stay host arrays.
+    With log_var / log_ext / log_sel also (MemoryVar, ExtAlu, Select): MemoryVar writes the two extension operands of
+    every ExtAlu operation (read once each), Select reads a bit constant (addresses n_const - 2 / n_const - 1 hold 0 / 1)
+    and two other constants."""
     rng = np.random.default_rng(seed)
     n_perm = max(1, int((1 << log_p2) * fill))
     n_alu = max(1, int((4 << log_alu) * fill))
-    n_const = n_perm + 15
+    n_const = n_perm + 15 + 2
     assert n_const <= (2 << log_mem), "MemoryConst too short for the constants of this program"
     consts = rng.integers(1, P, n_const, dtype=np.uint64)              # non-zero: BaseAlu divides by them
+    consts[-2:] = (0, 1)                                               # the two bit constants (never ALU operands)
     reads = np.zeros(n_const, np.uint64)
     # Poseidon2 instructions
     win = np.arange(n_perm)[:, None] + np.arange(16)[None, :]          # addresses read by permutation k
@@ -383,8 +388,8 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
                                 np.zeros((n_perm, 16), np.int64)], axis=1).astype(np.uint64)
     p2_inputs = to_monty(consts[win])
     # BaseAlu instructions
-    a1 = rng.integers(0, n_const, n_alu)
-    a2 = rng.integers(0, n_const, n_alu)
+    a1 = rng.integers(0, n_const - 2, n_alu)
+    a2 = rng.integers(0, n_const - 2, n_alu)
     np.add.at(reads, a1, 1)
     np.add.at(reads, a2, 1)
     op = rng.integers(0, 4, n_alu)                                     # 0 add, 1 sub, 2 mul, 3 div
@@ -400,6 +405,65 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
     # MemoryConst: entries (value block, addr, mult), two per row
     mem_rows = 1 << log_mem
     mem_prep = np.zeros((mem_rows * 2, 6), np.uint64)
+    extra = []
+    if log_sel is not None:
+        # SelectChip: out1 = bit ? in2 : in1, out2 = bit ? in1 : in2 (chips/select.rs:242-249); SelectIo order
+        # {bit, out1, out2, in1, in2}; outputs go to fresh addresses nobody reads
+        rows_s = 1 << log_sel
+        n_sel = max(1, int(rows_s * fill))
+        bit = rng.integers(0, 2, n_sel)
+        s1, s2 = rng.integers(0, n_const - 2, n_sel), rng.integers(0, n_const - 2, n_sel)
+        for a in (n_const - 2 + bit, s1, s2):
+            np.add.at(reads, a, 1)
+        v1, v2 = consts[s1], consts[s2]
+        sel_main = np.zeros((rows_s, 5), np.uint64)
+        sel_main[:n_sel] = np.stack([bit.astype(np.uint64), np.where(bit == 1, v2, v1), np.where(bit == 1, v1, v2), v1, v2], axis=1)
+        sel_prep = np.zeros((rows_s, 8), np.uint64)
+        sel_prep[:n_sel, 0] = 1
+        sel_prep[:n_sel, 1], sel_prep[:n_sel, 4], sel_prep[:n_sel, 5] = n_const - 2 + bit, s1, s2
+        sel_prep[:n_sel, 2] = (1 << 25) + 2 * np.arange(n_sel)
+        sel_prep[:n_sel, 3] = (1 << 25) + 2 * np.arange(n_sel) + 1
+        sel = Chip("Select", "Select", M(sel_main), preprocessed=M(sel_prep), local_only=True)
+        sel.canon = (sel_prep, sel_main)
+        extra.append(sel)
+    if log_ext is not None:
+        rows_e = 1 << log_ext
+        n_ext = max(1, int(4 * rows_e * fill))
+        assert 2 * n_ext <= (2 << log_var), "MemoryVar too short for the ExtAlu operands"
+        eop = rng.integers(0, 4, n_ext)                                # 0 add, 1 sub, 2 mul, 3 div
+        u = rng.integers(0, P, (n_ext, 4), dtype=np.uint64)
+        v = rng.integers(0, P, (n_ext, 4), dtype=np.uint64)
+
+        def emul(a, c):                                                # F_p[X] / (X^4 - 3)
+            r = np.zeros_like(a)
+            for i in range(4):
+                for j in range(4):
+                    t = a[:, i] * c[:, j] % P
+                    r[:, (i + j) % 4] = (r[:, (i + j) % 4] + (3 * t if i + j >= 4 else t)) % P
+            return r
+        # add: out = in1 + in2; sub: in1 = in2 + out; mul: out = in1 * in2; div: in1 = in2 * out (so out = in1 / in2)
+        in2 = v
+        out = np.where((eop == 0)[:, None], (u + v) % P, np.where((eop == 2)[:, None], emul(u, v), u))
+        in1 = np.where((eop == 1)[:, None], (v + u) % P, np.where((eop == 3)[:, None], emul(v, u), u))
+        ext_main = np.zeros((4 * rows_e, 12), np.uint64)
+        ext_main[:n_ext] = np.concatenate([out, in1, in2], axis=1)
+        ext_prep = np.zeros((4 * rows_e, 8), np.uint64)
+        var_base = 1 << 24
+        ext_prep[:n_ext, 0] = (1 << 26) + np.arange(n_ext)
+        ext_prep[:n_ext, 1], ext_prep[:n_ext, 2] = var_base + 2 * np.arange(n_ext), var_base + 2 * np.arange(n_ext) + 1
+        ext_prep[np.arange(n_ext), 3 + eop] = 1
+        rows_v = 1 << log_var
+        var_main = np.zeros((2 * rows_v, 4), np.uint64)
+        var_main[0:2 * n_ext:2], var_main[1:2 * n_ext:2] = in1, in2
+        var_prep = np.zeros((2 * rows_v, 2), np.uint64)
+        var_prep[:2 * n_ext, 0], var_prep[:2 * n_ext, 1] = var_base + np.arange(2 * n_ext), 1
+        var = Chip("MemoryVar", "MemoryVar", M(var_main.reshape(rows_v, 8)), preprocessed=M(var_prep.reshape(rows_v, 4)),
+                   local_only=True)
+        var.canon = (var_prep.reshape(rows_v, 4), var_main.reshape(rows_v, 8))
+        ext = Chip("ExtAlu", "ExtAlu", M(ext_main.reshape(rows_e, 48)), preprocessed=M(ext_prep.reshape(rows_e, 32)),
+                   local_only=True)
+        ext.canon = (ext_prep.reshape(rows_e, 32), ext_main.reshape(rows_e, 48))
+        extra += [var, ext]
     mem_prep[:n_const, 0], mem_prep[:n_const, 4], mem_prep[:n_const, 5] = consts, np.arange(n_const), reads
     names = names or ("MemoryConst", "BaseAlu", f"Poseidon2WideDeg{degree}")
     mem = Chip(names[0], "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
@@ -412,4 +476,4 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
     p2 = Chip(names[2], air, None, preprocessed=poseidon2_wide_prep_rows(to_monty(p2_instrs), 1 << log_p2),
               local_only=True, log_quotient_degree=1 if degree == 3 else 3, events=p2_inputs, tracegen=air,
               rows=1 << log_p2)
-    return [mem, alu, p2]
+    return [mem, alu, p2] + extra
