@@ -121,3 +121,24 @@ def test_recursion_program_chips_satisfy_their_airs():
     bad = alu.canon[1].copy()
     bad[0, 0] = (bad[0, 0] + 1) % ae_P                      # a wrong result
     assert any(v.any() for v in _constraints_on_trace(library.base_alu(), bad, alu.canon[0])[:20])
+
+
+def test_exporter_output_without_logup_constraints_loads_to_the_same_program():
+    """rust/air-export writes a chip's OWN constraints and its lookups; `Air.from_exported_json` appends the LogUp
+    constraints.  Simulated here by stripping them from the hand transcriptions: same constraints, same generated
+    CUDA, for chips with sends and receives, with a preprocessed trace, and with 8-lookup batches (DEGREE 9)."""
+    for make in (library.add_sub, library.lt, library.base_alu, library.ext_alu, lambda: library.poseidon2_wide(3),
+                 lambda: library.poseidon2_wide(9)):
+        air = make()
+        d = json.loads(air.to_json())
+        n_logup = (air.perm_width - 1) + 3
+        d["constraints"] = d["constraints"][:-n_logup]
+        d["permutation_constraints_included"] = False
+        d["perm_width"] = 0
+        # the exporter never emits permutation / challenge / cumulative-sum leaves: cut the node list where they start
+        cut = min(i for i, n in enumerate(d["nodes"]) if n[0] in ("perm", "chal", "lcs"))
+        assert all(c < cut for c in d["constraints"])
+        d["nodes"] = d["nodes"][:cut]
+        loaded = Air.from_exported_json(json.dumps(d))
+        assert loaded.num_constraints == air.num_constraints and loaded.perm_width == air.perm_width
+        assert codegen.generate([loaded]) == codegen.generate([air])

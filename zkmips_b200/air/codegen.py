@@ -210,13 +210,28 @@ def generate(airs):
     return out
 
 
-def write(gen_dir=None):
-    """Writes csrc/gen/ (files are only rewritten when their text changes, so make-style staleness works)."""
+def exported_airs(json_dir):
+    """the chips a Rust-side exporter (rust/air-export) wrote into `json_dir`, one <Chip>.json each"""
+    from .ir import Air
+    return [Air.from_exported_json(open(os.path.join(json_dir, f)).read())
+            for f in sorted(os.listdir(json_dir)) if f.endswith(".json")]
+
+
+def write(gen_dir=None, json_dir=None):
+    """Writes csrc/gen/ (files are only rewritten when their text changes, so make-style staleness works).
+    `json_dir` (env ZK_AIR_JSON_DIR): chips exported from the Ziren workspace are compiled in as well; an exported chip
+    replaces the library's transcription of the same name."""
     from . import library
     here = os.path.dirname(os.path.abspath(__file__))
     gen_dir = gen_dir or os.path.join(os.path.dirname(here), "csrc", "gen")
     os.makedirs(gen_dir, exist_ok=True)
-    for name, text in generate(library.all_airs()).items():
+    airs = library.all_airs()
+    json_dir = json_dir or os.environ.get("ZK_AIR_JSON_DIR")
+    if json_dir:
+        extra = exported_airs(json_dir)
+        names = {a.name for a in extra}
+        airs = [a for a in airs if a.name not in names] + extra
+    for name, text in generate(airs).items():
         path = os.path.join(gen_dir, name)
         old = open(path).read() if os.path.exists(path) else None
         if old != text:
@@ -226,4 +241,5 @@ def write(gen_dir=None):
 
 
 if __name__ == "__main__":
-    print(write())
+    import sys
+    print(write(json_dir=sys.argv[sys.argv.index("--from-json") + 1] if "--from-json" in sys.argv else None))

@@ -193,6 +193,22 @@ class Air:
         a.lookups_finalized = True
         return a
 
+    @classmethod
+    def from_exported_json(cls, text):
+        """Load what the Rust-side exporter (rust/air-export) writes: the chip's own constraints as a node DAG plus its
+        lookups, WITHOUT the LogUp constraints (`permutation_constraints_included: false`) -- those are appended here,
+        after the chip's own, exactly as `Chip::eval` does (crates/stark/src/chip.rs:259-270).  A file that already
+        includes them (`Air.to_json`) loads unchanged."""
+        d = json.loads(text)
+        if d.get("permutation_constraints_included", True):
+            return cls.from_json(text)
+        a = cls.from_json(text)
+        a._memo = {n: i for i, n in enumerate(a.nodes)}
+        a.lookups_finalized = False
+        a.perm_width = 0
+        AirBuilder(a).eval_permutation_constraints(batch_size=d.get("batch_size", 2))
+        return a
+
     def uses_next_row(self):
         """does any constraint read the next row of the preprocessed / main trace?  (a `local_only` chip must not)"""
         need, stack = set(), list(self.constraints)
