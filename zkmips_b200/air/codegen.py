@@ -46,6 +46,50 @@ def _parts(air):
     return parts
 
 
+def _vec_width(width):
+    """columns fetched by one load: rows of a committed LDE start 8-byte aligned (even pitch, zkgpu_internal.cuh
+    `lde_pitch`), 16-byte aligned when the pitch is a multiple of 4 words.  One thread reads one ROW, so a warp's scalar
+    column load touches 32 sectors for 32 words; fetching the aligned group of 4 (2) adjacent columns at once divides
+    the load-store unit's work by the group size (wide_bitwise_4096 at 2^16 rows: 537 M scalar loads per quotient)."""
+    pitch = (width + 1) & ~1
+    return 4 if pitch % 4 == 0 else 2
+
+
+class _Loads:
+    """vector loads of one kernel part: the first use of a column fetches its whole aligned group, provided at least
+    two columns of the group are used by the part"""
+
+    def __init__(self, air, needed):
+        self.air = air
+        self.count = {}
+        for n in needed:
+            node = air.nodes[n]
+            if node[0] in ("main", "prep"):
+                key = self.key(node)
+                self.count[key] = self.count.get(key, 0) + 1
+        self.loaded = set()
+
+    def key(self, node):
+        vw = _vec_width(self.air.main_width if node[0] == "main" else self.air.prep_width)
+        return (node[0], node[1], node[2] // vw, vw)
+
+    def emit(self, n):
+        node = self.air.nodes[n]
+        key = self.key(node)
+        kind, row, grp, vw = key
+        src = f"R.{'m' if kind == 'main' else 'p'}{row}"
+        if self.count[key] < 2:
+            return [f"const uint32_t n{n} = __ldg({src} + {node[2]});"]
+        g = f"g{'m' if kind == 'main' else 'p'}{row}_{grp}"
+        lines = []
+        if key not in self.loaded:
+            self.loaded.add(key)
+            ty = "uint4" if vw == 4 else "uint2"
+            lines.append(f"const {ty} {g} = __ldg(reinterpret_cast<const {ty}*>({src} + {grp * vw}));")
+        lines.append(f"const uint32_t n{n} = {g}.{'xyzw'[node[2] % vw]};")
+        return lines
+
+
 def _emit_node(air, n):
     node, ty = air.nodes[n], air.types[n]
     k = node[0]
@@ -171,11 +215,15 @@ def generate(airs):
             # demand-driven emission: a node is materialised right before the first constraint that needs
             # it, which keeps live ranges (registers) short for wide chips
             done = set()
+            loads = _Loads(air, _needed(air, [c for _, c in part]))
             for k, c in part:
                 for n in _needed(air, [c]):
                     if n not in done:
                         done.add(n)
-                        out.append("  " + _emit_node(air, n))
+                        if air.nodes[n][0] in ("main", "prep"):
+                            out += ["  " + line for line in loads.emit(n)]
+                        else:
+                            out.append("  " + _emit_node(air, n))
                 f = "fold_b" if air.types[c] == "b" else "fold_e"
                 out.append(f"  acc = quot::{f}(acc, A.alpha_pows + {4 * k}, n{c});")
             out.append(f"  quot::epilogue(A, i, R, acc, {'true' if pi == 0 else 'false'});")

@@ -50,6 +50,11 @@ static int32_t lde_of(const zk_pdata* pd, uint32_t idx, uint32_t want_w, uint64_
   if (!pd || idx >= pd->n) return zk_fail(ZK_ERR_ARG, std::string(what) + " trace is required by this AIR");
   if (pd->widths[idx] != want_w) return zk_fail(ZK_ERR_ARG, std::string(what) + " trace has the wrong width");
   if (pd->heights[idx] < want_h) return zk_fail(ZK_ERR_ARG, std::string(what) + " LDE is shorter than the quotient domain");
+  // the generated kernels fetch groups of adjacent columns with 64- / 128-bit loads (codegen.py `_vec_width`), which
+  // the even row pitch of a committed LDE guarantees to be aligned
+  if (pd->pitches[idx] != lde_pitch(want_w))
+    return zk_fail(ZK_ERR_ARG, std::string(what) + " LDE has a dense odd row pitch (committed with ZK_EVEN_PITCH=0): the "
+                                                   "quotient kernels need the even pitch");
   *ptr = pd->mats[idx];
   *pitch = pd->pitches[idx];
   return ZK_OK;

@@ -1148,7 +1148,7 @@ extern "C" int32_t zk_pdata_import(zk_ctx* c, uint32_t n_mats, const uint32_t* c
   pd->n = n_mats;
   pd->heights.assign(heights, heights + n_mats);
   pd->widths.assign(widths, widths + n_mats);
-  pd->pitches.assign(widths, widths + n_mats);  // imported matrices are dense
+  pd->pitches.assign(widths, widths + n_mats);
   pd->mats.assign(n_mats, nullptr);
   pd->owned.assign(n_mats, true);
   pd->traces.assign(n_mats, nullptr);
@@ -1160,9 +1160,26 @@ extern "C" int32_t zk_pdata_import(zk_ctx* c, uint32_t n_mats, const uint32_t* c
   for (uint32_t i = 0; i < n_mats; i++) {
     const uint64_t bytes = heights[i] * widths[i] * 4ull;
     if (bytes && !ldes_host[i]) return fail(zk_fail(ZK_ERR_ARG, "null matrix pointer"));
-    if ((rc = dev_alloc(c, bytes, (void**)&pd->mats[i]))) return fail(rc);
-    if (bytes && cudaMemcpyAsync(pd->mats[i], ldes_host[i], bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
-      return fail(zk_fail(ZK_ERR_CUDA, "upload of an LDE matrix failed"));
+    // same layout as a committed LDE: odd widths get the even row pitch (the generated quotient kernels and the opening
+    // reduction read rows with vector loads), padding column zero
+    pd->pitches[i] = c->even_pitch ? lde_pitch(widths[i]) : widths[i];
+    if ((rc = dev_alloc(c, heights[i] * pd->pitches[i] * 4ull, (void**)&pd->mats[i]))) return fail(rc);
+    if (pd->pitches[i] == widths[i]) {
+      if (bytes && cudaMemcpyAsync(pd->mats[i], ldes_host[i], bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        return fail(zk_fail(ZK_ERR_CUDA, "upload of an LDE matrix failed"));
+    } else {
+      uint32_t* dense = nullptr;
+      if ((rc = dev_alloc(c, bytes, (void**)&dense))) return fail(rc);
+      bool ok = cudaMemcpyAsync(dense, ldes_host[i], bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+      if (ok) {
+        const unsigned blocks = (unsigned)std::min<uint64_t>((heights[i] + 7) / 8, 148 * 16);
+        ZK_LAUNCH(spread_rows_kernel, blocks, 256, 0, c->stream, dense, pd->mats[i], widths[i], pd->pitches[i], heights[i]);
+        ok = cudaGetLastError() == cudaSuccess;
+        c->launches++;
+      }
+      dev_free(c, dense);
+      if (!ok) return fail(zk_fail(ZK_ERR_CUDA, "upload of an LDE matrix failed"));
+    }
     if (traces_host && traces_host[i]) {
       if (heights[i] >> log_blowup == 0) return fail(zk_fail(ZK_ERR_ARG, "committed height below the blowup"));
       const uint64_t tb = (heights[i] >> log_blowup) * widths[i] * 4ull;
