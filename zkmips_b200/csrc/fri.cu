@@ -111,10 +111,25 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   RC(sc.alloc(&d_status, 4));
   RC(sc.alloc(&d_found, 4));
   RC(sc.alloc(&d_beta, 16));
-  RC(sc.alloc(&d_red, 32));
-  RC(sc.alloc(&d_aoff, 32));
-  RC(sc.alloc(&d_rowred, Hmax * 16));
-  RC(sc.alloc(&d_partial, (uint64_t)nchunks_max * 2 * std::max(S.max_w, 1u) * 16));
+  // the opening reduction runs the per-matrix kernel chains on up to NSIDE streams: one set of scratch per slot
+  const int nslots = c->open_streams;
+  uint32_t *s_red[zk_ctx::NSIDE], *s_aoff[zk_ctx::NSIDE], *s_rowred[zk_ctx::NSIDE], *s_partial[zk_ctx::NSIDE];
+  for (int i = 0; i < nslots; i++) {
+    RC(sc.alloc(&s_red[i], 32));
+    RC(sc.alloc(&s_aoff[i], 32));
+    RC(sc.alloc(&s_rowred[i], Hmax * 16));
+    RC(sc.alloc(&s_partial[i], (uint64_t)nchunks_max * 2 * std::max(S.max_w, 1u) * 16));
+  }
+  d_red = s_red[0]; d_aoff = s_aoff[0]; d_rowred = s_rowred[0]; d_partial = s_partial[0];
+  (void)d_red; (void)d_aoff; (void)d_rowred; (void)d_partial;
+  if (nslots > 1 && !c->side_fork) {
+    CK(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
+    for (int i = 0; i < zk_ctx::NSIDE; i++) {
+      CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->side_prod[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->side_cons[i], cudaEventDisableTiming));
+    }
+  }
   RC(sc.alloc(&d_idx, (uint64_t)std::max(num_queries, 1u) * 8));
   RC(sc.alloc(&d_ch, sizeof(fri::Chal)));
   CK(cudaMemcpyAsync(d_ch, ch, sizeof(fri::Chal), cudaMemcpyHostToDevice, st));
@@ -146,58 +161,95 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   std::map<DenKey, DenBuf> dens;  // per (LDE height, opening point): fri::inv_den_kernel
   {
     ProfScope ps(c, "open_reduce");
+    // pass 1 (context stream): output buffers per height, and 1 / (z - x_r) over the LDE domain + the barycentric
+    // weights over its low coset once per (height, point)
+    {
+      const uint32_t* pt = d_pts;
+      uint32_t k = 0;
+      for (uint32_t r = 0; r < n_rounds; r++) {
+        const zk_pdata* pd = rounds[r];
+        for (uint32_t m = 0; m < pd->n; m++, k++) {
+          uint64_t H = pd->heights[m];
+          uint32_t L = kbh::log2_exact(H), n = L - log_blowup;
+          if (!ro[L]) {
+            RC(sc.alloc(&ro[L], H * 16));
+            CK(cudaMemsetAsync(ro[L], 0, H * 16, st));
+          }
+          if (pd->widths[m] != 0) {
+            uint32_t gL = kbh::two_adic_generator(L);
+            for (uint32_t q = 0; q < n_points[k]; q++) {
+              const uint32_t* hz = points + 4 * (size_t)((pt - d_pts) / 4 + q);
+              DenKey key{L, {hz[0], hz[1], hz[2], hz[3]}};
+              if (dens.find(key) == dens.end()) {
+                DenBuf b;
+                RC(sc.alloc(&b.inv, H * 16));
+                RC(sc.alloc(&b.wts, (1ull << n) * 32));
+                ZK_LAUNCH(fri::inv_den_kernel, (unsigned)((H / fri::INV_BATCH + 255) / 256 + 1), 256, 0, st, pt + 4 * q, L, n, gL,
+                          b.inv, b.wts);
+                c->launches++;
+                dens.emplace(key, b);
+              }
+            }
+          }
+          pt += 4 * n_points[k];
+        }
+      }
+      CK(cudaGetLastError());
+    }
+    // pass 2: the chain of one matrix -- row reduction, barycentric partial sums and their finish, reduced openings --
+    // runs on side stream (matrix index mod nslots); only the accumulation into ro[L] stays on the context's stream, in
+    // matrix order.  Most of these kernels are far too small to fill the GPU (a 2^19 x 4 quotient chunk: 128 CTAs, 29 us),
+    // so the chains of different matrices overlap instead of queueing behind each other.
+    const bool fork = nslots > 1;
+    bool slot_used[zk_ctx::NSIDE] = {false, false, false, false};
+    if (fork) {
+      CK(cudaEventRecord(c->side_fork, st));
+      for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(c->side[i], c->side_fork, 0));
+    }
     uint32_t* out = d_proof;
     const uint32_t* pt = d_pts;
-    uint32_t k = 0;
+    uint32_t k = 0, live = 0;
     for (uint32_t r = 0; r < n_rounds; r++) {
       const zk_pdata* pd = rounds[r];
       for (uint32_t m = 0; m < pd->n; m++, k++) {
         uint64_t H = pd->heights[m];
         uint32_t w = pd->widths[m], pitch = pd->pitches[m];
         uint32_t L = kbh::log2_exact(H), n = L - log_blowup;
-        if (!ro[L]) {
-          RC(sc.alloc(&ro[L], H * 16));
-          CK(cudaMemsetAsync(ro[L], 0, H * 16, st));
-        }
         if (w == 0 || n_points[k] == 0) {
           pt += 4 * n_points[k];
           continue;
         }
-        uint32_t gL = kbh::two_adic_generator(L);
+        const int slot = fork ? (int)(live++ % (uint32_t)nslots) : 0;
+        cudaStream_t ss = fork ? c->side[slot] : st;
+        uint32_t *rowred = s_rowred[slot], *partial = s_partial[slot], *red = s_red[slot], *aoff = s_aoff[slot];
+        // the slot's buffers are free once the context stream has consumed their previous contents
+        if (fork && slot_used[slot]) CK(cudaStreamWaitEvent(ss, c->side_cons[slot], 0));
         if (w >= 64) {
           if (H % 4 == 0) {  // one warp per four rows
             auto kfn = fri::row_reduce_warp_kernel<4>;
-            ZK_LAUNCH_COOP(kfn, (unsigned)((H / 4 * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split, d_rowred);
+            ZK_LAUNCH_COOP(kfn, (unsigned)((H / 4 * 32 + 255) / 256), 256, 0, ss, pd->mats[m], H, w, pitch, d_apow_split, rowred);
           } else {
             auto kfn = fri::row_reduce_warp_kernel<1>;
-            ZK_LAUNCH_COOP(kfn, (unsigned)((H * 32 + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split, d_rowred);
+            ZK_LAUNCH_COOP(kfn, (unsigned)((H * 32 + 255) / 256), 256, 0, ss, pd->mats[m], H, w, pitch, d_apow_split, rowred);
           }
         } else
-          ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, st, pd->mats[m], H, w, pitch, d_apow_split,
-                         d_rowred);
+          ZK_LAUNCH_COOP(fri::row_reduce_kernel, (unsigned)((H + 255) / 256), 256, 0, ss, pd->mats[m], H, w, pitch, d_apow_split,
+                         rowred);
         c->launches++;
         for (uint32_t p0 = 0; p0 < n_points[k]; p0 += 2) {
           uint32_t np = std::min(2u, n_points[k] - p0);
           uint64_t N = 1ull << n;
           uint32_t nchunks = (uint32_t)((N + fri::BARY_ROWS - 1) / fri::BARY_ROWS);
-          // 1 / (z - x_r) over the LDE domain and the barycentric weights over its low coset: once per (height, point)
           const uint32_t *invp[2] = {nullptr, nullptr}, *wtsp[2] = {nullptr, nullptr};
           for (uint32_t q = 0; q < np; q++) {
             const uint32_t* hz = points + 4 * (size_t)((pt - d_pts) / 4 + q);
             DenKey key{L, {hz[0], hz[1], hz[2], hz[3]}};
             auto it = dens.find(key);
-            if (it == dens.end()) {
-              DenBuf b;
-              RC(sc.alloc(&b.inv, H * 16));
-              RC(sc.alloc(&b.wts, N * 32));
-              ZK_LAUNCH(fri::inv_den_kernel, (unsigned)((H / fri::INV_BATCH + 255) / 256 + 1), 256, 0, st, pt + 4 * q, L, n, gL,
-                        b.inv, b.wts);
-              c->launches++;
-              it = dens.emplace(key, b).first;
-            }
             invp[q] = it->second.inv;
             wtsp[q] = it->second.wts;
           }
+          // a second pair of points of the same matrix reuses the slot's red / aoff / partial
+          if (fork && p0 > 0) CK(cudaStreamWaitEvent(ss, c->side_cons[slot], 0));
           {
             // two columns per lane need 8-byte aligned rows: an even PITCH (odd widths are padded), the lane past the
             // last column accumulates the padding column and drops it
@@ -207,16 +259,24 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
             const uint32_t ntile = (w + (cpl << log_cw) - 1) / (cpl << log_cw);
             if (cpl == 2) {
               auto kfn = fri::bary_partial_kernel<2>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, ss, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, partial);
             } else {
               auto kfn = fri::bary_partial_kernel<1>;
-              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, st, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, d_partial);
+              ZK_LAUNCH_COOP(kfn, nchunks * ntile, 256, 0, ss, pd->mats[m], n, w, pitch, wtsp[0], wtsp[1], np, log_cw, partial);
             }
           }
-          ZK_LAUNCH_COOP(fri::bary_final_kernel, w, 128, 0, st, d_partial, nchunks, w, n, pt, np, out);
-          ZK_LAUNCH_COOP(fri::reduce_ys_kernel, 1, 256, 0, st, out, d_apow, d_alpha, w, np, num_reduced[L], d_red, d_aoff);
-          ZK_LAUNCH(fri::ro_accumulate_kernel, (unsigned)((H + 255) / 256), 256, 0, st, ro[L], d_rowred, L, invp[0], invp[1], np,
-                    d_red, d_aoff);
+          ZK_LAUNCH_COOP(fri::bary_final_kernel, w, 128, 0, ss, partial, nchunks, w, n, pt, np, out);
+          ZK_LAUNCH_COOP(fri::reduce_ys_kernel, 1, 256, 0, ss, out, d_apow, d_alpha, w, np, num_reduced[L], red, aoff);
+          if (fork) {
+            CK(cudaEventRecord(c->side_prod[slot], ss));
+            CK(cudaStreamWaitEvent(st, c->side_prod[slot], 0));
+          }
+          ZK_LAUNCH(fri::ro_accumulate_kernel, (unsigned)((H + 255) / 256), 256, 0, st, ro[L], rowred, L, invp[0], invp[1], np,
+                    red, aoff);
+          if (fork) {
+            CK(cudaEventRecord(c->side_cons[slot], st));
+            slot_used[slot] = true;
+          }
           CK(cudaGetLastError());
           c->launches += 4;
           num_reduced[L] += (uint64_t)np * w;
@@ -225,6 +285,8 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
         }
       }
     }
+    // every side chain ends in an ro_accumulate on the context's stream, which waited for it: the side streams are idle
+    // once the context stream reaches this point
   }
 
   // ---- FRI commit phase ------------------------------------------------------------------------

@@ -89,6 +89,7 @@ static int32_t ctx_init(zk_ctx* c) {
     if (v >= 1) c->slab_bytes = (uint64_t)v << 20;
   }
   if (const char* e = getenv("ZK_STREAM_MIN_BYTES")) c->stream_min_bytes = strtoull(e, nullptr, 10);
+  if (const char* e = getenv("ZK_OPEN_STREAMS")) c->open_streams = std::max(1, std::min((int)zk_ctx::NSIDE, atoi(e)));
   if (const char* e = getenv("ZK_EVEN_PITCH")) c->even_pitch = atoi(e) != 0;  // 0: dense LDEs (A/B measurements)
   if (const char* e = getenv("ZK_HASH_VEC_MIN_ROWS")) c->hash_vec_min_rows = strtoull(e, nullptr, 10);
   // a private stream-ordered pool per context: contexts that prove shards concurrently on one GPU must not
@@ -244,6 +245,12 @@ static void ctx_teardown(zk_ctx* c) {
   }
   helper_release(c);
   if (c->pool) cudaMemPoolDestroy(c->pool);
+  for (int i = 0; i < zk_ctx::NSIDE; i++) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->side_prod[i]) cudaEventDestroy(c->side_prod[i]);
+    if (c->side_cons[i]) cudaEventDestroy(c->side_cons[i]);
+  }
+  if (c->side_fork) cudaEventDestroy(c->side_fork);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

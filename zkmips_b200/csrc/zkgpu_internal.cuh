@@ -51,6 +51,13 @@ struct zk_ctx {
   uint64_t hash_vec_min_rows = 1ull << 19;  // streamed sponge: vector-load kernel from this many rows (env ZK_HASH_VEC_MIN_ROWS)
   bool even_pitch = true;                   // committed LDEs of odd width get a padding column (env ZK_EVEN_PITCH=0: dense)
   uint64_t stream_min_bytes = 8ull << 20;  // smaller matrices go up in one piece (env ZK_STREAM_MIN_BYTES)
+  // side streams of the opening reduction (fri.cu): the per-matrix chains of small kernels (row reduction, barycentric
+  // partial sums, their finish, the reduced openings) of different matrices overlap; created on first use
+  static constexpr int NSIDE = 4;
+  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t side_prod[NSIDE] = {nullptr, nullptr, nullptr, nullptr}, side_cons[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t side_fork = nullptr;
+  int open_streams = 4;  // env ZK_OPEN_STREAMS (1 = everything on the context's stream)
   std::mutex mu;
   uint32_t log_L = 22;                    // twiddle table group; NTT sizes up to 2^22 rows (MAX_CPU_LOG_DEGREE, crates/core/machine/src/cpu/mod.rs:8)
   uint32_t* tw[2] = {nullptr, nullptr};   // g_L^(+e), g_L^(-e), e < 2^(L-1)
