@@ -122,14 +122,7 @@ extern "C" int32_t zk_pcs_open(zk_ctx* c, uint32_t n_rounds, const zk_pdata* con
   }
   d_red = s_red[0]; d_aoff = s_aoff[0]; d_rowred = s_rowred[0]; d_partial = s_partial[0];
   (void)d_red; (void)d_aoff; (void)d_rowred; (void)d_partial;
-  if (nslots > 1 && !c->side_fork) {
-    CK(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
-    for (int i = 0; i < zk_ctx::NSIDE; i++) {
-      CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&c->side_prod[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->side_cons[i], cudaEventDisableTiming));
-    }
-  }
+  if (nslots > 1) RC(ensure_side_streams(c));
   RC(sc.alloc(&d_idx, (uint64_t)std::max(num_queries, 1u) * 8));
   RC(sc.alloc(&d_ch, sizeof(fri::Chal)));
   CK(cudaMemcpyAsync(d_ch, ch, sizeof(fri::Chal), cudaMemcpyHostToDevice, st));

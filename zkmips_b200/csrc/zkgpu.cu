@@ -143,6 +143,17 @@ extern "C" int32_t zk_ctx_create_on_stream(int32_t device, void* stream, zk_ctx*
 extern "C" int32_t zk_ctx_create(int32_t device, zk_ctx** out) { return zk_ctx_create_on_stream(device, nullptr, out); }
 
 static void ctx_teardown(zk_ctx* c);
+// side streams + their events (zkgpu_internal.cuh), created on first use
+int32_t ensure_side_streams(zk_ctx* c) {
+  if (c->side_fork) return ZK_OK;
+  CK(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
+  for (int i = 0; i < zk_ctx::NSIDE; i++) {
+    CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->side_prod[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->side_cons[i], cudaEventDisableTiming));
+  }
+  return ZK_OK;
+}
 
 // ---- upload helper -------------------------------------------------------------------------------------------
 static void helper_release(zk_ctx* c) {
@@ -965,7 +976,24 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
     }
     std::map<uint64_t, int> pending = members;
     tp.leaves_streamed = leaves_done;
+    // Device-resident sources (permutation traces, quotient chunks, generated traces): the transforms of DIFFERENT
+    // matrices are independent, and most of these matrices are far too narrow to fill the GPU (ten quotient chunks of
+    // 4 columns: ~8 launches of 10-15 us each), so matrix i runs on side stream i mod NSIDE and the context's stream
+    // joins them before the tree is built.  lde_dev and everything below it enqueue on c->stream: the context mutex is
+    // held, so the stream is swapped for the duration of the call.
+    cudaStream_t main_stream = c->stream;
+    const bool fan_out = !src_is_host && n_mats > 1 && c->open_streams > 1 && ensure_side_streams(c) == ZK_OK;
+    bool side_used[zk_ctx::NSIDE] = {false, false, false, false};
+    if (fan_out && cudaEventRecord(c->side_fork, main_stream) != cudaSuccess) rc = zk_fail(ZK_ERR_CUDA, "event record failed");
     for (uint32_t i = 0; i < n_mats && rc == ZK_OK; i++) {
+      if (fan_out) {
+        const int sl = (int)(i % (uint32_t)c->open_streams);
+        if (!side_used[sl]) {
+          cudaStreamWaitEvent(c->side[sl], c->side_fork, 0);
+          side_used[sl] = true;
+        }
+        c->stream = c->side[sl];
+      }
       uint32_t shift = kbh::mul(kbh::GEN, kbh::inv(domain_shifts[i]));  // GENERATOR / domain.shift
       uint32_t* keep = nullptr;
       if (c->keep_traces) {
@@ -986,11 +1014,18 @@ static int32_t commit_common(zk_ctx* c, uint32_t n_mats, const uint32_t* const* 
         if (st) st->remaining--;
       } else
         rc = lde_dev(c, src[i], heights[i], widths[i], log_blowup, shift, pd->mats[i], pd->pitches[i]);
+      c->stream = main_stream;
       pending[pd->heights[i]]--;
       // host traces: hash complete height classes and build every tree layer that is already determined while
       // the copy stream is still uploading the remaining matrices
       if (rc == ZK_OK && src_is_host && i + 1 < n_mats) rc = mmcs_advance(c, pd, tp, &pending);
     }
+    if (fan_out)
+      for (int sl = 0; sl < zk_ctx::NSIDE; sl++)
+        if (side_used[sl]) {
+          cudaEventRecord(c->side_prod[sl], c->side[sl]);
+          cudaStreamWaitEvent(main_stream, c->side_prod[sl], 0);
+        }
     for (auto& kv : cls)
       if (kv.second.state) dev_free(c, kv.second.state);
   } else {

@@ -138,6 +138,7 @@ struct zk_pdata {
 };
 
 int32_t dev_alloc(zk_ctx* c, uint64_t bytes, void** out);
+int32_t ensure_side_streams(zk_ctx* c);
 int32_t dev_free(zk_ctx* c, void* p);
 template <class T>
 int32_t DevScope::alloc(T** p, uint64_t bytes) {
