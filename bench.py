@@ -315,6 +315,11 @@ def exec_shard_leg(ctx, torch, args):
 NUM_PV = 8  # StarkMachine::num_pv_elts of the synthetic machine
 
 
+def num_pv(config):
+    """the recursion machines observe PROOF_MAX_NUM_PVS = 231 public values (stark/src/types.rs:73, machine.rs:127)"""
+    return 231 if config == "recursion" else NUM_PV
+
+
 FRI_PARAMS = {"recursion": (2, 42, 16)}  # compressed_fri_config (kb31_poseidon2.rs:216-227); default (1, 84, 16)
 
 
@@ -327,12 +332,12 @@ def shard_chips(config, rank=0, scale=0):
             log-21 execution shard's size);
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
-            MemoryVar, Select, MemoryConst, BaseAlu, ExtAlu and Poseidon2Wide are the REAL chips running a toy program
-            whose memory bus balances (synth.recursion_program_chips); the Poseidon2 rows (313 + 49 columns, 32 memory
-            sends) are filled on the device from the 16-word permutation inputs (zk_tracegen_poseidon2_wide).  The
-            stand-in of BatchFRI is the real Lt chip of the core machine, filled on the device from its AluEvent
-            records; ExpReverseBitsLen / PublicValues are this library's synthetic AIRs at the reference's heights.
-            Many small matrices, latency-bound."""
+            All NINE chips are the reference's own compress-machine chips (recursion/core/src/machine.rs:112-128),
+            transcribed from their Air::eval, running a toy program whose memory bus balances
+            (synth.recursion_program_chips): BatchFRI accumulators feed ExtAlu, ExpReverseBitsLen results feed
+            BaseAlu, PublicValues ties the digest of the 231 public values to memory; the Poseidon2 rows (313 + 49
+            columns, 32 memory sends) are filled on the device from the 16-word permutation inputs
+            (zk_tracegen_poseidon2_wide).  Many small matrices, latency-bound."""
     from zkmips_b200 import synth
     d = scale
     if config == "keccak":
@@ -342,13 +347,10 @@ def shard_chips(config, rank=0, scale=0):
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
     if config == "recursion":
-        mem, alu, p2, sel, var, ext = synth.recursion_program_chips(
+        mem, alu, p2, sel, var, ext, bfri, erb, pvc = synth.recursion_program_chips(
             16 - d, 15 - d, 16 - d, 3, seed=41 + rank, names=("MemoryConst", "BaseAlu", "Poseidon2Wide"),
-            log_var=18 - d, log_ext=15 - d, log_sel=18 - d)
-        return [var, sel, mem, alu, ext, p2,
-                synth.lt_chip(17 - d, seed=4 + rank, name="BatchFRI", device=True),
-                synth.wide_chip(17 - d, 64, seed=7 + rank, name="ExpReverseBitsLen"),
-                synth.fibonacci_chip(max(4 - d, 2), 1 + rank, 1, name="PublicValues")]
+            log_var=18 - d, log_ext=15 - d, log_sel=18 - d, log_bf=17 - d, log_exp=17 - d, pv=True)
+        return [var, sel, mem, alu, ext, p2, bfri, erb, pvc]
     send, recv = synth.lookup_side_chips(18 - d, seed=9 + rank)
     return [synth.wide_chip(16 - d, 1024, seed=11 + rank), synth.wide_chip(18 - d, 64, seed=12 + rank),
             synth.fibonacci_chip(20 - d, 1 + rank, 1), send, recv]
@@ -408,7 +410,7 @@ class ShardWorker:
     """One in-flight shard slot of a GPU: its own context (stream, pool, slab buffers) and prover; the proving key is
     committed ONCE per context (pk_to_device, prover.rs:63) and every shard gets a clone of the machine challenger."""
 
-    def __init__(self, ctx, chips, fri=(1, 84, 16)):
+    def __init__(self, ctx, chips, fri=(1, 84, 16), NUM_PV=NUM_PV):
         from zkmips_b200 import Challenger, synth
         from zkmips_b200.prover import GpuShardProver
         self.ctx = ctx
@@ -438,7 +440,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     chips = _pin(torch, shard_chips(args.shard_config, rank))
     cells = shard_cells(chips)
     fri = FRI_PARAMS.get(args.shard_config, (1, 84, 16))
-    w1 = ShardWorker(ctx, chips, fri)
+    w1 = ShardWorker(ctx, chips, fri, num_pv(args.shard_config))
     sp = w1.prove(chips)  # warm-up (also pages the generated quotient kernels in)
     w1.prover.phase_ms = {}  # host phase clocks of the timed steps only
     ctx.prof_reset()
@@ -469,7 +471,7 @@ def shard_leg(ctx, torch, dist, world, rank, args):
     for _ in range(args.in_flight - 1):
         cx = ctx.lib.ctx_create(torch.cuda.current_device())
         attach_helper(cx, getattr(args, "upload_helper", None))
-        wk = ShardWorker(cx, chips, fri)
+        wk = ShardWorker(cx, chips, fri, num_pv(args.shard_config))
         wk.prove(chips)  # warm-up of the extra context
         workers.append(wk)
     S = args.multi_shards
@@ -540,9 +542,9 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
     while True:
         chips = shard_chips(args.shard_config, 0, scale)
         fri = FRI_PARAMS.get(args.shard_config, (1, 84, 16))
-        op = osp.OracleShardProver(airs, fri[0], fri[1], fri[2], num_pv_elts=NUM_PV)
+        op = osp.OracleShardProver(airs, fri[0], fri[1], fri[2], num_pv_elts=num_pv(args.shard_config))
         from zkmips_b200 import synth
-        pvs = synth.public_values_for(chips, NUM_PV)
+        pvs = synth.public_values_for(chips, num_pv(args.shard_config))
         t = time.perf_counter()
         host_chips = with_host_traces(chips)      # generate_trace on the CPU, as the reference does
         tracegen_s = time.perf_counter() - t
@@ -557,7 +559,7 @@ def shard_cpu_leg(args, ctx, torch, full_cells):
         scale -= 1 if dt > 2.0 else 2
         scale = max(scale, 0)
     cells = shard_cells(chips)
-    w = ShardWorker(ctx, chips, fri)
+    w = ShardWorker(ctx, chips, fri, num_pv(args.shard_config))
     t = time.perf_counter()
     sp = w.prove(chips)
     gpu_dt = time.perf_counter() - t

@@ -1,6 +1,8 @@
 """The constraint IR: JSON round trip of the real chips (the Rust-side exporter's target format) and the transcribed
 chips' shapes against the reference's cost table."""
 import json
+
+import numpy as np
 import os
 
 from zkmips_b200.air import codegen, library
@@ -15,7 +17,8 @@ def test_exported_json_reproduces_the_generated_kernels():
     program as the hand transcription: identical JSON again, and byte-identical generated CUDA."""
     for make in (library.add_sub, library.lt, library.bitwise, lambda: library.poseidon2_wide(3),
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
-                 library.ext_alu, library.select):
+                 library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
+                 library.public_values_chip):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -42,7 +45,7 @@ def test_real_chip_shapes_match_mips_costs():
         assert air.max_degree() == 3  # log_quotient_degree 1
 
 
-def _constraints_on_trace(air, main, prep=None, seed=5):
+def _constraints_on_trace(air, main, prep=None, seed=5, pvs=()):
     """every constraint of `air` (own + LogUp) on the trace domain itself: rows local / next, selectors as indicator
     vectors, permutation trace from the numpy LogUp restatement.  All must vanish on a valid trace."""
     import numpy as np
@@ -59,7 +62,7 @@ def _constraints_on_trace(air, main, prep=None, seed=5):
     first[0], last[n - 1] = 1, 1
     sel = {"first": first, "last": last, "trans": 1 - last}
     out = []
-    for c in ae.eval_rows(air, rows, sel, chal, lcs, (0,) * 14, ()):
+    for c in ae.eval_rows(air, rows, sel, chal, lcs, (0,) * 14, tuple(int(x) for x in pvs)):
         out.append(np.stack(c.c) if isinstance(c, ae.VExt) else np.asarray(c))
     return out
 
@@ -121,6 +124,34 @@ def test_recursion_program_chips_satisfy_their_airs():
     bad = alu.canon[1].copy()
     bad[0, 0] = (bad[0, 0] + 1) % ae_P                      # a wrong result
     assert any(v.any() for v in _constraints_on_trace(library.base_alu(), bad, alu.canon[0])[:20])
+
+
+def test_compress_machine_chips_satisfy_their_airs():
+    """The three chips that complete the reference's compress machine (recursion/core/src/machine.rs:112-128) beside the
+    six above: BatchFRI (13 + 6 columns: dummy + 12 accumulator constraints, 3 reads, 1 write), ExpReverseBitsLen
+    (7 + 10: 8 constraints, 3 sends with signed multiplicities) and PublicValues (1 + 10, 231 public values, digest at
+    223..231), on the toy program of synth.recursion_program_chips; all three read the NEXT row or none of the
+    `local_only` chips' shortcuts.  A corrupted cell breaks a constraint of each."""
+    from zkmips_b200 import synth
+    chips = synth.recursion_program_chips(5, 4, 5, log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=True)
+    assert [c.air for c in chips] == ["MemoryConst", "BaseAlu", "Poseidon2WideDeg3", "Select", "MemoryVar", "ExtAlu",
+                                      "BatchFRI", "ExpReverseBitsLen", "PublicValues"]
+    pvs = np.zeros(231, np.uint64)
+    pvs[223:231] = chips[8].pv_digest
+    for chip, air, shape, cell in ((chips[6], library.batch_fri(3), (13, 6, 1, 3, 13), (2, 1)),
+                                   (chips[7], library.exp_reverse_bits_len(3), (7, 10, 3, 0, 8), (3, 4)),
+                                   (chips[8], library.public_values_chip(), (1, 10, 1, 0, 8), (5, 0))):
+        assert (air.main_width, air.prep_width, len(air.sends), len(air.receives)) == shape[:4]
+        assert air.num_constraints == shape[4] + (air.perm_width - 1) + 3
+        assert not air.local_only and air.max_degree() <= 3
+        assert all(not v.any() for v in _constraints_on_trace(air, chip.canon[1], chip.canon[0], pvs=pvs))
+        bad = chip.canon[1].copy()
+        bad[cell] = (bad[cell] + 1) % ae_P
+        assert any(v.any() for v in _constraints_on_trace(air, bad, chip.canon[0], pvs=pvs)[:shape[4]]), air.name
+    # the six older chips are unchanged by the additions (the accumulators / results only replace operands)
+    for chip, air in ((chips[0], library.memory_const()), (chips[1], library.base_alu()), (chips[4], library.memory_var()),
+                      (chips[5], library.ext_alu())):
+        assert all(not v.any() for v in _constraints_on_trace(air, chip.canon[1], chip.canon[0]))
 
 
 def test_exporter_output_without_logup_constraints_loads_to_the_same_program():

@@ -34,10 +34,13 @@ def p2w_host_chip(log_n, degree, **kw):
     return c
 
 
+COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=True)
+
+
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -57,7 +60,12 @@ def test_quotient_values_match_oracle(be, which):
             "BaseAlu": lambda: synth.recursion_program_chips(5, 4, 5)[1],
             "Select": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[3],
             "MemoryVar": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[4],
-            "ExtAlu": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[5]}[which]()
+            "ExtAlu": lambda: synth.recursion_program_chips(5, 4, 5, log_var=6, log_ext=4, log_sel=5)[5],
+            # the chips that complete the compress machine; they read the NEXT row (transition constraints) and
+            # PublicValues the shard's 231 public values
+            "BatchFRI": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[6],
+            "ExpReverseBitsLen": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[7],
+            "PublicValues": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[8]}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
@@ -88,7 +96,7 @@ def test_quotient_values_match_oracle(be, which):
         kw["perm"] = (perm_pd, 0)
         okw["perm_q"] = _natural(perm_pd.lde(0))
         okw["lcs"] = ob.from_monty(lcs)
-    pvs = su.public_values_for([chip])
+    pvs = su.public_values_for([chip], 231 if which == "PublicValues" else 8)
     gcs = su.M(np.arange(1, 15))
     dptr = ctx.quotient(chip.air, (main_pd, 0), n, lqd, alpha, perm_challenges=chal, public_values=pvs,
                         local_cumsum=lcs, global_cumsum=gcs, **kw)
@@ -111,8 +119,9 @@ def _machine(chips):
     return {c.name: c for c in chips}
 
 
-def _prove(ctx, chips, log_blowup, nq, pw, pc_start=0x1234, mutate=None):
+def _prove(ctx, chips, log_blowup, nq, pw, pc_start=0x1234, mutate=None, num_pv=None):
     """setup + the machine-level challenger (pk.observe_into) + prove one shard; returns what the verifier needs"""
+    NUM_PV = num_pv or globals()["NUM_PV"]
     prover = GpuShardProver(ctx, log_blowup, nq, pw, num_pv_elts=NUM_PV)
     pk = prover.setup(chips, pc_start=su.M([pc_start])[0], initial_global_cumulative_sum=su.M(np.arange(101, 115)))
     ch = Challenger(ctx)
@@ -310,6 +319,60 @@ def test_recursion_program_shard_verifies_completely(be):
     assert not ok and why.endswith("local cumulative sum is not zero"), why
     data.free()
     pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_compress_machine_shard_verifies_completely(be):
+    """The toy program on ALL NINE chips of the reference's compress machine (recursion/core/src/machine.rs:112-128:
+    MemoryConst, MemoryVar, BaseAlu, ExtAlu, Poseidon2Wide, BatchFRI, Select, ExpReverseBitsLen, PublicValues), with
+    the machine's 231 public values (PROOF_MAX_NUM_PVS, stark/src/types.rs:73) observed and the digest constrained by
+    PublicValues: BatchFRI accumulators feed ExtAlu, ExpReverseBitsLen results feed BaseAlu, the memory bus balances.
+    Complete verification, byte-identical with the CPU prover; a wrong digest in the public values is rejected by
+    PublicValues' constraint alone."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    logs = (5, 4, 5) if be == "emu" else (12, 11, 11)
+    more = COMPRESS_SMALL if be == "emu" else dict(log_var=14, log_ext=11, log_sel=12, log_bf=12, log_exp=11, pv=True)
+    chips = synth.recursion_program_chips(*logs, **more)
+    assert sorted(c.air for c in chips) == sorted(["MemoryConst", "MemoryVar", "BaseAlu", "ExtAlu", "Poseidon2WideDeg3",
+                                                   "BatchFRI", "Select", "ExpReverseBitsLen", "PublicValues"])
+    npv = 231
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw, num_pv=npv)
+    host = list(chips)
+    host[2] = p2w_host_chip(logs[0], 3)
+    host[2].preprocessed = chips[2].preprocessed
+    host[2].main = ob.poseidon2_wide_trace(chips[2].events, chips[2].rows, True)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(host), [sp], npv, 1, nq, pw)
+    assert ok, why
+    assert not sp.local_cumulative_sum().any()
+    assert all(sp.opened_values[sp.chip_ordering[c.name]].local_cumulative_sum.any() for c in chips)
+    # chips with transition constraints are opened at zeta and zeta * g; the local_only ones at zeta alone, their `next`
+    # row is the zero vector the reference puts there (prover.rs:576-600)
+    for c in chips:
+        v = sp.opened_values[sp.chip_ordering[c.name]]
+        assert (not np.asarray(v.preprocessed.next).any()) == su.AIRS[c.air].local_only, c.name
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=npv)
+    opk = op.setup(host, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    assert pf.to_bincode(op.prove(opk, host, och, su.public_values_for(host, npv))) == pf.to_bincode(sp)
+    # a public-values vector whose digest differs from what the program committed: same prover, rejected
+    bad_pvs = su.public_values_for(chips, npv).copy()
+    bad_pvs[225] = su.M([5])[0]
+    sp2 = prover.open(pk, prover.commit(chips, bad_pvs), _machine_challenger(ctx, pk))
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(host), [sp2], npv, 1, nq, pw)
+    assert not ok, "a wrong digest must violate PublicValues' constraint"
+    data.free()
+    pk.data.free()
+
+
+def _machine_challenger(ctx, pk):
+    ch = Challenger(ctx)
+    pk.observe_into(ch)
+    return Challenger(ctx, ch.w)
 
 
 @pytest.mark.parametrize("drop", ["public_values", "vk", "local_sum", "global_sum", "perm_commit", "local_only"])

@@ -229,12 +229,13 @@ class Air:
         return len(self.constraints)
 
     def max_degree(self):
-        """Degree of the constraints in the trace polynomials (selectors count 1), as
-        crates/stark/src/chip.rs:81-87 computes it for log_quotient_degree."""
+        """Degree of the constraints in the trace polynomials as crates/stark/src/chip.rs:81-87 computes it for
+        log_quotient_degree (p3 SymbolicExpression::degree_multiple: is_first_row / is_last_row count 1,
+        is_transition 0 -- its factor X - g^-1 is paid for by the vanishing polynomial)."""
         deg = []
         for n in self.nodes:
             k = n[0]
-            if k in ("prep", "main", "perm", "first", "last", "trans"):
+            if k in ("prep", "main", "perm", "first", "last"):
                 deg.append(1)
             elif k in ("add", "sub"):
                 deg.append(max(deg[n[1]], deg[n[2]]))

@@ -512,8 +512,104 @@ def select():
     return air
 
 
+def batch_fri(degree=3):
+    """BatchFRIChip<DEGREE> (crates/recursion/core/src/chips/batch_fri.rs:36-55 columns, :291-358 eval): one row per
+    (alpha_pow, p_at_z, p_at_x) triple of a BatchFRI instruction, acc accumulated down the rows of the instruction and
+    written to memory on its `is_end` row.  Main: acc[4], alpha_pow[4], p_at_z[4], p_at_x; preprocessed: is_real, is_end,
+    acc_addr, alpha_pow_addr, p_at_z_addr, p_at_x_addr.  Uses the next row (not `local_only`)."""
+    air = Air("BatchFRI", main_width=13, prep_width=6)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    p = b.preprocessed().local()
+    is_real, is_end, acc_addr, alpha_pow_addr, p_at_z_addr, p_at_x_addr = p
+
+    def cols(r):
+        return r[0:4], r[4:8], r[8:12], r[12]
+    acc, alpha_pow, p_at_z, p_at_x = cols(m)
+    n_acc, n_alpha_pow, n_p_at_z, n_p_at_x = cols(mn)
+    # :347-350 dummy constraint normalising the chip to DEGREE
+    lhs = is_real
+    for _ in range(degree - 1):
+        lhs = lhs * is_real
+    b.assert_eq(lhs, lhs)
+    # :300-307 memory reads of alpha_pow, p_at_z (blocks) and p_at_x (single); acc written with multiplicity is_end
+    b.receive(LOOKUP_MEMORY, [alpha_pow_addr] + list(alpha_pow), is_real)
+    b.receive(LOOKUP_MEMORY, [p_at_z_addr] + list(p_at_z), is_real)
+    b.receive(LOOKUP_MEMORY, [p_at_x_addr, p_at_x, 0, 0, 0], is_real)
+    b.send(LOOKUP_MEMORY, [acc_addr] + list(acc), is_end)
+
+    def term(ap, z, x):                                 # alpha_pow * (p_at_z - from_base(p_at_x))
+        return _ext_mul(ap, [z[0] - x, z[1], z[2], z[3]])
+    # :310-315 first row
+    for l, r in zip(acc, term(alpha_pow, p_at_z, p_at_x)):
+        b.when_first_row().assert_eq(l, r)
+    # :318-323 the row after an `is_end` row starts a new accumulator
+    for l, r in zip(n_acc, term(n_alpha_pow, n_p_at_z, n_p_at_x)):
+        b.when_transition().when(is_end).assert_eq(l, r)
+    # :326-332 otherwise it continues the running one
+    for l, a, r in zip(n_acc, acc, term(n_alpha_pow, n_p_at_z, n_p_at_x)):
+        b.when_transition().when_not(is_end).assert_eq(l, a + r)
+    b.eval_permutation_constraints(batch_size=2 if degree == 3 else 8)
+    return air
+
+
+def exp_reverse_bits_len(degree=3):
+    """ExpReverseBitsLenChip<DEGREE> (crates/recursion/core/src/chips/exp_reverse_bits.rs:32-67 columns, :355-426 eval):
+    one row per exponent bit, accum <- accum^2 * (bit ? x : 1).  Main: x, current_bit, prev_accum_squared,
+    prev_accum_squared_times_multiplier, accum, accum_squared, multiplier; preprocessed: x_mem, exponent_mem,
+    result_mem (MemoryAccessColsChips {addr, mult}: negative multiplicity = read, chips/mem/mod.rs:14-22),
+    iteration_num, is_first, is_last, is_real."""
+    air = Air("ExpReverseBitsLen", main_width=7, prep_width=10)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    p, pn = b.preprocessed().local(), b.preprocessed().next()
+    x, current_bit, prev_accum_squared, pasm, accum, accum_squared, multiplier = m
+    x_addr, x_mult, e_addr, e_mult, r_addr, r_mult, _iteration_num, is_first, is_last, is_real = p
+    n_is_real = pn[9]
+    if degree > 3:                                      # :366-370
+        lhs = is_real
+        for _ in range(degree - 1):
+            lhs = lhs * is_real
+        b.assert_eq(lhs, lhs)
+    b.send(LOOKUP_MEMORY, [x_addr, x, 0, 0, 0], x_mult)                                             # :374
+    b.when_transition().when(n_is_real).when_not(is_last).assert_eq(x, mn[0])                        # :377-381
+    b.send(LOOKUP_MEMORY, [e_addr, current_bit, 0, 0, 0], e_mult)                                    # :384-388
+    b.when(is_first).assert_eq(accum, multiplier)                                                    # :391
+    b.when(is_real).when(current_bit).assert_eq(multiplier, x)                                       # :394-397
+    b.when(is_real).when_not(current_bit).assert_eq(multiplier, 1)                                   # :398-401
+    b.when(is_real).assert_eq(pasm, prev_accum_squared * multiplier)                                 # :405-408
+    b.when(is_real).when_not(is_first).assert_eq(accum, pasm)                                        # :410-413
+    b.when(is_real).assert_eq(accum_squared, accum * accum)                                          # :416
+    b.when_transition().when(n_is_real).when_not(is_last).assert_eq(mn[2], accum_squared)            # :418-422
+    b.send(LOOKUP_MEMORY, [r_addr, accum, 0, 0, 0], r_mult)                                          # :425
+    b.eval_permutation_constraints(batch_size=2 if degree == 3 else 8)
+    return air
+
+
+RECURSIVE_PROOF_NUM_PV_ELTS = 231    # size_of::<RecursionPublicValues<u8>>() = PROOF_MAX_NUM_PVS (stark/src/types.rs:73)
+RECURSION_PV_DIGEST = 223            # RECURSION_PUBLIC_VALUES_COL_MAP.digest[0] (recursion/core/src/air/public_values.rs:79-145)
+
+
+def public_values_chip():
+    """PublicValuesChip (crates/recursion/core/src/chips/public_values.rs:37-50 columns, :289-309 eval): 16 rows, row i < 8
+    reads digest element i from memory (send_single with multiplicity -1) and ties it to the shard's public values:
+    pv_idx[i] * (public_values.digest[i] - pv_element) = 0.  Main: pv_element; preprocessed: pv_idx[8], pv_mem {addr,
+    mult}.  RecursionPublicValues is 231 elements, digest at 223..231."""
+    air = Air("PublicValues", main_width=1, prep_width=10, num_public_values=RECURSIVE_PROOF_NUM_PV_ELTS)
+    b = AirBuilder(air)
+    pv_element = b.main().local()[0]
+    p = b.preprocessed().local()
+    pv = b.public_values()
+    b.send(LOOKUP_MEMORY, [p[8], pv_element, 0, 0, 0], p[9])
+    for i in range(8):
+        b.when(p[i]).assert_eq(pv[RECURSION_PV_DIGEST + i], pv_element)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
-            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select()]
+            local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip()]

@@ -145,6 +145,9 @@ def public_values_for(chips, n=8):
         if c.air == "fibonacci":
             pv[0:3] = c.pvs
     pv[3] = LOOKUP_PV3
+    for c in chips:
+        if getattr(c, "pv_digest", None) is not None:                  # RecursionPublicValues.digest (air/public_values.rs:144)
+            pv[223:231] = c.pv_digest
     return M(pv)
 
 
@@ -366,12 +369,19 @@ def _inv_mod(x):
 
 
 def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, fill=0.75, names=None, log_var=None,
-                            log_ext=None, log_sel=None):
+                            log_ext=None, log_sel=None, log_bf=None, log_exp=None, pv=False):
     """(MemoryConst, BaseAlu, Poseidon2WideDeg<degree>) chips of the toy program; the Poseidon2 rows are filled on the
     device from the permutation inputs, the other two chips' traces are a few columns and stay host arrays.
     With log_var / log_ext / log_sel also (MemoryVar, ExtAlu, Select): MemoryVar writes the two extension operands of
     every ExtAlu operation (read once each), Select reads a bit constant (addresses n_const - 2 / n_const - 1 hold 0 / 1)
-    and two other constants."""
+    and two other constants.
+    With log_bf / log_exp / pv also (BatchFRI, ExpReverseBitsLen, PublicValues) -- with them the program runs on all NINE
+    chips of the reference's compress machine (recursion/core/src/machine.rs:112-128): a BatchFRI instruction of up to
+    four (alpha_pow, p_at_z, p_at_x) triples reads its extension operands from MemoryVar and p_at_x from the constants,
+    and its accumulator (written once, multiplicity 1) is the first operand of an ExtAlu operation; an
+    ExpReverseBitsLen instruction of up to five bits reads its base and its bits (the two bit constants) and its result
+    is the first operand of a BaseAlu operation; PublicValues reads eight constants, which are the digest of the
+    shard's RecursionPublicValues (`pv_digest` on the chip, public_values_for puts it at 223..231)."""
     rng = np.random.default_rng(seed)
     n_perm = max(1, int((1 << log_p2) * fill))
     n_alu = max(1, int((4 << log_alu) * fill))
@@ -390,17 +400,60 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
     # BaseAlu instructions
     a1 = rng.integers(0, n_const - 2, n_alu)
     a2 = rng.integers(0, n_const - 2, n_alu)
-    np.add.at(reads, a1, 1)
+    exp_chip = None
+    a1_addr = a1.astype(np.int64)
+    x = consts[a1]
+    from_const = np.ones(n_alu, bool)
+    if log_exp is not None:
+        # ExpReverseBitsLenChip (chips/exp_reverse_bits.rs:100-141 preprocessed, :216-246 main): one row per bit
+        rows_x = 1 << log_exp
+        n_xr = max(1, int(rows_x * fill))
+        starts = np.arange(0, n_xr, 5)
+        n_xi = len(starts)
+        assert n_xi <= n_alu, "BaseAlu too short to consume the ExpReverseBitsLen results"
+        instr_of = np.arange(n_xr) // 5
+        it = np.arange(n_xr) % 5
+        last = np.zeros(n_xr, bool)
+        last[np.minimum(starts + 4, n_xr - 1)] = True
+        base_addr = rng.integers(0, n_const - 2, n_xi)
+        bits = rng.integers(0, 2, n_xr)
+        np.add.at(reads, base_addr, 1)                                 # x is read once, on the first row
+        np.add.at(reads, n_const - 2 + bits, 1)                        # every row reads its bit
+        xb = consts[base_addr][instr_of]
+        mult_col = np.where(bits == 1, xb, 1).astype(np.uint64)
+        exp_main = np.zeros((rows_x, 7), np.uint64)
+        accum = np.uint64(1)
+        results = np.zeros(n_xi, np.uint64)
+        for r in range(n_xr):
+            prev = np.uint64(1) if it[r] == 0 else accum
+            pas = prev * prev % P
+            accum = pas * mult_col[r] % P
+            exp_main[r] = (xb[r], bits[r], pas, accum, accum, accum * accum % P, mult_col[r])
+            if last[r]:
+                results[instr_of[r]] = accum
+        exp_prep = np.zeros((rows_x, 10), np.uint64)
+        res_addr = (1 << 29) + np.arange(n_xi)
+        exp_prep[:n_xr, 0] = base_addr[instr_of]
+        exp_prep[:n_xr, 1] = np.where(it == 0, P - 1, 0)               # -1: read (chips/mem/mod.rs:14-22)
+        exp_prep[:n_xr, 2] = n_const - 2 + bits
+        exp_prep[:n_xr, 3] = P - 1
+        exp_prep[:n_xr, 4] = res_addr[instr_of]
+        exp_prep[:n_xr, 5] = last                                      # the result is written once, read by BaseAlu
+        exp_prep[:n_xr, 6], exp_prep[:n_xr, 7], exp_prep[:n_xr, 8], exp_prep[:n_xr, 9] = it, it == 0, last, 1
+        exp_chip = Chip("ExpReverseBitsLen", "ExpReverseBitsLen", M(exp_main), preprocessed=M(exp_prep))
+        exp_chip.canon = (exp_prep, exp_main)
+        a1_addr[:n_xi], x[:n_xi], from_const[:n_xi] = res_addr, results, False
+    np.add.at(reads, a1[from_const], 1)
     np.add.at(reads, a2, 1)
     op = rng.integers(0, 4, n_alu)                                     # 0 add, 1 sub, 2 mul, 3 div
-    x, y = consts[a1], consts[a2]
+    y = consts[a2]
     res = np.select([op == 0, op == 1, op == 2], [(x + y) % P, (x + P - y) % P, x * y % P], x * _inv_mod(y) % P)
     alu_rows = 1 << log_alu
     alu_main = np.zeros((alu_rows * 4, 3), np.uint64)
     alu_main[:n_alu] = np.stack([res, x, y], axis=1)                   # BaseAluIo {out, in1, in2}
     alu_prep = np.zeros((alu_rows * 4, 8), np.uint64)
     alu_prep[:n_alu, 0] = (1 << 23) + np.arange(n_alu)                 # fresh output addresses
-    alu_prep[:n_alu, 1], alu_prep[:n_alu, 2] = a1, a2
+    alu_prep[:n_alu, 1], alu_prep[:n_alu, 2] = a1_addr, a2
     alu_prep[np.arange(n_alu), 3 + op] = 1                             # is_add / is_sub / is_mul / is_div; mult = 0
     # MemoryConst: entries (value block, addr, mult), two per row
     mem_rows = 1 << log_mem
@@ -433,6 +486,22 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
         eop = rng.integers(0, 4, n_ext)                                # 0 add, 1 sub, 2 mul, 3 div
         u = rng.integers(0, P, (n_ext, 4), dtype=np.uint64)
         v = rng.integers(0, P, (n_ext, 4), dtype=np.uint64)
+        bf = None
+        if log_bf is not None:
+            # BatchFRIChip (chips/batch_fri.rs:90-118 preprocessed, :196-208 main): instructions of <= 4 triples
+            rows_b = 1 << log_bf
+            n_br = max(1, int(rows_b * fill))
+            b_instr = np.arange(n_br) // 4
+            n_bi = int(b_instr[-1]) + 1
+            assert n_bi <= n_ext, "ExtAlu too short to consume the BatchFRI accumulators"
+            b_end = np.zeros(n_br, bool)
+            b_end[np.minimum(np.arange(0, n_br, 4) + 3, n_br - 1)] = True
+            b_alpha = rng.integers(0, P, (n_br, 4), dtype=np.uint64)
+            b_z = rng.integers(0, P, (n_br, 4), dtype=np.uint64)
+            b_xaddr = rng.integers(0, n_const - 2, n_br)
+            np.add.at(reads, b_xaddr, 1)
+            bf = (rows_b, n_br, b_instr, n_bi, b_end, b_alpha, b_z, b_xaddr)
+            eop[:n_bi] = 2 * rng.integers(0, 2, n_bi)                  # add or mul: out follows from in1 = acc
 
         def emul(a, c):                                                # F_p[X] / (X^4 - 3)
             r = np.zeros_like(a)
@@ -457,6 +526,36 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
         var_main[0:2 * n_ext:2], var_main[1:2 * n_ext:2] = in1, in2
         var_prep = np.zeros((2 * rows_v, 2), np.uint64)
         var_prep[:2 * n_ext, 0], var_prep[:2 * n_ext, 1] = var_base + np.arange(2 * n_ext), 1
+        if bf is not None:
+            rows_b, n_br, b_instr, n_bi, b_end, b_alpha, b_z, b_xaddr = bf
+            assert 2 * n_ext + 2 * n_br <= 2 * rows_v, "MemoryVar too short for the BatchFRI operands"
+            b_x = consts[b_xaddr]
+            zx = b_z.copy()
+            zx[:, 0] = (zx[:, 0] + P - b_x) % P
+            terms = emul(b_alpha, zx)
+            b_acc = np.zeros((n_br, 4), np.uint64)
+            for r in range(n_br):
+                b_acc[r] = terms[r] if r % 4 == 0 else (b_acc[r - 1] + terms[r]) % P
+            acc_addr = (1 << 27) + np.arange(n_bi)
+            bf_main = np.zeros((rows_b, 13), np.uint64)
+            bf_main[:n_br] = np.concatenate([b_acc, b_alpha, b_z, b_x[:, None]], axis=1)
+            bf_prep = np.zeros((rows_b, 6), np.uint64)
+            opnd = (1 << 28) + np.arange(2 * n_br)
+            bf_prep[:n_br] = np.stack([np.ones(n_br, np.uint64), b_end.astype(np.uint64), acc_addr[b_instr].astype(np.uint64),
+                                       opnd[0::2].astype(np.uint64), opnd[1::2].astype(np.uint64), b_xaddr.astype(np.uint64)], axis=1)
+            o = 2 * n_ext
+            var_main[o:o + 2 * n_br:2], var_main[o + 1:o + 2 * n_br:2] = b_alpha, b_z
+            var_prep[o:o + 2 * n_br, 0], var_prep[o:o + 2 * n_br, 1] = opnd, 1
+            # the accumulators are the first operands of the first n_bi ExtAlu operations: their MemoryVar entries
+            # stay in the table with multiplicity 0 (written, never read)
+            accs = b_acc[b_end]
+            in1[:n_bi] = accs
+            out[:n_bi] = np.where((eop[:n_bi] == 0)[:, None], (accs + in2[:n_bi]) % P, emul(accs, in2[:n_bi]))
+            ext_main[:n_ext] = np.concatenate([out, in1, in2], axis=1)
+            ext_prep[:n_bi, 1] = acc_addr
+            var_prep[0:2 * n_bi:2, 1] = 0
+            bfc = Chip("BatchFRI", "BatchFRI", M(bf_main), preprocessed=M(bf_prep))
+            bfc.canon = (bf_prep, bf_main)
         var = Chip("MemoryVar", "MemoryVar", M(var_main.reshape(rows_v, 8)), preprocessed=M(var_prep.reshape(rows_v, 4)),
                    local_only=True)
         var.canon = (var_prep.reshape(rows_v, 4), var_main.reshape(rows_v, 8))
@@ -464,6 +563,25 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
                    local_only=True)
         ext.canon = (ext_prep.reshape(rows_e, 32), ext_main.reshape(rows_e, 48))
         extra += [var, ext]
+        if bf is not None:
+            extra.append(bfc)
+    else:
+        assert log_bf is None, "BatchFRI needs MemoryVar and ExtAlu (log_var, log_ext)"
+    if exp_chip is not None:
+        extra.append(exp_chip)
+    if pv:
+        # PublicValuesChip (chips/public_values.rs:82-125): 16 rows, row i < 8 reads digest element i
+        d_addr = rng.integers(0, n_const - 2, 8)
+        np.add.at(reads, d_addr, 1)
+        pv_prep = np.zeros((16, 10), np.uint64)
+        pv_prep[np.arange(8), np.arange(8)] = 1
+        pv_prep[:8, 8], pv_prep[:8, 9] = d_addr, P - 1
+        pv_main = np.zeros((16, 1), np.uint64)
+        pv_main[:8, 0] = consts[d_addr]
+        pvc = Chip("PublicValues", "PublicValues", M(pv_main), preprocessed=M(pv_prep))
+        pvc.canon = (pv_prep, pv_main)
+        pvc.pv_digest = consts[d_addr].copy()
+        extra.append(pvc)
     mem_prep[:n_const, 0], mem_prep[:n_const, 4], mem_prep[:n_const, 5] = consts, np.arange(n_const), reads
     names = names or ("MemoryConst", "BaseAlu", f"Poseidon2WideDeg{degree}")
     mem = Chip(names[0], "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
