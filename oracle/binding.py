@@ -127,6 +127,9 @@ def ref():
             R.ref_poseidon2_wide_event_to_row.argtypes = [_u32p, _u32p, C.c_int]
             R.ref_poseidon2_wide_instr_to_row.argtypes = [_u32p, _u32p]
             R.ref_add_sub_event_to_row.argtypes = [_u32p, _u32p]
+        if hasattr(R, "ref_poseidon2_skinny_event_to_rows"):
+            R.ref_poseidon2_skinny_event_to_rows.argtypes = [_u32p, _u32p]
+            R.ref_poseidon2_skinny_instr_to_row.argtypes = [_u32p, C.c_uint64, _u32p]
         _ref = R
     return _ref
 

@@ -4,6 +4,7 @@
 // includes
 //   crates/core/machine/include/kb31_t.hpp            (field class, host branch :458-623)
 //   crates/recursion/core/include/poseidon2_wide.hpp   (populate_perm :96-146)
+//   crates/recursion/core/include/poseidon2_skinny.hpp (event_to_row :50-76, instr_to_row :78-115)
 //   crates/recursion/core/include/poseidon2.hpp        (linear layers :21-71)
 //   crates/recursion/core/include/poseidon2_constants.hpp
 // through a shim for the cbindgen-generated header they expect (written by the Makefile; it carries
@@ -11,6 +12,7 @@
 // chips/poseidon2_skinny/trace.rs:47).
 #include "kb31_t.hpp"
 #include "poseidon2_wide.hpp"
+#include "poseidon2_skinny.hpp"
 #include <cstdint>
 
 using namespace zkm_recursion_core_sys;
@@ -48,5 +50,24 @@ void ref_poseidon2_wide_instr_to_row(const uint32_t instr[48], uint32_t cols[49]
   static_assert(sizeof(Poseidon2SkinnyInstr<kb31_t>) == 48 * 4 && sizeof(Poseidon2PreprocessedColsWide<kb31_t>) == 49 * 4);
   poseidon2_wide::instr_to_row<kb31_t>(*reinterpret_cast<const Poseidon2SkinnyInstr<kb31_t>*>(instr),
                                        *reinterpret_cast<Poseidon2PreprocessedColsWide<kb31_t>*>(cols));
+}
+}
+
+// ---- Poseidon2SkinnyChip fillers (crates/recursion/core/src/sys.rs binds poseidon2_skinny_event_to_row_koalabear /
+// poseidon2_skinny_instr_to_row_koalabear) -----------------------------------------------------------------------------
+extern "C" {
+// poseidon2_skinny::event_to_row (poseidon2_skinny.hpp:50-76): the ELEVEN main-trace rows (28 words each) of one
+// permutation from its 16-word input.
+void ref_poseidon2_skinny_event_to_rows(const uint32_t input[16], uint32_t rows[11 * 28]) {
+  static_assert(sizeof(Poseidon2<kb31_t>) == 28 * 4 && OUTPUT_ROUND_IDX + 1 == 11);
+  Poseidon2Event<kb31_t> ev{};
+  for (size_t i = 0; i < WIDTH; i++) ev.input[i] = kb31_t(input[i]);
+  poseidon2_skinny::event_to_row<kb31_t>(ev, reinterpret_cast<Poseidon2<kb31_t>*>(rows));
+}
+// poseidon2_skinny::instr_to_row (poseidon2_skinny.hpp:78-115): preprocessed row i (51 words) of an instruction.
+void ref_poseidon2_skinny_instr_to_row(const uint32_t instr[48], uint64_t i, uint32_t cols[51]) {
+  static_assert(sizeof(Poseidon2PreprocessedColsSkinny<kb31_t>) == 51 * 4);
+  poseidon2_skinny::instr_to_row<kb31_t>(*reinterpret_cast<const Poseidon2Instr<kb31_t>*>(instr), i,
+                                         *reinterpret_cast<Poseidon2PreprocessedColsSkinny<kb31_t>*>(cols));
 }
 }

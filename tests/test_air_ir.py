@@ -18,7 +18,7 @@ def test_exported_json_reproduces_the_generated_kernels():
     for make in (library.add_sub, library.lt, library.bitwise, lambda: library.poseidon2_wide(3),
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
-                 library.public_values_chip):
+                 library.public_values_chip, library.fri_fold, library.poseidon2_skinny):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -148,6 +148,29 @@ def test_compress_machine_chips_satisfy_their_airs():
         bad = chip.canon[1].copy()
         bad[cell] = (bad[cell] + 1) % ae_P
         assert any(v.any() for v in _constraints_on_trace(air, bad, chip.canon[0], pvs=pvs)[:shape[4]]), air.name
+    # FriFold (33 + 20 columns, nine signed-multiplicity sends, dummy + 17 constraints): the tenth chip of
+    # machine_wide_with_all_chips (machine.rs:68-87), on its own toy program
+    mem, var, ff = synth.fri_fold_program_chips()
+    air = library.fri_fold(3)
+    assert (air.main_width, air.prep_width, len(air.sends), len(air.receives), air.num_constraints) == (33, 20, 9, 0, 18 + 5 + 3)
+    assert all(not v.any() for v in _constraints_on_trace(air, ff.canon[1], ff.canon[0]))
+    bad = ff.canon[1].copy()
+    bad[1, 30] = (bad[1, 30] + 1) % ae_P                               # ro_output
+    assert any(v.any() for v in _constraints_on_trace(air, bad, ff.canon[0])[:18])
+    for chip, a in ((mem, library.memory_const()), (var, library.memory_var())):
+        assert all(not v.any() for v in _constraints_on_trace(a, chip.canon[1], chip.canon[0]))
+    # Poseidon2SkinnyDeg9, the Poseidon2 chip of the wrap machine (machine.rs:138-153): 28 + 51 columns, eleven rows per
+    # permutation tied by next-row constraints, dummy + 60 constraints of degree <= 9, LogUp batches of 8; its rows are
+    # pinned against the reference's poseidon2_skinny.hpp in tests/test_tracegen.py
+    mem, sk = synth.skinny_program_chips()
+    air = library.poseidon2_skinny(9)
+    assert (air.main_width, air.prep_width, len(air.sends), len(air.receives)) == (28, 51, 16, 0)
+    assert air.num_constraints == 61 + 2 + 3 and air.max_degree() == 9 and air.perm_width == 3 and not air.local_only
+    assert all(not v.any() for v in _constraints_on_trace(air, sk.canon[1], sk.canon[0]))
+    for cell in ((5, 20), (3, 7), (0, 2)):                              # an s0 column, an external round, the input row
+        bad = sk.canon[1].copy()
+        bad[cell] = (bad[cell] + 1) % ae_P
+        assert any(v.any() for v in _constraints_on_trace(air, bad, sk.canon[0])[:61]), cell
     # the six older chips are unchanged by the additions (the accumulators / results only replace operands)
     for chip, air in ((chips[0], library.memory_const()), (chips[1], library.base_alu()), (chips[4], library.memory_var()),
                       (chips[5], library.ext_alu())):

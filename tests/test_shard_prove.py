@@ -40,7 +40,7 @@ COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=T
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -65,7 +65,9 @@ def test_quotient_values_match_oracle(be, which):
             # PublicValues the shard's 231 public values
             "BatchFRI": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[6],
             "ExpReverseBitsLen": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[7],
-            "PublicValues": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[8]}[which]()
+            "PublicValues": lambda: synth.recursion_program_chips(5, 4, 5, **COMPRESS_SMALL)[8],
+            "FriFold": lambda: synth.fri_fold_program_chips()[2],
+            "Poseidon2SkinnyDeg9": lambda: synth.skinny_program_chips(5)[1]}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
@@ -365,6 +367,53 @@ def test_compress_machine_shard_verifies_completely(be):
     sp2 = prover.open(pk, prover.commit(chips, bad_pvs), _machine_challenger(ctx, pk))
     ok, why = su.machine_verify(su.vk_of(pk), _machine(host), [sp2], npv, 1, nq, pw)
     assert not ok, "a wrong digest must violate PublicValues' constraint"
+    data.free()
+    pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_fri_fold_program_shard_verifies_completely(be):
+    """FriFold, the chip machine_wide_with_all_chips has beyond the compress machine (machine.rs:68-87), on a toy program
+    with MemoryConst and MemoryVar: balanced bus, complete verification, byte-identical with the CPU prover."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    chips = synth.fri_fold_program_chips() if be == "emu" else synth.fri_fold_program_chips(14, 17, 13)
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 1, nq, pw)
+    assert ok, why
+    assert not sp.local_cumulative_sum().any()
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=NUM_PV)
+    opk = op.setup(chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))) == pf.to_bincode(sp)
+    data.free()
+    pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_poseidon2_skinny_program_shard_verifies_completely(be):
+    """Poseidon2SkinnyDeg9 -- the wrap machine's Poseidon2 chip (machine.rs:138-153), log_quotient_degree 3, eleven rows
+    per permutation -- with MemoryConst (log_quotient_degree 1) in one shard: balanced bus, complete verification,
+    byte-identical with the CPU prover."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    chips = synth.skinny_program_chips() if be == "emu" else synth.skinny_program_chips(15, 11)
+    prover, pk, data, sp = _prove(ctx, chips, 3, nq, pw)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 3, nq, pw)
+    assert ok, why
+    assert not sp.local_cumulative_sum().any()
+    op = osp.OracleShardProver(su.AIRS, 3, nq, pw, num_pv_elts=NUM_PV)
+    opk = op.setup(chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))) == pf.to_bincode(sp)
     data.free()
     pk.data.free()
 

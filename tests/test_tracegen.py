@@ -62,6 +62,30 @@ def test_oracle_poseidon2_wide_prep_matches_reference_cpp():
     assert not got[11:].any()
 
 
+def test_poseidon2_skinny_rows_match_reference_cpp():
+    """The numpy filler of Poseidon2SkinnyChip (synth.poseidon2_skinny_rows / _prep_rows; the transcribed AIR is checked on
+    its rows in tests/test_air_ir.py) against the reference's own poseidon2_skinny.hpp event_to_row / instr_to_row:
+    eleven 28-word main rows per permutation, eleven 51-word preprocessed rows per instruction."""
+    R = ob.ref()
+    if R is None or not hasattr(R, "ref_poseidon2_skinny_event_to_rows"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    x = _inputs(5)
+    got = to_monty(synth.poseidon2_skinny_rows(ob.from_monty(x), 64))
+    for k in range(5):
+        rows = np.zeros((11, 28), np.uint32)
+        R.ref_poseidon2_skinny_event_to_rows(ob._ptr(np.ascontiguousarray(x[k])), ob._ptr(rows))
+        assert np.array_equal(rows, got[11 * k:11 * k + 11]), k
+        assert np.array_equal(rows[10, :16], ob.permute(x[k]))
+    assert not got[55:].any()
+    ins = ob.from_monty(_instrs(5)).astype(np.uint64)
+    prep = to_monty(synth.poseidon2_skinny_prep_rows(ins[:, 0:16], ins[:, 16:32], ins[:, 32:48], 64))
+    for k in range(5):
+        for i in range(11):
+            row = np.zeros(51, np.uint32)
+            R.ref_poseidon2_skinny_instr_to_row(ob._ptr(np.ascontiguousarray(to_monty(ins[k]))), i, ob._ptr(row))
+            assert np.array_equal(row, prep[11 * k + i]), (k, i)
+
+
 def test_oracle_add_sub_rows_match_reference_cpp_and_numpy():
     ev, n = synth.add_sub_events(7)
     got = ob.add_sub_trace(ev, n)

@@ -586,6 +586,94 @@ def exp_reverse_bits_len(degree=3):
     return air
 
 
+def fri_fold(degree=3):
+    """FriFoldChip<DEGREE> (crates/recursion/core/src/chips/fri_fold.rs:45-83 columns, :371-462 eval; a chip of
+    machine_wide_with_all_chips, machine.rs:68-87): one row per opened polynomial of a FRI-fold instruction.
+    Main (33): z[4], alpha[4], x, p_at_x[4], p_at_z[4], alpha_pow_input[4], ro_input[4], alpha_pow_output[4],
+    ro_output[4]; preprocessed (20): is_first, then {addr, mult} of z, alpha, x, alpha_pow_input, ro_input, p_at_x,
+    p_at_z, ro_output, alpha_pow_output, then is_real.  Every access is a send with a signed multiplicity."""
+    air = Air("FriFold", main_width=33, prep_width=20)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    p, pn = b.preprocessed().local(), b.preprocessed().next()
+    z, alpha, x = m[0:4], m[4:8], m[8]
+    p_at_x, p_at_z, ap_in, ro_in, ap_out, ro_out = m[9:13], m[13:17], m[17:21], m[21:25], m[25:29], m[29:33]
+    (z_a, z_m), (al_a, al_m), (x_a, x_m), (api_a, api_m), (roi_a, roi_m), (px_a, px_m), (pz_a, pz_m), (roo_a, roo_m), \
+        (apo_a, apo_m) = [(p[1 + 2 * k], p[2 + 2 * k]) for k in range(9)]
+    is_real = p[19]
+    n_is_first, n_is_real = pn[0], pn[19]
+    lhs = is_real                                                      # :484-486 dummy constraint of degree DEGREE
+    for _ in range(degree - 1):
+        lhs = lhs * is_real
+    b.assert_eq(lhs, lhs)
+    same = lambda: b.when_transition().when(n_is_real).when_not(n_is_first)
+    b.send(LOOKUP_MEMORY, [x_a, x, 0, 0, 0], x_m)                      # :380
+    same().assert_eq(x, mn[8])                                         # :383-387
+    b.send(LOOKUP_MEMORY, [z_a] + list(z), z_m)                        # :390
+    for l, r in zip(z, mn[0:4]):                                       # :393-397
+        same().assert_eq(l, r)
+    b.send(LOOKUP_MEMORY, [al_a] + list(alpha), al_m)                  # :400
+    for l, r in zip(alpha, mn[4:8]):                                   # :403-407
+        same().assert_eq(l, r)
+    b.send(LOOKUP_MEMORY, [api_a] + list(ap_in), api_m)                # :410-441 vector inputs, then outputs
+    b.send(LOOKUP_MEMORY, [roi_a] + list(ro_in), roi_m)
+    b.send(LOOKUP_MEMORY, [pz_a] + list(p_at_z), pz_m)
+    b.send(LOOKUP_MEMORY, [px_a] + list(p_at_x), px_m)
+    b.send(LOOKUP_MEMORY, [apo_a] + list(ap_out), apo_m)
+    b.send(LOOKUP_MEMORY, [roo_a] + list(ro_out), roo_m)
+    for l, r in zip(_ext_mul(ap_in, alpha), ap_out):                   # :447 new_alpha_pow = old_alpha_pow * alpha
+        b.assert_eq(l, r)
+    # :458-461 (new_ro - old_ro) * (x - z) = (p_at_x - p_at_z) * old_alpha_pow
+    d_ro = [n - o for n, o in zip(ro_out, ro_in)]
+    x_minus_z = [x - z[0], 0 - z[1], 0 - z[2], 0 - z[3]]
+    d_p = [a - c for a, c in zip(p_at_x, p_at_z)]
+    for l, r in zip(_ext_mul(d_ro, x_minus_z), _ext_mul(d_p, ap_in)):
+        b.assert_eq(l, r)
+    b.eval_permutation_constraints(batch_size=2 if degree == 3 else 8)
+    return air
+
+
+def poseidon2_skinny(degree=9):
+    """Poseidon2SkinnyChip<DEGREE> (crates/recursion/core/src/chips/poseidon2_skinny/air.rs:25-163; columns/mod.rs:20-26,
+    columns/preprocessed.rs:5-19; the Poseidon2 chip of the wrap machine, machine.rs:138-153): ELEVEN rows per
+    permutation -- input row (memory reads), four external rounds, one row holding all 13 internal rounds, four
+    external rounds, output row (memory writes) -- tied together by next-row constraints selected by preprocessed round
+    flags.  Main (28): state_var[16], internal_rounds_s0[12]; preprocessed (51): 16 x {addr, mult}, is_input_round,
+    is_external_round, is_internal_round, round_constants[16].  DEGREE >= 9 only (S-boxes are not materialised)."""
+    assert degree >= 9
+    air = Air(f"Poseidon2SkinnyDeg{degree}", main_width=28, prep_width=51)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    p = b.preprocessed().local()
+    state, s0, nxt = list(m[0:16]), m[16:28], mn[0:16]
+    mem = [(p[2 * i], p[2 * i + 1]) for i in range(16)]
+    is_input, is_external, is_internal, rc = p[32], p[33], p[34], p[35:51]
+    lhs = state[0]                                                     # air.rs:43-45
+    for _ in range(degree - 1):
+        lhs = lhs * state[0]
+    b.assert_eq(lhs, lhs)
+    for i in range(16):                                                # air.rs:48-54
+        b.send(LOOKUP_MEMORY, [mem[i][0], state[i], 0, 0, 0], mem[i][1])
+    lin = _external_linear_layer(state)                                # eval_input_round, air.rs:71-91
+    for i in range(16):
+        b.when_transition().when(is_input).assert_eq(nxt[i], lin[i])
+    add_rc = [state[i] + rc[i] for i in range(16)]                     # eval_external_round, air.rs:93-127
+    lin = _external_linear_layer([x * x * x for x in add_rc])
+    for i in range(16):
+        b.when_transition().when(is_external).assert_eq(nxt[i], lin[i])
+    st = list(state)                                                   # eval_internal_rounds, air.rs:129-162
+    for r in range(13):
+        x = (st[0] if r == 0 else s0[r - 1]) + rc[r]
+        st[0] = x * x * x
+        st = _internal_linear_layer(st)
+        if r < 12:
+            b.when(is_internal).assert_eq(s0[r], st[0])
+    for i in range(16):
+        b.when(is_internal).assert_eq(nxt[i], st[i])
+    b.eval_permutation_constraints(batch_size=8)
+    return air
+
+
 RECURSIVE_PROOF_NUM_PV_ELTS = 231    # size_of::<RecursionPublicValues<u8>>() = PROOF_MAX_NUM_PVS (stark/src/types.rs:73)
 RECURSION_PV_DIGEST = 223            # RECURSION_PUBLIC_VALUES_COL_MAP.digest[0] (recursion/core/src/air/public_values.rs:79-145)
 
@@ -612,4 +700,4 @@ def all_airs():
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip()]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9)]

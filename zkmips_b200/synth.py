@@ -595,3 +595,166 @@ def recursion_program_chips(log_p2=6, log_alu=5, log_mem=6, degree=3, seed=41, f
               local_only=True, log_quotient_degree=1 if degree == 3 else 3, events=p2_inputs, tracegen=air,
               rows=1 << log_p2)
     return [mem, alu, p2] + extra
+
+
+def fri_fold_program_chips(log_ff=5, log_var=8, log_mem=5, seed=43, fill=0.75):
+    """(MemoryConst, MemoryVar, FriFold): a toy program of FriFold instructions (crates/recursion/core/src/chips/
+    fri_fold.rs:117-184 preprocessed, :245-275 main) of up to three rows each with a balanced memory bus.  x comes from
+    the constants and z, alpha (read on the instruction's first row) and the four vector inputs of every row from
+    MemoryVar; the outputs are written with multiplicity 0.  ro_output = ro_input + alpha_pow_input * q with
+    p_at_x = p_at_z + q * (x - z), so no extension inversion is needed to build a valid row."""
+    rng = np.random.default_rng(seed)
+    rows = 1 << log_ff
+    n = max(1, int(rows * fill))
+    instr = np.arange(n) // 3
+    first = np.arange(n) % 3 == 0
+    n_i = int(instr[-1]) + 1
+    n_const = n_i
+    consts = rng.integers(1, P, n_const, dtype=np.uint64)
+    ext = lambda k: rng.integers(0, P, (k, 4), dtype=np.uint64)
+
+    def emul(a, c):
+        r = np.zeros_like(a)
+        for i in range(4):
+            for j in range(4):
+                t = a[:, i] * c[:, j] % P
+                r[:, (i + j) % 4] = (r[:, (i + j) % 4] + (3 * t if i + j >= 4 else t)) % P
+        return r
+    z_i, alpha_i = ext(n_i), ext(n_i)
+    z, alpha, x = z_i[instr], alpha_i[instr], consts[instr]
+    ap_in, ro_in, p_at_z, q = ext(n), ext(n), ext(n), ext(n)
+    x_minus_z = (P - z) % P
+    x_minus_z[:, 0] = (x + P - z[:, 0]) % P
+    p_at_x = (p_at_z + emul(q, x_minus_z)) % P
+    ap_out = emul(ap_in, alpha)
+    ro_out = (ro_in + emul(ap_in, q)) % P
+    main = np.zeros((rows, 33), np.uint64)
+    main[:n] = np.concatenate([z, alpha, x[:, None], p_at_x, p_at_z, ap_in, ro_in, ap_out, ro_out], axis=1)
+    # MemoryVar entries: z and alpha per instruction, then (alpha_pow_input, ro_input, p_at_x, p_at_z) per row
+    var_vals = np.concatenate([z_i, alpha_i, ap_in, ro_in, p_at_x, p_at_z])
+    n_var = len(var_vals)
+    rows_v = 1 << log_var
+    assert n_var <= 2 * rows_v, "MemoryVar too short for the FriFold operands"
+    base = 1 << 24
+    a_z, a_alpha = base + np.arange(n_i), base + n_i + np.arange(n_i)
+    a_vec = base + 2 * n_i + np.arange(4 * n).reshape(4, n)
+    neg1 = P - 1
+    prep = np.zeros((rows, 20), np.uint64)
+    prep[:n, 0] = first
+    prep[:n, 1], prep[:n, 2] = a_z[instr], np.where(first, neg1, 0)
+    prep[:n, 3], prep[:n, 4] = a_alpha[instr], np.where(first, neg1, 0)
+    prep[:n, 5], prep[:n, 6] = instr, np.where(first, neg1, 0)          # x: constant number `instr`
+    for k in range(4):                                                  # alpha_pow_input, ro_input, p_at_x, p_at_z
+        prep[:n, 7 + 2 * k], prep[:n, 8 + 2 * k] = a_vec[k], neg1
+    prep[:n, 15], prep[:n, 17] = (1 << 26) + np.arange(n), (1 << 27) + np.arange(n)   # outputs, multiplicity 0
+    prep[:n, 19] = 1
+    var_main = np.zeros((2 * rows_v, 4), np.uint64)
+    var_main[:n_var] = var_vals
+    var_prep = np.zeros((2 * rows_v, 2), np.uint64)
+    var_prep[:n_var, 0], var_prep[:n_var, 1] = base + np.arange(n_var), 1
+    mem_rows = 1 << log_mem
+    assert n_const <= 2 * mem_rows
+    mem_prep = np.zeros((2 * mem_rows, 6), np.uint64)
+    mem_prep[:n_const, 0], mem_prep[:n_const, 4], mem_prep[:n_const, 5] = consts, np.arange(n_const), 1
+    mem = Chip("MemoryConst", "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
+               local_only=True)
+    mem.canon = (mem_prep.reshape(mem_rows, 12), np.zeros((mem_rows, 1), np.uint64))
+    var = Chip("MemoryVar", "MemoryVar", M(var_main.reshape(rows_v, 8)), preprocessed=M(var_prep.reshape(rows_v, 4)),
+               local_only=True)
+    var.canon = (var_prep.reshape(rows_v, 4), var_main.reshape(rows_v, 8))
+    ff = Chip("FriFold", "FriFold", M(main), preprocessed=M(prep))
+    ff.canon = (prep, main)
+    return [mem, var, ff]
+
+
+class _Fp:
+    """numpy uint64 vectors mod P with + and * only, so that library._external_linear_layer / _internal_linear_layer
+    (written for constraint expressions) also run on values"""
+
+    def __init__(self, v):
+        self.v = np.asarray(v, np.uint64) % np.uint64(P)
+
+    def __add__(self, o):
+        return _Fp((self.v + (o.v if isinstance(o, _Fp) else np.uint64(int(o) % P))) % np.uint64(P))
+
+    __radd__ = __add__
+
+    def __mul__(self, o):
+        return _Fp(self.v * (o.v if isinstance(o, _Fp) else np.uint64(int(o) % P)) % np.uint64(P))
+
+    __rmul__ = __mul__
+
+
+def poseidon2_skinny_rows(inputs, n):
+    """Poseidon2SkinnyChip::generate_trace (chips/poseidon2_skinny/trace.rs:77-130, populate_* :326-400), canonical
+    values: 11 rows per permutation -- input, 4 external rounds, the internal-rounds row, 4 external rounds, output."""
+    from .air import library as L
+    ext_rc, int_rc = L._poseidon2_round_constants()
+    inputs = np.asarray(inputs, np.uint64)
+    k = len(inputs)
+    assert 11 * k <= n
+    t = np.zeros((n, 28), np.uint64)
+    rows = np.arange(k) * 11
+    st = [_Fp(inputs[:, i]) for i in range(16)]
+    put = lambda i, s: t.__setitem__((rows + i, slice(0, 16)), np.stack([x.v for x in s], axis=1))
+    put(0, st)
+    st = L._external_linear_layer(st)
+    for i in range(1, 10):
+        put(i, st)
+        if i != 5:
+            r = i - 1 if i < 5 else i - 2
+            st = L._external_linear_layer([(x + ext_rc[r][j]) * (x + ext_rc[r][j]) * (x + ext_rc[r][j]) for j, x in enumerate(st)])
+        else:
+            for r in range(13):
+                x = st[0] + int_rc[r]
+                st[0] = x * x * x
+                st = L._internal_linear_layer(st)
+                if r < 12:
+                    t[rows + 5, 16 + r] = st[0].v
+    put(10, st)
+    return t
+
+
+def poseidon2_skinny_prep_rows(in_addrs, out_addrs, out_mults, n):
+    """generate_preprocessed_trace (trace.rs:184-251), canonical: memory accesses on the input (mult -1) and output rows,
+    round flags, and the round constants each row's constraints use (external: RC[round][0..16]; internal row:
+    RC[4 + j][0] for j < 16, i.e. the 13 internal constants followed by column 0 of external rows 17..19)"""
+    from .air import library as L
+    ext_rc, int_rc = L._poseidon2_round_constants()
+    k = len(in_addrs)
+    t = np.zeros((n, 51), np.uint64)
+    rows = np.arange(k) * 11
+    t[rows, 0:32:2], t[rows, 1:32:2] = in_addrs, P - 1
+    t[rows + 10, 0:32:2], t[rows + 10, 1:32:2] = out_addrs, out_mults
+    t[rows, 32] = 1
+    for i in (1, 2, 3, 4, 6, 7, 8, 9):
+        t[rows + i, 33] = 1
+        t[rows + i, 35:51] = ext_rc[i - 1 if i < 5 else i - 2]
+    t[rows + 5, 34] = 1
+    t[rows + 5, 35:51] = list(int_rc) + [ext_rc[4][0], ext_rc[5][0], ext_rc[6][0]]
+    return t
+
+
+def skinny_program_chips(log_sk=6, log_mem=4, seed=47):
+    """(MemoryConst, Poseidon2SkinnyDeg9): permutation k reads constants k .. k + 15 and writes its outputs to fresh
+    addresses nobody reads; as many permutations as fit (11 rows each)."""
+    rng = np.random.default_rng(seed)
+    n = 1 << log_sk
+    k = max(1, (n * 3 // 4) // 11)
+    n_const = k + 15
+    consts = rng.integers(0, P, n_const, dtype=np.uint64)
+    win = np.arange(k)[:, None] + np.arange(16)[None, :]
+    reads = np.zeros(n_const, np.uint64)
+    np.add.at(reads, win.ravel(), 1)
+    main = poseidon2_skinny_rows(consts[win], n)
+    prep = poseidon2_skinny_prep_rows(win, (1 << 22) + 16 * np.arange(k)[:, None] + np.arange(16)[None, :], 0, n)
+    mem_rows = 1 << log_mem
+    assert n_const <= 2 * mem_rows
+    mem_prep = np.zeros((2 * mem_rows, 6), np.uint64)
+    mem_prep[:n_const, 0], mem_prep[:n_const, 4], mem_prep[:n_const, 5] = consts, np.arange(n_const), reads
+    mem = Chip("MemoryConst", "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
+               local_only=True)
+    mem.canon = (mem_prep.reshape(mem_rows, 12), np.zeros((mem_rows, 1), np.uint64))
+    sk = Chip("Poseidon2SkinnyDeg9", "Poseidon2SkinnyDeg9", M(main), preprocessed=M(prep), log_quotient_degree=3)
+    sk.canon = (prep, main)
+    return [mem, sk]
