@@ -209,6 +209,16 @@ int32_t zk_tracegen_poseidon2_wide_dev(zk_ctx* ctx, zk_dptr inputs_dev, uint64_t
  * rows x 49 (Poseidon2PreprocessedColsWide); padding rows are zero */
 int32_t zk_tracegen_poseidon2_wide_prep(zk_ctx* ctx, const uint32_t* instrs_host, uint64_t n, uint64_t rows,
                                         zk_dptr* out_trace);
+/* Poseidon2SkinnyChip<DEGREE> (the wrap machine's Poseidon2 chip; crates/recursion/core/src/sys.rs binds
+ * poseidon2_skinny_event_to_row_koalabear / poseidon2_skinny_instr_to_row_koalabear -> include/poseidon2_skinny.hpp:50-115):
+ * ELEVEN rows of 28 (main) / 51 (preprocessed) words per permutation, rows = power of two >= 11 * n_events, zero padding. */
+uint32_t zk_tracegen_poseidon2_skinny_width(void);
+int32_t zk_tracegen_poseidon2_skinny(zk_ctx* ctx, const uint32_t* inputs_host, uint64_t n_events, uint64_t rows,
+                                     zk_dptr* out_trace);
+int32_t zk_tracegen_poseidon2_skinny_dev(zk_ctx* ctx, zk_dptr inputs_dev, uint64_t n_events, uint64_t rows,
+                                         zk_dptr* out_trace);
+int32_t zk_tracegen_poseidon2_skinny_prep(zk_ctx* ctx, const uint32_t* instrs_host, uint64_t n, uint64_t rows,
+                                          zk_dptr* out_trace);
 
 /* ---- DuplexChallenger<Val, Perm, 16, 8> (crates/stark/src/kb31_poseidon2.rs:180; semantics restated at
  *      crates/recursion/circuit/src/challenger.rs:90-233) ------------------------------------------------

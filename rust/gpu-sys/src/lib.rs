@@ -124,6 +124,10 @@ extern "C-unwind" {
     pub fn zk_tracegen_poseidon2_wide(ctx: *mut ZkCtx, inputs_host: *const u32, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_tracegen_poseidon2_wide_dev(ctx: *mut ZkCtx, inputs_dev: ZkDptr, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_tracegen_poseidon2_wide_prep(ctx: *mut ZkCtx, instrs_host: *const u32, n: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_skinny_width() -> u32;
+    pub fn zk_tracegen_poseidon2_skinny(ctx: *mut ZkCtx, inputs_host: *const u32, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_skinny_dev(ctx: *mut ZkCtx, inputs_dev: ZkDptr, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_poseidon2_skinny_prep(ctx: *mut ZkCtx, instrs_host: *const u32, n: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_challenger_init(ch: *mut ZkChallenger) -> i32;
     pub fn zk_challenger_observe(ctx: *mut ZkCtx, ch: *mut ZkChallenger, vals: *const u32, n: u32) -> i32;
     pub fn zk_challenger_sample_ext(ctx: *mut ZkCtx, ch: *mut ZkChallenger, n_ext: u32, out: *mut u32) -> i32;

@@ -398,14 +398,19 @@ def test_fri_fold_program_shard_verifies_completely(be):
 def test_poseidon2_skinny_program_shard_verifies_completely(be):
     """Poseidon2SkinnyDeg9 -- the wrap machine's Poseidon2 chip (machine.rs:138-153), log_quotient_degree 3, eleven rows
     per permutation -- with MemoryConst (log_quotient_degree 1) in one shard: balanced bus, complete verification,
-    byte-identical with the CPU prover."""
+    byte-identical with the CPU prover.  The prover gets the permutation INPUTS and fills the rows on the device
+    (zk_tracegen_poseidon2_skinny); the verifier and the CPU prover get the rows of the numpy filler, which is pinned
+    against the reference's poseidon2_skinny.hpp (tests/test_tracegen.py)."""
     from oracle import binding_fri as bf
     from oracle import shard_prover as osp
     from zkmips_b200 import proof as pf
     ctx = _backend(be)
     nq, pw = (6, 4) if be == "emu" else (84, 16)
-    chips = synth.skinny_program_chips() if be == "emu" else synth.skinny_program_chips(15, 11)
-    prover, pk, data, sp = _prove(ctx, chips, 3, nq, pw)
+    size = () if be == "emu" else (15, 11)
+    chips = synth.skinny_program_chips(*size)
+    dev_chips = synth.skinny_program_chips(*size, device=True)
+    assert dev_chips[1].main is None and dev_chips[1].events.shape[1] == 16
+    prover, pk, data, sp = _prove(ctx, dev_chips, 3, nq, pw)
     ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 3, nq, pw)
     assert ok, why
     assert not sp.local_cumulative_sum().any()

@@ -126,6 +126,21 @@ def _check_prep(ctx, n, rows):
     assert np.array_equal(got, ob.poseidon2_wide_prep(ins, rows))
 
 
+def _check_poseidon2_skinny(ctx, n_events, rows):
+    """device filler against the numpy filler, which is pinned against the reference's poseidon2_skinny.hpp above"""
+    x = _inputs(n_events, seed=rows + n_events)
+    dptr, w = ctx.tracegen_poseidon2_skinny(x, rows)
+    got = ctx.download(dptr, (rows, w))
+    ctx.dev_free(dptr)
+    assert w == 28 and np.array_equal(got, to_monty(synth.poseidon2_skinny_rows(ob.from_monty(x), rows)))
+    ins = _instrs(n_events, seed=3 + n_events)
+    dptr, w = ctx.tracegen_poseidon2_skinny_prep(ins, rows)
+    got = ctx.download(dptr, (rows, w))
+    ctx.dev_free(dptr)
+    c = ob.from_monty(ins).astype(np.uint64)
+    assert w == 51 and np.array_equal(got, to_monty(synth.poseidon2_skinny_prep_rows(c[:, 0:16], c[:, 16:32], c[:, 32:48], rows)))
+
+
 def test_tracegen_emu():
     """kernel index math on the CPU emulator (test-only build of the same sources)"""
     ctx = backends.emu()
@@ -134,6 +149,8 @@ def test_tracegen_emu():
     for chip in ("AddSub", "Bitwise", "Lt"):
         _check_alu(ctx, chip, 8, 0.7)
     _check_prep(ctx, 5, 8)
+    _check_poseidon2_skinny(ctx, 40, 512)      # two CTAs, the second one partial and partly padding
+    _check_poseidon2_skinny(ctx, 1, 16)
 
 
 @pytest.mark.gpu
@@ -141,6 +158,12 @@ def test_tracegen_emu():
 @pytest.mark.parametrize("n_events,rows", [(0, 1), (1, 1), (5, 8), (127, 128), (129, 256), (40000, 1 << 16), (1 << 14, 1 << 14)])
 def test_tracegen_poseidon2_wide_gpu(n_events, rows, sbox):
     _check_poseidon2_wide(backends.gpu(), n_events, rows, sbox)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_events,rows", [(0, 1), (1, 16), (2, 32), (32, 512), (93, 1024), (5957, 1 << 16), (23000, 1 << 18)])
+def test_tracegen_poseidon2_skinny_gpu(n_events, rows):
+    _check_poseidon2_skinny(backends.gpu(), n_events, rows)
 
 
 @pytest.mark.gpu

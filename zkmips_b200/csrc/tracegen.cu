@@ -41,6 +41,29 @@ int32_t poseidon2_wide(zk_ctx* c, const uint32_t* host, zk_dptr dev, uint64_t n_
   return ZK_OK;
 }
 
+int32_t poseidon2_skinny(zk_ctx* c, const uint32_t* host, zk_dptr dev, uint64_t n_events, uint64_t rows, zk_dptr* out_trace) {
+  if (!c || !out_trace || (n_events && !host && !dev)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (!pow2(rows) || n_events * tg::P2S_ROWS_PER_EVENT > rows)
+    return zk_fail(ZK_ERR_ARG, "rows must be a power of two >= 11 * n_events");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  ProfScope ps(c, "tracegen");
+  DevScope scope(c);
+  const uint32_t* ev = nullptr;
+  int32_t rc = stage_events(c, scope, host, dev, n_events * 16, &ev);
+  if (rc) return rc;
+  uint32_t* out = nullptr;
+  if ((rc = scope.alloc(&out, rows * tg::P2S_WIDTH * 4ull))) return rc;
+  const uint64_t per_cta = tg::P2S_EVENTS * tg::P2S_ROWS_PER_EVENT;
+  ZK_LAUNCH_COOP(tg::poseidon2_skinny_rows, (unsigned)((rows + per_cta - 1) / per_cta), tg::P2S_EVENTS, 0, c->stream, ev,
+                 n_events, rows, out);
+  CK(cudaGetLastError());
+  c->launches++;
+  scope.release(out);
+  *out_trace = (zk_dptr)out;
+  return ZK_OK;
+}
+
 template <class CHIP>
 void launch_alu(zk_ctx* c, const uint32_t* ev, uint64_t n_events, uint64_t rows, uint32_t* out) {
   unsigned grid = (unsigned)((rows + tg::ROWS - 1) / tg::ROWS);
@@ -118,6 +141,35 @@ extern "C" int32_t zk_tracegen_poseidon2_wide_prep(zk_ctx* c, const uint32_t* in
   uint32_t* out = nullptr;
   if ((rc = scope.alloc(&out, rows * 49 * 4ull))) return rc;
   ZK_LAUNCH(tg::poseidon2_wide_prep_rows, (unsigned)((rows * 49 + 255) / 256), 256, 0, c->stream, in, n, rows, out);
+  CK(cudaGetLastError());
+  c->launches++;
+  scope.release(out);
+  *out_trace = (zk_dptr)out;
+  return ZK_OK;
+}
+extern "C" uint32_t zk_tracegen_poseidon2_skinny_width(void) { return tg::P2S_WIDTH; }
+extern "C" int32_t zk_tracegen_poseidon2_skinny(zk_ctx* c, const uint32_t* inputs_host, uint64_t n_events, uint64_t rows,
+                                                zk_dptr* out_trace) {
+  return poseidon2_skinny(c, inputs_host, 0, n_events, rows, out_trace);
+}
+extern "C" int32_t zk_tracegen_poseidon2_skinny_dev(zk_ctx* c, zk_dptr inputs_dev, uint64_t n_events, uint64_t rows,
+                                                    zk_dptr* out_trace) {
+  return poseidon2_skinny(c, nullptr, inputs_dev, n_events, rows, out_trace);
+}
+extern "C" int32_t zk_tracegen_poseidon2_skinny_prep(zk_ctx* c, const uint32_t* instrs_host, uint64_t n, uint64_t rows,
+                                                     zk_dptr* out_trace) {
+  if (!c || !out_trace || (n && !instrs_host)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (!pow2(rows) || n * 11 > rows) return zk_fail(ZK_ERR_ARG, "rows must be a power of two >= 11 * n");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  ProfScope ps(c, "tracegen");
+  DevScope scope(c);
+  const uint32_t* in = nullptr;
+  int32_t rc = stage_events(c, scope, instrs_host, 0, n * 48, &in);
+  if (rc) return rc;
+  uint32_t* out = nullptr;
+  if ((rc = scope.alloc(&out, rows * 51 * 4ull))) return rc;
+  ZK_LAUNCH(tg::poseidon2_skinny_prep_rows, (unsigned)((rows * 51 + 255) / 256), 256, 0, c->stream, in, n, rows, out);
   CK(cudaGetLastError());
   c->launches++;
   scope.release(out);

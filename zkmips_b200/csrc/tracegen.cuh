@@ -112,6 +112,103 @@ __global__ void poseidon2_wide_prep_rows(const uint32_t* __restrict__ instrs, ui
   out[i] = v;
 }
 
+// ---- Poseidon2SkinnyChip<DEGREE>::generate_trace (crates/recursion/core/src/chips/poseidon2_skinny/trace.rs:77-130; C++
+//      twin poseidon2_skinny.hpp:50-76): ELEVEN rows of 28 words per permutation -- state_var[16] | internal_rounds_s0[12]
+//      (columns/mod.rs:20-26).  Row 0: the input; rows 1..4: the state entering external rounds 0..3; row 5: the state
+//      entering the 13 internal rounds, with s0 of rounds 0..11; rows 6..9: external rounds 4..7; row 10: the output.
+//      Padding rows (>= 11 * n_events) are ZERO (trace.rs:126 `rows.resize(.., [F::ZERO; ..])`), unlike the wide chip.
+//      One warp per CTA, one permutation per lane: the CTA's 32 x 11 rows are one contiguous run of 9856 words, staged in
+//      shared memory (38.5 KB) and written with 128-bit stores like the wide filler above.
+constexpr uint32_t P2S_WIDTH = 28, P2S_ROWS_PER_EVENT = 11, P2S_EVENTS = 32;
+constexpr uint32_t P2S_TILE = P2S_EVENTS * P2S_ROWS_PER_EVENT * P2S_WIDTH;  // words per CTA
+
+__global__ void __launch_bounds__(P2S_EVENTS) poseidon2_skinny_rows(const uint32_t* __restrict__ inputs, uint64_t n_events,
+                                                                    uint64_t rows, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t tile[P2S_TILE];
+  const uint32_t lane = threadIdx.x;
+  const uint64_t ev = (uint64_t)blockIdx.x * P2S_EVENTS + lane;
+  uint32_t* const t = tile + lane * (P2S_ROWS_PER_EVENT * P2S_WIDTH);
+#pragma unroll 4
+  for (uint32_t k = 0; k < P2S_ROWS_PER_EVENT * P2S_WIDTH; k++) t[k] = 0u;
+  if (ev < n_events) {
+    uint32_t s[16];
+    const uint4* in = reinterpret_cast<const uint4*>(inputs + ev * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      uint4 v = in[q];
+      s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+    }
+    auto put = [&](uint32_t row) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) t[row * P2S_WIDTH + i] = s[i];
+    };
+    put(0);
+    p2::external_layer(s);
+    put(1);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) s[i] = p2::sbox(s[i], p2::EXT_RC[r][i]);
+      p2::external_layer(s);
+      if (r == 3) {
+        put(5);
+#pragma unroll 1
+        for (int k = 0; k < 13; k++) {
+          s[0] = p2::sbox(s[0], p2::INT_RC[k]);
+          p2::internal_layer(s);
+          if (k < 12) t[5 * P2S_WIDTH + 16 + k] = s[0];
+        }
+        put(6);
+      } else {
+        put(r < 3 ? r + 2 : r + 3);
+      }
+    }
+  }
+  __syncthreads();
+  const uint64_t row0 = (uint64_t)blockIdx.x * (P2S_EVENTS * P2S_ROWS_PER_EVENT);
+  if (row0 >= rows) return;
+  if (row0 + P2S_EVENTS * P2S_ROWS_PER_EVENT <= rows) {
+    uint4* o = reinterpret_cast<uint4*>(out + row0 * P2S_WIDTH);  // 9856 words per CTA: 16-byte aligned
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+#pragma unroll 4
+    for (uint32_t k = lane; k < P2S_TILE / 4; k += P2S_EVENTS) o[k] = src[k];
+  } else {
+    for (uint64_t k = lane; k < (rows - row0) * P2S_WIDTH; k += P2S_EVENTS) out[row0 * P2S_WIDTH + k] = tile[k];
+  }
+}
+
+// ---- Poseidon2SkinnyChip::generate_preprocessed_trace (trace.rs:184-251; instr_to_row poseidon2_skinny.hpp:78-115): eleven
+//      51-word rows per instruction (input addrs[16], output addrs[16], mults[16]): memory_preprocessed[16] x {addr, mult}
+//      (input row: the input addresses with multiplicity -1; output row: output addresses and their multiplicities), then
+//      is_input_round, is_external_round, is_internal_round, round_constants[16] (external rows: RC[round][0..16]; the
+//      internal row: RC[4 + j][0], j < 16 -- the 13 internal constants, then column 0 of external rounds 4, 5, 6).
+__global__ void poseidon2_skinny_prep_rows(const uint32_t* __restrict__ instrs, uint64_t n, uint64_t rows,
+                                           uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 51) return;
+  const uint64_t r = i / 51;
+  const uint32_t c = (uint32_t)(i % 51);
+  const uint64_t e = r / 11;
+  const uint32_t k = (uint32_t)(r % 11);
+  uint32_t v = 0;
+  if (e < n) {
+    const uint32_t* in = instrs + e * 48;
+    const bool ext = k != 0 && k != 5 && k != 10;
+    if (c < 32) {
+      if (k == 0) v = (c & 1) ? kb::P - kb::ONE : in[c >> 1];
+      else if (k == 10) v = (c & 1) ? in[32 + (c >> 1)] : in[16 + (c >> 1)];
+    } else if (c == 32) v = k == 0 ? kb::ONE : 0u;
+    else if (c == 33) v = ext ? kb::ONE : 0u;
+    else if (c == 34) v = k == 5 ? kb::ONE : 0u;
+    else {
+      const uint32_t j = c - 35;
+      if (ext) v = p2::EXT_RC[k < 5 ? k - 1 : k - 2][j];
+      else if (k == 5) v = j < 13 ? p2::INT_RC[j] : p2::EXT_RC[j - 13 + 4][0];
+    }
+  }
+  out[i] = v;
+}
+
 // ---- ALU chips from `AluEvent` records (#[repr(C)], crates/core/executor/src/events/instr.rs:10-26: 7 words, the
 //      opcode in the low byte of word 2).  Each filler writes CANONICAL values into its zeroed staging row; the flush
 //      converts to Montgomery form.  Padding rows (>= n_events) stay zero, as the reference pads.

@@ -73,6 +73,10 @@ PROTOTYPES = {
     "zk_tracegen_poseidon2_wide": (i32, [vp, u32p, u64, u64, i32, u64p]),
     "zk_tracegen_poseidon2_wide_dev": (i32, [vp, u64, u64, u64, i32, u64p]),
     "zk_tracegen_poseidon2_wide_prep": (i32, [vp, u32p, u64, u64, u64p]),
+    "zk_tracegen_poseidon2_skinny_width": (u32, []),
+    "zk_tracegen_poseidon2_skinny": (i32, [vp, u32p, u64, u64, u64p]),
+    "zk_tracegen_poseidon2_skinny_dev": (i32, [vp, u64, u64, u64, u64p]),
+    "zk_tracegen_poseidon2_skinny_prep": (i32, [vp, u32p, u64, u64, u64p]),
     "zk_challenger_init": (i32, [vp]),
     "zk_challenger_observe": (i32, [vp, vp, u32p, u32]),
     "zk_challenger_sample_ext": (i32, [vp, vp, u32, u32p]),
@@ -412,6 +416,25 @@ class Ctx:
         out = u64()
         self.lib.check(self.d.zk_tracegen_poseidon2_wide_prep(self.h, _p32(x), len(x), rows, C.byref(out)))
         return out.value, 49
+
+    def tracegen_poseidon2_skinny(self, inputs, rows):
+        """Poseidon2SkinnyChip main trace (eleven 28-word rows per permutation) from the permutation inputs ([n, 16]
+        Montgomery words, host array or (device pointer, n)); returns (device pointer, 28)."""
+        out = u64()
+        if isinstance(inputs, tuple):
+            dptr, n = inputs
+            self.lib.check(self.d.zk_tracegen_poseidon2_skinny_dev(self.h, dptr, n, rows, C.byref(out)))
+        else:
+            x = _arr(inputs, np.uint32).reshape(-1, 16)
+            self.lib.check(self.d.zk_tracegen_poseidon2_skinny(self.h, _p32(x), len(x), rows, C.byref(out)))
+        return out.value, self.d.zk_tracegen_poseidon2_skinny_width()
+
+    def tracegen_poseidon2_skinny_prep(self, instrs, rows):
+        """Poseidon2SkinnyChip preprocessed trace from [n, 48] instruction words; returns (device pointer, 51)."""
+        x = _arr(instrs, np.uint32).reshape(-1, 48)
+        out = u64()
+        self.lib.check(self.d.zk_tracegen_poseidon2_skinny_prep(self.h, _p32(x), len(x), rows, C.byref(out)))
+        return out.value, 51
 
     def download(self, dptr, shape):
         out = np.empty(shape, np.uint32)

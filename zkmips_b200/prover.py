@@ -55,7 +55,7 @@ class Chip:
     # device trace generation (MachineAir::generate_trace on the GPU, csrc/tracegen.cuh): the event records of the
     # shard's ExecutionRecord for this chip, the filler's name and the padded height (MachineAir::num_rows)
     events: Optional[np.ndarray] = None
-    tracegen: Optional[str] = None       # "AddSub" | "Bitwise" | "Lt" | "Poseidon2WideDeg3" | "Poseidon2WideDeg9"
+    tracegen: Optional[str] = None       # "AddSub" | "Bitwise" | "Lt" | "Poseidon2WideDeg3" | "Poseidon2WideDeg9" | "Poseidon2SkinnyDeg9"
     rows: Optional[int] = None
 
     @property
@@ -140,6 +140,8 @@ class GpuShardProver:
             return self.ctx.tracegen_alu(chip.tracegen, chip.events, chip.height)
         if chip.tracegen in ("Poseidon2WideDeg3", "Poseidon2WideDeg9"):
             return self.ctx.tracegen_poseidon2_wide(chip.events, chip.height, chip.tracegen.endswith("3"))
+        if chip.tracegen == "Poseidon2SkinnyDeg9":
+            return self.ctx.tracegen_poseidon2_skinny(chip.events, chip.height)
         raise ValueError(f"{chip.name}: no device trace filler named {chip.tracegen!r}")
 
     def setup(self, chips, pc_start=0, initial_global_cumulative_sum=None):

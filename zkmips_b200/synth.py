@@ -735,9 +735,10 @@ def poseidon2_skinny_prep_rows(in_addrs, out_addrs, out_mults, n):
     return t
 
 
-def skinny_program_chips(log_sk=6, log_mem=4, seed=47):
+def skinny_program_chips(log_sk=6, log_mem=4, seed=47, device=False):
     """(MemoryConst, Poseidon2SkinnyDeg9): permutation k reads constants k .. k + 15 and writes its outputs to fresh
-    addresses nobody reads; as many permutations as fit (11 rows each)."""
+    addresses nobody reads; as many permutations as fit (11 rows each).  `device=True`: the Skinny chip carries its
+    permutation inputs (events) and the prover fills the rows on the GPU (zk_tracegen_poseidon2_skinny)."""
     rng = np.random.default_rng(seed)
     n = 1 << log_sk
     k = max(1, (n * 3 // 4) // 11)
@@ -755,6 +756,10 @@ def skinny_program_chips(log_sk=6, log_mem=4, seed=47):
     mem = Chip("MemoryConst", "MemoryConst", np.zeros((mem_rows, 1), np.uint32), preprocessed=M(mem_prep.reshape(mem_rows, 12)),
                local_only=True)
     mem.canon = (mem_prep.reshape(mem_rows, 12), np.zeros((mem_rows, 1), np.uint64))
-    sk = Chip("Poseidon2SkinnyDeg9", "Poseidon2SkinnyDeg9", M(main), preprocessed=M(prep), log_quotient_degree=3)
+    if device:
+        sk = Chip("Poseidon2SkinnyDeg9", "Poseidon2SkinnyDeg9", None, preprocessed=M(prep), log_quotient_degree=3,
+                  events=M(consts[win]), tracegen="Poseidon2SkinnyDeg9", rows=n)
+    else:
+        sk = Chip("Poseidon2SkinnyDeg9", "Poseidon2SkinnyDeg9", M(main), preprocessed=M(prep), log_quotient_degree=3)
     sk.canon = (prep, main)
     return [mem, sk]
