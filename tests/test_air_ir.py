@@ -18,7 +18,8 @@ def test_exported_json_reproduces_the_generated_kernels():
     for make in (library.add_sub, library.lt, library.bitwise, lambda: library.poseidon2_wide(3),
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
-                 library.public_values_chip, library.fri_fold, library.poseidon2_skinny):
+                 library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
+                 library.branch, library.shift_left):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -32,8 +33,10 @@ def test_real_chip_shapes_match_mips_costs():
     """committed columns per row = main + 4 * permutation + 4 * quotient chunks (Chip::cost, crates/stark/src/chip.rs:
     151-162) must equal crates/core/executor/src/artifacts/mips_costs.json: AddSub 47, Lt 56, Bitwise 42; constraint
     counts as StarkMachine::setup computes them (own + count_permutation_constraints, permutation.rs:355-388)."""
-    want = {"AddSub": (19, 47, 14, 8), "Lt": (36, 56, 32, 4), "Bitwise": (18, 42, 5, 5)}
-    for make in (library.add_sub, library.lt, library.bitwise):
+    want = {"AddSub": (19, 47, 14, 8), "Lt": (36, 56, 32, 4), "Bitwise": (18, 42, 5, 5), "MovCond": (32, 48, 43, 1),
+            "Jump": (66, 82, 60, 2), "Branch": (62, 90, 60, 8), "ShiftLeft": (44, 68, 64, 5)}
+    for make in (library.add_sub, library.lt, library.bitwise, library.mov_cond, library.jump, library.branch,
+                 library.shift_left):
         air = make()
         width, cost, own, n_lookups = want[air.name]
         assert air.main_width == width
@@ -99,10 +102,26 @@ def test_alu_airs_vanish_on_their_fillers_rows():
     import numpy as np
     for make, events, rows in ((library.add_sub, synth.add_sub_events, synth.add_sub_rows),
                                (library.lt, synth.lt_events, synth.lt_rows),
-                               (library.bitwise, synth.bitwise_events, synth.bitwise_rows)):
+                               (library.bitwise, synth.bitwise_events, synth.bitwise_rows),
+                               (library.mov_cond, synth.mov_cond_events, synth.mov_cond_rows),
+                               (library.jump, synth.jump_events, synth.jump_rows),
+                               (library.branch, synth.branch_events, synth.branch_rows),
+                               (library.shift_left, synth.shift_left_events, synth.shift_left_rows)):
         ev, n = events(5)
         vals = _constraints_on_trace(make(), rows(ev, n))
-        assert all(not v.any() for v in vals)
+        assert all(not v.any() for v in vals), make.__name__
+    # one wrong cell each: MovCond's is_zero result, Jump's link address, Branch's decision, ShiftLeft's carry
+    for make, events, rows, cell in ((library.mov_cond, synth.mov_cond_events, synth.mov_cond_rows, (2, 28)),
+                                     (library.jump, synth.jump_events, synth.jump_rows, (3, 37)),
+                                     (library.branch, synth.branch_events, synth.branch_rows, (1, 59)),
+                                     (library.shift_left, synth.shift_left_events, synth.shift_left_rows, (2, 35))):
+        ev, n = events(5)
+        bad = rows(ev, n)
+        bad[cell] = (bad[cell] + 1) % ae_P
+        assert any(v.any() for v in _constraints_on_trace(make(), bad)), make.__name__
+    # ShiftLeft's first rows are the (a, b, c) triples of the reference's own test (alu/sll/mod.rs prove_koalabear)
+    ev, n = synth.shift_left_events(5)
+    assert [(int(e[4]), int(e[5]), int(e[6])) for e in ev[:19]] == synth.SLL_REFERENCE_CASES
 
 
 ae_P = 0x7F000001

@@ -695,9 +695,252 @@ def public_values_chip():
     return air
 
 
+OP_MEQ, OP_MNE, OP_WSBH = 50, 51, 52                                    # Opcode, executor/src/opcode.rs:70-72
+
+
+def _is_zero_operation(b, a, inverse, result, is_real):
+    """IsZeroOperation::eval (core/machine/src/operations/is_zero.rs:47-68)"""
+    b.when(is_real).assert_eq(1 - inverse * a, result)
+    b.when(is_real).assert_bool(result)
+    b.when(is_real).when(result).assert_zero(a)
+
+
+def _is_zero_word_operation(b, word, cols, is_real):
+    """IsZeroWordOperation::eval (core/machine/src/operations/is_zero_word.rs:44-78); cols = is_zero_byte[4] x {inverse,
+    result}, is_lower_half_zero, is_upper_half_zero, result (11 columns)"""
+    byte = [(cols[2 * i], cols[2 * i + 1]) for i in range(4)]
+    lower, upper, result = cols[8], cols[9], cols[10]
+    for i in range(4):
+        _is_zero_operation(b, word[i], byte[i][0], byte[i][1], is_real)
+    b.assert_bool(is_real)
+    r = b.when(is_real)
+    r.assert_bool(lower)
+    r.assert_bool(upper)
+    r.assert_bool(result)
+    r.assert_eq(lower, byte[0][1] * byte[1][1])
+    r.assert_eq(upper, byte[2][1] * byte[3][1])
+    r.assert_eq(result, lower * upper)
+
+
+def mov_cond():
+    """MovCondChip (crates/core/machine/src/misc/mov_cond/mod.rs:34-55 columns, :152-240 eval): MEQ / MNE (conditional
+    move on c == 0 / c != 0; a keeps its previous value otherwise) and WSBH (byte swap inside each half word).  32 main
+    columns: pc, next_pc, op_a_value, prev_a_value, op_b_value, op_c_value (words), IsZeroWordOperation c_eq_0 (11),
+    is_mne, is_meq, is_wsbh; one instruction receive whose `hi` slot carries prev_a_value and whose is_rw_a is
+    is_mne + is_meq; 43 constraints; `local_only`.  mips_costs.json: 32 + 4 * 2 + 8 = 48."""
+    air = Air("MovCond", main_width=32, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    a, prev_a, bb, c = m[2:6], m[6:10], m[10:14], m[14:18]
+    c_eq_0 = m[18:29]
+    is_mne, is_meq, is_wsbh = m[29], m[30], m[31]
+    is_real = is_mne + is_meq + is_wsbh
+    opcode = is_wsbh * OP_WSBH + is_meq * OP_MEQ + is_mne * OP_MNE
+    # receive_instruction(shard 0, clk 0, pc, next_pc, next_pc + 4, 0, opcode, a, b, c, hi = prev_a, op_a_immutable 0,
+    #                     is_rw_a = is_mne + is_meq, is_check_memory 0, is_halt 0, is_sequential 1; is_real)
+    b.receive(LOOKUP_INSTRUCTION, [0, 0, pc, next_pc, next_pc + 4, 0, opcode] + list(a) + list(bb) + list(c) + list(prev_a)
+              + [0, is_mne + is_meq, 0, 0, 1], is_real)
+    _is_zero_word_operation(b, c, c_eq_0, is_real)
+    c_zero = c_eq_0[10]
+    for flag, when_zero, other in ((is_meq, True, bb), (is_meq, False, prev_a), (is_mne, False, bb), (is_mne, True, prev_a)):
+        f = b.when(flag).when(c_zero) if when_zero else b.when(flag).when_not(c_zero)
+        for l, r in zip(a, other):
+            f.assert_eq(l, r)
+    for i, j in ((0, 1), (1, 0), (2, 3), (3, 2)):                      # eval_wsbh
+        b.when(is_wsbh).assert_eq(a[i], bb[j])
+    b.assert_bool(is_mne)
+    b.assert_bool(is_meq)
+    b.assert_bool(is_wsbh)
+    b.assert_bool(is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+OP_JUMP, OP_JUMPI, OP_JUMPDIRECT = 27, 28, 29                          # Opcode, executor/src/opcode.rs:45-47
+UNUSED_PC, DEFAULT_PC_INC = 1, 4                                        # stark/src/air/builder.rs:19-22
+
+
+def _reduce(word):
+    """Word::reduce (stark/src/word.rs:60-63)"""
+    return word[0] + word[1] * (1 << 8) + word[2] * (1 << 16) + word[3] * (1 << 24)
+
+
+def _koalabear_word_range_check(b, value, cols, is_real):
+    """KoalaBearWordRangeChecker::range_check (core/machine/src/operations/koala_bear_word.rs:45-100): the word is < p =
+    0x7F000001.  cols = most_sig_byte_decomp[8], and_most_sig_byte_decomp_0_to_{2..7} (14 columns); 17 constraints."""
+    bits, ands = cols[0:8], cols[8:14]
+    recomposed = 0
+    for i in range(8):
+        b.when(is_real).assert_bool(bits[i])
+        recomposed = recomposed + bits[i] * (1 << i)
+    b.when(is_real).assert_eq(recomposed, value[3])
+    b.when(is_real).assert_zero(bits[7])
+    b.when(is_real).assert_eq(ands[0], bits[0] * bits[1])
+    for k in range(1, 6):
+        b.when(is_real).assert_eq(ands[k], ands[k - 1] * bits[k + 1])
+    b.when(is_real).when(ands[5]).assert_zero(value[0] + value[1] + value[2])
+
+
+def _send_alu(b, opcode, a, bb, c, mult):
+    """ZKMAirBuilder::send_alu -> send_alu_with_hi -> send_instruction (stark/src/air/builder.rs:282-324): pc = UNUSED_PC,
+    hi = 0, is_sequential = 1"""
+    b.send(LOOKUP_INSTRUCTION, [0, 0, UNUSED_PC, UNUSED_PC + DEFAULT_PC_INC, UNUSED_PC + 2 * DEFAULT_PC_INC, 0, opcode]
+           + list(a) + list(bb) + list(c) + [0, 0, 0, 0] + [0, 0, 0, 0, 1], mult)
+
+
+def jump():
+    """JumpChip (crates/core/machine/src/control_flow/jump/columns.rs:11-29, air.rs:21-112): Jump / Jumpi (target in
+    op_b) and JumpDirect (target = next_pc + op_b, delegated to the ADD chip through send_alu); op_a is the link address
+    next_pc + 4.  66 main columns: pc, next_pc (word + range checker), next_next_pc (word + range checker), op_a, op_b,
+    op_c, three opcode flags, op_a's range checker; 60 constraints, one instruction receive (is_sequential = 0: the CPU
+    does not derive next_next_pc itself), one ALU send; `local_only`.  mips_costs.json: 66 + 4 * 2 + 8 = 82."""
+    air = Air("Jump", main_width=66, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc, next_pc_rc = m[0], m[1:5], m[5:19]
+    nnpc, nnpc_rc = m[19:23], m[23:37]
+    a, bb, c = m[37:41], m[41:45], m[45:49]
+    is_jump, is_jumpi, is_jumpdirect = m[49], m[50], m[51]
+    a_rc = m[52:66]
+    b.assert_bool(is_jump)
+    b.assert_bool(is_jumpi)
+    b.assert_bool(is_jumpdirect)
+    is_real = is_jump + is_jumpi + is_jumpdirect
+    b.assert_bool(is_real)
+    opcode = is_jump * OP_JUMP + is_jumpi * OP_JUMPI + is_jumpdirect * OP_JUMPDIRECT
+    b.receive(LOOKUP_INSTRUCTION, [0, 0, pc, _reduce(next_pc), _reduce(nnpc), 0, opcode] + list(a) + list(bb) + list(c)
+              + [0, 0, 0, 0] + [0, 0, 0, 0, 0], is_real)
+    b.when(is_real).assert_eq(_reduce(a), _reduce(next_pc) + 4)
+    _koalabear_word_range_check(b, a, a_rc, is_real)
+    _koalabear_word_range_check(b, next_pc, next_pc_rc, is_real)
+    _koalabear_word_range_check(b, nnpc, nnpc_rc, is_real)
+    for l, r in zip(nnpc, bb):
+        b.when(is_jump + is_jumpi).assert_eq(l, r)
+    _send_alu(b, OP_ADD, nnpc, next_pc, bb, is_jumpdirect)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+OP_BEQ, OP_BGEZ, OP_BGTZ, OP_BLEZ, OP_BLTZ, OP_BNE = 21, 22, 23, 24, 25, 26   # Opcode, executor/src/opcode.rs:39-44
+
+
+def branch():
+    """BranchChip (crates/core/machine/src/control_flow/branch/columns.rs:10-49, air.rs:26-208): BEQ / BNE / BLTZ / BLEZ /
+    BGTZ / BGEZ.  The comparison bits a_lt_b / a_gt_b come from the LT chip (two SLT sends), the branch target
+    next_pc + c from the ADD chip (send with multiplicity is_branching); next_next_pc = target if branching else
+    next_pc + 4.  62 main columns; 60 constraints; one instruction receive (op_a_immutable = 1, is_sequential = 0), three
+    ALU sends, four byte range-check sends (multiplicity is_real - is_branching); `local_only`.
+    mips_costs.json: 62 + 4 * 5 + 8 = 90."""
+    air = Air("Branch", main_width=62, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc, next_pc_rc = m[0], m[1:5], m[5:19]
+    target_pc, nnpc, nnpc_rc = m[19:23], m[23:27], m[27:41]
+    a, bb, c = m[41:45], m[45:49], m[49:53]
+    is_beq, is_bne, is_bltz, is_blez, is_bgtz, is_bgez = m[53:59]
+    is_branching, a_gt_b, a_lt_b = m[59], m[60], m[61]
+    for f in (is_beq, is_bne, is_bltz, is_bgez, is_blez, is_bgtz):
+        b.assert_bool(f)
+    is_real = is_beq + is_bne + is_bltz + is_bgez + is_blez + is_bgtz
+    b.assert_bool(is_real)
+    opcode = (is_beq * OP_BEQ + is_bne * OP_BNE + is_bltz * OP_BLTZ + is_bgez * OP_BGEZ + is_blez * OP_BLEZ
+              + is_bgtz * OP_BGTZ)
+    b.receive(LOOKUP_INSTRUCTION, [0, 0, pc, _reduce(next_pc), _reduce(nnpc), 0, opcode] + list(a) + list(bb) + list(c)
+              + [0, 0, 0, 0] + [1, 0, 0, 0, 0], is_real)
+    _koalabear_word_range_check(b, next_pc, next_pc_rc, is_real)
+    _koalabear_word_range_check(b, nnpc, nnpc_rc, is_real)
+    _send_alu(b, OP_ADD, target_pc, next_pc, c, is_branching)
+    b.when(is_real).when_not(is_branching).assert_eq(_reduce(next_pc) + 4, _reduce(nnpc))
+    _slice_range_check_u8(b, next_pc, is_real - is_branching)
+    _slice_range_check_u8(b, nnpc, is_real - is_branching)
+    for l, r in zip(target_pc, nnpc):
+        b.when(is_real).when(is_branching).assert_eq(l, r)
+    b.when_not(is_real).assert_zero(is_branching)
+    b.when(is_real).assert_bool(is_branching)
+    ne = a_gt_b + a_lt_b
+    b.when(is_beq * is_branching).assert_zero(ne)
+    b.when(is_beq).when_not(is_branching).assert_one(ne)
+    b.when(is_bne * is_branching).assert_one(ne)
+    b.when(is_bne).when_not(is_branching).assert_zero(ne)
+    b.when(is_bltz * is_branching).assert_one(a_lt_b)
+    b.when(is_bltz).when_not(is_branching).assert_zero(a_lt_b)
+    b.when(is_blez * is_branching).assert_zero(a_gt_b)
+    b.when(is_blez).when_not(is_branching).assert_one(a_gt_b)
+    b.when(is_bgtz * is_branching).assert_one(a_gt_b)
+    b.when(is_bgtz).when_not(is_branching).assert_zero(a_gt_b)
+    b.when(is_bgez * is_branching).assert_zero(a_lt_b)
+    b.when(is_bgez).when_not(is_branching).assert_one(a_lt_b)
+    _send_alu(b, OP_SLT, [a_lt_b, 0, 0, 0], a, bb, is_real)
+    _send_alu(b, OP_SLT, [a_gt_b, 0, 0, 0], bb, a, is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
+OP_SLL = 9                                                             # Opcode, executor/src/opcode.rs:26
+
+
+def shift_left():
+    """ShiftLeft (crates/core/machine/src/alu/sll/mod.rs:31-55 columns, :228-345 eval): a = b << (c mod 32) as a bit shift
+    (multiplication of the bytes by 2^(c mod 8) with carries) followed by a byte shift.  44 main columns: pc, next_pc,
+    a, b, c, c_least_sig_byte[8], shift_by_n_bits[8], bit_shift_multiplier, bit_shift_result[4],
+    bit_shift_result_carry[4], shift_by_n_bytes[4], is_real; 64 constraints (the one-hot sums hold on padding rows too,
+    which is why the padding row is not zero), four byte range-check sends, one instruction receive; `local_only`.
+    mips_costs.json: 44 + 4 * 4 + 8 = 68."""
+    air = Air("ShiftLeft", main_width=44, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    a, bb, c = m[2:6], m[6:10], m[10:14]
+    c_bits, by_bits, mult = m[14:22], m[22:30], m[30]
+    res, carry, by_bytes, is_real = m[31:35], m[35:39], m[39:43], m[43]
+    c_byte_sum = 0
+    for i in range(8):
+        c_byte_sum = c_byte_sum + c_bits[i] * (1 << i)
+    b.assert_eq(c_byte_sum, c[0])
+    num_bits = 0
+    for i in range(3):
+        num_bits = num_bits + c_bits[i] * (1 << i)
+    for i in range(8):
+        b.when(by_bits[i]).assert_eq(num_bits, i)
+    for i in range(8):
+        b.when(by_bits[i]).assert_eq(mult, 1 << i)
+    for i in range(4):
+        v = bb[i] * mult - carry[i] * 256
+        if i > 0:
+            v = v + carry[i - 1]
+        b.assert_eq(res[i], v)
+    num_bytes = c_bits[3] + c_bits[4] * 2
+    for i in range(4):
+        b.when(by_bytes[i]).assert_eq(num_bytes, i)
+    for k in range(4):
+        for i in range(4):
+            b.when(by_bytes[k]).assert_eq(a[i], 0 if i < k else res[i - k])
+    for x in c_bits:
+        b.assert_bool(x)
+    for x in by_bits:
+        b.assert_bool(x)
+    total = 0
+    for x in by_bits:
+        total = total + x
+    b.assert_eq(total, 1)
+    _slice_range_check_u8(b, res, is_real)
+    _slice_range_check_u8(b, carry, is_real)
+    for x in by_bytes:
+        b.assert_bool(x)
+    total = 0
+    for x in by_bytes:
+        total = total + x
+    b.assert_eq(total, 1)
+    b.assert_bool(is_real)
+    _receive_instruction(b, pc, next_pc, OP_SLL, a, bb, c, is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9)]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left()]

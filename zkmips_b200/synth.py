@@ -322,6 +322,202 @@ def lt_chip(log_n, seed=23, fill=0.75, name="Lt", device=False):
     return ch
 
 
+def mov_cond_events(log_n, seed=24, fill=0.75):
+    """random MEQ / MNE / WSBH events: (pc, next_pc, opcode, a, b, c, prev_a) per row (MovCondEvent,
+    crates/core/executor/src/events/instr.rs), c == 0 in about a third of the conditional moves"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    prev_a = rng.integers(0, 1 << 32, real, dtype=np.uint64)
+    c = np.where(rng.integers(0, 3, real) == 0, 0, c).astype(np.uint64)
+    c = np.where(rng.integers(0, 5, real) == 0, c & np.uint64(0xFF00), c)         # zero bytes inside a non-zero word
+    op = rng.integers(0, 3, real)                                                 # 0 MEQ, 1 MNE, 2 WSBH
+    wsbh = ((b & np.uint64(0x00FF00FF)) << np.uint64(8)) | ((b & np.uint64(0xFF00FF00)) >> np.uint64(8))
+    a = np.select([op == 0, op == 1], [np.where(c == 0, b, prev_a), np.where(c != 0, b, prev_a)], wsbh)
+    ev = np.stack([pc, (pc + 4) % P, np.array([50, 51, 52], np.uint64)[op], a, b, c, prev_a], axis=1).astype(np.uint64)
+    return ev, n
+
+
+def mov_cond_rows(events, n):
+    """MovCondChip::event_to_row + IsZeroWordOperation::populate (misc/mov_cond/mod.rs:125-143, operations/is_zero_word.rs:
+    26-42, is_zero.rs:31-43): canonical rows, zero padding"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 32), np.uint64)
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10] = _bytes(ev[:, 3]), _bytes(ev[:, 6])
+    t[:real, 10:14], t[:real, 14:18] = _bytes(ev[:, 4]), _bytes(ev[:, 5])
+    cb = _bytes(ev[:, 5])
+    inv = np.array([[pow(int(x), P - 2, P) if x else 0 for x in row] for row in cb], np.uint64).reshape(real, 4)
+    zero = (cb == 0).astype(np.uint64)
+    t[:real, 18:26:2], t[:real, 19:26:2] = inv, zero
+    t[:real, 26], t[:real, 27] = zero[:, 0] * zero[:, 1], zero[:, 2] * zero[:, 3]
+    t[:real, 28] = ev[:, 5] == 0
+    t[:real, 29], t[:real, 30], t[:real, 31] = ev[:, 2] == 51, ev[:, 2] == 50, ev[:, 2] == 52
+    return t
+
+
+def mov_cond_chip(log_n, seed=24, fill=0.75, name="MovCond"):
+    ev, n = mov_cond_events(log_n, seed, fill)
+    t = mov_cond_rows(ev, n)
+    ch = Chip(name, "MovCond", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
+def _kb_range_cols(v):
+    """KoalaBearWordRangeChecker::populate (operations/koala_bear_word.rs:28-43): bits of the top byte and their running
+    AND from bit 0"""
+    v = np.asarray(v, np.uint64)
+    bits = np.stack([(v >> np.uint64(24 + i)) & np.uint64(1) for i in range(8)], axis=1)
+    ands = np.zeros((len(v), 6), np.uint64)
+    acc = bits[:, 0] * bits[:, 1]
+    ands[:, 0] = acc
+    for k in range(1, 6):
+        acc = acc * bits[:, k + 1]
+        ands[:, k] = acc
+    return np.concatenate([bits, ands], axis=1)
+
+
+def jump_events(log_n, seed=25, fill=0.75):
+    """random Jump / Jumpi / JumpDirect events (JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c): a = next_pc + 4;
+    Jump / Jumpi jump to b, JumpDirect to next_pc + b; every address is below p (one row sits on the largest)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    next_pc = (pc + 4) % P
+    op = rng.integers(0, 3, real)                                                  # 0 Jump, 1 Jumpi, 2 JumpDirect
+    target = rng.integers(0, P - 8, real, dtype=np.uint64)
+    target[0] = P - 1                                                              # 0x7F000000: the range checker's edge
+    b = np.where(op == 2, (target + (1 << 32) - next_pc) & np.uint64(0xFFFFFFFF), target)
+    ev = np.stack([pc, next_pc, target, np.array([27, 28, 29], np.uint64)[op], next_pc + 4, b, c], axis=1).astype(np.uint64)
+    return ev, n
+
+
+def jump_rows(events, n):
+    """JumpChip::event_to_row (control_flow/jump/trace.rs:81-102)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 66), np.uint64)
+    t[:real, 0] = ev[:, 0]
+    t[:real, 1:5], t[:real, 5:19] = _bytes(ev[:, 1]), _kb_range_cols(ev[:, 1])
+    t[:real, 19:23], t[:real, 23:37] = _bytes(ev[:, 2]), _kb_range_cols(ev[:, 2])
+    t[:real, 37:41], t[:real, 41:45], t[:real, 45:49] = _bytes(ev[:, 4]), _bytes(ev[:, 5]), _bytes(ev[:, 6])
+    t[:real, 49], t[:real, 50], t[:real, 51] = ev[:, 3] == 27, ev[:, 3] == 28, ev[:, 3] == 29
+    t[:real, 52:66] = _kb_range_cols(ev[:, 4])
+    return t
+
+
+def jump_chip(log_n, seed=25, fill=0.75, name="Jump"):
+    ev, n = jump_events(log_n, seed, fill)
+    t = jump_rows(ev, n)
+    ch = Chip(name, "Jump", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
+def branch_events(log_n, seed=26, fill=0.75):
+    """random BEQ / BNE / BLTZ / BLEZ / BGTZ / BGEZ events (BranchEvent: pc, next_pc, next_next_pc, opcode, a, b, c);
+    b = 0 for the compare-with-zero forms, a == b in a third of the BEQ / BNE rows; the offset c is signed"""
+    n, real, rng, pc, b, _ = _events(log_n, seed, fill)
+    pc = pc + 0x10000
+    next_pc = pc + 4
+    op = rng.integers(0, 6, real)                                                  # index into the opcode list below
+    opc = np.array([21, 26, 25, 24, 23, 22], np.uint64)[op]                        # BEQ BNE BLTZ BLEZ BGTZ BGEZ
+    a = rng.integers(0, 1 << 32, real, dtype=np.uint64)
+    a = np.where(rng.integers(0, 4, real) == 0, 0, a).astype(np.uint64)
+    b = np.where(op >= 2, 0, np.where(rng.integers(0, 3, real) == 0, a, b)).astype(np.uint64)
+    sa, sb = a.astype(np.uint32).view(np.int32), b.astype(np.uint32).view(np.int32)
+    lt, gt, eq = sa < sb, sa > sb, sa == sb
+    branching = np.select([op == 0, op == 1, op == 2, op == 3, op == 4], [eq, ~eq, lt, lt | eq, gt], eq | gt)
+    off = rng.integers(-0x4000, 0x4000, real) * 4
+    c = (off & 0xFFFFFFFF).astype(np.uint64)
+    target = (next_pc + c) & np.uint64(0xFFFFFFFF)
+    nnpc = np.where(branching, target, next_pc + 4)
+    return np.stack([pc, next_pc, nnpc, opc, a, b, c], axis=1).astype(np.uint64), n
+
+
+def branch_rows(events, n):
+    """BranchChip::event_to_row (control_flow/branch/trace.rs:81-131)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    a, b = ev[:, 4].astype(np.uint32).view(np.int32), ev[:, 5].astype(np.uint32).view(np.int32)
+    lt, gt, eq = a < b, a > b, a == b
+    opc = ev[:, 3]
+    branching = np.select([opc == 21, opc == 26, opc == 25, opc == 24, opc == 23], [eq, ~eq, lt, lt | eq, gt], eq | gt)
+    t = np.zeros((n, 62), np.uint64)
+    t[:real, 0] = ev[:, 0]
+    t[:real, 1:5], t[:real, 5:19] = _bytes(ev[:, 1]), _kb_range_cols(ev[:, 1])
+    t[:real, 19:23] = _bytes((ev[:, 1] + ev[:, 6]) & np.uint64(0xFFFFFFFF))
+    t[:real, 23:27], t[:real, 27:41] = _bytes(ev[:, 2]), _kb_range_cols(ev[:, 2])
+    t[:real, 41:45], t[:real, 45:49], t[:real, 49:53] = _bytes(ev[:, 4]), _bytes(ev[:, 5]), _bytes(ev[:, 6])
+    for k, o in enumerate((21, 26, 25, 24, 23, 22)):                               # is_beq, is_bne, is_bltz, is_blez, is_bgtz, is_bgez
+        t[:real, 53 + k] = opc == o
+    t[:real, 59], t[:real, 60], t[:real, 61] = branching, gt, lt
+    return t
+
+
+def branch_chip(log_n, seed=26, fill=0.75, name="Branch"):
+    ev, n = branch_events(log_n, seed, fill)
+    t = branch_rows(ev, n)
+    ch = Chip(name, "Branch", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
+# the (a, b, c) triples of the reference's own ShiftLeft test (alu/sll/mod.rs `prove_koalabear`): a = b << (c mod 32)
+SLL_REFERENCE_CASES = [
+    (0x00000002, 0x00000001, 1), (0x00000080, 0x00000001, 7), (0x00004000, 0x00000001, 14), (0x80000000, 0x00000001, 31),
+    (0xffffffff, 0xffffffff, 0), (0xfffffffe, 0xffffffff, 1), (0xffffff80, 0xffffffff, 7), (0xffffc000, 0xffffffff, 14),
+    (0x80000000, 0xffffffff, 31), (0x21212121, 0x21212121, 0), (0x42424242, 0x21212121, 1), (0x90909080, 0x21212121, 7),
+    (0x48484000, 0x21212121, 14), (0x80000000, 0x21212121, 31), (0x21212121, 0x21212121, 0xffffffe0),
+    (0x42424242, 0x21212121, 0xffffffe1), (0x90909080, 0x21212121, 0xffffffe7), (0x48484000, 0x21212121, 0xffffffee),
+    (0x00000000, 0x21212120, 0xffffffff)]
+
+
+def shift_left_events(log_n, seed=27, fill=0.75):
+    """SLL AluEvents: the reference test's cases first, then random ones (a = b << (c mod 32))"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    c = np.where(rng.integers(0, 2, real) == 0, c & np.uint64(31), c)
+    k = min(real, len(SLL_REFERENCE_CASES))
+    b[:k] = [t[1] for t in SLL_REFERENCE_CASES[:k]]
+    c[:k] = [t[2] for t in SLL_REFERENCE_CASES[:k]]
+    a = (b << (c & np.uint64(31))) & np.uint64(0xFFFFFFFF)
+    assert all(int(a[i]) == SLL_REFERENCE_CASES[i][0] for i in range(k))
+    return _alu_event_array(pc, 9, a, b, c), n
+
+
+def shift_left_rows(events, n):
+    """ShiftLeft::event_to_row (alu/sll/mod.rs:150-215) and the non-zero padding row of generate_trace (:95-106)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 44), np.uint64)
+    t[:, 22], t[:, 39], t[:, 30] = 1, 1, 1                                         # padding: shift by 0 bits / 0 bytes
+    a, b, c = ev[:, 4], ev[:, 5], ev[:, 6]
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(a), _bytes(b), _bytes(c)
+    for i in range(8):
+        t[:real, 14 + i] = (c >> np.uint64(i)) & np.uint64(1)
+        t[:real, 22 + i] = (c % np.uint64(8)) == i
+    mult = np.uint64(1) << (c % np.uint64(8))
+    t[:real, 30] = mult
+    bb = _bytes(b)
+    carry = np.zeros(real, np.uint64)
+    for i in range(4):
+        v = bb[:, i] * mult + carry
+        carry = v >> np.uint64(8)
+        t[:real, 31 + i], t[:real, 35 + i] = v & np.uint64(0xFF), carry
+    nb = (c & np.uint64(31)) >> np.uint64(3)
+    for i in range(4):
+        t[:real, 39 + i] = nb == i
+    t[:real, 43] = 1
+    return t
+
+
+def shift_left_chip(log_n, seed=27, fill=0.75, name="ShiftLeft"):
+    ev, n = shift_left_events(log_n, seed, fill)
+    t = shift_left_rows(ev, n)
+    ch = Chip(name, "ShiftLeft", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
