@@ -19,7 +19,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
-                 library.branch, library.shift_left):
+                 library.branch, library.shift_left, library.clo_clz):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -34,9 +34,9 @@ def test_real_chip_shapes_match_mips_costs():
     151-162) must equal crates/core/executor/src/artifacts/mips_costs.json: AddSub 47, Lt 56, Bitwise 42; constraint
     counts as StarkMachine::setup computes them (own + count_permutation_constraints, permutation.rs:355-388)."""
     want = {"AddSub": (19, 47, 14, 8), "Lt": (36, 56, 32, 4), "Bitwise": (18, 42, 5, 5), "MovCond": (32, 48, 43, 1),
-            "Jump": (66, 82, 60, 2), "Branch": (62, 90, 60, 8), "ShiftLeft": (44, 68, 64, 5)}
+            "Jump": (66, 82, 60, 2), "Branch": (62, 90, 60, 8), "ShiftLeft": (44, 68, 64, 5), "CloClz": (22, 46, 20, 5)}
     for make in (library.add_sub, library.lt, library.bitwise, library.mov_cond, library.jump, library.branch,
-                 library.shift_left):
+                 library.shift_left, library.clo_clz):
         air = make()
         width, cost, own, n_lookups = want[air.name]
         assert air.main_width == width
@@ -44,7 +44,7 @@ def test_real_chip_shapes_match_mips_costs():
         assert len(air.sends) + len(air.receives) == n_lookups
         assert air.perm_width == -(-n_lookups // 2) + 1
         assert air.num_constraints == own + (air.perm_width - 1) + 3
-        assert air.local_only and air.commit_scope == "local"
+        assert air.local_only == (air.name != "CloClz") and air.commit_scope == "local"   # alu/clo_clz has no local_only()
         assert air.max_degree() == 3  # log_quotient_degree 1
 
 
@@ -106,7 +106,8 @@ def test_alu_airs_vanish_on_their_fillers_rows():
                                (library.mov_cond, synth.mov_cond_events, synth.mov_cond_rows),
                                (library.jump, synth.jump_events, synth.jump_rows),
                                (library.branch, synth.branch_events, synth.branch_rows),
-                               (library.shift_left, synth.shift_left_events, synth.shift_left_rows)):
+                               (library.shift_left, synth.shift_left_events, synth.shift_left_rows),
+                               (library.clo_clz, synth.clo_clz_events, synth.clo_clz_rows)):
         ev, n = events(5)
         vals = _constraints_on_trace(make(), rows(ev, n))
         assert all(not v.any() for v in vals), make.__name__
@@ -114,7 +115,8 @@ def test_alu_airs_vanish_on_their_fillers_rows():
     for make, events, rows, cell in ((library.mov_cond, synth.mov_cond_events, synth.mov_cond_rows, (2, 28)),
                                      (library.jump, synth.jump_events, synth.jump_rows, (3, 37)),
                                      (library.branch, synth.branch_events, synth.branch_rows, (1, 59)),
-                                     (library.shift_left, synth.shift_left_events, synth.shift_left_rows, (2, 35))):
+                                     (library.shift_left, synth.shift_left_events, synth.shift_left_rows, (2, 35)),
+                                     (library.clo_clz, synth.clo_clz_events, synth.clo_clz_rows, (2, 15))):
         ev, n = events(5)
         bad = rows(ev, n)
         bad[cell] = (bad[cell] + 1) % ae_P
@@ -122,6 +124,8 @@ def test_alu_airs_vanish_on_their_fillers_rows():
     # ShiftLeft's first rows are the (a, b, c) triples of the reference's own test (alu/sll/mod.rs prove_koalabear)
     ev, n = synth.shift_left_events(5)
     assert [(int(e[4]), int(e[5]), int(e[6])) for e in ev[:19]] == synth.SLL_REFERENCE_CASES
+    ev, n = synth.clo_clz_events(5)                                    # and CloClz's (alu/clo_clz/mod.rs prove_koalabear)
+    assert [(int(e[2]), int(e[4]), int(e[5])) for e in ev[:6]] == synth.CLOCLZ_REFERENCE_CASES
 
 
 ae_P = 0x7F000001

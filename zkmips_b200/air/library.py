@@ -938,9 +938,49 @@ def shift_left():
     return air
 
 
+OP_SRL, OP_CLZ, OP_CLO = 10, 19, 20                                    # Opcode, executor/src/opcode.rs:27,36-37
+
+
+def clo_clz():
+    """CloClzChip (crates/core/machine/src/alu/clo_clz/mod.rs:28-49 columns, :137-232 eval): a = number of leading zeros
+    (CLZ) or ones (CLO) of b.  bb = b or its complement; a <= 32 by a byte LTU lookup; bb = 0 gives 32, otherwise
+    bb >> (31 - a) must equal 1, which is delegated to the shift-right chip (send_alu SRL).  22 main columns: pc, next_pc,
+    a, b, bb, is_bb_zero, sr1, is_clz, is_clo, is_real; 20 constraints; three byte sends, one instruction receive, one ALU
+    send; NOT `local_only`; the padding row is CLZ of 0 (a = 32).  mips_costs.json: 22 + 4 * 4 + 8 = 46."""
+    air = Air("CloClz", main_width=22)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    a, bv, bb, is_bb_zero, sr1 = m[2:6], m[6:10], m[10:14], m[14], m[15:19]
+    is_clz, is_clo, is_real = m[19], m[20], m[21]
+    for x, y in zip(bv, bb):
+        b.when(is_clo).assert_eq(x + y, 255)
+        b.when(is_clz).assert_eq(x, y)
+    _slice_range_check_u8(b, bb, is_real)
+    _send_byte(b, BYTE_LTU, 1, a[0], 33, is_real)
+    b.when(is_real).assert_zero(a[1])
+    b.when(is_real).assert_zero(a[2])
+    b.when(is_real).assert_zero(a[3])
+    opcode = is_clo * OP_CLO + is_clz * OP_CLZ
+    b.receive(LOOKUP_INSTRUCTION, [0, 0, pc, next_pc, next_pc + 4, 0, opcode] + list(a) + list(bv) + [0, 0, 0, 0]
+              + [0, 0, 0, 0] + [0, 0, 0, 0, 1], is_real)
+    b.assert_bool(is_bb_zero)
+    b.when(is_bb_zero).assert_zero(_reduce(bb))
+    b.when(is_bb_zero).assert_zero(bb[3])
+    b.when(is_bb_zero).assert_eq(a[0], 32)
+    _send_alu(b, OP_SRL, sr1, bb, [31 - a[0], 0, 0, 0], 1 - is_bb_zero)
+    b.when_not(is_bb_zero).assert_one(_reduce(sr1))
+    b.when_not(is_bb_zero).assert_zero(sr1[3])
+    b.assert_bool(is_clo)
+    b.assert_bool(is_clz)
+    b.assert_one(is_clo + is_clz)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left()]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz()]

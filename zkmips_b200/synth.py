@@ -518,6 +518,54 @@ def shift_left_chip(log_n, seed=27, fill=0.75, name="ShiftLeft"):
     return ch
 
 
+# the (opcode, a, b) cases of the reference's own CloClz test (alu/clo_clz/mod.rs `prove_koalabear`)
+CLOCLZ_REFERENCE_CASES = [(19, 32, 0), (19, 8, 0x00800000), (19, 0, 0xffffffff), (20, 32, 0xffffffff), (20, 8, 0xff7fffff),
+                          (20, 0, 0)]
+
+
+def clo_clz_events(log_n, seed=28, fill=0.75):
+    """CLZ / CLO AluEvents (c = 0): the reference test's cases first, then random words with a random number of leading
+    zeros / ones"""
+    n, real, rng, pc, b, _ = _events(log_n, seed, fill)
+    op = rng.integers(0, 2, real)                                                  # 0 CLZ, 1 CLO
+    b = b >> rng.integers(0, 33, real).astype(np.uint64)                           # CLZ operand with that many zeros
+    k = min(real, len(CLOCLZ_REFERENCE_CASES))
+    bb = b.copy()
+    b = np.where(op == 1, np.uint64(0xFFFFFFFF) - b, b)
+    for i, (o, _, bv) in enumerate(CLOCLZ_REFERENCE_CASES[:k]):
+        op[i], b[i] = o - 19, bv
+        bb[i] = bv if o == 19 else 0xFFFFFFFF - bv
+    a = np.array([32 - int(x).bit_length() for x in bb], np.uint64)
+    assert all(int(a[i]) == CLOCLZ_REFERENCE_CASES[i][1] for i in range(k))
+    return _alu_event_array(pc, 19 + op, a, b, np.zeros(real, np.uint64)), n
+
+
+def clo_clz_rows(events, n):
+    """CloClzChip::generate_trace (alu/clo_clz/mod.rs:64-128): padding rows are CLZ of zero"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 22), np.uint64)
+    t[:, 2], t[:, 19], t[:, 14] = 32, 1, 1
+    a, b = ev[:, 4], ev[:, 5]
+    clo = (ev[:, 2] & np.uint64(0xFF)) == 20
+    bb = np.where(clo, np.uint64(0xFFFFFFFF) - b, b)
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(a), _bytes(b), _bytes(bb)
+    t[:real, 14] = bb == 0
+    sr1 = np.where(bb == 0, 0, bb >> (np.uint64(31) - np.minimum(a, 31)))
+    t[:real, 15:19] = _bytes(sr1)
+    t[:real, 19], t[:real, 20], t[:real, 21] = ~clo, clo, 1
+    return t
+
+
+def clo_clz_chip(log_n, seed=28, fill=0.75, name="CloClz"):
+    ev, n = clo_clz_events(log_n, seed, fill)
+    t = clo_clz_rows(ev, n)
+    ch = Chip(name, "CloClz", M(t))
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
