@@ -19,7 +19,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
-                 library.branch, library.shift_left, library.clo_clz):
+                 library.branch, library.shift_left, library.clo_clz, library.byte_chip):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -198,6 +198,43 @@ def test_compress_machine_chips_satisfy_their_airs():
     for chip, air in ((chips[0], library.memory_const()), (chips[1], library.base_alu()), (chips[4], library.memory_var()),
                       (chips[5], library.ext_alu())):
         assert all(not v.any() for v in _constraints_on_trace(air, chip.canon[1], chip.canon[0]))
+
+
+def test_byte_chip_answers_the_core_chips_byte_lookups():
+    """ByteChip (bytes/air.rs:22-74: 12 preprocessed + 10 multiplicity columns, ten receives, cost 54) with the
+    multiplicities ByteChip::generate_trace would count (synth.byte_chip_for: every byte lookup the eight transcribed core
+    chips send is looked up in the table and CHECKED against it).  The byte bus then balances: with the lookups of the
+    other kinds removed, the LogUp cumulative sums of the nine chips add up to zero for random challenges -- and no
+    longer do when one multiplicity is off by one."""
+    import copy
+    from oracle import logup
+    from zkmips_b200 import synth
+    chips = [synth.add_sub_chip(6), synth.lt_chip(6), synth.bitwise_chip(5), synth.mov_cond_chip(5), synth.jump_chip(5),
+             synth.branch_chip(6), synth.shift_left_chip(5), synth.clo_clz_chip(5)]
+    byte = synth.byte_chip_for(chips)
+    air = library.byte_chip()
+    assert (air.main_width, air.prep_width, len(air.sends), len(air.receives), air.num_constraints) == (10, 12, 0, 10, 5 + 3)
+    assert air.prep_width + air.main_width + 4 * air.perm_width + 8 == 54          # Chip::cost counts preprocessed columns
+    assert byte.canon[1].sum() > 500 and byte.canon[1][:, [0, 1, 2, 4, 6, 9]].any(axis=0).all()
+    assert all(not v.any() for v in _constraints_on_trace(air, byte.canon[1], byte.canon[0]))
+    rng = np.random.default_rng(3)
+    alpha, beta = ([int(x) for x in rng.integers(1, ae_P, 4)] for _ in range(2))
+
+    def byte_bus_sum(all_chips):
+        total = np.zeros(4, np.uint64)
+        for ch in all_chips:
+            only = copy.copy({a.name: a for a in [getattr(library, f)() for f in
+                                                  ("add_sub", "lt", "bitwise", "mov_cond", "jump", "branch", "shift_left",
+                                                   "clo_clz", "byte_chip")]}[ch.air])
+            only.sends = [l for l in only.sends if l["kind"] == 4]
+            only.receives = [l for l in only.receives if l["kind"] == 4]
+            _, lcs = logup.generate_permutation_trace(only, ch.canon[0], ch.canon[1], alpha, beta)
+            total = (total + np.asarray(lcs, np.uint64)) % ae_P
+        return total
+    assert not byte_bus_sum(chips + [byte]).any()
+    assert byte_bus_sum(chips).any()
+    byte.canon[1][np.nonzero(byte.canon[1][:, 4])[0][0], 4] += 1
+    assert byte_bus_sum(chips + [byte]).any()
 
 
 def test_exporter_output_without_logup_constraints_loads_to_the_same_program():

@@ -978,9 +978,28 @@ def clo_clz():
     return air
 
 
+def byte_chip():
+    """ByteChip (crates/core/machine/src/bytes/columns.rs:10-44, air.rs:22-74): the 2^16-row table that ANSWERS every byte
+    lookup of the machine.  Preprocessed (12): b, c, and, or, xor, nor, sll, shr, shr_carry, ltu, msb, value_u16 for every
+    byte pair (row index b * 256 + c); main (10): one multiplicity per ByteOpcode.  No constraints of its own, ten byte
+    receives in opcode order.  Chip::cost counts the preprocessed columns: 12 + 10 + 4 * 6 + 8 = 54 (mips_costs.json)."""
+    air = Air("Byte", main_width=10, prep_width=12)
+    b = AirBuilder(air)
+    mult = b.main().local()
+    p = b.preprocessed().local()
+    bv, cv = p[0], p[1]
+    for opcode, (a1, a2, x, y) in enumerate(((p[2], 0, bv, cv), (p[3], 0, bv, cv), (p[4], 0, bv, cv), (p[6], 0, bv, cv),
+                                             (0, 0, bv, cv), (p[7], p[8], bv, cv), (p[9], 0, bv, cv), (p[10], 0, bv, 0),
+                                             (p[11], 0, 0, 0), (p[5], 0, bv, cv))):
+        # AND, OR, XOR, SLL, U8Range, ShrCarry, LTU, MSB, U16Range, NOR (ByteOpcode::all, executor/src/events/byte.rs:165-177)
+        b.receive(LOOKUP_BYTE, [opcode, a1, a2, x, y], mult[opcode])
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz()]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip()]

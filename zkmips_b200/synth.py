@@ -566,6 +566,71 @@ def clo_clz_chip(log_n, seed=28, fill=0.75, name="CloClz"):
     return ch
 
 
+def byte_table():
+    """ByteChip::trace (crates/core/machine/src/bytes/mod.rs:36-104), canonical: one row per byte pair (b, c), index
+    b * 256 + c: b, c, and, or, xor, nor, sll, shr, shr_carry, ltu, msb, value_u16"""
+    bc = np.arange(1 << 16, dtype=np.uint64)
+    b, c = bc >> np.uint64(8), bc & np.uint64(0xFF)
+    k = c & np.uint64(7)
+    shr = b >> k
+    carry = np.where(k == 0, 0, ((b << (np.uint64(8) - k)) & np.uint64(0xFF)) >> (np.uint64(8) - k))
+    return np.stack([b, c, b & c, b | c, b ^ c, (~(b | c)) & np.uint64(0xFF), (b << k) & np.uint64(0xFF), shr, carry,
+                     b < c, b >> np.uint64(7), bc], axis=1).astype(np.uint64)
+
+
+_AIR_CACHE = {}
+
+
+def _air(name):
+    if not _AIR_CACHE:
+        from .air import library
+        _AIR_CACHE.update({a.name: a for a in library.all_airs()})
+    return _AIR_CACHE[name]
+
+
+def _lf_values(lf, prep, main, h):
+    """VirtualPairCol::apply over all rows of a canonical trace (an affine form of the row's columns)"""
+    c, terms = lf
+    acc = np.full(h, int(c) % P, np.uint64)
+    for (t, col, w) in terms:
+        src = main if t == "main" else prep
+        acc = (acc + np.asarray(src[:, col], np.uint64) * np.uint64(int(w) % P)) % np.uint64(P)
+    return acc
+
+
+def byte_chip_for(chips):
+    """ByteChip::generate_trace (bytes/trace.rs:46-67) for a shard of `chips` (each with canonical rows in .canon): every
+    byte lookup the chips SEND -- read off their AIRs' recorded lookups, row by row -- is looked up in the table
+    (U16Range by value, everything else by (b, c)), checked against it, and counted in the multiplicity column of its
+    opcode.  Returns the Byte chip (preprocessed = the table)."""
+    table = byte_table()
+    mult = np.zeros((1 << 16, 10), np.uint64)
+    col_of = {0: 2, 1: 3, 2: 4, 3: 6, 5: 7, 6: 9, 7: 10, 9: 5}                    # opcode -> table column of a1
+    for ch in chips:
+        air = _air(ch.air)
+        prep, main = ch.canon
+        h = main.shape[0]
+        for l in air.sends:
+            if l["kind"] != 4:
+                continue
+            m = _lf_values(l["mult"], prep, main, h)
+            op, a1, a2, b, c = (_lf_values(v, prep, main, h) for v in l["values"])
+            live = m != 0
+            assert (m[live] < (1 << 20)).all(), f"{ch.name}: byte lookup with a negative multiplicity"
+            row = np.where(op == 8, a1, (b << np.uint64(8)) + c)
+            assert (row[live] < (1 << 16)).all() and (op[live] < 10).all(), f"{ch.name}: byte lookup outside the table"
+            r, o = row[live].astype(np.int64), op[live].astype(np.int64)
+            for code, col in col_of.items():                                       # the looked-up value must be the table's
+                sel = o == code
+                assert (table[r[sel], col] == a1[live][sel]).all(), f"{ch.name}: byte lookup {code} disagrees with the table"
+            sel = o == 5
+            assert (table[r[sel], 8] == a2[live][sel]).all(), f"{ch.name}: ShrCarry carry disagrees with the table"
+            np.add.at(mult, (r, o), m[live])
+    byte = Chip("Byte", "Byte", M(mult % np.uint64(P)), preprocessed=M(table))
+    byte.canon = (table, mult % np.uint64(P))
+    return byte
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
