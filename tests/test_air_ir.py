@@ -19,7 +19,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
-                 library.branch, library.shift_left, library.clo_clz, library.byte_chip):
+                 library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -217,6 +217,12 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
     assert air.prep_width + air.main_width + 4 * air.perm_width + 8 == 54          # Chip::cost counts preprocessed columns
     assert byte.canon[1].sum() > 500 and byte.canon[1][:, [0, 1, 2, 4, 6, 9]].any(axis=0).all()
     assert all(not v.any() for v in _constraints_on_trace(air, byte.canon[1], byte.canon[0]))
+    # ProgramChip: the other table chip of the core machine (14 preprocessed + 1 multiplicity column, cost 31)
+    pair = library.program_chip()
+    prog = synth.program_chip(5)
+    assert (pair.main_width, pair.prep_width, len(pair.receives), pair.num_constraints) == (1, 14, 1, 1 + 3)
+    assert pair.prep_width + pair.main_width + 4 * pair.perm_width + 8 == 31
+    assert all(not v.any() for v in _constraints_on_trace(pair, prog.canon[1], prog.canon[0]))
     rng = np.random.default_rng(3)
     alpha, beta = ([int(x) for x in rng.integers(1, ae_P, 4)] for _ in range(2))
 

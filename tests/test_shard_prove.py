@@ -40,7 +40,7 @@ COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=T
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -73,7 +73,8 @@ def test_quotient_values_match_oracle(be, which):
             "Branch": lambda: synth.branch_chip(6), "ShiftLeft": lambda: synth.shift_left_chip(6),
             "CloClz": lambda: synth.clo_clz_chip(5),
             # the 2^16-row byte table with the multiplicities of two small chips' lookups
-            "Byte": lambda: synth.byte_chip_for([synth.bitwise_chip(4), synth.lt_chip(4)])}[which]()
+            "Byte": lambda: synth.byte_chip_for([synth.bitwise_chip(4), synth.lt_chip(4)]),
+            "Program": lambda: synth.program_chip(6)}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"

@@ -997,9 +997,21 @@ def byte_chip():
     return air
 
 
+def program_chip():
+    """ProgramChip (crates/core/machine/src/program/mod.rs:25-37 columns, :84-94 eval): the program as a preprocessed
+    table -- pc, InstructionCols {opcode, op_a, op_b[4], op_c[4], op_a_0, imm_b, imm_c} (cpu/columns/instruction.rs:12-33) --
+    and one multiplicity column (how often the shard executed each instruction); a single receive_program lookup
+    (air/program.rs:29-42) that answers the CPU's instruction fetches.  Cost 14 + 1 + 4 * 2 + 8 = 31 (mips_costs.json)."""
+    air = Air("Program", main_width=1, prep_width=14)
+    b = AirBuilder(air)
+    b.receive(LOOKUP_PROGRAM, list(b.preprocessed().local()), b.main().local()[0])
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip()]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip()]

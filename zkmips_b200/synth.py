@@ -631,6 +631,26 @@ def byte_chip_for(chips):
     return byte
 
 
+def program_chip(log_n, seed=29, fill=0.75, name="Program"):
+    """ProgramChip::generate_preprocessed_trace / generate_trace (program/mod.rs:56-81 and the multiplicity count): a random
+    program of `fill * 2^log_n` instructions at pc = 4 i and how often each was executed"""
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    real = max(1, int(n * fill))
+    prep = np.zeros((n, 14), np.uint64)
+    prep[:real, 0] = 4 * np.arange(real)
+    prep[:real, 1] = rng.integers(0, 56, real)                                     # opcode
+    op_a = rng.integers(0, 34, real)
+    prep[:real, 2] = op_a
+    prep[:real, 3:7], prep[:real, 7:11] = _bytes(rng.integers(0, 1 << 32, real, dtype=np.uint64)), _bytes(rng.integers(0, 1 << 32, real, dtype=np.uint64))
+    prep[:real, 11], prep[:real, 12], prep[:real, 13] = op_a == 0, rng.integers(0, 2, real), rng.integers(0, 2, real)
+    main = np.zeros((n, 1), np.uint64)
+    main[:real, 0] = rng.integers(0, 1000, real)
+    ch = Chip(name, "Program", M(main), preprocessed=M(prep))
+    ch.canon = (prep, main)
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
