@@ -19,7 +19,8 @@ def test_exported_json_reproduces_the_generated_kernels():
                  lambda: library.poseidon2_wide(9), library.memory_const, library.base_alu, library.memory_var,
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
-                 library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip):
+                 library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip,
+                 lambda: library.syscall_chip("Core"), lambda: library.syscall_chip("Precompile")):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -223,6 +224,12 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
     assert (pair.main_width, pair.prep_width, len(pair.receives), pair.num_constraints) == (1, 14, 1, 1 + 3)
     assert pair.prep_width + pair.main_width + 4 * pair.perm_width + 8 == 31
     assert all(not v.any() for v in _constraints_on_trace(pair, prog.canon[1], prog.canon[0]))
+    # SyscallCore / SyscallPrecompile (6 columns, one constraint, a syscall lookup and a Global-table send each, cost 22)
+    for kind in ("Core", "Precompile"):
+        sc, ch = library.syscall_chip(kind), synth.syscall_chip(5, kind)
+        assert (sc.main_width, len(sc.sends), len(sc.receives), sc.num_constraints) == (6, 1 + (kind != "Core"), kind == "Core", 1 + 4)
+        assert sc.main_width + 4 * sc.perm_width + 8 == 22 and not sc.local_only
+        assert all(not v.any() for v in _constraints_on_trace(sc, ch.canon[1]))
     rng = np.random.default_rng(3)
     alpha, beta = ([int(x) for x in rng.integers(1, ae_P, 4)] for _ in range(2))
 

@@ -1009,9 +1009,32 @@ def program_chip():
     return air
 
 
+LOOKUP_SYSCALL, LOOKUP_GLOBAL = 6, 7                                   # LookupKind, stark/src/lookup/lookup.rs:38-43
+
+
+def syscall_chip(kind="Core"):
+    """SyscallChip (crates/core/machine/src/syscall/chip.rs:55-70 columns, :221-293 eval), `SyscallCore` in core shards and
+    `SyscallPrecompile` in precompile shards: shard, clk, syscall_id, arg1, arg2, is_real.  The core flavour RECEIVES the
+    syscall from the CPU and forwards it to the Global table as a send (…, 1, 0, Syscall); the precompile flavour SENDS it
+    to the precompile chip of its shard and forwards a receive (…, 0, 1, Syscall).  One boolean constraint, two lookups;
+    cost 6 + 4 * 2 + 8 = 22 (mips_costs.json)."""
+    assert kind in ("Core", "Precompile")
+    air = Air("Syscall" + kind, main_width=6)
+    b = AirBuilder(air)
+    shard, clk, syscall_id, arg1, arg2, is_real = b.main().local()
+    b.assert_bool(is_real)
+    core = kind == "Core"
+    (b.receive if core else b.send)(LOOKUP_SYSCALL, [shard, clk, syscall_id, arg1, arg2], is_real)
+    b.send(LOOKUP_GLOBAL, [shard, clk, syscall_id, arg1, arg2, 0, 0, is_real * (1 if core else 0), is_real * (0 if core else 1),
+                           LOOKUP_SYSCALL], is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
-            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip()]
+            batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
+            syscall_chip("Precompile")]

@@ -651,6 +651,22 @@ def program_chip(log_n, seed=29, fill=0.75, name="Program"):
     return ch
 
 
+def syscall_chip(log_n, kind="Core", seed=30, fill=0.75):
+    """SyscallChip::generate_trace (syscall/chip.rs:100-170): one row per syscall event: shard, clk, syscall_id, arg1, arg2"""
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    real = max(1, int(n * fill))
+    t = np.zeros((n, 6), np.uint64)
+    t[:real, 0] = 1 + rng.integers(0, 4, real)
+    t[:real, 1] = 5 * np.arange(real) + 24
+    t[:real, 2] = rng.integers(0, 0x130, real)
+    t[:real, 3], t[:real, 4] = 4 * rng.integers(0, 1 << 20, real), 4 * rng.integers(0, 1 << 20, real)
+    t[:real, 5] = 1
+    ch = Chip("Syscall" + kind, "Syscall" + kind, M(t))
+    ch.canon = (None, t)
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
