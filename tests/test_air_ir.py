@@ -20,7 +20,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  library.ext_alu, library.select, library.batch_fri, library.exp_reverse_bits_len,
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
                  library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip,
-                 lambda: library.syscall_chip("Core"), lambda: library.syscall_chip("Precompile")):
+                 lambda: library.syscall_chip("Core"), lambda: library.syscall_chip("Precompile"), library.memory_local):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -230,6 +230,11 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
         assert (sc.main_width, len(sc.sends), len(sc.receives), sc.num_constraints) == (6, 1 + (kind != "Core"), kind == "Core", 1 + 4)
         assert sc.main_width + 4 * sc.perm_width + 8 == 22 and not sc.local_only
         assert all(not v.any() for v in _constraints_on_trace(sc, ch.canon[1]))
+    # MemoryLocal (four cells of 14 columns per row, one constraint and four lookups per cell, cost 100)
+    ml, ch = library.memory_local(), synth.memory_local_chip(4)
+    assert (ml.main_width, len(ml.sends), len(ml.receives), ml.num_constraints) == (56, 12, 4, 4 + 8 + 3)
+    assert ml.main_width + 4 * ml.perm_width + 8 == 100 and not ml.local_only
+    assert all(not v.any() for v in _constraints_on_trace(ml, ch.canon[1]))
     rng = np.random.default_rng(3)
     alpha, beta = ([int(x) for x in rng.integers(1, ae_P, 4)] for _ in range(2))
 

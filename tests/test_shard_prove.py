@@ -40,7 +40,7 @@ COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=T
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile", "MemoryLocal"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -77,7 +77,8 @@ def test_quotient_values_match_oracle(be, which):
             # the 2^16-row byte table with the multiplicities of two small chips' lookups
             "Byte": lambda: synth.byte_chip_for([synth.bitwise_chip(4), synth.lt_chip(4)]),
             "Program": lambda: synth.program_chip(6), "SyscallCore": lambda: synth.syscall_chip(5, "Core"),
-            "SyscallPrecompile": lambda: synth.syscall_chip(4, "Precompile")}[which]()
+            "SyscallPrecompile": lambda: synth.syscall_chip(4, "Precompile"),
+            "MemoryLocal": lambda: synth.memory_local_chip(4)}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"

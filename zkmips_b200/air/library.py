@@ -1031,10 +1031,31 @@ def syscall_chip(kind="Core"):
     return air
 
 
+def memory_local():
+    """MemoryLocalChip (crates/core/machine/src/memory/local.rs:28-61 columns, :204-270 eval): four memory cells per row,
+    each {addr, initial_shard, final_shard, initial_clk, final_clk, initial_value[4], final_value[4], is_real}.  Per cell
+    the initial state is received from the shard's memory bus and forwarded to the Global table as a receive
+    (…, 0, 1, Memory), the final state is forwarded as a send (…, 1, 0, Memory) and put on the memory bus: one boolean
+    constraint and four lookups per cell.  Cost 56 + 4 * 9 + 8 = 100 (mips_costs.json)."""
+    air = Air("MemoryLocal", main_width=56)
+    b = AirBuilder(air)
+    m = b.main().local()
+    for e in range(4):
+        addr, ishard, fshard, iclk, fclk = m[14 * e:14 * e + 5]
+        ival, fval, is_real = m[14 * e + 5:14 * e + 9], m[14 * e + 9:14 * e + 13], m[14 * e + 13]
+        b.assert_bool(is_real)
+        b.receive(LOOKUP_MEMORY, [ishard, iclk, addr] + list(ival), is_real)
+        b.send(LOOKUP_GLOBAL, [ishard, iclk, addr] + list(ival) + [is_real * 0, is_real * 1, LOOKUP_MEMORY], is_real)
+        b.send(LOOKUP_GLOBAL, [fshard, fclk, addr] + list(fval) + [is_real * 1, is_real * 0, LOOKUP_MEMORY], is_real)
+        b.send(LOOKUP_MEMORY, [fshard, fclk, addr] + list(fval), is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
             batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
-            syscall_chip("Precompile")]
+            syscall_chip("Precompile"), memory_local()]

@@ -667,6 +667,25 @@ def syscall_chip(log_n, kind="Core", seed=30, fill=0.75):
     return ch
 
 
+def memory_local_chip(log_n, seed=31, fill=0.75):
+    """MemoryLocalChip::generate_trace (memory/local.rs:125-175): four MemoryLocalEvents per row (the last real row may be
+    partly filled)"""
+    n = 1 << log_n
+    rng = np.random.default_rng(seed)
+    cells = max(1, int(4 * n * fill) - 1)
+    t = np.zeros((4 * n, 14), np.uint64)
+    t[:cells, 0] = 4 * rng.permutation(1 << 22)[:cells]
+    t[:cells, 1] = rng.integers(0, 3, cells)
+    t[:cells, 2] = 3
+    t[:cells, 3], t[:cells, 4] = rng.integers(0, 1 << 20, cells), rng.integers(1 << 20, 1 << 21, cells)
+    t[:cells, 5:9], t[:cells, 9:13] = _bytes(rng.integers(0, 1 << 32, cells, dtype=np.uint64)), _bytes(rng.integers(0, 1 << 32, cells, dtype=np.uint64))
+    t[:cells, 13] = 1
+    t = t.reshape(n, 56)
+    ch = Chip("MemoryLocal", "MemoryLocal", M(t))
+    ch.canon = (None, t)
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
