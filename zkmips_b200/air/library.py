@@ -1052,10 +1052,82 @@ def memory_local():
     return air
 
 
+OP_SRA, OP_ROR = 11, 12                                                # Opcode, executor/src/opcode.rs:28-29
+BYTE_SHR_CARRY, BYTE_MSB = 5, 7                                         # ByteOpcode, executor/src/opcode.rs:195-199
+
+
+def shift_right():
+    """ShiftRightChip (crates/core/machine/src/alu/sr/mod.rs:40-78 columns, :266-430 eval): SRL / SRA / ROR as a byte shift of
+    the 8-byte extension of b (zeros, sign bytes, or b again for the rotation) followed by a bit shift whose per-byte
+    (shifted, carry) pairs come from the Byte table's ShrCarry.  71 main columns; 83 constraints; one MSB lookup, eight
+    ShrCarry lookups (bytes 7..0), sixteen range-check pairs, one instruction receive; NOT `local_only`; padding rows have
+    shift_by_n_bits[0] = shift_by_n_bytes[0] = 1.  mips_costs.json: 71 + 4 * 14 + 8 = 135."""
+    air = Air("ShiftRight", main_width=71)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    a, bv, c = m[2:6], m[6:10], m[10:14]
+    by_bits, by_bytes = m[14:22], m[22:26]
+    byte_res, bit_res, carry, shifted = m[26:34], m[34:42], m[42:50], m[50:58]
+    b_msb, c_bits = m[58], m[59:67]
+    is_srl, is_ror, is_sra, is_real = m[67], m[68], m[69], m[70]
+    _send_byte(b, BYTE_MSB, b_msb, bv[3], 0, is_real)
+    c_byte_sum = 0
+    for i in range(8):
+        c_byte_sum = c_byte_sum + c_bits[i] * (1 << i)
+    b.assert_eq(c_byte_sum, c[0])
+    num_bits = 0
+    for i in range(3):
+        num_bits = num_bits + c_bits[i] * (1 << i)
+    for i in range(8):
+        b.when(by_bits[i]).assert_eq(num_bits, i)
+    total = 0
+    for x in by_bits:
+        total = total + x
+    b.assert_eq(total, 1)
+    num_bytes = c_bits[3] + c_bits[4] * 2
+    for i in range(4):
+        b.when(by_bytes[i]).assert_eq(num_bytes, i)
+    total = 0
+    for x in by_bytes:
+        total = total + x
+    b.assert_eq(total, 1)
+    ext = list(bv) + [is_sra * b_msb * 0xFF + is_ror * bv[i] for i in range(4)]
+    for k in range(4):
+        for i in range(8 - k):
+            b.when(by_bytes[k]).assert_eq(byte_res[i], ext[i + k])
+    carry_multiplier = 0
+    for i in range(8):
+        carry_multiplier = carry_multiplier + by_bits[i] * (1 << (8 - i))
+    for i in reversed(range(8)):
+        b.send(LOOKUP_BYTE, [BYTE_SHR_CARRY, shifted[i], carry[i], byte_res[i], num_bits], is_real)
+    for i in reversed(range(8)):
+        v = shifted[i]
+        if i + 1 < 8:
+            v = v + carry[i + 1] * carry_multiplier
+        b.assert_eq(v, bit_res[i])
+    for i in range(4):
+        b.assert_eq(a[i], bit_res[i])
+    for f in (is_srl, is_sra, is_ror, is_real, b_msb):
+        b.assert_bool(f)
+    for x in list(by_bytes) + list(by_bits) + list(c_bits):
+        b.assert_bool(x)
+    for long_word in (byte_res, bit_res, carry, shifted):
+        _slice_range_check_u8(b, long_word, is_real)
+    b.assert_bool(is_srl)
+    b.assert_bool(is_sra)
+    b.assert_bool(is_ror)
+    b.assert_bool(is_real)
+    b.assert_eq(is_srl + is_sra + is_ror, is_real)
+    _receive_instruction(b, pc, next_pc, is_srl * OP_SRL + is_sra * OP_SRA + is_ror * OP_ROR, a, bv, c, is_real)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
             batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
-            syscall_chip("Precompile"), memory_local()]
+            syscall_chip("Precompile"), memory_local(), shift_right()]

@@ -686,6 +686,69 @@ def memory_local_chip(log_n, seed=31, fill=0.75):
     return ch
 
 
+def shift_right_events(log_n, seed=32, fill=0.75):
+    """random SRL / SRA / ROR AluEvents; half of the shift amounts carry garbage above bit 4 (MIPS takes c mod 32)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    c = np.where(rng.integers(0, 2, real) == 0, c & np.uint64(31), c)
+    op = rng.integers(0, 3, real)                                                  # 0 SRL, 1 SRA, 2 ROR
+    sh = c & np.uint64(31)
+    srl = b >> sh
+    sra = (b.astype(np.uint32).view(np.int32).astype(np.int64) >> sh.astype(np.int64)).astype(np.uint64) & np.uint64(0xFFFFFFFF)
+    ror = ((b >> sh) | (b << (np.uint64(32) - sh))) & np.uint64(0xFFFFFFFF)
+    a = np.select([op == 0, op == 1], [srl, sra], ror)
+    return _alu_event_array(pc, 10 + op, a, b, c), n
+
+
+def shift_right_rows(events, n):
+    """ShiftRightChip::event_to_row (alu/sr/mod.rs:153-247) and the padding row of generate_trace (:108-111)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 71), np.uint64)
+    t[:, 14], t[:, 22] = 1, 1
+    a, b, c = ev[:, 4], ev[:, 5], ev[:, 6]
+    opc = ev[:, 2] & np.uint64(0xFF)
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14] = _bytes(a), _bytes(b), _bytes(c)
+    nbits, nbytes = (c & np.uint64(31)) % np.uint64(8), (c & np.uint64(31)) // np.uint64(8)
+    for i in range(8):
+        t[:real, 14 + i] = nbits == i
+        t[:real, 59 + i] = (c >> np.uint64(i)) & np.uint64(1)
+    for i in range(4):
+        t[:real, 22 + i] = nbytes == i
+    msb = (b >> np.uint64(31)) & np.uint64(1)
+    t[:real, 58] = msb
+    bb = _bytes(b)
+    hi = np.where((opc == 11)[:, None], (msb * np.uint64(0xFF))[:, None] * np.ones(4, np.uint64)[None, :],
+                  np.where((opc == 12)[:, None], bb, 0))
+    ext = np.concatenate([bb, hi], axis=1).astype(np.uint64)                       # the 8-byte extension of b
+    byte_res = np.zeros((real, 8), np.uint64)
+    for i in range(8):
+        src = i + nbytes.astype(np.int64)
+        ok = src < 8
+        byte_res[ok, i] = ext[np.nonzero(ok)[0], src[ok]]
+    k = nbits
+    shifted = byte_res >> k[:, None]
+    carry = np.where((k == 0)[:, None], 0, ((byte_res << (np.uint64(8) - k)[:, None]) & np.uint64(0xFF)) >> (np.uint64(8) - k)[:, None])
+    mult = np.uint64(1) << (np.uint64(8) - k)
+    bit_res = np.zeros((real, 8), np.uint64)
+    last = np.zeros(real, np.uint64)
+    for i in reversed(range(8)):
+        bit_res[:, i] = (shifted[:, i] + last * mult) & np.uint64(0xFF)
+        last = carry[:, i]
+    assert (bit_res[:, :4] == _bytes(a)).all(), "ShiftRight filler disagrees with the event's a"
+    t[:real, 26:34], t[:real, 34:42], t[:real, 42:50], t[:real, 50:58] = byte_res, bit_res, carry, shifted
+    t[:real, 67], t[:real, 68], t[:real, 69], t[:real, 70] = opc == 10, opc == 12, opc == 11, 1
+    return t
+
+
+def shift_right_chip(log_n, seed=32, fill=0.75, name="ShiftRight"):
+    ev, n = shift_right_events(log_n, seed, fill)
+    t = shift_right_rows(ev, n)
+    ch = Chip(name, "ShiftRight", M(t))
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
