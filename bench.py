@@ -330,6 +330,9 @@ def shard_chips(config, rank=0, scale=0):
     keccak: BASELINE config 3, wide_bitwise_4096 at 2^16 rows (6144 degree-3 constraints) + Fibonacci 2^16;
     large : wide_bitwise_1024 2^19, wide_bitwise_64 2^21, Fibonacci 2^21, LogUp pair 2^20 (6.8e8 cells: a maximal
             log-21 execution shard's size);
+    core  : FOURTEEN real MipsAir chips (AddSub, Lt, Bitwise filled on the device from AluEvents; ShiftLeft, ShiftRight,
+            Branch, Jump, MovCond, CloClz, MemoryLocal, SyscallCore, Program and the Byte table from host rows) at the
+            proportions of a log-19 execution shard, 67 M cells;
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
             All NINE chips are the reference's own compress-machine chips (recursion/core/src/machine.rs:112-128),
@@ -346,6 +349,22 @@ def shard_chips(config, rank=0, scale=0):
         send, recv = synth.lookup_side_chips(20 - d, seed=9 + rank)
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
+    if config == "core":
+        # a core-machine shard on FOURTEEN real MipsAir chips transcribed from their Air::eval (library.py): the ALU chips
+        # with device fillers carry events only; Byte answers every byte lookup of the others (multiplicities counted from
+        # the lookups their AIRs record).  Heights in the proportions of a log-19 execution shard.
+        ev = lambda f, lg, **kw: f(max(lg - d, 2), **kw)
+        host = [ev(synth.shift_left_chip, 17, seed=27 + rank), ev(synth.shift_right_chip, 17, seed=32 + rank),
+                ev(synth.branch_chip, 18, seed=26 + rank), ev(synth.jump_chip, 16, seed=25 + rank),
+                ev(synth.mov_cond_chip, 16, seed=24 + rank), ev(synth.clo_clz_chip, 14, seed=28 + rank),
+                ev(synth.memory_local_chip, 16, seed=31 + rank), synth.syscall_chip(max(10 - d, 2), "Core", seed=30 + rank),
+                ev(synth.program_chip, 16, seed=29 + rank)]
+        alu_host = [ev(synth.add_sub_chip, 19, seed=21 + rank), ev(synth.lt_chip, 18, seed=23 + rank),
+                    ev(synth.bitwise_chip, 18, seed=22 + rank)]
+        byte = synth.byte_chip_for(host[:6] + alu_host)
+        alu_dev = [ev(synth.add_sub_chip, 19, seed=21 + rank, device=True), ev(synth.lt_chip, 18, seed=23 + rank, device=True),
+                   ev(synth.bitwise_chip, 18, seed=22 + rank, device=True)]
+        return alu_dev + host + [byte]
     if config == "recursion":
         mem, alu, p2, sel, var, ext, bfri, erb, pvc = synth.recursion_program_chips(
             16 - d, 15 - d, 16 - d, 3, seed=41 + rank, names=("MemoryConst", "BaseAlu", "Poseidon2Wide"),
@@ -654,7 +673,7 @@ def main():
     ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
     ap.add_argument("--in-flight", type=int, default=2, help="shards in flight per GPU in the multi-shard leg (contexts)")
-    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion"],
+    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion", "core"],
                     help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 + LogUp pair 2^18 (88 M cells); keccak: BASELINE "
                          "config 3, one 2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells); "
                          "large: 6.8e8 cells, the size of a maximal log-21 execution shard")

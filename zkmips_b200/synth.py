@@ -322,6 +322,9 @@ def lt_chip(log_n, seed=23, fill=0.75, name="Lt", device=False):
     return ch
 
 
+_BYTE_INVERSES = np.array([0] + [pow(x, P - 2, P) for x in range(1, 256)], np.uint64)
+
+
 def mov_cond_events(log_n, seed=24, fill=0.75):
     """random MEQ / MNE / WSBH events: (pc, next_pc, opcode, a, b, c, prev_a) per row (MovCondEvent,
     crates/core/executor/src/events/instr.rs), c == 0 in about a third of the conditional moves"""
@@ -346,7 +349,7 @@ def mov_cond_rows(events, n):
     t[:real, 2:6], t[:real, 6:10] = _bytes(ev[:, 3]), _bytes(ev[:, 6])
     t[:real, 10:14], t[:real, 14:18] = _bytes(ev[:, 4]), _bytes(ev[:, 5])
     cb = _bytes(ev[:, 5])
-    inv = np.array([[pow(int(x), P - 2, P) if x else 0 for x in row] for row in cb], np.uint64).reshape(real, 4)
+    inv = _BYTE_INVERSES[cb.astype(np.int64)]
     zero = (cb == 0).astype(np.uint64)
     t[:real, 18:26:2], t[:real, 19:26:2] = inv, zero
     t[:real, 26], t[:real, 27] = zero[:, 0] * zero[:, 1], zero[:, 2] * zero[:, 3]
@@ -535,7 +538,7 @@ def clo_clz_events(log_n, seed=28, fill=0.75):
     for i, (o, _, bv) in enumerate(CLOCLZ_REFERENCE_CASES[:k]):
         op[i], b[i] = o - 19, bv
         bb[i] = bv if o == 19 else 0xFFFFFFFF - bv
-    a = np.array([32 - int(x).bit_length() for x in bb], np.uint64)
+    a = (32 - np.where(bb == 0, 0, np.floor(np.log2(np.maximum(bb, 1).astype(np.float64))).astype(np.int64) + 1)).astype(np.uint64)
     assert all(int(a[i]) == CLOCLZ_REFERENCE_CASES[i][1] for i in range(k))
     return _alu_event_array(pc, 19 + op, a, b, np.zeros(real, np.uint64)), n
 
