@@ -330,8 +330,8 @@ def shard_chips(config, rank=0, scale=0):
     keccak: BASELINE config 3, wide_bitwise_4096 at 2^16 rows (6144 degree-3 constraints) + Fibonacci 2^16;
     large : wide_bitwise_1024 2^19, wide_bitwise_64 2^21, Fibonacci 2^21, LogUp pair 2^20 (6.8e8 cells: a maximal
             log-21 execution shard's size);
-    core  : FOURTEEN real MipsAir chips (AddSub, Lt, Bitwise filled on the device from AluEvents; ShiftLeft, ShiftRight,
-            Branch, Jump, MovCond, CloClz, MemoryLocal, SyscallCore, Program and the Byte table from host rows) at the
+    core  : FOURTEEN real MipsAir chips (AddSub, Lt, Bitwise, ShiftLeft, ShiftRight, CloClz filled on the device from
+            AluEvents; Branch, Jump, MovCond, MemoryLocal, SyscallCore, Program and the Byte table from host rows) at the
             proportions of a log-19 execution shard, 67 M cells;
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
@@ -354,16 +354,15 @@ def shard_chips(config, rank=0, scale=0):
         # with device fillers carry events only; Byte answers every byte lookup of the others (multiplicities counted from
         # the lookups their AIRs record).  Heights in the proportions of a log-19 execution shard.
         ev = lambda f, lg, **kw: f(max(lg - d, 2), **kw)
-        host = [ev(synth.shift_left_chip, 17, seed=27 + rank), ev(synth.shift_right_chip, 17, seed=32 + rank),
-                ev(synth.branch_chip, 18, seed=26 + rank), ev(synth.jump_chip, 16, seed=25 + rank),
-                ev(synth.mov_cond_chip, 16, seed=24 + rank), ev(synth.clo_clz_chip, 14, seed=28 + rank),
+        host = [ev(synth.branch_chip, 18, seed=26 + rank), ev(synth.jump_chip, 16, seed=25 + rank),
+                ev(synth.mov_cond_chip, 16, seed=24 + rank),
                 ev(synth.memory_local_chip, 16, seed=31 + rank), synth.syscall_chip(max(10 - d, 2), "Core", seed=30 + rank),
                 ev(synth.program_chip, 16, seed=29 + rank)]
-        alu_host = [ev(synth.add_sub_chip, 19, seed=21 + rank), ev(synth.lt_chip, 18, seed=23 + rank),
-                    ev(synth.bitwise_chip, 18, seed=22 + rank)]
-        byte = synth.byte_chip_for(host[:6] + alu_host)
-        alu_dev = [ev(synth.add_sub_chip, 19, seed=21 + rank, device=True), ev(synth.lt_chip, 18, seed=23 + rank, device=True),
-                   ev(synth.bitwise_chip, 18, seed=22 + rank, device=True)]
+        alu = ((synth.add_sub_chip, 19, 21), (synth.lt_chip, 18, 23), (synth.bitwise_chip, 18, 22),
+               (synth.shift_left_chip, 17, 27), (synth.shift_right_chip, 17, 32), (synth.clo_clz_chip, 14, 28))
+        alu_host = [ev(f, lg, seed=sd + rank) for f, lg, sd in alu]          # host rows: only to count Byte's multiplicities
+        byte = synth.byte_chip_for(host[:3] + alu_host)
+        alu_dev = [ev(f, lg, seed=sd + rank, device=True) for f, lg, sd in alu]
         return alu_dev + host + [byte]
     if config == "recursion":
         mem, alu, p2, sel, var, ext, bfri, erb, pvc = synth.recursion_program_chips(
@@ -419,7 +418,9 @@ def with_host_traces(chips):
             if c.tracegen.startswith("Poseidon2Wide"):
                 c.main = ob.poseidon2_wide_trace(c.events, c.rows, c.tracegen.endswith("3"))
             else:
-                rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows}[c.tracegen]
+                rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows,
+                           "ShiftLeft": synth.shift_left_rows, "ShiftRight": synth.shift_right_rows,
+                           "CloClz": synth.clo_clz_rows}[c.tracegen]
                 c.main = to_monty(rows_of(c.events, c.rows))
         out.append(c)
     return out

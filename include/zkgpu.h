@@ -192,8 +192,9 @@ typedef struct { /* AluEvent, #[repr(C)]: crates/core/executor/src/events/instr.
   uint8_t pad_[3];
   uint32_t hi, a, b, c;
 } zk_alu_event;
-enum { ZK_CHIP_ADD_SUB = 0, ZK_CHIP_BITWISE = 1, ZK_CHIP_LT = 2 };
-uint32_t zk_tracegen_alu_width(int32_t chip); /* 19 / 18 / 36 main columns; 0 for an unknown chip */
+enum { ZK_CHIP_ADD_SUB = 0, ZK_CHIP_BITWISE = 1, ZK_CHIP_LT = 2, ZK_CHIP_SHIFT_LEFT = 3, ZK_CHIP_SHIFT_RIGHT = 4,
+       ZK_CHIP_CLO_CLZ = 5 }; /* alu/add_sub, bitwise, lt, sll, sr, clo_clz: every chip whose events are AluEvents */
+uint32_t zk_tracegen_alu_width(int32_t chip); /* 19 / 18 / 36 / 44 / 71 / 22 main columns; 0 for an unknown chip */
 int32_t zk_tracegen_alu(zk_ctx* ctx, int32_t chip, const zk_alu_event* events_host, uint64_t n_events, uint64_t rows,
                         zk_dptr* out_trace);
 int32_t zk_tracegen_alu_dev(zk_ctx* ctx, int32_t chip, zk_dptr events_dev, uint64_t n_events, uint64_t rows,

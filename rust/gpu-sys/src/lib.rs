@@ -40,6 +40,9 @@ pub struct ZkAluEvent {
 pub const ZK_CHIP_ADD_SUB: i32 = 0;
 pub const ZK_CHIP_BITWISE: i32 = 1;
 pub const ZK_CHIP_LT: i32 = 2;
+pub const ZK_CHIP_SHIFT_LEFT: i32 = 3;
+pub const ZK_CHIP_SHIFT_RIGHT: i32 = 4;
+pub const ZK_CHIP_CLO_CLZ: i32 = 5;
 
 /// 34-word image of a Plonky3 `DuplexChallenger<KoalaBear, Perm, 16, 8>`: `sponge_state`, `input_buffer` (+ length),
 /// `output_buffer` (+ length; samples pop from the END).

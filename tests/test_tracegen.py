@@ -109,8 +109,11 @@ def _check_poseidon2_wide(ctx, n_events, rows, sbox):
 
 
 def _check_alu(ctx, chip, log_n, fill):
-    events_of = {"AddSub": synth.add_sub_events, "Bitwise": synth.bitwise_events, "Lt": synth.lt_events}[chip]
-    rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows}[chip]
+    events_of = {"AddSub": synth.add_sub_events, "Bitwise": synth.bitwise_events, "Lt": synth.lt_events,
+                 "ShiftLeft": synth.shift_left_events, "ShiftRight": synth.shift_right_events,
+                 "CloClz": synth.clo_clz_events}[chip]
+    rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows,
+               "ShiftLeft": synth.shift_left_rows, "ShiftRight": synth.shift_right_rows, "CloClz": synth.clo_clz_rows}[chip]
     ev, n = events_of(log_n, fill=fill)
     dptr, w = ctx.tracegen_alu(chip, ev, n)
     got = ctx.download(dptr, (n, w))
@@ -146,7 +149,7 @@ def test_tracegen_emu():
     ctx = backends.emu()
     _check_poseidon2_wide(ctx, 100, 256, True)
     _check_poseidon2_wide(ctx, 3, 8, False)
-    for chip in ("AddSub", "Bitwise", "Lt"):
+    for chip in ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz"):
         _check_alu(ctx, chip, 8, 0.7)
     _check_prep(ctx, 5, 8)
     _check_poseidon2_skinny(ctx, 40, 512)      # two CTAs, the second one partial and partly padding
@@ -167,7 +170,7 @@ def test_tracegen_poseidon2_skinny_gpu(n_events, rows):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("chip", ["AddSub", "Bitwise", "Lt"])
+@pytest.mark.parametrize("chip", ["AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz"])
 @pytest.mark.parametrize("log_n,fill", [(0, 1.0), (3, 0.5), (7, 1.0), (12, 0.75), (17, 0.9)])
 def test_tracegen_alu_gpu(chip, log_n, fill):
     _check_alu(backends.gpu(), chip, log_n, fill)

@@ -88,6 +88,9 @@ int32_t alu(zk_ctx* c, int32_t chip, const uint32_t* host, zk_dptr dev, uint64_t
   switch (chip) {
     case ZK_CHIP_ADD_SUB: launch_alu<tg::AddSub>(c, ev, n_events, rows, out); break;
     case ZK_CHIP_BITWISE: launch_alu<tg::Bitwise>(c, ev, n_events, rows, out); break;
+    case ZK_CHIP_SHIFT_LEFT: launch_alu<tg::ShiftLeft>(c, ev, n_events, rows, out); break;
+    case ZK_CHIP_SHIFT_RIGHT: launch_alu<tg::ShiftRight>(c, ev, n_events, rows, out); break;
+    case ZK_CHIP_CLO_CLZ: launch_alu<tg::CloClz>(c, ev, n_events, rows, out); break;
     default: launch_alu<tg::Lt>(c, ev, n_events, rows, out); break;
   }
   CK(cudaGetLastError());
@@ -104,6 +107,9 @@ extern "C" uint32_t zk_tracegen_alu_width(int32_t chip) {
     case ZK_CHIP_ADD_SUB: return tg::AddSub::W;
     case ZK_CHIP_BITWISE: return tg::Bitwise::W;
     case ZK_CHIP_LT: return tg::Lt::W;
+    case ZK_CHIP_SHIFT_LEFT: return tg::ShiftLeft::W;
+    case ZK_CHIP_SHIFT_RIGHT: return tg::ShiftRight::W;
+    case ZK_CHIP_CLO_CLZ: return tg::CloClz::W;
     default: return 0;
   }
 }

@@ -211,7 +211,8 @@ __global__ void poseidon2_skinny_prep_rows(const uint32_t* __restrict__ instrs, 
 
 // ---- ALU chips from `AluEvent` records (#[repr(C)], crates/core/executor/src/events/instr.rs:10-26: 7 words, the
 //      opcode in the low byte of word 2).  Each filler writes CANONICAL values into its zeroed staging row; the flush
-//      converts to Montgomery form.  Padding rows (>= n_events) stay zero, as the reference pads.
+//      converts to Montgomery form.  Padding rows (>= n_events) are what the reference's generate_trace leaves there: zero, or the chip's
+//      padding row (CHIP::pad).
 struct AluEv {
   uint32_t pc, next_pc, opcode, hi, a, b, c;
 };
@@ -220,6 +221,7 @@ struct AluEv {
 // operations/add.rs:26-60; C++ twin crates/core/machine/include/add_sub.hpp:8-39)
 struct AddSub {
   static constexpr uint32_t W = 19;
+  __device__ static void pad(uint32_t*) {}
   __device__ static void fill(const AluEv& e, uint32_t* t) {
     bool is_add = e.opcode == 0;  // Opcode::ADD
     uint32_t op1 = is_add ? e.b : e.a, op2 = e.c, val = op1 + op2, carry = 0;
@@ -242,6 +244,7 @@ struct AddSub {
 // BitwiseChip::event_to_row (crates/core/machine/src/alu/bitwise/mod.rs:141-170)
 struct Bitwise {
   static constexpr uint32_t W = 18;
+  __device__ static void pad(uint32_t*) {}
   __device__ static void fill(const AluEv& e, uint32_t* t) {
     t[0] = e.pc;
     t[1] = e.next_pc;
@@ -261,6 +264,7 @@ struct Bitwise {
 // LtChip::event_to_row (crates/core/machine/src/alu/lt/mod.rs:179-262)
 struct Lt {
   static constexpr uint32_t W = 36;
+  __device__ static void pad(uint32_t*) {}
   __device__ static void fill(const AluEv& e, uint32_t* t) {
     const uint32_t is_slt = e.opcode == 13;  // Opcode::SLT (SLTU = 14)
     uint32_t bb[4], cb[4];
@@ -306,6 +310,105 @@ struct Lt {
   }
 };
 
+// ShiftLeft::event_to_row (crates/core/machine/src/alu/sll/mod.rs:150-215); the padding row is not zero (:95-106): the
+// one-hot sums of shift_by_n_bits / shift_by_n_bytes are constrained on every row
+struct ShiftLeft {
+  static constexpr uint32_t W = 44;
+  __device__ static void pad(uint32_t* t) { t[22] = 1; t[30] = 1; t[39] = 1; }
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+    const uint32_t nbits = e.c & 7, nbytes = (e.c & 31) >> 3, mult = 1u << nbits;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      t[2 + k] = (e.a >> (8 * k)) & 0xFF;
+      t[6 + k] = (e.b >> (8 * k)) & 0xFF;
+      t[10 + k] = (e.c >> (8 * k)) & 0xFF;
+      uint32_t v = ((e.b >> (8 * k)) & 0xFF) * mult + carry;
+      carry = v >> 8;
+      t[31 + k] = v & 0xFF;
+      t[35 + k] = carry;
+      t[39 + k] = nbytes == (uint32_t)k;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      t[14 + i] = (e.c >> i) & 1;
+      t[22 + i] = nbits == (uint32_t)i;
+    }
+    t[30] = mult;
+    t[43] = 1;
+  }
+};
+
+// ShiftRightChip::event_to_row (crates/core/machine/src/alu/sr/mod.rs:153-247): SRL 10 / SRA 11 / ROR 12 over the 8-byte
+// extension of b; padding rows have shift_by_n_bits[0] = shift_by_n_bytes[0] = 1 (:108-111)
+struct ShiftRight {
+  static constexpr uint32_t W = 71;
+  __device__ static void pad(uint32_t* t) { t[14] = 1; t[22] = 1; }
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+    const uint32_t nbits = e.c & 7, nbytes = (e.c & 31) >> 3, msb = e.b >> 31;
+    const uint32_t hi = e.opcode == 11 ? (msb ? 0xFFFFFFFFu : 0u) : e.opcode == 12 ? e.b : 0u;
+    const uint64_t ext = ((uint64_t)hi << 32) | e.b;
+    const uint64_t shifted_bytes = ext >> (8 * nbytes);  // byte_shift_result: bytes above the top are zero
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      t[2 + k] = (e.a >> (8 * k)) & 0xFF;
+      t[6 + k] = (e.b >> (8 * k)) & 0xFF;
+      t[10 + k] = (e.c >> (8 * k)) & 0xFF;
+      t[22 + k] = nbytes == (uint32_t)k;
+    }
+    uint32_t last = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      const uint32_t byte = (uint32_t)(shifted_bytes >> (8 * i)) & 0xFF;
+      const uint32_t sh = byte >> nbits, carry = nbits ? ((byte << (8 - nbits)) & 0xFF) >> (8 - nbits) : 0u;
+      t[26 + i] = byte;
+      t[34 + i] = (sh + (last << (8 - nbits))) & 0xFF;
+      t[42 + i] = carry;
+      t[50 + i] = sh;
+      last = carry;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      t[14 + i] = nbits == (uint32_t)i;
+      t[59 + i] = (e.c >> i) & 1;
+    }
+    t[58] = msb;
+    t[67] = e.opcode == 10;
+    t[68] = e.opcode == 12;
+    t[69] = e.opcode == 11;
+    t[70] = 1;
+  }
+};
+
+// CloClzChip::generate_trace (crates/core/machine/src/alu/clo_clz/mod.rs:64-128): CLZ 19 / CLO 20; the padding row is CLZ
+// of zero (a = 32, is_clz, is_bb_zero)
+struct CloClz {
+  static constexpr uint32_t W = 22;
+  __device__ static void pad(uint32_t* t) { t[2] = 32; t[14] = 1; t[19] = 1; }
+  __device__ static void fill(const AluEv& e, uint32_t* t) {
+    const bool clo = e.opcode == 20;
+    const uint32_t bb = clo ? 0xFFFFFFFFu - e.b : e.b;
+    const uint32_t sr1 = bb ? bb >> (31 - min(e.a, 31u)) : 0u;
+    t[0] = e.pc;
+    t[1] = e.next_pc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      t[2 + k] = (e.a >> (8 * k)) & 0xFF;
+      t[6 + k] = (e.b >> (8 * k)) & 0xFF;
+      t[10 + k] = (bb >> (8 * k)) & 0xFF;
+      t[15 + k] = (sr1 >> (8 * k)) & 0xFF;
+    }
+    t[14] = bb == 0;
+    t[19] = !clo;
+    t[20] = clo;
+    t[21] = 1;
+  }
+};
+
 template <class CHIP>
 __global__ void __launch_bounds__(ROWS) alu_rows(const uint32_t* __restrict__ events, uint64_t n_events, uint64_t rows,
                                                  uint32_t* __restrict__ out) {
@@ -321,6 +424,8 @@ __global__ void __launch_bounds__(ROWS) alu_rows(const uint32_t* __restrict__ ev
     const uint32_t* e = ev + 7 * tid;
     AluEv a{e[0], e[1], e[2] & 0xFFu, e[3], e[4], e[5], e[6]};
     CHIP::fill(a, tile[tid]);
+  } else {
+    CHIP::pad(tile[tid]);
   }
   __syncthreads();
   uint64_t base = row0 * W, end = rows * W;

@@ -383,7 +383,7 @@ class Ctx:
         return out.value, lcs
 
     # ---- device trace generation (csrc/tracegen.cuh)
-    ALU_CHIPS = {"AddSub": 0, "Bitwise": 1, "Lt": 2}
+    ALU_CHIPS = {"AddSub": 0, "Bitwise": 1, "Lt": 2, "ShiftLeft": 3, "ShiftRight": 4, "CloClz": 5}
 
     def tracegen_alu(self, chip, events, rows):
         """`AluEvent` records ([n, 7] uint32, host array or device pointer + count) -> device pointer of the padded

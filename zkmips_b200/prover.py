@@ -55,7 +55,7 @@ class Chip:
     # device trace generation (MachineAir::generate_trace on the GPU, csrc/tracegen.cuh): the event records of the
     # shard's ExecutionRecord for this chip, the filler's name and the padded height (MachineAir::num_rows)
     events: Optional[np.ndarray] = None
-    tracegen: Optional[str] = None       # "AddSub" | "Bitwise" | "Lt" | "Poseidon2WideDeg3" | "Poseidon2WideDeg9" | "Poseidon2SkinnyDeg9"
+    tracegen: Optional[str] = None       # "AddSub" | "Bitwise" | "Lt" | "ShiftLeft" | "ShiftRight" | "CloClz" | "Poseidon2WideDeg3" | "Poseidon2WideDeg9" | "Poseidon2SkinnyDeg9"
     rows: Optional[int] = None
 
     @property

@@ -513,8 +513,10 @@ def shift_left_rows(events, n):
     return t
 
 
-def shift_left_chip(log_n, seed=27, fill=0.75, name="ShiftLeft"):
+def shift_left_chip(log_n, seed=27, fill=0.75, name="ShiftLeft", device=False):
     ev, n = shift_left_events(log_n, seed, fill)
+    if device:                                                    # rows filled on the GPU from the AluEvents (zk_tracegen_alu)
+        return Chip(name, "ShiftLeft", None, local_only=True, events=ev, tracegen="ShiftLeft", rows=n)
     t = shift_left_rows(ev, n)
     ch = Chip(name, "ShiftLeft", M(t), local_only=True)
     ch.canon, ch.events = (None, t), ev
@@ -561,8 +563,10 @@ def clo_clz_rows(events, n):
     return t
 
 
-def clo_clz_chip(log_n, seed=28, fill=0.75, name="CloClz"):
+def clo_clz_chip(log_n, seed=28, fill=0.75, name="CloClz", device=False):
     ev, n = clo_clz_events(log_n, seed, fill)
+    if device:                                                    # rows filled on the GPU from the AluEvents (zk_tracegen_alu)
+        return Chip(name, "CloClz", None, events=ev, tracegen="CloClz", rows=n)
     t = clo_clz_rows(ev, n)
     ch = Chip(name, "CloClz", M(t))
     ch.canon, ch.events = (None, t), ev
@@ -744,8 +748,10 @@ def shift_right_rows(events, n):
     return t
 
 
-def shift_right_chip(log_n, seed=32, fill=0.75, name="ShiftRight"):
+def shift_right_chip(log_n, seed=32, fill=0.75, name="ShiftRight", device=False):
     ev, n = shift_right_events(log_n, seed, fill)
+    if device:                                                    # rows filled on the GPU from the AluEvents (zk_tracegen_alu)
+        return Chip(name, "ShiftRight", None, events=ev, tracegen="ShiftRight", rows=n)
     t = shift_right_rows(ev, n)
     ch = Chip(name, "ShiftRight", M(t))
     ch.canon, ch.events = (None, t), ev
