@@ -119,6 +119,29 @@ def test_upload_helper_commit(monkeypatch):
         ctx.destroy()
 
 
+def _ragged_cases():
+    out = []
+    for be, sizes in (("emu", [(8, 20), (9, 6), (10, 24), (9, 36), (12, 8), (10, 22)]),
+                      ("gpu", [(8, 20), (9, 6), (13, 20), (14, 36), (15, 8), (16, 24), (17, 72), (16, 56), (18, 22), (13, 6), (19, 20)])):
+        for n, w in sizes:
+            out.append(pytest.param(be, n, w, id=f"{be}-2^{n}x{w}", marks=[pytest.mark.gpu] if be == "gpu" else []))
+    return out
+
+
+@pytest.mark.parametrize("be,n,w", _ragged_cases())
+def test_ntt_ragged_widths(be, n, w):
+    """widths that are not a multiple of the 16-column tile: the last column group of <= 8 (<= 4) columns runs as its own
+    launch on 8- (4-) column tiles (ntt_kernels.cuh launch_smem) -- passes of 8, 9 and 10 stages, first / middle / last
+    passes, both directions, blowup 1 and 2, against the oracle; ZK_NTT_SPLIT=0 (one launch on 16-column tiles) gives the
+    same matrices by construction of the test."""
+    ctx = _backend(be)
+    shift = ob.lib().ork_to_monty(3)
+    m = _mont(1 << n, w, seed=1200 + n + w)
+    assert (ctx.dft_batch(m) == ob.dft_batch(m)).all()
+    for lb in (1, 2):
+        assert (ctx.coset_lde(m, lb, shift) == ob.coset_lde(m, lb, shift)).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,w", [(17, 4), (18, 4), (18, 2), (19, 4), (20, 2)])
 def test_ntt_narrow_tiles(n, w):

@@ -274,24 +274,52 @@ inline cudaError_t launch_smem_cpt(const PassArgs& A, const PassExtra& X, cudaSt
   ZK_LAUNCH_COOP(kfn, (unsigned)blocks, (C / CPT) << B, (pass_smem_bytes<B, C>()), st, A, X);
   return cudaGetLastError();
 }
+// Ragged widths: a 16-column tile whose column group holds only a few real columns still runs all its lanes (zeros in the
+// others), and these passes are bound by the integer pipes.  Real chips are rarely a multiple of 16 columns wide (19, 36,
+// 44, 62, 66, 71 ...; permutation traces 8, 20, 36, 56 ...), so the last column group of a matrix goes out as its own launch
+// on 8- or 4-column tiles when it has <= 8 (<= 4) columns: 20 columns cost 16 + 4 lanes' worth instead of 32, an
+// 8-column permutation trace 8 instead of 16.  (C = 4 needs B >= 4 and C = 8 needs B >= 3 for a CTA of at least a warp.)
+constexpr int HALF_COLS = 8;
+template <int B, int DIR, int C>
+inline cudaError_t launch_smem_c(const PassArgs& A, bool first, bool passtw, const PassExtra& X, cudaStream_t st) {
+  if (first) return passtw ? launch_smem_cpt<B, DIR, true, true, 2, C>(A, X, st) : launch_smem_cpt<B, DIR, true, false, 2, C>(A, X, st);
+  return passtw ? launch_smem_cpt<B, DIR, false, true, 2, C>(A, X, st) : launch_smem_cpt<B, DIR, false, false, 2, C>(A, X, st);
+}
+inline bool split_pref() {
+  static bool on = [] {
+    const char* e = getenv("ZK_NTT_SPLIT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 template <int B, int DIR>
 inline cudaError_t launch_smem(const PassArgs& A, bool first, const PassExtra& X, cudaStream_t st) {
   const bool passtw = A.log_n - A.s0 - (5 + B) > 0;
   const bool two = cpt_pref() == 2 && pass_aligned(A);
-  // (tiles of >= 512 rows only: below that a 4-column CTA is less than a warp, and such matrices are tiny anyway)
-  const bool narrow = two && A.nc <= NARROW_COLS && B >= 4;
-#define ZK_NTT_CASE(F, T)                                                               \
-  if (first == F && passtw == T) {                                                      \
-    if constexpr (B >= 4)                                                               \
-      if (narrow) return launch_smem_cpt<B, DIR, F, T, 2, NARROW_COLS>(A, X, st);       \
-    return two ? launch_smem_cpt<B, DIR, F, T, 2>(A, X, st) : launch_smem_cpt<B, DIR, F, T, 1>(A, X, st); \
+  if (!two) {
+    if (first) return passtw ? launch_smem_cpt<B, DIR, true, true, 1>(A, X, st) : launch_smem_cpt<B, DIR, true, false, 1>(A, X, st);
+    return passtw ? launch_smem_cpt<B, DIR, false, true, 1>(A, X, st) : launch_smem_cpt<B, DIR, false, false, 1>(A, X, st);
   }
-  ZK_NTT_CASE(false, false)
-  ZK_NTT_CASE(false, true)
-  ZK_NTT_CASE(true, false)
-  ZK_NTT_CASE(true, true)
-#undef ZK_NTT_CASE
-  return cudaErrorInvalidValue;
+  if constexpr (B >= 3) {
+    const uint32_t rem = A.nc % TILE_COLS, main = A.nc - rem;
+    const bool split = split_pref() ? rem != 0 && rem <= HALF_COLS : (main == 0 && rem <= NARROW_COLS && B >= 4);
+    if (split) {
+      if (main) {
+        PassArgs M = A;
+        M.nc = main;
+        cudaError_t e = launch_smem_c<B, DIR, TILE_COLS>(M, first, passtw, X, st);
+        if (e != cudaSuccess) return e;
+      }
+      PassArgs R = A;
+      R.c0s += main;
+      R.c0d += main;
+      R.nc = rem;
+      if constexpr (B >= 4)
+        if (rem <= NARROW_COLS) return launch_smem_c<B, DIR, NARROW_COLS>(R, first, passtw, X, st);
+      return launch_smem_c<B, DIR, HALF_COLS>(R, first, passtw, X, st);
+    }
+  }
+  return launch_smem_c<B, DIR, TILE_COLS>(A, first, passtw, X, st);
 }
 
 template <int DIR>
@@ -324,7 +352,11 @@ inline cudaError_t configure_b() {
   if constexpr (B >= 4 && CPTV == 2)                                                                              \
     if (e == cudaSuccess)                                                                                         \
       e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR, F, T, 2, NARROW_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)pass_smem_bytes<B, NARROW_COLS>());
+                               (int)pass_smem_bytes<B, NARROW_COLS>());                                         \
+  if constexpr (B >= 3 && CPTV == 2)                                                                              \
+    if (e == cudaSuccess)                                                                                         \
+      e = cudaFuncSetAttribute(ntt_pass_smem<B, DIR, F, T, 2, HALF_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)pass_smem_bytes<B, HALF_COLS>());
   ZK_NTT_ATTR(false, false, 1) ZK_NTT_ATTR(false, true, 1) ZK_NTT_ATTR(true, false, 1) ZK_NTT_ATTR(true, true, 1)
   ZK_NTT_ATTR(false, false, 2) ZK_NTT_ATTR(false, true, 2) ZK_NTT_ATTR(true, false, 2) ZK_NTT_ATTR(true, true, 2)
 #undef ZK_NTT_ATTR
