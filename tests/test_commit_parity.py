@@ -130,10 +130,9 @@ def _ragged_cases():
 
 @pytest.mark.parametrize("be,n,w", _ragged_cases())
 def test_ntt_ragged_widths(be, n, w):
-    """widths that are not a multiple of the 16-column tile: the last column group of <= 8 (<= 4) columns runs as its own
-    launch on 8- (4-) column tiles (ntt_kernels.cuh launch_smem) -- passes of 8, 9 and 10 stages, first / middle / last
-    passes, both directions, blowup 1 and 2, against the oracle; ZK_NTT_SPLIT=0 (one launch on 16-column tiles) gives the
-    same matrices by construction of the test."""
+    """widths that are not a multiple of the 16-column tile (the last column group has idle lanes; with ZK_NTT_SPLIT=1 it
+    runs as its own launch on 8- / 4-column tiles, an experiment that is bit-exact and did not pay) -- passes of 8, 9 and
+    10 stages, first / middle / last passes, both directions, blowup 1 and 2, against the oracle."""
     ctx = _backend(be)
     shift = ob.lib().ork_to_monty(3)
     m = _mont(1 << n, w, seed=1200 + n + w)

@@ -274,11 +274,13 @@ inline cudaError_t launch_smem_cpt(const PassArgs& A, const PassExtra& X, cudaSt
   ZK_LAUNCH_COOP(kfn, (unsigned)blocks, (C / CPT) << B, (pass_smem_bytes<B, C>()), st, A, X);
   return cudaGetLastError();
 }
-// Ragged widths: a 16-column tile whose column group holds only a few real columns still runs all its lanes (zeros in the
-// others), and these passes are bound by the integer pipes.  Real chips are rarely a multiple of 16 columns wide (19, 36,
-// 44, 62, 66, 71 ...; permutation traces 8, 20, 36, 56 ...), so the last column group of a matrix goes out as its own launch
-// on 8- or 4-column tiles when it has <= 8 (<= 4) columns: 20 columns cost 16 + 4 lanes' worth instead of 32, an
-// 8-column permutation trace 8 instead of 16.  (C = 4 needs B >= 4 and C = 8 needs B >= 3 for a CTA of at least a warp.)
+// Ragged widths (EXPERIMENT, off by default, ZK_NTT_SPLIT=1 enables it): a 16-column tile whose column group holds only a
+// few real columns still runs all its lanes, and real chips are rarely a multiple of 16 columns wide (19, 36, 44, 62, 66,
+// 71 ...; permutation traces 8, 20, 36, 56 ...).  Sending the last column group of <= 8 (<= 4) columns out as its own
+// launch on 8- (4-) column tiles is bit-exact (tests/test_commit_parity.py::test_ntt_ragged_widths ran green with it on)
+// and did NOT pay: core shard 24.93 -> 25.26 ms, recursion 18.96 -> 19.02, mixed 19.99 -> 19.96
+// (profiles/r2b_ntt_split_ab.txt) -- at these heights (2^16..2^19 rows) a pass is bound by launch and memory latency,
+// not by the idle lanes' arithmetic, and the extra launch costs what the narrower tile saves.
 constexpr int HALF_COLS = 8;
 template <int B, int DIR, int C>
 inline cudaError_t launch_smem_c(const PassArgs& A, bool first, bool passtw, const PassExtra& X, cudaStream_t st) {
@@ -288,7 +290,7 @@ inline cudaError_t launch_smem_c(const PassArgs& A, bool first, bool passtw, con
 inline bool split_pref() {
   static bool on = [] {
     const char* e = getenv("ZK_NTT_SPLIT");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
