@@ -672,6 +672,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="skip the shard-prove leg (commit + quotient + open)")
     ap.add_argument("--shard-steps", type=int, default=3)
+    ap.add_argument("--no-real-chip-shards", action="store_true", help="skip the core / recursion real-chip shard legs")
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
     ap.add_argument("--in-flight", type=int, default=2, help="shards in flight per GPU in the multi-shard leg (contexts)")
     ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion", "core"],
@@ -876,6 +877,14 @@ def main():
     if not args.no_shard and world == 1:
         out["exec_shard_commit"] = exec_shard_leg(ctx, torch, args)
         out["tracegen"] = tracegen_leg(ctx, torch, args)
+        if args.shard_config == "mixed" and not args.no_real_chip_shards:
+            # the same proof on REAL chips (no CPU leg here: `--shard-only --shard-config core|recursion` runs it):
+            # fourteen MipsAir chips of a core shard, and the nine chips of the compress machine at its FRI parameters
+            import copy
+            for cfg in ("core", "recursion"):
+                a2 = copy.copy(args)
+                a2.shard_config, a2.no_cpu_baseline, a2.multi_shards = cfg, True, 8
+                out["shard_prove_" + cfg] = shard_leg(ctx, torch, dist, world, rank, a2)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host core again
         v, cores, sample, _, slog, oroot = cpu_commit_sample(host_np)
