@@ -1124,10 +1124,88 @@ def shift_right():
     return air
 
 
+OP_MUL, OP_MULT, OP_MULTU = 2, 3, 4                                    # Opcode, executor/src/opcode.rs:19-21
+BYTE_U16RANGE = 8
+MEM_POS_HI, REG_HI = 4, 33                                             # MemoryAccessPosition::HI, the HI register
+
+
+def _eval_memory_access(b, shard, clk, addr, cols, do_check):
+    """MemoryAirBuilder::eval_memory_access for MemoryReadWriteCols (core/machine/src/air/memory.rs:14-137;
+    memory/consistency/columns.rs:20-51): cols = prev_value[4], value[4], prev_shard, prev_clk, compare_clk,
+    diff_16bit_limb, diff_8bit_limb.  The access happens after the previous one (same shard: by clk, else by shard; the
+    difference minus one fits 24 bits), the previous state is consumed from the memory bus and the new one put on it."""
+    prev_value, value = cols[0:4], cols[4:8]
+    prev_shard, prev_clk, compare_clk, d16, d8 = cols[8:13]
+    b.assert_bool(do_check)
+    b.when(do_check).assert_bool(compare_clk)
+    b.when(do_check).when(compare_clk).assert_eq(shard, prev_shard)
+    prev_comp = compare_clk * prev_clk + (1 - compare_clk) * prev_shard
+    cur_comp = compare_clk * clk + (1 - compare_clk) * shard
+    b.when(do_check).assert_eq(cur_comp - prev_comp - 1, d16 + d8 * (1 << 16))
+    _send_byte(b, BYTE_U16RANGE, d16, 0, 0, do_check)
+    _send_byte(b, BYTE_U8RANGE, 0, 0, d8, do_check)
+    b.send(LOOKUP_MEMORY, [prev_shard, prev_clk, addr] + list(prev_value), do_check)
+    b.receive(LOOKUP_MEMORY, [shard, clk, addr] + list(value), do_check)
+
+
+def mul():
+    """MulChip (crates/core/machine/src/alu/mul/mod.rs:41-85 columns, :335-498 eval): MUL / MULT / MULTU as an 8-byte
+    schoolbook product of the (sign-extended) operands with byte carries; the low word is a, the high word goes to HI,
+    whose register write is checked through eval_memory_access when the event carries it.  58 main columns; 41
+    constraints; two MSB lookups, eight U16 and four paired U8 range checks, the instruction receive (is_check_memory =
+    hi_record_is_real) and the memory access's two range checks, bus send and bus receive; `local_only`.
+    mips_costs.json: 58 + 4 * 11 + 8 = 110."""
+    air = Air("Mul", main_width=58, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    hi, a, bv, cv = m[2:6], m[6:10], m[10:14], m[14:18]
+    carry, product = m[18:26], m[26:34]
+    b_msb, c_msb, b_sx, c_sx = m[34], m[35], m[36], m[37]
+    is_mul, is_mult, is_multu, is_real = m[38], m[39], m[40], m[41]
+    hi_access, hi_real, shard, clk = m[42:55], m[55], m[56], m[57]
+    _send_byte(b, BYTE_MSB, b_msb, bv[3], 0, is_real)
+    _send_byte(b, BYTE_MSB, c_msb, cv[3], 0, is_real)
+    b.assert_eq(b_sx, is_mult * b_msb)
+    b.assert_eq(c_sx, is_mult * c_msb)
+    be = list(bv) + [b_sx * 0xFF] * 4
+    ce = list(cv) + [c_sx * 0xFF] * 4
+    mm = [0] * 8
+    for i in range(8):
+        for j in range(8):
+            if i + j < 8:
+                mm[i + j] = mm[i + j] + be[i] * ce[j]
+    for i in range(8):
+        b.assert_eq(product[i], mm[i] - carry[i] * 256 if i == 0 else mm[i] + carry[i - 1] - carry[i] * 256)
+    has_hi = is_mult + is_multu
+    for i in range(4):
+        b.assert_eq(product[i], a[i])
+        b.when(has_hi).assert_eq(product[i + 4], hi[i])
+    for f in (b_msb, c_msb, b_sx, c_sx, is_mul, is_mult, is_multu, is_real, hi_real):
+        b.assert_bool(f)
+    b.when(b_sx).assert_eq(b_msb, 1)
+    b.when(c_sx).assert_eq(c_msb, 1)
+    b.when(is_real).assert_one(is_mul + is_mult + is_multu)
+    opcode = is_mul * OP_MUL + is_mult * OP_MULT + is_multu * OP_MULTU
+    for x in carry:
+        _send_byte(b, BYTE_U16RANGE, x, 0, 0, is_real)
+    _slice_range_check_u8(b, product, is_real)
+    b.receive(LOOKUP_INSTRUCTION, [shard, clk, pc, next_pc, next_pc + 4, 0, opcode] + list(a) + list(bv) + list(cv) + list(hi)
+              + [0, 0, hi_real, 0, 1], is_real)
+    _eval_memory_access(b, shard, clk + MEM_POS_HI, REG_HI, hi_access, hi_real)
+    b.when(hi_real).assert_one(is_mult + is_multu)
+    for l, r in zip(hi, hi_access[4:8]):
+        b.when(hi_real).assert_eq(l, r)
+    b.when_not(hi_real).assert_zero(clk)
+    b.when_not(hi_real).assert_zero(shard)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
             batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
-            syscall_chip("Precompile"), memory_local(), shift_right()]
+            syscall_chip("Precompile"), memory_local(), shift_right(), mul()]

@@ -758,6 +758,79 @@ def shift_right_chip(log_n, seed=32, fill=0.75, name="ShiftRight", device=False)
     return ch
 
 
+def mul_events(log_n, seed=33, fill=0.75):
+    """random MUL / MULT / MULTU events (CompAluEvent: pc, next_pc, opcode, hi, a, b, c, shard, clk, hi_record_is_real and
+    the HI register's write record): columns pc, next_pc, opcode, hi, a, b, c, hi_record_is_real, shard, clk, prev_hi,
+    prev_shard, prev_clk.  MUL keeps only the low word; MULT / MULTU write HI, with the register write checked in about
+    half of them (from this shard or an earlier one)."""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    small = rng.integers(0, 4, real) == 0
+    b = np.where(small, b & np.uint64(0xFF), b)
+    op = rng.integers(0, 3, real)                                                  # 0 MUL, 1 MULT, 2 MULTU
+    sb = np.where(op == 1, b.astype(np.uint32).view(np.int32).astype(np.int64), b.astype(np.int64))
+    sc = np.where(op == 1, c.astype(np.uint32).view(np.int32).astype(np.int64), c.astype(np.int64))
+    prod = [(int(x) * int(y)) & 0xFFFFFFFFFFFFFFFF for x, y in zip(sb, sc)]
+    a = np.array([p & 0xFFFFFFFF for p in prod], np.uint64)
+    hi = np.where(op == 0, 0, np.array([p >> 32 for p in prod], np.uint64))
+    hi_real = (op != 0) & (rng.integers(0, 2, real) == 1)
+    shard = np.where(hi_real, 3, 0)
+    clk = np.where(hi_real, 24 + 5 * np.arange(real), 0)
+    same = rng.integers(0, 2, real) == 1
+    prev_shard = np.where(hi_real, np.where(same, 3, rng.integers(0, 3, real)), 0)
+    prev_clk = np.where(hi_real, np.where(same, clk - rng.integers(0, 20, real), rng.integers(0, 1 << 20, real)), 0)
+    prev_hi = np.where(hi_real, rng.integers(0, 1 << 32, real, dtype=np.uint64), 0)
+    ev = np.stack([pc, (pc + 4) % P, 2 + op, hi, a, b, c, hi_real, shard, clk, prev_hi, prev_shard, prev_clk], axis=1)
+    return ev.astype(np.uint64), n
+
+
+def mul_rows(events, n):
+    """MulChip::event_to_row (alu/mul/mod.rs:221-325) with MemoryReadWriteCols::populate_write
+    (memory/consistency/trace.rs:43-105)"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 58), np.uint64)
+    opc, hi, a, b, c, hi_real, shard, clk, prev_hi, prev_shard, prev_clk = (ev[:, k] for k in range(2, 13))
+    t[:real, 0], t[:real, 1] = ev[:, 0], ev[:, 1]
+    t[:real, 2:6], t[:real, 6:10], t[:real, 10:14], t[:real, 14:18] = _bytes(hi), _bytes(a), _bytes(b), _bytes(c)
+    b_msb, c_msb = (b >> np.uint64(31)) & np.uint64(1), (c >> np.uint64(31)) & np.uint64(1)
+    b_sx, c_sx = (opc == 3) & (b_msb == 1), (opc == 3) & (c_msb == 1)
+    be = np.concatenate([_bytes(b), np.where(b_sx[:, None], 0xFF, 0) * np.ones((real, 4), np.uint64)], axis=1).astype(np.uint64)
+    ce = np.concatenate([_bytes(c), np.where(c_sx[:, None], 0xFF, 0) * np.ones((real, 4), np.uint64)], axis=1).astype(np.uint64)
+    prod = np.zeros((real, 8), np.uint64)
+    for i in range(8):
+        for j in range(8 - i):
+            prod[:, i + j] += be[:, i] * ce[:, j]
+    for i in range(8):
+        carry = prod[:, i] >> np.uint64(8)
+        prod[:, i] &= np.uint64(0xFF)
+        if i + 1 < 8:
+            prod[:, i + 1] += carry
+        t[:real, 18 + i] = carry
+    t[:real, 26:34] = prod
+    assert (prod[:, :4] == _bytes(a)).all() and (prod[opc != 2][:, 4:] == _bytes(hi[opc != 2])).all(), "Mul filler disagrees with the events"
+    t[:real, 34], t[:real, 35], t[:real, 36], t[:real, 37] = b_msb, c_msb, b_sx, c_sx
+    t[:real, 38], t[:real, 39], t[:real, 40], t[:real, 41] = opc == 2, opc == 3, opc == 4, 1
+    live = hi_real == 1
+    t[:real, 42:46] = np.where(live[:, None], _bytes(prev_hi), 0)
+    t[:real, 46:50] = np.where(live[:, None], _bytes(hi), 0)
+    compare = live & (prev_shard == shard)
+    cur = np.where(compare, clk + 4, shard)                                        # the HI access happens at clk + 4
+    prv = np.where(compare, prev_clk, prev_shard)
+    diff = np.where(live, cur - prv - 1, 0)
+    t[:real, 50], t[:real, 51], t[:real, 52] = np.where(live, prev_shard, 0), np.where(live, prev_clk, 0), compare
+    t[:real, 53], t[:real, 54] = diff & np.uint64(0xFFFF), (diff >> np.uint64(16)) & np.uint64(0xFF)
+    t[:real, 55], t[:real, 56], t[:real, 57] = hi_real, shard, clk
+    return t
+
+
+def mul_chip(log_n, seed=33, fill=0.75, name="Mul"):
+    ev, n = mul_events(log_n, seed, fill)
+    t = mul_rows(ev, n)
+    ch = Chip(name, "Mul", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
