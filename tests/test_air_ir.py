@@ -21,7 +21,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
                  library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip,
                  lambda: library.syscall_chip("Core"), lambda: library.syscall_chip("Precompile"), library.memory_local,
-                 library.shift_right, library.mul):
+                 library.shift_right, library.mul, library.cpu):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -260,6 +260,57 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
     assert byte_bus_sum(chips).any()
     byte.canon[1][np.nonzero(byte.canon[1][:, 4])[0][0], 4] += 1
     assert byte_bus_sum(chips + [byte]).any()
+
+
+def test_core_program_chips_interlock():
+    """A toy core-machine program (synth.core_program_chips: straight-line ALU instructions over registers 1..31) on ELEVEN
+    real chips: Cpu (cpu/air/mod.rs: 67 columns, 57 constraints, 19 lookups, cost 119), Program, AddSub, Bitwise, Lt,
+    ShiftLeft, ShiftRight, CloClz, Mul, MemoryLocal and Byte.  Every constraint of every chip vanishes on the rows, and
+    the chips interlock as in the reference's machine: taken kind by kind, the LogUp sums of the MEMORY bus (register
+    accesses chained from MemoryLocal's initial to its final state), the PROGRAM bus (instruction fetches), the
+    INSTRUCTION bus (CPU -> the chip implementing the opcode, plus CloClz's SRL dependency on ShiftRight) and the BYTE bus
+    cancel across the shard; only MemoryLocal's Global-kind forwards have no partner (the Global chip is not transcribed)."""
+    import copy
+    from oracle import logup
+    from zkmips_b200 import synth
+    chips, pv_of = synth.core_program_chips(7)
+    assert [c.air for c in chips] == ["Cpu", "Program", "AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Mul",
+                                      "MemoryLocal", "Byte"]
+    airs = {a.name: a for a in (library.cpu(), library.program_chip(), library.add_sub(), library.bitwise(), library.lt(),
+                                library.shift_left(), library.shift_right(), library.clo_clz(), library.mul(),
+                                library.memory_local(), library.byte_chip())}
+    cpu = airs["Cpu"]
+    assert (cpu.main_width, len(cpu.sends), len(cpu.receives), cpu.num_constraints) == (67, 16, 3, 57 + 10 + 3)
+    assert cpu.main_width + 4 * cpu.perm_width + 8 == 119 and not cpu.local_only and cpu.uses_next_row()
+    pvs = np.zeros(231, np.uint64)
+    for k, v in pv_of.items():
+        pvs[k] = v
+    for ch in chips:
+        assert all(not v.any() for v in _constraints_on_trace(airs[ch.air], ch.canon[1], ch.canon[0], pvs=pvs)), ch.name
+    for cell in ((3, 6), (2, 38), (5, 45), (4, 0)):                    # next_pc, the written value, a timestamp limb, shard
+        bad = chips[0].canon[1].copy()
+        bad[cell] = (bad[cell] + 1) % ae_P
+        assert any(v.any() for v in _constraints_on_trace(cpu, bad, None, pvs=pvs)[:57]), cell
+    wrong = pvs.copy()
+    wrong[41] += 4                                                     # public next_pc
+    assert any(v.any() for v in _constraints_on_trace(cpu, chips[0].canon[1], None, pvs=wrong)[:57])
+    rng = np.random.default_rng(3)
+    alpha, beta = ([int(x) for x in rng.integers(1, ae_P, 4)] for _ in range(2))
+
+    def bus_sum(kind, these):
+        total = np.zeros(4, np.uint64)
+        for ch in these:
+            only = copy.copy(airs[ch.air])
+            only.sends = [l for l in only.sends if l["kind"] == kind]
+            only.receives = [l for l in only.receives if l["kind"] == kind]
+            if only.sends or only.receives:
+                _, lcs = logup.generate_permutation_trace(only, ch.canon[0], ch.canon[1], alpha, beta)
+                total = (total + np.asarray(lcs, np.uint64)) % ae_P
+        return total
+    for kind in (1, 2, 3, 4):                                          # Memory, Program, Instruction, Byte
+        assert not bus_sum(kind, chips).any(), kind
+        assert bus_sum(kind, chips[1:]).any(), kind                    # without the CPU every one of them is open
+    assert bus_sum(7, chips).any()                                     # Global: MemoryLocal's forwards
 
 
 def test_exporter_output_without_logup_constraints_loads_to_the_same_program():

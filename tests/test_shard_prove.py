@@ -40,7 +40,7 @@ COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=T
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile", "MemoryLocal", "ShiftRight", "Mul"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile", "MemoryLocal", "ShiftRight", "Mul", "Cpu"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -79,7 +79,7 @@ def test_quotient_values_match_oracle(be, which):
             "Program": lambda: synth.program_chip(6), "SyscallCore": lambda: synth.syscall_chip(5, "Core"),
             "SyscallPrecompile": lambda: synth.syscall_chip(4, "Precompile"),
             "MemoryLocal": lambda: synth.memory_local_chip(4), "ShiftRight": lambda: synth.shift_right_chip(6),
-            "Mul": lambda: synth.mul_chip(6)}[which]()
+            "Mul": lambda: synth.mul_chip(6), "Cpu": lambda: synth.core_program_chips(6)[0][0]}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
@@ -110,7 +110,7 @@ def test_quotient_values_match_oracle(be, which):
         kw["perm"] = (perm_pd, 0)
         okw["perm_q"] = _natural(perm_pd.lde(0))
         okw["lcs"] = ob.from_monty(lcs)
-    pvs = su.public_values_for([chip], 231 if which == "PublicValues" else 8)
+    pvs = su.public_values_for([chip], 231 if which in ("PublicValues", "Cpu") else 8)
     gcs = su.M(np.arange(1, 15))
     dptr = ctx.quotient(chip.air, (main_pd, 0), n, lqd, alpha, perm_challenges=chal, public_values=pvs,
                         local_cumsum=lcs, global_cumsum=gcs, **kw)
@@ -437,6 +437,40 @@ def test_poseidon2_skinny_program_shard_verifies_completely(be):
     och = bf.new_challenger()
     opk.observe_into(och)
     assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, NUM_PV))) == pf.to_bincode(sp)
+    data.free()
+    pk.data.free()
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_core_program_shard(be):
+    """The toy core-machine program on eleven real chips -- Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
+    CloClz, Mul, MemoryLocal, Byte (GPU only: 2^16 rows) -- with the core machine's 231 public values (start_pc, next_pc,
+    execution_shard constrained by the CPU chip): the proof is byte-identical with the CPU prover's and every per-chip
+    check of the verifier passes; the memory, program, instruction and byte buses cancel (tests/test_air_ir.py), so what
+    is left in the shard's cumulative sum are MemoryLocal's Global-kind forwards."""
+    from oracle import binding_fri as bf
+    from oracle import shard_prover as osp
+    from zkmips_b200 import proof as pf
+    ctx = _backend(be)
+    nq, pw = (6, 4) if be == "emu" else (84, 16)
+    chips, _ = synth.core_program_chips(6 if be == "emu" else 12)
+    if be == "emu":
+        chips = chips[:-1]
+    npv = 231
+    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw, num_pv=npv)
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], npv, 1, nq, pw)
+    assert not ok and why.endswith("local cumulative sum is not zero"), why
+    op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=npv)
+    opk = op.setup(chips, pc_start=pk.pc_start, initial_global_cumulative_sum=pk.initial_global_cumulative_sum)
+    och = bf.new_challenger()
+    opk.observe_into(och)
+    assert pf.to_bincode(op.prove(opk, chips, och, su.public_values_for(chips, npv))) == pf.to_bincode(sp)
+    # wrong public next_pc: the CPU chip's own constraint fails
+    bad_pvs = su.public_values_for(chips, npv).copy()
+    bad_pvs[41] = su.M([7])[0]
+    sp2 = prover.open(pk, prover.commit(chips, bad_pvs), _machine_challenger(ctx, pk))
+    ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp2], npv, 1, nq, pw)
+    assert not ok and not why.endswith("local cumulative sum is not zero"), why
     data.free()
     pk.data.free()
 

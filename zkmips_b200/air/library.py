@@ -1202,10 +1202,101 @@ def mul():
     return air
 
 
+MEM_POS_C, MEM_POS_B, MEM_POS_A = 1, 2, 3                              # MemoryAccessPosition, executor/src/events/memory.rs:29-40
+PV_START_PC, PV_NEXT_PC, PV_EXECUTION_SHARD = 40, 41, 44               # PublicValues<Word<T>, T>, stark/src/air/public_values.rs:17-46
+CORE_NUM_PV_ELTS = 231                                                  # PROOF_MAX_NUM_PVS
+
+
+def _read_cols_as_rw(cols):
+    """MemoryReadCols {access} seen through MemoryCols: prev_value() = value() (memory/consistency/columns.rs:60-90)"""
+    return list(cols[0:4]) + list(cols)
+
+
+def cpu():
+    """CpuChip (crates/core/machine/src/cpu/columns/mod.rs:16-62, air/mod.rs:20-211, air/register.rs:11-76): one row per
+    executed instruction.  It fetches the instruction from the Program table, reads op_b / op_c and writes op_a through
+    three eval_memory_access (registers are memory cells 0..33; clk + 2, + 1, + 3), hands the instruction with its operand
+    VALUES to whichever chip implements the opcode (send_instruction), and chains shard / clk / pc from row to row and to
+    the shard's public values (start_pc, next_pc, execution_shard).  67 main columns, 61 constraints, 19 lookups.
+    mips_costs.json: 67 + 4 * 11 + 8 = 119."""
+    air = Air("Cpu", main_width=67, num_public_values=CORE_NUM_PV_ELTS)
+    b = AirBuilder(air)
+    m, mn = b.main().local(), b.main().next()
+    pv = b.public_values()
+
+    def cols(r):
+        return dict(shard=r[0], clk16=r[1], clk8=r[2], shard_to_send=r[3], clk_to_send=r[4], pc=r[5], next_pc=r[6],
+                    next_next_pc=r[7], opcode=r[8], op_a=r[9], op_b=r[10:14], op_c=r[14:18], op_a_0=r[18], imm_b=r[19],
+                    imm_c=r[20], num_extra_cycles=r[21], is_rw_a=r[22], is_check_memory=r[23], is_halt=r[24],
+                    is_sequential=r[25], op_a_value=r[26:30], hi_or_prev_a=r[30:34], a_access=r[34:47], b_access=r[47:56],
+                    c_access=r[56:65], is_real=r[65], op_a_immutable=r[66])
+    l, n = cols(m), cols(mn)
+    is_real = l["is_real"]
+    clk = l["clk8"] * (1 << 16) + l["clk16"]
+    instruction = [l["opcode"], l["op_a"]] + list(l["op_b"]) + list(l["op_c"]) + [l["op_a_0"], l["imm_b"], l["imm_c"]]
+    b.send(LOOKUP_PROGRAM, [l["pc"]] + instruction, is_real)                                   # send_program
+    # eval_registers (air/register.rs)
+    a_val, a_prev = l["a_access"][4:8], l["a_access"][0:4]
+    b_val, c_val = l["b_access"][0:4], l["c_access"][0:4]
+    for x, y in zip(b_val, l["op_b"]):
+        b.when(l["imm_b"]).assert_eq(x, y)
+    for x, y in zip(c_val, l["op_c"]):
+        b.when(l["imm_c"]).assert_eq(x, y)
+    _eval_memory_access(b, l["shard"], clk + MEM_POS_B, l["op_b"][0], _read_cols_as_rw(l["b_access"]), 1 - l["imm_b"])
+    _eval_memory_access(b, l["shard"], clk + MEM_POS_C, l["op_c"][0], _read_cols_as_rw(l["c_access"]), 1 - l["imm_c"])
+    for x in a_val:
+        b.when(l["op_a_0"]).assert_zero(x)
+    for x, y in zip(l["op_a_value"], a_val):
+        b.when_not(l["op_a_0"]).assert_eq(x, y)
+    for x, y in zip(l["hi_or_prev_a"], a_prev):
+        b.when(l["is_rw_a"]).assert_eq(x, y)
+    _eval_memory_access(b, l["shard"], clk + MEM_POS_A, l["op_a"], l["a_access"], is_real)
+    _slice_range_check_u8(b, a_val, is_real)
+    for x, y in zip(a_val, a_prev):
+        b.when(l["op_a_immutable"]).assert_eq(x, y)
+    # air/mod.rs:49-76: what is sent along with the instruction
+    b.when(is_real).assert_eq(l["shard_to_send"], l["is_check_memory"] * l["shard"] + (1 - l["is_check_memory"]) * 0)
+    b.when(is_real).assert_eq(l["clk_to_send"], l["is_check_memory"] * clk + (1 - l["is_check_memory"]) * 0)
+    b.send(LOOKUP_INSTRUCTION, [l["shard_to_send"], l["clk_to_send"], l["pc"], l["next_pc"], l["next_next_pc"],
+                                l["num_extra_cycles"], l["opcode"]] + list(l["op_a_value"]) + list(b_val) + list(c_val)
+           + list(l["hi_or_prev_a"]) + [l["op_a_immutable"], l["is_rw_a"], l["is_check_memory"], l["is_halt"],
+                                        l["is_sequential"]], is_real)
+    # eval_shard_clk
+    b.when_transition().when(n["is_real"]).assert_eq(l["shard"], n["shard"])
+    _send_byte(b, BYTE_U16RANGE, l["shard"], 0, 0, is_real)
+    b.when_first_row().assert_zero(clk)
+    next_clk = n["clk8"] * (1 << 16) + n["clk16"]
+    b.when_transition().when(n["is_real"]).assert_eq(clk + 5 + l["num_extra_cycles"], next_clk)
+    b.when(is_real).assert_eq(clk, l["clk16"] + l["clk8"] * (1 << 16))                         # eval_range_check_24bits
+    _send_byte(b, BYTE_U16RANGE, l["clk16"], 0, 0, is_real)
+    _send_byte(b, BYTE_U8RANGE, 0, 0, l["clk8"], is_real)
+    # eval_pc
+    b.when(is_real).assert_eq(pv[PV_EXECUTION_SHARD], l["shard"])
+    b.when_first_row().assert_eq(pv[PV_START_PC], l["pc"])
+    b.when_first_row().when_not(l["is_halt"]).assert_eq(l["pc"] + 4, l["next_pc"])
+    b.when_transition().when(n["is_real"]).assert_eq(l["next_pc"], n["pc"])
+    b.when_transition().when(n["is_real"]).when_not(n["is_halt"]).assert_eq(l["next_next_pc"], n["next_pc"])
+    b.when_transition().when(is_real).when(l["is_sequential"]).assert_eq(l["next_next_pc"], l["next_pc"] + 4)
+    b.when_transition().when(is_real - n["is_real"]).assert_eq(pv[PV_NEXT_PC], l["next_pc"])
+    b.when_last_row().when(is_real).assert_eq(pv[PV_NEXT_PC], l["next_pc"])
+    # eval_is_real
+    b.assert_bool(is_real)
+    b.when_first_row().assert_one(is_real)
+    b.when_transition().when_not(is_real).assert_zero(n["is_real"])
+    b.when_transition().when(l["is_halt"]).assert_zero(n["is_real"])
+    # padding rows carry imm_b = imm_c = is_rw_a = 1
+    not_real = 1 - is_real
+    b.when(not_real).assert_zero(1 - l["imm_b"])
+    b.when(not_real).assert_zero(1 - l["imm_c"])
+    b.when(not_real).assert_zero(1 - l["is_rw_a"])
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 def all_airs():
     return [fibonacci(), lookup_pair(), wide_bitwise(64, "wide_bitwise_64"), wide_bitwise(256, "wide_bitwise_256"),
             wide_bitwise(1024, "wide_bitwise_1024"),
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
             batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
-            syscall_chip("Precompile"), memory_local(), shift_right(), mul()]
+            syscall_chip("Precompile"), memory_local(), shift_right(), mul(), cpu()]

@@ -146,6 +146,8 @@ def public_values_for(chips, n=8):
             pv[0:3] = c.pvs
     pv[3] = LOOKUP_PV3
     for c in chips:
+        for k, v in (getattr(c, "core_pvs", None) or {}).items():      # start_pc, next_pc, execution_shard of the core machine
+            pv[k] = v
         if getattr(c, "pv_digest", None) is not None:                  # RecursionPublicValues.digest (air/public_values.rs:144)
             pv[223:231] = c.pv_digest
     return M(pv)
@@ -1272,3 +1274,143 @@ def skinny_program_chips(log_sk=6, log_mem=4, seed=47, device=False):
         sk = Chip("Poseidon2SkinnyDeg9", "Poseidon2SkinnyDeg9", M(main), preprocessed=M(prep), log_quotient_degree=3)
     sk.canon = (prep, main)
     return [mem, sk]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A toy core-machine PROGRAM: straight-line ALU instructions over registers 1..31, executed here, from which the rows of
+# the CPU chip, the Program table, the seven ALU chips that implement the opcodes, MemoryLocal (initial / final register
+# states) and the Byte table all follow.  The chips then interlock exactly as in the reference's machine: every
+# instruction the CPU sends is received by one ALU chip, every instruction fetch is answered by Program, every register
+# access chains on the memory bus from MemoryLocal's initial state to its final state, and every byte lookup is answered
+# by Byte -- only the Global-kind lookups of MemoryLocal have no partner (the Global chip is not transcribed).
+# ------------------------------------------------------------------------------------------------------------------
+_CORE_OPS = {0: "AddSub", 1: "AddSub", 15: "Bitwise", 16: "Bitwise", 17: "Bitwise", 18: "Bitwise", 13: "Lt", 14: "Lt",
+             9: "ShiftLeft", 10: "ShiftRight", 11: "ShiftRight", 12: "ShiftRight", 19: "CloClz", 20: "CloClz", 2: "Mul"}
+
+
+def _core_op(opcode, b, c):
+    M32 = 0xFFFFFFFF
+    sb, sc = b - (1 << 32) if b >> 31 else b, c - (1 << 32) if c >> 31 else c
+    sh = c & 31
+    if opcode == 0: return (b + c) & M32
+    if opcode == 1: return (b - c) & M32
+    if opcode == 15: return b & c
+    if opcode == 16: return b | c
+    if opcode == 17: return b ^ c
+    if opcode == 18: return ~(b | c) & M32
+    if opcode == 13: return int(sb < sc)
+    if opcode == 14: return int(b < c)
+    if opcode == 9: return (b << sh) & M32
+    if opcode == 10: return b >> sh
+    if opcode == 11: return (sb >> sh) & M32
+    if opcode == 12: return ((b >> sh) | (b << (32 - sh))) & M32
+    if opcode == 19: return 32 - b.bit_length()
+    if opcode == 20: return 32 - ((~b) & M32).bit_length()
+    if opcode == 2: return (b * c) & M32
+    raise ValueError(opcode)
+
+
+def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
+    """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, MemoryLocal, Byte], public values
+    (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU rows."""
+    rng = np.random.default_rng(seed)
+    n = 1 << log_cpu
+    real = max(2, int(n * fill))
+    regs = {r: int(rng.integers(0, 1 << 32)) for r in range(1, 32)}
+    initial = dict(regs)
+    last = {r: (0, 0) for r in regs}                                   # (shard, clk) of the previous access
+    touched = set()
+    opcodes = list(_CORE_OPS)
+    cpu = np.zeros((n, 67), np.uint64)
+    cpu[:, 19], cpu[:, 20], cpu[:, 22] = 1, 1, 1                       # padding rows: imm_b = imm_c = is_rw_a = 1
+    prog = np.zeros((n, 14), np.uint64)
+    events = {name: [] for name in set(_CORE_OPS.values())}
+
+    def access(row, base, reg, clk, value, prev_value=None):
+        """MemoryAccessCols::populate_access (memory/consistency/trace.rs:69-105) at columns base.."""
+        ps, pc_ = last[reg]
+        touched.add(reg)
+        compare = ps == shard
+        diff = ((clk if compare else shard) - (pc_ if compare else ps) - 1) & 0xFFFFFFFF
+        assert diff < (1 << 24)
+        if prev_value is not None:
+            row[base:base + 4] = [(prev_value >> (8 * k)) & 0xFF for k in range(4)]
+            base += 4
+        row[base:base + 4] = [(value >> (8 * k)) & 0xFF for k in range(4)]
+        row[base + 4:base + 9] = [ps, pc_, int(compare), diff & 0xFFFF, diff >> 16]
+        last[reg] = (shard, clk)
+
+    for i in range(real):
+        opcode = opcodes[int(rng.integers(0, len(opcodes)))]
+        ra, rb, rc = (int(x) for x in rng.integers(1, 32, 3))
+        imm_c = opcode in (19, 20) or int(rng.integers(0, 4)) == 0
+        clk, pc = 5 * i, pc_start + 4 * i
+        row = cpu[i]
+        cval = (0 if opcode in (19, 20) else int(rng.integers(0, 1 << 16))) if imm_c else regs[rc]
+        if not imm_c:
+            access(row, 56, rc, clk + 1, cval)
+        else:
+            row[56:60] = [(cval >> (8 * k)) & 0xFF for k in range(4)]
+        bval = regs[rb]
+        access(row, 47, rb, clk + 2, bval)
+        aval = _core_op(opcode, bval, cval)
+        access(row, 34, ra, clk + 3, aval, prev_value=regs[ra])
+        regs[ra] = aval
+        op_c_word = cval if imm_c else rc
+        row[0], row[1], row[2] = shard, clk & 0xFFFF, clk >> 16
+        row[5], row[6], row[7] = pc, pc + 4, pc + 8
+        row[8], row[9] = opcode, ra
+        row[10:14] = [rb, 0, 0, 0]
+        row[14:18] = [(op_c_word >> (8 * k)) & 0xFF for k in range(4)]
+        row[18], row[19], row[20] = 0, 0, int(imm_c)
+        row[22], row[25] = 0, 1                                        # is_rw_a = 0, is_sequential = 1
+        row[26:30] = [(aval >> (8 * k)) & 0xFF for k in range(4)]
+        row[65] = 1
+        prog[i] = [pc, opcode, ra, rb, 0, 0, 0] + [(op_c_word >> (8 * k)) & 0xFF for k in range(4)] + [0, 0, int(imm_c)]
+        events[_CORE_OPS[opcode]].append((pc, opcode, aval, bval, cval))
+        if opcode in (19, 20):
+            # CloClzChip's dependency (alu/clo_clz/mod.rs eval: send_alu(SRL, sr1, bb, 31 - a) unless bb = 0): an extra SRL
+            # event at UNUSED_PC for the shift-right chip, as the executor's generate_dependencies adds it
+            bb = bval if opcode == 19 else 0xFFFFFFFF - bval
+            if bb:
+                events["ShiftRight"].append((1, 10, bb >> (31 - aval), bb, 31 - aval))
+
+    def pow2(k):
+        return max(2, (max(k, 1) - 1).bit_length())
+    chips = []
+    c = Chip("Cpu", "Cpu", M(cpu))
+    c.canon = (None, cpu)
+    chips.append(c)
+    mult = np.zeros((n, 1), np.uint64)
+    mult[:real] = 1
+    c = Chip("Program", "Program", M(mult), preprocessed=M(prog))
+    c.canon = (prog, mult)
+    chips.append(c)
+    fillers = {"AddSub": add_sub_rows, "Bitwise": bitwise_rows, "Lt": lt_rows, "ShiftLeft": shift_left_rows,
+               "ShiftRight": shift_right_rows, "CloClz": clo_clz_rows}
+    for name in ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Mul"):
+        e = np.array(events[name], np.uint64).reshape(-1, 5)
+        h = 1 << pow2(len(e))
+        if name == "Mul":                                              # MUL: no HI write, shard = clk = 0
+            ev = np.zeros((len(e), 13), np.uint64)
+            ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 4], ev[:, 5], ev[:, 6] = e[:, 0], e[:, 0] + 4, e[:, 1], e[:, 2], e[:, 3], e[:, 4]
+            t = mul_rows(ev, h)
+        else:
+            t = fillers[name](_alu_event_array(e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4]), h)
+        c = Chip(name, name, M(t), local_only=_air(name).local_only)
+        c.canon = (None, t)
+        chips.append(c)
+    regs_used = sorted(touched)
+    rows_m = 1 << pow2(-(-len(regs_used) // 4))
+    ml = np.zeros((4 * rows_m, 14), np.uint64)
+    for k, r in enumerate(regs_used):
+        ml[k] = [r, 0, last[r][0], 0, last[r][1]] + [(initial[r] >> (8 * j)) & 0xFF for j in range(4)] \
+            + [(regs[r] >> (8 * j)) & 0xFF for j in range(4)] + [1]
+    ml = ml.reshape(rows_m, 56)
+    c = Chip("MemoryLocal", "MemoryLocal", M(ml))
+    c.canon = (None, ml)
+    chips.append(c)
+    chips.append(byte_chip_for([ch for ch in chips if ch.air != "Program"]))
+    pvs = {40: pc_start, 41: pc_start + 4 * real, 44: shard}
+    chips[0].core_pvs = pvs
+    return chips, pvs
