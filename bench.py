@@ -317,7 +317,7 @@ NUM_PV = 8  # StarkMachine::num_pv_elts of the synthetic machine
 
 def num_pv(config):
     """the recursion machines observe PROOF_MAX_NUM_PVS = 231 public values (stark/src/types.rs:73, machine.rs:127)"""
-    return 231 if config == "recursion" else NUM_PV
+    return 231 if config in ("recursion", "program") else NUM_PV
 
 
 FRI_PARAMS = {"recursion": (2, 42, 16)}  # compressed_fri_config (kb31_poseidon2.rs:216-227); default (1, 84, 16)
@@ -333,6 +333,9 @@ def shard_chips(config, rank=0, scale=0):
     core  : FOURTEEN real MipsAir chips (AddSub, Lt, Bitwise, ShiftLeft, ShiftRight, CloClz filled on the device from
             AluEvents; Branch, Jump, MovCond, MemoryLocal, SyscallCore, Program and the Byte table from host rows) at the
             proportions of a log-19 execution shard, 67 M cells;
+    program: a toy core-machine program of 2^17 * 0.9 straight-line ALU instructions executed in Python, on ELEVEN real
+            chips that interlock (Cpu 2^17 x 67, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul,
+            MemoryLocal, Byte): the CPU's instruction, program, memory and byte lookups are all answered in the shard;
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
             All NINE chips are the reference's own compress-machine chips (recursion/core/src/machine.rs:112-128),
@@ -349,6 +352,10 @@ def shard_chips(config, rank=0, scale=0):
         send, recv = synth.lookup_side_chips(20 - d, seed=9 + rank)
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
+    if config == "program":
+        # a toy core-machine PROGRAM executed in Python (synth.core_program_chips): Cpu, Program, seven ALU chips,
+        # MemoryLocal and Byte whose memory / program / instruction / byte buses cancel across the shard
+        return synth.core_program_chips(17 - d, seed=51 + rank)[0]
     if config == "core":
         # a core-machine shard on FOURTEEN real MipsAir chips transcribed from their Air::eval (library.py): the ALU chips
         # with device fillers carry events only; Byte answers every byte lookup of the others (multiplicities counted from
@@ -675,7 +682,7 @@ def main():
     ap.add_argument("--no-real-chip-shards", action="store_true", help="skip the core / recursion real-chip shard legs")
     ap.add_argument("--shard-only", action="store_true", help="profiling aid: run only the shard-prove leg")
     ap.add_argument("--in-flight", type=int, default=2, help="shards in flight per GPU in the multi-shard leg (contexts)")
-    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion", "core"],
+    ap.add_argument("--shard-config", default="mixed", choices=["mixed", "keccak", "large", "recursion", "core", "program"],
                     help="mixed: 2^16x1024 + 2^18x64 + Fibonacci 2^20 + LogUp pair 2^18 (88 M cells); keccak: BASELINE "
                          "config 3, one 2^16 x 4096 chip with 6144 degree-3 constraints + Fibonacci 2^16 (268 M cells); "
                          "large: 6.8e8 cells, the size of a maximal log-21 execution shard")
@@ -881,7 +888,7 @@ def main():
             # the same proof on REAL chips (no CPU leg here: `--shard-only --shard-config core|recursion` runs it):
             # fourteen MipsAir chips of a core shard, and the nine chips of the compress machine at its FRI parameters
             import copy
-            for cfg in ("core", "recursion"):
+            for cfg in ("core", "program", "recursion"):
                 a2 = copy.copy(args)
                 a2.shard_config, a2.no_cpu_baseline, a2.multi_shards = cfg, True, 8
                 out["shard_prove_" + cfg] = shard_leg(ctx, torch, dist, world, rank, a2)
