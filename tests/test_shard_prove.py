@@ -443,8 +443,8 @@ def test_poseidon2_skinny_program_shard_verifies_completely(be):
 
 @pytest.mark.parametrize("be", BACKENDS)
 def test_core_program_shard(be):
-    """The toy core-machine program on eleven real chips -- Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
-    CloClz, Mul, MemoryLocal, Byte (GPU only: 2^16 rows) -- with the core machine's 231 public values (start_pc, next_pc,
+    """The toy core-machine program on fourteen real chips -- Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
+    CloClz, Mul, MovCond, Jump, Branch, MemoryLocal, Byte (GPU only: 2^16 rows) -- with the core machine's 231 public values (start_pc, next_pc,
     execution_shard constrained by the CPU chip): the proof is byte-identical with the CPU prover's and every per-chip
     check of the verifier passes; the memory, program, instruction and byte buses cancel (tests/test_air_ir.py), so what
     is left in the shard's cumulative sum are MemoryLocal's Global-kind forwards."""

@@ -1311,8 +1311,13 @@ def _core_op(opcode, b, c):
 
 
 def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
-    """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, MemoryLocal, Byte], public values
-    (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU rows."""
+    """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, MovCond, Jump, Branch, MemoryLocal,
+    Byte], public values (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU
+    rows.  About 70 % of the instructions are ALU operations, the rest conditional moves (MEQ / MNE / WSBH), branches
+    (all six, with the delay slot: next_next_pc = target when taken) and jumps (Jumpi, JumpDirect); control flow always
+    goes FORWARD to fresh addresses, so every executed pc is one row of the Program table.  The chips' own dependencies
+    are generated as the executor's generate_dependencies does: CloClz's SRL on ShiftRight, Branch's two SLT on Lt and
+    its target ADD on AddSub, JumpDirect's target ADD on AddSub, all at UNUSED_PC."""
     rng = np.random.default_rng(seed)
     n = 1 << log_cpu
     real = max(2, int(n * fill))
@@ -1320,60 +1325,125 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     initial = dict(regs)
     last = {r: (0, 0) for r in regs}                                   # (shard, clk) of the previous access
     touched = set()
-    opcodes = list(_CORE_OPS)
+    alu_ops = list(_CORE_OPS)
     cpu = np.zeros((n, 67), np.uint64)
     cpu[:, 19], cpu[:, 20], cpu[:, 22] = 1, 1, 1                       # padding rows: imm_b = imm_c = is_rw_a = 1
     prog = np.zeros((n, 14), np.uint64)
     events = {name: [] for name in set(_CORE_OPS.values())}
+    mov_events, jump_events, branch_events = [], [], []
+    M32 = 0xFFFFFFFF
+
+    def word(v):
+        return [(v >> (8 * k)) & 0xFF for k in range(4)]
 
     def access(row, base, reg, clk, value, prev_value=None):
         """MemoryAccessCols::populate_access (memory/consistency/trace.rs:69-105) at columns base.."""
         ps, pc_ = last[reg]
         touched.add(reg)
         compare = ps == shard
-        diff = ((clk if compare else shard) - (pc_ if compare else ps) - 1) & 0xFFFFFFFF
+        diff = ((clk if compare else shard) - (pc_ if compare else ps) - 1) & M32
         assert diff < (1 << 24)
         if prev_value is not None:
-            row[base:base + 4] = [(prev_value >> (8 * k)) & 0xFF for k in range(4)]
+            row[base:base + 4] = word(prev_value)
             base += 4
-        row[base:base + 4] = [(value >> (8 * k)) & 0xFF for k in range(4)]
+        row[base:base + 4] = word(value)
         row[base + 4:base + 9] = [ps, pc_, int(compare), diff & 0xFFFF, diff >> 16]
         last[reg] = (shard, clk)
 
+    pc, next_pc, hi_pc = pc_start, pc_start + 4, pc_start + 4
+    after_cf = False
     for i in range(real):
-        opcode = opcodes[int(rng.integers(0, len(opcodes)))]
+        what = int(rng.integers(0, 100))
+        kind = "alu" if after_cf or what < 70 else "mov" if what < 82 else "branch" if what < 92 else "jump"
+        after_cf = kind in ("branch", "jump")
         ra, rb, rc = (int(x) for x in rng.integers(1, 32, 3))
-        imm_c = opcode in (19, 20) or int(rng.integers(0, 4)) == 0
-        clk, pc = 5 * i, pc_start + 4 * i
+        clk = 5 * i
         row = cpu[i]
-        cval = (0 if opcode in (19, 20) else int(rng.integers(0, 1 << 16))) if imm_c else regs[rc]
+        nnpc = next_pc + 4
+        imm_b, is_rw_a, immutable, sequential, hi_slot = False, 0, 0, 1, 0
+        if kind == "alu":
+            opcode = alu_ops[int(rng.integers(0, len(alu_ops)))]
+            imm_c = opcode in (19, 20) or int(rng.integers(0, 4)) == 0
+            cval = (0 if opcode in (19, 20) else int(rng.integers(0, 1 << 16))) if imm_c else regs[rc]
+        elif kind == "mov":
+            opcode = (50, 51, 52)[int(rng.integers(0, 3))]             # MEQ, MNE, WSBH
+            imm_c = opcode == 52 or int(rng.integers(0, 3)) == 0       # an immediate 0 makes c == 0 a common case
+            cval = 0 if imm_c else regs[rc]
+        elif kind == "branch":
+            opcode = (21, 26, 25, 24, 23, 22)[int(rng.integers(0, 6))]  # BEQ BNE BLTZ BLEZ BGTZ BGEZ
+            imm_b = opcode not in (21, 26)                             # the compare-with-zero forms: b = 0
+            imm_c = True
+            target = max(hi_pc, next_pc) + 4 * int(rng.integers(1, 9))
+            cval = (target - next_pc) & M32
+        else:
+            opcode = (28, 29)[int(rng.integers(0, 2))]                 # Jumpi, JumpDirect
+            imm_b, imm_c, cval = True, True, 0
+            target = max(hi_pc, next_pc) + 4 * int(rng.integers(1, 9))
         if not imm_c:
             access(row, 56, rc, clk + 1, cval)
         else:
-            row[56:60] = [(cval >> (8 * k)) & 0xFF for k in range(4)]
-        bval = regs[rb]
-        access(row, 47, rb, clk + 2, bval)
-        aval = _core_op(opcode, bval, cval)
-        access(row, 34, ra, clk + 3, aval, prev_value=regs[ra])
+            row[56:60] = word(cval)
+        if kind == "jump":
+            bval = target if opcode == 28 else (target - next_pc) & M32
+        elif imm_b:
+            bval = 0
+        else:
+            if kind == "branch" and int(rng.integers(0, 3)) == 0:
+                rb = ra                                                # equal operands: BEQ taken / BNE not taken
+            bval = regs[rb]
+        if not imm_b:
+            access(row, 47, rb, clk + 2, bval)
+        else:
+            row[47:51] = word(bval)
+        prev_a = regs[ra]
+        if kind == "alu":
+            aval = _core_op(opcode, bval, cval)
+            events[_CORE_OPS[opcode]].append((pc, opcode, aval, bval, cval, next_pc))
+            if opcode in (19, 20):
+                # CloClz's dependency (alu/clo_clz eval: send_alu(SRL, sr1, bb, 31 - a) unless bb = 0) at UNUSED_PC
+                bb = bval if opcode == 19 else M32 - bval
+                if bb:
+                    events["ShiftRight"].append((1, 10, bb >> (31 - aval), bb, 31 - aval, 5))
+        elif kind == "mov":
+            if opcode == 52:
+                aval = ((bval & 0x00FF00FF) << 8) | ((bval & 0xFF00FF00) >> 8)
+            else:
+                take = (cval == 0) == (opcode == 50)
+                aval = bval if take else prev_a
+                is_rw_a, hi_slot = 1, prev_a
+            mov_events.append((pc, next_pc, opcode, aval, bval, cval, hi_slot))
+        elif kind == "branch":
+            aval, immutable, sequential = prev_a, 1, 0
+            sa, sb = (aval ^ 0x80000000) - 0x80000000, (bval ^ 0x80000000) - 0x80000000
+            lt, gt, eq = sa < sb, sa > sb, sa == sb
+            taken = {21: eq, 26: not eq, 25: lt, 24: lt or eq, 23: gt, 22: eq or gt}[opcode]
+            if taken:
+                nnpc = target
+                events["AddSub"].append((1, 0, target, next_pc, cval, 5))  # send_alu(ADD, target_pc, next_pc, c)
+            events["Lt"].append((1, 13, int(lt), aval, bval, 5))        # send_alu(SLT, a_lt_b, a, b)
+            events["Lt"].append((1, 13, int(gt), bval, aval, 5))        # send_alu(SLT, a_gt_b, b, a)
+            branch_events.append((pc, next_pc, nnpc, opcode, aval, bval, cval))
+        else:
+            aval, sequential, nnpc = (next_pc + 4) & M32, 0, target    # the link address goes to register ra
+            if opcode == 29:
+                events["AddSub"].append((1, 0, target, next_pc, bval, 5))  # send_alu(ADD, next_next_pc, next_pc, op_b)
+            jump_events.append((pc, next_pc, nnpc, opcode, aval, bval, cval))
+        access(row, 34, ra, clk + 3, aval, prev_value=prev_a)
         regs[ra] = aval
+        op_b_word = bval if imm_b else rb
         op_c_word = cval if imm_c else rc
         row[0], row[1], row[2] = shard, clk & 0xFFFF, clk >> 16
-        row[5], row[6], row[7] = pc, pc + 4, pc + 8
+        row[5], row[6], row[7] = pc, next_pc, nnpc
         row[8], row[9] = opcode, ra
-        row[10:14] = [rb, 0, 0, 0]
-        row[14:18] = [(op_c_word >> (8 * k)) & 0xFF for k in range(4)]
-        row[18], row[19], row[20] = 0, 0, int(imm_c)
-        row[22], row[25] = 0, 1                                        # is_rw_a = 0, is_sequential = 1
-        row[26:30] = [(aval >> (8 * k)) & 0xFF for k in range(4)]
-        row[65] = 1
-        prog[i] = [pc, opcode, ra, rb, 0, 0, 0] + [(op_c_word >> (8 * k)) & 0xFF for k in range(4)] + [0, 0, int(imm_c)]
-        events[_CORE_OPS[opcode]].append((pc, opcode, aval, bval, cval))
-        if opcode in (19, 20):
-            # CloClzChip's dependency (alu/clo_clz/mod.rs eval: send_alu(SRL, sr1, bb, 31 - a) unless bb = 0): an extra SRL
-            # event at UNUSED_PC for the shift-right chip, as the executor's generate_dependencies adds it
-            bb = bval if opcode == 19 else 0xFFFFFFFF - bval
-            if bb:
-                events["ShiftRight"].append((1, 10, bb >> (31 - aval), bb, 31 - aval))
+        row[10:14], row[14:18] = word(op_b_word), word(op_c_word)
+        row[18], row[19], row[20] = 0, int(imm_b), int(imm_c)
+        row[22], row[25] = is_rw_a, sequential
+        row[26:30], row[30:34] = word(aval), word(hi_slot)
+        row[65], row[66] = 1, immutable
+        prog[i] = [pc, opcode, ra] + word(op_b_word) + word(op_c_word) + [0, int(imm_b), int(imm_c)]
+        hi_pc = max(hi_pc, pc, next_pc, nnpc)
+        pc, next_pc = next_pc, nnpc
+    final_next_pc = pc                                                 # the last executed row's next_pc
 
     def pow2(k):
         return max(2, (max(k, 1) - 1).bit_length())
@@ -1389,28 +1459,36 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     fillers = {"AddSub": add_sub_rows, "Bitwise": bitwise_rows, "Lt": lt_rows, "ShiftLeft": shift_left_rows,
                "ShiftRight": shift_right_rows, "CloClz": clo_clz_rows}
     for name in ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Mul"):
-        e = np.array(events[name], np.uint64).reshape(-1, 5)
+        e = np.array(events[name], np.uint64).reshape(-1, 6)          # pc, opcode, a, b, c, next_pc
         h = 1 << pow2(len(e))
         if name == "Mul":                                              # MUL: no HI write, shard = clk = 0
             ev = np.zeros((len(e), 13), np.uint64)
-            ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 4], ev[:, 5], ev[:, 6] = e[:, 0], e[:, 0] + 4, e[:, 1], e[:, 2], e[:, 3], e[:, 4]
+            ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 4], ev[:, 5], ev[:, 6] = e[:, 0], e[:, 5], e[:, 1], e[:, 2], e[:, 3], e[:, 4]
             t = mul_rows(ev, h)
         else:
-            t = fillers[name](_alu_event_array(e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4]), h)
+            ev = _alu_event_array(e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4])
+            ev[:, 1] = e[:, 5]                                         # the delay slot of a taken branch: next_pc = target
+            t = fillers[name](ev, h)
         c = Chip(name, name, M(t), local_only=_air(name).local_only)
+        c.canon = (None, t)
+        chips.append(c)
+    for name, evs, rows_of in (("MovCond", mov_events, mov_cond_rows), ("Jump", jump_events, jump_rows),
+                               ("Branch", branch_events, branch_rows)):
+        e = np.array(evs, np.uint64).reshape(-1, 7)
+        t = rows_of(e, 1 << pow2(len(e)))
+        c = Chip(name, name, M(t), local_only=True)
         c.canon = (None, t)
         chips.append(c)
     regs_used = sorted(touched)
     rows_m = 1 << pow2(-(-len(regs_used) // 4))
     ml = np.zeros((4 * rows_m, 14), np.uint64)
     for k, r in enumerate(regs_used):
-        ml[k] = [r, 0, last[r][0], 0, last[r][1]] + [(initial[r] >> (8 * j)) & 0xFF for j in range(4)] \
-            + [(regs[r] >> (8 * j)) & 0xFF for j in range(4)] + [1]
+        ml[k] = [r, 0, last[r][0], 0, last[r][1]] + word(initial[r]) + word(regs[r]) + [1]
     ml = ml.reshape(rows_m, 56)
     c = Chip("MemoryLocal", "MemoryLocal", M(ml))
     c.canon = (None, ml)
     chips.append(c)
     chips.append(byte_chip_for([ch for ch in chips if ch.air != "Program"]))
-    pvs = {40: pc_start, 41: pc_start + 4 * real, 44: shard}
+    pvs = {40: pc_start, 41: final_next_pc, 44: shard}
     chips[0].core_pvs = pvs
     return chips, pvs
