@@ -21,7 +21,7 @@ def test_exported_json_reproduces_the_generated_kernels():
                  library.public_values_chip, library.fri_fold, library.poseidon2_skinny, library.mov_cond, library.jump,
                  library.branch, library.shift_left, library.clo_clz, library.byte_chip, library.program_chip,
                  lambda: library.syscall_chip("Core"), lambda: library.syscall_chip("Precompile"), library.memory_local,
-                 library.shift_right, library.mul, library.cpu):
+                 library.shift_right, library.mul, library.cpu, library.div_rem):
         air = make()
         text = open(os.path.join(EXPORTED, air.name + ".json")).read()
         assert json.loads(text) == json.loads(air.to_json()), f"{air.name}.json is stale: run tools/export_airs.py"
@@ -37,9 +37,9 @@ def test_real_chip_shapes_match_mips_costs():
     counts as StarkMachine::setup computes them (own + count_permutation_constraints, permutation.rs:355-388)."""
     want = {"AddSub": (19, 47, 14, 8), "Lt": (36, 56, 32, 4), "Bitwise": (18, 42, 5, 5), "MovCond": (32, 48, 43, 1),
             "Jump": (66, 82, 60, 2), "Branch": (62, 90, 60, 8), "ShiftLeft": (44, 68, 64, 5), "CloClz": (22, 46, 20, 5),
-            "ShiftRight": (71, 135, 83, 26), "Mul": (58, 110, 41, 19)}
+            "ShiftRight": (71, 135, 83, 26), "Mul": (58, 110, 41, 19), "DivRem": (106, 162, 126, 21)}
     for make in (library.add_sub, library.lt, library.bitwise, library.mov_cond, library.jump, library.branch,
-                 library.shift_left, library.clo_clz, library.shift_right, library.mul):
+                 library.shift_left, library.clo_clz, library.shift_right, library.mul, library.div_rem):
         air = make()
         width, cost, own, n_lookups = want[air.name]
         assert air.main_width == width
@@ -112,7 +112,8 @@ def test_alu_airs_vanish_on_their_fillers_rows():
                                (library.shift_left, synth.shift_left_events, synth.shift_left_rows),
                                (library.clo_clz, synth.clo_clz_events, synth.clo_clz_rows),
                                (library.shift_right, synth.shift_right_events, synth.shift_right_rows),
-                               (library.mul, synth.mul_events, synth.mul_rows)):
+                               (library.mul, synth.mul_events, synth.mul_rows),
+                               (library.div_rem, synth.div_rem_events, synth.div_rem_rows)):
         ev, n = events(5)
         vals = _constraints_on_trace(make(), rows(ev, n))
         assert all(not v.any() for v in vals), make.__name__
@@ -123,7 +124,8 @@ def test_alu_airs_vanish_on_their_fillers_rows():
                                      (library.shift_left, synth.shift_left_events, synth.shift_left_rows, (2, 35)),
                                      (library.clo_clz, synth.clo_clz_events, synth.clo_clz_rows, (2, 15)),
                                      (library.shift_right, synth.shift_right_events, synth.shift_right_rows, (3, 43)),
-                                     (library.mul, synth.mul_events, synth.mul_rows, (2, 20))):
+                                     (library.mul, synth.mul_events, synth.mul_rows, (2, 20)),
+                                     (library.div_rem, synth.div_rem_events, synth.div_rem_rows, (2, 38))):
         ev, n = events(5)
         bad = rows(ev, n)
         bad[cell] = (bad[cell] + 1) % ae_P
@@ -209,7 +211,7 @@ def test_compress_machine_chips_satisfy_their_airs():
 
 def test_byte_chip_answers_the_core_chips_byte_lookups():
     """ByteChip (bytes/air.rs:22-74: 12 preprocessed + 10 multiplicity columns, ten receives, cost 54) with the
-    multiplicities ByteChip::generate_trace would count (synth.byte_chip_for: every byte lookup the ten transcribed core
+    multiplicities ByteChip::generate_trace would count (synth.byte_chip_for: every byte lookup the eleven transcribed core
     chips send is looked up in the table and CHECKED against it).  The byte bus then balances: with the lookups of the
     other kinds removed, the LogUp cumulative sums of the nine chips add up to zero for random challenges -- and no
     longer do when one multiplicity is off by one."""
@@ -218,7 +220,7 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
     from zkmips_b200 import synth
     chips = [synth.add_sub_chip(6), synth.lt_chip(6), synth.bitwise_chip(5), synth.mov_cond_chip(5), synth.jump_chip(5),
              synth.branch_chip(6), synth.shift_left_chip(5), synth.clo_clz_chip(5), synth.shift_right_chip(6),
-             synth.mul_chip(6)]
+             synth.mul_chip(6), synth.div_rem_chip(6)]
     byte = synth.byte_chip_for(chips)
     air = library.byte_chip()
     assert (air.main_width, air.prep_width, len(air.sends), len(air.receives), air.num_constraints) == (10, 12, 0, 10, 5 + 3)
@@ -250,7 +252,7 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
         for ch in all_chips:
             only = copy.copy({a.name: a for a in [getattr(library, f)() for f in
                                                   ("add_sub", "lt", "bitwise", "mov_cond", "jump", "branch", "shift_left",
-                                                   "clo_clz", "shift_right", "mul", "byte_chip")]}[ch.air])
+                                                   "clo_clz", "shift_right", "mul", "div_rem", "byte_chip")]}[ch.air])
             only.sends = [l for l in only.sends if l["kind"] == 4]
             only.receives = [l for l in only.receives if l["kind"] == 4]
             _, lcs = logup.generate_permutation_trace(only, ch.canon[0], ch.canon[1], alpha, beta)

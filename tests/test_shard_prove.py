@@ -40,7 +40,7 @@ COMPRESS_SMALL = dict(log_var=7, log_ext=4, log_sel=5, log_bf=5, log_exp=5, pv=T
 @pytest.mark.parametrize("be", BACKENDS)
 @pytest.mark.parametrize("which", ["fibonacci", "wide", "lookup", "wide1024", "wide4096", "global", "local_bool", "AddSub",
                                    "Lt", "Bitwise", "Poseidon2WideDeg3", "Poseidon2WideDeg9", "MemoryConst", "BaseAlu",
-                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile", "MemoryLocal", "ShiftRight", "Mul", "Cpu"])
+                                   "MemoryVar", "ExtAlu", "Select", "BatchFRI", "ExpReverseBitsLen", "PublicValues", "FriFold", "Poseidon2SkinnyDeg9", "MovCond", "Jump", "Branch", "ShiftLeft", "CloClz", "Byte", "Program", "SyscallCore", "SyscallPrecompile", "MemoryLocal", "ShiftRight", "Mul", "Cpu", "DivRem"])
 def test_quotient_values_match_oracle(be, which):
     """`wide1024` (2^10 rows) and `wide4096` (2^8 rows) are the chips bench.py's shard-prove legs time: their
     constraint programs are cut into several kernels (codegen parts of <= 1500 nodes) that ACCUMULATE into the
@@ -79,7 +79,8 @@ def test_quotient_values_match_oracle(be, which):
             "Program": lambda: synth.program_chip(6), "SyscallCore": lambda: synth.syscall_chip(5, "Core"),
             "SyscallPrecompile": lambda: synth.syscall_chip(4, "Precompile"),
             "MemoryLocal": lambda: synth.memory_local_chip(4), "ShiftRight": lambda: synth.shift_right_chip(6),
-            "Mul": lambda: synth.mul_chip(6), "Cpu": lambda: synth.core_program_chips(6)[0][0]}[which]()
+            "Mul": lambda: synth.mul_chip(6), "Cpu": lambda: synth.core_program_chips(6)[0][0],
+            "DivRem": lambda: synth.div_rem_chip(6)}[which]()
     lqd = chip.log_quotient_degree
     if which in ("wide1024", "wide4096"):
         assert ctx.air_info(chip.air)["num_kernels"] > 1, "this case must exercise the multi-part accumulate path"
@@ -243,13 +244,13 @@ def test_real_alu_chips_shard(be):
     chips = [synth.add_sub_chip(logs[0]), synth.lt_chip(logs[1]), synth.bitwise_chip(logs[2]),
              synth.mov_cond_chip(logs[2]), synth.jump_chip(logs[2] - 1), synth.branch_chip(logs[1]),
              synth.shift_left_chip(logs[1] - 1), synth.clo_clz_chip(logs[2]), synth.shift_right_chip(logs[2]),
-             synth.mul_chip(logs[2])]
+             synth.mul_chip(logs[2]), synth.div_rem_chip(logs[2] - 1)]
     if be != "emu":
         chips.append(synth.byte_chip_for(chips))          # the 2^16-row Byte table answering their byte lookups (GPU only: size)
     for c in chips:
         air = su.AIRS[c.air]
         assert c.main.shape[1] + 4 * air.perm_width + 8 == {"AddSub": 47, "Lt": 56, "Bitwise": 42, "MovCond": 48, "Jump": 82,
-                                                            "Branch": 90, "ShiftLeft": 68, "CloClz": 46, "ShiftRight": 135, "Mul": 110, "Byte": 54 - 12}[c.air]  # mips_costs.json
+                                                            "Branch": 90, "ShiftLeft": 68, "CloClz": 46, "ShiftRight": 135, "Mul": 110, "DivRem": 162, "Byte": 54 - 12}[c.air]  # mips_costs.json
     prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw)
     ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], NUM_PV, 1, nq, pw)
     assert not ok and why.endswith("local cumulative sum is not zero"), why

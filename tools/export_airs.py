@@ -19,7 +19,8 @@ for air in (library.add_sub(), library.lt(), library.bitwise(), library.poseidon
             library.poseidon2_skinny(9), library.mov_cond(), library.jump(), library.branch(), library.shift_left(),
             library.clo_clz(), library.byte_chip(), library.program_chip(),
             library.syscall_chip("Core"), library.syscall_chip("Precompile"), library.memory_local(),
-            library.shift_right(), library.mul(), library.cpu()):
+            library.shift_right(), library.mul(), library.cpu(),
+            library.div_rem()):
     with open(os.path.join(OUT, air.name + ".json"), "w") as fh:
         fh.write(air.to_json() + "\n")
     print(air.name, air.num_constraints, "constraints,", len(air.nodes), "nodes")

@@ -1202,6 +1202,98 @@ def mul():
     return air
 
 
+OP_DIV, OP_DIVU, OP_MOD, OP_MODU = 5, 6, 7, 8                          # Opcode, executor/src/opcode.rs:22-25
+
+
+def _send_alu_with_hi(b, opcode, a, bb, c, hi, mult):
+    """ZKMAirBuilder::send_alu_with_hi (stark/src/air/builder.rs:295-324)"""
+    b.send(LOOKUP_INSTRUCTION, [0, 0, UNUSED_PC, UNUSED_PC + DEFAULT_PC_INC, UNUSED_PC + 2 * DEFAULT_PC_INC, 0, opcode]
+           + list(a) + list(bb) + list(c) + list(hi) + [0, 0, 0, 0, 1], mult)
+
+
+def div_rem():
+    """DivRemChip (crates/core/machine/src/alu/divrem/mod.rs:38-93 columns, :375-750 eval): DIV / DIVU (quotient to op_a,
+    remainder to HI through eval_memory_access) and MOD / MODU (remainder to op_a).  b = c * quotient + remainder is checked
+    on 8 bytes with carries, c * quotient comes from the Mul chip (send_alu_with_hi MULT / MULTU), |remainder| < max(|c|, 1)
+    from the Lt chip (SLTU), the absolute values from the AddSub chip (0 = x + |x| for negative x); division by zero gives
+    quotient 0xFFFFFFFF, i32::MIN / -1 is the overflow case.  106 main columns; 126 constraints; 21 lookups; `local_only`.
+    mips_costs.json: 106 + 4 * 12 + 8 = 162."""
+    air = Air("DivRem", main_width=106, local_only=True)
+    b = AirBuilder(air)
+    m = b.main().local()
+    pc, next_pc = m[0], m[1]
+    bv, cv, quotient, remainder = m[2:6], m[6:10], m[10:14], m[14:18]
+    abs_rem, abs_c, max_abs = m[18:22], m[22:26], m[26:30]
+    ctq, carry = m[30:38], m[38:46]
+    is_c_0 = m[46:57]
+    is_div, is_divu, is_mod, is_modu, is_overflow = m[57:62]
+    ovf_b, ovf_c = m[62:73], m[73:84]
+    b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg = m[84:90]
+    rcm, hi_access, shard, clk = m[90], m[91:104], m[104], m[105]
+    is_real = is_div + is_divu + is_mod + is_modu
+    signed = is_div + is_mod
+    for msb, neg in ((b_msb, b_neg), (rem_msb, rem_neg), (c_msb, c_neg)):
+        b.assert_eq(msb * signed, neg)
+    _send_alu_with_hi(b, signed * OP_MULT + (is_divu + is_modu) * OP_MULTU, ctq[0:4], quotient, cv, ctq[4:8], is_real)
+    # IsEqualWordOperation::eval (operations/is_equal_word.rs:32-50) against i32::MIN and -1
+    for word, const, cols in ((bv, (0, 0, 0, 0x80), ovf_b), (cv, (0xFF, 0xFF, 0xFF, 0xFF), ovf_c)):
+        b.assert_bool(is_real)
+        _is_zero_word_operation(b, [x - k for x, k in zip(word, const)], cols, is_real)
+    b.assert_eq(is_overflow, ovf_b[10] * ovf_c[10] * signed)
+    sign_extension = rem_neg * 0xFF
+    cqr = []
+    for i in range(8):
+        v = ctq[i] + (remainder[i] if i < 4 else sign_extension) - carry[i] * 256
+        if i > 0:
+            v = v + carry[i - 1]
+        cqr.append(v)
+    not_overflow = 1 - is_overflow
+    for i in range(8):
+        if i < 4:
+            b.assert_eq(bv[i], cqr[i])
+        else:
+            b.when(not_overflow).when(b_neg).assert_eq(cqr[i], 0xFF)
+            b.when(not_overflow).when(1 - b_neg).assert_zero(cqr[i])
+            b.when(is_overflow).assert_zero(cqr[i])
+    rem_byte_sum = remainder[0] + remainder[1] + remainder[2] + remainder[3]
+    b.when(rem_neg).assert_one(b_neg)
+    b.when(rem_byte_sum).when(1 - rem_neg).assert_zero(b_neg)
+    _is_zero_word_operation(b, cv, is_c_0, is_real)
+    c_zero = is_c_0[10]
+    for i in range(4):
+        b.when(c_zero).assert_eq(quotient[i], 0xFF)
+    for i in range(4):
+        b.when_not(c_neg).assert_eq(cv[i], abs_c[i])
+        b.when_not(rem_neg).assert_eq(remainder[i], abs_rem[i])
+    _send_alu(b, OP_ADD, [0, 0, 0, 0], cv, abs_c, c_neg)
+    _send_alu(b, OP_ADD, [0, 0, 0, 0], remainder, abs_rem, rem_neg)
+    want = [c_zero * 1 + (1 - c_zero) * abs_c[0]] + [(1 - c_zero) * abs_c[i] for i in range(1, 4)]
+    for i in range(4):
+        b.when(is_real).assert_eq(max_abs[i], want[i])
+    b.assert_eq((1 - c_zero) * is_real, rcm)
+    _send_alu(b, OP_SLTU, [1, 0, 0, 0], abs_rem, max_abs, rcm)
+    for msb, byte in ((b_msb, bv[3]), (c_msb, cv[3]), (rem_msb, remainder[3])):
+        _send_byte(b, BYTE_MSB, msb, byte, 0, is_real)
+    _slice_range_check_u8(b, quotient, is_real)
+    _slice_range_check_u8(b, remainder, is_real)
+    for x in carry:
+        b.assert_bool(x)
+    _slice_range_check_u8(b, ctq, is_real)
+    for f in (is_div, is_divu, is_mod, is_modu, is_overflow, b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg):
+        b.assert_bool(f)
+    b.when(is_real).assert_eq(1, is_divu + is_div + is_mod + is_modu)
+    opcode = is_divu * OP_DIVU + is_div * OP_DIV + is_mod * OP_MOD + is_modu * OP_MODU
+    b.receive(LOOKUP_INSTRUCTION, [shard, clk, pc, next_pc, next_pc + 4, 0, opcode] + list(quotient) + list(bv) + list(cv)
+              + list(remainder) + [0, 0, 1, 0, 1], is_div + is_divu)
+    b.receive(LOOKUP_INSTRUCTION, [0, 0, pc, next_pc, next_pc + 4, 0, opcode] + list(remainder) + list(bv) + list(cv)
+              + [0, 0, 0, 0] + [0, 0, 0, 0, 1], is_mod + is_modu)
+    _eval_memory_access(b, shard, clk + MEM_POS_HI, REG_HI, hi_access, is_div + is_divu)
+    for l, r in zip(remainder, hi_access[4:8]):
+        b.when(is_div + is_divu).assert_eq(l, r)
+    b.eval_permutation_constraints(batch_size=2)
+    return air
+
+
 MEM_POS_C, MEM_POS_B, MEM_POS_A = 1, 2, 3                              # MemoryAccessPosition, executor/src/events/memory.rs:29-40
 PV_START_PC, PV_NEXT_PC, PV_EXECUTION_SHARD = 40, 41, 44               # PublicValues<Word<T>, T>, stark/src/air/public_values.rs:17-46
 CORE_NUM_PV_ELTS = 231                                                  # PROOF_MAX_NUM_PVS
@@ -1299,4 +1391,4 @@ def all_airs():
             wide_bitwise(4096, "wide_bitwise_4096"), quintic(), lookup_side(True), lookup_side(False), global_tail(),
             local_bool(), add_sub(), lt(), bitwise(), poseidon2_wide(3), poseidon2_wide(9), memory_const(), base_alu(), memory_var(), ext_alu(), select(),
             batch_fri(3), exp_reverse_bits_len(3), public_values_chip(), fri_fold(3), poseidon2_skinny(9), mov_cond(), jump(), branch(), shift_left(), clo_clz(), byte_chip(), program_chip(), syscall_chip("Core"),
-            syscall_chip("Precompile"), memory_local(), shift_right(), mul(), cpu()]
+            syscall_chip("Precompile"), memory_local(), shift_right(), mul(), cpu(), div_rem()]

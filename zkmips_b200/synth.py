@@ -833,6 +833,106 @@ def mul_chip(log_n, seed=33, fill=0.75, name="Mul"):
     return ch
 
 
+def _quotient_remainder(b, c, signed):
+    """get_quotient_and_remainder (crates/core/executor/src/utils.rs:33-43): c = 0 gives (0xFFFFFFFF, b); signed division
+    truncates toward zero and wraps on i32::MIN / -1"""
+    M32 = 0xFFFFFFFF
+    if c == 0:
+        return M32, b
+    if not signed:
+        return b // c, b % c
+    sb, sc = (b ^ 0x80000000) - 0x80000000, (c ^ 0x80000000) - 0x80000000
+    q = abs(sb) // abs(sc)
+    if (sb < 0) != (sc < 0):
+        q = -q
+    r = sb - q * sc
+    return q & M32, r & M32
+
+
+def div_rem_events(log_n, seed=34, fill=0.75):
+    """random DIV / DIVU / MOD / MODU events, including division by zero, i32::MIN / -1, small divisors and negative
+    operands: columns pc, next_pc, opcode, b, c, shard, clk, prev_hi, prev_shard, prev_clk (the HI register's write record
+    of DIV / DIVU; zero for MOD / MODU)"""
+    n, real, rng, pc, b, c = _events(log_n, seed, fill)
+    pick = rng.integers(0, 8, real)
+    c = np.where(pick == 0, 0, np.where(pick == 1, c & np.uint64(0xFF), np.where(pick == 2, np.uint64(0xFFFFFFFF), c)))
+    b = np.where(pick == 2, np.where(rng.integers(0, 2, real) == 0, np.uint64(0x80000000), b), b)
+    op = rng.integers(0, 4, real)                                                  # DIV 5, DIVU 6, MOD 7, MODU 8
+    has_hi = op < 2
+    shard = np.where(has_hi, 3, 0)
+    clk = np.where(has_hi, 24 + 5 * np.arange(real), 0)
+    same = rng.integers(0, 2, real) == 1
+    prev_shard = np.where(has_hi, np.where(same, 3, rng.integers(0, 3, real)), 0)
+    prev_clk = np.where(has_hi, np.where(same, clk - rng.integers(0, 20, real), rng.integers(0, 1 << 20, real)), 0)
+    prev_hi = np.where(has_hi, rng.integers(0, 1 << 32, real, dtype=np.uint64), 0)
+    ev = np.stack([pc, (pc + 4) % P, 5 + op, b, c, shard, clk, prev_hi, prev_shard, prev_clk], axis=1)
+    return ev.astype(np.uint64), n
+
+
+def div_rem_rows(events, n):
+    """DivRemChip::generate_trace (alu/divrem/mod.rs:112-340); padding rows are zero"""
+    ev = np.asarray(events, np.uint64)
+    real = len(ev)
+    t = np.zeros((n, 106), np.uint64)
+    M32 = 0xFFFFFFFF
+
+    def word(v):
+        return [(int(v) >> (8 * k)) & 0xFF for k in range(4)]
+
+    def is_zero_word(vals):                                            # IsZeroWordOperation::populate_from_field_element
+        inv = [pow(int(x), P - 2, P) if x else 0 for x in vals]
+        z = [int(x == 0) for x in vals]
+        out = []
+        for i in range(4):
+            out += [inv[i], z[i]]
+        return out + [z[0] * z[1], z[2] * z[3], int(all(z))]
+    for r in range(real):
+        pc, next_pc, opc, b, c, shard, clk, prev_hi, prev_shard, prev_clk = (int(x) for x in ev[r])
+        signed = opc in (5, 7)
+        q, rem = _quotient_remainder(b, c, signed)
+        row = t[r]
+        row[0], row[1] = pc, next_pc
+        row[2:6], row[6:10], row[10:14], row[14:18] = word(b), word(c), word(q), word(rem)
+        sc, srem = (c ^ 0x80000000) - 0x80000000, (rem ^ 0x80000000) - 0x80000000
+        abs_rem, abs_c = (abs(srem) & M32, abs(sc) & M32) if signed else (rem, c)
+        row[18:22], row[22:26], row[26:30] = word(abs_rem), word(abs_c), word(max(1, abs_c))
+        sq = (q ^ 0x80000000) - 0x80000000
+        ctq = ((sq * sc) if signed else (q * c)) & 0xFFFFFFFFFFFFFFFF
+        ctq_b = [(ctq >> (8 * k)) & 0xFF for k in range(8)]
+        rem64 = (srem if signed else rem) & 0xFFFFFFFFFFFFFFFF
+        rem_b = [(rem64 >> (8 * k)) & 0xFF for k in range(8)]
+        carry = 0
+        for i in range(8):
+            carry = (ctq_b[i] + rem_b[i] + carry) >> 8
+            row[38 + i] = carry
+        row[30:38] = ctq_b
+        row[46:57] = is_zero_word(word(c))
+        row[57], row[58], row[59], row[60] = opc == 5, opc == 6, opc == 7, opc == 8
+        row[61] = signed and b == 0x80000000 and c == M32
+        row[62:73] = is_zero_word([(x - k) % P for x, k in zip(word(b), (0, 0, 0, 0x80))])
+        row[73:84] = is_zero_word([(x - 0xFF) % P for x in word(c)])
+        b_msb, rem_msb, c_msb = b >> 31, rem >> 31, c >> 31
+        row[84], row[85], row[86] = b_msb, rem_msb, c_msb
+        if signed:
+            row[87], row[88], row[89] = b_msb, rem_msb, c_msb
+        row[90] = int(c != 0)
+        if opc in (5, 6):
+            compare = prev_shard == shard
+            diff = ((clk + 4 if compare else shard) - (prev_clk if compare else prev_shard) - 1) & M32
+            row[91:95], row[95:99] = word(prev_hi), word(rem)
+            row[99:104] = [prev_shard, prev_clk, int(compare), diff & 0xFFFF, (diff >> 16) & 0xFF]
+            row[104], row[105] = shard, clk
+    return t
+
+
+def div_rem_chip(log_n, seed=34, fill=0.75, name="DivRem"):
+    ev, n = div_rem_events(log_n, seed, fill)
+    t = div_rem_rows(ev, n)
+    ch = Chip(name, "DivRem", M(t), local_only=True)
+    ch.canon, ch.events = (None, t), ev
+    return ch
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Recursion chip Poseidon2WideDeg3 / Deg9 (library.poseidon2_wide): random permutation inputs and memory addresses.
 # The main trace is ALWAYS produced on the device from the 16-word inputs (zk_tracegen_poseidon2_wide); the
