@@ -333,9 +333,9 @@ def shard_chips(config, rank=0, scale=0):
     core  : FOURTEEN real MipsAir chips (AddSub, Lt, Bitwise, ShiftLeft, ShiftRight, CloClz filled on the device from
             AluEvents; Branch, Jump, MovCond, MemoryLocal, SyscallCore, Program and the Byte table from host rows) at the
             proportions of a log-19 execution shard, 67 M cells;
-    program: a toy core-machine program of 2^17 * 0.9 instructions (ALU, conditional moves, branches, jumps) executed in
-            Python, on FOURTEEN real chips that interlock (Cpu 2^17 x 67, Program, AddSub, Bitwise, Lt, ShiftLeft,
-            ShiftRight, CloClz, Mul, MovCond, Jump, Branch, MemoryLocal, Byte): the CPU's instruction, program, memory and
+    program: a toy core-machine program of 2^17 * 0.9 instructions (ALU, MULT / DIV / MOD with HI, conditional moves,
+            branches, jumps) executed in Python, on FIFTEEN real chips that interlock (Cpu 2^17 x 67, Program, AddSub,
+            Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, DivRem, MovCond, Jump, Branch, MemoryLocal, Byte): the CPU's instruction, program, memory and
             byte lookups are all answered in the shard;
     recursion: the chip heights of the FASTEST compress shape (crates/recursion/core/src/shape.rs:135-146: 2^18, 2^18,
             2^16, 2^17, 2^15, 2^15, 2^17, 2^16, 2^4) under the compress FRI configuration (blowup 4, 42 queries).
@@ -354,7 +354,7 @@ def shard_chips(config, rank=0, scale=0):
         return [synth.wide_chip(19 - d, 1024, seed=11 + rank), synth.wide_chip(21 - d, 64, seed=12 + rank),
                 synth.fibonacci_chip(21 - d, 1 + rank, 1), send, recv]
     if config == "program":
-        # a toy core-machine PROGRAM executed in Python (synth.core_program_chips): Cpu, Program, seven ALU chips, MovCond,
+        # a toy core-machine PROGRAM executed in Python (synth.core_program_chips): Cpu, Program, eight ALU chips, MovCond,
         # Jump, Branch, MemoryLocal and Byte whose memory / program / instruction / byte buses cancel across the shard
         return synth.core_program_chips(17 - d, seed=51 + rank)[0]
     if config == "core":

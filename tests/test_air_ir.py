@@ -266,27 +266,29 @@ def test_byte_chip_answers_the_core_chips_byte_lookups():
 
 def test_core_program_chips_interlock():
     """A toy core-machine program (synth.core_program_chips: ALU instructions, conditional moves, branches with their delay
-    slots and jumps over registers 1..31, executed in Python) on FOURTEEN real chips: Cpu (cpu/air/mod.rs: 67 columns, 57
-    constraints, 19 lookups, cost 119), Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, MovCond, Jump,
-    Branch, MemoryLocal and Byte.  Every constraint of every chip vanishes on the rows, and the chips interlock as in the
+    slots, jumps, and MULT / DIV / MOD with the HI register over registers 1..31, executed in Python) on FIFTEEN real chips:
+    Cpu (cpu/air/mod.rs: 67 columns, 57 constraints, 19 lookups, cost 119), Program, AddSub, Bitwise, Lt, ShiftLeft,
+    ShiftRight, CloClz, Mul, DivRem, MovCond, Jump, Branch, MemoryLocal and Byte.  Every constraint of every chip vanishes on the rows, and the chips interlock as in the
     reference's machine: taken kind by kind, the LogUp sums of the MEMORY bus (register accesses chained from
     MemoryLocal's initial to its final state), the PROGRAM bus (instruction fetches), the INSTRUCTION bus (CPU -> the chip
-    implementing the opcode, plus the chips' own dependencies: CloClz's SRL on ShiftRight, Branch's two SLT on Lt and its
-    target ADD on AddSub, JumpDirect's ADD) and the BYTE bus cancel across the shard; only MemoryLocal's Global-kind
+    implementing the opcode, with shard and clk for the instructions that write HI, plus the chips' own dependencies:
+    CloClz's SRL on ShiftRight, Branch's two SLT on Lt and its target ADD on AddSub, JumpDirect's ADD, DivRem's product
+    on Mul, its absolute values on AddSub and its remainder check on Lt) and the BYTE bus cancel across the shard; only MemoryLocal's Global-kind
     forwards have no partner (the Global chip is not transcribed)."""
     import copy
     from oracle import logup
     from zkmips_b200 import synth
-    chips, pv_of = synth.core_program_chips(8)
+    chips, pv_of = synth.core_program_chips(9)
     assert [c.air for c in chips] == ["Cpu", "Program", "AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Mul",
-                                      "MovCond", "Jump", "Branch", "MemoryLocal", "Byte"]
+                                      "DivRem", "MovCond", "Jump", "Branch", "MemoryLocal", "Byte"]
     airs = {a.name: a for a in (library.cpu(), library.program_chip(), library.add_sub(), library.bitwise(), library.lt(),
                                 library.shift_left(), library.shift_right(), library.clo_clz(), library.mul(),
-                                library.mov_cond(), library.jump(), library.branch(), library.memory_local(),
-                                library.byte_chip())}
-    branch = chips[11].canon[1]
+                                library.div_rem(), library.mov_cond(), library.jump(), library.branch(),
+                                library.memory_local(), library.byte_chip())}
+    branch = chips[12].canon[1]
     assert 0 < branch[:, 59].sum() < branch[:, 53:59].sum()            # taken and not-taken branches both occur
     assert chips[0].canon[1][:, 22].sum() > 0 and (chips[0].canon[1][:, 25] == 0).sum() > 0   # is_rw_a rows, non-sequential rows
+    assert chips[0].canon[1][:, 23].sum() > 0 and chips[9].canon[1][:, 57:61].sum() > 0       # is_check_memory rows, divisions
     cpu = airs["Cpu"]
     assert (cpu.main_width, len(cpu.sends), len(cpu.receives), cpu.num_constraints) == (67, 16, 3, 57 + 10 + 3)
     assert cpu.main_width + 4 * cpu.perm_width + 8 == 119 and not cpu.local_only and cpu.uses_next_row()

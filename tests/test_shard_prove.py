@@ -444,8 +444,8 @@ def test_poseidon2_skinny_program_shard_verifies_completely(be):
 
 @pytest.mark.parametrize("be", BACKENDS)
 def test_core_program_shard(be):
-    """The toy core-machine program on fourteen real chips -- Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
-    CloClz, Mul, MovCond, Jump, Branch, MemoryLocal, Byte (GPU only: 2^16 rows) -- with the core machine's 231 public values (start_pc, next_pc,
+    """The toy core-machine program on fifteen real chips -- Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
+    CloClz, Mul, DivRem, MovCond, Jump, Branch, MemoryLocal, Byte (GPU only: 2^16 rows) -- with the core machine's 231 public values (start_pc, next_pc,
     execution_shard constrained by the CPU chip): the proof is byte-identical with the CPU prover's and every per-chip
     check of the verifier passes; the memory, program, instruction and byte buses cancel (tests/test_air_ir.py), so what
     is left in the shard's cumulative sum are MemoryLocal's Global-kind forwards."""
@@ -454,7 +454,7 @@ def test_core_program_shard(be):
     from zkmips_b200 import proof as pf
     ctx = _backend(be)
     nq, pw = (6, 4) if be == "emu" else (84, 16)
-    chips, _ = synth.core_program_chips(6 if be == "emu" else 12)
+    chips, _ = synth.core_program_chips(7 if be == "emu" else 12)
     if be == "emu":
         chips = chips[:-1]
     npv = 231

@@ -1411,17 +1411,20 @@ def _core_op(opcode, b, c):
 
 
 def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
-    """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, MovCond, Jump, Branch, MemoryLocal,
-    Byte], public values (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU
-    rows.  About 70 % of the instructions are ALU operations, the rest conditional moves (MEQ / MNE / WSBH), branches
+    """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, DivRem, MovCond, Jump, Branch,
+    MemoryLocal, Byte], public values (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU
+    rows.  About 60 % of the instructions are simple ALU operations, 8 % MULT / MULTU / DIV / DIVU / MOD / MODU (the HI
+    register is written through the ALU chip's own memory access at clk + 4, and the CPU sends shard and clk along:
+    is_check_memory), the rest conditional moves (MEQ / MNE / WSBH), branches
     (all six, with the delay slot: next_next_pc = target when taken) and jumps (Jumpi, JumpDirect); control flow always
     goes FORWARD to fresh addresses, so every executed pc is one row of the Program table.  The chips' own dependencies
     are generated as the executor's generate_dependencies does: CloClz's SRL on ShiftRight, Branch's two SLT on Lt and
-    its target ADD on AddSub, JumpDirect's target ADD on AddSub, all at UNUSED_PC."""
+    its target ADD on AddSub, JumpDirect's target ADD on AddSub, DivRem's MULT / MULTU on Mul, its ADDs on AddSub and its
+    SLTU on Lt, all at UNUSED_PC."""
     rng = np.random.default_rng(seed)
     n = 1 << log_cpu
     real = max(2, int(n * fill))
-    regs = {r: int(rng.integers(0, 1 << 32)) for r in range(1, 32)}
+    regs = {r: int(rng.integers(0, 1 << 32)) for r in list(range(1, 32)) + [33]}   # 33: the HI register
     initial = dict(regs)
     last = {r: (0, 0) for r in regs}                                   # (shard, clk) of the previous access
     touched = set()
@@ -1430,7 +1433,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     cpu[:, 19], cpu[:, 20], cpu[:, 22] = 1, 1, 1                       # padding rows: imm_b = imm_c = is_rw_a = 1
     prog = np.zeros((n, 14), np.uint64)
     events = {name: [] for name in set(_CORE_OPS.values())}
-    mov_events, jump_events, branch_events = [], [], []
+    mov_events, jump_events, branch_events, div_events, mult_events = [], [], [], [], []
     M32 = 0xFFFFFFFF
 
     def word(v):
@@ -1454,17 +1457,22 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     after_cf = False
     for i in range(real):
         what = int(rng.integers(0, 100))
-        kind = "alu" if after_cf or what < 70 else "mov" if what < 82 else "branch" if what < 92 else "jump"
+        kind = ("alu" if after_cf or what < 62 else "muldiv" if what < 70 else "mov" if what < 82 else "branch" if what < 92
+                else "jump")
         after_cf = kind in ("branch", "jump")
         ra, rb, rc = (int(x) for x in rng.integers(1, 32, 3))
         clk = 5 * i
         row = cpu[i]
         nnpc = next_pc + 4
-        imm_b, is_rw_a, immutable, sequential, hi_slot = False, 0, 0, 1, 0
+        imm_b, is_rw_a, immutable, sequential, hi_slot, check_memory = False, 0, 0, 1, 0, 0
         if kind == "alu":
             opcode = alu_ops[int(rng.integers(0, len(alu_ops)))]
             imm_c = opcode in (19, 20) or int(rng.integers(0, 4)) == 0
             cval = (0 if opcode in (19, 20) else int(rng.integers(0, 1 << 16))) if imm_c else regs[rc]
+        elif kind == "muldiv":
+            opcode = (3, 4, 5, 6, 7, 8)[int(rng.integers(0, 6))]       # MULT MULTU DIV DIVU MOD MODU
+            imm_c = int(rng.integers(0, 4)) == 0
+            cval = int(rng.integers(0, 3)) if imm_c else regs[rc]      # small immediates: division by 0, 1, 2
         elif kind == "mov":
             opcode = (50, 51, 52)[int(rng.integers(0, 3))]             # MEQ, MNE, WSBH
             imm_c = opcode == 52 or int(rng.integers(0, 3)) == 0       # an immediate 0 makes c == 0 a common case
@@ -1504,6 +1512,36 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
                 bb = bval if opcode == 19 else M32 - bval
                 if bb:
                     events["ShiftRight"].append((1, 10, bb >> (31 - aval), bb, 31 - aval, 5))
+        elif kind == "muldiv":
+            signed = opcode in (3, 5, 7)
+            sx = lambda v: (v ^ 0x80000000) - 0x80000000 if signed else v
+            if opcode in (3, 4):                                       # MULT / MULTU: low word to ra, high word to HI
+                p64 = (sx(bval) * sx(cval)) & 0xFFFFFFFFFFFFFFFF
+                aval, hi_val = p64 & M32, p64 >> 32
+            else:
+                q, rem = _quotient_remainder(bval, cval, signed)
+                aval, hi_val = (q, rem) if opcode in (5, 6) else (rem, None)
+                # DivRemChip's dependencies (alu/divrem eval): c * quotient on Mul, the absolute values on AddSub,
+                # |remainder| < max(|c|, 1) on Lt -- all at UNUSED_PC
+                ctq = (sx(q) * sx(cval)) & 0xFFFFFFFFFFFFFFFF
+                mult_events.append((1, 5, 3 if signed else 4, ctq >> 32, ctq & M32, q, cval, 0, 0, 0, 0, 0, 0))
+                abs_c, abs_rem = (abs(sx(cval)) & M32, abs(sx(rem)) & M32)
+                if signed and cval >> 31:
+                    events["AddSub"].append((1, 0, 0, cval, abs_c, 5))
+                if signed and rem >> 31:
+                    events["AddSub"].append((1, 0, 0, rem, abs_rem, 5))
+                if cval:
+                    events["Lt"].append((1, 14, 1, abs_rem, max(1, abs_c), 5))
+            if hi_val is not None:                                     # the HI register write, checked by the ALU chip at clk + 4
+                check_memory, hi_slot = 1, hi_val
+                ps, pc_ = last[33]
+                touched.add(33)
+                rec = (shard, clk, regs[33], ps, pc_)
+                last[33], regs[33] = (shard, clk + 4), hi_val
+            if opcode in (3, 4):
+                mult_events.append((pc, next_pc, opcode, hi_val, aval, bval, cval, 1) + rec)
+            else:
+                div_events.append((pc, next_pc, opcode, bval, cval) + (rec if hi_val is not None else (0, 0, 0, 0, 0)))
         elif kind == "mov":
             if opcode == 52:
                 aval = ((bval & 0x00FF00FF) << 8) | ((bval & 0xFF00FF00) >> 8)
@@ -1533,6 +1571,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
         op_b_word = bval if imm_b else rb
         op_c_word = cval if imm_c else rc
         row[0], row[1], row[2] = shard, clk & 0xFFFF, clk >> 16
+        row[3], row[4], row[23] = shard * check_memory, clk * check_memory, check_memory
         row[5], row[6], row[7] = pc, next_pc, nnpc
         row[8], row[9] = opcode, ra
         row[10:14], row[14:18] = word(op_b_word), word(op_c_word)
@@ -1564,6 +1603,9 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
         if name == "Mul":                                              # MUL: no HI write, shard = clk = 0
             ev = np.zeros((len(e), 13), np.uint64)
             ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 4], ev[:, 5], ev[:, 6] = e[:, 0], e[:, 5], e[:, 1], e[:, 2], e[:, 3], e[:, 4]
+            # MULT / MULTU instructions (HI written) and DivRem's c * quotient products (at UNUSED_PC, HI not written)
+            ev = np.concatenate([ev, np.array(mult_events, np.uint64).reshape(-1, 13)])
+            h = 1 << pow2(len(ev))
             t = mul_rows(ev, h)
         else:
             ev = _alu_event_array(e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4])
@@ -1572,6 +1614,11 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
         c = Chip(name, name, M(t), local_only=_air(name).local_only)
         c.canon = (None, t)
         chips.append(c)
+    e = np.array(div_events, np.uint64).reshape(-1, 10)
+    t = div_rem_rows(e, 1 << pow2(len(e)))
+    c = Chip("DivRem", "DivRem", M(t), local_only=True)
+    c.canon = (None, t)
+    chips.append(c)
     for name, evs, rows_of in (("MovCond", mov_events, mov_cond_rows), ("Jump", jump_events, jump_rows),
                                ("Branch", branch_events, branch_rows)):
         e = np.array(evs, np.uint64).reshape(-1, 7)
