@@ -1,5 +1,8 @@
-"""AIRs compiled into libzkgpu.  Real Ziren chips need the Rust-side exporter; these are
-the synthetic ones BASELINE.md section 4 names."""
+"""AIRs compiled into libzkgpu: the synthetic ones BASELINE.md section 4 names (fibonacci, wide_bitwise_*, lookup_*, ...)
+and 28 REAL Ziren chips transcribed by hand from their `Air::eval`, one function per chip citing the lines it follows --
+seventeen of the core machine (Cpu, AddSub, Mul, DivRem, Lt, Bitwise, ShiftLeft, ShiftRight, CloClz, MovCond, Jump,
+Branch, MemoryLocal, SyscallCore, SyscallPrecompile, Byte, Program) and all eleven RecursionAir variants.  The other
+MipsAir chips need the Rust-side exporter (rust/air-export), whose JSON `Air.from_exported_json` loads."""
 from .ir import Air, AirBuilder
 
 
