@@ -356,7 +356,7 @@ def shard_chips(config, rank=0, scale=0):
     if config == "program":
         # a toy core-machine PROGRAM executed in Python (synth.core_program_chips): Cpu, Program, eight ALU chips, MovCond,
         # Jump, Branch, MemoryLocal and Byte whose memory / program / instruction / byte buses cancel across the shard
-        return synth.core_program_chips(17 - d, seed=51 + rank)[0]
+        return synth.core_program_chips(17 - d, seed=51 + rank, device=True)[0]   # the CPU rows are filled on the GPU from events
     if config == "core":
         # a core-machine shard on FOURTEEN real MipsAir chips transcribed from their Air::eval (library.py): the ALU chips
         # with device fillers carry events only; Byte answers every byte lookup of the others (multiplicities counted from
@@ -425,6 +425,8 @@ def with_host_traces(chips):
             c = copy.copy(c)
             if c.tracegen.startswith("Poseidon2Wide"):
                 c.main = ob.poseidon2_wide_trace(c.events, c.rows, c.tracegen.endswith("3"))
+            elif c.tracegen == "Cpu":
+                c.main = to_monty(c.canon[1])                          # the rows the program generator wrote (CpuChip::event_to_row)
             else:
                 rows_of = {"AddSub": synth.add_sub_rows, "Bitwise": synth.bitwise_rows, "Lt": synth.lt_rows,
                            "ShiftLeft": synth.shift_left_rows, "ShiftRight": synth.shift_right_rows,

@@ -199,6 +199,19 @@ int32_t zk_tracegen_alu(zk_ctx* ctx, int32_t chip, const zk_alu_event* events_ho
                         zk_dptr* out_trace);
 int32_t zk_tracegen_alu_dev(zk_ctx* ctx, int32_t chip, zk_dptr events_dev, uint64_t n_events, uint64_t rows,
                             zk_dptr* out_trace);
+/* CpuChip (crates/core/machine/src/cpu/trace.rs:118-237, columns cpu/columns/mod.rs:16-62): one 67-column row per executed
+ * instruction from a packed event: the CpuEvent's scalars, its instruction and the previous (shard, clk) of the three register
+ * accesses (a_record / b_record / c_record; ignored for an immediate operand).  flags: bit 0 op_a_0, 1 imm_b, 2 imm_c,
+ * 3 is_rw_a, 4 is_check_memory, 5 is_halt, 6 is_sequential, 7 op_a_immutable.  Padding rows as generate_trace leaves them
+ * (imm_b = imm_c = is_rw_a = 1). */
+typedef struct {
+  uint32_t pc, next_pc, next_next_pc, clk, shard, opcode, op_a, op_b, op_c, flags, num_extra_cycles;
+  uint32_t a, b, c, hi;
+  uint32_t a_prev_value, a_prev_shard, a_prev_clk, b_prev_shard, b_prev_clk, c_prev_shard, c_prev_clk;
+} zk_cpu_event;
+uint32_t zk_tracegen_cpu_width(void); /* 67 */
+int32_t zk_tracegen_cpu(zk_ctx* ctx, const zk_cpu_event* events_host, uint64_t n_events, uint64_t rows, zk_dptr* out_trace);
+int32_t zk_tracegen_cpu_dev(zk_ctx* ctx, zk_dptr events_dev, uint64_t n_events, uint64_t rows, zk_dptr* out_trace);
 /* Poseidon2WideChip<DEGREE>: inputs = n_events x 16 Montgomery words (Poseidon2Event::input); sbox_state = 1 for
  * DEGREE 3 (313 columns), 0 for DEGREE 9 (172 columns). */
 uint32_t zk_tracegen_poseidon2_wide_width(int32_t sbox_state);

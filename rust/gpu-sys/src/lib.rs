@@ -37,6 +37,17 @@ pub struct ZkAluEvent {
     pub b: u32,
     pub c: u32,
 }
+/// `zk_cpu_event`: the CpuEvent's scalars, its instruction and the previous (shard, clk) of its three register accesses, packed
+/// by the host from `CpuEvent` + `Instruction` (crates/core/executor/src/events/cpu.rs) -- 22 words per executed instruction.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct ZkCpuEvent {
+    pub pc: u32, pub next_pc: u32, pub next_next_pc: u32, pub clk: u32, pub shard: u32, pub opcode: u32, pub op_a: u32,
+    pub op_b: u32, pub op_c: u32, pub flags: u32, pub num_extra_cycles: u32,
+    pub a: u32, pub b: u32, pub c: u32, pub hi: u32,
+    pub a_prev_value: u32, pub a_prev_shard: u32, pub a_prev_clk: u32, pub b_prev_shard: u32, pub b_prev_clk: u32,
+    pub c_prev_shard: u32, pub c_prev_clk: u32,
+}
 pub const ZK_CHIP_ADD_SUB: i32 = 0;
 pub const ZK_CHIP_BITWISE: i32 = 1;
 pub const ZK_CHIP_LT: i32 = 2;
@@ -123,6 +134,9 @@ extern "C-unwind" {
     pub fn zk_tracegen_alu_width(chip: i32) -> u32;
     pub fn zk_tracegen_alu(ctx: *mut ZkCtx, chip: i32, events_host: *const ZkAluEvent, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_tracegen_alu_dev(ctx: *mut ZkCtx, chip: i32, events_dev: ZkDptr, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_cpu_width() -> u32;
+    pub fn zk_tracegen_cpu(ctx: *mut ZkCtx, events_host: *const ZkCpuEvent, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
+    pub fn zk_tracegen_cpu_dev(ctx: *mut ZkCtx, events_dev: ZkDptr, n_events: u64, rows: u64, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_tracegen_poseidon2_wide_width(sbox_state: i32) -> u32;
     pub fn zk_tracegen_poseidon2_wide(ctx: *mut ZkCtx, inputs_host: *const u32, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;
     pub fn zk_tracegen_poseidon2_wide_dev(ctx: *mut ZkCtx, inputs_dev: ZkDptr, n_events: u64, rows: u64, sbox_state: i32, out_trace: *mut ZkDptr) -> i32;

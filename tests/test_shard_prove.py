@@ -455,10 +455,12 @@ def test_core_program_shard(be):
     ctx = _backend(be)
     nq, pw = (6, 4) if be == "emu" else (84, 16)
     chips, _ = synth.core_program_chips(7 if be == "emu" else 12)
+    dev_chips, _ = synth.core_program_chips(7 if be == "emu" else 12, device=True)   # the CPU chip as events (zk_tracegen_cpu)
+    assert dev_chips[0].main is None and dev_chips[0].events.shape[1] == 22
     if be == "emu":
-        chips = chips[:-1]
+        chips, dev_chips = chips[:-1], dev_chips[:-1]
     npv = 231
-    prover, pk, data, sp = _prove(ctx, chips, 1, nq, pw, num_pv=npv)
+    prover, pk, data, sp = _prove(ctx, dev_chips, 1, nq, pw, num_pv=npv)
     ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp], npv, 1, nq, pw)
     assert not ok and why.endswith("local cumulative sum is not zero"), why
     op = osp.OracleShardProver(su.AIRS, 1, nq, pw, num_pv_elts=npv)
@@ -469,7 +471,7 @@ def test_core_program_shard(be):
     # wrong public next_pc: the CPU chip's own constraint fails
     bad_pvs = su.public_values_for(chips, npv).copy()
     bad_pvs[41] = su.M([7])[0]
-    sp2 = prover.open(pk, prover.commit(chips, bad_pvs), _machine_challenger(ctx, pk))
+    sp2 = prover.open(pk, prover.commit(dev_chips, bad_pvs), _machine_challenger(ctx, pk))
     ok, why = su.machine_verify(su.vk_of(pk), _machine(chips), [sp2], npv, 1, nq, pw)
     assert not ok and not why.endswith("local cumulative sum is not zero"), why
     data.free()

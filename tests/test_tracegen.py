@@ -144,6 +144,17 @@ def _check_poseidon2_skinny(ctx, n_events, rows):
     assert w == 51 and np.array_equal(got, to_monty(synth.poseidon2_skinny_prep_rows(c[:, 0:16], c[:, 16:32], c[:, 32:48], rows)))
 
 
+def _check_cpu(ctx, log_cpu):
+    """device filler of the CPU chip against the numpy rows of the toy core-machine program (which satisfy the transcribed
+    CPU AIR and balance the machine's buses, tests/test_air_ir.py)"""
+    chips, _ = synth.core_program_chips(log_cpu)
+    cpu = chips[0]
+    dptr, w = ctx.tracegen_cpu(cpu.cpu_events, cpu.height)
+    got = ctx.download(dptr, (cpu.height, w))
+    ctx.dev_free(dptr)
+    assert w == 67 and np.array_equal(got, to_monty(cpu.canon[1]))
+
+
 def test_tracegen_emu():
     """kernel index math on the CPU emulator (test-only build of the same sources)"""
     ctx = backends.emu()
@@ -154,6 +165,7 @@ def test_tracegen_emu():
     _check_prep(ctx, 5, 8)
     _check_poseidon2_skinny(ctx, 40, 512)      # two CTAs, the second one partial and partly padding
     _check_poseidon2_skinny(ctx, 1, 16)
+    _check_cpu(ctx, 8)
 
 
 @pytest.mark.gpu
@@ -161,6 +173,12 @@ def test_tracegen_emu():
 @pytest.mark.parametrize("n_events,rows", [(0, 1), (1, 1), (5, 8), (127, 128), (129, 256), (40000, 1 << 16), (1 << 14, 1 << 14)])
 def test_tracegen_poseidon2_wide_gpu(n_events, rows, sbox):
     _check_poseidon2_wide(backends.gpu(), n_events, rows, sbox)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_cpu", [2, 7, 13])
+def test_tracegen_cpu_gpu(log_cpu):
+    _check_cpu(backends.gpu(), log_cpu)
 
 
 @pytest.mark.gpu

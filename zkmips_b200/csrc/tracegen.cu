@@ -64,6 +64,26 @@ int32_t poseidon2_skinny(zk_ctx* c, const uint32_t* host, zk_dptr dev, uint64_t 
   return ZK_OK;
 }
 
+int32_t cpu_trace(zk_ctx* c, const uint32_t* host, zk_dptr dev, uint64_t n_events, uint64_t rows, zk_dptr* out_trace) {
+  if (!c || !out_trace || (n_events && !host && !dev)) return zk_fail(ZK_ERR_ARG, "null argument");
+  if (!pow2(rows) || n_events > rows) return zk_fail(ZK_ERR_ARG, "rows must be a power of two >= n_events");
+  std::lock_guard<std::mutex> g(c->mu);
+  CK(cudaSetDevice(c->device));
+  ProfScope ps(c, "tracegen");
+  DevScope scope(c);
+  const uint32_t* ev = nullptr;
+  int32_t rc = stage_events(c, scope, host, dev, n_events * tg::CPU_EV_WORDS, &ev);
+  if (rc) return rc;
+  uint32_t* out = nullptr;
+  if ((rc = scope.alloc(&out, rows * tg::CPU_W * 4ull))) return rc;
+  ZK_LAUNCH_COOP(tg::cpu_rows, (unsigned)((rows + tg::ROWS - 1) / tg::ROWS), tg::ROWS, 0, c->stream, ev, n_events, rows, out);
+  CK(cudaGetLastError());
+  c->launches++;
+  scope.release(out);
+  *out_trace = (zk_dptr)out;
+  return ZK_OK;
+}
+
 template <class CHIP>
 void launch_alu(zk_ctx* c, const uint32_t* ev, uint64_t n_events, uint64_t rows, uint32_t* out) {
   unsigned grid = (unsigned)((rows + tg::ROWS - 1) / tg::ROWS);
@@ -181,4 +201,13 @@ extern "C" int32_t zk_tracegen_poseidon2_skinny_prep(zk_ctx* c, const uint32_t* 
   scope.release(out);
   *out_trace = (zk_dptr)out;
   return ZK_OK;
+}
+extern "C" uint32_t zk_tracegen_cpu_width(void) { return tg::CPU_W; }
+extern "C" int32_t zk_tracegen_cpu(zk_ctx* c, const zk_cpu_event* events_host, uint64_t n_events, uint64_t rows,
+                                   zk_dptr* out_trace) {
+  static_assert(sizeof(zk_cpu_event) == 4 * tg::CPU_EV_WORDS, "zk_cpu_event is 22 words");
+  return cpu_trace(c, (const uint32_t*)events_host, 0, n_events, rows, out_trace);
+}
+extern "C" int32_t zk_tracegen_cpu_dev(zk_ctx* c, zk_dptr events_dev, uint64_t n_events, uint64_t rows, zk_dptr* out_trace) {
+  return cpu_trace(c, nullptr, events_dev, n_events, rows, out_trace);
 }

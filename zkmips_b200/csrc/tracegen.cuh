@@ -409,6 +409,88 @@ struct CloClz {
   }
 };
 
+// ---- CpuChip::event_to_row (crates/core/machine/src/cpu/trace.rs:118-237, MemoryAccessCols::populate_access
+//      memory/consistency/trace.rs:69-105) from packed CPU events of 22 words (zk_cpu_event, include/zkgpu.h): the 67-column
+//      CPU row of one executed instruction -- shard / clk limbs, pcs, the instruction, the flags, the operand words and
+//      the three register-access records (previous shard / clk, same-shard flag, 16 + 8 bit limbs of the timestamp
+//      difference).  Padding rows carry imm_b = imm_c = is_rw_a = 1 (trace.rs:60-66).  Canonical values in the staging row;
+//      the flush converts to Montgomery form.
+constexpr uint32_t CPU_EV_WORDS = 22, CPU_W = 67;
+struct CpuEv {
+  uint32_t pc, next_pc, next_next_pc, clk, shard, opcode, op_a, op_b, op_c, flags, num_extra_cycles, a, b, c, hi, a_prev_value,
+      a_prev_shard, a_prev_clk, b_prev_shard, b_prev_clk, c_prev_shard, c_prev_clk;
+};
+__device__ __forceinline__ void cpu_put_word(uint32_t* t, uint32_t v) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) t[k] = (v >> (8 * k)) & 0xFF;
+}
+// access columns at t: value[4], prev_shard, prev_clk, compare_clk, diff_16bit_limb, diff_8bit_limb
+__device__ __forceinline__ void cpu_put_access(uint32_t* t, uint32_t value, uint32_t shard, uint32_t clk, uint32_t prev_shard,
+                                               uint32_t prev_clk) {
+  cpu_put_word(t, value);
+  const bool same = prev_shard == shard;
+  const uint32_t diff = (same ? clk : shard) - (same ? prev_clk : prev_shard) - 1u;
+  t[4] = prev_shard;
+  t[5] = prev_clk;
+  t[6] = same;
+  t[7] = diff & 0xFFFF;
+  t[8] = (diff >> 16) & 0xFF;
+}
+__global__ void __launch_bounds__(ROWS) cpu_rows(const uint32_t* __restrict__ events, uint64_t n_events, uint64_t rows,
+                                                 uint32_t* __restrict__ out) {
+  __shared__ uint32_t tile[ROWS][CPU_W + 1];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
+  uint32_t* t = tile[tid];
+  for (uint32_t c = 0; c < CPU_W; c++) t[c] = 0u;
+  if (row0 + tid < n_events) {
+    const uint32_t* p = events + (row0 + tid) * CPU_EV_WORDS;
+    CpuEv e;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&e);
+#pragma unroll
+    for (uint32_t k = 0; k < CPU_EV_WORDS; k++) w[k] = __ldg(p + k);
+    const uint32_t imm_b = (e.flags >> 1) & 1, imm_c = (e.flags >> 2) & 1, check = (e.flags >> 4) & 1;
+    t[0] = e.shard;
+    t[1] = e.clk & 0xFFFF;
+    t[2] = (e.clk >> 16) & 0xFF;
+    t[3] = check ? e.shard : 0u;
+    t[4] = check ? e.clk : 0u;
+    t[5] = e.pc;
+    t[6] = e.next_pc;
+    t[7] = e.next_next_pc;
+    t[8] = e.opcode;
+    t[9] = e.op_a;
+    cpu_put_word(t + 10, e.op_b);
+    cpu_put_word(t + 14, e.op_c);
+    t[18] = e.flags & 1;
+    t[19] = imm_b;
+    t[20] = imm_c;
+    t[21] = e.num_extra_cycles;
+    t[22] = (e.flags >> 3) & 1;
+    t[23] = check;
+    t[24] = (e.flags >> 5) & 1;
+    t[25] = (e.flags >> 6) & 1;
+    cpu_put_word(t + 26, e.a);
+    cpu_put_word(t + 30, e.hi);
+    cpu_put_word(t + 34, e.a_prev_value);
+    cpu_put_access(t + 38, e.a, e.shard, e.clk + 3, e.a_prev_shard, e.a_prev_clk);
+    if (imm_b) cpu_put_word(t + 47, e.b);
+    else cpu_put_access(t + 47, e.b, e.shard, e.clk + 2, e.b_prev_shard, e.b_prev_clk);
+    if (imm_c) cpu_put_word(t + 56, e.c);
+    else cpu_put_access(t + 56, e.c, e.shard, e.clk + 1, e.c_prev_shard, e.c_prev_clk);
+    t[65] = 1;
+    t[66] = (e.flags >> 7) & 1;
+  } else {
+    t[19] = 1;
+    t[20] = 1;
+    t[22] = 1;
+  }
+  __syncthreads();
+  uint64_t base = row0 * CPU_W, end = rows * CPU_W;
+  for (uint32_t idx = tid; idx < ROWS * CPU_W; idx += ROWS)
+    if (base + idx < end) out[base + idx] = kb::to_monty(tile[idx / CPU_W][idx % CPU_W]);
+}
+
 template <class CHIP>
 __global__ void __launch_bounds__(ROWS) alu_rows(const uint32_t* __restrict__ events, uint64_t n_events, uint64_t rows,
                                                  uint32_t* __restrict__ out) {

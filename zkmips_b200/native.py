@@ -69,6 +69,9 @@ PROTOTYPES = {
     "zk_tracegen_alu_width": (u32, [i32]),
     "zk_tracegen_alu": (i32, [vp, i32, vp, u64, u64, u64p]),
     "zk_tracegen_alu_dev": (i32, [vp, i32, u64, u64, u64, u64p]),
+    "zk_tracegen_cpu_width": (u32, []),
+    "zk_tracegen_cpu": (i32, [vp, vp, u64, u64, u64p]),
+    "zk_tracegen_cpu_dev": (i32, [vp, u64, u64, u64, u64p]),
     "zk_tracegen_poseidon2_wide_width": (u32, [i32]),
     "zk_tracegen_poseidon2_wide": (i32, [vp, u32p, u64, u64, i32, u64p]),
     "zk_tracegen_poseidon2_wide_dev": (i32, [vp, u64, u64, u64, i32, u64p]),
@@ -416,6 +419,18 @@ class Ctx:
         out = u64()
         self.lib.check(self.d.zk_tracegen_poseidon2_wide_prep(self.h, _p32(x), len(x), rows, C.byref(out)))
         return out.value, 49
+
+    def tracegen_cpu(self, events, rows):
+        """CpuChip main trace from packed CPU events ([n, 22] uint32: zk_cpu_event, host array or (device pointer, n));
+        returns (device pointer, 67)."""
+        out = u64()
+        if isinstance(events, tuple):
+            dptr, n = events
+            self.lib.check(self.d.zk_tracegen_cpu_dev(self.h, dptr, n, rows, C.byref(out)))
+        else:
+            ev = _arr(events, np.uint32).reshape(-1, 22)
+            self.lib.check(self.d.zk_tracegen_cpu(self.h, ev.ctypes.data_as(vp), len(ev), rows, C.byref(out)))
+        return out.value, self.d.zk_tracegen_cpu_width()
 
     def tracegen_poseidon2_skinny(self, inputs, rows):
         """Poseidon2SkinnyChip main trace (eleven 28-word rows per permutation) from the permutation inputs ([n, 16]

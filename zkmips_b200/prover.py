@@ -140,6 +140,8 @@ class GpuShardProver:
             return self.ctx.tracegen_alu(chip.tracegen, chip.events, chip.height)
         if chip.tracegen in ("Poseidon2WideDeg3", "Poseidon2WideDeg9"):
             return self.ctx.tracegen_poseidon2_wide(chip.events, chip.height, chip.tracegen.endswith("3"))
+        if chip.tracegen == "Cpu":
+            return self.ctx.tracegen_cpu(chip.events, chip.height)
         if chip.tracegen == "Poseidon2SkinnyDeg9":
             return self.ctx.tracegen_poseidon2_skinny(chip.events, chip.height)
         raise ValueError(f"{chip.name}: no device trace filler named {chip.tracegen!r}")

@@ -1410,7 +1410,7 @@ def _core_op(opcode, b, c):
     raise ValueError(opcode)
 
 
-def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
+def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000, device=False):
     """Returns ([Cpu, Program, AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz, Mul, DivRem, MovCond, Jump, Branch,
     MemoryLocal, Byte], public values (start_pc, next_pc, execution_shard)).  CpuChip::event_to_row (cpu/trace.rs:118-237) for the CPU
     rows.  About 60 % of the instructions are simple ALU operations, 8 % MULT / MULTU / DIV / DIVU / MOD / MODU (the HI
@@ -1431,6 +1431,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     alu_ops = list(_CORE_OPS)
     cpu = np.zeros((n, 67), np.uint64)
     cpu[:, 19], cpu[:, 20], cpu[:, 22] = 1, 1, 1                       # padding rows: imm_b = imm_c = is_rw_a = 1
+    cpu_ev = np.zeros((real, 22), np.uint32)                           # zk_cpu_event records (include/zkgpu.h)
     prog = np.zeros((n, 14), np.uint64)
     events = {name: [] for name in set(_CORE_OPS.values())}
     mov_events, jump_events, branch_events, div_events, mult_events = [], [], [], [], []
@@ -1487,6 +1488,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
             opcode = (28, 29)[int(rng.integers(0, 2))]                 # Jumpi, JumpDirect
             imm_b, imm_c, cval = True, True, 0
             target = max(hi_pc, next_pc) + 4 * int(rng.integers(1, 9))
+        c_prev = last[rc] if not imm_c else (0, 0)
         if not imm_c:
             access(row, 56, rc, clk + 1, cval)
         else:
@@ -1499,6 +1501,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
             if kind == "branch" and int(rng.integers(0, 3)) == 0:
                 rb = ra                                                # equal operands: BEQ taken / BNE not taken
             bval = regs[rb]
+        b_prev = last[rb] if not imm_b else (0, 0)
         if not imm_b:
             access(row, 47, rb, clk + 2, bval)
         else:
@@ -1566,6 +1569,7 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
             if opcode == 29:
                 events["AddSub"].append((1, 0, target, next_pc, bval, 5))  # send_alu(ADD, next_next_pc, next_pc, op_b)
             jump_events.append((pc, next_pc, nnpc, opcode, aval, bval, cval))
+        a_prev = last[ra]
         access(row, 34, ra, clk + 3, aval, prev_value=prev_a)
         regs[ra] = aval
         op_b_word = bval if imm_b else rb
@@ -1580,6 +1584,9 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
         row[26:30], row[30:34] = word(aval), word(hi_slot)
         row[65], row[66] = 1, immutable
         prog[i] = [pc, opcode, ra] + word(op_b_word) + word(op_c_word) + [0, int(imm_b), int(imm_c)]
+        flags = int(imm_b) << 1 | int(imm_c) << 2 | is_rw_a << 3 | check_memory << 4 | sequential << 6 | immutable << 7
+        cpu_ev[i] = [pc, next_pc, nnpc, clk, shard, opcode, ra, op_b_word, op_c_word, flags, 0, aval, bval, cval, hi_slot,
+                     prev_a, a_prev[0], a_prev[1], b_prev[0], b_prev[1], c_prev[0], c_prev[1]]
         hi_pc = max(hi_pc, pc, next_pc, nnpc)
         pc, next_pc = next_pc, nnpc
     final_next_pc = pc                                                 # the last executed row's next_pc
@@ -1587,8 +1594,8 @@ def core_program_chips(log_cpu=7, seed=51, fill=0.9, shard=1, pc_start=0x1000):
     def pow2(k):
         return max(2, (max(k, 1) - 1).bit_length())
     chips = []
-    c = Chip("Cpu", "Cpu", M(cpu))
-    c.canon = (None, cpu)
+    c = Chip("Cpu", "Cpu", None, events=cpu_ev, tracegen="Cpu", rows=n) if device else Chip("Cpu", "Cpu", M(cpu))
+    c.canon, c.cpu_events = (None, cpu), cpu_ev                        # device=True: the rows are filled on the GPU (zk_tracegen_cpu)
     chips.append(c)
     mult = np.zeros((n, 1), np.uint64)
     mult[:real] = 1
