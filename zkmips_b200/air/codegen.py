@@ -8,6 +8,11 @@ import os
 
 from .ir import P
 
+# minimum resident CTAs per SM the generated quotient kernels are compiled for (register cap 65536 / (128 * n)); env
+# ZK_QUOT_MIN_CTAS for A/B builds.  Real chips' programs keep 150-255 values live (quot_Cpu_p0 255 registers with
+# spills at 1), which leaves 12 % of the warp slots occupied and the kernels latency-bound (profiles/README.md).
+QUOT_MIN_CTAS = int(os.environ.get("ZK_QUOT_MIN_CTAS", "1"))
+
 MAX_NODES = 1500
 R = 1 << 32
 
@@ -206,7 +211,7 @@ def generate(airs):
             hdr.append(f"__global__ void {fn}(quot::Args A);")
             out = files[nk % N_KERNEL_FILES]
             nk += 1
-            out.append(f"__global__ void __launch_bounds__(128) {fn}(quot::Args A) {{")
+            out.append(f"__global__ void __launch_bounds__(128, {QUOT_MIN_CTAS}) {fn}(quot::Args A) {{")
             out.append("  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;")
             out.append("  if (i >= (1u << (A.log_n + A.lqd))) return;")
             out.append("  quot::Row R;")
